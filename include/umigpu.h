@@ -1,0 +1,206 @@
+/*
+ * umigpu.h — C ABI of libumigpu.so: the B200-native (sm_100a) UMI clustering hot path of
+ * umi-collapse-rs, as a drop-in behind the reference's CLI / trait surface.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the
+ * reference repository, tkob-vh/umi-collapse-rs).  The reference-side binding a maintainer
+ * would add (a Rust `extern "C"` crate + one new `impl DeduplicateInterface`) is shown in
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross this boundary;
+ *   - every function returns 0 (UMIGPU_OK) or a negative UMIGPU_ERR_* code, never throws and
+ *     never aborts; umigpu_last_error() returns a human-readable message.  (The reference
+ *     panics on every error with panic="abort", Cargo.toml:19; the Rust shim turns a non-zero
+ *     return into panic! to keep that behaviour.)
+ *   - inputs are borrowed for the duration of the call; results are library-owned until
+ *     umigpu_result_free / umigpu_destroy;
+ *   - a context is bound to one CUDA device and is not thread-safe (the reference is
+ *     single-threaded: &mut self on every trait method);
+ *   - there is no CPU fallback: without a CUDA device umigpu_create fails.
+ */
+#ifndef UMIGPU_H
+#define UMIGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UMIGPU_OK                 0
+#define UMIGPU_ERR_ARG           -1   /* bad argument / unsupported combination                       */
+#define UMIGPU_ERR_CUDA          -2   /* CUDA runtime error (message has the cudaError string)        */
+#define UMIGPU_ERR_BAD_BASE      -3   /* UMI byte not in {A,C,G,T,N}: reference panics, utils/mod.rs:78 */
+#define UMIGPU_ERR_NOMEM         -4
+#define UMIGPU_ERR_UNSUPPORTED   -5   /* key wider than 128 bits, umi_len > 32, > 2^32-2 reads ...    */
+#define UMIGPU_ERR_STATE         -6   /* call order violated (e.g. fetch before run)                  */
+
+/* --algo (src/cli.rs:33-36, dispatch src/main.rs:52-92) */
+#define UMIGPU_ALGO_DIR           0   /* src/algo/directional.rs:58-91                                */
+#define UMIGPU_ALGO_ADJ           1   /* src/algo/adjacency.rs:31-63 AS WRITTEN: remove_near(.,k,0)
+                                         removes only the query, every unique UMI is kept   */
+#define UMIGPU_ALGO_ADJ_UPSTREAM  2   /* opt-in: adjacency with max_freq = i32::MAX (upstream intent)  */
+#define UMIGPU_ALGO_CC            3   /* help text only in the reference: directional with
+                                         an infinite threshold = one representative per component     */
+
+/* --merge (src/cli.rs:37-40, src/merge/mod.rs:18-51) */
+#define UMIGPU_MERGE_ANY          0   /* AnyMerge: first read of a (bucket, UMI) is its representative */
+#define UMIGPU_MERGE_AVGQUAL      1   /* AvgQualMerge: keep existing iff a.avg_qual >= b.avg_qual       */
+#define UMIGPU_MERGE_MAPQUAL      2   /* MapQualMerge: same on MAPQ                                     */
+
+/* flags */
+#define UMIGPU_FLAG_LABELS        1u  /* also produce the per-read cluster root (ClusterTracker, --tag) */
+#define UMIGPU_FLAG_NO_CULL       2u  /* evaluate every tile pair (disable exact prefix culling)        */
+#define UMIGPU_FLAG_KERNEL_DIRECT 4u  /* use the direct XOR+popcount tile kernel instead of bit-sliced  */
+
+typedef struct umigpu_ctx umigpu_ctx;
+
+/* Mirrors the fields of `struct Cli` (src/cli.rs:7-77) that reach the hot path:
+ * Directional::new / Adjacency::new capture k and percentage (directional.rs:22-28). */
+typedef struct umigpu_config {
+    int32_t  k;            /* -k, src/cli.rs:18-19                                                  */
+    float    percentage;   /* -p, src/cli.rs:25-26 (f32 like the reference)                         */
+    int32_t  algo;         /* UMIGPU_ALGO_*                                                         */
+    int32_t  merge;        /* UMIGPU_MERGE_*; selects nothing but whether `score` is honoured        */
+    uint32_t umi_len;      /* -u / autodetected by the host (utils/read.rs:87-94); 1..32             */
+    int32_t  device;       /* CUDA device ordinal                                                   */
+    uint32_t flags;        /* UMIGPU_FLAG_*                                                         */
+    uint32_t reserved;
+    void    *stream;       /* cudaStream_t to launch on; NULL = a stream owned by the context       */
+} umigpu_config;
+
+/* The six end-of-run counters of src/deduplicate_sam.rs:243-267 (a13) plus path statistics. */
+typedef struct umigpu_counters {
+    uint64_t total_reads;       /* reads pushed (deduplicate_sam.rs:100; filters are applied by the host) */
+    uint64_t n_buckets;         /* unique alignment positions, :198                                  */
+    uint64_t total_umis;        /* sum over buckets of unique UMIs, :217                             */
+    uint64_t max_umis;          /* max unique UMIs in a bucket, :218                                 */
+    uint64_t n_kept;            /* reads after deduplicating, :219                                   */
+    uint64_t unordered_pairs;   /* sum_b N_b (N_b - 1) / 2: what Naive must cover                    */
+    uint64_t pairs_evaluated;   /* pairs the device actually evaluated (after exact tile culling)    */
+    uint64_t n_edges;           /* directed edges that passed the distance and count rule            */
+    uint64_t n_tile_items;      /* tile-pair work items executed                                     */
+    uint64_t n_sweeps;          /* label-propagation sweeps                                          */
+} umigpu_counters;
+
+typedef struct umigpu_result {
+    uint64_t         n_kept;
+    const uint64_t  *kept_read_index;  /* ascending input order: what UcWriter::write receives
+                                          (deduplicate_sam.rs:227-231), canonical order              */
+    uint64_t         n_reads;
+    const uint64_t  *read_cluster_root;/* FLAG_LABELS only: per pushed read (push order), the read index
+                                          of the emitted representative of its cluster                */
+    umigpu_counters  counters;
+} umigpu_result;
+
+/* stage ids for umigpu_stage_ms */
+enum {
+    UMIGPU_STAGE_PACK = 0,      /* K1 umi_pack (+H2D in the host entry)     */
+    UMIGPU_STAGE_KEYS,          /* K1b build sort keys                      */
+    UMIGPU_STAGE_SORT,          /* K2 bucket_group radix sort               */
+    UMIGPU_STAGE_UNIQUE,        /* K3 umi_count_merge                       */
+    UMIGPU_STAGE_WORKLIST,      /* bucket segmentation + tile work list     */
+    UMIGPU_STAGE_NEIGHBOURS,    /* K5 hamming_neighbours                    */
+    UMIGPU_STAGE_CLUSTER,       /* K6 cluster (label propagation)           */
+    UMIGPU_STAGE_EMIT,          /* K7 emit_compact                          */
+    UMIGPU_STAGE_TOTAL,         /* run() first launch -> last launch        */
+    UMIGPU_N_STAGES
+};
+
+const char *umigpu_version(void);
+/* message of the last failing call on this thread (also valid when ctx == NULL) */
+const char *umigpu_last_error(const umigpu_ctx *ctx);
+
+/* Replaces DeduplicateSAM::new + Directional::new/Adjacency::new (deduplicate_sam.rs:46-68,
+ * directional.rs:22-28, main.rs:52-92). */
+int  umigpu_create(const umigpu_config *cfg, umigpu_ctx **out);
+void umigpu_destroy(umigpu_ctx *ctx);
+/* forget all pushed reads and results, keep device buffers (next batch / next bucket) */
+int  umigpu_reset(umigpu_ctx *ctx);
+
+/*
+ * HOT LOOP A, deduplicate_sam.rs:93-177, batched.  One call appends `n` reads (host SoA):
+ *   tid            record.tid()                    (bucket key part, :137/:144)
+ *   unclipped_pos  get_unclipped_pos(&record)      (utils/mod.rs:96-104)
+ *   is_reverse     record.is_reverse()             (0/1)
+ *   umi_ascii      n * umi_len bytes, get_umi()    (utils/read.rs:96-111) before to_bitset
+ *   score          avg_qual (read.rs:56-63) or MAPQ (read.rs:77-79); may be NULL for MERGE_ANY
+ *   weight         NULL = every read counts 1 (the reference); else per-read multiplicity
+ *                  (used by umigpu_cluster_bucket to present pre-counted UMIs)
+ *   first_read_index  index the caller gives to the first read of this chunk; kept indices are
+ *                  reported in this numbering (chunks must be pushed in ascending index order)
+ * The copy to the device and the UMI packing kernel are asynchronous on the context's stream.
+ */
+int umigpu_push_reads(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, const int64_t *unclipped_pos,
+                      const uint8_t *is_reverse, const uint8_t *umi_ascii, const int32_t *score,
+                      const int32_t *weight, uint64_t first_read_index);
+/* same, but every pointer is a DEVICE pointer valid on ctx's device (inputs already in HBM) */
+int umigpu_push_reads_device(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, const int64_t *unclipped_pos,
+                             const uint8_t *is_reverse, const uint8_t *umi_ascii, const int32_t *score,
+                             const int32_t *weight, uint64_t first_read_index);
+
+/* HOT LOOP B, deduplicate_sam.rs:207-233 over all buckets at once: group, count, merge, neighbour
+ * search, cluster, compact.  Asynchronous apart from a few scalar read-backs. */
+int umigpu_run(umigpu_ctx *ctx);
+/* Wait for run() and copy the kept indices (and labels) to host memory owned by the context. */
+int umigpu_fetch(umigpu_ctx *ctx, umigpu_result *out);
+/* run + fetch */
+int umigpu_finish(umigpu_ctx *ctx, umigpu_result *out);
+/* counters of the last run without copying the kept list */
+int umigpu_get_counters(umigpu_ctx *ctx, umigpu_counters *out);
+
+/*
+ * Algorithm::apply-shaped entry (src/algo/mod.rs:13-20, called deduplicate_sam.rs:211-213): one
+ * bucket of `n` distinct UMIs (ASCII, n*umi_len) with their frequencies.
+ *   keep[i]  = 1 iff UMI i's representative is emitted
+ *   label[i] = index of the emitted UMI whose cluster contains UMI i (what ClusterTracker records)
+ * Visit order = (freq descending, UMI ascending A<C<G<T<N) — one of the reference's possible orders.
+ */
+int umigpu_cluster_bucket(umigpu_ctx *ctx, uint64_t n, const uint8_t *umi_ascii, const int32_t *freq,
+                          uint8_t *keep, int32_t *label);
+
+/*
+ * DataStruct-shaped entries (src/data/mod.rs:11-17, src/data/naive.rs:22-44).
+ * umigpu_remove_near: out[i] = 1 iff Naive::remove_near(query, k, max_freq) would remove UMI i:
+ *   dist <= k && (dist == 0 || freq[i] <= max_freq).
+ * umigpu_neighbours: the whole bucket at once as CSR adjacency over the input indices:
+ *   col[row_ptr[i] .. row_ptr[i+1]) = ascending j != i with dist(i,j) <= k and, when apply_rule != 0,
+ *   freq[j] <= trunc_i32(f32(percentage) * f32(freq[i] + 1)) (directional.rs:38).  col_capacity is the
+ *   size of col; *n_edges always receives the true edge count (call again with a larger col if it
+ *   exceeds col_capacity; UMIGPU_ERR_ARG is returned in that case).
+ */
+int umigpu_remove_near(umigpu_ctx *ctx, uint64_t n, const uint8_t *umi_ascii, const int32_t *freq,
+                       const uint8_t *query, int32_t k, int32_t max_freq, uint8_t *out);
+int umigpu_neighbours(umigpu_ctx *ctx, uint64_t n, const uint8_t *umi_ascii, const int32_t *freq,
+                      int32_t apply_rule, uint64_t *row_ptr, uint32_t *col, uint64_t col_capacity,
+                      uint64_t *n_edges);
+
+/* UcSAMRead::new score, utils/read.rs:56-63: per read trunc_i32(f32 sum of qual bytes / f32 len).
+ * qual = concatenated phred bytes, offsets[n+1] (host pointers); out = n scores. */
+int umigpu_avg_qual(umigpu_ctx *ctx, uint64_t n, const uint8_t *qual, const uint64_t *offsets, int32_t *out);
+
+/* device time of a stage of the last run (CUDA events on the context's stream), milliseconds */
+int umigpu_stage_ms(umigpu_ctx *ctx, int stage, float *ms);
+/* number of kernels this context has launched since create / since the last call with reset != 0 */
+uint64_t umigpu_launch_count(umigpu_ctx *ctx, int reset);
+void umigpu_result_free(umigpu_ctx *ctx);
+
+/*
+ * Multi-GPU sharding plan: buckets are independent, so each device takes a
+ * slice balanced by sum N_b^2 with no collective.  Given per-read bucket keys on the host it
+ * assigns every read to one of n_shards with longest-processing-time-first over estimated
+ * bucket cost (reads_in_bucket^2); shard_of_read[n] receives the shard id.  Pure host helper.
+ */
+int umigpu_shard_plan(uint64_t n, const int32_t *tid, const int64_t *unclipped_pos, const uint8_t *is_reverse,
+                      int32_t n_shards, int32_t *shard_of_read, uint64_t *shard_cost /* n_shards */);
+
+/* integer-pipe microbenchmark used as the roofline denominator of the neighbour search:
+ * ops/s of a dependent-free LOP3 stream and of POPC on the context's device. */
+int umigpu_int_peak(umigpu_ctx *ctx, double *lop3_ops_per_s, double *popc_ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UMIGPU_H */

@@ -1,0 +1,107 @@
+// cluster.cuh — K6 cluster_{dir,cc,adj} and K7 emit_compact.
+//
+// Directional / cc (src/algo/directional.rs:30-54, :74-88): the reference visits UMIs by
+// frequency descending and, from each UMI still present, removes everything reachable through
+// edges u -> v (dist <= k, freq[v] <= thr[u]) by a recursive DFS.  The set removed after a root is
+// closed under reachability, so   v is emitted  <=>  no earlier-visited UMI reaches v,   and the
+// root that removes v is the earliest-visited UMI that reaches it.  That is a minimum-label
+// propagation over the directed edge list: label[u] starts as its visit rank, every sweep does
+// label[dst] = min(label[dst], label[src]) until nothing changes; the fixpoint is unique, so the
+// result does not depend on thread scheduling (bit-exact, order-dependent clustering without
+// replaying the recursion).
+//
+// Upstream-intended adjacency (opt-in; the reference's adj keeps everything): greedy in
+// visit order without recursion = lexicographically-first maximal independent set, resolved in
+// rounds: a UMI is kept once all its earlier neighbours are removed, removed once one is kept.
+#pragma once
+#include "common.cuh"
+#include "pack.cuh"
+
+__global__ void __launch_bounds__(256) label_sweep_kernel(const uint2 *__restrict__ edges, u64 n_edges,
+                                                          unsigned long long *label, DevScalars *sc) {
+    u64 stride = (u64)gridDim.x * 256;
+    u32 any = 0;
+    for (u64 e = (u64)blockIdx.x * 256 + threadIdx.x; e < n_edges; e += stride) {
+        uint2 ed = edges[e];
+        unsigned long long ls = label[ed.x];
+        if (ls < label[ed.y]) { atomicMin(&label[ed.y], ls); any = 1; }
+    }
+    if (__any_sync(0xffffffffu, any) && lane_id() == 0) sc->changed = 1;
+}
+
+// keep[u] = (root(u) == u); root id = low 32 bits of the label
+__global__ void __launch_bounds__(256) keep_from_label_kernel(u32 n_unique, const unsigned long long *__restrict__ label,
+                                                              u8 *__restrict__ keep) {
+    u32 u = blockIdx.x * 256 + threadIdx.x;
+    if (u < n_unique) keep[u] = ((u32)label[u] == u) ? 1 : 0;
+}
+
+// ---- upstream adjacency (greedy MIS) ----
+#define MIS_UNDECIDED 0
+#define MIS_KEPT 1
+#define MIS_REMOVED 2
+
+__global__ void __launch_bounds__(256) mis_edge_kernel(const uint2 *__restrict__ edges, u64 n_edges,
+                                                       const unsigned long long *__restrict__ prio, u8 *state, u8 *blocked) {
+    u64 stride = (u64)gridDim.x * 256;
+    for (u64 e = (u64)blockIdx.x * 256 + threadIdx.x; e < n_edges; e += stride) {
+        uint2 ed = edges[e];
+        if (prio[ed.x] < prio[ed.y] && state[ed.y] == MIS_UNDECIDED) {
+            u8 s = state[ed.x];
+            if (s == MIS_KEPT) state[ed.y] = MIS_REMOVED;
+            else if (s == MIS_UNDECIDED) blocked[ed.y] = 1;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) mis_node_kernel(u32 n_unique, u8 *state, u8 *blocked, DevScalars *sc) {
+    u32 u = blockIdx.x * 256 + threadIdx.x;
+    u32 any = 0;
+    if (u < n_unique) {
+        if (state[u] == MIS_UNDECIDED) {
+            if (!blocked[u]) state[u] = MIS_KEPT;
+            any = 1;                      // something was undecided at the start of this round
+        }
+        blocked[u] = 0;
+    }
+    if (__any_sync(0xffffffffu, any) && lane_id() == 0) sc->changed = 1;
+}
+// label of a removed UMI = earliest kept neighbour (the visit that removed it); kept UMIs label themselves
+__global__ void __launch_bounds__(256) mis_label_kernel(const uint2 *__restrict__ edges, u64 n_edges,
+                                                        const unsigned long long *__restrict__ prio, const u8 *__restrict__ state,
+                                                        unsigned long long *label) {
+    u64 stride = (u64)gridDim.x * 256;
+    for (u64 e = (u64)blockIdx.x * 256 + threadIdx.x; e < n_edges; e += stride) {
+        uint2 ed = edges[e];
+        if (state[ed.x] == MIS_KEPT && state[ed.y] == MIS_REMOVED) atomicMin(&label[ed.y], prio[ed.x]);
+    }
+}
+__global__ void __launch_bounds__(256) mis_keep_kernel(u32 n_unique, const u8 *__restrict__ state, u8 *__restrict__ keep) {
+    u32 u = blockIdx.x * 256 + threadIdx.x;
+    if (u < n_unique) keep[u] = state[u] == MIS_KEPT ? 1 : 0;
+}
+
+// ---- K7 emit_compact (src/deduplicate_sam.rs:227-231): kept representatives -> ascending read
+// indices (canonical output order = input order).  A bitmap over reads makes the order free.
+__global__ void __launch_bounds__(256) mark_kept_kernel(u32 n_unique, const u8 *__restrict__ keep, const u32 *__restrict__ rep_idx,
+                                                        u32 *__restrict__ bitmap) {
+    u32 u = blockIdx.x * 256 + threadIdx.x;
+    if (u < n_unique && keep[u]) { u32 r = rep_idx[u]; atomicOr(&bitmap[r >> 5], 1u << (r & 31)); }
+}
+struct BitmapCount { const u32 *bm; __device__ u32 operator()(u64 w) const { return __popc(bm[w]); } };
+struct BitmapEmit {
+    const u32 *bm; u32 *kept; u64 n_words; DevScalars *sc;
+    __device__ void operator()(u64 w, u32 cnt, u32 ex) const {
+        u32 bits = bm[w];
+        u32 o = ex;
+        while (bits) { u32 b = __ffs(bits) - 1; bits &= bits - 1; kept[o++] = (u32)(w * 32 + b); }
+        if (w == n_words - 1) sc->n_kept = ex + cnt;
+    }
+};
+
+// per read: read index of the emitted representative of its cluster (ClusterTracker, --tag)
+__global__ void __launch_bounds__(256) read_roots_kernel(u64 n, const u32 *__restrict__ read_uid,
+                                                         const unsigned long long *__restrict__ label,
+                                                         const u32 *__restrict__ rep_idx, u32 *__restrict__ out) {
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) out[i] = rep_idx[(u32)label[read_uid[i]]];
+}

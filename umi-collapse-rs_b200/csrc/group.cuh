@@ -1,0 +1,163 @@
+// group.cuh — K3 umi_count_merge, bucket segmentation and the tile work list.
+//   K3 replaces the per-read map update of src/deduplicate_sam.rs:160-176 with the Merge policies of
+//   src/merge/mod.rs:18-51: for every (bucket, UMI) segment of the sorted reads, freq = number of
+//   reads (or sum of weights) and representative = first read in input order attaining the maximum
+//   score (`keep_existing = a.score >= b.score` only ever replaces on a strictly larger score).
+#pragma once
+#include "common.cuh"
+#include "pack.cuh"
+#include "scan.cuh"
+
+struct SortedKeys {
+    const u64 *k0, *k1;   // k1 == nullptr for one-word keys
+    int umi_bits;
+    __device__ __forceinline__ bool same_key(u64 i, u64 j) const {
+        return k0[i] == k0[j] && (k1 == nullptr || k1[i] == k1[j]);
+    }
+    __device__ __forceinline__ bool same_bucket(u64 i, u64 j) const {
+        if (umi_bits == 64) return k1[i] == k1[j];
+        if ((k0[i] >> umi_bits) != (k0[j] >> umi_bits)) return false;
+        return k1 == nullptr || k1[i] == k1[j];
+    }
+};
+
+struct HeadFlag {
+    SortedKeys sk;
+    __device__ u32 operator()(u64 i) const { return (i == 0 || !sk.same_key(i, i - 1)) ? 1u : 0u; }
+};
+
+struct UniqueEmit {
+    SortedKeys sk;
+    u64 n;
+    const u32 *idx;       // sorted position -> read index
+    const i32 *score;     // per read, may be null (MERGE_ANY)
+    const i32 *weight;    // per read, may be null
+    int L, has_n;
+    u32 *useg;            // [U+1] first sorted position of each unique
+    uint2 *planes; u32 *nplane;
+    u8 *bhead;            // unique starts a new bucket
+    unsigned long long *rep;   // packed (score biased << 32 | ~read idx), max wins
+    i32 *wsum;            // weighted freq (only with weights)
+    u32 *read_uid;        // optional: read index -> unique id
+    __device__ void operator()(u64 i, u32 flag, u32 ex) const {
+        u32 uid = ex + flag - 1;
+        u32 r = idx[i];
+        if (flag) {
+            useg[uid] = (u32)i;
+            u64 code = sk.umi_bits == 64 ? sk.k0[i] : (sk.k0[i] & ((1ull << sk.umi_bits) - 1));
+            u32 p0, p1, pn;
+            code_to_planes(code, L, has_n, p0, p1, pn);
+            planes[uid] = make_uint2(p0, p1);
+            if (has_n) nplane[uid] = pn;
+            bhead[uid] = (i == 0 || !sk.same_bucket(i, i - 1)) ? 1 : 0;
+        }
+        if (i == n - 1) useg[uid + 1] = (u32)n;
+        u32 s = score ? (u32)score[r] ^ 0x80000000u : 0u;
+        atomicMax(&rep[uid], ((unsigned long long)s << 32) | (u32)~r);
+        if (weight) atomicAdd(&wsum[uid], weight[r]);
+        if (read_uid) read_uid[r] = uid;
+    }
+};
+
+// per unique: freq, directional threshold (directional.rs:38), representative read, initial label.
+// label = (~freq << 32 | unique id): ascending label = the reference's visit order (freq descending,
+// directional.rs:67-72) with the canonical tie-break (UMI ascending = unique id ascending in a bucket).
+__global__ void __launch_bounds__(256) unique_finalize_kernel(
+    u32 n_unique, const u32 *__restrict__ useg, const unsigned long long *__restrict__ rep, const i32 *__restrict__ wsum,
+    float percentage, int algo_inf_thr, i32 *__restrict__ freq, i32 *__restrict__ thr, u32 *__restrict__ rep_idx,
+    unsigned long long *__restrict__ label) {
+    u32 u = blockIdx.x * 256 + threadIdx.x;
+    if (u >= n_unique) return;
+    i32 f = wsum ? wsum[u] : (i32)(useg[u + 1] - useg[u]);
+    freq[u] = f;
+    thr[u] = algo_inf_thr ? 0x7fffffff : dir_threshold(percentage, f);
+    rep_idx[u] = ~(u32)rep[u];
+    label[u] = ((unsigned long long)(u32)~(u32)f << 32) | u;
+}
+
+struct BucketHead { const u8 *bhead; __device__ u32 operator()(u64 u) const { return bhead[u]; } };
+struct BucketEmit {
+    u32 *bstart; u64 n_unique;
+    __device__ void operator()(u64 u, u32 flag, u32 ex) const {
+        if (flag) bstart[ex] = (u32)u;
+        if (u == n_unique - 1) bstart[ex + flag] = (u32)n_unique;
+    }
+};
+
+// Tile geometry of the neighbour search (rows x cols of unique UMIs of one bucket).
+#define HT_ROWS 2048
+#define HT_COLS 2048
+
+struct TileItem { u32 row_start, col_start, row_cnt, col_cnt_diag; };   // col_cnt | diag << 31
+
+__device__ __forceinline__ u32 bucket_tiles(u32 nb) { return (nb + HT_ROWS - 1) / HT_ROWS; }
+
+// number of tile pairs (ti <= tj) of a bucket; buckets with one UMI need no comparison at all
+struct BucketItems {
+    const u32 *bstart;
+    __device__ u32 operator()(u64 b) const {
+        u32 nb = bstart[b + 1] - bstart[b];
+        if (nb < 2) return 0;
+        u32 t = bucket_tiles(nb);
+        return t * (t + 1) / 2;
+    }
+};
+struct BucketItemsEmit {
+    u32 *item_off; u64 n_buckets;
+    __device__ void operator()(u64 b, u32 v, u32 ex) const {
+        item_off[b] = ex;
+        if (b == n_buckets - 1) item_off[b + 1] = ex + v;
+    }
+};
+
+__global__ void __launch_bounds__(256) bucket_stats_kernel(u32 n_buckets, const u32 *__restrict__ bstart, DevScalars *sc) {
+    u32 b = blockIdx.x * 256 + threadIdx.x;
+    u32 nb = b < n_buckets ? bstart[b + 1] - bstart[b] : 0;
+    u64 pairs = (u64)nb * (nb ? nb - 1 : 0) / 2;
+    u32 mx = nb;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane_id() == 0 && mx) {
+        atomicAdd((unsigned long long *)&sc->pairs, (unsigned long long)pairs);
+        atomicMax(&sc->max_umis, mx);
+    }
+}
+
+// one thread per work item: bucket by binary search over item_off, (ti, tj) by triangular decode
+__global__ void __launch_bounds__(256) build_items_kernel(u32 n_items, u32 n_buckets, const u32 *__restrict__ item_off,
+                                                          const u32 *__restrict__ bstart, TileItem *__restrict__ items,
+                                                          DevScalars *sc) {
+    u32 w = blockIdx.x * 256 + threadIdx.x;
+    u64 npairs = 0;
+    if (w < n_items) {
+    u32 lo = 0, hi = n_buckets;            // last b with item_off[b] <= w
+    while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (item_off[mid] <= w) lo = mid; else hi = mid; }
+    u32 b = lo, local = w - item_off[b];
+    u32 s = bstart[b], nb = bstart[b + 1] - s, t = bucket_tiles(nb);
+    // row-major upper triangle: row ti holds (t - ti) items
+    u32 ti = 0;
+    {
+        double tt = 2.0 * t + 1.0;
+        double r = (tt - sqrt(tt * tt - 8.0 * (double)local)) * 0.5;
+        ti = (u32)r; if (ti >= t) ti = t - 1;
+        // first item index of row ti = ti*t - ti*(ti-1)/2
+        while (ti > 0 && (u64)ti * t - (u64)ti * (ti - 1) / 2 > local) ti--;
+        while ((u64)(ti + 1) * t - (u64)(ti + 1) * ti / 2 <= local) ti++;
+    }
+    u32 tj = ti + (local - (u32)((u64)ti * t - (u64)ti * (ti - 1) / 2));
+    TileItem it;
+    it.row_start = s + ti * HT_ROWS;
+    it.col_start = s + tj * HT_COLS;
+    it.row_cnt = min((u32)HT_ROWS, nb - ti * HT_ROWS);
+    u32 cc = min((u32)HT_COLS, nb - tj * HT_COLS);
+    it.col_cnt_diag = cc | (ti == tj ? 0x80000000u : 0u);
+    items[w] = it;
+    npairs = ti == tj ? (u64)cc * (cc - 1) / 2 : (u64)it.row_cnt * cc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
+    if (lane_id() == 0 && npairs) atomicAdd((unsigned long long *)&sc->pairs_eval, (unsigned long long)npairs);
+}

@@ -1,0 +1,116 @@
+// hamming.cuh — K5 hamming_neighbours: all-pairs Hamming <= k over the unique UMIs of a bucket,
+// tile by tile, emitting the directed edges that pass the reference's count rule.
+//
+// Replaces Naive::remove_near (src/data/naive.rs:26-40) + umi_dist (src/utils/mod.rs:24-26,
+// src/utils/bitset.rs:77-91).  Naive scans every remaining UMI once per removed UMI; here every
+// unordered pair of a bucket is evaluated exactly once and the result is kept as an edge list, so
+// the clustering (K6) never needs a distance again.
+//
+// Distance: a UMI is three bit planes (one bit per base): p0/p1 = low/high bit of the base code,
+// pn = "is N".  mismatch mask m = (a.p0^b.p0) | (a.p1^b.p1) | (a.pn^b.pn); dist = popc(m).  This is
+// plain Hamming distance over {A,C,G,T,N} (N==N matches, N!=base mismatches), which is exactly what
+// the reference's popcount formula computes (bitset.rs:77-91; checked in tests/test_oracle.py).
+// Any umi_len <= 32 costs the same: 2 LOP3 per pair for m, +1 with N.
+//
+// Edge rule (directional.rs:38, naive.rs:31): u -> v  iff dist(u,v) <= k and freq[v] <= thr[u],
+// thr[u] = trunc(p * (freq[u] + 1)) precomputed per UMI (INT_MAX for cc / upstream adjacency).
+#pragma once
+#include "common.cuh"
+#include "group.cuh"
+
+#define HT_THREADS 256
+#define HT_RPT     (HT_ROWS / HT_THREADS)   // rows per thread = 8
+
+struct EdgeSink {
+    uint2 *edges;
+    unsigned long long *count;
+    u64 cap;
+    const i32 *freq, *thr;
+};
+
+// cold path: a < b are unique ids with dist <= k
+__device__ __noinline__ void record_hit(const EdgeSink &es, u32 a, u32 b) {
+    i32 fa = es.freq[a], fb = es.freq[b];
+    bool ab = fb <= es.thr[a], ba = fa <= es.thr[b];
+    u32 cnt = (ab ? 1 : 0) + (ba ? 1 : 0);
+    if (!cnt) return;
+    u64 at = atomicAdd(es.count, (unsigned long long)cnt);
+    if (ab) { if (at < es.cap) es.edges[at] = make_uint2(a, b); at++; }
+    if (ba) { if (at < es.cap) es.edges[at] = make_uint2(b, a); }
+}
+
+template <int K>
+__device__ __forceinline__ bool within_k(u32 m) {
+    if (K == 1) return (m & (m - 1)) == 0;
+    return __popc(m) <= K;
+}
+
+// Direct tile kernel: each thread keeps HT_RPT row UMIs in registers, the column tile sits in
+// shared memory and is read with broadcast LDS.128 (two columns per load).
+template <int K, bool HASN>
+__global__ void __launch_bounds__(HT_THREADS) hamming_tiles_direct(
+    const TileItem *__restrict__ items, u32 n_items, const uint2 *__restrict__ planes, const u32 *__restrict__ nplane,
+    EdgeSink es, int kdyn) {
+    __shared__ __align__(16) uint2 scol[HT_COLS];
+    __shared__ u32 sncol[HASN ? HT_COLS : 1];
+    for (u32 w = blockIdx.x; w < n_items; w += gridDim.x) {
+        TileItem it = items[w];
+        const u32 col_cnt = it.col_cnt_diag & 0x7fffffffu;
+        const bool diag = it.col_cnt_diag >> 31;
+        const u32 cols_pad = (col_cnt + 3) & ~3u;
+        __syncthreads();
+        for (u32 c = threadIdx.x; c < cols_pad; c += HT_THREADS) {
+            bool v = c < col_cnt;
+            scol[c] = v ? planes[it.col_start + c] : make_uint2(0xffffffffu, 0xffffffffu);
+            if (HASN) sncol[c] = v ? nplane[it.col_start + c] : 0u;
+        }
+        u32 r0[HT_RPT], r1[HT_RPT], rn[HT_RPT];
+#pragma unroll
+        for (int r = 0; r < HT_RPT; r++) {
+            u32 gi = threadIdx.x + r * HT_THREADS;
+            bool v = gi < it.row_cnt;
+            uint2 p = v ? planes[it.row_start + gi] : make_uint2(0xffffffffu, 0u);
+            r0[r] = p.x; r1[r] = p.y;
+            rn[r] = (HASN && v) ? nplane[it.row_start + gi] : 0u;
+        }
+        __syncthreads();
+        for (u32 c = 0; c < cols_pad; c += 2) {
+            uint4 cc = *reinterpret_cast<const uint4 *>(&scol[c]);
+            u32 n0 = 0, n1 = 0;
+            if (HASN) { n0 = sncol[c]; n1 = sncol[c + 1]; }
+#pragma unroll
+            for (int r = 0; r < HT_RPT; r++) {
+                u32 m0 = (r0[r] ^ cc.x) | (r1[r] ^ cc.y);
+                u32 m1 = (r0[r] ^ cc.z) | (r1[r] ^ cc.w);
+                if (HASN) { m0 |= rn[r] ^ n0; m1 |= rn[r] ^ n1; }
+                bool h0 = K > 0 ? within_k<K>(m0) : (__popc(m0) <= kdyn);
+                bool h1 = K > 0 ? within_k<K>(m1) : (__popc(m1) <= kdyn);
+                if (h0 | h1) {
+                    u32 gi = threadIdx.x + r * HT_THREADS;
+                    if (gi < it.row_cnt) {
+                        u32 a = it.row_start + gi;
+                        if (h0 && c < col_cnt) { u32 b = it.col_start + c; if (!diag || a < b) record_hit(es, a, b); }
+                        if (h1 && c + 1 < col_cnt) { u32 b = it.col_start + c + 1; if (!diag || a < b) record_hit(es, a, b); }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Naive::remove_near for ONE query (DataStruct-shaped API, naive.rs:26-40):
+// out[i] = dist <= k && (dist == 0 || freq[i] <= max_freq)
+__global__ void __launch_bounds__(256) remove_near_kernel(u32 n, const u64 *__restrict__ umi2, const u32 *__restrict__ nmask,
+                                                          u64 q2, u32 qn, const i32 *__restrict__ freq, int k, i32 max_freq,
+                                                          u8 *__restrict__ out) {
+    u32 i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    u64 x = umi2[i] ^ q2;
+    u64 m = (x | (x >> 1)) & 0x5555555555555555ull;
+    // spread the N masks to the even bit of each base
+    u32 nx = nmask[i] ^ qn;
+    u64 ns = 0;
+    for (int b = 0; b < 32; b++) ns |= (u64)((nx >> b) & 1) << (2 * b);
+    int dist = __popcll(m | ns);
+    out[i] = (dist <= k && (dist == 0 || freq[i] <= max_freq)) ? 1 : 0;
+}

@@ -1,0 +1,106 @@
+// pack.cuh — K1 umi_pack and K1b build_keys.
+//   K1  replaces to_bitset (src/utils/mod.rs:63-83, table src/utils/read.rs:22-31): ASCII UMI ->
+//       2 bits/base (A0 C1 G2 T3, base 0 most significant, so integer order = string order) plus a
+//       1 bit/base N mask.  The reference's 3-bit equidistant code exists only to make
+//       popcount(xor)/2 a Hamming distance; the bit-plane form used by K5 gives the same distance
+//       (see hamming.cuh).  Also reduces min/max of tid and unclipped position for the key layout.
+//   K1b replaces the Alignment key (src/deduplicate_sam.rs:485-514, built :131-146): packs
+//       (tid, unclipped pos, strand, UMI code) into one 64/128-bit sort key using only as many
+//       bits as the batch needs.
+#pragma once
+#include "common.cuh"
+
+struct DevScalars {
+    i32 tid_min, tid_max;
+    i64 pos_min, pos_max;
+    u32 any_n, bad_base;
+    u32 n_unique, n_buckets;
+    u32 max_umis, changed;
+    u32 n_kept, n_items;
+    u64 pairs, pairs_eval, edge_count;
+    u64 scratch;
+};
+
+struct KeyLayout {
+    int umi_len, umi_bits, pos_bits, tid_bits, bucket_bits, total_bits, nw, has_n;
+    i64 pos_min;
+    i32 tid_min;
+};
+
+#define PACK_THREADS 256
+
+__global__ void __launch_bounds__(PACK_THREADS) umi_pack_kernel(
+    const u8 *__restrict__ ascii, u64 n, int L, const i32 *__restrict__ tid, const i64 *__restrict__ pos,
+    u64 *__restrict__ umi2, u32 *__restrict__ nmask, DevScalars *sc) {
+    u64 i = (u64)blockIdx.x * PACK_THREADS + threadIdx.x;
+    i32 tmin = 0x7fffffff, tmax = (i32)0x80000000;
+    i64 pmin = 0x7fffffffffffffffLL, pmax = (i64)0x8000000000000000LL;
+    u32 anyn = 0, bad = 0;
+    if (i < n) {
+        const u8 *s = ascii + i * (u64)L;
+        u64 code = 0; u32 nm = 0;
+        for (int b = 0; b < L; b++) {
+            u32 c = s[b], v;
+            // utils/read.rs:22-31 alphabet; anything else panics in the reference (utils/mod.rs:78)
+            if (c == 'A') v = 0; else if (c == 'C') v = 1; else if (c == 'G') v = 2; else if (c == 'T') v = 3;
+            else if (c == 'N') { v = 0; nm |= 1u << (L - 1 - b); }
+            else { v = 0; bad = 1; }
+            code = (code << 2) | v;
+        }
+        umi2[i] = code; nmask[i] = nm; anyn = nm != 0;
+        tmin = tmax = tid[i]; pmin = pmax = pos[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tmin = min(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+        tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        pmin = min(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+        pmax = max(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+        anyn |= __shfl_xor_sync(0xffffffffu, anyn, o);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if (lane_id() == 0) {
+        atomicMin(&sc->tid_min, tmin); atomicMax(&sc->tid_max, tmax);
+        atomicMin((long long *)&sc->pos_min, (long long)pmin); atomicMax((long long *)&sc->pos_max, (long long)pmax);
+        if (anyn) atomicOr(&sc->any_n, 1u);
+        if (bad) atomicOr(&sc->bad_base, 1u);
+    }
+}
+
+// UMI code used inside the sort key: 2 bits/base when the batch has no N, else 3 bits/base with
+// N = 4, so that ascending code = ascending string with A < C < G < T < N (the canonical tie-break).
+__device__ __forceinline__ u64 umi_sort_code(u64 umi2, u32 nm, int L, int has_n) {
+    if (!has_n) return umi2;
+    u64 code = 0;
+    for (int b = 0; b < L; b++) {
+        int sh = L - 1 - b;
+        u64 c = (nm >> sh) & 1 ? 4 : (umi2 >> (2 * sh)) & 3;
+        code = (code << 3) | c;
+    }
+    return code;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(256) build_keys_kernel(
+    u64 n, const i32 *__restrict__ tid, const i64 *__restrict__ pos, const u8 *__restrict__ rev,
+    const u64 *__restrict__ umi2, const u32 *__restrict__ nmask, KeyLayout lay, u64 *__restrict__ k0, u64 *__restrict__ k1) {
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    u64 bucket = ((u64)(u32)(tid[i] - lay.tid_min) << (lay.pos_bits + 1)) | ((u64)(pos[i] - lay.pos_min) << 1) | (rev[i] ? 1u : 0u);
+    u64 code = umi_sort_code(umi2[i], nmask[i], lay.umi_len, lay.has_n);
+    int ub = lay.umi_bits;
+    u64 lo = (ub < 64 ? bucket << ub : 0) | code;
+    k0[i] = lo;
+    if (NW == 2) k1[i] = ub == 64 ? bucket : (ub == 0 ? 0 : bucket >> (64 - ub));
+}
+
+// bit planes of a sort code: plane0 bit b = low bit of base b's code, plane1 = high bit, planeN = N flag.
+// (base 0 lands on bit L-1; any fixed permutation of positions leaves the Hamming distance unchanged)
+__device__ __forceinline__ void code_to_planes(u64 code, int L, int has_n, u32 &p0, u32 &p1, u32 &pn) {
+    p0 = p1 = pn = 0;
+    if (!has_n) {
+        for (int b = 0; b < L; b++) { u32 c = (u32)(code >> (2 * b)) & 3; p0 |= (c & 1) << b; p1 |= (c >> 1) << b; }
+    } else {
+        for (int b = 0; b < L; b++) { u32 c = (u32)(code >> (3 * b)) & 7; p0 |= (c & 1) << b; p1 |= ((c >> 1) & 1) << b; pn |= (c >> 2) << b; }
+    }
+}

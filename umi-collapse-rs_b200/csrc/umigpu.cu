@@ -1,0 +1,826 @@
+// umigpu.cu — libumigpu.so: C ABI (include/umigpu.h) and the host-side pipeline that strings the
+// sm_100a kernels together.  No CPU fallback: every compute step below is a kernel launch.
+#include "../../include/umigpu.h"
+
+#include <algorithm>
+#include <queue>
+#include <stdarg.h>
+#include <unordered_map>
+
+#include "cluster.cuh"
+#include "common.cuh"
+#include "group.cuh"
+#include "hamming.cuh"
+#include "hamming_bs.cuh"
+#include "misc.cuh"
+#include "pack.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+static thread_local std::string g_last_error;
+
+struct Chunk { u64 start, n, first_index; };
+
+struct umigpu_ctx {
+    umigpu_config cfg;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    u64 launches = 0;
+    int num_sms = NUM_SMS_B200;
+
+    // accumulated reads (SoA in HBM)
+    u64 n_reads = 0;
+    std::vector<Chunk> chunks;
+    int have_score = -1, have_weight = -1;
+    DevBuf d_tid, d_pos, d_rev, d_umi2, d_nmask, d_score, d_weight, d_ascii;
+    DevBuf d_sc;
+    DevScalars *h_sc = nullptr;   // pinned
+
+    DevBuf d_key[2][2], d_idx[2], d_hist, d_tiles;
+    DevBuf d_useg, d_rep, d_planes, d_nplane, d_bhead, d_wsum, d_read_uid, d_freq, d_thr, d_repidx, d_label, d_prio;
+    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_onehot;
+
+    // results
+    bool ran = false;
+    umigpu_counters ctr;
+    u32 n_unique = 0, n_buckets = 0;
+    u64 n_edges = 0;
+    KeyLayout lay;
+    u32 *h_kept32 = nullptr; size_t h_kept32_cap = 0;   // pinned
+    u32 *h_roots32 = nullptr; size_t h_roots32_cap = 0; // pinned
+    std::vector<u64> h_kept, h_roots;
+
+    cudaEvent_t ev[UMIGPU_N_STAGES][2];
+    bool ev_ok[UMIGPU_N_STAGES];
+};
+
+static int fail(umigpu_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_last_error = buf;
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? UMIGPU_ERR_NOMEM : UMIGPU_ERR_CUDA, \
+                                           "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define LAUNCH(kern, grid, block, ...)                                                             \
+    do {                                                                                           \
+        kern<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);                                    \
+        ctx->launches++;                                                                           \
+        CK(cudaGetLastError());                                                                    \
+    } while (0)
+
+static inline int bits_for(u64 range) { int b = 0; while (range) { b++; range >>= 1; } return b; }
+static inline u32 grid_for(u64 n, u32 block) { return (u32)std::max<u64>(1, ceil_div_u64(n, block)); }
+
+#define STAGE_BEGIN(s) do { CK(cudaEventRecord(ctx->ev[s][0], ctx->stream)); } while (0)
+#define STAGE_END(s)   do { CK(cudaEventRecord(ctx->ev[s][1], ctx->stream)); ctx->ev_ok[s] = true; } while (0)
+
+extern "C" const char *umigpu_version(void) { return "umigpu 0.1 (sm_100a)"; }
+extern "C" const char *umigpu_last_error(const umigpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+extern "C" int umigpu_create(const umigpu_config *cfg, umigpu_ctx **out) {
+    umigpu_ctx *ctx = nullptr;
+    if (!cfg || !out) return fail(nullptr, UMIGPU_ERR_ARG, "umigpu_create: null argument");
+    *out = nullptr;
+    if (cfg->umi_len < 1 || cfg->umi_len > 32) return fail(nullptr, UMIGPU_ERR_UNSUPPORTED, "umi_len %u outside 1..32", cfg->umi_len);
+    if (cfg->k < 0) return fail(nullptr, UMIGPU_ERR_ARG, "k must be >= 0");
+    if (cfg->algo < UMIGPU_ALGO_DIR || cfg->algo > UMIGPU_ALGO_CC)
+        return fail(nullptr, UMIGPU_ERR_ARG, "Invalid algorithm %d", cfg->algo);       // main.rs:86-91 panics
+    if (cfg->merge < UMIGPU_MERGE_ANY || cfg->merge > UMIGPU_MERGE_MAPQUAL)
+        return fail(nullptr, UMIGPU_ERR_ARG, "Invalid merge %d", cfg->merge);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, UMIGPU_ERR_CUDA, "no CUDA device (%s); libumigpu has no CPU fallback", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, UMIGPU_ERR_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+    ctx = new (std::nothrow) umigpu_ctx();
+    if (!ctx) return fail(nullptr, UMIGPU_ERR_NOMEM, "out of host memory");
+    ctx->cfg = *cfg;
+    memset(&ctx->ctr, 0, sizeof ctx->ctr);
+    for (int s = 0; s < UMIGPU_N_STAGES; s++) { ctx->ev_ok[s] = false; ctx->ev[s][0] = ctx->ev[s][1] = nullptr; }
+#define CKC(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { int rc = fail(nullptr, UMIGPU_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e2)); delete ctx; return rc; } } while (0)
+    CKC(cudaSetDevice(cfg->device));
+    int sms = 0;
+    CKC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+    ctx->num_sms = sms > 0 ? sms : NUM_SMS_B200;
+    if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
+    else { CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    for (int s = 0; s < UMIGPU_N_STAGES; s++) { CKC(cudaEventCreate(&ctx->ev[s][0])); CKC(cudaEventCreate(&ctx->ev[s][1])); }
+    CKC(ctx->d_sc.reserve(sizeof(DevScalars)));
+    CKC(cudaMallocHost((void **)&ctx->h_sc, sizeof(DevScalars)));
+#undef CKC
+    *out = ctx;
+    return umigpu_reset(ctx);
+}
+
+extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->d_tid, &ctx->d_pos, &ctx->d_rev, &ctx->d_umi2, &ctx->d_nmask, &ctx->d_score, &ctx->d_weight, &ctx->d_ascii,
+                      &ctx->d_sc, &ctx->d_key[0][0], &ctx->d_key[0][1], &ctx->d_key[1][0], &ctx->d_key[1][1], &ctx->d_idx[0], &ctx->d_idx[1],
+                      &ctx->d_hist, &ctx->d_tiles, &ctx->d_useg, &ctx->d_rep, &ctx->d_planes, &ctx->d_nplane, &ctx->d_bhead, &ctx->d_wsum,
+                      &ctx->d_read_uid, &ctx->d_freq, &ctx->d_thr, &ctx->d_repidx, &ctx->d_label, &ctx->d_prio, &ctx->d_bstart, &ctx->d_itemoff,
+                      &ctx->d_items, &ctx->d_edges, &ctx->d_keep, &ctx->d_state, &ctx->d_blocked, &ctx->d_bitmap, &ctx->d_kept, &ctx->d_roots,
+                      &ctx->d_onehot};
+    for (DevBuf *b : bufs) b->release();
+    if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
+    if (ctx->h_kept32) cudaFreeHost(ctx->h_kept32);
+    if (ctx->h_roots32) cudaFreeHost(ctx->h_roots32);
+    for (int s = 0; s < UMIGPU_N_STAGES; s++) { if (ctx->ev[s][0]) cudaEventDestroy(ctx->ev[s][0]); if (ctx->ev[s][1]) cudaEventDestroy(ctx->ev[s][1]); }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+static int init_scalars(umigpu_ctx *ctx) {
+    DevScalars z; memset(&z, 0, sizeof z);
+    z.tid_min = 0x7fffffff; z.tid_max = (i32)0x80000000;
+    z.pos_min = 0x7fffffffffffffffLL; z.pos_max = (i64)0x8000000000000000LL;
+    *ctx->h_sc = z;
+    CK(cudaMemcpyAsync(ctx->d_sc.p, ctx->h_sc, sizeof z, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // h_sc is reused as the read-back buffer
+    return UMIGPU_OK;
+}
+
+extern "C" int umigpu_reset(umigpu_ctx *ctx) {
+    if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
+    CK(cudaSetDevice(ctx->cfg.device));
+    ctx->n_reads = 0; ctx->chunks.clear(); ctx->have_score = ctx->have_weight = -1;
+    ctx->ran = false; ctx->n_unique = ctx->n_buckets = 0; ctx->n_edges = 0;
+    memset(&ctx->ctr, 0, sizeof ctx->ctr);
+    for (int s = 0; s < UMIGPU_N_STAGES; s++) ctx->ev_ok[s] = false;
+    return init_scalars(ctx);
+}
+
+static int read_scalars(umigpu_ctx *ctx) {
+    CK(cudaMemcpyAsync(ctx->h_sc, ctx->d_sc.p, sizeof(DevScalars), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return UMIGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// push
+// ------------------------------------------------------------------------------------------------
+static int push_common(umigpu_ctx *ctx, u64 n, const i32 *tid, const i64 *pos, const u8 *rev, const u8 *ascii,
+                       const i32 *score, const i32 *weight, u64 first_index, cudaMemcpyKind kind) {
+    if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (ctx->ran) return fail(ctx, UMIGPU_ERR_STATE, "push after run: call umigpu_reset first");
+    if (n == 0) return UMIGPU_OK;
+    if (!ascii) return fail(ctx, UMIGPU_ERR_ARG, "umi_ascii is null");
+    if (ctx->n_reads + n > 0xfffffffeull) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "more than 2^32-2 reads in one batch");
+    if (ctx->have_score < 0) { ctx->have_score = score != nullptr; ctx->have_weight = weight != nullptr; }
+    if ((score != nullptr) != (ctx->have_score == 1) || (weight != nullptr) != (ctx->have_weight == 1))
+        return fail(ctx, UMIGPU_ERR_ARG, "score/weight must be given for all chunks or for none");
+    if (!ctx->chunks.empty()) {
+        const Chunk &c = ctx->chunks.back();
+        if (first_index < c.first_index + c.n) return fail(ctx, UMIGPU_ERR_ARG, "chunks must be pushed in ascending read-index order");
+    }
+    const u64 old = ctx->n_reads, tot = old + n;
+    const int L = (int)ctx->cfg.umi_len;
+    cudaStream_t s = ctx->stream;
+    STAGE_BEGIN(UMIGPU_STAGE_PACK);
+    CK(ctx->d_tid.reserve_keep(tot * 4, old * 4, s));
+    CK(ctx->d_pos.reserve_keep(tot * 8, old * 8, s));
+    CK(ctx->d_rev.reserve_keep(tot, old, s));
+    CK(ctx->d_umi2.reserve_keep(tot * 8, old * 8, s));
+    CK(ctx->d_nmask.reserve_keep(tot * 4, old * 4, s));
+    if (score) CK(ctx->d_score.reserve_keep(tot * 4, old * 4, s));
+    if (weight) CK(ctx->d_weight.reserve_keep(tot * 4, old * 4, s));
+    if (tid) CK(cudaMemcpyAsync(ctx->d_tid.as<i32>() + old, tid, n * 4, kind, s)); else CK(cudaMemsetAsync(ctx->d_tid.as<i32>() + old, 0, n * 4, s));
+    if (pos) CK(cudaMemcpyAsync(ctx->d_pos.as<i64>() + old, pos, n * 8, kind, s)); else CK(cudaMemsetAsync(ctx->d_pos.as<i64>() + old, 0, n * 8, s));
+    if (rev) CK(cudaMemcpyAsync(ctx->d_rev.as<u8>() + old, rev, n, kind, s)); else CK(cudaMemsetAsync(ctx->d_rev.as<u8>() + old, 0, n, s));
+    if (score) CK(cudaMemcpyAsync(ctx->d_score.as<i32>() + old, score, n * 4, kind, s));
+    if (weight) CK(cudaMemcpyAsync(ctx->d_weight.as<i32>() + old, weight, n * 4, kind, s));
+    const u8 *d_ascii = ascii;
+    if (kind == cudaMemcpyHostToDevice) {
+        CK(ctx->d_ascii.reserve(n * L));
+        CK(cudaMemcpyAsync(ctx->d_ascii.p, ascii, n * L, kind, s));
+        d_ascii = ctx->d_ascii.as<u8>();
+    }
+    LAUNCH(umi_pack_kernel, grid_for(n, PACK_THREADS), PACK_THREADS, d_ascii, n, L, ctx->d_tid.as<i32>() + old,
+           ctx->d_pos.as<i64>() + old, ctx->d_umi2.as<u64>() + old, ctx->d_nmask.as<u32>() + old, ctx->d_sc.as<DevScalars>());
+    STAGE_END(UMIGPU_STAGE_PACK);
+    ctx->chunks.push_back({old, n, first_index});
+    ctx->n_reads = tot;
+    return UMIGPU_OK;
+}
+
+extern "C" int umigpu_push_reads(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, const int64_t *unclipped_pos,
+                                 const uint8_t *is_reverse, const uint8_t *umi_ascii, const int32_t *score,
+                                 const int32_t *weight, uint64_t first_read_index) {
+    if (n && (!tid || !unclipped_pos || !is_reverse)) return fail(ctx, UMIGPU_ERR_ARG, "tid/unclipped_pos/is_reverse are null");
+    return push_common(ctx, n, tid, unclipped_pos, is_reverse, umi_ascii, score, weight, first_read_index, cudaMemcpyHostToDevice);
+}
+extern "C" int umigpu_push_reads_device(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, const int64_t *unclipped_pos,
+                                        const uint8_t *is_reverse, const uint8_t *umi_ascii, const int32_t *score,
+                                        const int32_t *weight, uint64_t first_read_index) {
+    if (n && (!tid || !unclipped_pos || !is_reverse)) return fail(ctx, UMIGPU_ERR_ARG, "tid/unclipped_pos/is_reverse are null");
+    return push_common(ctx, n, tid, unclipped_pos, is_reverse, umi_ascii, score, weight, first_read_index, cudaMemcpyDeviceToDevice);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-wide scan driver
+// ------------------------------------------------------------------------------------------------
+template <class F, class G>
+static int run_scan(umigpu_ctx *ctx, F f, G g, u64 n, u32 *total_dev /* may be null */) {
+    u64 ntiles = ceil_div_u64(n, SCAN_TILE);
+    CK(ctx->d_tiles.reserve(ntiles * sizeof(u32)));
+    u32 *ts = ctx->d_tiles.as<u32>();
+    LAUNCH((scan_tile_sums<u32, F>), (u32)ntiles, SCAN_THREADS, f, n, ts);
+    LAUNCH((scan_spine<u32>), 1, 1024, ts, ntiles, total_dev);
+    LAUNCH((scan_apply<u32, F, G>), (u32)ntiles, SCAN_THREADS, f, g, n, (const u32 *)ts);
+    return UMIGPU_OK;
+}
+
+// stable LSD radix sort over `total_bits` of the NW-word keys in d_key[0]; returns the buffer index
+// holding the result.  iota_first: the first pass synthesises idx = position.
+static int run_sort(umigpu_ctx *ctx, u64 n, int nw, int total_bits, int *cur_out) {
+    std::vector<SortPass> passes = rs_plan(total_bits);
+    u32 nblk = (u32)ceil_div_u64(n, RS_TILE);
+    CK(ctx->d_hist.reserve((size_t)256 * nblk * sizeof(u32)));
+    u32 *hist = ctx->d_hist.as<u32>();
+    int cur = 0;
+    bool first = true;
+    for (const SortPass &p : passes) {
+        KeyArr in{{ctx->d_key[cur][0].as<u64>(), ctx->d_key[cur][1].as<u64>()}};
+        KeyArr out{{ctx->d_key[cur ^ 1][0].as<u64>(), ctx->d_key[cur ^ 1][1].as<u64>()}};
+        u32 mask = (1u << p.bits) - 1;
+        LAUNCH(radix_hist, nblk, RS_THREADS, (const u64 *)in.w[p.word], n, p.shift, mask, hist, nblk);
+        int rc = run_scan(ctx, HistLoad{hist}, HistStore{hist}, (u64)256 * nblk, nullptr);
+        if (rc) return rc;
+        if (nw == 1)
+            LAUNCH(radix_scatter<1>, nblk, RS_THREADS, in, (const u32 *)ctx->d_idx[cur].as<u32>(), out, ctx->d_idx[cur ^ 1].as<u32>(), n,
+                   p.word, p.shift, mask, (const u32 *)hist, nblk, first ? 1 : 0);
+        else
+            LAUNCH(radix_scatter<2>, nblk, RS_THREADS, in, (const u32 *)ctx->d_idx[cur].as<u32>(), out, ctx->d_idx[cur ^ 1].as<u32>(), n,
+                   p.word, p.shift, mask, (const u32 *)hist, nblk, first ? 1 : 0);
+        cur ^= 1;
+        first = false;
+    }
+    *cur_out = cur;
+    return UMIGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// run
+// ------------------------------------------------------------------------------------------------
+enum RunMode { RUN_FULL = 0, RUN_EDGES_ONLY = 1 };
+
+static int launch_neighbours(umigpu_ctx *ctx, u32 n_items, EdgeSink es, bool has_n);
+
+static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_inf_thr) {
+    if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (ctx->ran) return fail(ctx, UMIGPU_ERR_STATE, "run called twice without reset");
+    const u64 n = ctx->n_reads;
+    const umigpu_config &cfg = ctx->cfg;
+    memset(&ctx->ctr, 0, sizeof ctx->ctr);
+    ctx->ctr.total_reads = n;
+    ctx->ran = true;
+    if (n == 0) return UMIGPU_OK;
+    DevScalars *sc = ctx->d_sc.as<DevScalars>();
+    STAGE_BEGIN(UMIGPU_STAGE_TOTAL);
+
+    // ---- key layout from the batch's ranges ----
+    int rc = read_scalars(ctx);
+    if (rc) return rc;
+    if (ctx->h_sc->bad_base)
+        return fail(ctx, UMIGPU_ERR_BAD_BASE, "Unknown character in UMI sequence");            // utils/mod.rs:78
+    KeyLayout lay;
+    lay.umi_len = (int)cfg.umi_len;
+    lay.has_n = ctx->h_sc->any_n ? 1 : 0;
+    if (lay.has_n && lay.umi_len > 21) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "UMIs containing N are supported up to 21 nt");
+    lay.umi_bits = lay.has_n ? 3 * lay.umi_len : 2 * lay.umi_len;
+    lay.tid_min = ctx->h_sc->tid_min; lay.pos_min = ctx->h_sc->pos_min;
+    u64 tid_range = (u64)((i64)ctx->h_sc->tid_max - (i64)ctx->h_sc->tid_min);
+    u64 pos_range = (u64)ctx->h_sc->pos_max - (u64)ctx->h_sc->pos_min;
+    lay.tid_bits = bits_for(tid_range); lay.pos_bits = bits_for(pos_range);
+    lay.bucket_bits = lay.tid_bits + lay.pos_bits + 1;
+    if (lay.bucket_bits > 64) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "bucket key needs %d bits (> 64)", lay.bucket_bits);
+    lay.total_bits = lay.bucket_bits + lay.umi_bits;
+    lay.nw = lay.total_bits <= 64 ? 1 : 2;
+    ctx->lay = lay;
+    const bool has_n = lay.has_n != 0;
+
+    // ---- K1b keys ----
+    STAGE_BEGIN(UMIGPU_STAGE_KEYS);
+    for (int b = 0; b < 2; b++) {
+        CK(ctx->d_key[b][0].reserve(n * 8));
+        if (lay.nw == 2) CK(ctx->d_key[b][1].reserve(n * 8));
+        CK(ctx->d_idx[b].reserve(n * 4));
+    }
+    if (lay.nw == 1)
+        LAUNCH(build_keys_kernel<1>, grid_for(n, 256), 256, n, (const i32 *)ctx->d_tid.p, (const i64 *)ctx->d_pos.p, (const u8 *)ctx->d_rev.p,
+               (const u64 *)ctx->d_umi2.p, (const u32 *)ctx->d_nmask.p, lay, ctx->d_key[0][0].as<u64>(), (u64 *)nullptr);
+    else
+        LAUNCH(build_keys_kernel<2>, grid_for(n, 256), 256, n, (const i32 *)ctx->d_tid.p, (const i64 *)ctx->d_pos.p, (const u8 *)ctx->d_rev.p,
+               (const u64 *)ctx->d_umi2.p, (const u32 *)ctx->d_nmask.p, lay, ctx->d_key[0][0].as<u64>(), ctx->d_key[0][1].as<u64>());
+    STAGE_END(UMIGPU_STAGE_KEYS);
+
+    // ---- K2 sort ----
+    STAGE_BEGIN(UMIGPU_STAGE_SORT);
+    int cur = 0;
+    rc = run_sort(ctx, n, lay.nw, lay.total_bits, &cur);
+    if (rc) return rc;
+    STAGE_END(UMIGPU_STAGE_SORT);
+    SortedKeys sk{ctx->d_key[cur][0].as<u64>(), lay.nw == 2 ? ctx->d_key[cur][1].as<u64>() : nullptr, lay.umi_bits};
+    const u32 *sorted_idx = ctx->d_idx[cur].as<u32>();
+
+    // ---- K3 unique / count / merge ----
+    STAGE_BEGIN(UMIGPU_STAGE_UNIQUE);
+    CK(ctx->d_useg.reserve((n + 1) * 4));
+    CK(ctx->d_rep.reserve(n * 8));
+    CK(ctx->d_planes.reserve(n * 8));
+    if (has_n) CK(ctx->d_nplane.reserve(n * 4));
+    CK(ctx->d_bhead.reserve(n));
+    const bool weighted = ctx->have_weight == 1;
+    if (weighted) { CK(ctx->d_wsum.reserve(n * 4)); CK(cudaMemsetAsync(ctx->d_wsum.p, 0, n * 4, ctx->stream)); }
+    if (want_labels) CK(ctx->d_read_uid.reserve(n * 4));
+    CK(cudaMemsetAsync(ctx->d_rep.p, 0, n * 8, ctx->stream));
+    const bool use_score = ctx->have_score == 1 && cfg.merge != UMIGPU_MERGE_ANY;
+    UniqueEmit ue;
+    ue.sk = sk; ue.n = n; ue.idx = sorted_idx; ue.score = use_score ? ctx->d_score.as<i32>() : nullptr;
+    ue.weight = weighted ? ctx->d_weight.as<i32>() : nullptr; ue.L = lay.umi_len; ue.has_n = lay.has_n;
+    ue.useg = ctx->d_useg.as<u32>(); ue.planes = ctx->d_planes.as<uint2>(); ue.nplane = ctx->d_nplane.as<u32>();
+    ue.bhead = ctx->d_bhead.as<u8>(); ue.rep = ctx->d_rep.as<unsigned long long>(); ue.wsum = ctx->d_wsum.as<i32>();
+    ue.read_uid = want_labels ? ctx->d_read_uid.as<u32>() : nullptr;
+    rc = run_scan(ctx, HeadFlag{sk}, ue, n, &sc->n_unique);
+    if (rc) return rc;
+    rc = read_scalars(ctx);
+    if (rc) return rc;
+    const u32 U = ctx->h_sc->n_unique;
+    ctx->n_unique = U;
+    CK(ctx->d_freq.reserve((size_t)U * 4)); CK(ctx->d_thr.reserve((size_t)U * 4)); CK(ctx->d_repidx.reserve((size_t)U * 4));
+    CK(ctx->d_label.reserve((size_t)U * 8)); CK(ctx->d_keep.reserve(U));
+    const bool inf_thr = force_inf_thr || cfg.algo == UMIGPU_ALGO_CC || cfg.algo == UMIGPU_ALGO_ADJ_UPSTREAM;
+    LAUNCH(unique_finalize_kernel, grid_for(U, 256), 256, U, (const u32 *)ctx->d_useg.p, (const unsigned long long *)ctx->d_rep.p,
+           weighted ? (const i32 *)ctx->d_wsum.p : (const i32 *)nullptr, cfg.percentage, inf_thr ? 1 : 0, ctx->d_freq.as<i32>(),
+           ctx->d_thr.as<i32>(), ctx->d_repidx.as<u32>(), ctx->d_label.as<unsigned long long>());
+    STAGE_END(UMIGPU_STAGE_UNIQUE);
+
+    // ---- buckets + work list ----
+    STAGE_BEGIN(UMIGPU_STAGE_WORKLIST);
+    CK(ctx->d_bstart.reserve(((size_t)U + 1) * 4));
+    rc = run_scan(ctx, BucketHead{ctx->d_bhead.as<u8>()}, BucketEmit{ctx->d_bstart.as<u32>(), U}, U, &sc->n_buckets);
+    if (rc) return rc;
+    rc = read_scalars(ctx);
+    if (rc) return rc;
+    const u32 B = ctx->h_sc->n_buckets;
+    ctx->n_buckets = B;
+    LAUNCH(bucket_stats_kernel, grid_for(B, 256), 256, B, (const u32 *)ctx->d_bstart.p, sc);
+
+    const bool need_edges = (mode == RUN_EDGES_ONLY || cfg.algo != UMIGPU_ALGO_ADJ) && cfg.k > 0 && U > B;
+    u32 W = 0;
+    u64 n_edges = 0;
+    if (need_edges) {
+        CK(ctx->d_itemoff.reserve(((size_t)B + 1) * 4));
+        rc = run_scan(ctx, BucketItems{ctx->d_bstart.as<u32>()}, BucketItemsEmit{ctx->d_itemoff.as<u32>(), B}, B, &sc->n_items);
+        if (rc) return rc;
+        rc = read_scalars(ctx);
+        if (rc) return rc;
+        W = ctx->h_sc->n_items;
+        CK(ctx->d_items.reserve((size_t)W * sizeof(TileItem)));
+        LAUNCH(build_items_kernel, grid_for(W, 256), 256, W, B, (const u32 *)ctx->d_itemoff.p, (const u32 *)ctx->d_bstart.p,
+               ctx->d_items.as<TileItem>(), sc);
+    }
+    STAGE_END(UMIGPU_STAGE_WORKLIST);
+
+    // ---- K5 neighbours ----
+    STAGE_BEGIN(UMIGPU_STAGE_NEIGHBOURS);
+    if (need_edges && W > 0) {
+        u64 cap = std::max<u64>((u64)1 << 20, (u64)U * 8);
+        if (ctx->d_edges.cap / sizeof(uint2) > cap) cap = ctx->d_edges.cap / sizeof(uint2);
+        for (int attempt = 0; attempt < 2; attempt++) {
+            CK(ctx->d_edges.reserve(cap * sizeof(uint2)));
+            CK(cudaMemsetAsync(&sc->edge_count, 0, sizeof(u64), ctx->stream));
+            EdgeSink es{ctx->d_edges.as<uint2>(), (unsigned long long *)&sc->edge_count, cap, ctx->d_freq.as<i32>(), ctx->d_thr.as<i32>()};
+            rc = launch_neighbours(ctx, W, es, has_n);
+            if (rc) return rc;
+            rc = read_scalars(ctx);
+            if (rc) return rc;
+            n_edges = ctx->h_sc->edge_count;
+            if (n_edges <= cap) break;
+            if (attempt == 1) return fail(ctx, UMIGPU_ERR_CUDA, "edge count changed between passes");
+            cap = n_edges;                 // exact count is known now: one more pass with the right size
+        }
+    } else {
+        rc = read_scalars(ctx);
+        if (rc) return rc;
+    }
+    STAGE_END(UMIGPU_STAGE_NEIGHBOURS);
+    ctx->n_edges = n_edges;
+    ctx->ctr.n_buckets = B; ctx->ctr.total_umis = U; ctx->ctr.max_umis = ctx->h_sc->max_umis;
+    ctx->ctr.unordered_pairs = ctx->h_sc->pairs; ctx->ctr.pairs_evaluated = ctx->h_sc->pairs_eval;
+    ctx->ctr.n_edges = n_edges; ctx->ctr.n_tile_items = W;
+    if (mode == RUN_EDGES_ONLY) { STAGE_END(UMIGPU_STAGE_TOTAL); return UMIGPU_OK; }
+
+    // ---- K6 cluster ----
+    STAGE_BEGIN(UMIGPU_STAGE_CLUSTER);
+    u8 *keep = ctx->d_keep.as<u8>();
+    unsigned long long *label = ctx->d_label.as<unsigned long long>();
+    const uint2 *edges = ctx->d_edges.as<uint2>();
+    u32 egrid = (u32)std::min<u64>(std::max<u64>(1, ceil_div_u64(n_edges, 256)), (u64)ctx->num_sms * 16);
+    u64 sweeps = 0;
+    if (cfg.algo == UMIGPU_ALGO_ADJ || n_edges == 0) {
+        CK(cudaMemsetAsync(keep, 1, U, ctx->stream));     // adjacency.rs:56 removes only the query itself
+    } else if (cfg.algo == UMIGPU_ALGO_ADJ_UPSTREAM) {
+        CK(ctx->d_state.reserve(U)); CK(ctx->d_blocked.reserve(U)); CK(ctx->d_prio.reserve((size_t)U * 8));
+        CK(cudaMemsetAsync(ctx->d_state.p, 0, U, ctx->stream)); CK(cudaMemsetAsync(ctx->d_blocked.p, 0, U, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_prio.p, label, (size_t)U * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        const unsigned long long *prio = ctx->d_prio.as<unsigned long long>();
+        for (;;) {
+            CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
+            LAUNCH(mis_edge_kernel, egrid, 256, edges, n_edges, prio, ctx->d_state.as<u8>(), ctx->d_blocked.as<u8>());
+            LAUNCH(mis_node_kernel, grid_for(U, 256), 256, U, ctx->d_state.as<u8>(), ctx->d_blocked.as<u8>(), sc);
+            sweeps++;
+            rc = read_scalars(ctx);
+            if (rc) return rc;
+            if (!ctx->h_sc->changed) break;
+        }
+        LAUNCH(mis_label_kernel, egrid, 256, edges, n_edges, prio, (const u8 *)ctx->d_state.p, label);
+        LAUNCH(mis_keep_kernel, grid_for(U, 256), 256, U, (const u8 *)ctx->d_state.p, keep);
+    } else {
+        for (;;) {
+            CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
+            for (int i = 0; i < 4; i++) LAUNCH(label_sweep_kernel, egrid, 256, edges, n_edges, label, sc);
+            sweeps += 4;
+            rc = read_scalars(ctx);
+            if (rc) return rc;
+            if (!ctx->h_sc->changed) break;
+        }
+        LAUNCH(keep_from_label_kernel, grid_for(U, 256), 256, U, (const unsigned long long *)label, keep);
+    }
+    ctx->ctr.n_sweeps = sweeps;
+    STAGE_END(UMIGPU_STAGE_CLUSTER);
+
+    // ---- K7 emit ----
+    STAGE_BEGIN(UMIGPU_STAGE_EMIT);
+    u64 n_words = ceil_div_u64(n, 32);
+    CK(ctx->d_bitmap.reserve(n_words * 4));
+    CK(cudaMemsetAsync(ctx->d_bitmap.p, 0, n_words * 4, ctx->stream));
+    LAUNCH(mark_kept_kernel, grid_for(U, 256), 256, U, (const u8 *)keep, (const u32 *)ctx->d_repidx.p, ctx->d_bitmap.as<u32>());
+    CK(ctx->d_kept.reserve((size_t)U * 4));
+    rc = run_scan(ctx, BitmapCount{ctx->d_bitmap.as<u32>()}, BitmapEmit{ctx->d_bitmap.as<u32>(), ctx->d_kept.as<u32>(), n_words, sc}, n_words, nullptr);
+    if (rc) return rc;
+    if (want_labels) {
+        CK(ctx->d_roots.reserve(n * 4));
+        LAUNCH(read_roots_kernel, grid_for(n, 256), 256, n, (const u32 *)ctx->d_read_uid.p, (const unsigned long long *)label,
+               (const u32 *)ctx->d_repidx.p, ctx->d_roots.as<u32>());
+    }
+    STAGE_END(UMIGPU_STAGE_EMIT);
+    STAGE_END(UMIGPU_STAGE_TOTAL);
+    rc = read_scalars(ctx);
+    if (rc) return rc;
+    ctx->ctr.n_kept = ctx->h_sc->n_kept;
+    return UMIGPU_OK;
+}
+
+static int launch_neighbours(umigpu_ctx *ctx, u32 n_items, EdgeSink es, bool has_n) {
+    const umigpu_config &cfg = ctx->cfg;
+    const TileItem *items = ctx->d_items.as<TileItem>();
+    const uint2 *planes = ctx->d_planes.as<uint2>();
+    const u32 *nplane = ctx->d_nplane.as<u32>();
+    u32 grid = std::min<u32>(n_items, (u32)ctx->num_sms * 4);
+    const int k = cfg.k;
+    if (!(cfg.flags & UMIGPU_FLAG_KERNEL_DIRECT)) {
+        int rc = launch_neighbours_bitsliced(ctx->stream, ctx->num_sms, items, n_items, planes, nplane, (int)cfg.umi_len, k, has_n, es,
+                                             &ctx->d_onehot);
+        if (rc == 0) { ctx->launches += 1; CK(cudaGetLastError()); return UMIGPU_OK; }
+        if (rc < 0) return fail(ctx, UMIGPU_ERR_CUDA, "bit-sliced neighbour kernel: %s", cudaGetErrorString(cudaGetLastError()));
+        // rc > 0: configuration not covered by the bit-sliced kernel (k > 3) -> direct kernel
+    }
+#define HD(KK, NN) LAUNCH((hamming_tiles_direct<KK, NN>), grid, HT_THREADS, items, n_items, planes, nplane, es, k)
+    if (!has_n) { if (k == 1) HD(1, false); else if (k == 2) HD(2, false); else HD(0, false); }
+    else        { if (k == 1) HD(1, true);  else if (k == 2) HD(2, true);  else HD(0, true); }
+#undef HD
+    return UMIGPU_OK;
+}
+
+extern "C" int umigpu_run(umigpu_ctx *ctx) {
+    if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
+    return run_internal(ctx, RUN_FULL, (ctx->cfg.flags & UMIGPU_FLAG_LABELS) != 0, false);
+}
+
+static int translate_indices(const umigpu_ctx *ctx, const u32 *in, u64 n, std::vector<u64> &out, bool ascending) {
+    out.resize(n);
+    const std::vector<Chunk> &ch = ctx->chunks;
+    if (ch.size() == 1) { const u64 off = ch[0].first_index; for (u64 i = 0; i < n; i++) out[i] = off + in[i]; return 0; }
+    size_t c = 0;
+    for (u64 i = 0; i < n; i++) {
+        u64 r = in[i];
+        if (ascending) { while (c + 1 < ch.size() && r >= ch[c].start + ch[c].n) c++; }
+        else { c = std::upper_bound(ch.begin(), ch.end(), r, [](u64 v, const Chunk &k) { return v < k.start; }) - ch.begin() - 1; }
+        out[i] = ch[c].first_index + (r - ch[c].start);
+    }
+    return 0;
+}
+
+static int fetch_internal(umigpu_ctx *ctx, bool want_labels) {
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (!ctx->ran) return fail(ctx, UMIGPU_ERR_STATE, "fetch before run");
+    const u64 nk = ctx->ctr.n_kept, n = ctx->n_reads;
+    if (nk > ctx->h_kept32_cap) {
+        if (ctx->h_kept32) cudaFreeHost(ctx->h_kept32);
+        ctx->h_kept32 = nullptr; ctx->h_kept32_cap = 0;
+        CK(cudaMallocHost((void **)&ctx->h_kept32, (nk + nk / 4 + 16) * 4));
+        ctx->h_kept32_cap = nk + nk / 4 + 16;
+    }
+    if (nk) CK(cudaMemcpyAsync(ctx->h_kept32, ctx->d_kept.p, nk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_labels && n) {
+        if (n > ctx->h_roots32_cap) {
+            if (ctx->h_roots32) cudaFreeHost(ctx->h_roots32);
+            ctx->h_roots32 = nullptr; ctx->h_roots32_cap = 0;
+            CK(cudaMallocHost((void **)&ctx->h_roots32, (n + 16) * 4));
+            ctx->h_roots32_cap = n + 16;
+        }
+        CK(cudaMemcpyAsync(ctx->h_roots32, ctx->d_roots.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    translate_indices(ctx, ctx->h_kept32, nk, ctx->h_kept, true);
+    if (want_labels) translate_indices(ctx, ctx->h_roots32, n, ctx->h_roots, false); else ctx->h_roots.clear();
+    return UMIGPU_OK;
+}
+
+extern "C" int umigpu_fetch(umigpu_ctx *ctx, umigpu_result *out) {
+    if (!ctx || !out) return fail(ctx, UMIGPU_ERR_ARG, "null argument");
+    const bool want_labels = (ctx->cfg.flags & UMIGPU_FLAG_LABELS) != 0;
+    int rc = fetch_internal(ctx, want_labels);
+    if (rc) return rc;
+    out->n_kept = ctx->ctr.n_kept;
+    out->kept_read_index = ctx->h_kept.data();
+    out->n_reads = ctx->n_reads;
+    out->read_cluster_root = want_labels ? ctx->h_roots.data() : nullptr;
+    out->counters = ctx->ctr;
+    return UMIGPU_OK;
+}
+
+extern "C" int umigpu_finish(umigpu_ctx *ctx, umigpu_result *out) {
+    int rc = umigpu_run(ctx);
+    if (rc) return rc;
+    return umigpu_fetch(ctx, out);
+}
+
+extern "C" int umigpu_get_counters(umigpu_ctx *ctx, umigpu_counters *out) {
+    if (!ctx || !out) return fail(ctx, UMIGPU_ERR_ARG, "null argument");
+    if (!ctx->ran) return fail(ctx, UMIGPU_ERR_STATE, "counters before run");
+    *out = ctx->ctr;
+    return UMIGPU_OK;
+}
+
+extern "C" void umigpu_result_free(umigpu_ctx *ctx) {
+    if (!ctx) return;
+    std::vector<u64>().swap(ctx->h_kept);
+    std::vector<u64>().swap(ctx->h_roots);
+}
+
+extern "C" int umigpu_stage_ms(umigpu_ctx *ctx, int stage, float *ms) {
+    if (!ctx || !ms || stage < 0 || stage >= UMIGPU_N_STAGES) return fail(ctx, UMIGPU_ERR_ARG, "bad stage");
+    *ms = 0.0f;
+    if (!ctx->ev_ok[stage]) return UMIGPU_OK;
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaEventSynchronize(ctx->ev[stage][1]));
+    CK(cudaEventElapsedTime(ms, ctx->ev[stage][0], ctx->ev[stage][1]));
+    return UMIGPU_OK;
+}
+
+extern "C" uint64_t umigpu_launch_count(umigpu_ctx *ctx, int reset) {
+    if (!ctx) return 0;
+    u64 v = ctx->launches;
+    if (reset) ctx->launches = 0;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Algorithm::apply / DataStruct shaped entries
+// ------------------------------------------------------------------------------------------------
+extern "C" int umigpu_cluster_bucket(umigpu_ctx *ctx, uint64_t n, const uint8_t *umi_ascii, const int32_t *freq,
+                                     uint8_t *keep, int32_t *label) {
+    if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
+    if (n && (!umi_ascii || !freq || !keep || !label)) return fail(ctx, UMIGPU_ERR_ARG, "null argument");
+    if (n > 0x7fffffffull) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "bucket too large");
+    int rc = umigpu_reset(ctx);
+    if (rc) return rc;
+    if (n == 0) return UMIGPU_OK;
+    rc = push_common(ctx, n, nullptr, nullptr, nullptr, umi_ascii, nullptr, freq, 0, cudaMemcpyHostToDevice);
+    if (rc) return rc;
+    rc = run_internal(ctx, RUN_FULL, true, false);
+    if (rc) return rc;
+    rc = fetch_internal(ctx, true);
+    if (rc) return rc;
+    if (ctx->n_unique != n) return fail(ctx, UMIGPU_ERR_ARG, "umigpu_cluster_bucket: UMIs of a bucket must be distinct (%u unique of %llu)",
+                                         ctx->n_unique, (unsigned long long)n);
+    for (u64 i = 0; i < n; i++) { label[i] = (i32)ctx->h_roots[i]; keep[i] = ctx->h_roots[i] == i ? 1 : 0; }
+    return UMIGPU_OK;
+}
+
+extern "C" int umigpu_remove_near(umigpu_ctx *ctx, uint64_t n, const uint8_t *umi_ascii, const int32_t *freq,
+                                  const uint8_t *query, int32_t k, int32_t max_freq, uint8_t *out) {
+    if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
+    if (!query || (n && (!umi_ascii || !freq || !out))) return fail(ctx, UMIGPU_ERR_ARG, "null argument");
+    if (n > 0x7fffffffull) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "set too large");
+    int rc = umigpu_reset(ctx);
+    if (rc) return rc;
+    const int L = (int)ctx->cfg.umi_len;
+    // the query rides along as read n so that it is packed (and validated) by the same kernel
+    std::vector<u8> all((n + 1) * L);
+    if (n) memcpy(all.data(), umi_ascii, n * L);
+    memcpy(all.data() + n * L, query, L);
+    rc = push_common(ctx, n + 1, nullptr, nullptr, nullptr, all.data(), nullptr, nullptr, 0, cudaMemcpyHostToDevice);
+    if (rc) return rc;
+    rc = read_scalars(ctx);
+    if (rc) return rc;
+    if (ctx->h_sc->bad_base) return fail(ctx, UMIGPU_ERR_BAD_BASE, "Unknown character in UMI sequence");
+    if (n == 0) return UMIGPU_OK;
+    u64 q2; u32 qn;
+    CK(cudaMemcpyAsync(&q2, ctx->d_umi2.as<u64>() + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&qn, ctx->d_nmask.as<u32>() + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->d_freq.reserve(n * 4)); CK(ctx->d_keep.reserve(n));
+    CK(cudaMemcpyAsync(ctx->d_freq.p, freq, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(remove_near_kernel, grid_for(n, 256), 256, (u32)n, (const u64 *)ctx->d_umi2.p, (const u32 *)ctx->d_nmask.p, q2, qn,
+           (const i32 *)ctx->d_freq.p, (int)k, max_freq, ctx->d_keep.as<u8>());
+    CK(cudaMemcpyAsync(out, ctx->d_keep.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return UMIGPU_OK;
+}
+
+// edges (unique ids) -> (src input index << 32 | dst input index)
+__global__ void __launch_bounds__(256) edges_to_keys_kernel(const uint2 *__restrict__ edges, u64 n_edges, const u32 *__restrict__ rep_idx,
+                                                            u64 *__restrict__ keys) {
+    u64 e = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (e < n_edges) { uint2 ed = edges[e]; keys[e] = ((u64)rep_idx[ed.x] << 32) | rep_idx[ed.y]; }
+}
+__global__ void __launch_bounds__(256) csr_from_sorted_kernel(const u64 *__restrict__ keys, u64 n_edges, u32 n_rows,
+                                                              u64 *__restrict__ row_ptr, u32 *__restrict__ col) {
+    u64 e = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (e > n_edges) return;
+    // row_ptr[r] = first e with src >= r
+    u32 src_here = e < n_edges ? (u32)(keys[e] >> 32) : n_rows;
+    u32 src_prev = e > 0 ? (u32)(keys[e - 1] >> 32) : 0;
+    if (e == 0) for (u32 r = 0; r <= src_here; r++) row_ptr[r] = 0;
+    else for (u32 r = src_prev + 1; r <= src_here; r++) row_ptr[r] = e;
+    if (e < n_edges) col[e] = (u32)keys[e];
+}
+
+extern "C" int umigpu_neighbours(umigpu_ctx *ctx, uint64_t n, const uint8_t *umi_ascii, const int32_t *freq,
+                                 int32_t apply_rule, uint64_t *row_ptr, uint32_t *col, uint64_t col_capacity,
+                                 uint64_t *n_edges_out) {
+    if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
+    if (!row_ptr || !n_edges_out || (n && (!umi_ascii || !freq))) return fail(ctx, UMIGPU_ERR_ARG, "null argument");
+    if (n > 0x7fffffffull) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "bucket too large");
+    int rc = umigpu_reset(ctx);
+    if (rc) return rc;
+    *n_edges_out = 0;
+    if (n == 0) { row_ptr[0] = 0; return UMIGPU_OK; }
+    rc = push_common(ctx, n, nullptr, nullptr, nullptr, umi_ascii, nullptr, freq, 0, cudaMemcpyHostToDevice);
+    if (rc) return rc;
+    rc = run_internal(ctx, RUN_EDGES_ONLY, false, apply_rule == 0);
+    if (rc) return rc;
+    if (ctx->n_unique != n) return fail(ctx, UMIGPU_ERR_ARG, "umigpu_neighbours: UMIs must be distinct");
+    const u64 E = ctx->n_edges;
+    *n_edges_out = E;
+    if (E > col_capacity) return fail(ctx, UMIGPU_ERR_ARG, "col_capacity %llu < %llu edges", (unsigned long long)col_capacity, (unsigned long long)E);
+    if (E == 0) { for (u64 i = 0; i <= n; i++) row_ptr[i] = 0; return UMIGPU_OK; }
+    // sort (src, dst) in input-index space with the same radix sort, then cut rows
+    CK(ctx->d_key[0][0].reserve(E * 8)); CK(ctx->d_key[1][0].reserve(E * 8));
+    CK(ctx->d_idx[0].reserve(E * 4)); CK(ctx->d_idx[1].reserve(E * 4));
+    LAUNCH(edges_to_keys_kernel, grid_for(E, 256), 256, (const uint2 *)ctx->d_edges.p, E, (const u32 *)ctx->d_repidx.p, ctx->d_key[0][0].as<u64>());
+    int nb = bits_for(n - 1);
+    int cur = 0;
+    // keys are (src << 32 | dst): sort the dst bits, then the src bits
+    {
+        std::vector<SortPass> passes;
+        for (int part = 0; part < 2; part++) {
+            int done = 0, np = (nb + 7) / 8;
+            for (int i = 0; i < np; i++) { int b = (nb - done + (np - i) - 1) / (np - i); passes.push_back({0, part * 32 + done, b}); done += b; }
+        }
+        u32 nblk = (u32)ceil_div_u64(E, RS_TILE);
+        CK(ctx->d_hist.reserve((size_t)256 * nblk * 4));
+        u32 *hist = ctx->d_hist.as<u32>();
+        bool first = true;
+        for (const SortPass &p : passes) {
+            KeyArr in{{ctx->d_key[cur][0].as<u64>(), nullptr}}, outk{{ctx->d_key[cur ^ 1][0].as<u64>(), nullptr}};
+            u32 mask = (1u << p.bits) - 1;
+            LAUNCH(radix_hist, nblk, RS_THREADS, (const u64 *)in.w[0], E, p.shift, mask, hist, nblk);
+            rc = run_scan(ctx, HistLoad{hist}, HistStore{hist}, (u64)256 * nblk, nullptr);
+            if (rc) return rc;
+            LAUNCH(radix_scatter<1>, nblk, RS_THREADS, in, (const u32 *)ctx->d_idx[cur].as<u32>(), outk, ctx->d_idx[cur ^ 1].as<u32>(), E, 0,
+                   p.shift, mask, (const u32 *)hist, nblk, first ? 1 : 0);
+            cur ^= 1; first = false;
+        }
+    }
+    CK(ctx->d_rep.reserve((n + 1) * 8)); CK(ctx->d_kept.reserve(E * 4));
+    LAUNCH(csr_from_sorted_kernel, grid_for(E + 1, 256), 256, (const u64 *)ctx->d_key[cur][0].p, E, (u32)n, ctx->d_rep.as<u64>(), ctx->d_kept.as<u32>());
+    CK(cudaMemcpyAsync(row_ptr, ctx->d_rep.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(col, ctx->d_kept.p, E * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return UMIGPU_OK;
+}
+
+extern "C" int umigpu_avg_qual(umigpu_ctx *ctx, uint64_t n, const uint8_t *qual, const uint64_t *offsets, int32_t *out) {
+    if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
+    if (n == 0) return UMIGPU_OK;
+    if (!qual || !offsets || !out) return fail(ctx, UMIGPU_ERR_ARG, "null argument");
+    CK(cudaSetDevice(ctx->cfg.device));
+    const u64 total = offsets[n];
+    DevBuf dq, doff, dout;
+    int rc = UMIGPU_OK;
+#define CKQ(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(ctx, UMIGPU_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); goto done; } } while (0)
+    CKQ(dq.reserve(total + 1)); CKQ(doff.reserve((n + 1) * 8)); CKQ(dout.reserve(n * 4));
+    CKQ(cudaMemcpyAsync(dq.p, qual, total, cudaMemcpyHostToDevice, ctx->stream));
+    CKQ(cudaMemcpyAsync(doff.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    avg_qual_kernel<<<grid_for(n * 32, 256), 256, 0, ctx->stream>>>(n, dq.as<u8>(), doff.as<u64>(), dout.as<i32>());
+    ctx->launches++;
+    CKQ(cudaGetLastError());
+    CKQ(cudaMemcpyAsync(out, dout.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CKQ(cudaStreamSynchronize(ctx->stream));
+done:
+#undef CKQ
+    dq.release(); doff.release(); dout.release();
+    return rc;
+}
+
+extern "C" int umigpu_int_peak(umigpu_ctx *ctx, double *lop3_ops_per_s, double *popc_ops_per_s) {
+    if (!ctx || !lop3_ops_per_s || !popc_ops_per_s) return fail(ctx, UMIGPU_ERR_ARG, "null argument");
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(ctx->d_tiles.reserve(64));
+    const u32 iters = 1 << 16, grid = (u32)ctx->num_sms * 8;
+    cudaEvent_t a = ctx->ev[UMIGPU_STAGE_PACK][0], b = ctx->ev[UMIGPU_STAGE_PACK][1];
+    float best[2] = {1e30f, 1e30f};
+    for (int rep = 0; rep < 4; rep++) {
+        for (int which = 0; which < 2; which++) {
+            CK(cudaEventRecord(a, ctx->stream));
+            if (which == 0) LAUNCH(int_peak_lop3_kernel, grid, 256, iters, 12345u + rep, ctx->d_tiles.as<u32>());
+            else            LAUNCH(int_peak_popc_kernel, grid, 256, iters, 12345u + rep, ctx->d_tiles.as<u32>());
+            CK(cudaEventRecord(b, ctx->stream));
+            CK(cudaEventSynchronize(b));
+            float ms; CK(cudaEventElapsedTime(&ms, a, b));
+            if (rep > 0 && ms < best[which]) best[which] = ms;
+        }
+    }
+    const double ops = (double)iters * 8.0 * 256.0 * grid;
+    *lop3_ops_per_s = ops / (best[0] * 1e-3);
+    *popc_ops_per_s = ops / (best[1] * 1e-3);
+    return UMIGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU sharding plan (host helper; buckets are independent)
+// ------------------------------------------------------------------------------------------------
+struct BKey { i64 pos; i32 tid; u8 rev; bool operator==(const BKey &o) const { return pos == o.pos && tid == o.tid && rev == o.rev; } };
+struct BKeyHash {
+    size_t operator()(const BKey &k) const {
+        u64 x = (u64)k.pos * 0x9E3779B97F4A7C15ull ^ ((u64)(u32)k.tid << 1 | k.rev) * 0xC2B2AE3D27D4EB4Full;
+        x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+        return (size_t)x;
+    }
+};
+
+extern "C" int umigpu_shard_plan(uint64_t n, const int32_t *tid, const int64_t *unclipped_pos, const uint8_t *is_reverse,
+                                 int32_t n_shards, int32_t *shard_of_read, uint64_t *shard_cost) {
+    if (n_shards < 1 || (n && (!tid || !unclipped_pos || !is_reverse || !shard_of_read)))
+        return fail(nullptr, UMIGPU_ERR_ARG, "umigpu_shard_plan: bad argument");
+    try {
+        std::unordered_map<BKey, u32, BKeyHash> ids;
+        ids.reserve(1 << 16);
+        std::vector<u64> count;
+        std::vector<u32> bid(n);
+        for (u64 i = 0; i < n; i++) {
+            BKey k{unclipped_pos[i], tid[i], (u8)(is_reverse[i] ? 1 : 0)};
+            auto it = ids.find(k);
+            u32 id;
+            if (it == ids.end()) { id = (u32)count.size(); ids.emplace(k, id); count.push_back(0); } else id = it->second;
+            count[id]++; bid[i] = id;
+        }
+        const size_t nb = count.size();
+        std::vector<u32> order(nb);
+        for (size_t b = 0; b < nb; b++) order[b] = (u32)b;
+        // cost model: neighbour search ~ reads^2 (upper bound of N_b^2), plus a linear term for the HBM-bound stages
+        auto cost = [&](u32 b) { return count[b] * count[b] + 64 * count[b]; };
+        std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return cost(a) > cost(b); });
+        typedef std::pair<u64, i32> Load;   // (load, shard): least loaded first, ties to the lower shard id
+        std::priority_queue<Load, std::vector<Load>, std::greater<Load>> pq;
+        for (i32 s = 0; s < n_shards; s++) pq.push({0, s});
+        std::vector<i32> shard_of_bucket(nb);
+        std::vector<u64> loads(n_shards, 0);
+        for (u32 b : order) {
+            Load l = pq.top(); pq.pop();
+            shard_of_bucket[b] = l.second;
+            l.first += cost(b); loads[l.second] = l.first;
+            pq.push(l);
+        }
+        for (u64 i = 0; i < n; i++) shard_of_read[i] = shard_of_bucket[bid[i]];
+        if (shard_cost) for (i32 s = 0; s < n_shards; s++) shard_cost[s] = loads[s];
+    } catch (const std::bad_alloc &) {
+        return fail(nullptr, UMIGPU_ERR_NOMEM, "umigpu_shard_plan: out of host memory");
+    }
+    return UMIGPU_OK;
+}
