@@ -1,7 +1,155 @@
-// hamming_bs.cuh — bit-sliced one-hot neighbour kernel (placeholder until the first direct-kernel
-// measurements are in; returns 1 = "not covered" so the direct kernel runs).
+// hamming_bs.cuh — K5 hamming_neighbours, bit-sliced one-hot tile kernel (the production kernel).
+//
+// Same contract as hamming_tiles_direct (hamming.cuh) but 32 column UMIs are compared per
+// instruction.  For a tile of up to 2048 columns the CTA first builds, in shared memory, one-hot
+// match words
+//        eq[g][j][x]  (u32)   bit c = "column 32g+c has letter x at position j"      (warp ballots)
+// Each thread then owns one row UMI at a time.  For position j it loads the word selected by its
+// own letter a_j — the 32 columns that MATCH the row at j — and feeds a bit-sliced saturating
+// mismatch counter:   m1 &= w;  m2 = w ? m2 : m1;  [m3 = w ? m3 : m2; ...]   (one LOP3 each).
+// After umi_len positions, bit c of m_{k+1} says dist(row, column c) <= k.  That is k+1 LOP3 and one
+// broadcast LDS per base per 32 pairs (0.75 ALU ops per pair at 12 nt, k = 1) instead of ~4 per
+// pair for the direct XOR+popcount form; N needs no extra work (it is just a fifth letter).
+// Words of four consecutive column groups are interleaved so one LDS.128 feeds four counters.
+// Hits are rare (a handful per UMI) and go through the cold path record_hit().
 #pragma once
 #include "common.cuh"
 #include "hamming.cuh"
-static int launch_neighbours_bitsliced(cudaStream_t, int, const TileItem *, u32, const uint2 *, const u32 *, int, int, bool,
-                                       EdgeSink, DevBuf *) { return 1; }
+
+#define BS_THREADS 256
+#define BS_G4      (HT_COLS / 128)     // blocks of 4 column groups (128 columns) per tile
+
+template <int LP, int K, bool HASN>
+__global__ void __launch_bounds__(BS_THREADS) hamming_tiles_bs(
+    const TileItem *__restrict__ items, u32 n_items, const uint2 *__restrict__ planes, const u32 *__restrict__ nplane,
+    int L, EdgeSink es, u32 *work_counter) {
+    constexpr int XS = HASN ? 8 : 4;          // letter slots per position
+    constexpr int NLET = HASN ? 5 : 4;
+    extern __shared__ __align__(16) uint4 eq4[];   // [g4][LP][XS] x (4 groups)
+    __shared__ u32 s_item;
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const u32 w_item = s_item;
+        if (w_item >= n_items) break;
+        const TileItem it = items[w_item];
+        const u32 col_cnt = it.col_cnt_diag & 0x7fffffffu;
+        const bool diag = it.col_cnt_diag >> 31;
+        const u32 g4_cnt = (col_cnt + 127) >> 7;
+
+        // ---- build the one-hot match words of this column tile ----
+        for (u32 g = warp; g < g4_cnt * 4; g += BS_THREADS / 32) {
+            u32 c = g * 32 + lane;
+            bool valid = c < col_cnt;
+            uint2 p = valid ? planes[it.col_start + c] : make_uint2(0u, 0u);
+            u32 pn = (HASN && valid) ? nplane[it.col_start + c] : 0u;
+            u32 *dst = reinterpret_cast<u32 *>(eq4) + ((size_t)(g >> 2) * LP * XS) * 4 + (g & 3);
+#pragma unroll
+            for (int j = 0; j < LP; j++) {
+                u32 letter = ((p.y >> j) & 1u) * 2u + ((p.x >> j) & 1u);
+                if (HASN && ((pn >> j) & 1u)) letter = 4u;
+                if (!valid) letter = 15u;                 // padding column: matches no letter at any real position
+                u32 v = 0;
+#pragma unroll
+                for (int x = 0; x < NLET; x++) {
+                    u32 b = __ballot_sync(0xffffffffu, letter == (u32)x);
+                    if (lane == (u32)x) v = b;
+                }
+                if (j >= L) v = 0xffffffffu;              // positions beyond umi_len always match
+                if (lane < (u32)XS) dst[(j * XS + lane) * 4] = v;
+            }
+        }
+        __syncthreads();
+
+        // ---- rows ----
+        for (u32 gi = threadIdx.x; gi < it.row_cnt; gi += BS_THREADS) {
+            const uint2 rp = planes[it.row_start + gi];
+            const u32 rn = HASN ? nplane[it.row_start + gi] : 0u;
+            u32 off[LP];                                   // byte offset of the row's letter slot at position j
+#pragma unroll
+            for (int j = 0; j < LP; j++) {
+                u32 letter = ((rp.y >> j) & 1u) * 2u + ((rp.x >> j) & 1u);
+                if (HASN && ((rn >> j) & 1u)) letter = 4u;
+                off[j] = (u32)(j * XS + letter) * 16u;
+            }
+            const char *base = reinterpret_cast<const char *>(eq4);
+            for (u32 g4 = 0; g4 < g4_cnt; g4++, base += LP * XS * 16) {
+                uint4 m1 = make_uint4(~0u, ~0u, ~0u, ~0u), m2 = m1, m3 = m1, m4 = m1;
+#pragma unroll
+                for (int j = 0; j < LP; j++) {
+                    const uint4 w = *reinterpret_cast<const uint4 *>(base + off[j]);
+                    if (K >= 3) { m4.x = (w.x & m4.x) | (~w.x & m3.x); m4.y = (w.y & m4.y) | (~w.y & m3.y);
+                                  m4.z = (w.z & m4.z) | (~w.z & m3.z); m4.w = (w.w & m4.w) | (~w.w & m3.w); }
+                    if (K >= 2) { m3.x = (w.x & m3.x) | (~w.x & m2.x); m3.y = (w.y & m3.y) | (~w.y & m2.y);
+                                  m3.z = (w.z & m3.z) | (~w.z & m2.z); m3.w = (w.w & m3.w) | (~w.w & m2.w); }
+                    m2.x = (w.x & m2.x) | (~w.x & m1.x); m2.y = (w.y & m2.y) | (~w.y & m1.y);
+                    m2.z = (w.z & m2.z) | (~w.z & m1.z); m2.w = (w.w & m2.w) | (~w.w & m1.w);
+                    m1.x &= w.x; m1.y &= w.y; m1.z &= w.z; m1.w &= w.w;
+                }
+                const uint4 h = K == 1 ? m2 : (K == 2 ? m3 : m4);
+                if (h.x | h.y | h.z | h.w) {
+                    const u32 a = it.row_start + gi;
+                    const u32 hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        u32 bits = hv[i];
+                        while (bits) {
+                            u32 b = __ffs(bits) - 1; bits &= bits - 1;
+                            u32 c = (g4 * 4 + i) * 32 + b;
+                            if (c < col_cnt) {
+                                u32 bb = it.col_start + c;
+                                if (!diag || a < bb) record_hit(es, a, bb);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int LP, int K, bool HASN>
+static int bs_launch_one(cudaStream_t stream, int num_sms, const TileItem *items, u32 n_items, const uint2 *planes,
+                         const u32 *nplane, int L, EdgeSink es, u32 *counter) {
+    constexpr int XS = HASN ? 8 : 4;
+    size_t smem = (size_t)BS_G4 * LP * XS * 16;
+    auto kern = hamming_tiles_bs<LP, K, HASN>;
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BS_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
+    u32 grid = (u32)std::min<u64>((u64)n_items, (u64)num_sms * occ);
+    if (cudaMemsetAsync(counter, 0, sizeof(u32), stream) != cudaSuccess) return -1;
+    kern<<<grid, BS_THREADS, smem, stream>>>(items, n_items, planes, nplane, L, es, counter);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+template <int K, bool HASN>
+static int bs_launch_k(cudaStream_t stream, int num_sms, const TileItem *items, u32 n_items, const uint2 *planes,
+                       const u32 *nplane, int L, EdgeSink es, u32 *counter) {
+    if (L <= 8)  return bs_launch_one<8, K, HASN>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
+    if (L <= 12) return bs_launch_one<12, K, HASN>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
+    if (L <= 16) return bs_launch_one<16, K, HASN>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
+    if (L <= 24) return bs_launch_one<24, K, HASN>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
+    if (HASN) return 1;   // N-containing batches are limited to 21 nt upstream of here
+    return bs_launch_one<32, K, false>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
+}
+
+// returns 0 = launched, 1 = configuration not covered (caller uses the direct kernel), -1 = CUDA error
+static int launch_neighbours_bitsliced(cudaStream_t stream, int num_sms, const TileItem *items, u32 n_items,
+                                       const uint2 *planes, const u32 *nplane, int L, int k, bool has_n, EdgeSink es,
+                                       u32 *counter) {
+    if (k < 1 || k > 3) return 1;
+    if (!has_n) {
+        if (k == 1) return bs_launch_k<1, false>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
+        if (k == 2) return bs_launch_k<2, false>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
+        return bs_launch_k<3, false>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
+    }
+    if (k == 1) return bs_launch_k<1, true>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
+    if (k == 2) return bs_launch_k<2, true>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
+    return bs_launch_k<3, true>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
+}

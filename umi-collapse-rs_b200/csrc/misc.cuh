@@ -35,9 +35,12 @@ __global__ void __launch_bounds__(256) int_peak_lop3_kernel(u32 iters, u32 seed,
 #pragma unroll
     for (int j = 0; j < 8; j++) a[j] = seed * (threadIdx.x + 1) + j * 0x9e3779b9u;
     u32 x = seed ^ 0x5bd1e995u, y = seed + blockIdx.x;
-    for (u32 i = 0; i < iters; i++) {
+    for (u32 i = 0; i < iters; i += 8) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) a[j] = (a[j] ^ x) | (a[j] & y);   // one LOP3 each
+        for (int u = 0; u < 8; u++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) a[j] = (a[j] ^ x) | (a[j] & y);   // one LOP3 each
+        }
         x += 0x01000193u;
     }
     u32 r = 0;
@@ -49,9 +52,12 @@ __global__ void __launch_bounds__(256) int_peak_popc_kernel(u32 iters, u32 seed,
     u32 a[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) a[j] = seed * (threadIdx.x + 1) + j * 0x9e3779b9u;
-    for (u32 i = 0; i < iters; i++) {
+    for (u32 i = 0; i < iters; i += 4) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) a[j] = __popc(a[j]) + 0x7f4a7c15u;   // POPC + IADD
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) a[j] = __popc(a[j]) ^ 0x7f4a7c15u;   // POPC + LOP3
+        }
     }
     u32 r = 0;
 #pragma unroll

@@ -492,7 +492,7 @@ static int launch_neighbours(umigpu_ctx *ctx, u32 n_items, EdgeSink es, bool has
     const int k = cfg.k;
     if (!(cfg.flags & UMIGPU_FLAG_KERNEL_DIRECT)) {
         int rc = launch_neighbours_bitsliced(ctx->stream, ctx->num_sms, items, n_items, planes, nplane, (int)cfg.umi_len, k, has_n, es,
-                                             &ctx->d_onehot);
+                                             (u32 *)&ctx->d_sc.as<DevScalars>()->scratch);
         if (rc == 0) { ctx->launches += 1; CK(cudaGetLastError()); return UMIGPU_OK; }
         if (rc < 0) return fail(ctx, UMIGPU_ERR_CUDA, "bit-sliced neighbour kernel: %s", cudaGetErrorString(cudaGetLastError()));
         // rc > 0: configuration not covered by the bit-sliced kernel (k > 3) -> direct kernel
