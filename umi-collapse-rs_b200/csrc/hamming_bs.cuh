@@ -117,7 +117,7 @@ static int bs_launch_one(cudaStream_t stream, int num_sms, const TileItem *items
     constexpr int XS = HASN ? 8 : 4;
     size_t smem = (size_t)BS_G4 * LP * XS * 16;
     auto kern = hamming_tiles_bs<LP, K, HASN>;
-    if (smem > 48 * 1024) {
+    if (smem + 256 > 48 * 1024) {      // + the kernel's static shared memory
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     }
     int occ = 0;

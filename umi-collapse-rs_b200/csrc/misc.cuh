@@ -34,12 +34,12 @@ __global__ void __launch_bounds__(256) int_peak_lop3_kernel(u32 iters, u32 seed,
     u32 a[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) a[j] = seed * (threadIdx.x + 1) + j * 0x9e3779b9u;
-    u32 x = seed ^ 0x5bd1e995u, y = seed + blockIdx.x;
+    u32 x = seed ^ 0x5bd1e995u ^ blockIdx.x;
     for (u32 i = 0; i < iters; i += 8) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) a[j] = (a[j] ^ x) | (a[j] & y);   // one LOP3 each
+            for (int j = 0; j < 8; j++) a[j] = (a[j] ^ x) | (a[j] & 0x0f0f0f0fu);   // one LOP3 each, two register operands (no bank conflict)
         }
         x += 0x01000193u;
     }
