@@ -79,9 +79,11 @@ typedef struct umigpu_counters {
     uint64_t max_umis;          /* max unique UMIs in a bucket, :218                                 */
     uint64_t n_kept;            /* reads after deduplicating, :219                                   */
     uint64_t unordered_pairs;   /* sum_b N_b (N_b - 1) / 2: what Naive must cover                    */
-    uint64_t pairs_evaluated;   /* pairs the device actually evaluated (after exact tile culling)    */
+    uint64_t pairs_evaluated;   /* pair evaluations the device executed (after exact culling; blocks
+                                   on the diagonal are evaluated in full)                             */
     uint64_t n_edges;           /* directed edges that passed the distance and count rule            */
-    uint64_t n_tile_items;      /* tile-pair work items executed                                     */
+    uint64_t n_tile_items;      /* tile-pair work items executed (survivors of the exact cull)       */
+    uint64_t n_tile_candidates; /* tile pairs before culling                                         */
     uint64_t n_sweeps;          /* label-propagation sweeps                                          */
 } umigpu_counters;
 

@@ -294,7 +294,7 @@ def test_properties_at_scale():
     assert cadj["n_kept"] == cadj["total_umis"]
     assert (np.diff(kdir.astype(np.int64)) > 0).all()                     # canonical order: ascending, unique
     assert set(kcc.tolist()) <= set(kdir.tolist()) <= set(kadj.tolist())
-    assert cdir["unordered_pairs"] >= cdir["pairs_evaluated"] > 0 or cdir["unordered_pairs"] == 0
+    assert cdir["pairs_evaluated"] > 0 and cdir["n_tile_candidates"] >= cdir["n_tile_items"] > 0
     # idempotence: deduplicating the survivors of cc again keeps all of them under adj, and dir survivors of dir
     idx = torch.from_numpy(kdir.astype(np.int64)).cuda()
     sub = {k: v[idx].contiguous() for k, v in d.items()}

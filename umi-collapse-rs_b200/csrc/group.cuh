@@ -126,38 +126,111 @@ __global__ void __launch_bounds__(256) bucket_stats_kernel(u32 n_buckets, const 
     }
 }
 
-// one thread per work item: bucket by binary search over item_off, (ti, tj) by triangular decode
-__global__ void __launch_bounds__(256) build_items_kernel(u32 n_items, u32 n_buckets, const u32 *__restrict__ item_off,
-                                                          const u32 *__restrict__ bstart, TileItem *__restrict__ items,
-                                                          DevScalars *sc) {
-    u32 w = blockIdx.x * 256 + threadIdx.x;
-    u64 npairs = 0;
-    if (w < n_items) {
-    u32 lo = 0, hi = n_buckets;            // last b with item_off[b] <= w
-    while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (item_off[mid] <= w) lo = mid; else hi = mid; }
-    u32 b = lo, local = w - item_off[b];
-    u32 s = bstart[b], nb = bstart[b + 1] - s, t = bucket_tiles(nb);
-    // row-major upper triangle: row ti holds (t - ti) items
-    u32 ti = 0;
-    {
-        double tt = 2.0 * t + 1.0;
-        double r = (tt - sqrt(tt * tt - 8.0 * (double)local)) * 0.5;
-        ti = (u32)r; if (ti >= t) ti = t - 1;
-        // first item index of row ti = ti*t - ti*(ti-1)/2
-        while (ti > 0 && (u64)ti * t - (u64)ti * (ti - 1) / 2 > local) ti--;
-        while ((u64)(ti + 1) * t - (u64)(ti + 1) * ti / 2 <= local) ti++;
+// ---- exact tile culling ------------------------------------------------------------------------
+// Unique UMIs of a bucket are sorted, so a tile of 2048 consecutive UMIs shares a long prefix and uses
+// few letters at the next positions.  Per tile we keep, for each letter x, a mask S_x whose bit j says
+// "some UMI of the tile has letter x at position j".  For two tiles the number of positions whose
+// letter sets are disjoint is a lower bound of the Hamming distance of every cross pair; when it
+// exceeds k the tile pair cannot contain a neighbour and is never scheduled.  (Exact: no pair within
+// k is ever dropped; tests compare culled and unculled runs with the oracle.)
+#define TS_WORDS 8      // letter-set words per tile (A C G T N + padding)
+
+struct BucketTiles {
+    const u32 *bstart;
+    __device__ u32 operator()(u64 b) const { u32 nb = bstart[b + 1] - bstart[b]; return nb < 2 ? 0 : bucket_tiles(nb); }
+};
+struct BucketTilesEmit {
+    u32 *tile_off; u64 n_buckets;
+    __device__ void operator()(u64 b, u32 v, u32 ex) const {
+        tile_off[b] = ex;
+        if (b == n_buckets - 1) tile_off[b + 1] = ex + v;
     }
-    u32 tj = ti + (local - (u32)((u64)ti * t - (u64)ti * (ti - 1) / 2));
-    TileItem it;
-    it.row_start = s + ti * HT_ROWS;
-    it.col_start = s + tj * HT_COLS;
-    it.row_cnt = min((u32)HT_ROWS, nb - ti * HT_ROWS);
-    u32 cc = min((u32)HT_COLS, nb - tj * HT_COLS);
-    it.col_cnt_diag = cc | (ti == tj ? 0x80000000u : 0u);
-    items[w] = it;
-    npairs = ti == tj ? (u64)cc * (cc - 1) / 2 : (u64)it.row_cnt * cc;
+};
+
+__device__ __forceinline__ void onehot_planes(uint2 p, u32 pn, u32 lmask, u32 *oh /*5*/) {
+    u32 base = lmask & ~pn;
+    oh[0] = ~p.y & ~p.x & base; oh[1] = ~p.y & p.x & base; oh[2] = p.y & ~p.x & base; oh[3] = p.y & p.x & base; oh[4] = pn & lmask;
+}
+
+// one warp per tile
+__global__ void __launch_bounds__(256) tile_summary_kernel(u32 n_tiles, u32 n_buckets, const u32 *__restrict__ tile_off,
+                                                           const u32 *__restrict__ bstart, const uint2 *__restrict__ planes,
+                                                           const u32 *__restrict__ nplane, int L, u32 *__restrict__ tsum) {
+    u32 t = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (t >= n_tiles) return;
+    u32 lo = 0, hi = n_buckets;
+    while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (tile_off[mid] <= t) lo = mid; else hi = mid; }
+    u32 b = lo, ti = t - tile_off[b], s = bstart[b], nb = bstart[b + 1] - s;
+    u32 first = s + ti * HT_ROWS, cnt = min((u32)HT_ROWS, nb - ti * HT_ROWS);
+    u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
+    u32 acc[5] = {0, 0, 0, 0, 0};
+    for (u32 i = lane_id(); i < cnt; i += 32) {
+        u32 oh[5];
+        onehot_planes(planes[first + i], nplane ? nplane[first + i] : 0u, lmask, oh);
+#pragma unroll
+        for (int x = 0; x < 5; x++) acc[x] |= oh[x];
     }
 #pragma unroll
+    for (int x = 0; x < 5; x++) acc[x] = __reduce_or_sync(0xffffffffu, acc[x]);
+    if (lane_id() < TS_WORDS) {
+        u32 v = 0;
+#pragma unroll
+        for (int x = 0; x < 5; x++) if (lane_id() == (u32)x) v = acc[x];
+        tsum[(u64)t * TS_WORDS + lane_id()] = v;
+    }
+}
+
+__device__ __forceinline__ u32 disjoint_positions(const u32 *a, const u32 *b, u32 lmask) {
+    u32 t = (a[0] & b[0]) | (a[1] & b[1]) | (a[2] & b[2]) | (a[3] & b[3]) | (a[4] & b[4]);
+    return __popc(~t & lmask);
+}
+
+// one thread per candidate tile pair: bucket by binary search over item_off, (ti, tj) by triangular
+// decode; survivors of the cull test are appended (order is irrelevant: the edge SET is what matters)
+__global__ void __launch_bounds__(256) build_items_kernel(u32 n_cand, u32 n_buckets, const u32 *__restrict__ item_off,
+                                                          const u32 *__restrict__ bstart, const u32 *__restrict__ tile_off,
+                                                          const u32 *__restrict__ tsum, int L, int k, int cull,
+                                                          TileItem *__restrict__ items, DevScalars *sc) {
+    u32 w = blockIdx.x * 256 + threadIdx.x;
+    u64 npairs = 0;
+    bool live = false;
+    TileItem it;
+    if (w < n_cand) {
+        u32 lo = 0, hi = n_buckets;            // last b with item_off[b] <= w
+        while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (item_off[mid] <= w) lo = mid; else hi = mid; }
+        u32 b = lo, local = w - item_off[b];
+        u32 s = bstart[b], nb = bstart[b + 1] - s, t = bucket_tiles(nb);
+        // row-major upper triangle: row ti holds (t - ti) items
+        u32 ti = 0;
+        {
+            double tt = 2.0 * t + 1.0;
+            double r = (tt - sqrt(tt * tt - 8.0 * (double)local)) * 0.5;
+            ti = (u32)r; if (ti >= t) ti = t - 1;
+            // first item index of row ti = ti*t - ti*(ti-1)/2
+            while (ti > 0 && (u64)ti * t - (u64)ti * (ti - 1) / 2 > local) ti--;
+            while ((u64)(ti + 1) * t - (u64)(ti + 1) * ti / 2 <= local) ti++;
+        }
+        u32 tj = ti + (local - (u32)((u64)ti * t - (u64)ti * (ti - 1) / 2));
+        it.row_start = s + ti * HT_ROWS;
+        it.col_start = s + tj * HT_COLS;
+        it.row_cnt = min((u32)HT_ROWS, nb - ti * HT_ROWS);
+        u32 cc = min((u32)HT_COLS, nb - tj * HT_COLS);
+        it.col_cnt_diag = cc | (ti == tj ? 0x80000000u : 0u);
+        live = true;
+        if (cull && ti != tj) {
+            u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
+            const u32 *a = tsum + (u64)(tile_off[b] + ti) * TS_WORDS, *c = tsum + (u64)(tile_off[b] + tj) * TS_WORDS;
+            live = disjoint_positions(a, c, lmask) <= (u32)k;
+        }
+        if (live) npairs = (u64)it.row_cnt * cc;
+    }
+    // warp-aggregated append
+    u32 m = __ballot_sync(0xffffffffu, live);
+    u32 base = 0;
+    if (lane_id() == 0 && m) base = atomicAdd(&sc->n_items, (u32)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (live) items[base + __popc(m & lanemask_lt())] = it;
+#pragma unroll
     for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
-    if (lane_id() == 0 && npairs) atomicAdd((unsigned long long *)&sc->pairs_eval, (unsigned long long)npairs);
+    if (lane_id() == 0 && npairs) atomicAdd((unsigned long long *)&sc->scratch2, (unsigned long long)npairs);
 }

@@ -22,12 +22,15 @@
 template <int LP, int K, bool HASN>
 __global__ void __launch_bounds__(BS_THREADS) hamming_tiles_bs(
     const TileItem *__restrict__ items, u32 n_items, const uint2 *__restrict__ planes, const u32 *__restrict__ nplane,
-    int L, EdgeSink es, u32 *work_counter) {
+    int L, int cull, EdgeSink es, u32 *work_counter, unsigned long long *pairs_eval) {
     constexpr int XS = HASN ? 8 : 4;          // letter slots per position
     constexpr int NLET = HASN ? 5 : 4;
     extern __shared__ __align__(16) uint4 eq4[];   // [g4][LP][XS] x (4 groups)
+    __shared__ __align__(16) u32 sset[BS_G4 * 8];  // per 128-column block: letter-set masks (bit j = letter x occurs at position j)
     __shared__ u32 s_item;
     const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+    const u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
+    u64 evaluated = 0;
 
     for (;;) {
         __syncthreads();
@@ -63,11 +66,34 @@ __global__ void __launch_bounds__(BS_THREADS) hamming_tiles_bs(
             }
         }
         __syncthreads();
+        // letter sets of every 128-column block (for the in-kernel cull): lane = position
+        for (u32 task = warp; task < g4_cnt * 8; task += BS_THREADS / 32) {
+            u32 g4 = task >> 3, x = task & 7;
+            bool f = false;
+            if (x < (u32)NLET && lane < (u32)LP) {
+                uint4 v = eq4[((size_t)g4 * LP + lane) * XS + x];
+                f = (v.x | v.y | v.z | v.w) != 0u;
+            }
+            u32 bits = __ballot_sync(0xffffffffu, f);
+            if (lane == 0) sset[g4 * 8 + x] = bits;
+        }
+        __syncthreads();
 
-        // ---- rows ----
-        for (u32 gi = threadIdx.x; gi < it.row_cnt; gi += BS_THREADS) {
-            const uint2 rp = planes[it.row_start + gi];
-            const u32 rn = HASN ? nplane[it.row_start + gi] : 0u;
+        // ---- rows: each thread owns one row UMI per pass; a warp's 32 rows are consecutive sorted UMIs ----
+        for (u32 rbase = 0; rbase < it.row_cnt; rbase += BS_THREADS) {
+            const u32 gi = rbase + threadIdx.x;
+            const bool valid = gi < it.row_cnt;
+            const u32 nvalid = __popc(__ballot_sync(0xffffffffu, valid));
+            if (nvalid == 0) continue;
+            const uint2 rp = valid ? planes[it.row_start + gi] : make_uint2(0u, 0u);
+            const u32 rn = (HASN && valid) ? nplane[it.row_start + gi] : 0u;
+            u32 rs[5] = {0u, 0u, 0u, 0u, 0u};
+            if (cull) {
+                u32 oh[5];
+                onehot_planes(rp, rn, valid ? lmask : 0u, oh);
+#pragma unroll
+                for (int x = 0; x < NLET; x++) rs[x] = __reduce_or_sync(0xffffffffu, oh[x]);
+            }
             u32 off[LP];                                   // byte offset of the row's letter slot at position j
 #pragma unroll
             for (int j = 0; j < LP; j++) {
@@ -75,8 +101,19 @@ __global__ void __launch_bounds__(BS_THREADS) hamming_tiles_bs(
                 if (HASN && ((rn >> j) & 1u)) letter = 4u;
                 off[j] = (u32)(j * XS + letter) * 16u;
             }
+            const u32 row_lo = rbase + warp * 32;          // first row (tile-relative) of this warp
             const char *base = reinterpret_cast<const char *>(eq4);
             for (u32 g4 = 0; g4 < g4_cnt; g4++, base += LP * XS * 16) {
+                if (cull) {
+                    // diagonal tile: only pairs with column > row are wanted
+                    if (diag && g4 * 128 + 127 <= row_lo) continue;
+                    const uint4 s = *reinterpret_cast<const uint4 *>(&sset[g4 * 8]);
+                    u32 t = (rs[0] & s.x) | (rs[1] & s.y) | (rs[2] & s.z) | (rs[3] & s.w);
+                    if (HASN) t |= rs[4] & sset[g4 * 8 + 4];
+                    if (__popc(~t & lmask) > K) continue;   // >K positions with disjoint letter sets: no neighbour in this block
+                }
+                evaluated += (u64)nvalid * min(128u, col_cnt - g4 * 128);
+                if (!valid) continue;
                 uint4 m1 = make_uint4(~0u, ~0u, ~0u, ~0u), m2 = m1, m3 = m1, m4 = m1;
 #pragma unroll
                 for (int j = 0; j < LP; j++) {
@@ -109,47 +146,48 @@ __global__ void __launch_bounds__(BS_THREADS) hamming_tiles_bs(
             }
         }
     }
+    if (lane == 0 && evaluated) atomicAdd(pairs_eval, (unsigned long long)evaluated);
 }
 
 template <int LP, int K, bool HASN>
 static int bs_launch_one(cudaStream_t stream, int num_sms, const TileItem *items, u32 n_items, const uint2 *planes,
-                         const u32 *nplane, int L, EdgeSink es, u32 *counter) {
+                         const u32 *nplane, int L, int cull, EdgeSink es, u32 *counter, unsigned long long *pairs_eval) {
     constexpr int XS = HASN ? 8 : 4;
     size_t smem = (size_t)BS_G4 * LP * XS * 16;
     auto kern = hamming_tiles_bs<LP, K, HASN>;
-    if (smem + 256 > 48 * 1024) {      // + the kernel's static shared memory
+    if (smem + 1024 > 48 * 1024) {      // + the kernel's static shared memory
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     }
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BS_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
     u32 grid = (u32)std::min<u64>((u64)n_items, (u64)num_sms * occ);
     if (cudaMemsetAsync(counter, 0, sizeof(u32), stream) != cudaSuccess) return -1;
-    kern<<<grid, BS_THREADS, smem, stream>>>(items, n_items, planes, nplane, L, es, counter);
+    kern<<<grid, BS_THREADS, smem, stream>>>(items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 
 template <int K, bool HASN>
 static int bs_launch_k(cudaStream_t stream, int num_sms, const TileItem *items, u32 n_items, const uint2 *planes,
-                       const u32 *nplane, int L, EdgeSink es, u32 *counter) {
-    if (L <= 8)  return bs_launch_one<8, K, HASN>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
-    if (L <= 12) return bs_launch_one<12, K, HASN>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
-    if (L <= 16) return bs_launch_one<16, K, HASN>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
-    if (L <= 24) return bs_launch_one<24, K, HASN>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
+                       const u32 *nplane, int L, int cull, EdgeSink es, u32 *counter, unsigned long long *pairs_eval) {
+    if (L <= 8)  return bs_launch_one<8, K, HASN>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
+    if (L <= 12) return bs_launch_one<12, K, HASN>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
+    if (L <= 16) return bs_launch_one<16, K, HASN>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
+    if (L <= 24) return bs_launch_one<24, K, HASN>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
     if (HASN) return 1;   // N-containing batches are limited to 21 nt upstream of here
-    return bs_launch_one<32, K, false>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
+    return bs_launch_one<32, K, false>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
 }
 
 // returns 0 = launched, 1 = configuration not covered (caller uses the direct kernel), -1 = CUDA error
 static int launch_neighbours_bitsliced(cudaStream_t stream, int num_sms, const TileItem *items, u32 n_items,
-                                       const uint2 *planes, const u32 *nplane, int L, int k, bool has_n, EdgeSink es,
-                                       u32 *counter) {
+                                       const uint2 *planes, const u32 *nplane, int L, int k, bool has_n, int cull, EdgeSink es,
+                                       u32 *counter, unsigned long long *pairs_eval) {
     if (k < 1 || k > 3) return 1;
     if (!has_n) {
-        if (k == 1) return bs_launch_k<1, false>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
-        if (k == 2) return bs_launch_k<2, false>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
-        return bs_launch_k<3, false>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
+        if (k == 1) return bs_launch_k<1, false>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
+        if (k == 2) return bs_launch_k<2, false>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
+        return bs_launch_k<3, false>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
     }
-    if (k == 1) return bs_launch_k<1, true>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
-    if (k == 2) return bs_launch_k<2, true>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
-    return bs_launch_k<3, true>(stream, num_sms, items, n_items, planes, nplane, L, es, counter);
+    if (k == 1) return bs_launch_k<1, true>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
+    if (k == 2) return bs_launch_k<2, true>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
+    return bs_launch_k<3, true>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
 }

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) int_peak_lop3_kernel(u32 iters, u32 seed,
 #pragma unroll
         for (int u = 0; u < 8; u++) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) a[j] = (a[j] ^ x) | (a[j] & 0x0f0f0f0fu);   // one LOP3 each, two register operands (no bank conflict)
+            for (int j = 0; j < 8; j++) asm volatile("lop3.b32 %0, %0, 0x7f3f1f0f, %1, 0x6a;" : "+r"(a[j]) : "r"(x));   // ONE LOP3 each: (a & imm) ^ x
         }
         x += 0x01000193u;
     }

@@ -18,7 +18,9 @@ struct DevScalars {
     u32 max_umis, changed;
     u32 n_kept, n_items;
     u64 pairs, pairs_eval, edge_count;
-    u64 scratch;
+    u64 scratch;      // work counter of the neighbour kernel
+    u64 scratch2;     // pairs in scheduled tile items (direct kernel accounting)
+    u32 n_cand, n_tiles;
 };
 
 struct KeyLayout {
@@ -32,22 +34,39 @@ struct KeyLayout {
 __global__ void __launch_bounds__(PACK_THREADS) umi_pack_kernel(
     const u8 *__restrict__ ascii, u64 n, int L, const i32 *__restrict__ tid, const i64 *__restrict__ pos,
     u64 *__restrict__ umi2, u32 *__restrict__ nmask, DevScalars *sc) {
-    u64 i = (u64)blockIdx.x * PACK_THREADS + threadIdx.x;
+    __shared__ __align__(16) u8 sbuf[PACK_THREADS * 32];
+    __shared__ i32 s_tmin[PACK_THREADS / 32], s_tmax[PACK_THREADS / 32];
+    __shared__ i64 s_pmin[PACK_THREADS / 32], s_pmax[PACK_THREADS / 32];
+    __shared__ u32 s_flags[PACK_THREADS / 32];
+    const u64 base = (u64)blockIdx.x * PACK_THREADS;
+    const u32 cnt = (u32)min((u64)PACK_THREADS, n - base);
+    const u32 bytes = cnt * (u32)L;
+    const u8 *src = ascii + base * (u64)L;
+    // stage the block's contiguous ASCII span with coalesced (vector) loads
+    if ((((unsigned long long)src) & 15ull) == 0) {
+        const u32 nv = bytes >> 4;
+        for (u32 v = threadIdx.x; v < nv; v += PACK_THREADS) reinterpret_cast<uint4 *>(sbuf)[v] = reinterpret_cast<const uint4 *>(src)[v];
+        for (u32 b = (nv << 4) + threadIdx.x; b < bytes; b += PACK_THREADS) sbuf[b] = src[b];
+    } else {
+        for (u32 b = threadIdx.x; b < bytes; b += PACK_THREADS) sbuf[b] = src[b];
+    }
+    __syncthreads();
+    const u64 i = base + threadIdx.x;
     i32 tmin = 0x7fffffff, tmax = (i32)0x80000000;
     i64 pmin = 0x7fffffffffffffffLL, pmax = (i64)0x8000000000000000LL;
-    u32 anyn = 0, bad = 0;
-    if (i < n) {
-        const u8 *s = ascii + i * (u64)L;
+    u32 flags = 0;     // bit 0 = any N, bit 1 = bad base
+    if (threadIdx.x < cnt) {
+        const u8 *s = sbuf + threadIdx.x * (u32)L;
         u64 code = 0; u32 nm = 0;
         for (int b = 0; b < L; b++) {
             u32 c = s[b], v;
             // utils/read.rs:22-31 alphabet; anything else panics in the reference (utils/mod.rs:78)
             if (c == 'A') v = 0; else if (c == 'C') v = 1; else if (c == 'G') v = 2; else if (c == 'T') v = 3;
             else if (c == 'N') { v = 0; nm |= 1u << (L - 1 - b); }
-            else { v = 0; bad = 1; }
+            else { v = 0; flags |= 2u; }
             code = (code << 2) | v;
         }
-        umi2[i] = code; nmask[i] = nm; anyn = nm != 0;
+        umi2[i] = code; nmask[i] = nm; if (nm) flags |= 1u;
         tmin = tmax = tid[i]; pmin = pmax = pos[i];
     }
 #pragma unroll
@@ -56,14 +75,24 @@ __global__ void __launch_bounds__(PACK_THREADS) umi_pack_kernel(
         tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
         pmin = min(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
         pmax = max(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
-        anyn |= __shfl_xor_sync(0xffffffffu, anyn, o);
-        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        flags |= __shfl_xor_sync(0xffffffffu, flags, o);
     }
-    if (lane_id() == 0) {
-        atomicMin(&sc->tid_min, tmin); atomicMax(&sc->tid_max, tmax);
-        atomicMin((long long *)&sc->pos_min, (long long)pmin); atomicMax((long long *)&sc->pos_max, (long long)pmax);
-        if (anyn) atomicOr(&sc->any_n, 1u);
-        if (bad) atomicOr(&sc->bad_base, 1u);
+    const u32 w = threadIdx.x >> 5;
+    if (lane_id() == 0) { s_tmin[w] = tmin; s_tmax[w] = tmax; s_pmin[w] = pmin; s_pmax[w] = pmax; s_flags[w] = flags; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < PACK_THREADS / 32; k++) {
+            tmin = min(tmin, s_tmin[k]); tmax = max(tmax, s_tmax[k]); pmin = min(pmin, s_pmin[k]); pmax = max(pmax, s_pmax[k]);
+            flags |= s_flags[k];
+        }
+        // one guarded atomic per block and field: the running extrema stop changing quickly
+        volatile DevScalars *vs = sc;
+        if (tmin < vs->tid_min) atomicMin(&sc->tid_min, tmin);
+        if (tmax > vs->tid_max) atomicMax(&sc->tid_max, tmax);
+        if (pmin < vs->pos_min) atomicMin((long long *)&sc->pos_min, (long long)pmin);
+        if (pmax > vs->pos_max) atomicMax((long long *)&sc->pos_max, (long long)pmax);
+        if ((flags & 1u) && !vs->any_n) atomicOr(&sc->any_n, 1u);
+        if ((flags & 2u) && !vs->bad_base) atomicOr(&sc->bad_base, 1u);
     }
 }
 

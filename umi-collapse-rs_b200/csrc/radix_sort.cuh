@@ -17,22 +17,22 @@
 
 struct KeyArr { u64 *w[2]; };   // w[0] = least significant word
 
-// Ranks the tile's keys by digit.  packed[j] = digit | (rank within (warp, digit) << 8).
-// On return whist[w][d] = number of keys with digit d in warp w's slice (before any __syncthreads).
-__device__ __forceinline__ void rs_rank_tile(const u64 *__restrict__ wsel, u64 tile_base, u64 n, int sh,
-                                             u32 mask, u32 (*whist)[256], u32 *packed) {
+// Ranks the tile's keys by digit.  dig[j] = digit of the thread's j-th key (0xffffffff = past the end).
+// packed[j] = digit | (rank within (warp, digit) << 8).  On return whist[w][d] = number of keys with
+// digit d in warp w's slice (before any __syncthreads).  The digits are loaded by the caller in one
+// batch so that all RS_ITEMS global loads are in flight together; this loop only touches shared memory.
+__device__ __forceinline__ void rs_rank_tile(const u32 *dig, u32 (*whist)[256], u32 *packed) {
     const u32 w = threadIdx.x >> 5, lane = lane_id();
     for (u32 i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&whist[0][0])[i] = 0;
     __syncthreads();
     const u32 lt = lanemask_lt();
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; j++) {
-        u64 i = tile_base + (u64)(w * RS_ITEMS + j) * 32 + lane;
-        bool active = i < n;
-        u32 act = __ballot_sync(0xffffffffu, active);
+        const u32 d = dig[j];
+        const bool active = d != 0xffffffffu;
+        const u32 act = __ballot_sync(0xffffffffu, active);
         packed[j] = 0;
         if (active) {
-            u32 d = (u32)(wsel[i] >> sh) & mask;
             u32 peers = __match_any_sync(act, d);
             u32 leader = __ffs(peers) - 1;
             u32 old = 0;
@@ -47,13 +47,20 @@ __device__ __forceinline__ void rs_rank_tile(const u64 *__restrict__ wsel, u64 t
 __global__ void __launch_bounds__(RS_THREADS) radix_hist(const u64 *__restrict__ wsel, u64 n, int sh, u32 mask,
                                                          u32 *__restrict__ hist, u32 nblk) {
     __shared__ u32 whist[RS_WARPS][256];
-    u32 packed[RS_ITEMS];
-    rs_rank_tile(wsel, (u64)blockIdx.x * RS_TILE, n, sh, mask, whist, packed);
+    u32 dig[RS_ITEMS], packed[RS_ITEMS];
+    const u64 tile_base = (u64)blockIdx.x * RS_TILE;
+    const u32 w = threadIdx.x >> 5, lane = lane_id();
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++) {
+        u64 i = tile_base + (u64)(w * RS_ITEMS + j) * 32 + lane;
+        dig[j] = i < n ? ((u32)(wsel[i] >> sh) & mask) : 0xffffffffu;
+    }
+    rs_rank_tile(dig, whist, packed);
     __syncthreads();
     if (threadIdx.x < 256) {
         u32 s = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) s += whist[w][threadIdx.x];
+        for (int ww = 0; ww < RS_WARPS; ww++) s += whist[ww][threadIdx.x];
         hist[(u64)threadIdx.x * nblk + blockIdx.x] = s;
     }
 }
@@ -64,27 +71,42 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter(KeyArr in, const u32
                                                             const u32 *__restrict__ hist_scanned, u32 nblk, int iota) {
     __shared__ u32 whist[RS_WARPS][256];
     __shared__ u32 sbase[256];
-    u32 packed[RS_ITEMS];
+    u32 dig[RS_ITEMS], packed[RS_ITEMS], vidx[RS_ITEMS];
+    u64 key[NW][RS_ITEMS];
     const u64 tile_base = (u64)blockIdx.x * RS_TILE;
-    rs_rank_tile(in.w[wsel], tile_base, n, sh, mask, whist, packed);
+    const u32 w = threadIdx.x >> 5, lane = lane_id();
+    // batch every global load of the tile up front (RS_ITEMS * (NW + 1) independent loads per thread)
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++) {
+        u64 i = tile_base + (u64)(w * RS_ITEMS + j) * 32 + lane;
+        bool a = i < n;
+#pragma unroll
+        for (int k = 0; k < NW; k++) key[k][j] = a ? in.w[k][i] : 0;
+        vidx[j] = a ? (iota ? (u32)i : idx_in[i]) : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++) {
+        u64 i = tile_base + (u64)(w * RS_ITEMS + j) * 32 + lane;
+        u64 kw = NW == 1 ? key[0][j] : (wsel == 0 ? key[0][j] : key[NW - 1][j]);
+        dig[j] = i < n ? ((u32)(kw >> sh) & mask) : 0xffffffffu;
+    }
+    rs_rank_tile(dig, whist, packed);
     __syncthreads();
     if (threadIdx.x < 256) {
         u32 run = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) { u32 t = whist[w][threadIdx.x]; whist[w][threadIdx.x] = run; run += t; }
+        for (int ww = 0; ww < RS_WARPS; ww++) { u32 t = whist[ww][threadIdx.x]; whist[ww][threadIdx.x] = run; run += t; }
         sbase[threadIdx.x] = hist_scanned[(u64)threadIdx.x * nblk + blockIdx.x];
     }
     __syncthreads();
-    const u32 w = threadIdx.x >> 5, lane = lane_id();
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; j++) {
-        u64 i = tile_base + (u64)(w * RS_ITEMS + j) * 32 + lane;
-        if (i < n) {
+        if (dig[j] != 0xffffffffu) {
             u32 d = packed[j] & 0xff, r = packed[j] >> 8;
             u64 pos = (u64)sbase[d] + whist[w][d] + r;
 #pragma unroll
-            for (int k = 0; k < NW; k++) out.w[k][pos] = in.w[k][i];
-            idx_out[pos] = iota ? (u32)i : idx_in[i];
+            for (int k = 0; k < NW; k++) out.w[k][pos] = key[k][j];
+            idx_out[pos] = vidx[j];
         }
     }
 }

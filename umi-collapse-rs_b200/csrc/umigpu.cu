@@ -39,12 +39,13 @@ struct umigpu_ctx {
 
     DevBuf d_key[2][2], d_idx[2], d_hist, d_tiles;
     DevBuf d_useg, d_rep, d_planes, d_nplane, d_bhead, d_wsum, d_read_uid, d_freq, d_thr, d_repidx, d_label, d_prio;
-    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_onehot;
+    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_onehot, d_tileoff, d_tsum;
 
     // results
     bool ran = false;
     umigpu_counters ctr;
     u32 n_unique = 0, n_buckets = 0;
+    bool used_direct = false;
     u64 n_edges = 0;
     KeyLayout lay;
     u32 *h_kept32 = nullptr; size_t h_kept32_cap = 0;   // pinned
@@ -129,7 +130,7 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
                       &ctx->d_hist, &ctx->d_tiles, &ctx->d_useg, &ctx->d_rep, &ctx->d_planes, &ctx->d_nplane, &ctx->d_bhead, &ctx->d_wsum,
                       &ctx->d_read_uid, &ctx->d_freq, &ctx->d_thr, &ctx->d_repidx, &ctx->d_label, &ctx->d_prio, &ctx->d_bstart, &ctx->d_itemoff,
                       &ctx->d_items, &ctx->d_edges, &ctx->d_keep, &ctx->d_state, &ctx->d_blocked, &ctx->d_bitmap, &ctx->d_kept, &ctx->d_roots,
-                      &ctx->d_onehot};
+                      &ctx->d_onehot, &ctx->d_tileoff, &ctx->d_tsum};
     for (DevBuf *b : bufs) b->release();
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
     if (ctx->h_kept32) cudaFreeHost(ctx->h_kept32);
@@ -378,18 +379,35 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     LAUNCH(bucket_stats_kernel, grid_for(B, 256), 256, B, (const u32 *)ctx->d_bstart.p, sc);
 
     const bool need_edges = (mode == RUN_EDGES_ONLY || cfg.algo != UMIGPU_ALGO_ADJ) && cfg.k > 0 && U > B;
+    const int cull = (cfg.flags & UMIGPU_FLAG_NO_CULL) ? 0 : 1;
     u32 W = 0;
     u64 n_edges = 0;
     if (need_edges) {
         CK(ctx->d_itemoff.reserve(((size_t)B + 1) * 4));
-        rc = run_scan(ctx, BucketItems{ctx->d_bstart.as<u32>()}, BucketItemsEmit{ctx->d_itemoff.as<u32>(), B}, B, &sc->n_items);
+        CK(ctx->d_tileoff.reserve(((size_t)B + 1) * 4));
+        rc = run_scan(ctx, BucketItems{ctx->d_bstart.as<u32>()}, BucketItemsEmit{ctx->d_itemoff.as<u32>(), B}, B, &sc->n_cand);
+        if (rc) return rc;
+        rc = run_scan(ctx, BucketTiles{ctx->d_bstart.as<u32>()}, BucketTilesEmit{ctx->d_tileoff.as<u32>(), B}, B, &sc->n_tiles);
         if (rc) return rc;
         rc = read_scalars(ctx);
         if (rc) return rc;
+        const u32 n_cand = ctx->h_sc->n_cand, n_tiles = ctx->h_sc->n_tiles;
+        CK(ctx->d_tsum.reserve((size_t)std::max<u32>(n_tiles, 1) * TS_WORDS * 4));
+        if (cull && n_tiles)
+            LAUNCH(tile_summary_kernel, grid_for((u64)n_tiles * 32, 256), 256, n_tiles, B, (const u32 *)ctx->d_tileoff.p, (const u32 *)ctx->d_bstart.p,
+                   (const uint2 *)ctx->d_planes.p, has_n ? (const u32 *)ctx->d_nplane.p : (const u32 *)nullptr, lay.umi_len, ctx->d_tsum.as<u32>());
+        // candidates are tested in chunks so that the item buffer only has to hold the survivors of one chunk
+        // plus what is already there; in the worst case (no culling) it holds every candidate
+        CK(ctx->d_items.reserve((size_t)std::max<u32>(n_cand, 1) * sizeof(TileItem)));
+        CK(cudaMemsetAsync(&sc->n_items, 0, 4, ctx->stream));
+        CK(cudaMemsetAsync(&sc->scratch2, 0, 8, ctx->stream));
+        if (n_cand)
+            LAUNCH(build_items_kernel, grid_for(n_cand, 256), 256, n_cand, B, (const u32 *)ctx->d_itemoff.p, (const u32 *)ctx->d_bstart.p,
+                   (const u32 *)ctx->d_tileoff.p, (const u32 *)ctx->d_tsum.p, lay.umi_len, cfg.k, cull, ctx->d_items.as<TileItem>(), sc);
+        rc = read_scalars(ctx);
+        if (rc) return rc;
         W = ctx->h_sc->n_items;
-        CK(ctx->d_items.reserve((size_t)W * sizeof(TileItem)));
-        LAUNCH(build_items_kernel, grid_for(W, 256), 256, W, B, (const u32 *)ctx->d_itemoff.p, (const u32 *)ctx->d_bstart.p,
-               ctx->d_items.as<TileItem>(), sc);
+        ctx->ctr.n_tile_candidates = n_cand;
     }
     STAGE_END(UMIGPU_STAGE_WORKLIST);
 
@@ -401,6 +419,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
         for (int attempt = 0; attempt < 2; attempt++) {
             CK(ctx->d_edges.reserve(cap * sizeof(uint2)));
             CK(cudaMemsetAsync(&sc->edge_count, 0, sizeof(u64), ctx->stream));
+            CK(cudaMemsetAsync(&sc->pairs_eval, 0, sizeof(u64), ctx->stream));
             EdgeSink es{ctx->d_edges.as<uint2>(), (unsigned long long *)&sc->edge_count, cap, ctx->d_freq.as<i32>(), ctx->d_thr.as<i32>()};
             rc = launch_neighbours(ctx, W, es, has_n);
             if (rc) return rc;
@@ -418,7 +437,8 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     STAGE_END(UMIGPU_STAGE_NEIGHBOURS);
     ctx->n_edges = n_edges;
     ctx->ctr.n_buckets = B; ctx->ctr.total_umis = U; ctx->ctr.max_umis = ctx->h_sc->max_umis;
-    ctx->ctr.unordered_pairs = ctx->h_sc->pairs; ctx->ctr.pairs_evaluated = ctx->h_sc->pairs_eval;
+    ctx->ctr.unordered_pairs = ctx->h_sc->pairs;
+    ctx->ctr.pairs_evaluated = ctx->used_direct ? ctx->h_sc->scratch2 : ctx->h_sc->pairs_eval;
     ctx->ctr.n_edges = n_edges; ctx->ctr.n_tile_items = W;
     if (mode == RUN_EDGES_ONLY) { STAGE_END(UMIGPU_STAGE_TOTAL); return UMIGPU_OK; }
 
@@ -491,12 +511,15 @@ static int launch_neighbours(umigpu_ctx *ctx, u32 n_items, EdgeSink es, bool has
     u32 grid = std::min<u32>(n_items, (u32)ctx->num_sms * 4);
     const int k = cfg.k;
     if (!(cfg.flags & UMIGPU_FLAG_KERNEL_DIRECT)) {
-        int rc = launch_neighbours_bitsliced(ctx->stream, ctx->num_sms, items, n_items, planes, nplane, (int)cfg.umi_len, k, has_n, es,
-                                             (u32 *)&ctx->d_sc.as<DevScalars>()->scratch);
+        int rc = launch_neighbours_bitsliced(ctx->stream, ctx->num_sms, items, n_items, planes, nplane, (int)cfg.umi_len, k, has_n,
+                                             (cfg.flags & UMIGPU_FLAG_NO_CULL) ? 0 : 1, es, (u32 *)&ctx->d_sc.as<DevScalars>()->scratch,
+                                             (unsigned long long *)&ctx->d_sc.as<DevScalars>()->pairs_eval);
+        ctx->used_direct = false;
         if (rc == 0) { ctx->launches += 1; CK(cudaGetLastError()); return UMIGPU_OK; }
         if (rc < 0) return fail(ctx, UMIGPU_ERR_CUDA, "bit-sliced neighbour kernel: %s", cudaGetErrorString(cudaGetLastError()));
         // rc > 0: configuration not covered by the bit-sliced kernel (k > 3) -> direct kernel
     }
+    ctx->used_direct = true;
 #define HD(KK, NN) LAUNCH((hamming_tiles_direct<KK, NN>), grid, HT_THREADS, items, n_items, planes, nplane, es, k)
     if (!has_n) { if (k == 1) HD(1, false); else if (k == 2) HD(2, false); else HD(0, false); }
     else        { if (k == 1) HD(1, true);  else if (k == 2) HD(2, true);  else HD(0, true); }
