@@ -88,12 +88,21 @@ __global__ void __launch_bounds__(256) mark_kept_kernel(u32 n_unique, const u8 *
     if (u < n_unique && keep[u]) { u32 r = rep_idx[u]; atomicOr(&bitmap[r >> 5], 1u << (r & 31)); }
 }
 struct BitmapCount { const u32 *bm; __device__ u32 operator()(u64 w) const { return __popc(bm[w]); } };
+// push-order position -> caller's read index (umigpu_push_reads first_read_index), chunk table on the device
+struct ChunkMap {
+    const u64 *start, *first; u32 n;
+    __device__ __forceinline__ u64 operator()(u64 r) const {
+        u32 lo = 0, hi = n;
+        while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (start[mid] <= r) lo = mid; else hi = mid; }
+        return first[lo] + (r - start[lo]);
+    }
+};
 struct BitmapEmit {
-    const u32 *bm; u32 *kept; u64 n_words; DevScalars *sc;
+    const u32 *bm; u64 *kept; u64 n_words; DevScalars *sc; ChunkMap cm;
     __device__ void operator()(u64 w, u32 cnt, u32 ex) const {
         u32 bits = bm[w];
         u32 o = ex;
-        while (bits) { u32 b = __ffs(bits) - 1; bits &= bits - 1; kept[o++] = (u32)(w * 32 + b); }
+        while (bits) { u32 b = __ffs(bits) - 1; bits &= bits - 1; kept[o++] = cm(w * 32 + b); }
         if (w == n_words - 1) sc->n_kept = ex + cnt;
     }
 };
@@ -101,7 +110,7 @@ struct BitmapEmit {
 // per read: read index of the emitted representative of its cluster (ClusterTracker, --tag)
 __global__ void __launch_bounds__(256) read_roots_kernel(u64 n, const u32 *__restrict__ read_uid,
                                                          const unsigned long long *__restrict__ label,
-                                                         const u32 *__restrict__ rep_idx, u32 *__restrict__ out) {
+                                                         const u32 *__restrict__ rep_idx, ChunkMap cm, u64 *__restrict__ out) {
     u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
-    if (i < n) out[i] = rep_idx[(u32)label[read_uid[i]]];
+    if (i < n) out[i] = cm(rep_idx[(u32)label[read_uid[i]]]);
 }

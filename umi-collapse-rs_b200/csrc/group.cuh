@@ -86,6 +86,7 @@ struct BucketEmit {
 
 // Tile geometry of the neighbour search (rows x cols of unique UMIs of one bucket).
 #define HT_ROWS 2048
+#define SMALL_BUCKET 32   // buckets up to this many unique UMIs are handled one per warp
 #define HT_COLS 2048
 
 struct TileItem { u32 row_start, col_start, row_cnt, col_cnt_diag; };   // col_cnt | diag << 31
@@ -97,7 +98,7 @@ struct BucketItems {
     const u32 *bstart;
     __device__ u32 operator()(u64 b) const {
         u32 nb = bstart[b + 1] - bstart[b];
-        if (nb < 2) return 0;
+        if (nb <= SMALL_BUCKET) return 0;          // 0/1 UMIs: nothing to compare; 2..32: small_buckets_kernel
         u32 t = bucket_tiles(nb);
         return t * (t + 1) / 2;
     }
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(256) bucket_stats_kernel(u32 n_buckets, const 
 
 struct BucketTiles {
     const u32 *bstart;
-    __device__ u32 operator()(u64 b) const { u32 nb = bstart[b + 1] - bstart[b]; return nb < 2 ? 0 : bucket_tiles(nb); }
+    __device__ u32 operator()(u64 b) const { u32 nb = bstart[b + 1] - bstart[b]; return nb <= SMALL_BUCKET ? 0 : bucket_tiles(nb); }
 };
 struct BucketTilesEmit {
     u32 *tile_off; u64 n_buckets;

@@ -98,6 +98,37 @@ __global__ void __launch_bounds__(HT_THREADS) hamming_tiles_direct(
     }
 }
 
+// Buckets with 2..32 unique UMIs (the vast majority of alignment positions): one warp per bucket, one UMI
+// per lane, every other UMI of the bucket arrives by shuffle.  No shared memory, no tile item.
+__global__ void __launch_bounds__(256) small_buckets_kernel(u32 n_buckets, const u32 *__restrict__ bstart,
+                                                            const uint2 *__restrict__ planes, const u32 *__restrict__ nplane,
+                                                            int k, EdgeSink es, unsigned long long *pairs_eval) {
+    const u32 b = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = lane_id();
+    u64 np = 0;
+    if (b < n_buckets) {
+        const u32 s = bstart[b], nb = bstart[b + 1] - s;
+        if (nb >= 2 && nb <= SMALL_BUCKET) {
+            const bool v = lane < nb;
+            const uint2 p = v ? planes[s + lane] : make_uint2(0u, 0u);
+            const u32 pn = (v && nplane) ? nplane[s + lane] : 0u;
+            for (u32 j = 1; j < nb; j++) {
+                const u32 q0 = __shfl_sync(0xffffffffu, p.x, j), q1 = __shfl_sync(0xffffffffu, p.y, j);
+                const u32 qn = __shfl_sync(0xffffffffu, pn, j);
+                const u32 m = (p.x ^ q0) | (p.y ^ q1) | (pn ^ qn);
+                if (lane < j && __popc(m) <= k) record_hit(es, s + lane, s + j);
+            }
+            np = (u64)nb * (nb - 1) / 2;
+        }
+    }
+    // one atomic per warp would serialise on a single address: aggregate per CTA through shared memory
+    __shared__ unsigned long long s_np;
+    if (threadIdx.x == 0) s_np = 0;
+    __syncthreads();
+    if (lane == 0 && np) atomicAdd(&s_np, (unsigned long long)np);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_np) atomicAdd(pairs_eval, s_np);
+}
+
 // Naive::remove_near for ONE query (DataStruct-shaped API, naive.rs:26-40):
 // out[i] = dist <= k && (dist == 0 || freq[i] <= max_freq)
 __global__ void __launch_bounds__(256) remove_near_kernel(u32 n, const u64 *__restrict__ umi2, const u32 *__restrict__ nmask,

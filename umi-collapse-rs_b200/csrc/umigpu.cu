@@ -48,9 +48,9 @@ struct umigpu_ctx {
     bool used_direct = false;
     u64 n_edges = 0;
     KeyLayout lay;
-    u32 *h_kept32 = nullptr; size_t h_kept32_cap = 0;   // pinned
-    u32 *h_roots32 = nullptr; size_t h_roots32_cap = 0; // pinned
-    std::vector<u64> h_kept, h_roots;
+    u64 *h_kept = nullptr; size_t h_kept_cap = 0;       // pinned; what umigpu_result.kept_read_index points to
+    u64 *h_roots = nullptr; size_t h_roots_cap = 0;     // pinned
+    DevBuf d_chunks;
 
     cudaEvent_t ev[UMIGPU_N_STAGES][2];
     bool ev_ok[UMIGPU_N_STAGES];
@@ -133,8 +133,9 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
                       &ctx->d_onehot, &ctx->d_tileoff, &ctx->d_tsum};
     for (DevBuf *b : bufs) b->release();
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
-    if (ctx->h_kept32) cudaFreeHost(ctx->h_kept32);
-    if (ctx->h_roots32) cudaFreeHost(ctx->h_roots32);
+    if (ctx->h_kept) cudaFreeHost(ctx->h_kept);
+    if (ctx->h_roots) cudaFreeHost(ctx->h_roots);
+    ctx->d_chunks.release();
     for (int s = 0; s < UMIGPU_N_STAGES; s++) { if (ctx->ev[s][0]) cudaEventDestroy(ctx->ev[s][0]); if (ctx->ev[s][1]) cudaEventDestroy(ctx->ev[s][1]); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -413,7 +414,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
 
     // ---- K5 neighbours ----
     STAGE_BEGIN(UMIGPU_STAGE_NEIGHBOURS);
-    if (need_edges && W > 0) {
+    if (need_edges) {
         u64 cap = std::max<u64>((u64)1 << 20, (u64)U * 8);
         if (ctx->d_edges.cap / sizeof(uint2) > cap) cap = ctx->d_edges.cap / sizeof(uint2);
         for (int attempt = 0; attempt < 2; attempt++) {
@@ -421,8 +422,9 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
             CK(cudaMemsetAsync(&sc->edge_count, 0, sizeof(u64), ctx->stream));
             CK(cudaMemsetAsync(&sc->pairs_eval, 0, sizeof(u64), ctx->stream));
             EdgeSink es{ctx->d_edges.as<uint2>(), (unsigned long long *)&sc->edge_count, cap, ctx->d_freq.as<i32>(), ctx->d_thr.as<i32>()};
-            rc = launch_neighbours(ctx, W, es, has_n);
-            if (rc) return rc;
+            LAUNCH(small_buckets_kernel, grid_for((u64)B * 32, 256), 256, B, (const u32 *)ctx->d_bstart.p, (const uint2 *)ctx->d_planes.p,
+                   has_n ? (const u32 *)ctx->d_nplane.p : (const u32 *)nullptr, cfg.k, es, (unsigned long long *)&sc->pairs_eval);
+            if (W > 0) { rc = launch_neighbours(ctx, W, es, has_n); if (rc) return rc; } else ctx->used_direct = false;
             rc = read_scalars(ctx);
             if (rc) return rc;
             n_edges = ctx->h_sc->edge_count;
@@ -438,7 +440,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     ctx->n_edges = n_edges;
     ctx->ctr.n_buckets = B; ctx->ctr.total_umis = U; ctx->ctr.max_umis = ctx->h_sc->max_umis;
     ctx->ctr.unordered_pairs = ctx->h_sc->pairs;
-    ctx->ctr.pairs_evaluated = ctx->used_direct ? ctx->h_sc->scratch2 : ctx->h_sc->pairs_eval;
+    ctx->ctr.pairs_evaluated = ctx->h_sc->pairs_eval + (ctx->used_direct ? ctx->h_sc->scratch2 : 0);
     ctx->ctr.n_edges = n_edges; ctx->ctr.n_tile_items = W;
     if (mode == RUN_EDGES_ONLY) { STAGE_END(UMIGPU_STAGE_TOTAL); return UMIGPU_OK; }
 
@@ -487,13 +489,23 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     CK(ctx->d_bitmap.reserve(n_words * 4));
     CK(cudaMemsetAsync(ctx->d_bitmap.p, 0, n_words * 4, ctx->stream));
     LAUNCH(mark_kept_kernel, grid_for(U, 256), 256, U, (const u8 *)keep, (const u32 *)ctx->d_repidx.p, ctx->d_bitmap.as<u32>());
-    CK(ctx->d_kept.reserve((size_t)U * 4));
-    rc = run_scan(ctx, BitmapCount{ctx->d_bitmap.as<u32>()}, BitmapEmit{ctx->d_bitmap.as<u32>(), ctx->d_kept.as<u32>(), n_words, sc}, n_words, nullptr);
+    CK(ctx->d_kept.reserve((size_t)U * 8));
+    // chunk table (push-order position -> caller's read index) for the device-side translation
+    const u32 nch = (u32)ctx->chunks.size();
+    {
+        std::vector<u64> tab(2 * (size_t)nch);
+        for (u32 c = 0; c < nch; c++) { tab[c] = ctx->chunks[c].start; tab[nch + c] = ctx->chunks[c].first_index; }
+        CK(ctx->d_chunks.reserve(tab.size() * 8));
+        CK(cudaMemcpyAsync(ctx->d_chunks.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));     // tab is a stack-lifetime pageable buffer
+    }
+    ChunkMap cm{ctx->d_chunks.as<u64>(), ctx->d_chunks.as<u64>() + nch, nch};
+    rc = run_scan(ctx, BitmapCount{ctx->d_bitmap.as<u32>()}, BitmapEmit{ctx->d_bitmap.as<u32>(), ctx->d_kept.as<u64>(), n_words, sc, cm}, n_words, nullptr);
     if (rc) return rc;
     if (want_labels) {
-        CK(ctx->d_roots.reserve(n * 4));
+        CK(ctx->d_roots.reserve(n * 8));
         LAUNCH(read_roots_kernel, grid_for(n, 256), 256, n, (const u32 *)ctx->d_read_uid.p, (const unsigned long long *)label,
-               (const u32 *)ctx->d_repidx.p, ctx->d_roots.as<u32>());
+               (const u32 *)ctx->d_repidx.p, cm, ctx->d_roots.as<u64>());
     }
     STAGE_END(UMIGPU_STAGE_EMIT);
     STAGE_END(UMIGPU_STAGE_TOTAL);
@@ -532,43 +544,27 @@ extern "C" int umigpu_run(umigpu_ctx *ctx) {
     return run_internal(ctx, RUN_FULL, (ctx->cfg.flags & UMIGPU_FLAG_LABELS) != 0, false);
 }
 
-static int translate_indices(const umigpu_ctx *ctx, const u32 *in, u64 n, std::vector<u64> &out, bool ascending) {
-    out.resize(n);
-    const std::vector<Chunk> &ch = ctx->chunks;
-    if (ch.size() == 1) { const u64 off = ch[0].first_index; for (u64 i = 0; i < n; i++) out[i] = off + in[i]; return 0; }
-    size_t c = 0;
-    for (u64 i = 0; i < n; i++) {
-        u64 r = in[i];
-        if (ascending) { while (c + 1 < ch.size() && r >= ch[c].start + ch[c].n) c++; }
-        else { c = std::upper_bound(ch.begin(), ch.end(), r, [](u64 v, const Chunk &k) { return v < k.start; }) - ch.begin() - 1; }
-        out[i] = ch[c].first_index + (r - ch[c].start);
-    }
-    return 0;
-}
-
 static int fetch_internal(umigpu_ctx *ctx, bool want_labels) {
     CK(cudaSetDevice(ctx->cfg.device));
     if (!ctx->ran) return fail(ctx, UMIGPU_ERR_STATE, "fetch before run");
     const u64 nk = ctx->ctr.n_kept, n = ctx->n_reads;
-    if (nk > ctx->h_kept32_cap) {
-        if (ctx->h_kept32) cudaFreeHost(ctx->h_kept32);
-        ctx->h_kept32 = nullptr; ctx->h_kept32_cap = 0;
-        CK(cudaMallocHost((void **)&ctx->h_kept32, (nk + nk / 4 + 16) * 4));
-        ctx->h_kept32_cap = nk + nk / 4 + 16;
+    if (nk > ctx->h_kept_cap) {
+        if (ctx->h_kept) cudaFreeHost(ctx->h_kept);
+        ctx->h_kept = nullptr; ctx->h_kept_cap = 0;
+        CK(cudaMallocHost((void **)&ctx->h_kept, (nk + nk / 4 + 16) * 8));
+        ctx->h_kept_cap = nk + nk / 4 + 16;
     }
-    if (nk) CK(cudaMemcpyAsync(ctx->h_kept32, ctx->d_kept.p, nk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nk) CK(cudaMemcpyAsync(ctx->h_kept, ctx->d_kept.p, nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (want_labels && n) {
-        if (n > ctx->h_roots32_cap) {
-            if (ctx->h_roots32) cudaFreeHost(ctx->h_roots32);
-            ctx->h_roots32 = nullptr; ctx->h_roots32_cap = 0;
-            CK(cudaMallocHost((void **)&ctx->h_roots32, (n + 16) * 4));
-            ctx->h_roots32_cap = n + 16;
+        if (n > ctx->h_roots_cap) {
+            if (ctx->h_roots) cudaFreeHost(ctx->h_roots);
+            ctx->h_roots = nullptr; ctx->h_roots_cap = 0;
+            CK(cudaMallocHost((void **)&ctx->h_roots, (n + 16) * 8));
+            ctx->h_roots_cap = n + 16;
         }
-        CK(cudaMemcpyAsync(ctx->h_roots32, ctx->d_roots.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_roots, ctx->d_roots.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    translate_indices(ctx, ctx->h_kept32, nk, ctx->h_kept, true);
-    if (want_labels) translate_indices(ctx, ctx->h_roots32, n, ctx->h_roots, false); else ctx->h_roots.clear();
     return UMIGPU_OK;
 }
 
@@ -578,9 +574,9 @@ extern "C" int umigpu_fetch(umigpu_ctx *ctx, umigpu_result *out) {
     int rc = fetch_internal(ctx, want_labels);
     if (rc) return rc;
     out->n_kept = ctx->ctr.n_kept;
-    out->kept_read_index = ctx->h_kept.data();
+    out->kept_read_index = ctx->h_kept;
     out->n_reads = ctx->n_reads;
-    out->read_cluster_root = want_labels ? ctx->h_roots.data() : nullptr;
+    out->read_cluster_root = want_labels ? ctx->h_roots : nullptr;
     out->counters = ctx->ctr;
     return UMIGPU_OK;
 }
@@ -600,8 +596,9 @@ extern "C" int umigpu_get_counters(umigpu_ctx *ctx, umigpu_counters *out) {
 
 extern "C" void umigpu_result_free(umigpu_ctx *ctx) {
     if (!ctx) return;
-    std::vector<u64>().swap(ctx->h_kept);
-    std::vector<u64>().swap(ctx->h_roots);
+    if (ctx->h_kept) cudaFreeHost(ctx->h_kept);
+    if (ctx->h_roots) cudaFreeHost(ctx->h_roots);
+    ctx->h_kept = ctx->h_roots = nullptr; ctx->h_kept_cap = ctx->h_roots_cap = 0;
 }
 
 extern "C" int umigpu_stage_ms(umigpu_ctx *ctx, int stage, float *ms) {

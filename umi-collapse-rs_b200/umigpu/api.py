@@ -125,19 +125,24 @@ class Context:
     def run(self):
         L.check(self._lib.umigpu_run(self._h), self._h)
 
-    def fetch(self):
+    def fetch(self, copy: bool = True):
+        """copy=False returns views of the library-owned (pinned) result buffers: valid until the next
+        reset / run / close of this context."""
         res = L.Result()
         L.check(self._lib.umigpu_fetch(self._h, C.byref(res)), self._h)
         self._keepalive.clear()
-        kept = np.ctypeslib.as_array(res.kept_read_index, shape=(res.n_kept,)).copy() if res.n_kept else np.zeros(0, np.uint64)
+        kept = np.ctypeslib.as_array(res.kept_read_index, shape=(res.n_kept,)) if res.n_kept else np.zeros(0, np.uint64)
         roots = None
         if res.read_cluster_root:
-            roots = np.ctypeslib.as_array(res.read_cluster_root, shape=(res.n_reads,)).copy()
+            roots = np.ctypeslib.as_array(res.read_cluster_root, shape=(res.n_reads,))
+        if copy:
+            kept = kept.copy()
+            roots = None if roots is None else roots.copy()
         return kept, roots, res.counters.as_dict()
 
-    def finish(self):
+    def finish(self, copy: bool = True):
         self.run()
-        return self.fetch()
+        return self.fetch(copy)
 
     def counters(self) -> dict:
         c = L.Counters()
