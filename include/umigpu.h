@@ -133,7 +133,9 @@ int  umigpu_reset(umigpu_ctx *ctx);
  *                  (used by umigpu_cluster_bucket to present pre-counted UMIs)
  *   first_read_index  index the caller gives to the first read of this chunk; kept indices are
  *                  reported in this numbering (chunks must be pushed in ascending index order)
- * The copy to the device and the UMI packing kernel are asynchronous on the context's stream.
+ * The copy to the device and the UMI packing kernel are asynchronous on the context's stream:
+ * PAGEABLE host buffers may be reused as soon as the call returns (CUDA stages them), PINNED host buffers
+ * must stay unmodified until the next umigpu_run / umigpu_fetch / umigpu_reset returns.
  */
 int umigpu_push_reads(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, const int64_t *unclipped_pos,
                       const uint8_t *is_reverse, const uint8_t *umi_ascii, const int32_t *score,
