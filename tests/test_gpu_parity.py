@@ -310,3 +310,16 @@ def test_properties_at_scale():
         same = np.nonzero((key == key[r]) & (h["umi"] == h["umi"][r]).all(1))[0]
         best = same[h["score"][same] == h["score"][same].max()].min()
         assert best == r
+
+
+def test_sharded_matches_unsharded():
+    """whole buckets per device, no collective; two contexts (two devices when the box has them)."""
+    import torch
+    from umigpu import shard
+    d, cfg = small("C2", 0.004)
+    devs = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
+    args = umigpu.Cli(k=1, algo_str="dir", merge_str="avgqual")
+    merged, ctrs, cost = shard.dedup_sharded_inprocess(args, d, devs)
+    okept, _, octr = O.dedup(d["tid"], d["pos"], d["rev"], d["umi"], d["score"], O.ALGO_DIR, O.MERGE_AVGQUAL, 1, 0.5)
+    assert merged.tolist() == okept.tolist()
+    assert sum(c["n_buckets"] for c in ctrs) == octr["n_buckets"] and sum(c["total_reads"] for c in ctrs) == len(d["tid"])
