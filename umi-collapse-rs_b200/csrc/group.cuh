@@ -89,7 +89,11 @@ struct BucketEmit {
 #define SMALL_BUCKET 32   // buckets up to this many unique UMIs are handled one per warp
 #define HT_COLS 2048
 
-struct TileItem { u32 row_start, col_start, row_cnt, col_cnt_diag; };   // col_cnt | diag << 31
+// cnts = row_cnt | col_cnt << 12 | diag << 31 (counts <= 2048); col_tile = global id of the column tile
+struct TileItem { u32 row_start, col_start, cnts, col_tile; };
+__device__ __forceinline__ u32 item_row_cnt(const TileItem &it) { return it.cnts & 0xfffu; }
+__device__ __forceinline__ u32 item_col_cnt(const TileItem &it) { return (it.cnts >> 12) & 0xfffu; }
+__device__ __forceinline__ bool item_diag(const TileItem &it) { return it.cnts >> 31; }
 
 __device__ __forceinline__ u32 bucket_tiles(u32 nb) { return (nb + HT_ROWS - 1) / HT_ROWS; }
 
@@ -153,10 +157,12 @@ __device__ __forceinline__ void onehot_planes(uint2 p, u32 pn, u32 lmask, u32 *o
     oh[0] = ~p.y & ~p.x & base; oh[1] = ~p.y & p.x & base; oh[2] = p.y & ~p.x & base; oh[3] = p.y & p.x & base; oh[4] = pn & lmask;
 }
 
-// one warp per tile
+// one warp per tile: letter sets of each 128-UMI block of the tile (bsum) and of the whole tile (tsum)
+#define BLOCKS_PER_TILE (HT_COLS / 128)
 __global__ void __launch_bounds__(256) tile_summary_kernel(u32 n_tiles, u32 n_buckets, const u32 *__restrict__ tile_off,
                                                            const u32 *__restrict__ bstart, const uint2 *__restrict__ planes,
-                                                           const u32 *__restrict__ nplane, int L, u32 *__restrict__ tsum) {
+                                                           const u32 *__restrict__ nplane, int L, u32 *__restrict__ tsum,
+                                                           u32 *__restrict__ bsum) {
     u32 t = (blockIdx.x * 256 + threadIdx.x) >> 5;
     if (t >= n_tiles) return;
     u32 lo = 0, hi = n_buckets;
@@ -164,19 +170,28 @@ __global__ void __launch_bounds__(256) tile_summary_kernel(u32 n_tiles, u32 n_bu
     u32 b = lo, ti = t - tile_off[b], s = bstart[b], nb = bstart[b + 1] - s;
     u32 first = s + ti * HT_ROWS, cnt = min((u32)HT_ROWS, nb - ti * HT_ROWS);
     u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
-    u32 acc[5] = {0, 0, 0, 0, 0};
-    for (u32 i = lane_id(); i < cnt; i += 32) {
-        u32 oh[5];
-        onehot_planes(planes[first + i], nplane ? nplane[first + i] : 0u, lmask, oh);
+    u32 tot[5] = {0, 0, 0, 0, 0};
+    for (u32 blk = 0; blk < BLOCKS_PER_TILE; blk++) {
+        u32 acc[5] = {0, 0, 0, 0, 0};
+        for (u32 i = blk * 128 + lane_id(); i < min(cnt, (blk + 1) * 128); i += 32) {
+            u32 oh[5];
+            onehot_planes(planes[first + i], nplane ? nplane[first + i] : 0u, lmask, oh);
 #pragma unroll
-        for (int x = 0; x < 5; x++) acc[x] |= oh[x];
+            for (int x = 0; x < 5; x++) acc[x] |= oh[x];
+        }
+#pragma unroll
+        for (int x = 0; x < 5; x++) { acc[x] = __reduce_or_sync(0xffffffffu, acc[x]); tot[x] |= acc[x]; }
+        if (lane_id() < TS_WORDS) {
+            u32 v = 0;
+#pragma unroll
+            for (int x = 0; x < 5; x++) if (lane_id() == (u32)x) v = acc[x];
+            bsum[((u64)t * BLOCKS_PER_TILE + blk) * TS_WORDS + lane_id()] = v;
+        }
     }
-#pragma unroll
-    for (int x = 0; x < 5; x++) acc[x] = __reduce_or_sync(0xffffffffu, acc[x]);
     if (lane_id() < TS_WORDS) {
         u32 v = 0;
 #pragma unroll
-        for (int x = 0; x < 5; x++) if (lane_id() == (u32)x) v = acc[x];
+        for (int x = 0; x < 5; x++) if (lane_id() == (u32)x) v = tot[x];
         tsum[(u64)t * TS_WORDS + lane_id()] = v;
     }
 }
@@ -214,16 +229,17 @@ __global__ void __launch_bounds__(256) build_items_kernel(u32 n_cand, u32 n_buck
         u32 tj = ti + (local - (u32)((u64)ti * t - (u64)ti * (ti - 1) / 2));
         it.row_start = s + ti * HT_ROWS;
         it.col_start = s + tj * HT_COLS;
-        it.row_cnt = min((u32)HT_ROWS, nb - ti * HT_ROWS);
+        u32 rc = min((u32)HT_ROWS, nb - ti * HT_ROWS);
         u32 cc = min((u32)HT_COLS, nb - tj * HT_COLS);
-        it.col_cnt_diag = cc | (ti == tj ? 0x80000000u : 0u);
+        it.cnts = rc | (cc << 12) | (ti == tj ? 0x80000000u : 0u);
+        it.col_tile = tile_off[b] + tj;
         live = true;
         if (cull && ti != tj) {
             u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
             const u32 *a = tsum + (u64)(tile_off[b] + ti) * TS_WORDS, *c = tsum + (u64)(tile_off[b] + tj) * TS_WORDS;
             live = disjoint_positions(a, c, lmask) <= (u32)k;
         }
-        if (live) npairs = (u64)it.row_cnt * cc;
+        if (live) npairs = (u64)rc * cc;
     }
     // warp-aggregated append
     u32 m = __ballot_sync(0xffffffffu, live);

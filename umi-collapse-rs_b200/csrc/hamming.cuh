@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(HT_THREADS) hamming_tiles_direct(
     __shared__ u32 sncol[HASN ? HT_COLS : 1];
     for (u32 w = blockIdx.x; w < n_items; w += gridDim.x) {
         TileItem it = items[w];
-        const u32 col_cnt = it.col_cnt_diag & 0x7fffffffu;
-        const bool diag = it.col_cnt_diag >> 31;
+        const u32 col_cnt = item_col_cnt(it), row_cnt = item_row_cnt(it);
+        const bool diag = item_diag(it);
         const u32 cols_pad = (col_cnt + 3) & ~3u;
         __syncthreads();
         for (u32 c = threadIdx.x; c < cols_pad; c += HT_THREADS) {
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(HT_THREADS) hamming_tiles_direct(
 #pragma unroll
         for (int r = 0; r < HT_RPT; r++) {
             u32 gi = threadIdx.x + r * HT_THREADS;
-            bool v = gi < it.row_cnt;
+            bool v = gi < row_cnt;
             uint2 p = v ? planes[it.row_start + gi] : make_uint2(0xffffffffu, 0u);
             r0[r] = p.x; r1[r] = p.y;
             rn[r] = (HASN && v) ? nplane[it.row_start + gi] : 0u;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(HT_THREADS) hamming_tiles_direct(
                 bool h1 = K > 0 ? within_k<K>(m1) : (__popc(m1) <= kdyn);
                 if (h0 | h1) {
                     u32 gi = threadIdx.x + r * HT_THREADS;
-                    if (gi < it.row_cnt) {
+                    if (gi < row_cnt) {
                         u32 a = it.row_start + gi;
                         if (h0 && c < col_cnt) { u32 b = it.col_start + c; if (!diag || a < b) record_hit(es, a, b); }
                         if (h1 && c + 1 < col_cnt) { u32 b = it.col_start + c + 1; if (!diag || a < b) record_hit(es, a, b); }

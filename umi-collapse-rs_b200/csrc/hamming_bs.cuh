@@ -22,29 +22,72 @@
 template <int LP, int K, bool HASN>
 __global__ void __launch_bounds__(BS_THREADS) hamming_tiles_bs(
     const TileItem *__restrict__ items, u32 n_items, const uint2 *__restrict__ planes, const u32 *__restrict__ nplane,
-    int L, int cull, EdgeSink es, u32 *work_counter, unsigned long long *pairs_eval) {
+    const u32 *__restrict__ bsum, int L, int cull, EdgeSink es, u32 *work_counter, unsigned long long *pairs_eval) {
     constexpr int XS = HASN ? 8 : 4;          // letter slots per position
     constexpr int NLET = HASN ? 5 : 4;
+    constexpr int PASSES = HT_ROWS / BS_THREADS;
     extern __shared__ __align__(16) uint4 eq4[];   // [g4][LP][XS] x (4 groups)
     __shared__ __align__(16) u32 sset[BS_G4 * 8];  // per 128-column block: letter-set masks (bit j = letter x occurs at position j)
-    __shared__ u32 s_item;
+    __shared__ u32 s_item, s_need;
     const u32 lane = lane_id(), warp = threadIdx.x >> 5;
     const u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
     u64 evaluated = 0;
 
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1u);
+        if (threadIdx.x == 0) { s_item = atomicAdd(work_counter, 1u); s_need = 0; }
         __syncthreads();
         const u32 w_item = s_item;
         if (w_item >= n_items) break;
         const TileItem it = items[w_item];
-        const u32 col_cnt = it.col_cnt_diag & 0x7fffffffu;
-        const bool diag = it.col_cnt_diag >> 31;
+        const u32 col_cnt = item_col_cnt(it), row_cnt = item_row_cnt(it);
+        const bool diag = item_diag(it);
         const u32 g4_cnt = (col_cnt + 127) >> 7;
+        const u32 all_g4 = (g4_cnt >= 32 ? 0xffffffffu : ((1u << g4_cnt) - 1));
 
-        // ---- build the one-hot match words of this column tile ----
+        // ---- phase 0: letter sets of the column tile's 128-column blocks (precomputed per tile) ----
+        if (cull) {
+            if (threadIdx.x < g4_cnt * 8) sset[threadIdx.x] = bsum[(u64)it.col_tile * (BS_G4 * 8) + threadIdx.x];
+            __syncthreads();
+        }
+        // ---- phase 1: which (32-row warp slice) x (128-column block) pairs can contain a neighbour at all ----
+        // A warp's 32 rows are consecutive sorted UMIs, so their letter sets are small; a block pair with more
+        // than K positions of disjoint letter sets cannot contain a pair within K.
+        u32 mask[PASSES];
+        u32 need = 0;
+#pragma unroll
+        for (int ps = 0; ps < PASSES; ps++) {
+            mask[ps] = 0;
+            const u32 rbase = ps * BS_THREADS;
+            if (rbase + warp * 32 >= row_cnt) continue;        // warp-uniform
+            if (!cull) { mask[ps] = all_g4; need |= all_g4; continue; }
+            const u32 gi = rbase + threadIdx.x;
+            const bool valid = gi < row_cnt;
+            const uint2 rp = valid ? planes[it.row_start + gi] : make_uint2(0u, 0u);
+            const u32 rn = (HASN && valid) ? nplane[it.row_start + gi] : 0u;
+            u32 oh[5], rs[5] = {0u, 0u, 0u, 0u, 0u};
+            onehot_planes(rp, rn, valid ? lmask : 0u, oh);
+#pragma unroll
+            for (int x = 0; x < NLET; x++) rs[x] = __reduce_or_sync(0xffffffffu, oh[x]);
+            const u32 row_lo = rbase + warp * 32;
+            u32 mk = 0;
+            for (u32 g4 = 0; g4 < g4_cnt; g4++) {
+                if (diag && g4 * 128 + 127 <= row_lo) continue;   // diagonal tile: only column > row is wanted
+                const uint4 s = *reinterpret_cast<const uint4 *>(&sset[g4 * 8]);
+                u32 t = (rs[0] & s.x) | (rs[1] & s.y) | (rs[2] & s.z) | (rs[3] & s.w);
+                if (HASN) t |= rs[4] & sset[g4 * 8 + 4];
+                if (__popc(~t & lmask) <= K) mk |= 1u << g4;
+            }
+            mask[ps] = mk; need |= mk;
+        }
+        if (lane == 0 && need) atomicOr(&s_need, need);
+        __syncthreads();
+        const u32 needed = s_need;
+        if (needed == 0) continue;                              // nothing in this tile pair survives the exact cull
+
+        // ---- phase 2: one-hot match words of the needed column blocks ----
         for (u32 g = warp; g < g4_cnt * 4; g += BS_THREADS / 32) {
+            if (!((needed >> (g >> 2)) & 1u)) continue;         // warp-uniform
             u32 c = g * 32 + lane;
             bool valid = c < col_cnt;
             uint2 p = valid ? planes[it.col_start + c] : make_uint2(0u, 0u);
@@ -66,34 +109,17 @@ __global__ void __launch_bounds__(BS_THREADS) hamming_tiles_bs(
             }
         }
         __syncthreads();
-        // letter sets of every 128-column block (for the in-kernel cull): lane = position
-        for (u32 task = warp; task < g4_cnt * 8; task += BS_THREADS / 32) {
-            u32 g4 = task >> 3, x = task & 7;
-            bool f = false;
-            if (x < (u32)NLET && lane < (u32)LP) {
-                uint4 v = eq4[((size_t)g4 * LP + lane) * XS + x];
-                f = (v.x | v.y | v.z | v.w) != 0u;
-            }
-            u32 bits = __ballot_sync(0xffffffffu, f);
-            if (lane == 0) sset[g4 * 8 + x] = bits;
-        }
-        __syncthreads();
 
-        // ---- rows: each thread owns one row UMI per pass; a warp's 32 rows are consecutive sorted UMIs ----
-        for (u32 rbase = 0; rbase < it.row_cnt; rbase += BS_THREADS) {
-            const u32 gi = rbase + threadIdx.x;
-            const bool valid = gi < it.row_cnt;
+        // ---- phase 3: evaluate the surviving blocks; each thread owns one row UMI per pass ----
+#pragma unroll
+        for (int ps = 0; ps < PASSES; ps++) {
+            u32 mk = mask[ps];
+            if (mk == 0) continue;                              // warp-uniform
+            const u32 gi = ps * BS_THREADS + threadIdx.x;
+            const bool valid = gi < row_cnt;
             const u32 nvalid = __popc(__ballot_sync(0xffffffffu, valid));
-            if (nvalid == 0) continue;
             const uint2 rp = valid ? planes[it.row_start + gi] : make_uint2(0u, 0u);
             const u32 rn = (HASN && valid) ? nplane[it.row_start + gi] : 0u;
-            u32 rs[5] = {0u, 0u, 0u, 0u, 0u};
-            if (cull) {
-                u32 oh[5];
-                onehot_planes(rp, rn, valid ? lmask : 0u, oh);
-#pragma unroll
-                for (int x = 0; x < NLET; x++) rs[x] = __reduce_or_sync(0xffffffffu, oh[x]);
-            }
             u32 off[LP];                                   // byte offset of the row's letter slot at position j
 #pragma unroll
             for (int j = 0; j < LP; j++) {
@@ -101,19 +127,11 @@ __global__ void __launch_bounds__(BS_THREADS) hamming_tiles_bs(
                 if (HASN && ((rn >> j) & 1u)) letter = 4u;
                 off[j] = (u32)(j * XS + letter) * 16u;
             }
-            const u32 row_lo = rbase + warp * 32;          // first row (tile-relative) of this warp
-            const char *base = reinterpret_cast<const char *>(eq4);
-            for (u32 g4 = 0; g4 < g4_cnt; g4++, base += LP * XS * 16) {
-                if (cull) {
-                    // diagonal tile: only pairs with column > row are wanted
-                    if (diag && g4 * 128 + 127 <= row_lo) continue;
-                    const uint4 s = *reinterpret_cast<const uint4 *>(&sset[g4 * 8]);
-                    u32 t = (rs[0] & s.x) | (rs[1] & s.y) | (rs[2] & s.z) | (rs[3] & s.w);
-                    if (HASN) t |= rs[4] & sset[g4 * 8 + 4];
-                    if (__popc(~t & lmask) > K) continue;   // >K positions with disjoint letter sets: no neighbour in this block
-                }
+            while (mk) {
+                const u32 g4 = __ffs(mk) - 1; mk &= mk - 1;
                 evaluated += (u64)nvalid * min(128u, col_cnt - g4 * 128);
                 if (!valid) continue;
+                const char *base = reinterpret_cast<const char *>(eq4) + (size_t)g4 * (LP * XS * 16);
                 uint4 m1 = make_uint4(~0u, ~0u, ~0u, ~0u), m2 = m1, m3 = m1, m4 = m1;
 #pragma unroll
                 for (int j = 0; j < LP; j++) {
@@ -151,7 +169,7 @@ __global__ void __launch_bounds__(BS_THREADS) hamming_tiles_bs(
 
 template <int LP, int K, bool HASN>
 static int bs_launch_one(cudaStream_t stream, int num_sms, const TileItem *items, u32 n_items, const uint2 *planes,
-                         const u32 *nplane, int L, int cull, EdgeSink es, u32 *counter, unsigned long long *pairs_eval) {
+                         const u32 *nplane, const u32 *bsum, int L, int cull, EdgeSink es, u32 *counter, unsigned long long *pairs_eval) {
     constexpr int XS = HASN ? 8 : 4;
     size_t smem = (size_t)BS_G4 * LP * XS * 16;
     auto kern = hamming_tiles_bs<LP, K, HASN>;
@@ -162,32 +180,32 @@ static int bs_launch_one(cudaStream_t stream, int num_sms, const TileItem *items
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BS_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
     u32 grid = (u32)std::min<u64>((u64)n_items, (u64)num_sms * occ);
     if (cudaMemsetAsync(counter, 0, sizeof(u32), stream) != cudaSuccess) return -1;
-    kern<<<grid, BS_THREADS, smem, stream>>>(items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
+    kern<<<grid, BS_THREADS, smem, stream>>>(items, n_items, planes, nplane, bsum, L, cull, es, counter, pairs_eval);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 
 template <int K, bool HASN>
 static int bs_launch_k(cudaStream_t stream, int num_sms, const TileItem *items, u32 n_items, const uint2 *planes,
-                       const u32 *nplane, int L, int cull, EdgeSink es, u32 *counter, unsigned long long *pairs_eval) {
-    if (L <= 8)  return bs_launch_one<8, K, HASN>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
-    if (L <= 12) return bs_launch_one<12, K, HASN>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
-    if (L <= 16) return bs_launch_one<16, K, HASN>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
-    if (L <= 24) return bs_launch_one<24, K, HASN>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
+                       const u32 *nplane, const u32 *bsum, int L, int cull, EdgeSink es, u32 *counter, unsigned long long *pairs_eval) {
+    if (L <= 8)  return bs_launch_one<8, K, HASN>(stream, num_sms, items, n_items, planes, nplane, bsum, L, cull, es, counter, pairs_eval);
+    if (L <= 12) return bs_launch_one<12, K, HASN>(stream, num_sms, items, n_items, planes, nplane, bsum, L, cull, es, counter, pairs_eval);
+    if (L <= 16) return bs_launch_one<16, K, HASN>(stream, num_sms, items, n_items, planes, nplane, bsum, L, cull, es, counter, pairs_eval);
+    if (L <= 24) return bs_launch_one<24, K, HASN>(stream, num_sms, items, n_items, planes, nplane, bsum, L, cull, es, counter, pairs_eval);
     if (HASN) return 1;   // N-containing batches are limited to 21 nt upstream of here
-    return bs_launch_one<32, K, false>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
+    return bs_launch_one<32, K, false>(stream, num_sms, items, n_items, planes, nplane, bsum, L, cull, es, counter, pairs_eval);
 }
 
 // returns 0 = launched, 1 = configuration not covered (caller uses the direct kernel), -1 = CUDA error
 static int launch_neighbours_bitsliced(cudaStream_t stream, int num_sms, const TileItem *items, u32 n_items,
-                                       const uint2 *planes, const u32 *nplane, int L, int k, bool has_n, int cull, EdgeSink es,
+                                       const uint2 *planes, const u32 *nplane, const u32 *bsum, int L, int k, bool has_n, int cull, EdgeSink es,
                                        u32 *counter, unsigned long long *pairs_eval) {
     if (k < 1 || k > 3) return 1;
     if (!has_n) {
-        if (k == 1) return bs_launch_k<1, false>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
-        if (k == 2) return bs_launch_k<2, false>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
-        return bs_launch_k<3, false>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
+        if (k == 1) return bs_launch_k<1, false>(stream, num_sms, items, n_items, planes, nplane, bsum, L, cull, es, counter, pairs_eval);
+        if (k == 2) return bs_launch_k<2, false>(stream, num_sms, items, n_items, planes, nplane, bsum, L, cull, es, counter, pairs_eval);
+        return bs_launch_k<3, false>(stream, num_sms, items, n_items, planes, nplane, bsum, L, cull, es, counter, pairs_eval);
     }
-    if (k == 1) return bs_launch_k<1, true>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
-    if (k == 2) return bs_launch_k<2, true>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
-    return bs_launch_k<3, true>(stream, num_sms, items, n_items, planes, nplane, L, cull, es, counter, pairs_eval);
+    if (k == 1) return bs_launch_k<1, true>(stream, num_sms, items, n_items, planes, nplane, bsum, L, cull, es, counter, pairs_eval);
+    if (k == 2) return bs_launch_k<2, true>(stream, num_sms, items, n_items, planes, nplane, bsum, L, cull, es, counter, pairs_eval);
+    return bs_launch_k<3, true>(stream, num_sms, items, n_items, planes, nplane, bsum, L, cull, es, counter, pairs_eval);
 }

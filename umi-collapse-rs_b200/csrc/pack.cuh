@@ -21,6 +21,7 @@ struct DevScalars {
     u64 scratch;      // work counter of the neighbour kernel
     u64 scratch2;     // pairs in scheduled tile items (direct kernel accounting)
     u32 n_cand, n_tiles;
+    u32 sort_ticket, sort_err;
 };
 
 struct KeyLayout {

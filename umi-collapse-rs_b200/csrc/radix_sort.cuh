@@ -3,35 +3,99 @@
 // src/deduplicate_sam.rs:148-176: after the sort, reads of one (bucket, UMI) are adjacent and
 // buckets are contiguous, so counting and merging become segmented scans.
 //
-// Per pass (<= 8 bits):  radix_hist -> scan of the digit-major histogram table -> radix_scatter.
+// One-sweep design: a single pre-pass (radix_global_hist) reads the keys once and builds the 256-bin
+// digit histogram of EVERY pass (digit counts do not depend on the order of the keys).  Each pass is
+// then one kernel (radix_onesweep): a CTA takes the next tile (atomic ticket, so all predecessors are
+// resident), ranks its keys by digit, publishes its per-digit counts and obtains its global offsets
+// by decoupled look-back over the predecessors' published states — keys and indices are read once
+// and written once per pass.
 // Ranking inside a tile is warp-synchronous: MATCH.ANY groups equal digits, the group leader bumps
 // the warp's private counter, so there are no shared-memory atomics and the order is stable.
 #pragma once
 #include "common.cuh"
-#include "scan.cuh"
 
 #define RS_THREADS 512
 #define RS_WARPS   (RS_THREADS / 32)
-#define RS_ITEMS   16
-#define RS_TILE    (RS_THREADS * RS_ITEMS)   // 8192 keys per CTA
+#define RS_MAX_PASSES 16
 
 struct KeyArr { u64 *w[2]; };   // w[0] = least significant word
+struct SortPass { int word, shift, bits; };
+struct SortPlan { int npass; SortPass p[RS_MAX_PASSES]; };
 
-// Ranks the tile's keys by digit.  dig[j] = digit of the thread's j-th key (0xffffffff = past the end).
-// packed[j] = digit | (rank within (warp, digit) << 8).  On return whist[w][d] = number of keys with
-// digit d in warp w's slice (before any __syncthreads).  The digits are loaded by the caller in one
-// batch so that all RS_ITEMS global loads are in flight together; this loop only touches shared memory.
-__device__ __forceinline__ void rs_rank_tile(const u32 *dig, u32 (*whist)[256], u32 *packed) {
+#define RS_FLAG_AGG    (1ull << 62)
+#define RS_FLAG_PREFIX (2ull << 62)
+#define RS_FLAG_MASK   (3ull << 62)
+
+// ---- pre-pass: global digit histograms of all passes in one read of the keys -------------------
+// Each thread walks 8 consecutive keys and aggregates runs of equal digits in a register before
+// touching shared memory, so the highly repetitive high digits of coordinate-sorted input do not
+// serialise on one shared-memory address.
+#define GH_THREADS 256
+#define GH_ITEMS   8
+__global__ void __launch_bounds__(GH_THREADS) radix_global_hist(KeyArr in, u64 n, SortPlan plan, u32 *__restrict__ ghist /* [npass][256] */) {
+    __shared__ u32 sh[RS_MAX_PASSES * 256];
+    for (u32 i = threadIdx.x; i < (u32)plan.npass * 256; i += GH_THREADS) sh[i] = 0;
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * GH_THREADS * GH_ITEMS;
+    for (u64 base = ((u64)blockIdx.x * GH_THREADS + threadIdx.x) * GH_ITEMS; base < n; base += stride) {
+        u64 k0[GH_ITEMS], k1[GH_ITEMS];
+#pragma unroll
+        for (int j = 0; j < GH_ITEMS; j++) {
+            u64 i = base + j;
+            k0[j] = i < n ? in.w[0][i] : 0;
+            k1[j] = (i < n && in.w[1]) ? in.w[1][i] : 0;
+        }
+        const int cnt = (int)min((u64)GH_ITEMS, n - base);
+        for (int p = 0; p < plan.npass; p++) {
+            const int sh_ = plan.p[p].shift; const u32 mask = (1u << plan.p[p].bits) - 1; const bool hi = plan.p[p].word != 0;
+            u32 run_d = 0xffffffffu, run_c = 0;
+#pragma unroll
+            for (int j = 0; j < GH_ITEMS; j++) {
+                if (j < cnt) {
+                    u32 d = (u32)((hi ? k1[j] : k0[j]) >> sh_) & mask;
+                    if (d != run_d) { if (run_c) atomicAdd(&sh[p * 256 + run_d], run_c); run_d = d; run_c = 0; }
+                    run_c++;
+                }
+            }
+            if (run_c) atomicAdd(&sh[p * 256 + run_d], run_c);
+        }
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < (u32)plan.npass * 256; i += GH_THREADS) if (sh[i]) atomicAdd(&ghist[i], sh[i]);
+}
+
+// exclusive scan of each pass's 256 bins (one warp-pair per pass; tiny)
+__global__ void __launch_bounds__(256) radix_digit_starts(u32 *ghist, int npass) {
+    __shared__ u32 s[256];
+    for (int p = 0; p < npass; p++) {
+        u32 v = ghist[p * 256 + threadIdx.x];
+        s[threadIdx.x] = v;
+        __syncthreads();
+        // Hillis-Steele inclusive scan over 256 elements
+        for (int o = 1; o < 256; o <<= 1) {
+            u32 t = threadIdx.x >= (u32)o ? s[threadIdx.x - o] : 0;
+            __syncthreads();
+            s[threadIdx.x] += t;
+            __syncthreads();
+        }
+        ghist[p * 256 + threadIdx.x] = s[threadIdx.x] - v;
+        __syncthreads();
+    }
+}
+
+// Ranks the thread's keys by digit.  packed[j] = digit | (rank within (warp, digit) << 8), or
+// 0xffffffff past the end.  On return whist[w][d] = number of keys with digit d in warp w's slice.
+template <int ITEMS>
+__device__ __forceinline__ void rs_rank_tile(u32 *packed /* in: digit or 0xffffffff */, u32 (*whist)[256]) {
     const u32 w = threadIdx.x >> 5, lane = lane_id();
     for (u32 i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&whist[0][0])[i] = 0;
     __syncthreads();
     const u32 lt = lanemask_lt();
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; j++) {
-        const u32 d = dig[j];
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 d = packed[j];
         const bool active = d != 0xffffffffu;
         const u32 act = __ballot_sync(0xffffffffu, active);
-        packed[j] = 0;
         if (active) {
             u32 peers = __match_any_sync(act, d);
             u32 leader = __ffs(peers) - 1;
@@ -44,64 +108,73 @@ __device__ __forceinline__ void rs_rank_tile(const u32 *dig, u32 (*whist)[256], 
     }
 }
 
-__global__ void __launch_bounds__(RS_THREADS) radix_hist(const u64 *__restrict__ wsel, u64 n, int sh, u32 mask,
-                                                         u32 *__restrict__ hist, u32 nblk) {
-    __shared__ u32 whist[RS_WARPS][256];
-    u32 dig[RS_ITEMS], packed[RS_ITEMS];
-    const u64 tile_base = (u64)blockIdx.x * RS_TILE;
-    const u32 w = threadIdx.x >> 5, lane = lane_id();
-#pragma unroll
-    for (int j = 0; j < RS_ITEMS; j++) {
-        u64 i = tile_base + (u64)(w * RS_ITEMS + j) * 32 + lane;
-        dig[j] = i < n ? ((u32)(wsel[i] >> sh) & mask) : 0xffffffffu;
-    }
-    rs_rank_tile(dig, whist, packed);
-    __syncthreads();
-    if (threadIdx.x < 256) {
-        u32 s = 0;
-#pragma unroll
-        for (int ww = 0; ww < RS_WARPS; ww++) s += whist[ww][threadIdx.x];
-        hist[(u64)threadIdx.x * nblk + blockIdx.x] = s;
-    }
-}
-
-template <int NW>
-__global__ void __launch_bounds__(RS_THREADS) radix_scatter(KeyArr in, const u32 *__restrict__ idx_in, KeyArr out,
-                                                            u32 *__restrict__ idx_out, u64 n, int wsel, int sh, u32 mask,
-                                                            const u32 *__restrict__ hist_scanned, u32 nblk, int iota) {
+// One pass.  err[0] is set if a look-back ever exceeds its spin budget (cannot happen with ticketed
+// tiles; it turns a would-be hang into a reported error).
+template <int NW, int ITEMS>
+__global__ void __launch_bounds__(RS_THREADS, (NW == 1 ? 2 : 1)) radix_onesweep(
+    KeyArr in, const u32 *__restrict__ idx_in, KeyArr out, u32 *__restrict__ idx_out, u64 n, int wsel, int sh, u32 mask,
+    const u32 *__restrict__ digit_start, unsigned long long *tile_state /* [ntiles][256] */, u32 *ticket, u32 *err, int iota) {
+    constexpr u32 TILE = RS_THREADS * ITEMS;
     __shared__ u32 whist[RS_WARPS][256];
     __shared__ u32 sbase[256];
-    u32 dig[RS_ITEMS], packed[RS_ITEMS], vidx[RS_ITEMS];
-    u64 key[NW][RS_ITEMS];
-    const u64 tile_base = (u64)blockIdx.x * RS_TILE;
+    __shared__ u32 s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u64 tile_base = (u64)tile * TILE;
     const u32 w = threadIdx.x >> 5, lane = lane_id();
-    // batch every global load of the tile up front (RS_ITEMS * (NW + 1) independent loads per thread)
+    u32 packed[ITEMS], vidx[ITEMS];
+    u64 key[NW][ITEMS];
+    // every global load of the tile is issued before anything else (ITEMS * (NW + 1) loads in flight per thread)
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; j++) {
-        u64 i = tile_base + (u64)(w * RS_ITEMS + j) * 32 + lane;
+    for (int j = 0; j < ITEMS; j++) {
+        u64 i = tile_base + (u64)(w * ITEMS + j) * 32 + lane;
         bool a = i < n;
 #pragma unroll
         for (int k = 0; k < NW; k++) key[k][j] = a ? in.w[k][i] : 0;
         vidx[j] = a ? (iota ? (u32)i : idx_in[i]) : 0;
     }
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; j++) {
-        u64 i = tile_base + (u64)(w * RS_ITEMS + j) * 32 + lane;
+    for (int j = 0; j < ITEMS; j++) {
+        u64 i = tile_base + (u64)(w * ITEMS + j) * 32 + lane;
         u64 kw = NW == 1 ? key[0][j] : (wsel == 0 ? key[0][j] : key[NW - 1][j]);
-        dig[j] = i < n ? ((u32)(kw >> sh) & mask) : 0xffffffffu;
+        packed[j] = i < n ? ((u32)(kw >> sh) & mask) : 0xffffffffu;
     }
-    rs_rank_tile(dig, whist, packed);
+    rs_rank_tile<ITEMS>(packed, whist);
     __syncthreads();
     if (threadIdx.x < 256) {
-        u32 run = 0;
+        const u32 d = threadIdx.x;
+        u32 total = 0;
 #pragma unroll
-        for (int ww = 0; ww < RS_WARPS; ww++) { u32 t = whist[ww][threadIdx.x]; whist[ww][threadIdx.x] = run; run += t; }
-        sbase[threadIdx.x] = hist_scanned[(u64)threadIdx.x * nblk + blockIdx.x];
+        for (int ww = 0; ww < RS_WARPS; ww++) { u32 t = whist[ww][d]; whist[ww][d] = total; total += t; }
+        unsigned long long *mine = tile_state + (u64)tile * 256 + d;
+        u64 excl = 0;
+        if (tile == 0) {
+            atomicExch(mine, RS_FLAG_PREFIX | (unsigned long long)total);
+        } else {
+            atomicExch(mine, RS_FLAG_AGG | (unsigned long long)total);
+            u32 p = tile;
+            u32 spins = 0;
+            while (p > 0) {
+                const volatile unsigned long long *prev = tile_state + (u64)(p - 1) * 256 + d;
+                unsigned long long v = *prev;
+                if ((v & RS_FLAG_MASK) == 0) {
+                    if (++spins > (1u << 27)) { err[0] = 1; break; }
+                    __nanosleep(20);
+                    continue;
+                }
+                excl += v & ~RS_FLAG_MASK;
+                if ((v & RS_FLAG_MASK) == RS_FLAG_PREFIX) break;
+                p--;
+            }
+            atomicExch(mine, RS_FLAG_PREFIX | (unsigned long long)(excl + total));
+        }
+        sbase[d] = digit_start[d] + (u32)excl;
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; j++) {
-        if (dig[j] != 0xffffffffu) {
+    for (int j = 0; j < ITEMS; j++) {
+        if (packed[j] != 0xffffffffu) {
             u32 d = packed[j] & 0xff, r = packed[j] >> 8;
             u64 pos = (u64)sbase[d] + whist[w][d] + r;
 #pragma unroll
@@ -111,14 +184,9 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter(KeyArr in, const u32
     }
 }
 
-struct HistLoad  { const u32 *h; __device__ u32 operator()(u64 i) const { return h[i]; } };
-struct HistStore { u32 *h; __device__ void operator()(u64 i, u32, u32 ex) const { h[i] = ex; } };
-
-struct SortPass { int word, shift, bits; };
-
 // Plans the passes that cover bit range [0, total_bits) of the key without straddling a word.
-static inline std::vector<SortPass> rs_plan(int total_bits) {
-    std::vector<SortPass> p;
+static inline SortPlan rs_plan(int total_bits) {
+    SortPlan pl; pl.npass = 0;
     for (int word = 0; word < 2; word++) {
         int lo = word * 64, hi = total_bits < lo + 64 ? total_bits : lo + 64;
         if (hi <= lo) break;
@@ -127,9 +195,9 @@ static inline std::vector<SortPass> rs_plan(int total_bits) {
         int done = 0;
         for (int i = 0; i < npass; i++) {
             int b = (nbits - done + (npass - i) - 1) / (npass - i);
-            p.push_back({word, done, b});
+            pl.p[pl.npass++] = {word, done, b};
             done += b;
         }
     }
-    return p;
+    return pl;
 }

@@ -39,7 +39,7 @@ struct umigpu_ctx {
 
     DevBuf d_key[2][2], d_idx[2], d_hist, d_tiles;
     DevBuf d_useg, d_rep, d_planes, d_nplane, d_bhead, d_wsum, d_read_uid, d_freq, d_thr, d_repidx, d_label, d_prio;
-    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_onehot, d_tileoff, d_tsum;
+    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_onehot, d_tileoff, d_tsum, d_tilestate, d_bsum;
 
     // results
     bool ran = false;
@@ -130,7 +130,7 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
                       &ctx->d_hist, &ctx->d_tiles, &ctx->d_useg, &ctx->d_rep, &ctx->d_planes, &ctx->d_nplane, &ctx->d_bhead, &ctx->d_wsum,
                       &ctx->d_read_uid, &ctx->d_freq, &ctx->d_thr, &ctx->d_repidx, &ctx->d_label, &ctx->d_prio, &ctx->d_bstart, &ctx->d_itemoff,
                       &ctx->d_items, &ctx->d_edges, &ctx->d_keep, &ctx->d_state, &ctx->d_blocked, &ctx->d_bitmap, &ctx->d_kept, &ctx->d_roots,
-                      &ctx->d_onehot, &ctx->d_tileoff, &ctx->d_tsum};
+                      &ctx->d_onehot, &ctx->d_tileoff, &ctx->d_tsum, &ctx->d_tilestate, &ctx->d_bsum};
     for (DevBuf *b : bufs) b->release();
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
     if (ctx->h_kept) cudaFreeHost(ctx->h_kept);
@@ -242,30 +242,38 @@ static int run_scan(umigpu_ctx *ctx, F f, G g, u64 n, u32 *total_dev /* may be n
     return UMIGPU_OK;
 }
 
-// stable LSD radix sort over `total_bits` of the NW-word keys in d_key[0]; returns the buffer index
-// holding the result.  iota_first: the first pass synthesises idx = position.
-static int run_sort(umigpu_ctx *ctx, u64 n, int nw, int total_bits, int *cur_out) {
-    std::vector<SortPass> passes = rs_plan(total_bits);
-    u32 nblk = (u32)ceil_div_u64(n, RS_TILE);
-    CK(ctx->d_hist.reserve((size_t)256 * nblk * sizeof(u32)));
-    u32 *hist = ctx->d_hist.as<u32>();
+// stable LSD radix sort of the NW-word keys in d_key[0] (+ index payload) over the passes of `plan`;
+// returns the buffer index holding the result.  The first pass synthesises idx = position.
+#define RS_ITEMS_1 12     // keys per thread, one-word keys  (tile 6144, 2 CTAs/SM)
+#define RS_ITEMS_2 8      // keys per thread, two-word keys  (tile 4096)
+static int run_sort(umigpu_ctx *ctx, u64 n, int nw, const SortPlan &plan, int *cur_out) {
+    DevScalars *sc = ctx->d_sc.as<DevScalars>();
+    const u32 tile = RS_THREADS * (nw == 1 ? RS_ITEMS_1 : RS_ITEMS_2);
+    const u32 ntiles = (u32)ceil_div_u64(n, tile);
+    CK(ctx->d_hist.reserve((size_t)RS_MAX_PASSES * 256 * sizeof(u32)));
+    CK(ctx->d_tilestate.reserve((size_t)ntiles * 256 * 8));
+    u32 *ghist = ctx->d_hist.as<u32>();
+    CK(cudaMemsetAsync(ghist, 0, (size_t)plan.npass * 256 * 4, ctx->stream));
+    CK(cudaMemsetAsync(&sc->sort_err, 0, 4, ctx->stream));
+    KeyArr k0{{ctx->d_key[0][0].as<u64>(), nw == 2 ? ctx->d_key[0][1].as<u64>() : nullptr}};
+    u32 ggrid = (u32)std::min<u64>(ceil_div_u64(n, (u64)GH_THREADS * GH_ITEMS), (u64)ctx->num_sms * 8);
+    LAUNCH(radix_global_hist, ggrid, GH_THREADS, k0, n, plan, ghist);
+    LAUNCH(radix_digit_starts, 1, 256, ghist, plan.npass);
     int cur = 0;
-    bool first = true;
-    for (const SortPass &p : passes) {
+    for (int pi = 0; pi < plan.npass; pi++) {
+        const SortPass &p = plan.p[pi];
         KeyArr in{{ctx->d_key[cur][0].as<u64>(), ctx->d_key[cur][1].as<u64>()}};
         KeyArr out{{ctx->d_key[cur ^ 1][0].as<u64>(), ctx->d_key[cur ^ 1][1].as<u64>()}};
-        u32 mask = (1u << p.bits) - 1;
-        LAUNCH(radix_hist, nblk, RS_THREADS, (const u64 *)in.w[p.word], n, p.shift, mask, hist, nblk);
-        int rc = run_scan(ctx, HistLoad{hist}, HistStore{hist}, (u64)256 * nblk, nullptr);
-        if (rc) return rc;
+        const u32 mask = (1u << p.bits) - 1;
+        CK(cudaMemsetAsync(ctx->d_tilestate.p, 0, (size_t)ntiles * 256 * 8, ctx->stream));
+        CK(cudaMemsetAsync(&sc->sort_ticket, 0, 4, ctx->stream));
         if (nw == 1)
-            LAUNCH(radix_scatter<1>, nblk, RS_THREADS, in, (const u32 *)ctx->d_idx[cur].as<u32>(), out, ctx->d_idx[cur ^ 1].as<u32>(), n,
-                   p.word, p.shift, mask, (const u32 *)hist, nblk, first ? 1 : 0);
+            LAUNCH((radix_onesweep<1, RS_ITEMS_1>), ntiles, RS_THREADS, in, (const u32 *)ctx->d_idx[cur].as<u32>(), out, ctx->d_idx[cur ^ 1].as<u32>(), n,
+                   p.word, p.shift, mask, (const u32 *)(ghist + pi * 256), ctx->d_tilestate.as<unsigned long long>(), &sc->sort_ticket, &sc->sort_err, pi == 0 ? 1 : 0);
         else
-            LAUNCH(radix_scatter<2>, nblk, RS_THREADS, in, (const u32 *)ctx->d_idx[cur].as<u32>(), out, ctx->d_idx[cur ^ 1].as<u32>(), n,
-                   p.word, p.shift, mask, (const u32 *)hist, nblk, first ? 1 : 0);
+            LAUNCH((radix_onesweep<2, RS_ITEMS_2>), ntiles, RS_THREADS, in, (const u32 *)ctx->d_idx[cur].as<u32>(), out, ctx->d_idx[cur ^ 1].as<u32>(), n,
+                   p.word, p.shift, mask, (const u32 *)(ghist + pi * 256), ctx->d_tilestate.as<unsigned long long>(), &sc->sort_ticket, &sc->sort_err, pi == 0 ? 1 : 0);
         cur ^= 1;
-        first = false;
     }
     *cur_out = cur;
     return UMIGPU_OK;
@@ -330,7 +338,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     // ---- K2 sort ----
     STAGE_BEGIN(UMIGPU_STAGE_SORT);
     int cur = 0;
-    rc = run_sort(ctx, n, lay.nw, lay.total_bits, &cur);
+    rc = run_sort(ctx, n, lay.nw, rs_plan(lay.total_bits), &cur);
     if (rc) return rc;
     STAGE_END(UMIGPU_STAGE_SORT);
     SortedKeys sk{ctx->d_key[cur][0].as<u64>(), lay.nw == 2 ? ctx->d_key[cur][1].as<u64>() : nullptr, lay.umi_bits};
@@ -358,6 +366,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     if (rc) return rc;
     rc = read_scalars(ctx);
     if (rc) return rc;
+    if (ctx->h_sc->sort_err) return fail(ctx, UMIGPU_ERR_CUDA, "radix sort look-back exceeded its spin budget");
     const u32 U = ctx->h_sc->n_unique;
     ctx->n_unique = U;
     CK(ctx->d_freq.reserve((size_t)U * 4)); CK(ctx->d_thr.reserve((size_t)U * 4)); CK(ctx->d_repidx.reserve((size_t)U * 4));
@@ -394,9 +403,10 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
         if (rc) return rc;
         const u32 n_cand = ctx->h_sc->n_cand, n_tiles = ctx->h_sc->n_tiles;
         CK(ctx->d_tsum.reserve((size_t)std::max<u32>(n_tiles, 1) * TS_WORDS * 4));
+        CK(ctx->d_bsum.reserve((size_t)std::max<u32>(n_tiles, 1) * BLOCKS_PER_TILE * TS_WORDS * 4));
         if (cull && n_tiles)
             LAUNCH(tile_summary_kernel, grid_for((u64)n_tiles * 32, 256), 256, n_tiles, B, (const u32 *)ctx->d_tileoff.p, (const u32 *)ctx->d_bstart.p,
-                   (const uint2 *)ctx->d_planes.p, has_n ? (const u32 *)ctx->d_nplane.p : (const u32 *)nullptr, lay.umi_len, ctx->d_tsum.as<u32>());
+                   (const uint2 *)ctx->d_planes.p, has_n ? (const u32 *)ctx->d_nplane.p : (const u32 *)nullptr, lay.umi_len, ctx->d_tsum.as<u32>(), ctx->d_bsum.as<u32>());
         // candidates are tested in chunks so that the item buffer only has to hold the survivors of one chunk
         // plus what is already there; in the worst case (no culling) it holds every candidate
         CK(ctx->d_items.reserve((size_t)std::max<u32>(n_cand, 1) * sizeof(TileItem)));
@@ -523,7 +533,7 @@ static int launch_neighbours(umigpu_ctx *ctx, u32 n_items, EdgeSink es, bool has
     u32 grid = std::min<u32>(n_items, (u32)ctx->num_sms * 4);
     const int k = cfg.k;
     if (!(cfg.flags & UMIGPU_FLAG_KERNEL_DIRECT)) {
-        int rc = launch_neighbours_bitsliced(ctx->stream, ctx->num_sms, items, n_items, planes, nplane, (int)cfg.umi_len, k, has_n,
+        int rc = launch_neighbours_bitsliced(ctx->stream, ctx->num_sms, items, n_items, planes, nplane, ctx->d_bsum.as<u32>(), (int)cfg.umi_len, k, has_n,
                                              (cfg.flags & UMIGPU_FLAG_NO_CULL) ? 0 : 1, es, (u32 *)&ctx->d_sc.as<DevScalars>()->scratch,
                                              (unsigned long long *)&ctx->d_sc.as<DevScalars>()->pairs_eval);
         ctx->used_direct = false;
@@ -717,25 +727,12 @@ extern "C" int umigpu_neighbours(umigpu_ctx *ctx, uint64_t n, const uint8_t *umi
     int cur = 0;
     // keys are (src << 32 | dst): sort the dst bits, then the src bits
     {
-        std::vector<SortPass> passes;
+        SortPlan plan; plan.npass = 0;
         for (int part = 0; part < 2; part++) {
             int done = 0, np = (nb + 7) / 8;
-            for (int i = 0; i < np; i++) { int b = (nb - done + (np - i) - 1) / (np - i); passes.push_back({0, part * 32 + done, b}); done += b; }
+            for (int i = 0; i < np; i++) { int b = (nb - done + (np - i) - 1) / (np - i); plan.p[plan.npass++] = {0, part * 32 + done, b}; done += b; }
         }
-        u32 nblk = (u32)ceil_div_u64(E, RS_TILE);
-        CK(ctx->d_hist.reserve((size_t)256 * nblk * 4));
-        u32 *hist = ctx->d_hist.as<u32>();
-        bool first = true;
-        for (const SortPass &p : passes) {
-            KeyArr in{{ctx->d_key[cur][0].as<u64>(), nullptr}}, outk{{ctx->d_key[cur ^ 1][0].as<u64>(), nullptr}};
-            u32 mask = (1u << p.bits) - 1;
-            LAUNCH(radix_hist, nblk, RS_THREADS, (const u64 *)in.w[0], E, p.shift, mask, hist, nblk);
-            rc = run_scan(ctx, HistLoad{hist}, HistStore{hist}, (u64)256 * nblk, nullptr);
-            if (rc) return rc;
-            LAUNCH(radix_scatter<1>, nblk, RS_THREADS, in, (const u32 *)ctx->d_idx[cur].as<u32>(), outk, ctx->d_idx[cur ^ 1].as<u32>(), E, 0,
-                   p.shift, mask, (const u32 *)hist, nblk, first ? 1 : 0);
-            cur ^= 1; first = false;
-        }
+        if (plan.npass > 0) { rc = run_sort(ctx, E, 1, plan, &cur); if (rc) return rc; }
     }
     CK(ctx->d_rep.reserve((n + 1) * 8)); CK(ctx->d_kept.reserve(E * 4));
     LAUNCH(csr_from_sorted_kernel, grid_for(E + 1, 256), 256, (const u64 *)ctx->d_key[cur][0].p, E, (u32)n, ctx->d_rep.as<u64>(), ctx->d_kept.as<u32>());
