@@ -9,14 +9,16 @@
 // resident), ranks its keys by digit, publishes its per-digit counts and obtains its global offsets
 // by decoupled look-back over the predecessors' published states — keys and indices are read once
 // and written once per pass.
-// Ranking inside a tile is warp-synchronous: MATCH.ANY groups equal digits, the group leader bumps
+// Ranking inside a tile is warp-synchronous: per-bit ballots group equal digits, the group leader bumps
 // the warp's private counter, so there are no shared-memory atomics and the order is stable.
 #pragma once
 #include "common.cuh"
+#include "scan.cuh"
 
 #define RS_THREADS 512
 #define RS_WARPS   (RS_THREADS / 32)
 #define RS_MAX_PASSES 16
+#define RS_LB 8             // look-back window (predecessor tiles examined per round)
 
 struct KeyArr { u64 *w[2]; };   // w[0] = least significant word
 struct SortPass { int word, shift, bits; };
@@ -95,9 +97,16 @@ __device__ __forceinline__ void rs_rank_tile(u32 *packed /* in: digit or 0xfffff
     for (int j = 0; j < ITEMS; j++) {
         const u32 d = packed[j];
         const bool active = d != 0xffffffffu;
-        const u32 act = __ballot_sync(0xffffffffu, active);
+        // lanes holding the same digit: eight ballots (one per digit bit) instead of MATCH.ANY, whose cost
+        // grows with the number of distinct values in the warp (up to 32 for the random UMI digits)
+        u32 peers = __ballot_sync(0xffffffffu, active);
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const bool bit = (d >> b) & 1u;
+            const u32 m = __ballot_sync(0xffffffffu, active && bit);
+            peers &= bit ? m : ~m;
+        }
         if (active) {
-            u32 peers = __match_any_sync(act, d);
             u32 leader = __ffs(peers) - 1;
             u32 old = 0;
             if (lane == leader) { old = whist[w][d]; whist[w][d] = old + __popc(peers); }
@@ -108,20 +117,27 @@ __device__ __forceinline__ void rs_rank_tile(u32 *packed /* in: digit or 0xfffff
     }
 }
 
-// One pass.  err[0] is set if a look-back ever exceeds its spin budget (cannot happen with ticketed
-// tiles; it turns a would-be hang into a reported error).
+// One pass.  After ranking, the tile is permuted into digit order in shared memory, so that the
+// global writes of a warp are runs of consecutive addresses (one run per digit) instead of 32
+// unrelated 8-byte fragments.  err[0] is set if a look-back ever exceeds its spin budget (cannot
+// happen with ticketed tiles; it turns a would-be hang into a reported error).
 template <int NW, int ITEMS>
 __global__ void __launch_bounds__(RS_THREADS, (NW == 1 ? 2 : 1)) radix_onesweep(
     KeyArr in, const u32 *__restrict__ idx_in, KeyArr out, u32 *__restrict__ idx_out, u64 n, int wsel, int sh, u32 mask,
     const u32 *__restrict__ digit_start, unsigned long long *tile_state /* [ntiles][256] */, u32 *ticket, u32 *err, int iota) {
     constexpr u32 TILE = RS_THREADS * ITEMS;
+    extern __shared__ __align__(16) unsigned char rs_dyn[];          // u64 skey[NW][TILE]; u32 sidx[TILE]
+    u64 *skey = reinterpret_cast<u64 *>(rs_dyn);
+    u32 *sidx = reinterpret_cast<u32 *>(rs_dyn + (size_t)NW * TILE * 8);
     __shared__ u32 whist[RS_WARPS][256];
-    __shared__ u32 sbase[256];
+    __shared__ u32 sbase[256], slocal[256];
+    __shared__ u32 sscan[RS_THREADS / 32 + 1];
     __shared__ u32 s_tile;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const u32 tile = s_tile;
     const u64 tile_base = (u64)tile * TILE;
+    const u32 tile_count = (u32)min((u64)TILE, n - tile_base);
     const u32 w = threadIdx.x >> 5, lane = lane_id();
     u32 packed[ITEMS], vidx[ITEMS];
     u64 key[NW][ITEMS];
@@ -142,9 +158,9 @@ __global__ void __launch_bounds__(RS_THREADS, (NW == 1 ? 2 : 1)) radix_onesweep(
     }
     rs_rank_tile<ITEMS>(packed, whist);
     __syncthreads();
+    u32 total = 0;
     if (threadIdx.x < 256) {
         const u32 d = threadIdx.x;
-        u32 total = 0;
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ww++) { u32 t = whist[ww][d]; whist[ww][d] = total; total += t; }
         unsigned long long *mine = tile_state + (u64)tile * 256 + d;
@@ -153,33 +169,66 @@ __global__ void __launch_bounds__(RS_THREADS, (NW == 1 ? 2 : 1)) radix_onesweep(
             atomicExch(mine, RS_FLAG_PREFIX | (unsigned long long)total);
         } else {
             atomicExch(mine, RS_FLAG_AGG | (unsigned long long)total);
-            u32 p = tile;
+            // decoupled look-back, RS_LB predecessors per round: the loads of a round are independent
+            // (one latency per round instead of one per tile); a not-yet-published state ends the round
+            u32 p = tile;          // predecessors [0, p) are still to be accounted for
             u32 spins = 0;
-            while (p > 0) {
-                const volatile unsigned long long *prev = tile_state + (u64)(p - 1) * 256 + d;
-                unsigned long long v = *prev;
-                if ((v & RS_FLAG_MASK) == 0) {
-                    if (++spins > (1u << 27)) { err[0] = 1; break; }
-                    __nanosleep(20);
-                    continue;
+            bool done = false;
+            while (!done && p > 0) {
+                unsigned long long v[RS_LB];
+#pragma unroll
+                for (int i = 0; i < RS_LB; i++) {
+                    const volatile unsigned long long *prev = tile_state + (u64)(p > (u32)i ? p - 1 - i : 0) * 256 + d;
+                    v[i] = *prev;
                 }
-                excl += v & ~RS_FLAG_MASK;
-                if ((v & RS_FLAG_MASK) == RS_FLAG_PREFIX) break;
-                p--;
+#pragma unroll
+                for (int i = 0; i < RS_LB; i++) {
+                    if (done || p == 0) break;
+                    if ((v[i] & RS_FLAG_MASK) == 0) {
+                        if (++spins > (1u << 24)) { err[0] = 1; done = true; }
+                        if (i == 0) __nanosleep(40);
+                        break;                                   // re-poll from this predecessor
+                    }
+                    excl += v[i] & ~RS_FLAG_MASK;
+                    p--;
+                    if ((v[i] & RS_FLAG_MASK) == RS_FLAG_PREFIX) done = true;
+                }
             }
             atomicExch(mine, RS_FLAG_PREFIX | (unsigned long long)(excl + total));
         }
         sbase[d] = digit_start[d] + (u32)excl;
     }
+    // start of each digit inside the tile (exclusive scan of the tile's digit counts)
+    u32 tot_all;
+    const u32 lstart = block_exclusive_scan<u32, RS_THREADS>(total, sscan, &tot_all);
+    if (threadIdx.x < 256) slocal[threadIdx.x] = lstart;
     __syncthreads();
+    // permute the tile into digit order in shared memory
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         if (packed[j] != 0xffffffffu) {
-            u32 d = packed[j] & 0xff, r = packed[j] >> 8;
-            u64 pos = (u64)sbase[d] + whist[w][d] + r;
+            const u32 d = packed[j] & 0xff, r = packed[j] >> 8;
+            const u32 lp = slocal[d] + whist[w][d] + r;
 #pragma unroll
-            for (int k = 0; k < NW; k++) out.w[k][pos] = key[k][j];
-            idx_out[pos] = vidx[j];
+            for (int k = 0; k < NW; k++) skey[(size_t)k * TILE + lp] = key[k][j];
+            sidx[lp] = vidx[j];
+        }
+    }
+    __syncthreads();
+    // coalesced write-out: consecutive threads hold consecutive elements of (mostly) the same digit
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 i = threadIdx.x + j * RS_THREADS;
+        if (i < tile_count) {
+            u64 kk[NW];
+#pragma unroll
+            for (int k = 0; k < NW; k++) kk[k] = skey[(size_t)k * TILE + i];
+            const u64 kw = NW == 1 ? kk[0] : (wsel == 0 ? kk[0] : kk[NW - 1]);
+            const u32 d = (u32)(kw >> sh) & mask;
+            const u64 pos = (u64)sbase[d] + (i - slocal[d]);
+#pragma unroll
+            for (int k = 0; k < NW; k++) out.w[k][pos] = kk[k];
+            idx_out[pos] = sidx[i];
         }
     }
 }

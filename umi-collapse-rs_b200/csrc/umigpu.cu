@@ -77,6 +77,15 @@ static int fail(umigpu_ctx *ctx, int code, const char *fmt, ...) {
         CK(cudaGetLastError());                                                                    \
     } while (0)
 
+// launch with dynamic shared memory above the 48 KB default (opt-in attribute set on every call: cheap)
+#define LAUNCH_SMEM(kern, grid, block, smem, ...)                                                  \
+    do {                                                                                           \
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)));  \
+        kern<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);                               \
+        ctx->launches++;                                                                           \
+        CK(cudaGetLastError());                                                                    \
+    } while (0)
+
 static inline int bits_for(u64 range) { int b = 0; while (range) { b++; range >>= 1; } return b; }
 static inline u32 grid_for(u64 n, u32 block) { return (u32)std::max<u64>(1, ceil_div_u64(n, block)); }
 
@@ -267,11 +276,12 @@ static int run_sort(umigpu_ctx *ctx, u64 n, int nw, const SortPlan &plan, int *c
         const u32 mask = (1u << p.bits) - 1;
         CK(cudaMemsetAsync(ctx->d_tilestate.p, 0, (size_t)ntiles * 256 * 8, ctx->stream));
         CK(cudaMemsetAsync(&sc->sort_ticket, 0, 4, ctx->stream));
+        const size_t dyn = (size_t)tile * (nw * 8 + 4);
         if (nw == 1)
-            LAUNCH((radix_onesweep<1, RS_ITEMS_1>), ntiles, RS_THREADS, in, (const u32 *)ctx->d_idx[cur].as<u32>(), out, ctx->d_idx[cur ^ 1].as<u32>(), n,
+            LAUNCH_SMEM((radix_onesweep<1, RS_ITEMS_1>), ntiles, RS_THREADS, dyn, in, (const u32 *)ctx->d_idx[cur].as<u32>(), out, ctx->d_idx[cur ^ 1].as<u32>(), n,
                    p.word, p.shift, mask, (const u32 *)(ghist + pi * 256), ctx->d_tilestate.as<unsigned long long>(), &sc->sort_ticket, &sc->sort_err, pi == 0 ? 1 : 0);
         else
-            LAUNCH((radix_onesweep<2, RS_ITEMS_2>), ntiles, RS_THREADS, in, (const u32 *)ctx->d_idx[cur].as<u32>(), out, ctx->d_idx[cur ^ 1].as<u32>(), n,
+            LAUNCH_SMEM((radix_onesweep<2, RS_ITEMS_2>), ntiles, RS_THREADS, dyn, in, (const u32 *)ctx->d_idx[cur].as<u32>(), out, ctx->d_idx[cur ^ 1].as<u32>(), n,
                    p.word, p.shift, mask, (const u32 *)(ghist + pi * 256), ctx->d_tilestate.as<unsigned long long>(), &sc->sort_ticket, &sc->sort_err, pi == 0 ? 1 : 0);
         cur ^= 1;
     }
