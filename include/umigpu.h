@@ -85,6 +85,8 @@ typedef struct umigpu_counters {
     uint64_t n_tile_items;      /* tile-pair work items executed (survivors of the exact cull)       */
     uint64_t n_tile_candidates; /* tile pairs before culling                                         */
     uint64_t n_sweeps;          /* label-propagation sweeps                                          */
+    uint64_t n_unmapped;        /* records dropped by the unmapped filter (deduplicate_sam.rs:102-108;
+                                   BAM feed only)                                                    */
 } umigpu_counters;
 
 typedef struct umigpu_result {
@@ -144,6 +146,23 @@ int umigpu_push_reads(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, const int
 int umigpu_push_reads_device(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, const int64_t *unclipped_pos,
                              const uint8_t *is_reverse, const uint8_t *umi_ascii, const int32_t *score,
                              const int32_t *weight, uint64_t first_read_index);
+
+/*
+ * Host feed on the device: `records` holds raw BAM alignment records exactly as they
+ * appear in the BGZF-inflated stream (int32 block_size, then block_size bytes), `offsets[i]` is the byte offset
+ * of record i's block_size field relative to `records` and offsets[n] the end of the last one
+ * (umigpu_bam_record_offsets finds them).  Per record the device evaluates get_unclipped_pos
+ * (utils/mod.rs:96-104), UcSAMRead::get_umi after the first `umi_sep` (utils/read.rs:96-111), the score of the
+ * configured merge (avg_qual read.rs:56-63 / MAPQ :77-79) and the unmapped filter (deduplicate_sam.rs:102-108);
+ * survivors are appended like umigpu_push_reads.  Kept indices are first_read_index + record number within this
+ * call.  Single-end only (the reference's --paired path is out of scope).  Host pointers.
+ */
+int umigpu_push_bam_records(umigpu_ctx *ctx, uint64_t n, const uint8_t *records, const uint64_t *offsets,
+                            uint8_t umi_sep, uint64_t first_read_index, uint64_t *n_unmapped);
+/* Pure host helper: walks the block_size fields of buf[0..len) and writes up to max_records offsets (+ the end
+ * offset); *consumed = bytes covered by whole records (a trailing partial record is left for the next call). */
+int umigpu_bam_record_offsets(const uint8_t *buf, uint64_t len, uint64_t *offsets, uint64_t max_records,
+                              uint64_t *n_records, uint64_t *consumed);
 
 /* HOT LOOP B, deduplicate_sam.rs:207-233 over all buckets at once: group, count, merge, neighbour
  * search, cluster, compact.  Asynchronous apart from a few scalar read-backs. */

@@ -486,3 +486,37 @@ int64_t oracle_unclipped_pos(int64_t pos, int is_reverse, const uint32_t *cigar,
         return end - 1 + soft + hard;
     }
 }
+
+/* One raw BAM alignment record (int32 block_size + body, BAM specification §4.2) -> what HOT LOOP A extracts
+ * from it: the unmapped filter (deduplicate_sam.rs:102-108), get_unclipped_pos (utils/mod.rs:96-104), get_umi
+ * (utils/read.rs:96-111: first separator byte of the read name, then umi_len bytes) and the score
+ * (avg_qual read.rs:56-63 or MAPQ :77-79).  Returns 0, or -10 no separator ("failed to get the umi"),
+ * -11 name too short (slice panic in the reference), -12 malformed record. */
+int oracle_bam_decode(const uint8_t *r, uint64_t rec_len, int umi_len, uint8_t sep, int use_mapq,
+                      int32_t *tid, int64_t *pos, uint8_t *rev, uint8_t *umi_out, int32_t *score, uint8_t *valid) {
+    if (rec_len < 36) return -12;
+    uint32_t block_size; memcpy(&block_size, r, 4);
+    if ((uint64_t)block_size + 4 > rec_len) return -12;
+    int32_t ref_id, p; memcpy(&ref_id, r + 4, 4); memcpy(&p, r + 8, 4);
+    uint32_t l_read_name = r[12], mapq = r[13];
+    uint16_t n_cigar, flag; memcpy(&n_cigar, r + 16, 2); memcpy(&flag, r + 18, 2);
+    uint32_t l_seq; memcpy(&l_seq, r + 20, 4);
+    const uint8_t *qname = r + 36, *cigar = qname + l_read_name;
+    const uint8_t *qual = cigar + 4 * (uint64_t)n_cigar + (l_seq + 1) / 2;
+    if ((uint64_t)(qual - r) + l_seq > rec_len) return -12;
+    *valid = (flag & 0x4) ? 0 : 1;
+    if (!*valid) return ORACLE_OK;
+    uint32_t *cig = (uint32_t *)malloc(4 * (size_t)(n_cigar ? n_cigar : 1));
+    memcpy(cig, cigar, 4 * (size_t)n_cigar);
+    *rev = (flag & 0x10) ? 1 : 0;
+    *pos = oracle_unclipped_pos(p, *rev, cig, n_cigar);
+    free(cig);
+    *tid = ref_id;
+    uint32_t name_len = l_read_name ? l_read_name - 1 : 0, q = 0;
+    while (q < name_len && qname[q] != sep) q++;
+    if (q >= name_len) return -10;
+    if (q + 1 + (uint32_t)umi_len > name_len) return -11;
+    memcpy(umi_out, qname + q + 1, umi_len);
+    *score = use_mapq ? (int32_t)mapq : oracle_avg_qual(qual, l_seq);
+    return ORACLE_OK;
+}

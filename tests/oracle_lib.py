@@ -29,6 +29,7 @@ def lib():
         _lib.oracle_avg_qual.restype = C.c_int32
         _lib.oracle_unclipped_pos.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_int]
         _lib.oracle_unclipped_pos.restype = C.c_int64
+        _lib.oracle_bam_decode.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_uint8, C.c_int] + [C.c_void_p] * 6
     return _lib
 
 
@@ -88,3 +89,16 @@ def avg_qual(q: np.ndarray) -> int:
 def unclipped_pos(pos, rev, cigar):
     arr = np.array([(l << 4) | op for op, l in cigar], dtype=np.uint32)
     return lib().oracle_unclipped_pos(pos, int(rev), _p(arr), len(arr))
+
+
+def bam_decode(rec: bytes, umi_len: int, sep: int, use_mapq: bool):
+    """oracle_bam_decode on one raw record; returns dict or raises on the reference's panic conditions."""
+    tid, score = C.c_int32(), C.c_int32()
+    pos = C.c_int64()
+    rev, valid = C.c_uint8(), C.c_uint8()
+    umi = C.create_string_buffer(umi_len)
+    rc = lib().oracle_bam_decode(rec, C.c_uint64(len(rec)), umi_len, C.c_uint8(sep), int(use_mapq), C.byref(tid), C.byref(pos),
+                                 C.byref(rev), umi, C.byref(score), C.byref(valid))
+    if rc:
+        raise RuntimeError(f"oracle_bam_decode rc={rc}")
+    return dict(valid=valid.value, tid=tid.value, pos=pos.value, rev=rev.value, umi=umi.raw, score=score.value)

@@ -1,0 +1,57 @@
+"""CPU tests of the host feed: BGZF/BAM byte handling (pure host code), the record walker exported by the C ABI
+(a host function, no GPU), and the oracle's record decode against the literal Python restatement."""
+import random
+
+import numpy as np
+
+import oracle_lib as O
+import ref_literal as R
+from bam_fixtures import make_bam
+from umigpu import bamio
+
+
+def test_bgzf_roundtrip_and_header(tmp_path):
+    rng = random.Random(1)
+    header, recs, _ = make_bam(rng, 500)
+    data = header + b"".join(recs)
+    p = str(tmp_path / "t.bam")
+    bamio.bgzf_write_all(p, data, block=4096)
+    back = bamio.bgzf_read_all(p)
+    assert back == data
+    hdr, names, first = bamio.parse_header(back)
+    assert hdr == header and names == ["chr0", "chr1", "chr2"] and first == len(header)
+
+
+def test_record_offsets_walker():
+    rng = random.Random(2)
+    header, recs, _ = make_bam(rng, 300)
+    buf = header + b"".join(recs)
+    offs, consumed = bamio.record_offsets(buf, len(header))
+    assert len(offs) == 301 and consumed == len(buf) - len(header)
+    exp = np.cumsum([len(header)] + [len(r) for r in recs])
+    assert offs.tolist() == exp.tolist()
+    # a trailing partial record is left for the next call
+    offs2, consumed2 = bamio.record_offsets(buf[:-5], len(header))
+    assert len(offs2) == 300 and consumed2 == len(buf) - len(header) - len(recs[-1])
+
+
+def test_oracle_record_decode_matches_literal():
+    rng = random.Random(3)
+    _, recs, truth = make_bam(rng, 400, umi_len=7, alphabet="ACGTN")
+    for rec, t in zip(recs, truth):
+        for use_mapq in (False, True):
+            d = O.bam_decode(rec, 7, ord("_"), use_mapq)
+            assert d["valid"] == (0 if t["unmapped"] else 1)
+            if t["unmapped"]:
+                continue
+            assert d["tid"] == t["tid"] and d["rev"] == int(t["rev"]) and d["umi"] == t["umi"].encode()
+            assert d["pos"] == R.unclipped_pos(t["pos"], t["rev"], t["cigar"])
+            assert d["score"] == (t["mapq"] if use_mapq else R.avg_qual(t["qual"]))
+
+
+def test_umi_length_autodetect():
+    rng = random.Random(4)
+    header, recs, _ = make_bam(rng, 20, umi_len=9, unmapped_rate=0.5)
+    buf = header + b"".join(recs)
+    offs, _ = bamio.record_offsets(buf, len(header))
+    assert bamio.autodetect_umi_length(buf, offs, ord("_")) == 9

@@ -1,0 +1,105 @@
+"""GPU parity of the device-side host feed (umigpu_push_bam_records): raw BAM records in, kept record numbers out,
+against the oracle's record decode + dedup; plus the file-level driver BAM -> BAM."""
+import random
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import umigpu
+from bam_fixtures import make_bam
+from umigpu import bamio
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_from_records(recs, umi_len, sep, use_mapq, algo, merge, k, p):
+    idx, tid, pos, rev, umi, score = [], [], [], [], [], []
+    for i, r in enumerate(recs):
+        d = O.bam_decode(r, umi_len, sep, use_mapq)
+        if d["valid"]:
+            idx.append(i); tid.append(d["tid"]); pos.append(d["pos"]); rev.append(d["rev"]); umi.append(d["umi"]); score.append(d["score"])
+    a = np.frombuffer(b"".join(umi), np.uint8).reshape(len(umi), umi_len)
+    kept, _, ctr = O.dedup(tid, pos, rev, a, score, algo, merge, k, p)
+    return [idx[j] for j in kept.tolist()], ctr, len(recs) - len(idx)
+
+
+@pytest.mark.parametrize("merge,alphabet,umi_len", [(umigpu.MERGE_AVGQUAL, "ACGT", 8), (umigpu.MERGE_MAPQUAL, "ACGTN", 6), (umigpu.MERGE_ANY, "ACG", 10)])
+def test_push_bam_records_matches_oracle(merge, alphabet, umi_len):
+    rng = random.Random(umi_len)
+    header, recs, _ = make_bam(rng, 6000, umi_len=umi_len, alphabet=alphabet)
+    buf = header + b"".join(recs)
+    offs, _ = bamio.record_offsets(buf, len(header))
+    for chunk in (0, 1700):
+        with umigpu.Context(umi_len, 1, 0.5, umigpu.ALGO_DIR, merge) as ctx:
+            nun = 0
+            if chunk:
+                for s in range(0, len(recs), chunk):
+                    e = min(len(recs), s + chunk)
+                    nun += bamio.push_bam(ctx, buf, offs[s: e + 1], ord("_"), s)
+            else:
+                nun = bamio.push_bam(ctx, buf, offs, ord("_"), 0)
+            kept, _, ctr = ctx.finish()
+        okept, octr, ounmapped = oracle_from_records(recs, umi_len, ord("_"), merge == umigpu.MERGE_MAPQUAL, O.ALGO_DIR, merge, 1, 0.5)
+        assert kept.astype(np.int64).tolist() == okept
+        assert nun == ounmapped == ctr["n_unmapped"] and ctr["total_reads"] == len(recs)
+        assert ctr["n_buckets"] == octr["n_buckets"] and ctr["total_umis"] == octr["total_umis"] and ctr["max_umis"] == octr["max_umis"]
+
+
+def test_bam_feed_errors_match_reference_panics():
+    hdr = bamio.make_header(["c"], [1000])
+    def run(qname, umi_len=4):
+        rec = bamio.make_record(0, 10, 0, 30, qname, [(0, 10)], 10, bytes(10))
+        buf = hdr + rec
+        offs, _ = bamio.record_offsets(buf, len(hdr))
+        with umigpu.Context(umi_len) as ctx:
+            bamio.push_bam(ctx, buf, offs)
+    with pytest.raises(umigpu.UmiGpuError, match="failed to get the umi"):
+        run(b"noseparator")
+    with pytest.raises(umigpu.UmiGpuError, match="too short"):
+        run(b"r_AC")
+    with pytest.raises(umigpu.UmiGpuError, match="Unknown character"):
+        run(b"r_ACGx")
+    run(b"r_ACGT")      # fine
+
+
+def test_mixed_ascii_and_bam_chunks():
+    rng = random.Random(9)
+    header, recs, _ = make_bam(rng, 2000, umi_len=8, unmapped_rate=0.1)
+    buf = header + b"".join(recs)
+    offs, _ = bamio.record_offsets(buf, len(header))
+    h = 900
+    # first 900 records decoded by the oracle and pushed as SoA, the rest as raw records
+    idx, tid, pos, rev, umi, score = [], [], [], [], [], []
+    for i, r in enumerate(recs[:h]):
+        d = O.bam_decode(r, 8, ord("_"), False)
+        if d["valid"]:
+            idx.append(i); tid.append(d["tid"]); pos.append(d["pos"]); rev.append(d["rev"]); umi.append(d["umi"]); score.append(d["score"])
+    with umigpu.Context(8) as ctx:
+        a = np.frombuffer(b"".join(umi), np.uint8).reshape(len(umi), 8)
+        ctx.push_reads(np.array(tid, np.int32), np.array(pos, np.int64), np.array(rev, np.uint8), a, np.array(score, np.int32), None, 0)
+        bamio.push_bam(ctx, buf, offs[h:], ord("_"), 5000)
+        kept, _, _ = ctx.finish()
+    okept, _, _ = oracle_from_records(recs, 8, ord("_"), False, O.ALGO_DIR, O.MERGE_AVGQUAL, 1, 0.5)
+    pos_of = {r: j for j, r in enumerate(idx)}
+    expect = [pos_of[r] if r < h else 5000 + (r - h) for r in okept]
+    assert kept.astype(np.int64).tolist() == expect
+
+
+@pytest.mark.parametrize("keep_unmapped", [False, True])
+def test_file_level_bam_to_bam(tmp_path, keep_unmapped):
+    rng = random.Random(12)
+    header, recs, truth = make_bam(rng, 4000, umi_len=8)
+    inp, out = str(tmp_path / "in.bam"), str(tmp_path / "out.bam")
+    bamio.bgzf_write_all(inp, header + b"".join(recs))
+    args = umigpu.Cli(input=inp, output=out, k=1, algo_str="dir", merge_str="avgqual", data_str="naive", keep_unmapped=keep_unmapped)
+    ctr = bamio.deduplicate_and_merge(args)
+    back = bamio.bgzf_read_all(out)
+    hdr, _, first = bamio.parse_header(back)
+    assert hdr == header
+    offs, _ = bamio.record_offsets(back, first)
+    got = [bytes(back[int(offs[i]): int(offs[i + 1])]) for i in range(len(offs) - 1)]
+    okept, octr, _ = oracle_from_records(recs, 8, ord("_"), False, O.ALGO_DIR, O.MERGE_AVGQUAL, 1, 0.5)
+    keep = set(okept) | ({i for i, t in enumerate(truth) if t["unmapped"]} if keep_unmapped else set())
+    assert got == [recs[i] for i in sorted(keep)]              # byte-identical records, input order
+    assert ctr["n_kept"] == len(okept) == octr["n_kept"]

@@ -91,10 +91,11 @@ struct BitmapCount { const u32 *bm; __device__ u32 operator()(u64 w) const { ret
 // push-order position -> caller's read index (umigpu_push_reads first_read_index), chunk table on the device
 struct ChunkMap {
     const u64 *start, *first; u32 n;
+    const u32 *orig;      // optional: push-order position -> record number inside its chunk (BAM pushes drop filtered records)
     __device__ __forceinline__ u64 operator()(u64 r) const {
         u32 lo = 0, hi = n;
         while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (start[mid] <= r) lo = mid; else hi = mid; }
-        return first[lo] + (r - start[lo]);
+        return first[lo] + (orig ? (u64)orig[r] : r - start[lo]);
     }
 };
 struct BitmapEmit {

@@ -22,6 +22,7 @@ struct DevScalars {
     u64 scratch2;     // pairs in scheduled tile items (direct kernel accounting)
     u32 n_cand, n_tiles;
     u32 sort_ticket, sort_err;
+    u32 bam_err, bam_valid;
 };
 
 struct KeyLayout {

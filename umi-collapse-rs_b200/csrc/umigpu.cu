@@ -2,11 +2,13 @@
 // sm_100a kernels together.  No CPU fallback: every compute step below is a kernel launch.
 #include "../../include/umigpu.h"
 
+#include "pack.cuh"
 #include <algorithm>
 #include <queue>
 #include <stdarg.h>
 #include <unordered_map>
 
+#include "bam.cuh"
 #include "cluster.cuh"
 #include "common.cuh"
 #include "group.cuh"
@@ -51,6 +53,10 @@ struct umigpu_ctx {
     u64 *h_kept = nullptr; size_t h_kept_cap = 0;       // pinned; what umigpu_result.kept_read_index points to
     u64 *h_roots = nullptr; size_t h_roots_cap = 0;     // pinned
     DevBuf d_chunks;
+    // BAM feed
+    DevBuf d_bamraw, d_bamoff, d_btid, d_bpos, d_brev, d_bumi2, d_bnmask, d_bscore, d_bvalid, d_orig;
+    bool use_orig = false;
+    u64 n_unmapped = 0, n_records = 0;
 
     cudaEvent_t ev[UMIGPU_N_STAGES][2];
     bool ev_ok[UMIGPU_N_STAGES];
@@ -145,9 +151,16 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
     if (ctx->h_kept) cudaFreeHost(ctx->h_kept);
     if (ctx->h_roots) cudaFreeHost(ctx->h_roots);
     ctx->d_chunks.release();
+    DevBuf *bb[] = {&ctx->d_bamraw, &ctx->d_bamoff, &ctx->d_btid, &ctx->d_bpos, &ctx->d_brev, &ctx->d_bumi2, &ctx->d_bnmask, &ctx->d_bscore, &ctx->d_bvalid, &ctx->d_orig};
+    for (DevBuf *b : bb) b->release();
     for (int s = 0; s < UMIGPU_N_STAGES; s++) { if (ctx->ev[s][0]) cudaEventDestroy(ctx->ev[s][0]); if (ctx->ev[s][1]) cudaEventDestroy(ctx->ev[s][1]); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(u64 n, u32 *out) {
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) out[i] = (u32)i;
 }
 
 static int init_scalars(umigpu_ctx *ctx) {
@@ -165,6 +178,7 @@ extern "C" int umigpu_reset(umigpu_ctx *ctx) {
     CK(cudaSetDevice(ctx->cfg.device));
     ctx->n_reads = 0; ctx->chunks.clear(); ctx->have_score = ctx->have_weight = -1;
     ctx->ran = false; ctx->n_unique = ctx->n_buckets = 0; ctx->n_edges = 0;
+    ctx->use_orig = false; ctx->n_unmapped = 0; ctx->n_records = 0;
     memset(&ctx->ctr, 0, sizeof ctx->ctr);
     for (int s = 0; s < UMIGPU_N_STAGES; s++) ctx->ev_ok[s] = false;
     return init_scalars(ctx);
@@ -219,8 +233,13 @@ static int push_common(umigpu_ctx *ctx, u64 n, const i32 *tid, const i64 *pos, c
     LAUNCH(umi_pack_kernel, grid_for(n, PACK_THREADS), PACK_THREADS, d_ascii, n, L, ctx->d_tid.as<i32>() + old,
            ctx->d_pos.as<i64>() + old, ctx->d_umi2.as<u64>() + old, ctx->d_nmask.as<u32>() + old, ctx->d_sc.as<DevScalars>());
     STAGE_END(UMIGPU_STAGE_PACK);
+    if (ctx->use_orig) {
+        CK(ctx->d_orig.reserve_keep(tot * 4, old * 4, s));
+        LAUNCH(iota_kernel, grid_for(n, 256), 256, n, ctx->d_orig.as<u32>() + old);
+    }
     ctx->chunks.push_back({old, n, first_index});
     ctx->n_reads = tot;
+    ctx->n_records += n;
     return UMIGPU_OK;
 }
 
@@ -248,6 +267,85 @@ static int run_scan(umigpu_ctx *ctx, F f, G g, u64 n, u32 *total_dev /* may be n
     LAUNCH((scan_tile_sums<u32, F>), (u32)ntiles, SCAN_THREADS, f, n, ts);
     LAUNCH((scan_spine<u32>), 1, 1024, ts, ntiles, total_dev);
     LAUNCH((scan_apply<u32, F, G>), (u32)ntiles, SCAN_THREADS, f, g, n, (const u32 *)ts);
+    return UMIGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BAM feed: raw records -> SoA on the device (bam.cuh)
+// ------------------------------------------------------------------------------------------------
+extern "C" int umigpu_bam_record_offsets(const uint8_t *buf, uint64_t len, uint64_t *offsets, uint64_t max_records,
+                                         uint64_t *n_records, uint64_t *consumed) {
+    if (!buf || !offsets || !n_records || !consumed) return fail(nullptr, UMIGPU_ERR_ARG, "umigpu_bam_record_offsets: null argument");
+    u64 off = 0, n = 0;
+    while (n < max_records && off + 4 <= len) {
+        u32 bs = (u32)buf[off] | ((u32)buf[off + 1] << 8) | ((u32)buf[off + 2] << 16) | ((u32)buf[off + 3] << 24);
+        if (bs < 32) return fail(nullptr, UMIGPU_ERR_ARG, "umigpu_bam_record_offsets: record %llu has block_size %u", (unsigned long long)n, bs);
+        if (off + 4 + bs > len) break;            // partial record: the caller refills and continues from *consumed
+        offsets[n++] = off;
+        off += 4 + (u64)bs;
+    }
+    offsets[n] = off;
+    *n_records = n; *consumed = off;
+    return UMIGPU_OK;
+}
+
+extern "C" int umigpu_push_bam_records(umigpu_ctx *ctx, uint64_t n, const uint8_t *records, const uint64_t *offsets,
+                                       uint8_t umi_sep, uint64_t first_read_index, uint64_t *n_unmapped_out) {
+    if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (ctx->ran) return fail(ctx, UMIGPU_ERR_STATE, "push after run: call umigpu_reset first");
+    if (n_unmapped_out) *n_unmapped_out = 0;
+    if (n == 0) return UMIGPU_OK;
+    if (!records || !offsets) return fail(ctx, UMIGPU_ERR_ARG, "null argument");
+    if (n > 0xfffffffeull || ctx->n_reads + n > 0xfffffffeull) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "more than 2^32-2 reads in one batch");
+    if (ctx->have_score < 0) { ctx->have_score = 1; ctx->have_weight = 0; }
+    if (ctx->have_score != 1 || ctx->have_weight == 1) return fail(ctx, UMIGPU_ERR_ARG, "BAM pushes cannot be mixed with score-less or weighted pushes");
+    if (!ctx->chunks.empty()) {
+        const Chunk &c = ctx->chunks.back();
+        if (first_read_index < c.first_index + c.n) return fail(ctx, UMIGPU_ERR_ARG, "chunks must be pushed in ascending read-index order");
+    }
+    cudaStream_t s = ctx->stream;
+    DevScalars *sc = ctx->d_sc.as<DevScalars>();
+    const u64 old = ctx->n_reads, tot = old + n, base = offsets[0], bytes = offsets[n] - base;
+    STAGE_BEGIN(UMIGPU_STAGE_PACK);
+    if (!ctx->use_orig) {              // earlier ASCII chunks get the identity mapping
+        CK(ctx->d_orig.reserve_keep(tot * 4, 0, s));
+        for (const Chunk &c : ctx->chunks) LAUNCH(iota_kernel, grid_for(c.n, 256), 256, c.n, ctx->d_orig.as<u32>() + c.start);
+        ctx->use_orig = true;
+    } else CK(ctx->d_orig.reserve_keep(tot * 4, old * 4, s));
+    CK(ctx->d_bamraw.reserve(bytes + 16)); CK(ctx->d_bamoff.reserve((n + 1) * 8));
+    CK(ctx->d_btid.reserve(n * 4)); CK(ctx->d_bpos.reserve(n * 8)); CK(ctx->d_brev.reserve(n)); CK(ctx->d_bumi2.reserve(n * 8));
+    CK(ctx->d_bnmask.reserve(n * 4)); CK(ctx->d_bscore.reserve(n * 4)); CK(ctx->d_bvalid.reserve(n));
+    CK(ctx->d_tid.reserve_keep(tot * 4, old * 4, s)); CK(ctx->d_pos.reserve_keep(tot * 8, old * 8, s));
+    CK(ctx->d_rev.reserve_keep(tot, old, s)); CK(ctx->d_umi2.reserve_keep(tot * 8, old * 8, s));
+    CK(ctx->d_nmask.reserve_keep(tot * 4, old * 4, s)); CK(ctx->d_score.reserve_keep(tot * 4, old * 4, s));
+    CK(cudaMemcpyAsync(ctx->d_bamraw.p, records + base, bytes, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_bamoff.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(&sc->bam_err, 0, 8, s));
+    BamDecodeOut tmp{ctx->d_btid.as<i32>(), ctx->d_bpos.as<i64>(), ctx->d_brev.as<u8>(), ctx->d_bumi2.as<u64>(), ctx->d_bnmask.as<u32>(),
+                     ctx->d_bscore.as<i32>(), ctx->d_bvalid.as<u8>()};
+    // offsets are relative to `records`; the device copy starts at records + base
+    LAUNCH(bam_decode_kernel, grid_for(n, 128), 128, n, (const u8 *)ctx->d_bamraw.p - base, (const u64 *)ctx->d_bamoff.p, (int)ctx->cfg.umi_len,
+           (u32)umi_sep, ctx->cfg.merge == UMIGPU_MERGE_MAPQUAL ? 1 : 0, tmp, &sc->bam_err);
+    BamDecodeOut dst{ctx->d_tid.as<i32>() + old, ctx->d_pos.as<i64>() + old, ctx->d_rev.as<u8>() + old, ctx->d_umi2.as<u64>() + old,
+                     ctx->d_nmask.as<u32>() + old, ctx->d_score.as<i32>() + old, nullptr};
+    int rc = run_scan(ctx, BamValid{ctx->d_bvalid.as<u8>()}, BamCompact{tmp, dst, ctx->d_orig.as<u32>() + old, &sc->bam_valid, n}, n, nullptr);
+    if (rc) return rc;
+    rc = read_scalars(ctx);
+    if (rc) return rc;
+    const u32 e = ctx->h_sc->bam_err, m = ctx->h_sc->bam_valid;
+    if (e & BAM_ERR_TRUNC) return fail(ctx, UMIGPU_ERR_ARG, "truncated or malformed BAM record");
+    if (e & BAM_ERR_NO_SEP) return fail(ctx, UMIGPU_ERR_ARG, "failed to get the umi");                         // utils/read.rs:109
+    if (e & BAM_ERR_SHORT) return fail(ctx, UMIGPU_ERR_ARG, "read name too short for a UMI of %u bases", ctx->cfg.umi_len);
+    if (e & BAM_ERR_BAD_BASE) return fail(ctx, UMIGPU_ERR_BAD_BASE, "Unknown character in UMI sequence");      // utils/mod.rs:78
+    if (m) LAUNCH(range_reduce_kernel, grid_for(m, 256), 256, (u64)m, (const i32 *)(ctx->d_tid.as<i32>() + old), (const i64 *)(ctx->d_pos.as<i64>() + old),
+                  (const u32 *)(ctx->d_nmask.as<u32>() + old), sc);
+    STAGE_END(UMIGPU_STAGE_PACK);
+    if (m) ctx->chunks.push_back({old, m, first_read_index});
+    ctx->n_reads = old + m;
+    ctx->n_records += n;
+    ctx->n_unmapped += n - m;
+    if (n_unmapped_out) *n_unmapped_out = n - m;
     return UMIGPU_OK;
 }
 
@@ -303,7 +401,8 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     const u64 n = ctx->n_reads;
     const umigpu_config &cfg = ctx->cfg;
     memset(&ctx->ctr, 0, sizeof ctx->ctr);
-    ctx->ctr.total_reads = n;
+    ctx->ctr.total_reads = ctx->n_records;          // deduplicate_sam.rs:100 counts every record, mapped or not
+    ctx->ctr.n_unmapped = ctx->n_unmapped;
     ctx->ran = true;
     if (n == 0) return UMIGPU_OK;
     DevScalars *sc = ctx->d_sc.as<DevScalars>();
@@ -519,7 +618,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
         CK(cudaMemcpyAsync(ctx->d_chunks.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));     // tab is a stack-lifetime pageable buffer
     }
-    ChunkMap cm{ctx->d_chunks.as<u64>(), ctx->d_chunks.as<u64>() + nch, nch};
+    ChunkMap cm{ctx->d_chunks.as<u64>(), ctx->d_chunks.as<u64>() + nch, nch, ctx->use_orig ? ctx->d_orig.as<u32>() : (const u32 *)nullptr};
     rc = run_scan(ctx, BitmapCount{ctx->d_bitmap.as<u32>()}, BitmapEmit{ctx->d_bitmap.as<u32>(), ctx->d_kept.as<u64>(), n_words, sc, cm}, n_words, nullptr);
     if (rc) return rc;
     if (want_labels) {

@@ -22,7 +22,7 @@ SYMBOLS = [
     "umigpu_push_reads", "umigpu_push_reads_device", "umigpu_run", "umigpu_fetch", "umigpu_finish",
     "umigpu_get_counters", "umigpu_cluster_bucket", "umigpu_remove_near", "umigpu_neighbours",
     "umigpu_avg_qual", "umigpu_stage_ms", "umigpu_launch_count", "umigpu_result_free",
-    "umigpu_shard_plan", "umigpu_int_peak",
+    "umigpu_shard_plan", "umigpu_int_peak", "umigpu_push_bam_records", "umigpu_bam_record_offsets",
 ]
 
 
@@ -35,7 +35,7 @@ class Config(C.Structure):
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "total_reads", "n_buckets", "total_umis", "max_umis", "n_kept", "unordered_pairs",
-        "pairs_evaluated", "n_edges", "n_tile_items", "n_tile_candidates", "n_sweeps")]
+        "pairs_evaluated", "n_edges", "n_tile_items", "n_tile_candidates", "n_sweeps", "n_unmapped")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -74,6 +74,8 @@ def load() -> C.CDLL:
     lib.umigpu_reset.argtypes = [p]
     for name in ("umigpu_push_reads", "umigpu_push_reads_device"):
         getattr(lib, name).argtypes = [p, u64, p, p, p, p, p, p, u64]
+    lib.umigpu_push_bam_records.argtypes = [p, u64, p, p, C.c_uint8, u64, C.POINTER(u64)]
+    lib.umigpu_bam_record_offsets.argtypes = [p, u64, p, u64, C.POINTER(u64), C.POINTER(u64)]
     lib.umigpu_run.argtypes = [p]
     lib.umigpu_fetch.argtypes = [p, C.POINTER(Result)]
     lib.umigpu_finish.argtypes = [p, C.POINTER(Result)]

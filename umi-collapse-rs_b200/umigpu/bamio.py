@@ -1,0 +1,147 @@
+"""Minimal BAM / BGZF reader and writer (zlib only — no htslib in this image) and the file-level driver that
+mirrors DeduplicateInterface::deduplicate_and_merge (src/deduplicate_sam.rs:72-269) on top of the device feed
+umigpu_push_bam_records.  Host code here only moves bytes: BGZF inflate/deflate, header parsing and writing the
+surviving records; every per-record computation (unclipped position, UMI extraction, score, filter) and the
+whole clustering run on the GPU."""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import struct
+import zlib
+
+import numpy as np
+
+from . import _lib as L
+from .api import Cli, Context, resolve_cli
+
+_EOF_BLOCK = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def bgzf_read_all(path: str) -> bytes:
+    """BGZF is a series of gzip members; the gzip module reads them all."""
+    with gzip.open(path, "rb") as f:
+        return f.read()
+
+
+def bgzf_write_all(path: str, data: bytes, level: int = 1, block: int = 0xff00):
+    with open(path, "wb") as f:
+        for s in range(0, len(data), block):
+            chunk = data[s: s + block]
+            co = zlib.compressobj(level, zlib.DEFLATED, -15)
+            comp = co.compress(chunk) + co.flush()
+            bsize = len(comp) + 25
+            f.write(struct.pack("<BBBBIBBHBBHH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6, 66, 67, 2, bsize))
+            f.write(comp)
+            f.write(struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+        f.write(_EOF_BLOCK)
+
+
+def parse_header(buf: bytes):
+    """Returns (header_bytes, reference names, offset of the first alignment record)."""
+    if buf[:4] != b"BAM\x01":
+        raise ValueError("not a BAM stream")
+    l_text, = struct.unpack_from("<i", buf, 4)
+    off = 8 + l_text
+    n_ref, = struct.unpack_from("<i", buf, off)
+    off += 4
+    names = []
+    for _ in range(n_ref):
+        l_name, = struct.unpack_from("<i", buf, off)
+        names.append(buf[off + 4: off + 4 + l_name - 1].decode())
+        off += 4 + l_name + 4
+    return buf[:off], names, off
+
+
+def make_header(ref_names, ref_lens, text: str = "@HD\tVN:1.6\tSO:coordinate\n") -> bytes:
+    out = [b"BAM\x01", struct.pack("<i", len(text)), text.encode(), struct.pack("<i", len(ref_names))]
+    for nme, ln in zip(ref_names, ref_lens):
+        b = nme.encode() + b"\0"
+        out += [struct.pack("<i", len(b)), b, struct.pack("<i", ln)]
+    return b"".join(out)
+
+
+def make_record(tid: int, pos: int, flag: int, mapq: int, qname: bytes, cigar, seq_len: int, qual: bytes) -> bytes:
+    """cigar = [(op, len)] with op codes M0 I1 D2 N3 S4 H5 P6 =7 X8; sequence bases are irrelevant to the path (all A)."""
+    name = qname + b"\0"
+    body = struct.pack("<iiBBHHHiiii", tid, pos, len(name), mapq, 4680, len(cigar), flag, seq_len, -1, -1, 0)
+    body += name + b"".join(struct.pack("<I", (ln << 4) | op) for op, ln in cigar)
+    body += bytes((seq_len + 1) // 2) + qual
+    return struct.pack("<i", len(body)) + body
+
+
+def record_offsets(buf, start: int = 0):
+    """umigpu_bam_record_offsets over buf[start:]; offsets are relative to buf."""
+    lib = L.load()
+    arr = np.frombuffer(buf, dtype=np.uint8)
+    n_max = max(1, (len(arr) - start) // 36 + 1)
+    offs = np.zeros(n_max + 1, np.uint64)
+    n, consumed = C.c_uint64(), C.c_uint64()
+    L.check(lib.umigpu_bam_record_offsets(arr[start:].ctypes.data_as(C.c_void_p), len(arr) - start, offs.ctypes.data_as(C.c_void_p), n_max,
+                                          C.byref(n), C.byref(consumed)))
+    return offs[: n.value + 1] + np.uint64(start), int(consumed.value)
+
+
+def push_bam(ctx: Context, buf, offsets: np.ndarray, umi_sep: int = ord("_"), first_read_index: int = 0) -> int:
+    """umigpu_push_bam_records; returns the number of records dropped by the unmapped filter."""
+    arr = np.frombuffer(buf, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.uint64)
+    nun = C.c_uint64()
+    L.check(ctx._lib.umigpu_push_bam_records(ctx._h, len(offsets) - 1, arr.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p),
+                                             umi_sep, first_read_index, C.byref(nun)), ctx._h)
+    ctx._keepalive.append((arr, offsets))
+    return int(nun.value)
+
+
+def autodetect_umi_length(buf, offsets, sep: int) -> int:
+    """utils/read.rs:65-75,87-94 on the first mapped record: the run of [ATCGN] (caseless) after the first
+    separator of the read name."""
+    for i in range(len(offsets) - 1):
+        o = int(offsets[i])
+        flag, = struct.unpack_from("<H", buf, o + 18)
+        if flag & 4:
+            continue
+        l_name = buf[o + 12]
+        name = bytes(buf[o + 36: o + 36 + l_name - 1])
+        p = name.find(bytes([sep]))
+        if p < 0:
+            raise ValueError("failed to get the umi")
+        n = 0
+        while p + 1 + n < len(name) and name[p + 1 + n: p + 2 + n].upper() in (b"A", b"C", b"G", b"T", b"N"):
+            n += 1
+        return n
+    return 0
+
+
+def deduplicate_and_merge(args: Cli, device: int = 0, chunk_records: int = 1 << 22) -> dict:
+    """BAM in -> BAM out, every CLI flag of the reference that reaches the single-end path honoured
+    (-k -u -p --umi_sep --algo --merge --keep-unmapped; --data ignored like the reference; --paired unsupported).
+    Survivors are written in input order (canonical), unmapped reads too with --keep-unmapped
+    (deduplicate_sam.rs:102-108)."""
+    algo, merge = resolve_cli(args)
+    if args.paired:
+        raise NotImplementedError("--paired is outside the scope of this path (SURVEY §2)")
+    buf = bgzf_read_all(args.input)
+    header, _names, first = parse_header(buf)
+    offsets, consumed = record_offsets(buf, first)
+    n = len(offsets) - 1
+    umi_len = args.umi_length or autodetect_umi_length(buf, offsets, args.umi_separator)
+    if n == 0 or umi_len == 0:
+        bgzf_write_all(args.output, header)
+        return dict(total_reads=n, n_kept=0)
+    with Context(umi_len, args.k, args.percentage, algo, merge, device) as ctx:
+        for s in range(0, n, chunk_records):
+            e = min(n, s + chunk_records)
+            push_bam(ctx, buf, offsets[s: e + 1], args.umi_separator, s)
+        kept, _, ctr = ctx.finish()
+    keep = np.zeros(n, bool)
+    keep[kept.astype(np.int64)] = True
+    if args.keep_unmapped:
+        flags = np.array([struct.unpack_from("<H", buf, int(o) + 18)[0] for o in offsets[:-1]], dtype=np.uint16)
+        keep |= (flags & 4) != 0
+    out = [header]
+    mv = memoryview(buf)
+    for i in np.nonzero(keep)[0]:
+        out.append(mv[int(offsets[i]): int(offsets[i + 1])])
+    bgzf_write_all(args.output, b"".join(out))
+    return ctr
