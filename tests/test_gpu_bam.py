@@ -103,3 +103,62 @@ def test_file_level_bam_to_bam(tmp_path, keep_unmapped):
     keep = set(okept) | ({i for i, t in enumerate(truth) if t["unmapped"]} if keep_unmapped else set())
     assert got == [recs[i] for i in sorted(keep)]              # byte-identical records, input order
     assert ctr["n_kept"] == len(okept) == octr["n_kept"]
+
+
+def _cli(*argv):
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "umi-collapse-rs_b200", "host", "umicollapse_gpu")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe)])
+    return subprocess.run([exe, *argv], capture_output=True, text=True, timeout=300)
+
+
+@pytest.mark.parametrize("algo,merge", [("dir", "avgqual"), ("adj", "mapqual"), ("cc", "any")])
+def test_cpp_cli_bam_matches_oracle(tmp_path, algo, merge):
+    """The compiled C++ twin of the reference CLI: same flags as the README example of the reference
+    (--mode bam --data naive --merge avgqual --num-threads N), records byte-identical, input order."""
+    rng = random.Random(21)
+    header, recs, truth = make_bam(rng, 5000, umi_len=8)
+    inp, out = str(tmp_path / "in.bam"), str(tmp_path / "out.bam")
+    bamio.bgzf_write_all(inp, header + b"".join(recs))
+    r = _cli("--mode", "bam", "-i", inp, "-o", out, "--data", "naive", "--algo", algo, "--merge", merge, "-k", "1", "--num-threads", "4")
+    assert r.returncode == 0, r.stderr
+    back = bamio.bgzf_read_all(out)
+    hdr, _, first = bamio.parse_header(back)
+    offs, _ = bamio.record_offsets(back, first)
+    got = [bytes(back[int(offs[i]): int(offs[i + 1])]) for i in range(len(offs) - 1)]
+    oalgo = {"dir": O.ALGO_DIR, "adj": O.ALGO_ADJ_REF, "cc": O.ALGO_CC}[algo]
+    omerge = {"any": O.MERGE_ANY, "avgqual": O.MERGE_AVGQUAL, "mapqual": O.MERGE_MAPQUAL}[merge]
+    okept, octr, ounm = oracle_from_records(recs, 8, ord("_"), merge == "mapqual", oalgo, omerge, 1, 0.5)
+    assert hdr == header and got == [recs[i] for i in okept]
+    # the reference's end-of-run counters (deduplicate_sam.rs:243-267)
+    assert f"Number of input reads: {len(recs)}" in r.stderr
+    assert f"Number of removed unmapped reads: {ounm}" in r.stderr
+    assert f"Number of unique alignment positions: {octr['n_buckets']}" in r.stderr
+    assert f"Number of UMIs: {octr['total_umis']}" in r.stderr
+    assert f"Number of reads after deduplicating: {octr['n_kept']}" in r.stderr
+
+
+def test_cpp_cli_fastq_single_bucket(tmp_path):
+    """BASELINE config 4 shape: fastq, one global bucket (no reference behaviour: self-consistent with the oracle)."""
+    rng = random.Random(5)
+    n, L = 20000, 8
+    umis = ["".join(rng.choice("ACGT") for _ in range(L)) for _ in range(n)]
+    quals = ["".join(chr(33 + rng.randrange(2, 41)) for _ in range(30)) for _ in range(n)]
+    recs = [f"@r{i}_{umis[i]} extra\n{'A' * 30}\n+\n{quals[i]}\n" for i in range(n)]
+    inp, out = str(tmp_path / "in.fastq"), str(tmp_path / "out.fastq")
+    open(inp, "w").write("".join(recs))
+    r = _cli("--mode", "fastq", "-i", inp, "-o", out, "-k", "1", "--num-threads", "4")
+    assert r.returncode == 0, r.stderr
+    score = [sum(ord(c) - 33 for c in q) // len(q) for q in quals]
+    a = np.frombuffer("".join(umis).encode(), np.uint8).reshape(n, L)
+    okept, _, _ = O.dedup([0] * n, [0] * n, [0] * n, a, score, O.ALGO_DIR, O.MERGE_AVGQUAL, 1, 0.5)
+    assert open(out).read() == "".join(recs[i] for i in okept.tolist())
+
+
+def test_cpp_cli_rejects_like_the_reference():
+    r = _cli("-i", "a", "-o", "b", "--tag", "--two-pass")
+    assert r.returncode != 0 and "Cannot track clusters with the two pass algorithm!" in r.stderr
+    r = _cli("-i", "a", "-o", "b", "--paired", "--keep-unmapped")
+    assert r.returncode != 0 and "Cannot keep unmapped reads with paired-end reads!" in r.stderr

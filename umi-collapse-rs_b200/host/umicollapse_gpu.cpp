@@ -1,0 +1,308 @@
+// umicollapse_gpu — C++ twin of the umi-collapse-rs command line on top of libumigpu's C ABI.
+//
+// The reference host is Rust (clap + rust-htslib); this image has no Rust toolchain, so this program is the
+// compiled, tested stand-in for it: same flags (src/cli.rs:7-77), same defaults and validation
+// (src/main.rs:33-47), same dispatch (src/main.rs:49-92), same end-of-run counters
+// (src/deduplicate_sam.rs:243-267).  Host code only moves bytes (BGZF inflate/deflate with zlib, header
+// parsing, writing the surviving records); every per-record computation and the clustering run on the GPU.
+//
+// Differences from the reference, all deliberate: output is in input order, --algo cc
+// works, --mode fastq works (the reference's is an empty TODO, main.rs:49-51), --paired and --tag are refused.
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/umigpu.h"
+
+struct Cli {                                   // src/cli.rs:7-77 (same names, same defaults)
+    std::string mode = "bam", input, output, algo_str = "dir", merge_str, data_str = "ngrambktree";
+    int k = 1; unsigned umi_length = 0; float percentage = 0.5f; unsigned num_threads = 1; unsigned char umi_separator = '_';
+    bool two_pass = false, paired = false, remove_unpaired = false, remove_chimeric = false, keep_unmapped = false, track_clusters = false;
+    int device = 0;
+};
+
+[[noreturn]] static void die(const std::string &msg) { fprintf(stderr, "umicollapse_gpu: %s\n", msg.c_str()); exit(2); }
+static void check(int rc, umigpu_ctx *ctx, const char *what) {
+    if (rc != 0) die(std::string(what) + " failed (" + std::to_string(rc) + "): " + umigpu_last_error(ctx));   // the reference panics
+}
+
+static Cli parse(int argc, char **argv) {
+    Cli a;
+    auto need = [&](int &i) -> const char * { if (i + 1 >= argc) die(std::string("missing value for ") + argv[i]); return argv[++i]; };
+    for (int i = 1; i < argc; i++) {
+        std::string s = argv[i];
+        if (s == "-m" || s == "--mode") a.mode = need(i);
+        else if (s == "-i") a.input = need(i);
+        else if (s == "-o") a.output = need(i);
+        else if (s == "-k") a.k = atoi(need(i));
+        else if (s == "-u") a.umi_length = (unsigned)atoi(need(i));
+        else if (s == "-p") a.percentage = (float)atof(need(i));
+        else if (s == "--num-threads") a.num_threads = (unsigned)atoi(need(i));
+        else if (s == "--umi_sep") { const char *v = need(i); a.umi_separator = (strlen(v) == 1 && (v[0] < '0' || v[0] > '9')) ? (unsigned char)v[0] : (unsigned char)atoi(v); }
+        else if (s == "--algo") a.algo_str = need(i);
+        else if (s == "--merge") a.merge_str = need(i);
+        else if (s == "--data") a.data_str = need(i);
+        else if (s == "--two-pass") a.two_pass = true;
+        else if (s == "--paired") a.paired = true;
+        else if (s == "--remove-unpaired") a.remove_unpaired = true;
+        else if (s == "--remove-chimeric") a.remove_chimeric = true;
+        else if (s == "--keep-unmapped") a.keep_unmapped = true;
+        else if (s == "--tag") a.track_clusters = true;
+        else if (s == "--device") a.device = atoi(need(i));
+        else die("unexpected argument '" + s + "'");
+    }
+    if (a.input.empty() || a.output.empty()) die("the following required arguments were not provided: -i <INPUT_FILE> -o <OUITPUT_FILE>");
+    if (a.merge_str.empty()) a.merge_str = a.mode == "fastq" ? "avgqual" : "mapqual";                 // main.rs:33-39
+    if (a.track_clusters && a.two_pass) die("Cannot track clusters with the two pass algorithm!");    // main.rs:41-43
+    if (a.paired && a.keep_unmapped) die("Cannot keep unmapped reads with paired-end reads!");        // main.rs:45-47
+    return a;
+}
+
+static std::vector<uint8_t> read_file(const std::string &p) {
+    FILE *f = fopen(p.c_str(), "rb");
+    if (!f) die("Invalid input path: " + p);
+    fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> v((size_t)n);
+    if (n && fread(v.data(), 1, (size_t)n, f) != (size_t)n) die("short read on " + p);
+    fclose(f);
+    return v;
+}
+
+template <class F> static void parallel_for(size_t n, unsigned threads, F f) {
+    threads = std::max(1u, std::min<unsigned>(threads, (unsigned)std::max<size_t>(1, n)));
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> ts;
+    for (unsigned t = 0; t < threads; t++) ts.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < n;) f(i); });
+    for (auto &t : ts) t.join();
+}
+
+// ---- BGZF (SAM/BAM specification §4.1): independent gzip members with a BC extra field ----
+static std::vector<uint8_t> bgzf_inflate(const std::vector<uint8_t> &in, unsigned threads) {
+    struct Blk { size_t off, csize, usize, uoff; };
+    std::vector<Blk> blks;
+    size_t off = 0, utotal = 0;
+    while (off + 18 <= in.size()) {
+        if (in[off] != 0x1f || in[off + 1] != 0x8b) die("not a BGZF stream");
+        unsigned xlen = in[off + 10] | (in[off + 11] << 8);
+        size_t x = off + 12, xend = x + xlen, bsize = 0;
+        while (x + 4 <= xend) { unsigned slen = in[x + 2] | (in[x + 3] << 8); if (in[x] == 'B' && in[x + 1] == 'C') bsize = (size_t)(in[x + 4] | (in[x + 5] << 8)) + 1; x += 4 + slen; }
+        if (!bsize || off + bsize > in.size()) die("corrupt BGZF block");
+        size_t usize = in[off + bsize - 4] | (in[off + bsize - 3] << 8) | (in[off + bsize - 2] << 16) | ((size_t)in[off + bsize - 1] << 24);
+        blks.push_back({off + 12 + xlen, bsize - 12 - xlen - 8, usize, utotal});
+        utotal += usize; off += bsize;
+    }
+    std::vector<uint8_t> out(utotal);
+    parallel_for(blks.size(), threads, [&](size_t i) {
+        const Blk &b = blks[i];
+        if (!b.usize) return;
+        z_stream z; memset(&z, 0, sizeof z);
+        if (inflateInit2(&z, -15) != Z_OK) die("inflateInit2");
+        z.next_in = const_cast<Bytef *>(in.data() + b.off); z.avail_in = (uInt)b.csize;
+        z.next_out = out.data() + b.uoff; z.avail_out = (uInt)b.usize;
+        if (inflate(&z, Z_FINISH) != Z_STREAM_END) die("inflate failed");
+        inflateEnd(&z);
+    });
+    return out;
+}
+
+static void bgzf_write(const std::string &path, const std::vector<const uint8_t *> &ptr, const std::vector<size_t> &len, unsigned threads) {
+    // gather into one stream, cut into 0xff00-byte blocks, deflate the blocks in parallel
+    size_t total = 0; for (size_t l : len) total += l;
+    std::vector<uint8_t> data(total);
+    { size_t o = 0; for (size_t i = 0; i < ptr.size(); i++) { memcpy(data.data() + o, ptr[i], len[i]); o += len[i]; } }
+    const size_t B = 0xff00, nb = (total + B - 1) / B;
+    std::vector<std::vector<uint8_t>> comp(nb);
+    parallel_for(nb, threads, [&](size_t i) {
+        size_t s = i * B, n = std::min(B, total - s);
+        std::vector<uint8_t> &c = comp[i];
+        c.resize(compressBound((uLong)n) + 32);
+        z_stream z; memset(&z, 0, sizeof z);
+        if (deflateInit2(&z, 1, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) die("deflateInit2");
+        z.next_in = data.data() + s; z.avail_in = (uInt)n; z.next_out = c.data() + 18; z.avail_out = (uInt)(c.size() - 26);
+        if (deflate(&z, Z_FINISH) != Z_STREAM_END) die("deflate failed");
+        size_t cs = z.total_out; deflateEnd(&z);
+        const uint8_t h[12] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0};
+        memcpy(c.data(), h, 12); c[12] = 'B'; c[13] = 'C'; c[14] = 2; c[15] = 0;
+        size_t bsize = cs + 26 - 1; c[16] = bsize & 0xff; c[17] = (bsize >> 8) & 0xff;
+        uint32_t crc = (uint32_t)crc32(crc32(0, nullptr, 0), data.data() + s, (uInt)n), isz = (uint32_t)n;
+        memcpy(c.data() + 18 + cs, &crc, 4); memcpy(c.data() + 22 + cs, &isz, 4);
+        c.resize(cs + 26);
+    });
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) die("cannot open output " + path);
+    for (auto &c : comp) fwrite(c.data(), 1, c.size(), f);
+    static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    fwrite(eof, 1, 28, f);
+    fclose(f);
+}
+
+static int algo_code(const Cli &a) {                       // main.rs:52-92 (+ cc, which the reference only documents)
+    if (a.algo_str == "dir") return UMIGPU_ALGO_DIR;
+    if (a.algo_str == "adj") return UMIGPU_ALGO_ADJ;
+    if (a.algo_str == "cc") return UMIGPU_ALGO_CC;
+    if (a.algo_str == "adj-upstream") return UMIGPU_ALGO_ADJ_UPSTREAM;
+    die("Invalid algorithm combination: " + a.algo_str + " , " + a.merge_str + " and " + a.data_str);
+}
+static int merge_code(const Cli &a) {
+    if (a.merge_str == "any") return UMIGPU_MERGE_ANY;
+    if (a.merge_str == "avgqual") return UMIGPU_MERGE_AVGQUAL;
+    if (a.merge_str == "mapqual") return UMIGPU_MERGE_MAPQUAL;
+    die("Invalid algorithm combination: " + a.algo_str + " , " + a.merge_str + " and " + a.data_str);
+}
+
+static void report(const umigpu_counters &c, uint64_t unmapped) {      // deduplicate_sam.rs:243-267
+    fprintf(stderr, "Number of input reads: %llu\n", (unsigned long long)c.total_reads);
+    fprintf(stderr, "Number of removed unmapped reads: %llu\n", (unsigned long long)unmapped);
+    fprintf(stderr, "Number of unique alignment positions: %llu\n", (unsigned long long)c.n_buckets);
+    fprintf(stderr, "Number of UMIs: %llu\n", (unsigned long long)c.total_umis);
+    fprintf(stderr, "Average number of UMIs per alignment position: %g\n", c.n_buckets ? (double)c.total_umis / (double)c.n_buckets : 0.0);
+    fprintf(stderr, "Max number of UMIs over all alignment positions: %llu\n", (unsigned long long)c.max_umis);
+    fprintf(stderr, "Number of reads after deduplicating: %llu\n", (unsigned long long)c.n_kept);
+}
+
+static umigpu_ctx *make_ctx(const Cli &a, unsigned umi_len) {
+    umigpu_config cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.k = a.k; cfg.percentage = a.percentage; cfg.algo = algo_code(a); cfg.merge = merge_code(a); cfg.umi_len = umi_len; cfg.device = a.device;
+    umigpu_ctx *ctx = nullptr;
+    check(umigpu_create(&cfg, &ctx), nullptr, "umigpu_create");
+    return ctx;
+}
+
+// ---- --mode bam ----
+static int run_bam(const Cli &a) {
+    std::vector<uint8_t> raw = read_file(a.input);
+    std::vector<uint8_t> buf = bgzf_inflate(raw, a.num_threads);
+    std::vector<uint8_t>().swap(raw);
+    if (buf.size() < 12 || memcmp(buf.data(), "BAM\1", 4) != 0) die("Invalid input path: not a BAM file");
+    int32_t l_text, n_ref; memcpy(&l_text, buf.data() + 4, 4);
+    size_t off = 8 + (size_t)l_text; memcpy(&n_ref, buf.data() + off, 4); off += 4;
+    for (int r = 0; r < n_ref; r++) { int32_t l; memcpy(&l, buf.data() + off, 4); off += 4 + (size_t)l + 4; }
+    const size_t first = off;
+    std::vector<uint64_t> offs((buf.size() - first) / 36 + 2);
+    uint64_t n = 0, consumed = 0;
+    check(umigpu_bam_record_offsets(buf.data() + first, buf.size() - first, offs.data(), offs.size() - 1, &n, &consumed), nullptr, "umigpu_bam_record_offsets");
+    // -u 0: autodetect from the first mapped read (utils/read.rs:65-75,87-94)
+    unsigned umi_len = a.umi_length;
+    for (uint64_t i = 0; i < n && umi_len == 0; i++) {
+        const uint8_t *r = buf.data() + first + offs[i];
+        unsigned flag = r[18] | (r[19] << 8);
+        if (flag & 4) continue;
+        unsigned l_name = r[12]; const uint8_t *name = r + 36; unsigned len = l_name ? l_name - 1 : 0, p = 0;
+        while (p < len && name[p] != a.umi_separator) p++;
+        if (p >= len) die("failed to get the umi");
+        for (unsigned q = p + 1; q < len && strchr("ACGTNacgtn", name[q]); q++) umi_len++;
+        break;
+    }
+    std::vector<const uint8_t *> optr{buf.data()}; std::vector<size_t> olen{first};
+    umigpu_counters ctr; memset(&ctr, 0, sizeof ctr);
+    uint64_t unmapped = 0;
+    if (n && umi_len) {
+        umigpu_ctx *ctx = make_ctx(a, umi_len);
+        const uint64_t CH = 1ull << 22;
+        for (uint64_t s = 0; s < n; s += CH) {
+            uint64_t e = std::min(n, s + CH), nun = 0;
+            check(umigpu_push_bam_records(ctx, e - s, buf.data() + first, offs.data() + s, a.umi_separator, s, &nun), ctx, "umigpu_push_bam_records");
+            unmapped += nun;
+        }
+        umigpu_result res;
+        check(umigpu_finish(ctx, &res), ctx, "umigpu_finish");
+        ctr = res.counters;
+        // merge kept indices with (optionally) the unmapped records, input order
+        uint64_t kpos = 0;
+        for (uint64_t i = 0; i < n; i++) {
+            const uint8_t *r = buf.data() + first + offs[i];
+            bool keep = kpos < res.n_kept && res.kept_read_index[kpos] == i;
+            if (keep) kpos++;
+            else if (a.keep_unmapped && ((r[18] | (r[19] << 8)) & 4)) keep = true;          // deduplicate_sam.rs:104-106
+            if (keep) { optr.push_back(r); olen.push_back(offs[i + 1] - offs[i]); }
+        }
+        bgzf_write(a.output, optr, olen, a.num_threads);
+        umigpu_destroy(ctx);
+    } else {
+        bgzf_write(a.output, optr, olen, a.num_threads);
+        ctr.total_reads = n;
+    }
+    report(ctr, unmapped);
+    return 0;
+}
+
+// ---- --mode fastq: one global bucket (BASELINE config 4); the reference's fastq arm is an empty TODO (main.rs:49-51) ----
+static int run_fastq(const Cli &a) {
+    std::vector<uint8_t> raw = read_file(a.input);
+    std::vector<uint8_t> buf;
+    if (raw.size() > 2 && raw[0] == 0x1f && raw[1] == 0x8b) {           // gzip'ed FASTQ
+        gzFile g = gzopen(a.input.c_str(), "rb");
+        if (!g) die("Invalid input path");
+        std::vector<uint8_t> tmp(1 << 22); int got;
+        while ((got = gzread(g, tmp.data(), (unsigned)tmp.size())) > 0) buf.insert(buf.end(), tmp.begin(), tmp.begin() + got);
+        gzclose(g);
+    } else buf.swap(raw);
+    // record = 4 lines: @header, sequence, +, quality
+    std::vector<size_t> rec_start, hdr_end, qual_start, qual_end;
+    size_t p = 0, N = buf.size();
+    auto eol = [&](size_t s) { const void *q = memchr(buf.data() + s, '\n', N - s); return q ? (size_t)((const uint8_t *)q - buf.data()) : N; };
+    while (p < N) {
+        size_t e1 = eol(p); if (e1 >= N) break; size_t e2 = eol(e1 + 1); if (e2 >= N) break; size_t e3 = eol(e2 + 1); if (e3 >= N) break; size_t e4 = eol(e3 + 1);
+        if (buf[p] != '@') die("malformed FASTQ record");
+        rec_start.push_back(p); hdr_end.push_back(e1); qual_start.push_back(e3 + 1); qual_end.push_back(e4);
+        p = e4 + 1;
+    }
+    const size_t n = rec_start.size();
+    unsigned umi_len = a.umi_length;
+    if (n && !umi_len) {
+        size_t s = rec_start[0] + 1, e = hdr_end[0], q = s;
+        while (q < e && buf[q] != a.umi_separator) q++;
+        if (q >= e) die("failed to get the umi");
+        for (size_t t = q + 1; t < e && strchr("ACGTNacgtn", buf[t]); t++) umi_len++;
+    }
+    std::vector<const uint8_t *> optr; std::vector<size_t> olen;
+    umigpu_counters ctr; memset(&ctr, 0, sizeof ctr);
+    if (n && umi_len) {
+        std::vector<int32_t> tid(n, 0), score(n); std::vector<int64_t> pos(n, 0); std::vector<uint8_t> rev(n, 0), umi(n * (size_t)umi_len);
+        parallel_for(n, a.num_threads, [&](size_t i) {
+            size_t s = rec_start[i] + 1, e = hdr_end[i], q = s;
+            while (q < e && buf[q] != a.umi_separator) q++;
+            if (q >= e) die("failed to get the umi");
+            if (q + 1 + umi_len > e) die("read name too short for the UMI");
+            memcpy(umi.data() + i * umi_len, buf.data() + q + 1, umi_len);
+            // avg_qual with the reference's f32 formula (utils/read.rs:56-63) on phred = byte - 33
+            size_t ql = qual_end[i] - qual_start[i]; if (ql && buf[qual_end[i] - 1] == '\r') ql--;
+            float sum = 0.0f; for (size_t t = 0; t < ql; t++) sum += (float)(buf[qual_start[i] + t] - 33);
+            float qv = sum / (float)ql; score[i] = (qv != qv) ? 0 : (int32_t)qv;
+        });
+        umigpu_ctx *ctx = make_ctx(a, umi_len);
+        check(umigpu_push_reads(ctx, n, tid.data(), pos.data(), rev.data(), umi.data(), score.data(), nullptr, 0), ctx, "umigpu_push_reads");
+        umigpu_result res;
+        check(umigpu_finish(ctx, &res), ctx, "umigpu_finish");
+        ctr = res.counters;
+        for (uint64_t j = 0; j < res.n_kept; j++) { size_t i = (size_t)res.kept_read_index[j]; optr.push_back(buf.data() + rec_start[i]); olen.push_back(std::min(N, qual_end[i] + 1) - rec_start[i]); }
+        FILE *f = fopen(a.output.c_str(), "wb"); if (!f) die("cannot open output " + a.output);
+        for (size_t j = 0; j < optr.size(); j++) fwrite(optr[j], 1, olen[j], f);
+        fclose(f);
+        umigpu_destroy(ctx);
+    } else { FILE *f = fopen(a.output.c_str(), "wb"); if (f) fclose(f); ctr.total_reads = n; }
+    report(ctr, 0);
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    Cli a = parse(argc, argv);
+    auto t0 = std::chrono::steady_clock::now();
+    if (a.paired) die("--paired is outside the scope of the GPU path (SURVEY.md §2); use the reference's CPU path");
+    if (a.track_clusters) die("--tag: the reference collects cluster trackers and writes nothing (deduplicate_sam.rs:236-239); not offered here");
+    int rc;
+    if (a.mode == "fastq") rc = run_fastq(a);
+    else if (a.mode == "bam" || a.mode == "sam") rc = run_bam(a);
+    else die("unknown mode " + a.mode);
+    fprintf(stderr, "UMI collapsing finished in %.3f seconds\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());   // main.rs:97-102
+    return rc;
+}
