@@ -54,6 +54,8 @@ extern "C" {
 #define UMIGPU_FLAG_LABELS        1u  /* also produce the per-read cluster root (ClusterTracker, --tag) */
 #define UMIGPU_FLAG_NO_CULL       2u  /* evaluate every tile pair (disable exact prefix culling)        */
 #define UMIGPU_FLAG_KERNEL_DIRECT 4u  /* use the direct XOR+popcount tile kernel instead of bit-sliced  */
+#define UMIGPU_FLAG_KERNEL_TILES  8u  /* use the shared-memory tile form of the bit-sliced kernel instead of
+                                         the block-pair list form                                        */
 
 typedef struct umigpu_ctx umigpu_ctx;
 
@@ -85,6 +87,7 @@ typedef struct umigpu_counters {
     uint64_t n_tile_items;      /* tile-pair work items executed (survivors of the exact cull)       */
     uint64_t n_tile_candidates; /* tile pairs before culling                                         */
     uint64_t n_sweeps;          /* label-propagation sweeps                                          */
+    uint64_t n_block_pairs;     /* (128 x 128) block pairs evaluated by the block-pair kernel          */
     uint64_t n_unmapped;        /* records dropped by the unmapped filter (deduplicate_sam.rs:102-108;
                                    BAM feed only)                                                    */
 } umigpu_counters;

@@ -95,7 +95,8 @@ def test_algo_merge_matrix(algo, merge):
     check_against_oracle(d, algo, merge, 1, 0.5, labels=True)
 
 
-@pytest.mark.parametrize("flags", [0, umigpu.FLAG_KERNEL_DIRECT, umigpu.FLAG_NO_CULL, umigpu.FLAG_KERNEL_DIRECT | umigpu.FLAG_NO_CULL])
+@pytest.mark.parametrize("flags", [0, umigpu.FLAG_KERNEL_DIRECT, umigpu.FLAG_NO_CULL, umigpu.FLAG_KERNEL_DIRECT | umigpu.FLAG_NO_CULL,
+                                   umigpu.FLAG_KERNEL_TILES, umigpu.FLAG_KERNEL_TILES | umigpu.FLAG_NO_CULL])
 def test_large_bucket_multi_tile(flags):
     """One hot locus whose unique UMIs span several 2048-wide tiles (diagonal + off-diagonal tiles)."""
     d, _ = small("C2", 0.0008, n_loci=3, zipf_s=2.0, family=1.5, umi_len=8)
@@ -117,7 +118,7 @@ def test_percentage_sweep(p):
 
 
 def test_n_bases_and_both_kernels():
-    for flags in (0, umigpu.FLAG_KERNEL_DIRECT):
+    for flags in (0, umigpu.FLAG_KERNEL_DIRECT, umigpu.FLAG_KERNEL_TILES):
         d, _ = small("C1", 0.01, umi_len=9, n_loci=8, n_rate=0.05, seed=77)
         assert (d["umi"] == ord("N")).any()
         for algo in (umigpu.ALGO_DIR, umigpu.ALGO_CC, umigpu.ALGO_ADJ_UPSTREAM):

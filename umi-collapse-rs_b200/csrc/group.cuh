@@ -89,8 +89,9 @@ struct BucketEmit {
 #define SMALL_BUCKET 32   // buckets up to this many unique UMIs are handled one per warp
 #define HT_COLS 2048
 
-// cnts = row_cnt | col_cnt << 12 | diag << 31 (counts <= 2048); col_tile = global id of the column tile
-struct TileItem { u32 row_start, col_start, cnts, col_tile; };
+// cnts = row_cnt | col_cnt << 12 | diag << 31 (counts <= 2048); col_blk0 = global id of the column tile's first
+// 128-block (the row tile's is col_blk0 - (col_start - row_start) / 128: same bucket, 128-aligned)
+struct TileItem { u32 row_start, col_start, cnts, col_blk0; };
 __device__ __forceinline__ u32 item_row_cnt(const TileItem &it) { return it.cnts & 0xfffu; }
 __device__ __forceinline__ u32 item_col_cnt(const TileItem &it) { return (it.cnts >> 12) & 0xfffu; }
 __device__ __forceinline__ bool item_diag(const TileItem &it) { return it.cnts >> 31; }
@@ -152,6 +153,12 @@ struct BucketTilesEmit {
     }
 };
 
+// 128-UMI blocks of the buckets that go through the tile / block path (global block id = blk_off[b] + local block)
+struct BucketBlocks {
+    const u32 *bstart;
+    __device__ u32 operator()(u64 b) const { u32 nb = bstart[b + 1] - bstart[b]; return nb <= SMALL_BUCKET ? 0 : (nb + 127) / 128; }
+};
+
 __device__ __forceinline__ void onehot_planes(uint2 p, u32 pn, u32 lmask, u32 *oh /*5*/) {
     u32 base = lmask & ~pn;
     oh[0] = ~p.y & ~p.x & base; oh[1] = ~p.y & p.x & base; oh[2] = p.y & ~p.x & base; oh[3] = p.y & p.x & base; oh[4] = pn & lmask;
@@ -162,7 +169,8 @@ __device__ __forceinline__ void onehot_planes(uint2 p, u32 pn, u32 lmask, u32 *o
 __global__ void __launch_bounds__(256) tile_summary_kernel(u32 n_tiles, u32 n_buckets, const u32 *__restrict__ tile_off,
                                                            const u32 *__restrict__ bstart, const uint2 *__restrict__ planes,
                                                            const u32 *__restrict__ nplane, int L, u32 *__restrict__ tsum,
-                                                           u32 *__restrict__ bsum) {
+                                                           const u32 *__restrict__ blk_off, u32 *__restrict__ bsum,
+                                                           u32 *__restrict__ blk_first, u32 *__restrict__ blk_cnt) {
     u32 t = (blockIdx.x * 256 + threadIdx.x) >> 5;
     if (t >= n_tiles) return;
     u32 lo = 0, hi = n_buckets;
@@ -171,7 +179,8 @@ __global__ void __launch_bounds__(256) tile_summary_kernel(u32 n_tiles, u32 n_bu
     u32 first = s + ti * HT_ROWS, cnt = min((u32)HT_ROWS, nb - ti * HT_ROWS);
     u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
     u32 tot[5] = {0, 0, 0, 0, 0};
-    for (u32 blk = 0; blk < BLOCKS_PER_TILE; blk++) {
+    const u32 gb0 = blk_off[b] + ti * BLOCKS_PER_TILE;       // global id of the tile's first 128-block
+    for (u32 blk = 0; blk * 128 < cnt; blk++) {
         u32 acc[5] = {0, 0, 0, 0, 0};
         for (u32 i = blk * 128 + lane_id(); i < min(cnt, (blk + 1) * 128); i += 32) {
             u32 oh[5];
@@ -185,8 +194,9 @@ __global__ void __launch_bounds__(256) tile_summary_kernel(u32 n_tiles, u32 n_bu
             u32 v = 0;
 #pragma unroll
             for (int x = 0; x < 5; x++) if (lane_id() == (u32)x) v = acc[x];
-            bsum[((u64)t * BLOCKS_PER_TILE + blk) * TS_WORDS + lane_id()] = v;
+            bsum[((u64)gb0 + blk) * TS_WORDS + lane_id()] = v;
         }
+        if (lane_id() == 0) { blk_first[gb0 + blk] = first + blk * 128; blk_cnt[gb0 + blk] = min(128u, cnt - blk * 128); }
     }
     if (lane_id() < TS_WORDS) {
         u32 v = 0;
@@ -205,7 +215,7 @@ __device__ __forceinline__ u32 disjoint_positions(const u32 *a, const u32 *b, u3
 // decode; survivors of the cull test are appended (order is irrelevant: the edge SET is what matters)
 __global__ void __launch_bounds__(256) build_items_kernel(u32 n_cand, u32 n_buckets, const u32 *__restrict__ item_off,
                                                           const u32 *__restrict__ bstart, const u32 *__restrict__ tile_off,
-                                                          const u32 *__restrict__ tsum, int L, int k, int cull,
+                                                          const u32 *__restrict__ blk_off, const u32 *__restrict__ tsum, int L, int k, int cull,
                                                           TileItem *__restrict__ items, DevScalars *sc) {
     u32 w = blockIdx.x * 256 + threadIdx.x;
     u64 npairs = 0;
@@ -232,7 +242,7 @@ __global__ void __launch_bounds__(256) build_items_kernel(u32 n_cand, u32 n_buck
         u32 rc = min((u32)HT_ROWS, nb - ti * HT_ROWS);
         u32 cc = min((u32)HT_COLS, nb - tj * HT_COLS);
         it.cnts = rc | (cc << 12) | (ti == tj ? 0x80000000u : 0u);
-        it.col_tile = tile_off[b] + tj;
+        it.col_blk0 = blk_off[b] + tj * BLOCKS_PER_TILE;
         live = true;
         if (cull && ti != tj) {
             u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);

@@ -1,0 +1,222 @@
+// hamming_blocks.cuh — K5 hamming_neighbours, sparse block-pair form (production kernel).
+//
+// Same bit-sliced one-hot arithmetic as hamming_tiles_bs (hamming_bs.cuh), organised for the regime that
+// exact culling leaves behind: of the N^2/2 pairs of a hot locus only ~1 % of the (128 x 128) blocks can
+// contain a neighbour, so the work is a LIST of block pairs rather than dense tiles.
+//   onehot_build_kernel   once per run: one-hot match words of every 128-UMI block, in HBM (768 B per block at
+//                         12 nt): eq[block][j][x][4 groups], bit c of group g = "UMI 32g+c has letter x at position j"
+//   expand_blocks_kernel  one warp per surviving tile pair: tests its 16 x 16 block pairs with the per-block
+//                         letter sets (disjoint-positions bound) and appends the survivors
+//   hamming_blocks        one warp per block pair: four slices of 32 consecutive rows; a slice whose letter sets
+//                         are disjoint from the column block's in more than k positions is skipped; otherwise each
+//                         lane runs its row UMI against the 128 columns: one LDG.128 (L1-resident, 4 distinct
+//                         16-byte rows per warp) and 2(k+1) LOP3 per position.
+#pragma once
+#include "common.cuh"
+#include "hamming.cuh"
+
+#define BLK_COLS 128
+
+// ---- one-hot words of every 128-block (built once per run) ----
+template <bool HASN>
+__global__ void __launch_bounds__(256) onehot_build_kernel(u32 n_groups /* 4 per block */, const u32 *__restrict__ blk_first,
+                                                           const u32 *__restrict__ blk_cnt, const uint2 *__restrict__ planes,
+                                                           const u32 *__restrict__ nplane, int L, int LP, u32 *__restrict__ eq) {
+    constexpr int XS = HASN ? 8 : 4;
+    constexpr int NLET = HASN ? 5 : 4;
+    const u32 g = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = lane_id();
+    if (g >= n_groups) return;
+    const u32 gb = g >> 2, c = (g & 3) * 32 + lane;
+    const bool valid = c < blk_cnt[gb];
+    const u32 uid = blk_first[gb] + c;
+    const uint2 p = valid ? planes[uid] : make_uint2(0u, 0u);
+    const u32 pn = (HASN && valid) ? nplane[uid] : 0u;
+    u32 *dst = eq + (u64)gb * LP * XS * 4 + (g & 3);
+    for (int j = 0; j < LP; j++) {
+        u32 letter = ((p.y >> j) & 1u) * 2u + ((p.x >> j) & 1u);
+        if (HASN && ((pn >> j) & 1u)) letter = 4u;
+        if (!valid) letter = 15u;                 // padding column: matches no letter at any real position
+        u32 v = 0;
+#pragma unroll
+        for (int x = 0; x < NLET; x++) {
+            u32 b = __ballot_sync(0xffffffffu, letter == (u32)x);
+            if (lane == (u32)x) v = b;
+        }
+        if (j >= L) v = 0xffffffffu;              // positions beyond umi_len always match
+        if (lane < (u32)XS) dst[(j * XS + lane) * 4] = v;
+    }
+}
+
+// ---- surviving tile pairs -> surviving (128 x 128) block pairs ----
+// fill == 0: only counts (out_count += survivors); fill == 1: appends uint2(row block, col block)
+__global__ void __launch_bounds__(256) expand_blocks_kernel(const TileItem *__restrict__ items, u32 n_items, const u32 *__restrict__ bsum,
+                                                            int L, int k, int cull, int fill, uint2 *__restrict__ pairs,
+                                                            unsigned long long *out_count) {
+    const u32 w = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = lane_id();
+    if (w >= n_items) return;
+    const TileItem it = items[w];
+    const u32 nrb = (item_row_cnt(it) + 127) >> 7, ncb = (item_col_cnt(it) + 127) >> 7;
+    const bool diag = item_diag(it);
+    const u32 row_blk0 = it.col_blk0 - ((it.col_start - it.row_start) >> 7);
+    const u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
+    const u32 r = lane & 15, c0 = (lane >> 4) * 8;
+    u32 rs[5] = {0, 0, 0, 0, 0};
+    if (r < nrb) {
+#pragma unroll
+        for (int x = 0; x < 5; x++) rs[x] = bsum[(u64)(row_blk0 + r) * 8 + x];
+    }
+    u32 live = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const u32 c = c0 + i;
+        bool ok = r < nrb && c < ncb && (!diag || r <= c);
+        if (ok && cull && !(diag && r == c)) {
+            u32 cs[5];
+#pragma unroll
+            for (int x = 0; x < 5; x++) cs[x] = bsum[(u64)(it.col_blk0 + c) * 8 + x];
+            ok = disjoint_positions(rs, cs, lmask) <= (u32)k;
+        }
+        if (ok) live |= 1u << i;
+    }
+    u32 cnt = __popc(live);
+    // warp exclusive prefix of cnt
+    u32 inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (u32)o) inc += t; }
+    const u32 total = __shfl_sync(0xffffffffu, inc, 31);
+    if (total == 0) return;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(out_count, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (fill) {
+        u64 o = base + inc - cnt;
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (live & (1u << i)) pairs[o++] = make_uint2(row_blk0 + r, it.col_blk0 + c0 + i);
+    }
+}
+
+// ---- evaluation: one warp per block pair ----
+template <int LP, int K, bool HASN>
+__global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ pairs, u64 n_pairs, const u32 *__restrict__ blk_first,
+                                                      const u32 *__restrict__ blk_cnt, const u32 *__restrict__ bsum,
+                                                      const uint2 *__restrict__ planes, const u32 *__restrict__ nplane,
+                                                      const uint4 *__restrict__ eq, int L, int cull, EdgeSink es,
+                                                      unsigned long long *pairs_eval) {
+    constexpr int XS = HASN ? 8 : 4;
+    constexpr int NLET = HASN ? 5 : 4;
+    const u32 lane = lane_id();
+    const u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
+    const u64 nwarps = (u64)gridDim.x * (256 / 32);
+    u64 evaluated = 0;
+    for (u64 w = ((u64)blockIdx.x * 256 + threadIdx.x) >> 5; w < n_pairs; w += nwarps) {
+        const uint2 pr = pairs[w];
+        const u32 rfirst = blk_first[pr.x], rcnt = blk_cnt[pr.x], cfirst = blk_first[pr.y], ccnt = blk_cnt[pr.y];
+        const bool same = pr.x == pr.y;
+        u32 cs[5] = {0, 0, 0, 0, 0};
+        if (cull) {
+#pragma unroll
+            for (int x = 0; x < NLET; x++) cs[x] = bsum[(u64)pr.y * 8 + x];
+        }
+        const uint4 *base = eq + (u64)pr.y * (LP * XS);
+        for (u32 s = 0; s * 32 < rcnt; s++) {
+            const u32 r = s * 32 + lane;
+            const bool valid = r < rcnt;
+            const uint2 rp = valid ? planes[rfirst + r] : make_uint2(0u, 0u);
+            const u32 rn = (HASN && valid) ? nplane[rfirst + r] : 0u;
+            if (cull && !same) {
+                // the 32 rows of a slice are consecutive sorted UMIs: few letters per position
+                u32 oh[5], t = 0;
+                onehot_planes(rp, rn, valid ? lmask : 0u, oh);
+#pragma unroll
+                for (int x = 0; x < NLET; x++) t |= __reduce_or_sync(0xffffffffu, oh[x]) & cs[x];
+                if (__popc(~t & lmask) > K) continue;          // > K positions with disjoint letter sets
+            }
+            evaluated += (u64)__popc(__ballot_sync(0xffffffffu, valid)) * ccnt;
+            if (!valid) continue;
+            u32 off[LP];                                   // uint4 index of the row's letter slot at position j
+#pragma unroll
+            for (int j = 0; j < LP; j++) {
+                u32 letter = ((rp.y >> j) & 1u) * 2u + ((rp.x >> j) & 1u);
+                if (HASN && ((rn >> j) & 1u)) letter = 4u;
+                off[j] = (u32)(j * XS) + letter;
+            }
+            uint4 m1 = make_uint4(~0u, ~0u, ~0u, ~0u), m2 = m1, m3 = m1, m4 = m1;
+#pragma unroll
+            for (int j = 0; j < LP; j++) {
+                const uint4 wv = __ldg(base + off[j]);
+                if (K >= 3) { m4.x = (wv.x & m4.x) | (~wv.x & m3.x); m4.y = (wv.y & m4.y) | (~wv.y & m3.y);
+                              m4.z = (wv.z & m4.z) | (~wv.z & m3.z); m4.w = (wv.w & m4.w) | (~wv.w & m3.w); }
+                if (K >= 2) { m3.x = (wv.x & m3.x) | (~wv.x & m2.x); m3.y = (wv.y & m3.y) | (~wv.y & m2.y);
+                              m3.z = (wv.z & m3.z) | (~wv.z & m2.z); m3.w = (wv.w & m3.w) | (~wv.w & m2.w); }
+                m2.x = (wv.x & m2.x) | (~wv.x & m1.x); m2.y = (wv.y & m2.y) | (~wv.y & m1.y);
+                m2.z = (wv.z & m2.z) | (~wv.z & m1.z); m2.w = (wv.w & m2.w) | (~wv.w & m1.w);
+                m1.x &= wv.x; m1.y &= wv.y; m1.z &= wv.z; m1.w &= wv.w;
+            }
+            const uint4 h = K == 1 ? m2 : (K == 2 ? m3 : m4);
+            if (h.x | h.y | h.z | h.w) {
+                const u32 a = rfirst + r;
+                const u32 hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    u32 bits = hv[i];
+                    while (bits) {
+                        u32 b = __ffs(bits) - 1; bits &= bits - 1;
+                        u32 c = i * 32 + b;
+                        if (c < ccnt) {
+                            u32 bb = cfirst + c;
+                            if (!same || a < bb) record_hit(es, a, bb);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0 && evaluated) atomicAdd(pairs_eval, (unsigned long long)evaluated);
+}
+
+template <int LP, int K, bool HASN>
+static int blk_launch_one(cudaStream_t stream, int num_sms, const uint2 *pairs, u64 n_pairs, const u32 *blk_first, const u32 *blk_cnt,
+                          const u32 *bsum, const uint2 *planes, const u32 *nplane, const uint4 *eq, int L, int cull, EdgeSink es,
+                          unsigned long long *pairs_eval) {
+    auto kern = hamming_blocks<LP, K, HASN>;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0) != cudaSuccess || occ < 1) occ = 1;
+    u32 grid = (u32)std::min<u64>((n_pairs + 7) / 8, (u64)num_sms * occ * 4);
+    if (grid == 0) return 0;
+    kern<<<grid, 256, 0, stream>>>(pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, eq, L, cull, es, pairs_eval);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+static inline int blk_lp(int L) { return L <= 8 ? 8 : L <= 12 ? 12 : L <= 16 ? 16 : L <= 24 ? 24 : 32; }
+
+template <int K, bool HASN>
+static int blk_launch_k(cudaStream_t stream, int num_sms, const uint2 *pairs, u64 n_pairs, const u32 *blk_first, const u32 *blk_cnt,
+                        const u32 *bsum, const uint2 *planes, const u32 *nplane, const uint4 *eq, int L, int cull, EdgeSink es,
+                        unsigned long long *pairs_eval) {
+#define BLK_ARGS stream, num_sms, pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, eq, L, cull, es, pairs_eval
+    switch (blk_lp(L)) {
+    case 8:  return blk_launch_one<8, K, HASN>(BLK_ARGS);
+    case 12: return blk_launch_one<12, K, HASN>(BLK_ARGS);
+    case 16: return blk_launch_one<16, K, HASN>(BLK_ARGS);
+    case 24: return blk_launch_one<24, K, HASN>(BLK_ARGS);
+    default: if (HASN) return 1; return blk_launch_one<32, K, false>(BLK_ARGS);
+    }
+#undef BLK_ARGS
+}
+
+// returns 0 = launched, 1 = configuration not covered (k outside 1..3), -1 = CUDA error
+static int launch_neighbours_blocks(cudaStream_t stream, int num_sms, const uint2 *pairs, u64 n_pairs, const u32 *blk_first,
+                                    const u32 *blk_cnt, const u32 *bsum, const uint2 *planes, const u32 *nplane, const uint4 *eq,
+                                    int L, int k, bool has_n, int cull, EdgeSink es, unsigned long long *pairs_eval) {
+#define BLK_ARGS stream, num_sms, pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, eq, L, cull, es, pairs_eval
+    if (k < 1 || k > 3) return 1;
+    if (!has_n) {
+        if (k == 1) return blk_launch_k<1, false>(BLK_ARGS);
+        if (k == 2) return blk_launch_k<2, false>(BLK_ARGS);
+        return blk_launch_k<3, false>(BLK_ARGS);
+    }
+    if (k == 1) return blk_launch_k<1, true>(BLK_ARGS);
+    if (k == 2) return blk_launch_k<2, true>(BLK_ARGS);
+    return blk_launch_k<3, true>(BLK_ARGS);
+#undef BLK_ARGS
+}

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(BS_THREADS) hamming_tiles_bs(
 
         // ---- phase 0: letter sets of the column tile's 128-column blocks (precomputed per tile) ----
         if (cull) {
-            if (threadIdx.x < g4_cnt * 8) sset[threadIdx.x] = bsum[(u64)it.col_tile * (BS_G4 * 8) + threadIdx.x];
+            if (threadIdx.x < g4_cnt * 8) sset[threadIdx.x] = bsum[(u64)it.col_blk0 * 8 + threadIdx.x];
             __syncthreads();
         }
         // ---- phase 1: which (32-row warp slice) x (128-column block) pairs can contain a neighbour at all ----

@@ -23,6 +23,8 @@ struct DevScalars {
     u32 n_cand, n_tiles;
     u32 sort_ticket, sort_err;
     u32 bam_err, bam_valid;
+    u32 n_blocks, pad0;
+    u64 n_block_pairs;
 };
 
 struct KeyLayout {

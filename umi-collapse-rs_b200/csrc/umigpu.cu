@@ -14,6 +14,7 @@
 #include "group.cuh"
 #include "hamming.cuh"
 #include "hamming_bs.cuh"
+#include "hamming_blocks.cuh"
 #include "misc.cuh"
 #include "pack.cuh"
 #include "radix_sort.cuh"
@@ -41,13 +42,14 @@ struct umigpu_ctx {
 
     DevBuf d_key[2][2], d_idx[2], d_hist, d_tiles;
     DevBuf d_useg, d_rep, d_planes, d_nplane, d_bhead, d_wsum, d_read_uid, d_freq, d_thr, d_repidx, d_label, d_prio;
-    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_onehot, d_tileoff, d_tsum, d_tilestate, d_bsum;
+    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_onehot, d_tileoff, d_tsum, d_tilestate, d_bsum, d_blkoff, d_blkfirst, d_blkcnt, d_eq, d_pairs;
 
     // results
     bool ran = false;
     umigpu_counters ctr;
     u32 n_unique = 0, n_buckets = 0;
     bool used_direct = false;
+    u32 n_blocks = 0;
     u64 n_edges = 0;
     KeyLayout lay;
     u64 *h_kept = nullptr; size_t h_kept_cap = 0;       // pinned; what umigpu_result.kept_read_index points to
@@ -145,7 +147,7 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
                       &ctx->d_hist, &ctx->d_tiles, &ctx->d_useg, &ctx->d_rep, &ctx->d_planes, &ctx->d_nplane, &ctx->d_bhead, &ctx->d_wsum,
                       &ctx->d_read_uid, &ctx->d_freq, &ctx->d_thr, &ctx->d_repidx, &ctx->d_label, &ctx->d_prio, &ctx->d_bstart, &ctx->d_itemoff,
                       &ctx->d_items, &ctx->d_edges, &ctx->d_keep, &ctx->d_state, &ctx->d_blocked, &ctx->d_bitmap, &ctx->d_kept, &ctx->d_roots,
-                      &ctx->d_onehot, &ctx->d_tileoff, &ctx->d_tsum, &ctx->d_tilestate, &ctx->d_bsum};
+                      &ctx->d_onehot, &ctx->d_tileoff, &ctx->d_tsum, &ctx->d_tilestate, &ctx->d_bsum, &ctx->d_blkoff, &ctx->d_blkfirst, &ctx->d_blkcnt, &ctx->d_eq, &ctx->d_pairs};
     for (DevBuf *b : bufs) b->release();
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
     if (ctx->h_kept) cudaFreeHost(ctx->h_kept);
@@ -508,14 +510,21 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
         if (rc) return rc;
         rc = run_scan(ctx, BucketTiles{ctx->d_bstart.as<u32>()}, BucketTilesEmit{ctx->d_tileoff.as<u32>(), B}, B, &sc->n_tiles);
         if (rc) return rc;
+        CK(ctx->d_blkoff.reserve(((size_t)B + 1) * 4));
+        rc = run_scan(ctx, BucketBlocks{ctx->d_bstart.as<u32>()}, BucketTilesEmit{ctx->d_blkoff.as<u32>(), B}, B, &sc->n_blocks);
+        if (rc) return rc;
         rc = read_scalars(ctx);
         if (rc) return rc;
-        const u32 n_cand = ctx->h_sc->n_cand, n_tiles = ctx->h_sc->n_tiles;
+        const u32 n_cand = ctx->h_sc->n_cand, n_tiles = ctx->h_sc->n_tiles, n_blocks = ctx->h_sc->n_blocks;
+        ctx->n_blocks = n_blocks;
         CK(ctx->d_tsum.reserve((size_t)std::max<u32>(n_tiles, 1) * TS_WORDS * 4));
-        CK(ctx->d_bsum.reserve((size_t)std::max<u32>(n_tiles, 1) * BLOCKS_PER_TILE * TS_WORDS * 4));
-        if (cull && n_tiles)
+        CK(ctx->d_bsum.reserve((size_t)std::max<u32>(n_blocks, 1) * TS_WORDS * 4));
+        CK(ctx->d_blkfirst.reserve((size_t)std::max<u32>(n_blocks, 1) * 4));
+        CK(ctx->d_blkcnt.reserve((size_t)std::max<u32>(n_blocks, 1) * 4));
+        if (n_tiles)
             LAUNCH(tile_summary_kernel, grid_for((u64)n_tiles * 32, 256), 256, n_tiles, B, (const u32 *)ctx->d_tileoff.p, (const u32 *)ctx->d_bstart.p,
-                   (const uint2 *)ctx->d_planes.p, has_n ? (const u32 *)ctx->d_nplane.p : (const u32 *)nullptr, lay.umi_len, ctx->d_tsum.as<u32>(), ctx->d_bsum.as<u32>());
+                   (const uint2 *)ctx->d_planes.p, has_n ? (const u32 *)ctx->d_nplane.p : (const u32 *)nullptr, lay.umi_len, ctx->d_tsum.as<u32>(),
+                   (const u32 *)ctx->d_blkoff.p, ctx->d_bsum.as<u32>(), ctx->d_blkfirst.as<u32>(), ctx->d_blkcnt.as<u32>());
         // candidates are tested in chunks so that the item buffer only has to hold the survivors of one chunk
         // plus what is already there; in the worst case (no culling) it holds every candidate
         CK(ctx->d_items.reserve((size_t)std::max<u32>(n_cand, 1) * sizeof(TileItem)));
@@ -523,7 +532,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
         CK(cudaMemsetAsync(&sc->scratch2, 0, 8, ctx->stream));
         if (n_cand)
             LAUNCH(build_items_kernel, grid_for(n_cand, 256), 256, n_cand, B, (const u32 *)ctx->d_itemoff.p, (const u32 *)ctx->d_bstart.p,
-                   (const u32 *)ctx->d_tileoff.p, (const u32 *)ctx->d_tsum.p, lay.umi_len, cfg.k, cull, ctx->d_items.as<TileItem>(), sc);
+                   (const u32 *)ctx->d_tileoff.p, (const u32 *)ctx->d_blkoff.p, (const u32 *)ctx->d_tsum.p, lay.umi_len, cfg.k, cull, ctx->d_items.as<TileItem>(), sc);
         rc = read_scalars(ctx);
         if (rc) return rc;
         W = ctx->h_sc->n_items;
@@ -636,19 +645,45 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
 
 static int launch_neighbours(umigpu_ctx *ctx, u32 n_items, EdgeSink es, bool has_n) {
     const umigpu_config &cfg = ctx->cfg;
+    DevScalars *sc = ctx->d_sc.as<DevScalars>();
     const TileItem *items = ctx->d_items.as<TileItem>();
     const uint2 *planes = ctx->d_planes.as<uint2>();
     const u32 *nplane = ctx->d_nplane.as<u32>();
+    const int k = cfg.k, L = (int)cfg.umi_len;
+    const int cull = (cfg.flags & UMIGPU_FLAG_NO_CULL) ? 0 : 1;
+    ctx->used_direct = false;
+    if (!(cfg.flags & (UMIGPU_FLAG_KERNEL_DIRECT | UMIGPU_FLAG_KERNEL_TILES)) && k >= 1 && k <= 3 && !(has_n && L > 24)) {
+        // ---- production path: global one-hot words, block-pair list, one warp per block pair ----
+        const int LP = blk_lp(L), XS = has_n ? 8 : 4;
+        const u32 n_blocks = ctx->n_blocks;
+        CK(ctx->d_eq.reserve((size_t)std::max<u32>(n_blocks, 1) * LP * XS * 16));
+        if (has_n) LAUNCH(onehot_build_kernel<true>, grid_for((u64)n_blocks * 4 * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
+                          (const u32 *)ctx->d_blkcnt.p, planes, nplane, L, LP, ctx->d_eq.as<u32>());
+        else       LAUNCH(onehot_build_kernel<false>, grid_for((u64)n_blocks * 4 * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
+                          (const u32 *)ctx->d_blkcnt.p, planes, nplane, L, LP, ctx->d_eq.as<u32>());
+        CK(cudaMemsetAsync(&sc->n_block_pairs, 0, 8, ctx->stream));
+        LAUNCH(expand_blocks_kernel, grid_for((u64)n_items * 32, 256), 256, items, n_items, (const u32 *)ctx->d_bsum.p, L, k, cull, 0,
+               (uint2 *)nullptr, (unsigned long long *)&sc->n_block_pairs);
+        int rc = read_scalars(ctx);
+        if (rc) return rc;
+        const u64 n_pairs = ctx->h_sc->n_block_pairs;
+        CK(ctx->d_pairs.reserve(std::max<u64>(n_pairs, 1) * sizeof(uint2)));
+        CK(cudaMemsetAsync(&sc->n_block_pairs, 0, 8, ctx->stream));
+        LAUNCH(expand_blocks_kernel, grid_for((u64)n_items * 32, 256), 256, items, n_items, (const u32 *)ctx->d_bsum.p, L, k, cull, 1,
+               ctx->d_pairs.as<uint2>(), (unsigned long long *)&sc->n_block_pairs);
+        rc = launch_neighbours_blocks(ctx->stream, ctx->num_sms, ctx->d_pairs.as<uint2>(), n_pairs, (const u32 *)ctx->d_blkfirst.p,
+                                      (const u32 *)ctx->d_blkcnt.p, (const u32 *)ctx->d_bsum.p, planes, has_n ? nplane : (const u32 *)nullptr,
+                                      ctx->d_eq.as<uint4>(), L, k, has_n, cull, es, (unsigned long long *)&sc->pairs_eval);
+        if (rc < 0) return fail(ctx, UMIGPU_ERR_CUDA, "block-pair neighbour kernel: %s", cudaGetErrorString(cudaGetLastError()));
+        if (rc == 0) { ctx->launches += 1; ctx->ctr.n_block_pairs = n_pairs; CK(cudaGetLastError()); return UMIGPU_OK; }
+    }
     u32 grid = std::min<u32>(n_items, (u32)ctx->num_sms * 4);
-    const int k = cfg.k;
     if (!(cfg.flags & UMIGPU_FLAG_KERNEL_DIRECT)) {
-        int rc = launch_neighbours_bitsliced(ctx->stream, ctx->num_sms, items, n_items, planes, nplane, ctx->d_bsum.as<u32>(), (int)cfg.umi_len, k, has_n,
-                                             (cfg.flags & UMIGPU_FLAG_NO_CULL) ? 0 : 1, es, (u32 *)&ctx->d_sc.as<DevScalars>()->scratch,
-                                             (unsigned long long *)&ctx->d_sc.as<DevScalars>()->pairs_eval);
-        ctx->used_direct = false;
+        int rc = launch_neighbours_bitsliced(ctx->stream, ctx->num_sms, items, n_items, planes, nplane, ctx->d_bsum.as<u32>(), L, k, has_n,
+                                             cull, es, (u32 *)&sc->scratch, (unsigned long long *)&sc->pairs_eval);
         if (rc == 0) { ctx->launches += 1; CK(cudaGetLastError()); return UMIGPU_OK; }
         if (rc < 0) return fail(ctx, UMIGPU_ERR_CUDA, "bit-sliced neighbour kernel: %s", cudaGetErrorString(cudaGetLastError()));
-        // rc > 0: configuration not covered by the bit-sliced kernel (k > 3) -> direct kernel
+        // rc > 0: configuration not covered by the bit-sliced kernels (k > 3) -> direct kernel
     }
     ctx->used_direct = true;
 #define HD(KK, NN) LAUNCH((hamming_tiles_direct<KK, NN>), grid, HT_THREADS, items, n_items, planes, nplane, es, k)

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libumigpu.so")
 OK, ERR_ARG, ERR_CUDA, ERR_BAD_BASE, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 ALGO_DIR, ALGO_ADJ, ALGO_ADJ_UPSTREAM, ALGO_CC = 0, 1, 2, 3
 MERGE_ANY, MERGE_AVGQUAL, MERGE_MAPQUAL = 0, 1, 2
-FLAG_LABELS, FLAG_NO_CULL, FLAG_KERNEL_DIRECT = 1, 2, 4
+FLAG_LABELS, FLAG_NO_CULL, FLAG_KERNEL_DIRECT, FLAG_KERNEL_TILES = 1, 2, 4, 8
 STAGES = ["pack", "keys", "sort", "unique", "worklist", "neighbours", "cluster", "emit", "total"]
 
 # every symbol include/umigpu.h declares (tests check that the built library exports all of them)
@@ -35,7 +35,7 @@ class Config(C.Structure):
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "total_reads", "n_buckets", "total_umis", "max_umis", "n_kept", "unordered_pairs",
-        "pairs_evaluated", "n_edges", "n_tile_items", "n_tile_candidates", "n_sweeps", "n_unmapped")]
+        "pairs_evaluated", "n_edges", "n_tile_items", "n_tile_candidates", "n_sweeps", "n_block_pairs", "n_unmapped")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
