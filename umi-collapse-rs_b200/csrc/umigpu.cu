@@ -652,7 +652,10 @@ static int launch_neighbours(umigpu_ctx *ctx, u32 n_items, EdgeSink es, bool has
     const int k = cfg.k, L = (int)cfg.umi_len;
     const int cull = (cfg.flags & UMIGPU_FLAG_NO_CULL) ? 0 : 1;
     ctx->used_direct = false;
-    if (!(cfg.flags & (UMIGPU_FLAG_KERNEL_DIRECT | UMIGPU_FLAG_KERNEL_TILES)) && k >= 1 && k <= 3 && !(has_n && L > 24)) {
+    // Dense work (culling disabled, or a UMI space so saturated that most blocks survive) runs better as
+    // shared-memory tiles; sparse work (the normal case after culling) as a block-pair list.
+    bool use_blocks = !(cfg.flags & (UMIGPU_FLAG_KERNEL_DIRECT | UMIGPU_FLAG_KERNEL_TILES)) && k >= 1 && k <= 3 && !(has_n && L > 24) && cull;
+    if (use_blocks) {
         // ---- production path: global one-hot words, block-pair list, one warp per block pair ----
         const int LP = blk_lp(L), XS = has_n ? 8 : 4;
         const u32 n_blocks = ctx->n_blocks;
@@ -667,6 +670,9 @@ static int launch_neighbours(umigpu_ctx *ctx, u32 n_items, EdgeSink es, bool has
         int rc = read_scalars(ctx);
         if (rc) return rc;
         const u64 n_pairs = ctx->h_sc->n_block_pairs;
+        // more than ~30 % of the scheduled pair space survives block culling: treat as dense
+        if ((double)n_pairs * 16384.0 > 0.30 * (double)ctx->h_sc->scratch2) use_blocks = false;
+      if (use_blocks) {
         CK(ctx->d_pairs.reserve(std::max<u64>(n_pairs, 1) * sizeof(uint2)));
         CK(cudaMemsetAsync(&sc->n_block_pairs, 0, 8, ctx->stream));
         LAUNCH(expand_blocks_kernel, grid_for((u64)n_items * 32, 256), 256, items, n_items, (const u32 *)ctx->d_bsum.p, L, k, cull, 1,
@@ -676,6 +682,7 @@ static int launch_neighbours(umigpu_ctx *ctx, u32 n_items, EdgeSink es, bool has
                                       ctx->d_eq.as<uint4>(), L, k, has_n, cull, es, (unsigned long long *)&sc->pairs_eval);
         if (rc < 0) return fail(ctx, UMIGPU_ERR_CUDA, "block-pair neighbour kernel: %s", cudaGetErrorString(cudaGetLastError()));
         if (rc == 0) { ctx->launches += 1; ctx->ctr.n_block_pairs = n_pairs; CK(cudaGetLastError()); return UMIGPU_OK; }
+      }
     }
     u32 grid = std::min<u32>(n_items, (u32)ctx->num_sms * 4);
     if (!(cfg.flags & UMIGPU_FLAG_KERNEL_DIRECT)) {
