@@ -29,6 +29,22 @@ __global__ void __launch_bounds__(256) label_sweep_kernel(const uint2 *__restric
     if (__any_sync(0xffffffffu, any) && lane_id() == 0) sc->changed = 1;
 }
 
+// Pointer jumping: label[v] names a UMI r that reaches v; whatever reaches r reaches v too, so label[v] may take
+// label[r].  One jump per sweep turns the number of sweeps from O(longest chain) into O(log) of it.
+__global__ void __launch_bounds__(256) label_jump_kernel(u32 n_unique, unsigned long long *label, DevScalars *sc) {
+    u32 v = blockIdx.x * 256 + threadIdx.x;
+    u32 any = 0;
+    if (v < n_unique) {
+        unsigned long long l = label[v];
+        u32 r = (u32)l;
+        if (r != v) {
+            unsigned long long lr = label[r];
+            if (lr < l) { atomicMin(&label[v], lr); any = 1; }
+        }
+    }
+    if (__any_sync(0xffffffffu, any) && lane_id() == 0) sc->changed = 1;
+}
+
 // keep[u] = (root(u) == u); root id = low 32 bits of the label
 __global__ void __launch_bounds__(256) keep_from_label_kernel(u32 n_unique, const unsigned long long *__restrict__ label,
                                                               u8 *__restrict__ keep) {

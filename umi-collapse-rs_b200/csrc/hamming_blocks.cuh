@@ -95,6 +95,41 @@ __global__ void __launch_bounds__(256) expand_blocks_kernel(const TileItem *__re
     }
 }
 
+// ---- warp-buffered edge output ----
+// Every hit used to cost one atomicAdd on the single global edge counter; in a saturated UMI space (the fastq
+// single-bucket config: ~170 M edges) that one address serialises the whole kernel.  Each warp now stages its
+// edges in a private shared-memory buffer (positions by ballot/prefix, no atomics) and reserves global space
+// with ONE atomicAdd per flush of up to WB_CAP edges.
+#define WB_CAP 128
+struct WarpEdgeBuf {
+    uint2 *buf;      // this warp's WB_CAP slots in shared memory
+    u32 fill;        // warp-uniform
+};
+__device__ __forceinline__ void wb_flush(WarpEdgeBuf &wb, const EdgeSink &es) {
+    if (wb.fill == 0) return;
+    __syncwarp();
+    unsigned long long base = 0;
+    if (lane_id() == 0) base = atomicAdd(es.count, (unsigned long long)wb.fill);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (u32 i = lane_id(); i < wb.fill; i += 32) if (base + i < es.cap) es.edges[base + i] = wb.buf[i];
+    __syncwarp();
+    wb.fill = 0;
+}
+// called by all 32 lanes; ab / ba = this lane emits edge (a -> b) / (b -> a)
+__device__ __forceinline__ void wb_emit(WarpEdgeBuf &wb, const EdgeSink &es, bool ab, bool ba, u32 a, u32 b) {
+    const u32 cnt = (ab ? 1u : 0u) + (ba ? 1u : 0u);
+    u32 inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane_id() >= (u32)o) inc += t; }
+    const u32 total = __shfl_sync(0xffffffffu, inc, 31);
+    if (total == 0) return;
+    if (wb.fill + total > WB_CAP) wb_flush(wb, es);
+    u32 pos = wb.fill + inc - cnt;
+    if (ab) wb.buf[pos++] = make_uint2(a, b);
+    if (ba) wb.buf[pos] = make_uint2(b, a);
+    wb.fill += total;
+}
+
 // ---- evaluation: one warp per block pair ----
 template <int LP, int K, bool HASN>
 __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ pairs, u64 n_pairs, const u32 *__restrict__ blk_first,
@@ -107,6 +142,8 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
     const u32 lane = lane_id();
     const u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
     const u64 nwarps = (u64)gridDim.x * (256 / 32);
+    __shared__ uint2 s_edges[(256 / 32) * WB_CAP];
+    WarpEdgeBuf wb{s_edges + (threadIdx.x >> 5) * WB_CAP, 0u};
     u64 evaluated = 0;
     for (u64 w = ((u64)blockIdx.x * 256 + threadIdx.x) >> 5; w < n_pairs; w += nwarps) {
         const uint2 pr = pairs[w];
@@ -132,45 +169,52 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
                 if (__popc(~t & lmask) > K) continue;          // > K positions with disjoint letter sets
             }
             evaluated += (u64)__popc(__ballot_sync(0xffffffffu, valid)) * ccnt;
-            if (!valid) continue;
-            u32 off[LP];                                   // uint4 index of the row's letter slot at position j
+            uint4 h = make_uint4(0u, 0u, 0u, 0u);
+            if (valid) {
+                u32 off[LP];                                   // uint4 index of the row's letter slot at position j
 #pragma unroll
-            for (int j = 0; j < LP; j++) {
-                u32 letter = ((rp.y >> j) & 1u) * 2u + ((rp.x >> j) & 1u);
-                if (HASN && ((rn >> j) & 1u)) letter = 4u;
-                off[j] = (u32)(j * XS) + letter;
-            }
-            uint4 m1 = make_uint4(~0u, ~0u, ~0u, ~0u), m2 = m1, m3 = m1, m4 = m1;
+                for (int j = 0; j < LP; j++) {
+                    u32 letter = ((rp.y >> j) & 1u) * 2u + ((rp.x >> j) & 1u);
+                    if (HASN && ((rn >> j) & 1u)) letter = 4u;
+                    off[j] = (u32)(j * XS) + letter;
+                }
+                uint4 m1 = make_uint4(~0u, ~0u, ~0u, ~0u), m2 = m1, m3 = m1, m4 = m1;
 #pragma unroll
-            for (int j = 0; j < LP; j++) {
-                const uint4 wv = __ldg(base + off[j]);
-                if (K >= 3) { m4.x = (wv.x & m4.x) | (~wv.x & m3.x); m4.y = (wv.y & m4.y) | (~wv.y & m3.y);
-                              m4.z = (wv.z & m4.z) | (~wv.z & m3.z); m4.w = (wv.w & m4.w) | (~wv.w & m3.w); }
-                if (K >= 2) { m3.x = (wv.x & m3.x) | (~wv.x & m2.x); m3.y = (wv.y & m3.y) | (~wv.y & m2.y);
-                              m3.z = (wv.z & m3.z) | (~wv.z & m2.z); m3.w = (wv.w & m3.w) | (~wv.w & m2.w); }
-                m2.x = (wv.x & m2.x) | (~wv.x & m1.x); m2.y = (wv.y & m2.y) | (~wv.y & m1.y);
-                m2.z = (wv.z & m2.z) | (~wv.z & m1.z); m2.w = (wv.w & m2.w) | (~wv.w & m1.w);
-                m1.x &= wv.x; m1.y &= wv.y; m1.z &= wv.z; m1.w &= wv.w;
+                for (int j = 0; j < LP; j++) {
+                    const uint4 wv = __ldg(base + off[j]);
+                    if (K >= 3) { m4.x = (wv.x & m4.x) | (~wv.x & m3.x); m4.y = (wv.y & m4.y) | (~wv.y & m3.y);
+                                  m4.z = (wv.z & m4.z) | (~wv.z & m3.z); m4.w = (wv.w & m4.w) | (~wv.w & m3.w); }
+                    if (K >= 2) { m3.x = (wv.x & m3.x) | (~wv.x & m2.x); m3.y = (wv.y & m3.y) | (~wv.y & m2.y);
+                                  m3.z = (wv.z & m3.z) | (~wv.z & m2.z); m3.w = (wv.w & m3.w) | (~wv.w & m2.w); }
+                    m2.x = (wv.x & m2.x) | (~wv.x & m1.x); m2.y = (wv.y & m2.y) | (~wv.y & m1.y);
+                    m2.z = (wv.z & m2.z) | (~wv.z & m1.z); m2.w = (wv.w & m2.w) | (~wv.w & m1.w);
+                    m1.x &= wv.x; m1.y &= wv.y; m1.z &= wv.z; m1.w &= wv.w;
+                }
+                h = K == 1 ? m2 : (K == 2 ? m3 : m4);
             }
-            const uint4 h = K == 1 ? m2 : (K == 2 ? m3 : m4);
-            if (h.x | h.y | h.z | h.w) {
+            // ---- hits (rare): warp-uniform loop, one candidate per lane per round ----
+            if (__any_sync(0xffffffffu, (h.x | h.y | h.z | h.w) != 0u)) {
                 const u32 a = rfirst + r;
-                const u32 hv[4] = {h.x, h.y, h.z, h.w};
+                i32 fa = 0, ta = 0;
+                if (valid && (h.x | h.y | h.z | h.w)) { fa = es.freq[a]; ta = es.thr[a]; }
+                u32 hv[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    u32 bits = hv[i];
-                    while (bits) {
-                        u32 b = __ffs(bits) - 1; bits &= bits - 1;
-                        u32 c = i * 32 + b;
-                        if (c < ccnt) {
-                            u32 bb = cfirst + c;
-                            if (!same || a < bb) record_hit(es, a, bb);
-                        }
+                    while (__any_sync(0xffffffffu, hv[i] != 0u)) {
+                        bool ok = hv[i] != 0u;
+                        u32 b = ok ? (u32)__ffs(hv[i]) - 1 : 0u;
+                        hv[i] &= hv[i] - 1;
+                        const u32 c = i * 32 + b, bb = cfirst + c;
+                        ok = ok && c < ccnt && (!same || a < bb);
+                        bool ab = false, ba = false;
+                        if (ok) { ab = es.freq[bb] <= ta; ba = fa <= es.thr[bb]; }
+                        wb_emit(wb, es, ab, ba, a, bb);
                     }
                 }
             }
         }
     }
+    wb_flush(wb, es);
     if (lane == 0 && evaluated) atomicAdd(pairs_eval, (unsigned long long)evaluated);
 }
 

@@ -600,8 +600,11 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     } else {
         for (;;) {
             CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
-            for (int i = 0; i < 4; i++) LAUNCH(label_sweep_kernel, egrid, 256, edges, n_edges, label, sc);
-            sweeps += 4;
+            for (int i = 0; i < 2; i++) {
+                LAUNCH(label_sweep_kernel, egrid, 256, edges, n_edges, label, sc);
+                LAUNCH(label_jump_kernel, grid_for(U, 256), 256, U, label, sc);
+            }
+            sweeps += 2;
             rc = read_scalars(ctx);
             if (rc) return rc;
             if (!ctx->h_sc->changed) break;
