@@ -45,6 +45,61 @@ __global__ void __launch_bounds__(256) label_jump_kernel(u32 n_unique, unsigned 
     if (__any_sync(0xffffffffu, any) && lane_id() == 0) sc->changed = 1;
 }
 
+// ---- two-phase fixpoint: mutual components first, then the contracted graph ----
+// An edge (s,d) whose reverse (d,s) also passed the count rule is MUTUAL: s and d reach each other, so they end
+// with the same label.  Among frequency-1 UMIs every edge is mutual (1 >= 2*1-1) and their components can have a
+// large diameter, which is what made plain propagation need tens of sweeps on hot loci.
+//   Phase A  min-label connected components over the mutual edges only, with hooking (the smaller label is
+//            written to the current root of the other side) and pointer jumping: O(log) rounds.  Invariant:
+//            label[v] is always the priority of a UMI in v's own mutual component, so hooking is sound.
+//   Phase B  min-label propagation over ALL edges on the contracted graph (one entry per mutual component,
+//            comp[v] = its minimum-priority member): depth = chains of one-way edges, which follow strictly
+//            falling frequency and are short.
+// The fixpoint is the same unique one (label[v] = earliest visited UMI reaching v).
+__global__ void __launch_bounds__(256) sv_hook_kernel(const uint2 *__restrict__ edges, u64 n_edges, const i32 *__restrict__ freq,
+                                                      const i32 *__restrict__ thr, unsigned long long *label, DevScalars *sc) {
+    u64 stride = (u64)gridDim.x * 256;
+    u32 any = 0;
+    for (u64 e = (u64)blockIdx.x * 256 + threadIdx.x; e < n_edges; e += stride) {
+        uint2 ed = edges[e];
+        if (freq[ed.x] > thr[ed.y]) continue;                 // reverse edge did not pass the rule: one-way
+        unsigned long long ls = label[ed.x], ld = label[ed.y];
+        if (ls < ld) { atomicMin(&label[(u32)ld], ls); atomicMin(&label[ed.y], ls); any = 1; }
+    }
+    if (__any_sync(0xffffffffu, any) && lane_id() == 0) sc->changed = 1;
+}
+__global__ void __launch_bounds__(256) comp_from_label_kernel(u32 n_unique, const unsigned long long *__restrict__ label, u32 *__restrict__ comp) {
+    u32 v = blockIdx.x * 256 + threadIdx.x;
+    if (v < n_unique) comp[v] = (u32)label[v];
+}
+__global__ void __launch_bounds__(256) contracted_sweep_kernel(const uint2 *__restrict__ edges, u64 n_edges, const u32 *__restrict__ comp,
+                                                               unsigned long long *label, DevScalars *sc) {
+    u64 stride = (u64)gridDim.x * 256;
+    u32 any = 0;
+    for (u64 e = (u64)blockIdx.x * 256 + threadIdx.x; e < n_edges; e += stride) {
+        uint2 ed = edges[e];
+        u32 cs = comp[ed.x], cd = comp[ed.y];
+        if (cs == cd) continue;
+        unsigned long long ms = label[cs];
+        if (ms < label[cd]) { atomicMin(&label[cd], ms); any = 1; }
+    }
+    if (__any_sync(0xffffffffu, any) && lane_id() == 0) sc->changed = 1;
+}
+__global__ void __launch_bounds__(256) contracted_jump_kernel(u32 n_unique, const u32 *__restrict__ comp, unsigned long long *label, DevScalars *sc) {
+    u32 c = blockIdx.x * 256 + threadIdx.x;
+    u32 any = 0;
+    if (c < n_unique && comp[c] == c) {
+        unsigned long long l = label[c];
+        u32 r = comp[(u32)l];
+        if (r != c) { unsigned long long lr = label[r]; if (lr < l) { atomicMin(&label[c], lr); any = 1; } }
+    }
+    if (__any_sync(0xffffffffu, any) && lane_id() == 0) sc->changed = 1;
+}
+__global__ void __launch_bounds__(256) expand_labels_kernel(u32 n_unique, const u32 *__restrict__ comp, unsigned long long *label) {
+    u32 v = blockIdx.x * 256 + threadIdx.x;
+    if (v < n_unique) { u32 c = comp[v]; if (c != v) label[v] = label[c]; }
+}
+
 // keep[u] = (root(u) == u); root id = low 32 bits of the label
 __global__ void __launch_bounds__(256) keep_from_label_kernel(u32 n_unique, const unsigned long long *__restrict__ label,
                                                               u8 *__restrict__ keep) {

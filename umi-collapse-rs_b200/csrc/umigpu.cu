@@ -42,7 +42,7 @@ struct umigpu_ctx {
 
     DevBuf d_key[2][2], d_idx[2], d_hist, d_tiles;
     DevBuf d_useg, d_rep, d_planes, d_nplane, d_bhead, d_wsum, d_read_uid, d_freq, d_thr, d_repidx, d_label, d_prio;
-    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_onehot, d_tileoff, d_tsum, d_tilestate, d_bsum, d_blkoff, d_blkfirst, d_blkcnt, d_eq, d_pairs;
+    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_onehot, d_tileoff, d_tsum, d_tilestate, d_bsum, d_blkoff, d_blkfirst, d_blkcnt, d_eq, d_pairs, d_comp;
 
     // results
     bool ran = false;
@@ -147,7 +147,7 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
                       &ctx->d_hist, &ctx->d_tiles, &ctx->d_useg, &ctx->d_rep, &ctx->d_planes, &ctx->d_nplane, &ctx->d_bhead, &ctx->d_wsum,
                       &ctx->d_read_uid, &ctx->d_freq, &ctx->d_thr, &ctx->d_repidx, &ctx->d_label, &ctx->d_prio, &ctx->d_bstart, &ctx->d_itemoff,
                       &ctx->d_items, &ctx->d_edges, &ctx->d_keep, &ctx->d_state, &ctx->d_blocked, &ctx->d_bitmap, &ctx->d_kept, &ctx->d_roots,
-                      &ctx->d_onehot, &ctx->d_tileoff, &ctx->d_tsum, &ctx->d_tilestate, &ctx->d_bsum, &ctx->d_blkoff, &ctx->d_blkfirst, &ctx->d_blkcnt, &ctx->d_eq, &ctx->d_pairs};
+                      &ctx->d_onehot, &ctx->d_tileoff, &ctx->d_tsum, &ctx->d_tilestate, &ctx->d_bsum, &ctx->d_blkoff, &ctx->d_blkfirst, &ctx->d_blkcnt, &ctx->d_eq, &ctx->d_pairs, &ctx->d_comp};
     for (DevBuf *b : bufs) b->release();
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
     if (ctx->h_kept) cudaFreeHost(ctx->h_kept);
@@ -598,10 +598,24 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
         LAUNCH(mis_label_kernel, egrid, 256, edges, n_edges, prio, (const u8 *)ctx->d_state.p, label);
         LAUNCH(mis_keep_kernel, grid_for(U, 256), 256, U, (const u8 *)ctx->d_state.p, keep);
     } else {
+      if (n_edges < (8u << 20)) {
+        // small edge lists: plain sweeps converge in a handful of launches and have the lowest fixed cost
+        for (;;) {
+            CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
+            for (int i = 0; i < 4; i++) LAUNCH(label_sweep_kernel, egrid, 256, edges, n_edges, label, sc);
+            sweeps += 4;
+            rc = read_scalars(ctx);
+            if (rc) return rc;
+            if (!ctx->h_sc->changed) break;
+        }
+      } else {
+        // Phase A: mutual components (hook + jump), Phase B: contracted propagation (cluster.cuh)
+        CK(ctx->d_comp.reserve((size_t)U * 4));
+        u32 *comp = ctx->d_comp.as<u32>();
         for (;;) {
             CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
             for (int i = 0; i < 2; i++) {
-                LAUNCH(label_sweep_kernel, egrid, 256, edges, n_edges, label, sc);
+                LAUNCH(sv_hook_kernel, egrid, 256, edges, n_edges, (const i32 *)ctx->d_freq.p, (const i32 *)ctx->d_thr.p, label, sc);
                 LAUNCH(label_jump_kernel, grid_for(U, 256), 256, U, label, sc);
             }
             sweeps += 2;
@@ -609,6 +623,20 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
             if (rc) return rc;
             if (!ctx->h_sc->changed) break;
         }
+        LAUNCH(comp_from_label_kernel, grid_for(U, 256), 256, U, (const unsigned long long *)label, comp);
+        for (;;) {
+            CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
+            for (int i = 0; i < 2; i++) {
+                LAUNCH(contracted_sweep_kernel, egrid, 256, edges, n_edges, (const u32 *)comp, label, sc);
+                LAUNCH(contracted_jump_kernel, grid_for(U, 256), 256, U, (const u32 *)comp, label, sc);
+            }
+            sweeps += 2;
+            rc = read_scalars(ctx);
+            if (rc) return rc;
+            if (!ctx->h_sc->changed) break;
+        }
+        LAUNCH(expand_labels_kernel, grid_for(U, 256), 256, U, (const u32 *)comp, label);
+      }
         LAUNCH(keep_from_label_kernel, grid_for(U, 256), 256, U, (const unsigned long long *)label, keep);
     }
     ctx->ctr.n_sweeps = sweeps;
