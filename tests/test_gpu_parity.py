@@ -324,3 +324,31 @@ def test_sharded_matches_unsharded():
     okept, _, octr = O.dedup(d["tid"], d["pos"], d["rev"], d["umi"], d["score"], O.ALGO_DIR, O.MERGE_AVGQUAL, 1, 0.5)
     assert merged.tolist() == okept.tolist()
     assert sum(c["n_buckets"] for c in ctrs) == octr["n_buckets"] and sum(c["total_reads"] for c in ctrs) == len(d["tid"])
+
+
+def test_randomised_configurations_against_oracle():
+    """Many small random workloads over the whole parameter space (length, k, p, algo, merge, alphabet, bucket shape):
+    the CUDA path must agree with the oracle on the kept reads, the cluster roots and the counters every time."""
+    rng = random.Random(20261018)
+    algos = [umigpu.ALGO_DIR, umigpu.ALGO_DIR, umigpu.ALGO_CC, umigpu.ALGO_ADJ_UPSTREAM, umigpu.ALGO_ADJ]
+    for trial in range(60):
+        L = rng.choice([3, 4, 5, 6, 7, 9, 11, 13, 18, 21, 25, 32])
+        alphabet = rng.choice(["ACGT", "ACGT", "AC", "ACGTN"]) if L <= 21 else rng.choice(["ACGT", "AC"])
+        n = rng.choice([1, 2, 33, 500, 3000, 9000])
+        n_pos = rng.choice([1, 1, 2, 7, 60])
+        pool = ["".join(rng.choice(alphabet) for _ in range(L)) for _ in range(rng.choice([1, 3, 40, 400]))]
+        tid = np.array([rng.randrange(2) for _ in range(n)], np.int32)
+        pos = np.array([rng.randrange(n_pos) * 1000 - 5 for _ in range(n)], np.int64)
+        rev = np.array([rng.randrange(2) for _ in range(n)], np.uint8)
+        umis = []
+        for _ in range(n):
+            u = list(rng.choice(pool))
+            for _ in range(rng.choice([0, 0, 1, 2])):
+                u[rng.randrange(L)] = rng.choice(alphabet)
+            umis.append("".join(u))
+        score = np.array([rng.randrange(0, 5) for _ in range(n)], np.int32)
+        d = dict(tid=tid, pos=pos, rev=rev, umi=arr(umis), score=score)
+        algo, merge = rng.choice(algos), rng.choice([umigpu.MERGE_ANY, umigpu.MERGE_AVGQUAL, umigpu.MERGE_MAPQUAL])
+        k, p = rng.choice([0, 1, 1, 2, 3, 4]), rng.choice([0.5, 0.5, 0.2, 0.9])
+        flags = rng.choice([0, 0, umigpu.FLAG_NO_CULL, umigpu.FLAG_KERNEL_TILES, umigpu.FLAG_KERNEL_DIRECT])
+        check_against_oracle(d, algo, merge, k, p, flags=flags, chunk=rng.choice([0, 0, 257]), labels=True)
