@@ -35,6 +35,7 @@ struct UniqueEmit {
     int L, has_n;
     u32 *useg;            // [U+1] first sorted position of each unique
     uint2 *planes; u32 *nplane;
+    u64 *ucode;           // the unique's sort code (2 or 3 bits per base): letter j = (code >> bpb*j) & mask
     u8 *bhead;            // unique starts a new bucket
     unsigned long long *rep;   // packed (score biased << 32 | ~read idx), max wins
     i32 *wsum;            // weighted freq (only with weights)
@@ -48,6 +49,7 @@ struct UniqueEmit {
             u32 p0, p1, pn;
             code_to_planes(code, L, has_n, p0, p1, pn);
             planes[uid] = make_uint2(p0, p1);
+            ucode[uid] = code;
             if (has_n) nplane[uid] = pn;
             bhead[uid] = (i == 0 || !sk.same_bucket(i, i - 1)) ? 1 : 0;
         }

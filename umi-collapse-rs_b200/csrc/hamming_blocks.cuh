@@ -135,7 +135,7 @@ template <int LP, int K, bool HASN>
 __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ pairs, u64 n_pairs, const u32 *__restrict__ blk_first,
                                                       const u32 *__restrict__ blk_cnt, const u32 *__restrict__ bsum,
                                                       const uint2 *__restrict__ planes, const u32 *__restrict__ nplane,
-                                                      const uint4 *__restrict__ eq, int L, int cull, EdgeSink es,
+                                                      const u64 *__restrict__ ucode, const uint4 *__restrict__ eq, int L, int cull, EdgeSink es,
                                                       unsigned long long *pairs_eval) {
     constexpr int XS = HASN ? 8 : 4;
     constexpr int NLET = HASN ? 5 : 4;
@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
             const bool valid = r < rcnt;
             const uint2 rp = valid ? planes[rfirst + r] : make_uint2(0u, 0u);
             const u32 rn = (HASN && valid) ? nplane[rfirst + r] : 0u;
+            const u64 rc = valid ? ucode[rfirst + r] : 0ull;
             if (cull && !same) {
                 // the 32 rows of a slice are consecutive sorted UMIs: few letters per position
                 u32 oh[5], t = 0;
@@ -172,12 +173,10 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
             uint4 h = make_uint4(0u, 0u, 0u, 0u);
             if (valid) {
                 u32 off[LP];                                   // uint4 index of the row's letter slot at position j
+                // the letter at position j straight from the interleaved sort code: one shift + one mask
+                constexpr int BPB = HASN ? 3 : 2;
 #pragma unroll
-                for (int j = 0; j < LP; j++) {
-                    u32 letter = ((rp.y >> j) & 1u) * 2u + ((rp.x >> j) & 1u);
-                    if (HASN && ((rn >> j) & 1u)) letter = 4u;
-                    off[j] = (u32)(j * XS) + letter;
-                }
+                for (int j = 0; j < LP; j++) off[j] = (u32)(j * XS) + ((u32)(rc >> (BPB * j)) & (HASN ? 7u : 3u));
                 uint4 m1 = make_uint4(~0u, ~0u, ~0u, ~0u), m2 = m1, m3 = m1, m4 = m1;
 #pragma unroll
                 for (int j = 0; j < LP; j++) {
@@ -220,14 +219,14 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
 
 template <int LP, int K, bool HASN>
 static int blk_launch_one(cudaStream_t stream, int num_sms, const uint2 *pairs, u64 n_pairs, const u32 *blk_first, const u32 *blk_cnt,
-                          const u32 *bsum, const uint2 *planes, const u32 *nplane, const uint4 *eq, int L, int cull, EdgeSink es,
+                          const u32 *bsum, const uint2 *planes, const u32 *nplane, const u64 *ucode, const uint4 *eq, int L, int cull, EdgeSink es,
                           unsigned long long *pairs_eval) {
     auto kern = hamming_blocks<LP, K, HASN>;
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0) != cudaSuccess || occ < 1) occ = 1;
     u32 grid = (u32)std::min<u64>((n_pairs + 7) / 8, (u64)num_sms * occ * 4);
     if (grid == 0) return 0;
-    kern<<<grid, 256, 0, stream>>>(pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, eq, L, cull, es, pairs_eval);
+    kern<<<grid, 256, 0, stream>>>(pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, pairs_eval);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -235,9 +234,9 @@ static inline int blk_lp(int L) { return L <= 8 ? 8 : L <= 12 ? 12 : L <= 16 ? 1
 
 template <int K, bool HASN>
 static int blk_launch_k(cudaStream_t stream, int num_sms, const uint2 *pairs, u64 n_pairs, const u32 *blk_first, const u32 *blk_cnt,
-                        const u32 *bsum, const uint2 *planes, const u32 *nplane, const uint4 *eq, int L, int cull, EdgeSink es,
+                        const u32 *bsum, const uint2 *planes, const u32 *nplane, const u64 *ucode, const uint4 *eq, int L, int cull, EdgeSink es,
                         unsigned long long *pairs_eval) {
-#define BLK_ARGS stream, num_sms, pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, eq, L, cull, es, pairs_eval
+#define BLK_ARGS stream, num_sms, pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, pairs_eval
     switch (blk_lp(L)) {
     case 8:  return blk_launch_one<8, K, HASN>(BLK_ARGS);
     case 12: return blk_launch_one<12, K, HASN>(BLK_ARGS);
@@ -250,9 +249,9 @@ static int blk_launch_k(cudaStream_t stream, int num_sms, const uint2 *pairs, u6
 
 // returns 0 = launched, 1 = configuration not covered (k outside 1..3), -1 = CUDA error
 static int launch_neighbours_blocks(cudaStream_t stream, int num_sms, const uint2 *pairs, u64 n_pairs, const u32 *blk_first,
-                                    const u32 *blk_cnt, const u32 *bsum, const uint2 *planes, const u32 *nplane, const uint4 *eq,
-                                    int L, int k, bool has_n, int cull, EdgeSink es, unsigned long long *pairs_eval) {
-#define BLK_ARGS stream, num_sms, pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, eq, L, cull, es, pairs_eval
+                                    const u32 *blk_cnt, const u32 *bsum, const uint2 *planes, const u32 *nplane, const u64 *ucode,
+                                    const uint4 *eq, int L, int k, bool has_n, int cull, EdgeSink es, unsigned long long *pairs_eval) {
+#define BLK_ARGS stream, num_sms, pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, pairs_eval
     if (k < 1 || k > 3) return 1;
     if (!has_n) {
         if (k == 1) return blk_launch_k<1, false>(BLK_ARGS);

@@ -97,22 +97,22 @@ __device__ __forceinline__ void rs_rank_tile(u32 *packed /* in: digit or 0xfffff
     for (int j = 0; j < ITEMS; j++) {
         const u32 d = packed[j];
         const bool active = d != 0xffffffffu;
-        // lanes holding the same digit: eight ballots (one per digit bit) instead of MATCH.ANY, whose cost
-        // grows with the number of distinct values in the warp (up to 32 for the random UMI digits)
+        // lanes holding the same digit: eight ballots (one per digit bit) instead of MATCH.ANY, whose cost grows
+        // with the number of distinct values in the warp (up to 32 for the random UMI digits).  Every lane takes
+        // part in every collective with the full mask (no divergent collectives); lanes past the end are masked
+        // out of the result by `act`.
         u32 peers = __ballot_sync(0xffffffffu, active);
 #pragma unroll
         for (int b = 0; b < 8; b++) {
-            const bool bit = (d >> b) & 1u;
-            const u32 m = __ballot_sync(0xffffffffu, active && bit);
+            const bool bit = (d & (1u << b)) != 0u;
+            const u32 m = __ballot_sync(0xffffffffu, bit);
             peers &= bit ? m : ~m;
         }
-        if (active) {
-            u32 leader = __ffs(peers) - 1;
-            u32 old = 0;
-            if (lane == leader) { old = whist[w][d]; whist[w][d] = old + __popc(peers); }
-            old = __shfl_sync(peers, old, leader);
-            packed[j] = d | ((old + __popc(peers & lt)) << 8);
-        }
+        const u32 leader = active ? (u32)__ffs(peers) - 1u : lane;
+        u32 old = 0;
+        if (active && lane == leader) { old = whist[w][d]; whist[w][d] = old + __popc(peers); }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        if (active) packed[j] = d | ((old + __popc(peers & lt)) << 8);
         __syncwarp();
     }
 }

@@ -42,7 +42,7 @@ struct umigpu_ctx {
 
     DevBuf d_key[2][2], d_idx[2], d_hist, d_tiles;
     DevBuf d_useg, d_rep, d_planes, d_nplane, d_bhead, d_wsum, d_read_uid, d_freq, d_thr, d_repidx, d_label, d_prio;
-    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_onehot, d_tileoff, d_tsum, d_tilestate, d_bsum, d_blkoff, d_blkfirst, d_blkcnt, d_eq, d_pairs, d_comp;
+    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_onehot, d_tileoff, d_tsum, d_tilestate, d_bsum, d_blkoff, d_blkfirst, d_blkcnt, d_eq, d_pairs, d_comp, d_ucode;
 
     // results
     bool ran = false;
@@ -147,7 +147,7 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
                       &ctx->d_hist, &ctx->d_tiles, &ctx->d_useg, &ctx->d_rep, &ctx->d_planes, &ctx->d_nplane, &ctx->d_bhead, &ctx->d_wsum,
                       &ctx->d_read_uid, &ctx->d_freq, &ctx->d_thr, &ctx->d_repidx, &ctx->d_label, &ctx->d_prio, &ctx->d_bstart, &ctx->d_itemoff,
                       &ctx->d_items, &ctx->d_edges, &ctx->d_keep, &ctx->d_state, &ctx->d_blocked, &ctx->d_bitmap, &ctx->d_kept, &ctx->d_roots,
-                      &ctx->d_onehot, &ctx->d_tileoff, &ctx->d_tsum, &ctx->d_tilestate, &ctx->d_bsum, &ctx->d_blkoff, &ctx->d_blkfirst, &ctx->d_blkcnt, &ctx->d_eq, &ctx->d_pairs, &ctx->d_comp};
+                      &ctx->d_onehot, &ctx->d_tileoff, &ctx->d_tsum, &ctx->d_tilestate, &ctx->d_bsum, &ctx->d_blkoff, &ctx->d_blkfirst, &ctx->d_blkcnt, &ctx->d_eq, &ctx->d_pairs, &ctx->d_comp, &ctx->d_ucode};
     for (DevBuf *b : bufs) b->release();
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
     if (ctx->h_kept) cudaFreeHost(ctx->h_kept);
@@ -460,6 +460,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     CK(ctx->d_useg.reserve((n + 1) * 4));
     CK(ctx->d_rep.reserve(n * 8));
     CK(ctx->d_planes.reserve(n * 8));
+    CK(ctx->d_ucode.reserve(n * 8));
     if (has_n) CK(ctx->d_nplane.reserve(n * 4));
     CK(ctx->d_bhead.reserve(n));
     const bool weighted = ctx->have_weight == 1;
@@ -470,7 +471,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     UniqueEmit ue;
     ue.sk = sk; ue.n = n; ue.idx = sorted_idx; ue.score = use_score ? ctx->d_score.as<i32>() : nullptr;
     ue.weight = weighted ? ctx->d_weight.as<i32>() : nullptr; ue.L = lay.umi_len; ue.has_n = lay.has_n;
-    ue.useg = ctx->d_useg.as<u32>(); ue.planes = ctx->d_planes.as<uint2>(); ue.nplane = ctx->d_nplane.as<u32>();
+    ue.useg = ctx->d_useg.as<u32>(); ue.planes = ctx->d_planes.as<uint2>(); ue.nplane = ctx->d_nplane.as<u32>(); ue.ucode = ctx->d_ucode.as<u64>();
     ue.bhead = ctx->d_bhead.as<u8>(); ue.rep = ctx->d_rep.as<unsigned long long>(); ue.wsum = ctx->d_wsum.as<i32>();
     ue.read_uid = want_labels ? ctx->d_read_uid.as<u32>() : nullptr;
     rc = run_scan(ctx, HeadFlag{sk}, ue, n, &sc->n_unique);
@@ -710,7 +711,7 @@ static int launch_neighbours(umigpu_ctx *ctx, u32 n_items, EdgeSink es, bool has
                ctx->d_pairs.as<uint2>(), (unsigned long long *)&sc->n_block_pairs);
         rc = launch_neighbours_blocks(ctx->stream, ctx->num_sms, ctx->d_pairs.as<uint2>(), n_pairs, (const u32 *)ctx->d_blkfirst.p,
                                       (const u32 *)ctx->d_blkcnt.p, (const u32 *)ctx->d_bsum.p, planes, has_n ? nplane : (const u32 *)nullptr,
-                                      ctx->d_eq.as<uint4>(), L, k, has_n, cull, es, (unsigned long long *)&sc->pairs_eval);
+                                      (const u64 *)ctx->d_ucode.p, ctx->d_eq.as<uint4>(), L, k, has_n, cull, es, (unsigned long long *)&sc->pairs_eval);
         if (rc < 0) return fail(ctx, UMIGPU_ERR_CUDA, "block-pair neighbour kernel: %s", cudaGetErrorString(cudaGetLastError()));
         if (rc == 0) { ctx->launches += 1; ctx->ctr.n_block_pairs = n_pairs; CK(cudaGetLastError()); return UMIGPU_OK; }
       }
