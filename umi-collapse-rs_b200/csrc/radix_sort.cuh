@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) radix_digit_starts(u32 *ghist, int npass)
 
 // Ranks the thread's keys by digit.  packed[j] = digit | (rank within (warp, digit) << 8), or
 // 0xffffffff past the end.  On return whist[w][d] = number of keys with digit d in warp w's slice.
-template <int ITEMS>
+template <int ITEMS, bool FULL>
 __device__ __forceinline__ void rs_rank_tile(u32 *packed /* in: digit or 0xffffffff */, u32 (*whist)[256]) {
     const u32 w = threadIdx.x >> 5, lane = lane_id();
     for (u32 i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&whist[0][0])[i] = 0;
@@ -96,12 +96,12 @@ __device__ __forceinline__ void rs_rank_tile(u32 *packed /* in: digit or 0xfffff
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         const u32 d = packed[j];
-        const bool active = d != 0xffffffffu;
+        const bool active = FULL || d != 0xffffffffu;
         // lanes holding the same digit: eight ballots (one per digit bit) instead of MATCH.ANY, whose cost grows
         // with the number of distinct values in the warp (up to 32 for the random UMI digits).  Every lane takes
         // part in every collective with the full mask (no divergent collectives); lanes past the end are masked
         // out of the result by `act`.
-        u32 peers = __ballot_sync(0xffffffffu, active);
+        u32 peers = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, active);
 #pragma unroll
         for (int b = 0; b < 8; b++) {
             const bool bit = (d & (1u << b)) != 0u;
@@ -121,23 +121,23 @@ __device__ __forceinline__ void rs_rank_tile(u32 *packed /* in: digit or 0xfffff
 // global writes of a warp are runs of consecutive addresses (one run per digit) instead of 32
 // unrelated 8-byte fragments.  err[0] is set if a look-back ever exceeds its spin budget (cannot
 // happen with ticketed tiles; it turns a would-be hang into a reported error).
-template <int NW, int ITEMS>
-__global__ void __launch_bounds__(RS_THREADS, (NW == 1 ? 2 : 1)) radix_onesweep(
+struct RsShared {
+    u32 whist[RS_WARPS][256];
+    u32 sbase[256], slocal[256];
+    u32 sscan[RS_THREADS / 32 + 1];
+    u32 s_tile;
+};
+
+// FULL = the tile has all TILE keys: no per-key bounds checks anywhere (all tiles but the last)
+template <int NW, int ITEMS, bool FULL>
+__device__ __forceinline__ void rs_onesweep_body(
+    RsShared &S, u64 *skey, u32 *sidx, const u32 tile, const u32 tile_count,
     KeyArr in, const u32 *__restrict__ idx_in, KeyArr out, u32 *__restrict__ idx_out, u64 n, int wsel, int sh, u32 mask,
-    const u32 *__restrict__ digit_start, unsigned long long *tile_state /* [ntiles][256] */, u32 *ticket, u32 *err, int iota) {
+    const u32 *__restrict__ digit_start, unsigned long long *tile_state, u32 *err, int iota) {
     constexpr u32 TILE = RS_THREADS * ITEMS;
-    extern __shared__ __align__(16) unsigned char rs_dyn[];          // u64 skey[NW][TILE]; u32 sidx[TILE]
-    u64 *skey = reinterpret_cast<u64 *>(rs_dyn);
-    u32 *sidx = reinterpret_cast<u32 *>(rs_dyn + (size_t)NW * TILE * 8);
-    __shared__ u32 whist[RS_WARPS][256];
-    __shared__ u32 sbase[256], slocal[256];
-    __shared__ u32 sscan[RS_THREADS / 32 + 1];
-    __shared__ u32 s_tile;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const u32 tile = s_tile;
+    u32 (*whist)[256] = S.whist;
+    u32 *sbase = S.sbase, *slocal = S.slocal, *sscan = S.sscan;
     const u64 tile_base = (u64)tile * TILE;
-    const u32 tile_count = (u32)min((u64)TILE, n - tile_base);
     const u32 w = threadIdx.x >> 5, lane = lane_id();
     u32 packed[ITEMS], vidx[ITEMS];
     u64 key[NW][ITEMS];
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(RS_THREADS, (NW == 1 ? 2 : 1)) radix_onesweep(
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         u64 i = tile_base + (u64)(w * ITEMS + j) * 32 + lane;
-        bool a = i < n;
+        bool a = FULL || i < n;
 #pragma unroll
         for (int k = 0; k < NW; k++) key[k][j] = a ? in.w[k][i] : 0;
         vidx[j] = a ? (iota ? (u32)i : idx_in[i]) : 0;
@@ -154,9 +154,9 @@ __global__ void __launch_bounds__(RS_THREADS, (NW == 1 ? 2 : 1)) radix_onesweep(
     for (int j = 0; j < ITEMS; j++) {
         u64 i = tile_base + (u64)(w * ITEMS + j) * 32 + lane;
         u64 kw = NW == 1 ? key[0][j] : (wsel == 0 ? key[0][j] : key[NW - 1][j]);
-        packed[j] = i < n ? ((u32)(kw >> sh) & mask) : 0xffffffffu;
+        packed[j] = (FULL || i < n) ? ((u32)(kw >> sh) & mask) : 0xffffffffu;
     }
-    rs_rank_tile<ITEMS>(packed, whist);
+    rs_rank_tile<ITEMS, FULL>(packed, whist);
     __syncthreads();
     u32 total = 0;
     if (threadIdx.x < 256) {
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(RS_THREADS, (NW == 1 ? 2 : 1)) radix_onesweep(
     // permute the tile into digit order in shared memory
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
-        if (packed[j] != 0xffffffffu) {
+        if (FULL || packed[j] != 0xffffffffu) {
             const u32 d = packed[j] & 0xff, r = packed[j] >> 8;
             const u32 lp = slocal[d] + whist[w][d] + r;
 #pragma unroll
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(RS_THREADS, (NW == 1 ? 2 : 1)) radix_onesweep(
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         const u32 i = threadIdx.x + j * RS_THREADS;
-        if (i < tile_count) {
+        if (FULL || i < tile_count) {
             u64 kk[NW];
 #pragma unroll
             for (int k = 0; k < NW; k++) kk[k] = skey[(size_t)k * TILE + i];
@@ -231,6 +231,25 @@ __global__ void __launch_bounds__(RS_THREADS, (NW == 1 ? 2 : 1)) radix_onesweep(
             idx_out[pos] = sidx[i];
         }
     }
+}
+
+template <int NW, int ITEMS>
+__global__ void __launch_bounds__(RS_THREADS, (NW == 1 ? 2 : 1)) radix_onesweep(
+    KeyArr in, const u32 *__restrict__ idx_in, KeyArr out, u32 *__restrict__ idx_out, u64 n, int wsel, int sh, u32 mask,
+    const u32 *__restrict__ digit_start, unsigned long long *tile_state /* [ntiles][256] */, u32 *ticket, u32 *err, int iota) {
+    constexpr u32 TILE = RS_THREADS * ITEMS;
+    extern __shared__ __align__(16) unsigned char rs_dyn[];          // u64 skey[NW][TILE]; u32 sidx[TILE]
+    u64 *skey = reinterpret_cast<u64 *>(rs_dyn);
+    u32 *sidx = reinterpret_cast<u32 *>(rs_dyn + (size_t)NW * TILE * 8);
+    __shared__ RsShared S;
+    if (threadIdx.x == 0) S.s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 tile = S.s_tile;
+    const u32 tile_count = (u32)min((u64)TILE, n - (u64)tile * TILE);
+    if (tile_count == TILE)
+        rs_onesweep_body<NW, ITEMS, true>(S, skey, sidx, tile, tile_count, in, idx_in, out, idx_out, n, wsel, sh, mask, digit_start, tile_state, err, iota);
+    else
+        rs_onesweep_body<NW, ITEMS, false>(S, skey, sidx, tile, tile_count, in, idx_in, out, idx_out, n, wsel, sh, mask, digit_start, tile_state, err, iota);
 }
 
 // Plans the passes that cover bit range [0, total_bits) of the key without straddling a word.
