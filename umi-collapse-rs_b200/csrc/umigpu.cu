@@ -357,7 +357,9 @@ extern "C" int umigpu_push_bam_records(umigpu_ctx *ctx, uint64_t n, const uint8_
 #define RS_ITEMS_2 8      // keys per thread, two-word keys  (tile 4096)
 static int run_sort(umigpu_ctx *ctx, u64 n, int nw, const SortPlan &plan, int *cur_out) {
     DevScalars *sc = ctx->d_sc.as<DevScalars>();
-    const u32 tile = RS_THREADS * (nw == 1 ? RS_ITEMS_1 : RS_ITEMS_2);
+    static int items1 = 0;
+    if (!items1) { const char *e = getenv("UMIGPU_RS_ITEMS"); items1 = e ? atoi(e) : RS_ITEMS_1; if (items1 != 8 && items1 != 12 && items1 != 16) items1 = RS_ITEMS_1; }
+    const u32 tile = RS_THREADS * (nw == 1 ? items1 : RS_ITEMS_2);
     const u32 ntiles = (u32)ceil_div_u64(n, tile);
     CK(ctx->d_hist.reserve((size_t)RS_MAX_PASSES * 256 * sizeof(u32)));
     CK(ctx->d_tilestate.reserve((size_t)ntiles * 256 * 8));
@@ -377,9 +379,10 @@ static int run_sort(umigpu_ctx *ctx, u64 n, int nw, const SortPlan &plan, int *c
         CK(cudaMemsetAsync(ctx->d_tilestate.p, 0, (size_t)ntiles * 256 * 8, ctx->stream));
         CK(cudaMemsetAsync(&sc->sort_ticket, 0, 4, ctx->stream));
         const size_t dyn = (size_t)tile * (nw * 8 + 4);
-        if (nw == 1)
-            LAUNCH_SMEM((radix_onesweep<1, RS_ITEMS_1>), ntiles, RS_THREADS, dyn, in, (const u32 *)ctx->d_idx[cur].as<u32>(), out, ctx->d_idx[cur ^ 1].as<u32>(), n,
-                   p.word, p.shift, mask, (const u32 *)(ghist + pi * 256), ctx->d_tilestate.as<unsigned long long>(), &sc->sort_ticket, &sc->sort_err, pi == 0 ? 1 : 0);
+#define RS_LAUNCH1(IT) LAUNCH_SMEM((radix_onesweep<1, IT>), ntiles, RS_THREADS, dyn, in, (const u32 *)ctx->d_idx[cur].as<u32>(), out, ctx->d_idx[cur ^ 1].as<u32>(), n, \
+                   p.word, p.shift, mask, (const u32 *)(ghist + pi * 256), ctx->d_tilestate.as<unsigned long long>(), &sc->sort_ticket, &sc->sort_err, pi == 0 ? 1 : 0)
+        if (nw == 1) { if (items1 == 8) RS_LAUNCH1(8); else if (items1 == 16) RS_LAUNCH1(16); else RS_LAUNCH1(12); }
+#undef RS_LAUNCH1
         else
             LAUNCH_SMEM((radix_onesweep<2, RS_ITEMS_2>), ntiles, RS_THREADS, dyn, in, (const u32 *)ctx->d_idx[cur].as<u32>(), out, ctx->d_idx[cur ^ 1].as<u32>(), n,
                    p.word, p.shift, mask, (const u32 *)(ghist + pi * 256), ctx->d_tilestate.as<unsigned long long>(), &sc->sort_ticket, &sc->sort_err, pi == 0 ? 1 : 0);
