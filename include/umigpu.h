@@ -54,6 +54,7 @@ extern "C" {
 #define UMIGPU_FLAG_LABELS        1u  /* also produce the per-read cluster root (ClusterTracker, --tag) */
 #define UMIGPU_FLAG_NO_CULL       2u  /* evaluate every tile pair (disable exact prefix culling)        */
 #define UMIGPU_FLAG_KERNEL_DIRECT 4u  /* use the direct XOR+popcount tile kernel instead of bit-sliced  */
+#define UMIGPU_FLAG_NO_MULTI_INDEX 16u /* big buckets in one pass (disable the pigeonhole multi-index passes) */
 #define UMIGPU_FLAG_KERNEL_TILES  8u  /* use the shared-memory tile form of the bit-sliced kernel instead of
                                          the block-pair list form                                        */
 

@@ -96,7 +96,7 @@ def test_algo_merge_matrix(algo, merge):
 
 
 @pytest.mark.parametrize("flags", [0, umigpu.FLAG_KERNEL_DIRECT, umigpu.FLAG_NO_CULL, umigpu.FLAG_KERNEL_DIRECT | umigpu.FLAG_NO_CULL,
-                                   umigpu.FLAG_KERNEL_TILES, umigpu.FLAG_KERNEL_TILES | umigpu.FLAG_NO_CULL])
+                                   umigpu.FLAG_KERNEL_TILES, umigpu.FLAG_KERNEL_TILES | umigpu.FLAG_NO_CULL, umigpu.FLAG_NO_MULTI_INDEX])
 def test_large_bucket_multi_tile(flags):
     """One hot locus whose unique UMIs span several 2048-wide tiles (diagonal + off-diagonal tiles)."""
     d, _ = small("C2", 0.0008, n_loci=3, zipf_s=2.0, family=1.5, umi_len=8)
@@ -352,3 +352,18 @@ def test_randomised_configurations_against_oracle():
         k, p = rng.choice([0, 1, 1, 2, 3, 4]), rng.choice([0.5, 0.5, 0.2, 0.9])
         flags = rng.choice([0, 0, umigpu.FLAG_NO_CULL, umigpu.FLAG_KERNEL_TILES, umigpu.FLAG_KERNEL_DIRECT])
         check_against_oracle(d, algo, merge, k, p, flags=flags, chunk=rng.choice([0, 0, 257]), labels=True)
+
+
+@pytest.mark.parametrize("k,L,alphabet_n", [(1, 9, 0.0), (2, 9, 0.0), (3, 10, 0.0), (2, 12, 0.0), (1, 11, 0.02), (2, 10, 0.02)])
+def test_multi_index_passes_big_buckets(k, L, alphabet_n):
+    """Buckets above the multi-index threshold (4096 unique UMIs) are searched in k+1 passes, one per UMI part; every
+    pair within k must be found exactly once whatever part its mismatches fall in (edge count, kept set, roots)."""
+    d, _ = small("C2", 0.0012, n_loci=3, zipf_s=1.5, family=1.3, umi_len=L, err=0.3, n_rate=alphabet_n, seed=100 * k + L)
+    res = {}
+    for flags in (0, umigpu.FLAG_NO_MULTI_INDEX):
+        for algo in (umigpu.ALGO_DIR, umigpu.ALGO_CC):
+            ctr = check_against_oracle(d, algo, umigpu.MERGE_AVGQUAL, k, 0.5, flags=flags, labels=True)
+            res[(flags, algo)] = ctr
+    assert res[(0, umigpu.ALGO_DIR)]["max_umis"] > 4096
+    for algo in (umigpu.ALGO_DIR, umigpu.ALGO_CC):
+        assert res[(0, algo)]["n_edges"] == res[(umigpu.FLAG_NO_MULTI_INDEX, algo)]["n_edges"]      # no pair lost, none reported twice

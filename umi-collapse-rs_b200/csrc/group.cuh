@@ -79,12 +79,68 @@ __global__ void __launch_bounds__(256) unique_finalize_kernel(
 
 struct BucketHead { const u8 *bhead; __device__ u32 operator()(u64 u) const { return bhead[u]; } };
 struct BucketEmit {
-    u32 *bstart; u64 n_unique;
+    u32 *bstart; u64 n_unique; u32 *ubkt;      // ubkt[u] = bucket index of unique u
     __device__ void operator()(u64 u, u32 flag, u32 ex) const {
         if (flag) bstart[ex] = (u32)u;
         if (u == n_unique - 1) bstart[ex + flag] = (u32)n_unique;
+        ubkt[u] = ex + flag - 1;
     }
 };
+
+// ---- multi-index (pigeonhole) candidate generation for big buckets ---------------------------------------
+// A pair within Hamming distance k agrees exactly on at least one of k+1 disjoint parts of the UMI.  In the main
+// order (sorted by the whole code) pairs that agree on the top part are close together, but pairs whose mismatch is
+// IN the top part are far apart and cost most of the block pairs that survive letter-set culling.  So a big bucket
+// is processed in k+1 passes: pass q uses an order in which part q is the most significant, only considers blocks
+// whose part-q letter sets intersect at every position (= value ranges overlap: near-diagonal), and reports a pair
+// iff q is the FIRST part on which the two UMIs agree — every pair within k is reported exactly once.
+#define MI_MAX_PARTS 4
+#define MI_BIG 4096u        // buckets with more unique UMIs than this use the multi-index passes
+struct MiParams {
+    int part;                       // -1: off;  q: big buckets are filtered on part q
+    u32 big;                        // "big" threshold on the bucket's unique count
+    u32 pmask[MI_MAX_PARTS];        // plane-position mask of each part
+    unsigned long long cmask[MI_MAX_PARTS];   // code-bit mask of each part
+};
+__device__ __forceinline__ bool mi_accept(const MiParams &mi, unsigned long long ca, unsigned long long cb) {
+    const unsigned long long x = ca ^ cb;
+    if (x & mi.cmask[mi.part]) return false;                 // must agree on this pass's part
+    for (int q = 0; q < mi.part; q++) if (!(x & mi.cmask[q])) return false;   // ... and on no earlier one
+    return true;
+}
+struct BucketIsBig { const u32 *bstart; u32 big; __device__ u32 operator()(u64 b) const { return bstart[b + 1] - bstart[b] > big ? 1u : 0u; } };
+struct BucketBigEmit {
+    u32 *brank, *big_bid; u64 n_buckets;
+    __device__ void operator()(u64 b, u32 flag, u32 ex) const { brank[b] = flag ? ex : 0xffffffffu; if (flag) big_bid[ex] = (u32)b; }
+};
+struct BigSize { const u32 *bstart, *big_bid; __device__ u32 operator()(u64 r) const { u32 b = big_bid[r]; return bstart[b + 1] - bstart[b]; } };
+struct BigStartEmit {
+    u32 *bstart_big; u64 nbig;
+    __device__ void operator()(u64 r, u32 v, u32 ex) const { bstart_big[r] = ex; if (r == nbig - 1) bstart_big[r + 1] = ex + v; }
+};
+// uniques of big buckets, compacted in main order; key of pass q = (big-bucket rank, value of part q)
+__global__ void __launch_bounds__(256) mi_keys_kernel(u32 n_unique, const u32 *__restrict__ ubkt, const u32 *__restrict__ brank,
+                                                      const u32 *__restrict__ bstart, const u32 *__restrict__ bstart_big,
+                                                      const u64 *__restrict__ ucode, int shift, unsigned long long vmask, int pbits,
+                                                      u32 *__restrict__ big_uid, u64 *__restrict__ keys) {
+    u32 u = blockIdx.x * 256 + threadIdx.x;
+    if (u >= n_unique) return;
+    u32 b = ubkt[u], r = brank[b];
+    if (r == 0xffffffffu) return;
+    u32 m = bstart_big[r] + (u - bstart[b]);
+    big_uid[m] = u;
+    keys[m] = ((u64)r << pbits) | ((ucode[u] >> shift) & vmask);
+}
+__global__ void __launch_bounds__(256) mi_gather_kernel(u32 m_total, const u32 *__restrict__ perm, const u32 *__restrict__ big_uid,
+                                                        const uint2 *__restrict__ planes, const u32 *__restrict__ nplane,
+                                                        const u64 *__restrict__ ucode, uint2 *__restrict__ planes_q, u32 *__restrict__ nplane_q,
+                                                        u64 *__restrict__ ucode_q, u32 *__restrict__ uid_q) {
+    u32 m = blockIdx.x * 256 + threadIdx.x;
+    if (m >= m_total) return;
+    u32 u = big_uid[perm[m]];
+    planes_q[m] = planes[u]; ucode_q[m] = ucode[u]; uid_q[m] = u;
+    if (nplane) nplane_q[m] = nplane[u];
+}
 
 // Tile geometry of the neighbour search (rows x cols of unique UMIs of one bucket).
 #define HT_ROWS 2048
@@ -97,6 +153,7 @@ struct TileItem { u32 row_start, col_start, cnts, col_blk0; };
 __device__ __forceinline__ u32 item_row_cnt(const TileItem &it) { return it.cnts & 0xfffu; }
 __device__ __forceinline__ u32 item_col_cnt(const TileItem &it) { return (it.cnts >> 12) & 0xfffu; }
 __device__ __forceinline__ bool item_diag(const TileItem &it) { return it.cnts >> 31; }
+__device__ __forceinline__ bool item_filtered(const TileItem &it) { return (it.cnts >> 30) & 1u; }
 
 __device__ __forceinline__ u32 bucket_tiles(u32 nb) { return (nb + HT_ROWS - 1) / HT_ROWS; }
 
@@ -218,7 +275,7 @@ __device__ __forceinline__ u32 disjoint_positions(const u32 *a, const u32 *b, u3
 __global__ void __launch_bounds__(256) build_items_kernel(u32 n_cand, u32 n_buckets, const u32 *__restrict__ item_off,
                                                           const u32 *__restrict__ bstart, const u32 *__restrict__ tile_off,
                                                           const u32 *__restrict__ blk_off, const u32 *__restrict__ tsum, int L, int k, int cull,
-                                                          TileItem *__restrict__ items, DevScalars *sc) {
+                                                          MiParams mi, TileItem *__restrict__ items, DevScalars *sc) {
     u32 w = blockIdx.x * 256 + threadIdx.x;
     u64 npairs = 0;
     bool live = false;
@@ -243,13 +300,15 @@ __global__ void __launch_bounds__(256) build_items_kernel(u32 n_cand, u32 n_buck
         it.col_start = s + tj * HT_COLS;
         u32 rc = min((u32)HT_ROWS, nb - ti * HT_ROWS);
         u32 cc = min((u32)HT_COLS, nb - tj * HT_COLS);
-        it.cnts = rc | (cc << 12) | (ti == tj ? 0x80000000u : 0u);
+        const bool filt = mi.part >= 0 && nb > mi.big;         // multi-index pass: big buckets only see near-diagonal blocks
+        it.cnts = rc | (cc << 12) | (filt ? 0x40000000u : 0u) | (ti == tj ? 0x80000000u : 0u);
         it.col_blk0 = blk_off[b] + tj * BLOCKS_PER_TILE;
         live = true;
         if (cull && ti != tj) {
             u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
             const u32 *a = tsum + (u64)(tile_off[b] + ti) * TS_WORDS, *c = tsum + (u64)(tile_off[b] + tj) * TS_WORDS;
             live = disjoint_positions(a, c, lmask) <= (u32)k;
+            if (live && filt) live = disjoint_positions(a, c, mi.pmask[mi.part]) == 0;
         }
         if (live) npairs = (u64)rc * cc;
     }

@@ -50,13 +50,13 @@ __global__ void __launch_bounds__(256) onehot_build_kernel(u32 n_groups /* 4 per
 // ---- surviving tile pairs -> surviving (128 x 128) block pairs ----
 // fill == 0: only counts (out_count += survivors); fill == 1: appends uint2(row block, col block)
 __global__ void __launch_bounds__(256) expand_blocks_kernel(const TileItem *__restrict__ items, u32 n_items, const u32 *__restrict__ bsum,
-                                                            int L, int k, int cull, int fill, uint2 *__restrict__ pairs,
+                                                            int L, int k, int cull, MiParams mi, int fill, uint2 *__restrict__ pairs,
                                                             unsigned long long *out_count) {
     const u32 w = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = lane_id();
     if (w >= n_items) return;
     const TileItem it = items[w];
     const u32 nrb = (item_row_cnt(it) + 127) >> 7, ncb = (item_col_cnt(it) + 127) >> 7;
-    const bool diag = item_diag(it);
+    const bool diag = item_diag(it), filt = item_filtered(it);
     const u32 row_blk0 = it.col_blk0 - ((it.col_start - it.row_start) >> 7);
     const u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
     const u32 r = lane & 15, c0 = (lane >> 4) * 8;
@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(256) expand_blocks_kernel(const TileItem *__re
 #pragma unroll
             for (int x = 0; x < 5; x++) cs[x] = bsum[(u64)(it.col_blk0 + c) * 8 + x];
             ok = disjoint_positions(rs, cs, lmask) <= (u32)k;
+            if (ok && filt) ok = disjoint_positions(rs, cs, mi.pmask[mi.part]) == 0;     // part-q value ranges must overlap
         }
         if (ok) live |= 1u << i;
     }
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(256) expand_blocks_kernel(const TileItem *__re
     if (fill) {
         u64 o = base + inc - cnt;
 #pragma unroll
-        for (int i = 0; i < 8; i++) if (live & (1u << i)) pairs[o++] = make_uint2(row_blk0 + r, it.col_blk0 + c0 + i);
+        for (int i = 0; i < 8; i++) if (live & (1u << i)) pairs[o++] = make_uint2((row_blk0 + r) | (filt ? 0x80000000u : 0u), it.col_blk0 + c0 + i);
     }
 }
 
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
                                                       const u32 *__restrict__ blk_cnt, const u32 *__restrict__ bsum,
                                                       const uint2 *__restrict__ planes, const u32 *__restrict__ nplane,
                                                       const u64 *__restrict__ ucode, const uint4 *__restrict__ eq, int L, int cull, EdgeSink es,
-                                                      unsigned long long *pairs_eval) {
+                                                      MiParams mi, const u32 *__restrict__ uidmap, unsigned long long *pairs_eval) {
     constexpr int XS = HASN ? 8 : 4;
     constexpr int NLET = HASN ? 5 : 4;
     const u32 lane = lane_id();
@@ -146,7 +147,9 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
     WarpEdgeBuf wb{s_edges + (threadIdx.x >> 5) * WB_CAP, 0u};
     u64 evaluated = 0;
     for (u64 w = ((u64)blockIdx.x * 256 + threadIdx.x) >> 5; w < n_pairs; w += nwarps) {
-        const uint2 pr = pairs[w];
+        uint2 pr = pairs[w];
+        const bool filt = pr.x >> 31;                 // multi-index pass: report a pair only in the pass of its first equal part
+        pr.x &= 0x7fffffffu;
         const u32 rfirst = blk_first[pr.x], rcnt = blk_cnt[pr.x], cfirst = blk_first[pr.y], ccnt = blk_cnt[pr.y];
         const bool same = pr.x == pr.y;
         u32 cs[5] = {0, 0, 0, 0, 0};
@@ -193,9 +196,10 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
             }
             // ---- hits (rare): warp-uniform loop, one candidate per lane per round ----
             if (__any_sync(0xffffffffu, (h.x | h.y | h.z | h.w) != 0u)) {
-                const u32 a = rfirst + r;
+                const u32 a = rfirst + r;                               // index in this pass's order
+                const u32 ao = (valid && uidmap) ? uidmap[a] : a;       // unique id (edges, freq, thr use the main order)
                 i32 fa = 0, ta = 0;
-                if (valid && (h.x | h.y | h.z | h.w)) { fa = es.freq[a]; ta = es.thr[a]; }
+                if (valid && (h.x | h.y | h.z | h.w)) { fa = es.freq[ao]; ta = es.thr[ao]; }
                 u32 hv[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
@@ -205,9 +209,11 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
                         hv[i] &= hv[i] - 1;
                         const u32 c = i * 32 + b, bb = cfirst + c;
                         ok = ok && c < ccnt && (!same || a < bb);
+                        if (ok && filt) ok = mi_accept(mi, rc, ucode[bb]);
                         bool ab = false, ba = false;
-                        if (ok) { ab = es.freq[bb] <= ta; ba = fa <= es.thr[bb]; }
-                        wb_emit(wb, es, ab, ba, a, bb);
+                        u32 bo = bb;
+                        if (ok) { if (uidmap) bo = uidmap[bb]; ab = es.freq[bo] <= ta; ba = fa <= es.thr[bo]; }
+                        wb_emit(wb, es, ab, ba, ao, bo);
                     }
                 }
             }
@@ -220,13 +226,13 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
 template <int LP, int K, bool HASN>
 static int blk_launch_one(cudaStream_t stream, int num_sms, const uint2 *pairs, u64 n_pairs, const u32 *blk_first, const u32 *blk_cnt,
                           const u32 *bsum, const uint2 *planes, const u32 *nplane, const u64 *ucode, const uint4 *eq, int L, int cull, EdgeSink es,
-                          unsigned long long *pairs_eval) {
+                          MiParams mi, const u32 *uidmap, unsigned long long *pairs_eval) {
     auto kern = hamming_blocks<LP, K, HASN>;
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0) != cudaSuccess || occ < 1) occ = 1;
     u32 grid = (u32)std::min<u64>((n_pairs + 7) / 8, (u64)num_sms * occ * 4);
     if (grid == 0) return 0;
-    kern<<<grid, 256, 0, stream>>>(pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, pairs_eval);
+    kern<<<grid, 256, 0, stream>>>(pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, mi, uidmap, pairs_eval);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -235,8 +241,8 @@ static inline int blk_lp(int L) { return L <= 8 ? 8 : L <= 12 ? 12 : L <= 16 ? 1
 template <int K, bool HASN>
 static int blk_launch_k(cudaStream_t stream, int num_sms, const uint2 *pairs, u64 n_pairs, const u32 *blk_first, const u32 *blk_cnt,
                         const u32 *bsum, const uint2 *planes, const u32 *nplane, const u64 *ucode, const uint4 *eq, int L, int cull, EdgeSink es,
-                        unsigned long long *pairs_eval) {
-#define BLK_ARGS stream, num_sms, pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, pairs_eval
+                        MiParams mi, const u32 *uidmap, unsigned long long *pairs_eval) {
+#define BLK_ARGS stream, num_sms, pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, mi, uidmap, pairs_eval
     switch (blk_lp(L)) {
     case 8:  return blk_launch_one<8, K, HASN>(BLK_ARGS);
     case 12: return blk_launch_one<12, K, HASN>(BLK_ARGS);
@@ -250,8 +256,9 @@ static int blk_launch_k(cudaStream_t stream, int num_sms, const uint2 *pairs, u6
 // returns 0 = launched, 1 = configuration not covered (k outside 1..3), -1 = CUDA error
 static int launch_neighbours_blocks(cudaStream_t stream, int num_sms, const uint2 *pairs, u64 n_pairs, const u32 *blk_first,
                                     const u32 *blk_cnt, const u32 *bsum, const uint2 *planes, const u32 *nplane, const u64 *ucode,
-                                    const uint4 *eq, int L, int k, bool has_n, int cull, EdgeSink es, unsigned long long *pairs_eval) {
-#define BLK_ARGS stream, num_sms, pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, pairs_eval
+                                    const uint4 *eq, int L, int k, bool has_n, int cull, EdgeSink es, MiParams mi, const u32 *uidmap,
+                                    unsigned long long *pairs_eval) {
+#define BLK_ARGS stream, num_sms, pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, mi, uidmap, pairs_eval
     if (k < 1 || k > 3) return 1;
     if (!has_n) {
         if (k == 1) return blk_launch_k<1, false>(BLK_ARGS);

@@ -25,6 +25,7 @@ struct DevScalars {
     u32 bam_err, bam_valid;
     u32 n_blocks, pad0;
     u64 n_block_pairs;
+    u32 n_big, m_big;
 };
 
 struct KeyLayout {

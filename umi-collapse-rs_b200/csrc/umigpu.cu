@@ -42,7 +42,7 @@ struct umigpu_ctx {
 
     DevBuf d_key[2][2], d_idx[2], d_hist, d_tiles;
     DevBuf d_useg, d_rep, d_planes, d_nplane, d_bhead, d_wsum, d_read_uid, d_freq, d_thr, d_repidx, d_label, d_prio;
-    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_onehot, d_tileoff, d_tsum, d_tilestate, d_bsum, d_blkoff, d_blkfirst, d_blkcnt, d_eq, d_pairs, d_comp, d_ucode;
+    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_onehot, d_tileoff, d_tsum, d_tilestate, d_bsum, d_blkoff, d_blkfirst, d_blkcnt, d_eq, d_pairs, d_comp, d_ucode, d_ubkt, d_brank, d_bigbid, d_bstartbig, d_biguid, d_miplanes, d_minplane, d_miucode, d_miuid;
 
     // results
     bool ran = false;
@@ -50,6 +50,7 @@ struct umigpu_ctx {
     u32 n_unique = 0, n_buckets = 0;
     bool used_direct = false;
     u32 n_blocks = 0;
+    u64 direct_pairs = 0;
     u64 n_edges = 0;
     KeyLayout lay;
     u64 *h_kept = nullptr; size_t h_kept_cap = 0;       // pinned; what umigpu_result.kept_read_index points to
@@ -147,7 +148,8 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
                       &ctx->d_hist, &ctx->d_tiles, &ctx->d_useg, &ctx->d_rep, &ctx->d_planes, &ctx->d_nplane, &ctx->d_bhead, &ctx->d_wsum,
                       &ctx->d_read_uid, &ctx->d_freq, &ctx->d_thr, &ctx->d_repidx, &ctx->d_label, &ctx->d_prio, &ctx->d_bstart, &ctx->d_itemoff,
                       &ctx->d_items, &ctx->d_edges, &ctx->d_keep, &ctx->d_state, &ctx->d_blocked, &ctx->d_bitmap, &ctx->d_kept, &ctx->d_roots,
-                      &ctx->d_onehot, &ctx->d_tileoff, &ctx->d_tsum, &ctx->d_tilestate, &ctx->d_bsum, &ctx->d_blkoff, &ctx->d_blkfirst, &ctx->d_blkcnt, &ctx->d_eq, &ctx->d_pairs, &ctx->d_comp, &ctx->d_ucode};
+                      &ctx->d_onehot, &ctx->d_tileoff, &ctx->d_tsum, &ctx->d_tilestate, &ctx->d_bsum, &ctx->d_blkoff, &ctx->d_blkfirst, &ctx->d_blkcnt, &ctx->d_eq, &ctx->d_pairs, &ctx->d_comp, &ctx->d_ucode, &ctx->d_ubkt, &ctx->d_brank, &ctx->d_bigbid, &ctx->d_bstartbig, &ctx->d_biguid,
+                      &ctx->d_miplanes, &ctx->d_minplane, &ctx->d_miucode, &ctx->d_miuid};
     for (DevBuf *b : bufs) b->release();
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
     if (ctx->h_kept) cudaFreeHost(ctx->h_kept);
@@ -392,12 +394,111 @@ static int run_sort(umigpu_ctx *ctx, u64 n, int nw, const SortPlan &plan, int *c
     return UMIGPU_OK;
 }
 
+// One ordering of the unique UMIs of a set of buckets, as seen by the neighbour search.
+struct NView {
+    const uint2 *planes; const u32 *nplane; const u64 *ucode;
+    const u32 *uidmap;          // index in this ordering -> unique id (nullptr = identity: the main order)
+    const u32 *bstart; u32 n_buckets;
+};
+
+// Work list (tile pairs -> block pairs) and evaluation for one ordering.  *dense is set (and nothing is evaluated)
+// when a multi-index pass finds that culling does not thin the work out: the caller then restarts without it.
+static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, EdgeSink es, bool has_n, int cull, bool allow_blocks, bool *dense) {
+    const umigpu_config &cfg = ctx->cfg;
+    DevScalars *sc = ctx->d_sc.as<DevScalars>();
+    const int k = cfg.k, L = (int)cfg.umi_len;
+    const u32 B = v.n_buckets;
+    *dense = false;
+    if (B == 0) return UMIGPU_OK;
+    CK(ctx->d_itemoff.reserve(((size_t)B + 1) * 4));
+    CK(ctx->d_tileoff.reserve(((size_t)B + 1) * 4));
+    CK(ctx->d_blkoff.reserve(((size_t)B + 1) * 4));
+    int rc = run_scan(ctx, BucketItems{v.bstart}, BucketItemsEmit{ctx->d_itemoff.as<u32>(), B}, B, &sc->n_cand);
+    if (rc) return rc;
+    rc = run_scan(ctx, BucketTiles{v.bstart}, BucketTilesEmit{ctx->d_tileoff.as<u32>(), B}, B, &sc->n_tiles);
+    if (rc) return rc;
+    rc = run_scan(ctx, BucketBlocks{v.bstart}, BucketTilesEmit{ctx->d_blkoff.as<u32>(), B}, B, &sc->n_blocks);
+    if (rc) return rc;
+    rc = read_scalars(ctx);
+    if (rc) return rc;
+    const u32 n_cand = ctx->h_sc->n_cand, n_tiles = ctx->h_sc->n_tiles, n_blocks = ctx->h_sc->n_blocks;
+    if (n_cand == 0) return UMIGPU_OK;
+    CK(ctx->d_tsum.reserve((size_t)std::max<u32>(n_tiles, 1) * TS_WORDS * 4));
+    CK(ctx->d_bsum.reserve((size_t)std::max<u32>(n_blocks, 1) * TS_WORDS * 4));
+    CK(ctx->d_blkfirst.reserve((size_t)std::max<u32>(n_blocks, 1) * 4));
+    CK(ctx->d_blkcnt.reserve((size_t)std::max<u32>(n_blocks, 1) * 4));
+    LAUNCH(tile_summary_kernel, grid_for((u64)n_tiles * 32, 256), 256, n_tiles, B, (const u32 *)ctx->d_tileoff.p, v.bstart, v.planes, v.nplane, L,
+           ctx->d_tsum.as<u32>(), (const u32 *)ctx->d_blkoff.p, ctx->d_bsum.as<u32>(), ctx->d_blkfirst.as<u32>(), ctx->d_blkcnt.as<u32>());
+    CK(ctx->d_items.reserve((size_t)n_cand * sizeof(TileItem)));
+    CK(cudaMemsetAsync(&sc->n_items, 0, 4, ctx->stream));
+    CK(cudaMemsetAsync(&sc->scratch2, 0, 8, ctx->stream));
+    LAUNCH(build_items_kernel, grid_for(n_cand, 256), 256, n_cand, B, (const u32 *)ctx->d_itemoff.p, v.bstart, (const u32 *)ctx->d_tileoff.p,
+           (const u32 *)ctx->d_blkoff.p, (const u32 *)ctx->d_tsum.p, L, k, cull, mi, ctx->d_items.as<TileItem>(), sc);
+    rc = read_scalars(ctx);
+    if (rc) return rc;
+    const u32 W = ctx->h_sc->n_items;
+    const u64 item_pairs = ctx->h_sc->scratch2;
+    ctx->ctr.n_tile_candidates += n_cand;
+    if (W == 0) return UMIGPU_OK;
+    const TileItem *items = ctx->d_items.as<TileItem>();
+
+    if (allow_blocks) {
+        // ---- sparse form: global one-hot words, block-pair list, one warp per block pair ----
+        CK(cudaMemsetAsync(&sc->n_block_pairs, 0, 8, ctx->stream));
+        LAUNCH(expand_blocks_kernel, grid_for((u64)W * 32, 256), 256, items, W, (const u32 *)ctx->d_bsum.p, L, k, cull, mi, 0, (uint2 *)nullptr,
+               (unsigned long long *)&sc->n_block_pairs);
+        rc = read_scalars(ctx);
+        if (rc) return rc;
+        const u64 n_pairs = ctx->h_sc->n_block_pairs;
+        // more than ~30 % of the scheduled pair space survives block culling: dense work runs better as shared-memory tiles
+        const bool is_dense = (double)n_pairs * 16384.0 > 0.30 * (double)item_pairs;
+        if (is_dense && mi.part >= 0) { *dense = true; return UMIGPU_OK; }
+        if (!is_dense) {
+            const int LP = blk_lp(L), XS = has_n ? 8 : 4;
+            CK(ctx->d_eq.reserve((size_t)std::max<u32>(n_blocks, 1) * LP * XS * 16));
+            if (has_n) LAUNCH(onehot_build_kernel<true>, grid_for((u64)n_blocks * 4 * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
+                              (const u32 *)ctx->d_blkcnt.p, v.planes, v.nplane, L, LP, ctx->d_eq.as<u32>());
+            else       LAUNCH(onehot_build_kernel<false>, grid_for((u64)n_blocks * 4 * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
+                              (const u32 *)ctx->d_blkcnt.p, v.planes, v.nplane, L, LP, ctx->d_eq.as<u32>());
+            CK(ctx->d_pairs.reserve(std::max<u64>(n_pairs, 1) * sizeof(uint2)));
+            CK(cudaMemsetAsync(&sc->n_block_pairs, 0, 8, ctx->stream));
+            LAUNCH(expand_blocks_kernel, grid_for((u64)W * 32, 256), 256, items, W, (const u32 *)ctx->d_bsum.p, L, k, cull, mi, 1, ctx->d_pairs.as<uint2>(),
+                   (unsigned long long *)&sc->n_block_pairs);
+            rc = launch_neighbours_blocks(ctx->stream, ctx->num_sms, ctx->d_pairs.as<uint2>(), n_pairs, (const u32 *)ctx->d_blkfirst.p,
+                                          (const u32 *)ctx->d_blkcnt.p, (const u32 *)ctx->d_bsum.p, v.planes, v.nplane, v.ucode, ctx->d_eq.as<uint4>(),
+                                          L, k, has_n, cull, es, mi, v.uidmap, (unsigned long long *)&sc->pairs_eval);
+            if (rc != 0) return fail(ctx, UMIGPU_ERR_CUDA, "block-pair neighbour kernel: %s", cudaGetErrorString(cudaGetLastError()));
+            ctx->launches += 1;
+            CK(cudaGetLastError());
+            ctx->ctr.n_block_pairs += n_pairs; ctx->ctr.n_tile_items += W;
+            return UMIGPU_OK;
+        }
+    }
+    // ---- dense forms (main order only, no multi-index filter) ----
+    if (mi.part >= 0 || v.uidmap) return fail(ctx, UMIGPU_ERR_STATE, "internal: dense neighbour kernel reached inside a multi-index pass");
+    ctx->ctr.n_tile_items += W;
+    if (!(cfg.flags & UMIGPU_FLAG_KERNEL_DIRECT)) {
+        rc = launch_neighbours_bitsliced(ctx->stream, ctx->num_sms, items, W, v.planes, v.nplane, ctx->d_bsum.as<u32>(), L, k, has_n, cull, es,
+                                         (u32 *)&sc->scratch, (unsigned long long *)&sc->pairs_eval);
+        if (rc == 0) { ctx->launches += 1; CK(cudaGetLastError()); return UMIGPU_OK; }
+        if (rc < 0) return fail(ctx, UMIGPU_ERR_CUDA, "bit-sliced neighbour kernel: %s", cudaGetErrorString(cudaGetLastError()));
+        // rc > 0: configuration not covered by the bit-sliced kernels (k > 3) -> direct kernel
+    }
+    ctx->used_direct = true;
+    ctx->direct_pairs += item_pairs;
+    const u32 grid = std::min<u32>(W, (u32)ctx->num_sms * 4);
+#define HD(KK, NN) LAUNCH((hamming_tiles_direct<KK, NN>), grid, HT_THREADS, items, W, v.planes, v.nplane, es, k)
+    if (!has_n) { if (k == 1) HD(1, false); else if (k == 2) HD(2, false); else HD(0, false); }
+    else        { if (k == 1) HD(1, true);  else if (k == 2) HD(2, true);  else HD(0, true); }
+#undef HD
+    return UMIGPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // run
 // ------------------------------------------------------------------------------------------------
 enum RunMode { RUN_FULL = 0, RUN_EDGES_ONLY = 1 };
 
-static int launch_neighbours(umigpu_ctx *ctx, u32 n_items, EdgeSink es, bool has_n);
 
 static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_inf_thr) {
     if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
@@ -495,7 +596,8 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     // ---- buckets + work list ----
     STAGE_BEGIN(UMIGPU_STAGE_WORKLIST);
     CK(ctx->d_bstart.reserve(((size_t)U + 1) * 4));
-    rc = run_scan(ctx, BucketHead{ctx->d_bhead.as<u8>()}, BucketEmit{ctx->d_bstart.as<u32>(), U}, U, &sc->n_buckets);
+    CK(ctx->d_ubkt.reserve((size_t)U * 4));
+    rc = run_scan(ctx, BucketHead{ctx->d_bhead.as<u8>()}, BucketEmit{ctx->d_bstart.as<u32>(), U, ctx->d_ubkt.as<u32>()}, U, &sc->n_buckets);
     if (rc) return rc;
     rc = read_scalars(ctx);
     if (rc) return rc;
@@ -505,42 +607,41 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
 
     const bool need_edges = (mode == RUN_EDGES_ONLY || cfg.algo != UMIGPU_ALGO_ADJ) && cfg.k > 0 && U > B;
     const int cull = (cfg.flags & UMIGPU_FLAG_NO_CULL) ? 0 : 1;
-    u32 W = 0;
+    const int k = cfg.k, L = lay.umi_len;
+    const bool allow_blocks = !(cfg.flags & (UMIGPU_FLAG_KERNEL_DIRECT | UMIGPU_FLAG_KERNEL_TILES)) && k >= 1 && k <= 3 && !(has_n && L > 24) && cull;
     u64 n_edges = 0;
-    if (need_edges) {
-        CK(ctx->d_itemoff.reserve(((size_t)B + 1) * 4));
-        CK(ctx->d_tileoff.reserve(((size_t)B + 1) * 4));
-        rc = run_scan(ctx, BucketItems{ctx->d_bstart.as<u32>()}, BucketItemsEmit{ctx->d_itemoff.as<u32>(), B}, B, &sc->n_cand);
-        if (rc) return rc;
-        rc = run_scan(ctx, BucketTiles{ctx->d_bstart.as<u32>()}, BucketTilesEmit{ctx->d_tileoff.as<u32>(), B}, B, &sc->n_tiles);
-        if (rc) return rc;
-        CK(ctx->d_blkoff.reserve(((size_t)B + 1) * 4));
-        rc = run_scan(ctx, BucketBlocks{ctx->d_bstart.as<u32>()}, BucketTilesEmit{ctx->d_blkoff.as<u32>(), B}, B, &sc->n_blocks);
+    // ---- multi-index preparation: which buckets are big, their compacted unique list ----
+    const int P = k + 1;                                   // parts (pigeonhole)
+    bool mi_on = need_edges && allow_blocks && !(cfg.flags & UMIGPU_FLAG_NO_MULTI_INDEX) && L >= 2 * P;
+    u32 nbig = 0, m_big = 0;
+    MiParams mi0; memset(&mi0, 0, sizeof mi0); mi0.part = -1; mi0.big = MI_BIG;
+    int part_lo[MI_MAX_PARTS] = {0, 0, 0, 0}, part_len[MI_MAX_PARTS] = {0, 0, 0, 0};
+    const int bpb = has_n ? 3 : 2;
+    if (mi_on) {
+        int hi = L;
+        for (int q = 0; q < P; q++) {                      // part 0 = the most significant positions of the main order
+            int len = L / P + (q < L % P ? 1 : 0);
+            part_len[q] = len; part_lo[q] = hi - len; hi -= len;
+            mi0.pmask[q] = (u32)(((1ull << len) - 1) << part_lo[q]);
+            mi0.cmask[q] = (((len * bpb) >= 64 ? ~0ull : ((1ull << (len * bpb)) - 1))) << (part_lo[q] * bpb);
+        }
+        CK(ctx->d_brank.reserve((size_t)B * 4)); CK(ctx->d_bigbid.reserve((size_t)B * 4));
+        rc = run_scan(ctx, BucketIsBig{ctx->d_bstart.as<u32>(), MI_BIG}, BucketBigEmit{ctx->d_brank.as<u32>(), ctx->d_bigbid.as<u32>(), B}, B, &sc->n_big);
         if (rc) return rc;
         rc = read_scalars(ctx);
         if (rc) return rc;
-        const u32 n_cand = ctx->h_sc->n_cand, n_tiles = ctx->h_sc->n_tiles, n_blocks = ctx->h_sc->n_blocks;
-        ctx->n_blocks = n_blocks;
-        CK(ctx->d_tsum.reserve((size_t)std::max<u32>(n_tiles, 1) * TS_WORDS * 4));
-        CK(ctx->d_bsum.reserve((size_t)std::max<u32>(n_blocks, 1) * TS_WORDS * 4));
-        CK(ctx->d_blkfirst.reserve((size_t)std::max<u32>(n_blocks, 1) * 4));
-        CK(ctx->d_blkcnt.reserve((size_t)std::max<u32>(n_blocks, 1) * 4));
-        if (n_tiles)
-            LAUNCH(tile_summary_kernel, grid_for((u64)n_tiles * 32, 256), 256, n_tiles, B, (const u32 *)ctx->d_tileoff.p, (const u32 *)ctx->d_bstart.p,
-                   (const uint2 *)ctx->d_planes.p, has_n ? (const u32 *)ctx->d_nplane.p : (const u32 *)nullptr, lay.umi_len, ctx->d_tsum.as<u32>(),
-                   (const u32 *)ctx->d_blkoff.p, ctx->d_bsum.as<u32>(), ctx->d_blkfirst.as<u32>(), ctx->d_blkcnt.as<u32>());
-        // candidates are tested in chunks so that the item buffer only has to hold the survivors of one chunk
-        // plus what is already there; in the worst case (no culling) it holds every candidate
-        CK(ctx->d_items.reserve((size_t)std::max<u32>(n_cand, 1) * sizeof(TileItem)));
-        CK(cudaMemsetAsync(&sc->n_items, 0, 4, ctx->stream));
-        CK(cudaMemsetAsync(&sc->scratch2, 0, 8, ctx->stream));
-        if (n_cand)
-            LAUNCH(build_items_kernel, grid_for(n_cand, 256), 256, n_cand, B, (const u32 *)ctx->d_itemoff.p, (const u32 *)ctx->d_bstart.p,
-                   (const u32 *)ctx->d_tileoff.p, (const u32 *)ctx->d_blkoff.p, (const u32 *)ctx->d_tsum.p, lay.umi_len, cfg.k, cull, ctx->d_items.as<TileItem>(), sc);
+        nbig = ctx->h_sc->n_big;
+        if (nbig == 0) mi_on = false;
+    }
+    if (mi_on) {
+        CK(ctx->d_bstartbig.reserve(((size_t)nbig + 1) * 4));
+        rc = run_scan(ctx, BigSize{ctx->d_bstart.as<u32>(), ctx->d_bigbid.as<u32>()}, BigStartEmit{ctx->d_bstartbig.as<u32>(), nbig}, nbig, &sc->m_big);
+        if (rc) return rc;
         rc = read_scalars(ctx);
         if (rc) return rc;
-        W = ctx->h_sc->n_items;
-        ctx->ctr.n_tile_candidates = n_cand;
+        m_big = ctx->h_sc->m_big;
+        CK(ctx->d_biguid.reserve((size_t)m_big * 4)); CK(ctx->d_miplanes.reserve((size_t)m_big * 8)); CK(ctx->d_miucode.reserve((size_t)m_big * 8));
+        CK(ctx->d_miuid.reserve((size_t)m_big * 4)); if (has_n) CK(ctx->d_minplane.reserve((size_t)m_big * 4));
     }
     STAGE_END(UMIGPU_STAGE_WORKLIST);
 
@@ -549,19 +650,51 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     if (need_edges) {
         u64 cap = std::max<u64>((u64)1 << 20, (u64)U * 8);
         if (ctx->d_edges.cap / sizeof(uint2) > cap) cap = ctx->d_edges.cap / sizeof(uint2);
-        for (int attempt = 0; attempt < 2; attempt++) {
+        const NView main_view{ctx->d_planes.as<uint2>(), has_n ? ctx->d_nplane.as<u32>() : (const u32 *)nullptr, ctx->d_ucode.as<u64>(), nullptr,
+                              ctx->d_bstart.as<u32>(), B};
+        for (int attempt = 0; attempt < 3; attempt++) {
             CK(ctx->d_edges.reserve(cap * sizeof(uint2)));
             CK(cudaMemsetAsync(&sc->edge_count, 0, sizeof(u64), ctx->stream));
             CK(cudaMemsetAsync(&sc->pairs_eval, 0, sizeof(u64), ctx->stream));
+            ctx->ctr.n_tile_candidates = ctx->ctr.n_tile_items = ctx->ctr.n_block_pairs = 0;
+            ctx->used_direct = false; ctx->direct_pairs = 0;
             EdgeSink es{ctx->d_edges.as<uint2>(), (unsigned long long *)&sc->edge_count, cap, ctx->d_freq.as<i32>(), ctx->d_thr.as<i32>()};
             LAUNCH(small_buckets_kernel, grid_for((u64)B * 32, 256), 256, B, (const u32 *)ctx->d_bstart.p, (const uint2 *)ctx->d_planes.p,
                    has_n ? (const u32 *)ctx->d_nplane.p : (const u32 *)nullptr, cfg.k, es, (unsigned long long *)&sc->pairs_eval);
-            if (W > 0) { rc = launch_neighbours(ctx, W, es, has_n); if (rc) return rc; } else ctx->used_direct = false;
+            // pass 0: every bucket with more than 32 unique UMIs in the main order (big buckets filtered on part 0)
+            MiParams mi = mi0; mi.part = mi_on ? 0 : -1;
+            bool dense = false;
+            rc = neighbour_pass(ctx, main_view, mi, es, has_n, cull, allow_blocks, &dense);
+            if (rc) return rc;
+            if (dense) { mi_on = false; continue; }          // culling does not thin this input out: restart without multi-index
+            // passes 1..k: big buckets only, re-ordered so that part q is the most significant
+            for (int q = 1; mi_on && q < P; q++) {
+                const int pbits = part_len[q] * bpb, rbits = bits_for(nbig - 1);
+                CK(ctx->d_key[0][0].reserve((size_t)m_big * 8)); CK(ctx->d_key[1][0].reserve((size_t)m_big * 8));
+                CK(ctx->d_idx[0].reserve((size_t)m_big * 4)); CK(ctx->d_idx[1].reserve((size_t)m_big * 4));
+                LAUNCH(mi_keys_kernel, grid_for(U, 256), 256, U, (const u32 *)ctx->d_ubkt.p, (const u32 *)ctx->d_brank.p, (const u32 *)ctx->d_bstart.p,
+                       (const u32 *)ctx->d_bstartbig.p, (const u64 *)ctx->d_ucode.p, part_lo[q] * bpb,
+                       (unsigned long long)(pbits >= 64 ? ~0ull : ((1ull << pbits) - 1)), pbits, ctx->d_biguid.as<u32>(), ctx->d_key[0][0].as<u64>());
+                int cur = 0;
+                rc = run_sort(ctx, m_big, 1, rs_plan(pbits + rbits), &cur);
+                if (rc) return rc;
+                LAUNCH(mi_gather_kernel, grid_for(m_big, 256), 256, m_big, (const u32 *)ctx->d_idx[cur].p, (const u32 *)ctx->d_biguid.p,
+                       (const uint2 *)ctx->d_planes.p, has_n ? (const u32 *)ctx->d_nplane.p : (const u32 *)nullptr, (const u64 *)ctx->d_ucode.p,
+                       ctx->d_miplanes.as<uint2>(), ctx->d_minplane.as<u32>(), ctx->d_miucode.as<u64>(), ctx->d_miuid.as<u32>());
+                const NView view{ctx->d_miplanes.as<uint2>(), has_n ? ctx->d_minplane.as<u32>() : (const u32 *)nullptr, ctx->d_miucode.as<u64>(),
+                                 ctx->d_miuid.as<u32>(), ctx->d_bstartbig.as<u32>(), nbig};
+                mi.part = q;
+                rc = neighbour_pass(ctx, view, mi, es, has_n, cull, true, &dense);
+                if (rc) return rc;
+                if (dense) break;
+            }
+            if (dense) { mi_on = false; continue; }
             rc = read_scalars(ctx);
             if (rc) return rc;
+            if (ctx->h_sc->sort_err) return fail(ctx, UMIGPU_ERR_CUDA, "radix sort look-back exceeded its spin budget");
             n_edges = ctx->h_sc->edge_count;
             if (n_edges <= cap) break;
-            if (attempt == 1) return fail(ctx, UMIGPU_ERR_CUDA, "edge count changed between passes");
+            if (attempt == 2) return fail(ctx, UMIGPU_ERR_CUDA, "edge count changed between passes");
             cap = n_edges;                 // exact count is known now: one more pass with the right size
         }
     } else {
@@ -572,8 +705,8 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     ctx->n_edges = n_edges;
     ctx->ctr.n_buckets = B; ctx->ctr.total_umis = U; ctx->ctr.max_umis = ctx->h_sc->max_umis;
     ctx->ctr.unordered_pairs = ctx->h_sc->pairs;
-    ctx->ctr.pairs_evaluated = ctx->h_sc->pairs_eval + (ctx->used_direct ? ctx->h_sc->scratch2 : 0);
-    ctx->ctr.n_edges = n_edges; ctx->ctr.n_tile_items = W;
+    ctx->ctr.pairs_evaluated = ctx->h_sc->pairs_eval + (ctx->used_direct ? ctx->direct_pairs : 0);
+    ctx->ctr.n_edges = n_edges;
     if (mode == RUN_EDGES_ONLY) { STAGE_END(UMIGPU_STAGE_TOTAL); return UMIGPU_OK; }
 
     // ---- K6 cluster ----
@@ -675,63 +808,6 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     rc = read_scalars(ctx);
     if (rc) return rc;
     ctx->ctr.n_kept = ctx->h_sc->n_kept;
-    return UMIGPU_OK;
-}
-
-static int launch_neighbours(umigpu_ctx *ctx, u32 n_items, EdgeSink es, bool has_n) {
-    const umigpu_config &cfg = ctx->cfg;
-    DevScalars *sc = ctx->d_sc.as<DevScalars>();
-    const TileItem *items = ctx->d_items.as<TileItem>();
-    const uint2 *planes = ctx->d_planes.as<uint2>();
-    const u32 *nplane = ctx->d_nplane.as<u32>();
-    const int k = cfg.k, L = (int)cfg.umi_len;
-    const int cull = (cfg.flags & UMIGPU_FLAG_NO_CULL) ? 0 : 1;
-    ctx->used_direct = false;
-    // Dense work (culling disabled, or a UMI space so saturated that most blocks survive) runs better as
-    // shared-memory tiles; sparse work (the normal case after culling) as a block-pair list.
-    bool use_blocks = !(cfg.flags & (UMIGPU_FLAG_KERNEL_DIRECT | UMIGPU_FLAG_KERNEL_TILES)) && k >= 1 && k <= 3 && !(has_n && L > 24) && cull;
-    if (use_blocks) {
-        // ---- production path: global one-hot words, block-pair list, one warp per block pair ----
-        const int LP = blk_lp(L), XS = has_n ? 8 : 4;
-        const u32 n_blocks = ctx->n_blocks;
-        CK(ctx->d_eq.reserve((size_t)std::max<u32>(n_blocks, 1) * LP * XS * 16));
-        if (has_n) LAUNCH(onehot_build_kernel<true>, grid_for((u64)n_blocks * 4 * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
-                          (const u32 *)ctx->d_blkcnt.p, planes, nplane, L, LP, ctx->d_eq.as<u32>());
-        else       LAUNCH(onehot_build_kernel<false>, grid_for((u64)n_blocks * 4 * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
-                          (const u32 *)ctx->d_blkcnt.p, planes, nplane, L, LP, ctx->d_eq.as<u32>());
-        CK(cudaMemsetAsync(&sc->n_block_pairs, 0, 8, ctx->stream));
-        LAUNCH(expand_blocks_kernel, grid_for((u64)n_items * 32, 256), 256, items, n_items, (const u32 *)ctx->d_bsum.p, L, k, cull, 0,
-               (uint2 *)nullptr, (unsigned long long *)&sc->n_block_pairs);
-        int rc = read_scalars(ctx);
-        if (rc) return rc;
-        const u64 n_pairs = ctx->h_sc->n_block_pairs;
-        // more than ~30 % of the scheduled pair space survives block culling: treat as dense
-        if ((double)n_pairs * 16384.0 > 0.30 * (double)ctx->h_sc->scratch2) use_blocks = false;
-      if (use_blocks) {
-        CK(ctx->d_pairs.reserve(std::max<u64>(n_pairs, 1) * sizeof(uint2)));
-        CK(cudaMemsetAsync(&sc->n_block_pairs, 0, 8, ctx->stream));
-        LAUNCH(expand_blocks_kernel, grid_for((u64)n_items * 32, 256), 256, items, n_items, (const u32 *)ctx->d_bsum.p, L, k, cull, 1,
-               ctx->d_pairs.as<uint2>(), (unsigned long long *)&sc->n_block_pairs);
-        rc = launch_neighbours_blocks(ctx->stream, ctx->num_sms, ctx->d_pairs.as<uint2>(), n_pairs, (const u32 *)ctx->d_blkfirst.p,
-                                      (const u32 *)ctx->d_blkcnt.p, (const u32 *)ctx->d_bsum.p, planes, has_n ? nplane : (const u32 *)nullptr,
-                                      (const u64 *)ctx->d_ucode.p, ctx->d_eq.as<uint4>(), L, k, has_n, cull, es, (unsigned long long *)&sc->pairs_eval);
-        if (rc < 0) return fail(ctx, UMIGPU_ERR_CUDA, "block-pair neighbour kernel: %s", cudaGetErrorString(cudaGetLastError()));
-        if (rc == 0) { ctx->launches += 1; ctx->ctr.n_block_pairs = n_pairs; CK(cudaGetLastError()); return UMIGPU_OK; }
-      }
-    }
-    u32 grid = std::min<u32>(n_items, (u32)ctx->num_sms * 4);
-    if (!(cfg.flags & UMIGPU_FLAG_KERNEL_DIRECT)) {
-        int rc = launch_neighbours_bitsliced(ctx->stream, ctx->num_sms, items, n_items, planes, nplane, ctx->d_bsum.as<u32>(), L, k, has_n,
-                                             cull, es, (u32 *)&sc->scratch, (unsigned long long *)&sc->pairs_eval);
-        if (rc == 0) { ctx->launches += 1; CK(cudaGetLastError()); return UMIGPU_OK; }
-        if (rc < 0) return fail(ctx, UMIGPU_ERR_CUDA, "bit-sliced neighbour kernel: %s", cudaGetErrorString(cudaGetLastError()));
-        // rc > 0: configuration not covered by the bit-sliced kernels (k > 3) -> direct kernel
-    }
-    ctx->used_direct = true;
-#define HD(KK, NN) LAUNCH((hamming_tiles_direct<KK, NN>), grid, HT_THREADS, items, n_items, planes, nplane, es, k)
-    if (!has_n) { if (k == 1) HD(1, false); else if (k == 2) HD(2, false); else HD(0, false); }
-    else        { if (k == 1) HD(1, true);  else if (k == 2) HD(2, true);  else HD(0, true); }
-#undef HD
     return UMIGPU_OK;
 }
 

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libumigpu.so")
 OK, ERR_ARG, ERR_CUDA, ERR_BAD_BASE, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 ALGO_DIR, ALGO_ADJ, ALGO_ADJ_UPSTREAM, ALGO_CC = 0, 1, 2, 3
 MERGE_ANY, MERGE_AVGQUAL, MERGE_MAPQUAL = 0, 1, 2
-FLAG_LABELS, FLAG_NO_CULL, FLAG_KERNEL_DIRECT, FLAG_KERNEL_TILES = 1, 2, 4, 8
+FLAG_LABELS, FLAG_NO_CULL, FLAG_KERNEL_DIRECT, FLAG_KERNEL_TILES, FLAG_NO_MULTI_INDEX = 1, 2, 4, 8, 16
 STAGES = ["pack", "keys", "sort", "unique", "worklist", "neighbours", "cluster", "emit", "total"]
 
 # every symbol include/umigpu.h declares (tests check that the built library exports all of them)
