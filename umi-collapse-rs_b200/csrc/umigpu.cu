@@ -735,17 +735,22 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
         LAUNCH(mis_label_kernel, egrid, 256, edges, n_edges, prio, (const u8 *)ctx->d_state.p, label);
         LAUNCH(mis_keep_kernel, grid_for(U, 256), 256, U, (const u8 *)ctx->d_state.p, keep);
     } else {
-      if (n_edges < (8u << 20)) {
-        // small edge lists: plain sweeps converge in a handful of launches and have the lowest fixed cost
-        for (;;) {
-            CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
-            for (int i = 0; i < 4; i++) LAUNCH(label_sweep_kernel, egrid, 256, edges, n_edges, label, sc);
-            sweeps += 4;
-            rc = read_scalars(ctx);
-            if (rc) return rc;
-            if (!ctx->h_sc->changed) break;
-        }
-      } else {
+      // Plain sweeps first: most inputs converge in a handful of them and they have the lowest cost per sweep.
+      // An input with long mutual chains (a hot locus with millions of frequency-1 UMIs) does not: after 8 sweeps the
+      // labels are reset and the two-phase scheme (O(log) rounds) takes over.
+      bool converged = false;
+      const bool big_graph = n_edges >= (8u << 20);
+      if (big_graph) { CK(ctx->d_prio.reserve((size_t)U * 8)); CK(cudaMemcpyAsync(ctx->d_prio.p, label, (size_t)U * 8, cudaMemcpyDeviceToDevice, ctx->stream)); }
+      for (int round = 0; !converged && (round < 2 || !big_graph); round++) {
+          CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
+          for (int i = 0; i < 4; i++) LAUNCH(label_sweep_kernel, egrid, 256, edges, n_edges, label, sc);
+          sweeps += 4;
+          rc = read_scalars(ctx);
+          if (rc) return rc;
+          converged = !ctx->h_sc->changed;
+      }
+      if (!converged) {
+        CK(cudaMemcpyAsync(label, ctx->d_prio.p, (size_t)U * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         // Phase A: mutual components (hook + jump), Phase B: contracted propagation (cluster.cuh)
         CK(ctx->d_comp.reserve((size_t)U * 4));
         u32 *comp = ctx->d_comp.as<u32>();
