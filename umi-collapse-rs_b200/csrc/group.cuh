@@ -40,7 +40,17 @@ struct UniqueEmit {
     unsigned long long *rep;   // packed (score biased << 32 | ~read idx), max wins
     i32 *wsum;            // weighted freq (only with weights)
     u32 *read_uid;        // optional: read index -> unique id
-    __device__ void operator()(u64 i, u32 flag, u32 ex) const {
+    // a thread's SCAN_ITEMS elements are consecutive sorted reads: runs of one unique are folded in registers and
+    // cost ONE atomic per run instead of one per read
+    u32 pend_uid; unsigned long long pend_val; i32 pend_w;
+    __device__ __forceinline__ void flush() {
+        if (pend_uid != 0xffffffffu) {
+            atomicMax(&rep[pend_uid], pend_val);
+            if (weight) atomicAdd(&wsum[pend_uid], pend_w);
+        }
+    }
+    __device__ void finish() { flush(); }
+    __device__ void operator()(u64 i, u32 flag, u32 ex) {
         u32 uid = ex + flag - 1;
         u32 r = idx[i];
         if (flag) {
@@ -55,8 +65,10 @@ struct UniqueEmit {
         }
         if (i == n - 1) useg[uid + 1] = (u32)n;
         u32 s = score ? (u32)score[r] ^ 0x80000000u : 0u;
-        atomicMax(&rep[uid], ((unsigned long long)s << 32) | (u32)~r);
-        if (weight) atomicAdd(&wsum[uid], weight[r]);
+        const unsigned long long pk = ((unsigned long long)s << 32) | (u32)~r;
+        const i32 wv = weight ? weight[r] : 0;
+        if (uid == pend_uid) { pend_val = pk > pend_val ? pk : pend_val; pend_w += wv; }
+        else { flush(); pend_uid = uid; pend_val = pk; pend_w = wv; }
         if (read_uid) read_uid[r] = uid;
     }
 };

@@ -43,36 +43,40 @@ __global__ void __launch_bounds__(PACK_THREADS) umi_pack_kernel(
     __shared__ i32 s_tmin[PACK_THREADS / 32], s_tmax[PACK_THREADS / 32];
     __shared__ i64 s_pmin[PACK_THREADS / 32], s_pmax[PACK_THREADS / 32];
     __shared__ u32 s_flags[PACK_THREADS / 32];
-    const u64 base = (u64)blockIdx.x * PACK_THREADS;
-    const u32 cnt = (u32)min((u64)PACK_THREADS, n - base);
-    const u32 bytes = cnt * (u32)L;
-    const u8 *src = ascii + base * (u64)L;
-    // stage the block's contiguous ASCII span with coalesced (vector) loads
-    if ((((unsigned long long)src) & 15ull) == 0) {
-        const u32 nv = bytes >> 4;
-        for (u32 v = threadIdx.x; v < nv; v += PACK_THREADS) reinterpret_cast<uint4 *>(sbuf)[v] = reinterpret_cast<const uint4 *>(src)[v];
-        for (u32 b = (nv << 4) + threadIdx.x; b < bytes; b += PACK_THREADS) sbuf[b] = src[b];
-    } else {
-        for (u32 b = threadIdx.x; b < bytes; b += PACK_THREADS) sbuf[b] = src[b];
-    }
-    __syncthreads();
-    const u64 i = base + threadIdx.x;
     i32 tmin = 0x7fffffff, tmax = (i32)0x80000000;
     i64 pmin = 0x7fffffffffffffffLL, pmax = (i64)0x8000000000000000LL;
     u32 flags = 0;     // bit 0 = any N, bit 1 = bad base
-    if (threadIdx.x < cnt) {
-        const u8 *s = sbuf + threadIdx.x * (u32)L;
-        u64 code = 0; u32 nm = 0;
-        for (int b = 0; b < L; b++) {
-            u32 c = s[b], v;
-            // utils/read.rs:22-31 alphabet; anything else panics in the reference (utils/mod.rs:78)
-            if (c == 'A') v = 0; else if (c == 'C') v = 1; else if (c == 'G') v = 2; else if (c == 'T') v = 3;
-            else if (c == 'N') { v = 0; nm |= 1u << (L - 1 - b); }
-            else { v = 0; flags |= 2u; }
-            code = (code << 2) | v;
+    // persistent CTAs: a grid-stride loop over 256-read tiles, ONE range reduction per CTA at the end
+    for (u64 base = (u64)blockIdx.x * PACK_THREADS; base < n; base += (u64)gridDim.x * PACK_THREADS) {
+        const u32 cnt = (u32)min((u64)PACK_THREADS, n - base);
+        const u32 bytes = cnt * (u32)L;
+        const u8 *src = ascii + base * (u64)L;
+        __syncthreads();                      // the previous tile's bytes have been consumed
+        // stage the tile's contiguous ASCII span with coalesced (vector) loads
+        if ((((unsigned long long)src) & 15ull) == 0) {
+            const u32 nv = bytes >> 4;
+            for (u32 v = threadIdx.x; v < nv; v += PACK_THREADS) reinterpret_cast<uint4 *>(sbuf)[v] = reinterpret_cast<const uint4 *>(src)[v];
+            for (u32 b = (nv << 4) + threadIdx.x; b < bytes; b += PACK_THREADS) sbuf[b] = src[b];
+        } else {
+            for (u32 b = threadIdx.x; b < bytes; b += PACK_THREADS) sbuf[b] = src[b];
         }
-        umi2[i] = code; nmask[i] = nm; if (nm) flags |= 1u;
-        tmin = tmax = tid[i]; pmin = pmax = pos[i];
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+            const u64 i = base + threadIdx.x;
+            const u8 *s = sbuf + threadIdx.x * (u32)L;
+            u64 code = 0; u32 nm = 0;
+            for (int b = 0; b < L; b++) {
+                u32 c = s[b], v;
+                // utils/read.rs:22-31 alphabet; anything else panics in the reference (utils/mod.rs:78)
+                if (c == 'A') v = 0; else if (c == 'C') v = 1; else if (c == 'G') v = 2; else if (c == 'T') v = 3;
+                else if (c == 'N') { v = 0; nm |= 1u << (L - 1 - b); }
+                else { v = 0; flags |= 2u; }
+                code = (code << 2) | v;
+            }
+            umi2[i] = code; nmask[i] = nm; if (nm) flags |= 1u;
+            const i32 t = tid[i]; const i64 p = pos[i];
+            tmin = min(tmin, t); tmax = max(tmax, t); pmin = min(pmin, p); pmax = max(pmax, p);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -90,14 +94,12 @@ __global__ void __launch_bounds__(PACK_THREADS) umi_pack_kernel(
             tmin = min(tmin, s_tmin[k]); tmax = max(tmax, s_tmax[k]); pmin = min(pmin, s_pmin[k]); pmax = max(pmax, s_pmax[k]);
             flags |= s_flags[k];
         }
-        // one guarded atomic per block and field: the running extrema stop changing quickly
-        volatile DevScalars *vs = sc;
-        if (tmin < vs->tid_min) atomicMin(&sc->tid_min, tmin);
-        if (tmax > vs->tid_max) atomicMax(&sc->tid_max, tmax);
-        if (pmin < vs->pos_min) atomicMin((long long *)&sc->pos_min, (long long)pmin);
-        if (pmax > vs->pos_max) atomicMax((long long *)&sc->pos_max, (long long)pmax);
-        if ((flags & 1u) && !vs->any_n) atomicOr(&sc->any_n, 1u);
-        if ((flags & 2u) && !vs->bad_base) atomicOr(&sc->bad_base, 1u);
+        if (tmin <= tmax) {
+            atomicMin(&sc->tid_min, tmin); atomicMax(&sc->tid_max, tmax);
+            atomicMin((long long *)&sc->pos_min, (long long)pmin); atomicMax((long long *)&sc->pos_max, (long long)pmax);
+        }
+        if (flags & 1u) atomicOr(&sc->any_n, 1u);
+        if (flags & 2u) atomicOr(&sc->bad_base, 1u);
     }
 }
 

@@ -6,6 +6,8 @@
 // and a compare, so recomputing costs less HBM traffic than a flag array would.
 #pragma once
 #include "common.cuh"
+#include <type_traits>
+#include <utility>
 
 #define SCAN_THREADS 256
 #define SCAN_ITEMS   8
@@ -71,8 +73,13 @@ __global__ void __launch_bounds__(1024) scan_spine(T *tile_sums, u64 ntiles, T *
     if (threadIdx.x == 0 && total_out) *total_out = carry;
 }
 
+// consumers may keep per-thread state across their SCAN_ITEMS consecutive elements and flush it in finish()
+template <class G, class = void> struct scan_has_finish : std::false_type {};
+template <class G> struct scan_has_finish<G, std::void_t<decltype(std::declval<G &>().finish())>> : std::true_type {};
+
 template <class T, class F, class G>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_apply(F f, G g, u64 n, const T *tile_sums) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply(F f, G g_in, u64 n, const T *tile_sums) {
+    G g = g_in;
     __shared__ T sm[SCAN_THREADS / 32 + 1];
     u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
     T v[SCAN_ITEMS];
@@ -91,4 +98,5 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply(F f, G g, u64 n, cons
         if (i < n) g(i, v[j], ex);
         ex += v[j];
     }
+    if constexpr (scan_has_finish<G>::value) g.finish();
 }

@@ -234,7 +234,7 @@ static int push_common(umigpu_ctx *ctx, u64 n, const i32 *tid, const i64 *pos, c
         CK(cudaMemcpyAsync(ctx->d_ascii.p, ascii, n * L, kind, s));
         d_ascii = ctx->d_ascii.as<u8>();
     }
-    LAUNCH(umi_pack_kernel, grid_for(n, PACK_THREADS), PACK_THREADS, d_ascii, n, L, ctx->d_tid.as<i32>() + old,
+    LAUNCH(umi_pack_kernel, (u32)std::min<u64>(grid_for(n, PACK_THREADS), (u64)ctx->num_sms * 32), PACK_THREADS, d_ascii, n, L, ctx->d_tid.as<i32>() + old,
            ctx->d_pos.as<i64>() + old, ctx->d_umi2.as<u64>() + old, ctx->d_nmask.as<u32>() + old, ctx->d_sc.as<DevScalars>());
     STAGE_END(UMIGPU_STAGE_PACK);
     if (ctx->use_orig) {
@@ -578,6 +578,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     ue.useg = ctx->d_useg.as<u32>(); ue.planes = ctx->d_planes.as<uint2>(); ue.nplane = ctx->d_nplane.as<u32>(); ue.ucode = ctx->d_ucode.as<u64>();
     ue.bhead = ctx->d_bhead.as<u8>(); ue.rep = ctx->d_rep.as<unsigned long long>(); ue.wsum = ctx->d_wsum.as<i32>();
     ue.read_uid = want_labels ? ctx->d_read_uid.as<u32>() : nullptr;
+    ue.pend_uid = 0xffffffffu; ue.pend_val = 0; ue.pend_w = 0;
     rc = run_scan(ctx, HeadFlag{sk}, ue, n, &sc->n_unique);
     if (rc) return rc;
     rc = read_scalars(ctx);
