@@ -367,3 +367,11 @@ def test_multi_index_passes_big_buckets(k, L, alphabet_n):
     assert res[(0, umigpu.ALGO_DIR)]["max_umis"] > 4096
     for algo in (umigpu.ALGO_DIR, umigpu.ALGO_CC):
         assert res[(0, algo)]["n_edges"] == res[(umigpu.FLAG_NO_MULTI_INDEX, algo)]["n_edges"]      # no pair lost, none reported twice
+
+
+def test_c2_shape_one_million_reads_exact():
+    """The bench workload's generator at 1 M reads (hottest locus ~30 k unique UMIs: multi-index passes, block-pair
+    kernel, small-bucket kernel and the sort all take their production paths), exact against the oracle."""
+    d, cfg = small("C2", 0.02)
+    ctr = check_against_oracle(d, umigpu.ALGO_DIR, umigpu.MERGE_AVGQUAL, 1, 0.5, labels=True)
+    assert ctr["max_umis"] > 20000 and ctr["n_block_pairs"] > 0

@@ -422,6 +422,12 @@ static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, E
     rc = read_scalars(ctx);
     if (rc) return rc;
     const u32 n_cand = ctx->h_sc->n_cand, n_tiles = ctx->h_sc->n_tiles, n_blocks = ctx->h_sc->n_blocks;
+    // the candidate tile pairs are counted in 32 bits: sum_b T_b (T_b + 1) / 2 <= (T_max + 1) * n_tiles / 2 + n_tiles
+    {
+        const u64 t_max = (ctx->h_sc->max_umis + HT_ROWS - 1) / HT_ROWS;
+        if ((t_max + 1) * (u64)n_tiles / 2 + n_tiles >= 0x7fffffffull)
+            return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "a bucket of %u unique UMIs needs more than 2^31 tile pairs: split the batch", ctx->h_sc->max_umis);
+    }
     if (n_cand == 0) return UMIGPU_OK;
     CK(ctx->d_tsum.reserve((size_t)std::max<u32>(n_tiles, 1) * TS_WORDS * 4));
     CK(ctx->d_bsum.reserve((size_t)std::max<u32>(n_blocks, 1) * TS_WORDS * 4));
