@@ -1,4 +1,6 @@
-// hamming_bs.cuh — K5 hamming_neighbours, bit-sliced one-hot tile kernel (the production kernel).
+// hamming_bs.cuh — K5 hamming_neighbours, bit-sliced one-hot kernel in its dense shared-memory TILE form.
+// Used when the work is dense (culling disabled, or culling keeps > 30 % of the scheduled pair space) and with
+// UMIGPU_FLAG_KERNEL_TILES; the sparse block-pair form (hamming_blocks.cuh) is the default after culling.
 //
 // Same contract as hamming_tiles_direct (hamming.cuh) but 32 column UMIs are compared per
 // instruction.  For a tile of up to 2048 columns the CTA first builds, in shared memory, one-hot
