@@ -223,6 +223,18 @@ void umigpu_result_free(umigpu_ctx *ctx);
 int umigpu_shard_plan(uint64_t n, const int32_t *tid, const int64_t *unclipped_pos, const uint8_t *is_reverse,
                       int32_t n_shards, int32_t *shard_of_read, uint64_t *shard_cost /* n_shards */);
 
+/*
+ * One call, several GPUs of one box: plans the shards with umigpu_shard_plan, runs one context per
+ * device on its own host thread (push -> run -> fetch), and merges the survivors back into input order.  No
+ * collective and no peer traffic: buckets never interact (deduplicate_sam.rs:207-213).  device_ids may repeat a
+ * device.  *kept receives a malloc'ed array of *n_kept ascending read indices (free with umigpu_free); counters
+ * are summed over shards (max_umis is the maximum).  cfg->device and cfg->stream are ignored.
+ */
+int umigpu_dedup_sharded(const umigpu_config *cfg, int32_t n_devices, const int32_t *device_ids, uint64_t n,
+                         const int32_t *tid, const int64_t *unclipped_pos, const uint8_t *is_reverse, const uint8_t *umi_ascii,
+                         const int32_t *score, uint64_t **kept, uint64_t *n_kept, umigpu_counters *counters);
+void umigpu_free(void *p);
+
 /* integer-pipe microbenchmark used as the roofline denominator of the neighbour search:
  * ops/s of a dependent-free LOP3 stream and of POPC on the context's device. */
 int umigpu_int_peak(umigpu_ctx *ctx, double *lop3_ops_per_s, double *popc_ops_per_s);

@@ -375,3 +375,16 @@ def test_c2_shape_one_million_reads_exact():
     d, cfg = small("C2", 0.02)
     ctr = check_against_oracle(d, umigpu.ALGO_DIR, umigpu.MERGE_AVGQUAL, 1, 0.5, labels=True)
     assert ctr["max_umis"] > 20000 and ctr["n_block_pairs"] > 0
+
+
+def test_one_call_sharded_over_devices():
+    """umigpu_dedup_sharded: LPT shard plan, one context per device on its own host thread, merge in input order."""
+    import torch
+    d, cfg = small("C2", 0.004, seed=9)
+    nd = torch.cuda.device_count()
+    for devices in ([0], [0, 0, 0], list(range(nd)) if nd > 1 else [0, 0]):
+        kept, ctr = umigpu.dedup_sharded(cfg["umi_len"], devices, d["tid"], d["pos"], d["rev"], d["umi"], d["score"])
+        okept, _, octr = O.dedup(d["tid"], d["pos"], d["rev"], d["umi"], d["score"], O.ALGO_DIR, O.MERGE_AVGQUAL, 1, 0.5)
+        assert kept.astype(np.int64).tolist() == okept.tolist()
+        for key in ("total_reads", "n_buckets", "total_umis", "max_umis", "n_kept", "unordered_pairs"):
+            assert ctr[key] == octr[key], key

@@ -5,6 +5,7 @@
 #include "pack.cuh"
 #include <algorithm>
 #include <queue>
+#include <thread>
 #include <stdarg.h>
 #include <unordered_map>
 
@@ -1112,6 +1113,87 @@ extern "C" int umigpu_shard_plan(uint64_t n, const int32_t *tid, const int64_t *
         if (shard_cost) for (i32 s = 0; s < n_shards; s++) shard_cost[s] = loads[s];
     } catch (const std::bad_alloc &) {
         return fail(nullptr, UMIGPU_ERR_NOMEM, "umigpu_shard_plan: out of host memory");
+    }
+    return UMIGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// several GPUs of one box in one call: shard by bucket, one context + one host thread per device, merge
+// ------------------------------------------------------------------------------------------------
+extern "C" void umigpu_free(void *p) { free(p); }
+
+extern "C" int umigpu_dedup_sharded(const umigpu_config *cfg, int32_t n_devices, const int32_t *device_ids, uint64_t n,
+                                    const int32_t *tid, const int64_t *unclipped_pos, const uint8_t *is_reverse,
+                                    const uint8_t *umi_ascii, const int32_t *score, uint64_t **kept, uint64_t *n_kept,
+                                    umigpu_counters *counters) {
+    if (!cfg || !device_ids || n_devices < 1 || !kept || !n_kept) return fail(nullptr, UMIGPU_ERR_ARG, "umigpu_dedup_sharded: bad argument");
+    *kept = nullptr; *n_kept = 0;
+    if (counters) memset(counters, 0, sizeof *counters);
+    if (n == 0) return UMIGPU_OK;
+    if (!tid || !unclipped_pos || !is_reverse || !umi_ascii) return fail(nullptr, UMIGPU_ERR_ARG, "umigpu_dedup_sharded: null input");
+    const int L = (int)cfg->umi_len;
+    std::vector<i32> shard(n);
+    std::vector<u64> cost(n_devices);
+    int rc = umigpu_shard_plan(n, tid, unclipped_pos, is_reverse, n_devices, shard.data(), cost.data());
+    if (rc) return rc;
+    struct Part { std::vector<u64> idx; std::vector<i32> tid, score; std::vector<i64> pos; std::vector<u8> rev, umi; std::vector<u64> kept;
+                  umigpu_counters ctr; int rc = 0; std::string err; };
+    std::vector<Part> parts(n_devices);
+    for (u64 i = 0; i < n; i++) parts[shard[i]].idx.push_back(i);
+    std::vector<std::thread> th;
+    for (int s = 0; s < n_devices; s++) {
+        th.emplace_back([&, s] {
+            Part &p = parts[s];
+            memset(&p.ctr, 0, sizeof p.ctr);
+            const u64 m = p.idx.size();
+            if (m == 0) return;
+            p.tid.resize(m); p.pos.resize(m); p.rev.resize(m); p.umi.resize(m * (size_t)L); if (score) p.score.resize(m);
+            for (u64 j = 0; j < m; j++) {
+                const u64 i = p.idx[j];
+                p.tid[j] = tid[i]; p.pos[j] = unclipped_pos[i]; p.rev[j] = is_reverse[i];
+                memcpy(p.umi.data() + j * (size_t)L, umi_ascii + i * (size_t)L, (size_t)L);
+                if (score) p.score[j] = score[i];
+            }
+            umigpu_config c = *cfg; c.device = device_ids[s]; c.stream = nullptr;
+            umigpu_ctx *ctx = nullptr;
+            p.rc = umigpu_create(&c, &ctx);
+            if (p.rc) { p.err = umigpu_last_error(nullptr); return; }
+            umigpu_result res;
+            p.rc = umigpu_push_reads(ctx, m, p.tid.data(), p.pos.data(), p.rev.data(), p.umi.data(), score ? p.score.data() : nullptr, nullptr, 0);
+            if (!p.rc) p.rc = umigpu_finish(ctx, &res);
+            if (p.rc) { p.err = umigpu_last_error(ctx); umigpu_destroy(ctx); return; }
+            p.kept.resize(res.n_kept);
+            for (u64 j = 0; j < res.n_kept; j++) p.kept[j] = p.idx[res.kept_read_index[j]];      // local -> input index (idx is ascending)
+            p.ctr = res.counters;
+            umigpu_destroy(ctx);
+        });
+    }
+    for (auto &t : th) t.join();
+    u64 total = 0;
+    for (Part &p : parts) { if (p.rc) return fail(nullptr, p.rc, "shard failed: %s", p.err.c_str()); total += p.kept.size(); }
+    u64 *out = (u64 *)malloc(std::max<u64>(total, 1) * sizeof(u64));
+    if (!out) return fail(nullptr, UMIGPU_ERR_NOMEM, "out of host memory");
+    // k-way merge of ascending lists
+    std::vector<size_t> at(n_devices, 0);
+    typedef std::pair<u64, int> Head;
+    std::priority_queue<Head, std::vector<Head>, std::greater<Head>> pq;
+    for (int s = 0; s < n_devices; s++) if (!parts[s].kept.empty()) pq.push({parts[s].kept[0], s});
+    u64 o = 0;
+    while (!pq.empty()) {
+        Head h = pq.top(); pq.pop();
+        out[o++] = h.first;
+        Part &p = parts[h.second];
+        if (++at[h.second] < p.kept.size()) pq.push({p.kept[at[h.second]], h.second});
+    }
+    *kept = out; *n_kept = total;
+    if (counters) {
+        for (Part &p : parts) {
+            counters->total_reads += p.ctr.total_reads; counters->n_buckets += p.ctr.n_buckets; counters->total_umis += p.ctr.total_umis;
+            counters->max_umis = std::max(counters->max_umis, p.ctr.max_umis); counters->n_kept += p.ctr.n_kept;
+            counters->unordered_pairs += p.ctr.unordered_pairs; counters->pairs_evaluated += p.ctr.pairs_evaluated; counters->n_edges += p.ctr.n_edges;
+            counters->n_tile_items += p.ctr.n_tile_items; counters->n_tile_candidates += p.ctr.n_tile_candidates;
+            counters->n_sweeps = std::max(counters->n_sweeps, p.ctr.n_sweeps); counters->n_block_pairs += p.ctr.n_block_pairs;
+        }
     }
     return UMIGPU_OK;
 }

@@ -76,6 +76,10 @@ extern "C" {
     pub fn umigpu_result_free(ctx: *mut umigpu_ctx);
     pub fn umigpu_shard_plan(n: u64, tid: *const i32, unclipped_pos: *const i64, is_reverse: *const u8, n_shards: i32,
                              shard_of_read: *mut i32, shard_cost: *mut u64) -> c_int;
+    pub fn umigpu_dedup_sharded(cfg: *const umigpu_config, n_devices: i32, device_ids: *const i32, n: u64, tid: *const i32,
+                                unclipped_pos: *const i64, is_reverse: *const u8, umi_ascii: *const u8, score: *const i32,
+                                kept: *mut *mut u64, n_kept: *mut u64, counters: *mut umigpu_counters) -> c_int;
+    pub fn umigpu_free(p: *mut c_void);
     pub fn umigpu_int_peak(ctx: *mut umigpu_ctx, lop3_ops_per_s: *mut f64, popc_ops_per_s: *mut f64) -> c_int;
 }
 

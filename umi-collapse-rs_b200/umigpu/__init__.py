@@ -2,6 +2,6 @@
 from ._lib import (ALGO_ADJ, ALGO_ADJ_UPSTREAM, ALGO_CC, ALGO_DIR, FLAG_KERNEL_DIRECT, FLAG_KERNEL_TILES, FLAG_LABELS, FLAG_NO_CULL, FLAG_NO_MULTI_INDEX,
                    LIB_PATH, MERGE_ANY, MERGE_AVGQUAL, MERGE_MAPQUAL, STAGES, SYMBOLS, UmiGpuError, load)
 from .api import (Adjacency, AdjacencyUpstream, AnyMerge, AvgQualMerge, Cli, ConnectedComponents, Context,
-                  DeduplicateGPU, Directional, MapQualMerge, Naive, ReadFreq, resolve_cli, shard_plan)
+                  DeduplicateGPU, Directional, MapQualMerge, Naive, ReadFreq, dedup_sharded, resolve_cli, shard_plan)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

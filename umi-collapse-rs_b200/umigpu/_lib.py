@@ -23,6 +23,7 @@ SYMBOLS = [
     "umigpu_get_counters", "umigpu_cluster_bucket", "umigpu_remove_near", "umigpu_neighbours",
     "umigpu_avg_qual", "umigpu_stage_ms", "umigpu_launch_count", "umigpu_result_free",
     "umigpu_shard_plan", "umigpu_int_peak", "umigpu_push_bam_records", "umigpu_bam_record_offsets",
+    "umigpu_dedup_sharded", "umigpu_free",
 ]
 
 
@@ -76,6 +77,9 @@ def load() -> C.CDLL:
         getattr(lib, name).argtypes = [p, u64, p, p, p, p, p, p, u64]
     lib.umigpu_push_bam_records.argtypes = [p, u64, p, p, C.c_uint8, u64, C.POINTER(u64)]
     lib.umigpu_bam_record_offsets.argtypes = [p, u64, p, u64, C.POINTER(u64), C.POINTER(u64)]
+    lib.umigpu_dedup_sharded.argtypes = [C.POINTER(Config), i32, p, u64, p, p, p, p, p, C.POINTER(C.POINTER(u64)), C.POINTER(u64), C.POINTER(Counters)]
+    lib.umigpu_free.argtypes = [p]
+    lib.umigpu_free.restype = None
     lib.umigpu_run.argtypes = [p]
     lib.umigpu_fetch.argtypes = [p, C.POINTER(Result)]
     lib.umigpu_finish.argtypes = [p, C.POINTER(Result)]

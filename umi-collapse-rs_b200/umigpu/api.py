@@ -208,6 +208,22 @@ class Context:
         return float(a.value), float(b.value)
 
 
+def dedup_sharded(umi_len: int, devices, tid, pos, rev, umi, score=None, k: int = 1, percentage: float = 0.5,
+                  algo: int = L.ALGO_DIR, merge: int = L.MERGE_AVGQUAL, flags: int = 0):
+    """umigpu_dedup_sharded: one call, one context + host thread per device, survivors merged in input order."""
+    lib = L.load()
+    cfg = L.Config(k=k, percentage=percentage, algo=algo, merge=merge, umi_len=umi_len, device=0, flags=flags, reserved=0, stream=None)
+    tid = np.ascontiguousarray(tid, np.int32); pos = np.ascontiguousarray(pos, np.int64); rev = np.ascontiguousarray(rev, np.uint8)
+    umi = np.ascontiguousarray(umi, np.uint8); score = None if score is None else np.ascontiguousarray(score, np.int32)
+    dev = np.ascontiguousarray(devices, np.int32)
+    kept_p, nk, ctr = C.POINTER(C.c_uint64)(), C.c_uint64(), L.Counters()
+    L.check(lib.umigpu_dedup_sharded(C.byref(cfg), len(dev), _ptr(dev), tid.shape[0], _ptr(tid), _ptr(pos), _ptr(rev), _ptr(umi), _ptr(score),
+                                     C.byref(kept_p), C.byref(nk), C.byref(ctr)))
+    kept = np.ctypeslib.as_array(kept_p, shape=(nk.value,)).copy() if nk.value else np.zeros(0, np.uint64)
+    lib.umigpu_free(kept_p)
+    return kept, ctr.as_dict()
+
+
 def shard_plan(tid, pos, rev, n_shards: int):
     """umigpu_shard_plan: LPT over per-bucket cost; returns (shard_of_read int32[n], shard_cost uint64[n_shards])."""
     lib = L.load()
