@@ -55,3 +55,21 @@ def test_umi_length_autodetect():
     buf = header + b"".join(recs)
     offs, _ = bamio.record_offsets(buf, len(header))
     assert bamio.autodetect_umi_length(buf, offs, ord("_")) == 9
+
+
+def test_umi_length_autodetect_follows_the_reference_regex():
+    """^(?:.*?)_([ATCGN]+)(?:.*?)$ caseless: the first separator FOLLOWED BY A LETTER decides the length, even though
+    get_umi later cuts after the first separator (utils/read.rs:67 vs :100-101)."""
+    hdr = bamio.make_header(["c"], [1000])
+    def length(qname):
+        rec = bamio.make_record(0, 10, 0, 30, qname, [(0, 10)], 10, bytes(10))
+        buf = hdr + rec
+        offs, _ = bamio.record_offsets(buf, len(hdr))
+        return bamio.autodetect_umi_length(buf, offs, ord("_"))
+    assert length(b"read_ACGTAC") == 6
+    assert length(b"read_ACGTAC_tail") == 6
+    assert length(b"read_1_ACGT") == 4            # first separator is followed by a digit: the regex moves on
+    assert length(b"read_acgtn") == 5             # caseless
+    import pytest
+    with pytest.raises(ValueError):
+        length(b"read_12")

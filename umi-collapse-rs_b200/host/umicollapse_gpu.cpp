@@ -196,10 +196,14 @@ static int run_bam(const Cli &a) {
         const uint8_t *r = buf.data() + first + offs[i];
         unsigned flag = r[18] | (r[19] << 8);
         if (flag & 4) continue;
+        // the caseless regex ^(?:.*?)SEP([ATCGN]+)(?:.*?)$: first separator that is followed by an [ATCGN] letter
         unsigned l_name = r[12]; const uint8_t *name = r + 36; unsigned len = l_name ? l_name - 1 : 0, p = 0;
-        while (p < len && name[p] != a.umi_separator) p++;
-        if (p >= len) die("failed to get the umi");
-        for (unsigned q = p + 1; q < len && strchr("ACGTNacgtn", name[q]); q++) umi_len++;
+        for (;; p++) {
+            while (p < len && name[p] != a.umi_separator) p++;
+            if (p >= len) die("failed to get the umi");
+            if (p + 1 < len && name[p + 1] && strchr("ACGTNacgtn", name[p + 1])) break;
+        }
+        for (unsigned q = p + 1; q < len && name[q] && strchr("ACGTNacgtn", name[q]); q++) umi_len++;
         break;
     }
     std::vector<const uint8_t *> optr{buf.data()}; std::vector<size_t> olen{first};
@@ -260,9 +264,12 @@ static int run_fastq(const Cli &a) {
     unsigned umi_len = a.umi_length;
     if (n && !umi_len) {
         size_t s = rec_start[0] + 1, e = hdr_end[0], q = s;
-        while (q < e && buf[q] != a.umi_separator) q++;
-        if (q >= e) die("failed to get the umi");
-        for (size_t t = q + 1; t < e && strchr("ACGTNacgtn", buf[t]); t++) umi_len++;
+        for (;; q++) {
+            while (q < e && buf[q] != a.umi_separator) q++;
+            if (q >= e) die("failed to get the umi");
+            if (q + 1 < e && buf[q + 1] && strchr("ACGTNacgtn", buf[q + 1])) break;
+        }
+        for (size_t t = q + 1; t < e && buf[t] && strchr("ACGTNacgtn", buf[t]); t++) umi_len++;
     }
     std::vector<const uint8_t *> optr; std::vector<size_t> olen;
     umigpu_counters ctr; memset(&ctr, 0, sizeof ctr);

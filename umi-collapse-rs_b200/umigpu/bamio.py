@@ -94,8 +94,11 @@ def push_bam(ctx: Context, buf, offsets: np.ndarray, umi_sep: int = ord("_"), fi
 
 
 def autodetect_umi_length(buf, offsets, sep: int) -> int:
-    """utils/read.rs:65-75,87-94 on the first mapped record: the run of [ATCGN] (caseless) after the first
-    separator of the read name."""
+    """utils/read.rs:65-75,87-94 on the first mapped record: the caseless regex ^(?:.*?)SEP([ATCGN]+)(?:.*?)$ —
+    i.e. the run of [ATCGN] after the FIRST separator that is followed by at least one such letter.  (get_umi
+    itself always cuts after the first separator, utils/read.rs:100-101; when the two disagree the reference
+    goes on to panic in to_bitset, and so does this path with UMIGPU_ERR_BAD_BASE.)"""
+    letters = b"ACGTNacgtn"
     for i in range(len(offsets) - 1):
         o = int(offsets[i])
         flag, = struct.unpack_from("<H", buf, o + 18)
@@ -103,11 +106,15 @@ def autodetect_umi_length(buf, offsets, sep: int) -> int:
             continue
         l_name = buf[o + 12]
         name = bytes(buf[o + 36: o + 36 + l_name - 1])
-        p = name.find(bytes([sep]))
-        if p < 0:
-            raise ValueError("failed to get the umi")
+        p = -1
+        while True:
+            p = name.find(bytes([sep]), p + 1)
+            if p < 0:
+                raise ValueError("failed to get the umi")          # regex does not match: unwrap() panics
+            if p + 1 < len(name) and name[p + 1] in letters:
+                break
         n = 0
-        while p + 1 + n < len(name) and name[p + 1 + n: p + 2 + n].upper() in (b"A", b"C", b"G", b"T", b"N"):
+        while p + 1 + n < len(name) and name[p + 1 + n] in letters:
             n += 1
         return n
     return 0
