@@ -95,3 +95,24 @@ def test_shard_plan_keeps_buckets_whole_and_balances():
         assert int(cost.sum()) == int(c.sum())
         # LPT bound: max load <= mean + largest item
         assert cost.max() <= cost.sum() / shards + c.max()
+
+
+def test_cpp_cli_twin_validates_like_main_rs():
+    """umi-collapse-rs_b200/host/umicollapse_gpu (no GPU needed for argument handling): required arguments,
+    main.rs:41-47 panics, unknown flags."""
+    import subprocess
+    exe = os.path.join(REPO, "umi-collapse-rs_b200", "host", "umicollapse_gpu")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe)])
+    def run(*argv):
+        return subprocess.run([exe, *argv], capture_output=True, text=True, timeout=60)
+    r = run("-i", "a")
+    assert r.returncode != 0 and "required arguments" in r.stderr
+    r = run("-i", "a", "-o", "b", "--tag", "--two-pass")
+    assert r.returncode != 0 and "Cannot track clusters with the two pass algorithm!" in r.stderr
+    r = run("-i", "a", "-o", "b", "--paired", "--keep-unmapped")
+    assert r.returncode != 0 and "Cannot keep unmapped reads with paired-end reads!" in r.stderr
+    r = run("-i", "a", "-o", "b", "--bogus")
+    assert r.returncode != 0 and "unexpected argument" in r.stderr
+    r = run("-i", "/nonexistent/in.bam", "-o", "/tmp/out.bam", "--data", "ngrambktree", "--num-threads", "2")
+    assert r.returncode != 0 and "Invalid input path" in r.stderr          # deduplicate_sam.rs:78 expect("Invalid input path")
