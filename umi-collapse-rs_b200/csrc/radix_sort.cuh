@@ -15,6 +15,10 @@
 #include "common.cuh"
 #include "scan.cuh"
 
+#ifndef RS_RB
+#define RS_RB 8                  // digit width in bits (RS_RADIX bins)
+#endif
+#define RS_RADIX (1 << RS_RB)
 #define RS_THREADS 512
 #define RS_WARPS   (RS_THREADS / 32)
 #define RS_MAX_PASSES 16
@@ -34,9 +38,9 @@ struct SortPlan { int npass; SortPass p[RS_MAX_PASSES]; };
 // serialise on one shared-memory address.
 #define GH_THREADS 256
 #define GH_ITEMS   8
-__global__ void __launch_bounds__(GH_THREADS) radix_global_hist(KeyArr in, u64 n, SortPlan plan, u32 *__restrict__ ghist /* [npass][256] */) {
-    __shared__ u32 sh[RS_MAX_PASSES * 256];
-    for (u32 i = threadIdx.x; i < (u32)plan.npass * 256; i += GH_THREADS) sh[i] = 0;
+__global__ void __launch_bounds__(GH_THREADS) radix_global_hist(KeyArr in, u64 n, SortPlan plan, u32 *__restrict__ ghist /* [npass][RS_RADIX] */) {
+    __shared__ u32 sh[RS_MAX_PASSES * RS_RADIX];
+    for (u32 i = threadIdx.x; i < (u32)plan.npass * RS_RADIX; i += GH_THREADS) sh[i] = 0;
     __syncthreads();
     const u64 stride = (u64)gridDim.x * GH_THREADS * GH_ITEMS;
     for (u64 base = ((u64)blockIdx.x * GH_THREADS + threadIdx.x) * GH_ITEMS; base < n; base += stride) {
@@ -55,42 +59,42 @@ __global__ void __launch_bounds__(GH_THREADS) radix_global_hist(KeyArr in, u64 n
             for (int j = 0; j < GH_ITEMS; j++) {
                 if (j < cnt) {
                     u32 d = (u32)((hi ? k1[j] : k0[j]) >> sh_) & mask;
-                    if (d != run_d) { if (run_c) atomicAdd(&sh[p * 256 + run_d], run_c); run_d = d; run_c = 0; }
+                    if (d != run_d) { if (run_c) atomicAdd(&sh[p * RS_RADIX + run_d], run_c); run_d = d; run_c = 0; }
                     run_c++;
                 }
             }
-            if (run_c) atomicAdd(&sh[p * 256 + run_d], run_c);
+            if (run_c) atomicAdd(&sh[p * RS_RADIX + run_d], run_c);
         }
     }
     __syncthreads();
-    for (u32 i = threadIdx.x; i < (u32)plan.npass * 256; i += GH_THREADS) if (sh[i]) atomicAdd(&ghist[i], sh[i]);
+    for (u32 i = threadIdx.x; i < (u32)plan.npass * RS_RADIX; i += GH_THREADS) if (sh[i]) atomicAdd(&ghist[i], sh[i]);
 }
 
-// exclusive scan of each pass's 256 bins (one warp-pair per pass; tiny)
-__global__ void __launch_bounds__(256) radix_digit_starts(u32 *ghist, int npass) {
-    __shared__ u32 s[256];
+// exclusive scan of each pass's RS_RADIX bins (one CTA; tiny)
+__global__ void __launch_bounds__(RS_RADIX) radix_digit_starts(u32 *ghist, int npass) {
+    __shared__ u32 s[RS_RADIX];
     for (int p = 0; p < npass; p++) {
-        u32 v = ghist[p * 256 + threadIdx.x];
+        u32 v = ghist[p * RS_RADIX + threadIdx.x];
         s[threadIdx.x] = v;
         __syncthreads();
-        // Hillis-Steele inclusive scan over 256 elements
-        for (int o = 1; o < 256; o <<= 1) {
+        // Hillis-Steele inclusive scan
+        for (int o = 1; o < RS_RADIX; o <<= 1) {
             u32 t = threadIdx.x >= (u32)o ? s[threadIdx.x - o] : 0;
             __syncthreads();
             s[threadIdx.x] += t;
             __syncthreads();
         }
-        ghist[p * 256 + threadIdx.x] = s[threadIdx.x] - v;
+        ghist[p * RS_RADIX + threadIdx.x] = s[threadIdx.x] - v;
         __syncthreads();
     }
 }
 
-// Ranks the thread's keys by digit.  packed[j] = digit | (rank within (warp, digit) << 8), or
+// Ranks the thread's keys by digit.  packed[j] = digit | (rank within (warp, digit) << RS_RB), or
 // 0xffffffff past the end.  On return whist[w][d] = number of keys with digit d in warp w's slice.
 template <int ITEMS, bool FULL>
-__device__ __forceinline__ void rs_rank_tile(u32 *packed /* in: digit or 0xffffffff */, u32 (*whist)[256]) {
+__device__ __forceinline__ void rs_rank_tile(u32 *packed /* in: digit or 0xffffffff */, u32 (*whist)[RS_RADIX]) {
     const u32 w = threadIdx.x >> 5, lane = lane_id();
-    for (u32 i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&whist[0][0])[i] = 0;
+    for (u32 i = threadIdx.x; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&whist[0][0])[i] = 0;
     __syncthreads();
     const u32 lt = lanemask_lt();
 #pragma unroll
@@ -103,7 +107,7 @@ __device__ __forceinline__ void rs_rank_tile(u32 *packed /* in: digit or 0xfffff
         // out of the result by `act`.
         u32 peers = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, active);
 #pragma unroll
-        for (int b = 0; b < 8; b++) {
+        for (int b = 0; b < RS_RB; b++) {
             const bool bit = (d & (1u << b)) != 0u;
             const u32 m = __ballot_sync(0xffffffffu, bit);
             peers &= bit ? m : ~m;
@@ -112,7 +116,7 @@ __device__ __forceinline__ void rs_rank_tile(u32 *packed /* in: digit or 0xfffff
         u32 old = 0;
         if (active && lane == leader) { old = whist[w][d]; whist[w][d] = old + __popc(peers); }
         old = __shfl_sync(0xffffffffu, old, leader);
-        if (active) packed[j] = d | ((old + __popc(peers & lt)) << 8);
+        if (active) packed[j] = d | ((old + __popc(peers & lt)) << RS_RB);
         __syncwarp();
     }
 }
@@ -122,8 +126,8 @@ __device__ __forceinline__ void rs_rank_tile(u32 *packed /* in: digit or 0xfffff
 // unrelated 8-byte fragments.  err[0] is set if a look-back ever exceeds its spin budget (cannot
 // happen with ticketed tiles; it turns a would-be hang into a reported error).
 struct RsShared {
-    u32 whist[RS_WARPS][256];
-    u32 sbase[256], slocal[256];
+    u32 whist[RS_WARPS][RS_RADIX];
+    u32 sbase[RS_RADIX], slocal[RS_RADIX];
     u32 sscan[RS_THREADS / 32 + 1];
     u32 s_tile;
 };
@@ -135,7 +139,7 @@ __device__ __forceinline__ void rs_onesweep_body(
     KeyArr in, const u32 *__restrict__ idx_in, KeyArr out, u32 *__restrict__ idx_out, u64 n, int wsel, int sh, u32 mask,
     const u32 *__restrict__ digit_start, unsigned long long *tile_state, u32 *err, int iota) {
     constexpr u32 TILE = RS_THREADS * ITEMS;
-    u32 (*whist)[256] = S.whist;
+    u32 (*whist)[RS_RADIX] = S.whist;
     u32 *sbase = S.sbase, *slocal = S.slocal, *sscan = S.sscan;
     const u64 tile_base = (u64)tile * TILE;
     const u32 w = threadIdx.x >> 5, lane = lane_id();
@@ -159,11 +163,11 @@ __device__ __forceinline__ void rs_onesweep_body(
     rs_rank_tile<ITEMS, FULL>(packed, whist);
     __syncthreads();
     u32 total = 0;
-    if (threadIdx.x < 256) {
+    if (threadIdx.x < RS_RADIX) {
         const u32 d = threadIdx.x;
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ww++) { u32 t = whist[ww][d]; whist[ww][d] = total; total += t; }
-        unsigned long long *mine = tile_state + (u64)tile * 256 + d;
+        unsigned long long *mine = tile_state + (u64)tile * RS_RADIX + d;
         u64 excl = 0;
         if (tile == 0) {
             atomicExch(mine, RS_FLAG_PREFIX | (unsigned long long)total);
@@ -178,7 +182,7 @@ __device__ __forceinline__ void rs_onesweep_body(
                 unsigned long long v[RS_LB];
 #pragma unroll
                 for (int i = 0; i < RS_LB; i++) {
-                    const volatile unsigned long long *prev = tile_state + (u64)(p > (u32)i ? p - 1 - i : 0) * 256 + d;
+                    const volatile unsigned long long *prev = tile_state + (u64)(p > (u32)i ? p - 1 - i : 0) * RS_RADIX + d;
                     v[i] = *prev;
                 }
 #pragma unroll
@@ -201,13 +205,13 @@ __device__ __forceinline__ void rs_onesweep_body(
     // start of each digit inside the tile (exclusive scan of the tile's digit counts)
     u32 tot_all;
     const u32 lstart = block_exclusive_scan<u32, RS_THREADS>(total, sscan, &tot_all);
-    if (threadIdx.x < 256) slocal[threadIdx.x] = lstart;
+    if (threadIdx.x < RS_RADIX) slocal[threadIdx.x] = lstart;
     __syncthreads();
     // permute the tile into digit order in shared memory
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         if (FULL || packed[j] != 0xffffffffu) {
-            const u32 d = packed[j] & 0xff, r = packed[j] >> 8;
+            const u32 d = packed[j] & (RS_RADIX - 1), r = packed[j] >> RS_RB;
             const u32 lp = slocal[d] + whist[w][d] + r;
 #pragma unroll
             for (int k = 0; k < NW; k++) skey[(size_t)k * TILE + lp] = key[k][j];
@@ -236,7 +240,7 @@ __device__ __forceinline__ void rs_onesweep_body(
 template <int NW, int ITEMS>
 __global__ void __launch_bounds__(RS_THREADS, (NW == 1 ? 2 : 1)) radix_onesweep(
     KeyArr in, const u32 *__restrict__ idx_in, KeyArr out, u32 *__restrict__ idx_out, u64 n, int wsel, int sh, u32 mask,
-    const u32 *__restrict__ digit_start, unsigned long long *tile_state /* [ntiles][256] */, u32 *ticket, u32 *err, int iota) {
+    const u32 *__restrict__ digit_start, unsigned long long *tile_state /* [ntiles][RS_RADIX] */, u32 *ticket, u32 *err, int iota) {
     constexpr u32 TILE = RS_THREADS * ITEMS;
     extern __shared__ __align__(16) unsigned char rs_dyn[];          // u64 skey[NW][TILE]; u32 sidx[TILE]
     u64 *skey = reinterpret_cast<u64 *>(rs_dyn);
@@ -258,7 +262,7 @@ static inline SortPlan rs_plan(int total_bits) {
     for (int word = 0; word < 2; word++) {
         int lo = word * 64, hi = total_bits < lo + 64 ? total_bits : lo + 64;
         if (hi <= lo) break;
-        int nbits = hi - lo, npass = (nbits + 7) / 8;
+        int nbits = hi - lo, npass = (nbits + RS_RB - 1) / RS_RB;
         // spread the bits evenly over the passes (e.g. 53 bits -> 7 passes of 7/8 bits)
         int done = 0;
         for (int i = 0; i < npass; i++) {

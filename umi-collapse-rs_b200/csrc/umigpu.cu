@@ -364,31 +364,31 @@ static int run_sort(umigpu_ctx *ctx, u64 n, int nw, const SortPlan &plan, int *c
     if (!items1) { const char *e = getenv("UMIGPU_RS_ITEMS"); items1 = e ? atoi(e) : RS_ITEMS_1; if (items1 != 8 && items1 != 12 && items1 != 16) items1 = RS_ITEMS_1; }
     const u32 tile = RS_THREADS * (nw == 1 ? items1 : RS_ITEMS_2);
     const u32 ntiles = (u32)ceil_div_u64(n, tile);
-    CK(ctx->d_hist.reserve((size_t)RS_MAX_PASSES * 256 * sizeof(u32)));
-    CK(ctx->d_tilestate.reserve((size_t)ntiles * 256 * 8));
+    CK(ctx->d_hist.reserve((size_t)RS_MAX_PASSES * RS_RADIX * sizeof(u32)));
+    CK(ctx->d_tilestate.reserve((size_t)ntiles * RS_RADIX * 8));
     u32 *ghist = ctx->d_hist.as<u32>();
-    CK(cudaMemsetAsync(ghist, 0, (size_t)plan.npass * 256 * 4, ctx->stream));
+    CK(cudaMemsetAsync(ghist, 0, (size_t)plan.npass * RS_RADIX * 4, ctx->stream));
     CK(cudaMemsetAsync(&sc->sort_err, 0, 4, ctx->stream));
     KeyArr k0{{ctx->d_key[0][0].as<u64>(), nw == 2 ? ctx->d_key[0][1].as<u64>() : nullptr}};
     u32 ggrid = (u32)std::min<u64>(ceil_div_u64(n, (u64)GH_THREADS * GH_ITEMS), (u64)ctx->num_sms * 8);
     LAUNCH(radix_global_hist, ggrid, GH_THREADS, k0, n, plan, ghist);
-    LAUNCH(radix_digit_starts, 1, 256, ghist, plan.npass);
+    LAUNCH(radix_digit_starts, 1, RS_RADIX, ghist, plan.npass);
     int cur = 0;
     for (int pi = 0; pi < plan.npass; pi++) {
         const SortPass &p = plan.p[pi];
         KeyArr in{{ctx->d_key[cur][0].as<u64>(), ctx->d_key[cur][1].as<u64>()}};
         KeyArr out{{ctx->d_key[cur ^ 1][0].as<u64>(), ctx->d_key[cur ^ 1][1].as<u64>()}};
         const u32 mask = (1u << p.bits) - 1;
-        CK(cudaMemsetAsync(ctx->d_tilestate.p, 0, (size_t)ntiles * 256 * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_tilestate.p, 0, (size_t)ntiles * RS_RADIX * 8, ctx->stream));
         CK(cudaMemsetAsync(&sc->sort_ticket, 0, 4, ctx->stream));
         const size_t dyn = (size_t)tile * (nw * 8 + 4);
 #define RS_LAUNCH1(IT) LAUNCH_SMEM((radix_onesweep<1, IT>), ntiles, RS_THREADS, dyn, in, (const u32 *)ctx->d_idx[cur].as<u32>(), out, ctx->d_idx[cur ^ 1].as<u32>(), n, \
-                   p.word, p.shift, mask, (const u32 *)(ghist + pi * 256), ctx->d_tilestate.as<unsigned long long>(), &sc->sort_ticket, &sc->sort_err, pi == 0 ? 1 : 0)
+                   p.word, p.shift, mask, (const u32 *)(ghist + pi * RS_RADIX), ctx->d_tilestate.as<unsigned long long>(), &sc->sort_ticket, &sc->sort_err, pi == 0 ? 1 : 0)
         if (nw == 1) { if (items1 == 8) RS_LAUNCH1(8); else if (items1 == 16) RS_LAUNCH1(16); else RS_LAUNCH1(12); }
 #undef RS_LAUNCH1
         else
             LAUNCH_SMEM((radix_onesweep<2, RS_ITEMS_2>), ntiles, RS_THREADS, dyn, in, (const u32 *)ctx->d_idx[cur].as<u32>(), out, ctx->d_idx[cur ^ 1].as<u32>(), n,
-                   p.word, p.shift, mask, (const u32 *)(ghist + pi * 256), ctx->d_tilestate.as<unsigned long long>(), &sc->sort_ticket, &sc->sort_err, pi == 0 ? 1 : 0);
+                   p.word, p.shift, mask, (const u32 *)(ghist + pi * RS_RADIX), ctx->d_tilestate.as<unsigned long long>(), &sc->sort_ticket, &sc->sort_err, pi == 0 ? 1 : 0);
         cur ^= 1;
     }
     *cur_out = cur;
@@ -1004,7 +1004,7 @@ extern "C" int umigpu_neighbours(umigpu_ctx *ctx, uint64_t n, const uint8_t *umi
     {
         SortPlan plan; plan.npass = 0;
         for (int part = 0; part < 2; part++) {
-            int done = 0, np = (nb + 7) / 8;
+            int done = 0, np = (nb + RS_RB - 1) / RS_RB;
             for (int i = 0; i < np; i++) { int b = (nb - done + (np - i) - 1) / (np - i); plan.p[plan.npass++] = {0, part * 32 + done, b}; done += b; }
         }
         if (plan.npass > 0) { rc = run_sort(ctx, E, 1, plan, &cur); if (rc) return rc; }

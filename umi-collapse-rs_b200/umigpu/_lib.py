@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libumigpu.so")
+LIB_PATH = os.environ.get("UMIGPU_LIB") or os.path.join(os.path.dirname(_HERE), "csrc", "libumigpu.so")   # UMIGPU_LIB: A/B builds
 
 OK, ERR_ARG, ERR_CUDA, ERR_BAD_BASE, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 ALGO_DIR, ALGO_ADJ, ALGO_ADJ_UPSTREAM, ALGO_CC = 0, 1, 2, 3
