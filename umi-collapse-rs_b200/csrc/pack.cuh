@@ -66,11 +66,13 @@ __global__ void __launch_bounds__(PACK_THREADS) umi_pack_kernel(
             const u8 *s = sbuf + threadIdx.x * (u32)L;
             u64 code = 0; u32 nm = 0;
             for (int b = 0; b < L; b++) {
-                u32 c = s[b], v;
-                // utils/read.rs:22-31 alphabet; anything else panics in the reference (utils/mod.rs:78)
-                if (c == 'A') v = 0; else if (c == 'C') v = 1; else if (c == 'G') v = 2; else if (c == 'T') v = 3;
-                else if (c == 'N') { v = 0; nm |= 1u << (L - 1 - b); }
-                else { v = 0; flags |= 2u; }
+                // utils/read.rs:22-31 alphabet; anything else panics in the reference (utils/mod.rs:78).
+                // Branch-free: bits 1-2 of the ASCII code separate A,C,T,G (0,1,2,3); a Gray step turns that into
+                // A0 C1 G2 T3; the byte is valid iff it equals the letter its own bits name.
+                const u32 c = s[b], w = (c >> 1) & 3u;
+                u32 v = w ^ (w >> 1);
+                const bool acgt = c == ((0x47544341u >> (8u * w)) & 0xffu);
+                if (!acgt) { v = 0; if (c == 'N') nm |= 1u << (L - 1 - b); else flags |= 2u; }
                 code = (code << 2) | v;
             }
             umi2[i] = code; nmask[i] = nm; if (nm) flags |= 1u;
