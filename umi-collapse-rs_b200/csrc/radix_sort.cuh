@@ -167,12 +167,31 @@ __device__ __forceinline__ void rs_onesweep_body(
         const u32 d = threadIdx.x;
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ww++) { u32 t = whist[ww][d]; whist[ww][d] = total; total += t; }
+        // publish this tile's digit counts right away; the look-back itself is deferred until after the shared-memory
+        // permutation so that the predecessors have had that long to publish theirs
+        atomicExch(tile_state + (u64)tile * RS_RADIX + d, (tile == 0 ? RS_FLAG_PREFIX : RS_FLAG_AGG) | (unsigned long long)total);
+    }
+    // start of each digit inside the tile (exclusive scan of the tile's digit counts)
+    u32 tot_all;
+    const u32 lstart = block_exclusive_scan<u32, RS_THREADS>(total, sscan, &tot_all);
+    if (threadIdx.x < RS_RADIX) slocal[threadIdx.x] = lstart;
+    __syncthreads();
+    // permute the tile into digit order in shared memory
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        if (FULL || packed[j] != 0xffffffffu) {
+            const u32 d = packed[j] & (RS_RADIX - 1), r = packed[j] >> RS_RB;
+            const u32 lp = slocal[d] + whist[w][d] + r;
+#pragma unroll
+            for (int k = 0; k < NW; k++) skey[(size_t)k * TILE + lp] = key[k][j];
+            sidx[lp] = vidx[j];
+        }
+    }
+    if (threadIdx.x < RS_RADIX) {
+        const u32 d = threadIdx.x;
         unsigned long long *mine = tile_state + (u64)tile * RS_RADIX + d;
         u64 excl = 0;
-        if (tile == 0) {
-            atomicExch(mine, RS_FLAG_PREFIX | (unsigned long long)total);
-        } else {
-            atomicExch(mine, RS_FLAG_AGG | (unsigned long long)total);
+        if (tile != 0) {
             // decoupled look-back, RS_LB predecessors per round: the loads of a round are independent
             // (one latency per round instead of one per tile); a not-yet-published state ends the round
             u32 p = tile;          // predecessors [0, p) are still to be accounted for
@@ -201,22 +220,6 @@ __device__ __forceinline__ void rs_onesweep_body(
             atomicExch(mine, RS_FLAG_PREFIX | (unsigned long long)(excl + total));
         }
         sbase[d] = digit_start[d] + (u32)excl;
-    }
-    // start of each digit inside the tile (exclusive scan of the tile's digit counts)
-    u32 tot_all;
-    const u32 lstart = block_exclusive_scan<u32, RS_THREADS>(total, sscan, &tot_all);
-    if (threadIdx.x < RS_RADIX) slocal[threadIdx.x] = lstart;
-    __syncthreads();
-    // permute the tile into digit order in shared memory
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-        if (FULL || packed[j] != 0xffffffffu) {
-            const u32 d = packed[j] & (RS_RADIX - 1), r = packed[j] >> RS_RB;
-            const u32 lp = slocal[d] + whist[w][d] + r;
-#pragma unroll
-            for (int k = 0; k < NW; k++) skey[(size_t)k * TILE + lp] = key[k][j];
-            sidx[lp] = vidx[j];
-        }
     }
     __syncthreads();
     // coalesced write-out: consecutive threads hold consecutive elements of (mostly) the same digit
