@@ -101,6 +101,9 @@ typedef struct umigpu_result {
     const uint64_t  *read_cluster_root;/* FLAG_LABELS only: per pushed read (push order), the read index
                                           of the emitted representative of its cluster                */
     umigpu_counters  counters;
+    const uint64_t  *read_umi_rep;     /* FLAG_LABELS only: per pushed read, the read index of the representative of its own
+                                          (bucket, UMI) group — with read_cluster_root this is everything --tag needs
+                                          (cluster id / cluster_size / same_umi, src/cli.rs:64-76)                    */
 } umigpu_result;
 
 /* stage ids for umigpu_stage_ms */

@@ -162,3 +162,69 @@ def test_cpp_cli_rejects_like_the_reference():
     assert r.returncode != 0 and "Cannot track clusters with the two pass algorithm!" in r.stderr
     r = _cli("-i", "a", "-o", "b", "--paired", "--keep-unmapped")
     assert r.returncode != 0 and "Cannot keep unmapped reads with paired-end reads!" in r.stderr
+
+
+def _parse_tags(rec: bytes):
+    """(flag, {tag: value}) of one raw BAM record."""
+    import struct
+    l_name = rec[12]; n_cigar, flag = struct.unpack_from("<HH", rec, 16); l_seq, = struct.unpack_from("<i", rec, 20)
+    p = 36 + l_name + 4 * n_cigar + (l_seq + 1) // 2 + l_seq
+    tags = {}
+    while p < len(rec):
+        tag, typ = rec[p:p + 2].decode(), chr(rec[p + 2]); p += 3
+        if typ == "I":
+            tags[tag] = struct.unpack_from("<I", rec, p)[0]; p += 4
+        elif typ == "Z":
+            e = rec.index(b"\0", p); tags[tag] = rec[p:e].decode(); p = e + 1
+        else:
+            raise AssertionError(typ)
+    return flag, tags
+
+
+def test_cpp_cli_tag_mode(tmp_path):
+    """--tag as specified by the reference's help text (src/cli.rs:64-76; the reference itself writes nothing in this
+    mode): every mapped read is written, non-consensus reads carry the duplicate flag, MI / RX on all, cs on the
+    consensus read, su on the best read of each distinct UMI.  Expectations come from the oracle's cluster roots."""
+    rng = random.Random(33)
+    header, recs, truth = make_bam(rng, 3000, umi_len=8)
+    inp, out = str(tmp_path / "in.bam"), str(tmp_path / "out.bam")
+    bamio.bgzf_write_all(inp, header + b"".join(recs))
+    r = _cli("--mode", "bam", "-i", inp, "-o", out, "--algo", "dir", "--merge", "avgqual", "--tag", "--num-threads", "2")
+    assert r.returncode == 0, r.stderr
+    back = bamio.bgzf_read_all(out)
+    _, _, first = bamio.parse_header(back)
+    offs, _ = bamio.record_offsets(back, first)
+    got = [bytes(back[int(offs[i]): int(offs[i + 1])]) for i in range(len(offs) - 1)]
+    # oracle: decode, dedup with roots
+    idx, tid, pos, rev, umi, score = [], [], [], [], [], []
+    for i, rec in enumerate(recs):
+        d = O.bam_decode(rec, 8, ord("_"), False)
+        if d["valid"]:
+            idx.append(i); tid.append(d["tid"]); pos.append(d["pos"]); rev.append(d["rev"]); umi.append(d["umi"]); score.append(d["score"])
+    a = np.frombuffer(b"".join(umi), np.uint8).reshape(len(umi), 8)
+    kept, roots, _ = O.dedup(tid, pos, rev, a, score, O.ALGO_DIR, O.MERGE_AVGQUAL, 1, 0.5, want_roots=True)
+    assert len(got) == len(idx)                                        # every mapped read is written
+    roots = roots.tolist()
+    csize = {}
+    for rt in roots:
+        csize[rt] = csize.get(rt, 0) + 1
+    groups = {}
+    for j in range(len(idx)):
+        groups.setdefault((tid[j], pos[j], rev[j], umi[j]), []).append(j)
+    urep, same = {}, {}
+    for key, members in groups.items():
+        best = min(m for m in members if score[m] == max(score[x] for x in members))
+        urep[best] = True; same[best] = len(members)
+    mi_of_root = {}
+    for j, rec in enumerate(got):
+        flag, tags = _parse_tags(rec)
+        orig = recs[idx[j]]
+        assert rec[4:36 + orig[12]] [:14] == orig[4:18]               # untouched fixed fields before the flag
+        is_root = roots[j] == j
+        assert bool(flag & 0x400) == (not is_root)
+        assert tags["RX"] == umi[roots[j]].decode()
+        mi_of_root.setdefault(roots[j], tags["MI"])
+        assert tags["MI"] == mi_of_root[roots[j]]
+        assert ("cs" in tags) == is_root and (not is_root or tags["cs"] == csize[j])
+        assert ("su" in tags) == (j in urep) and (j not in urep or tags["su"] == same[j])
+    assert len(set(mi_of_root.values())) == len(mi_of_root) == len(kept)      # one id per cluster

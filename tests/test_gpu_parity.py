@@ -388,3 +388,19 @@ def test_one_call_sharded_over_devices():
         assert kept.astype(np.int64).tolist() == okept.tolist()
         for key in ("total_reads", "n_buckets", "total_umis", "max_umis", "n_kept", "unordered_pairs"):
             assert ctr[key] == octr[key], key
+
+
+def test_labels_expose_cluster_root_and_umi_representative():
+    """FLAG_LABELS: read_cluster_root (ClusterTracker) and read_umi_rep (the best read of the read's own UMI group)."""
+    d, _ = small("C1", 0.01, seed=41)
+    with umigpu.Context(d["umi"].shape[1], 1, 0.5, umigpu.ALGO_DIR, umigpu.MERGE_AVGQUAL, 0, umigpu.FLAG_LABELS) as ctx:
+        ctx.push_reads(d["tid"], d["pos"], d["rev"], d["umi"], d["score"])
+        kept, roots, _ = ctx.finish()
+        urep = ctx.last_umi_rep
+    groups = {}
+    for i in range(len(d["tid"])):
+        groups.setdefault((int(d["tid"][i]), int(d["pos"][i]), int(d["rev"][i]), bytes(d["umi"][i])), []).append(i)
+    for members in groups.values():
+        best = min(m for m in members if d["score"][m] == max(d["score"][x] for x in members))
+        assert all(int(urep[m]) == best for m in members)
+    assert set(roots.tolist()) == set(kept.tolist())

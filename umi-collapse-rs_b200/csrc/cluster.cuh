@@ -182,7 +182,12 @@ struct BitmapEmit {
 // per read: read index of the emitted representative of its cluster (ClusterTracker, --tag)
 __global__ void __launch_bounds__(256) read_roots_kernel(u64 n, const u32 *__restrict__ read_uid,
                                                          const unsigned long long *__restrict__ label,
-                                                         const u32 *__restrict__ rep_idx, ChunkMap cm, u64 *__restrict__ out) {
+                                                         const u32 *__restrict__ rep_idx, ChunkMap cm, u64 *__restrict__ out,
+                                                         u64 *__restrict__ out_umi_rep) {
     u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
-    if (i < n) out[i] = cm(rep_idx[(u32)label[read_uid[i]]]);
+    if (i < n) {
+        const u32 u = read_uid[i];
+        out[i] = cm(rep_idx[(u32)label[u]]);          // representative of the read's cluster
+        out_umi_rep[i] = cm(rep_idx[u]);              // representative of the read's own (bucket, UMI)
+    }
 }

@@ -56,6 +56,8 @@ struct umigpu_ctx {
     KeyLayout lay;
     u64 *h_kept = nullptr; size_t h_kept_cap = 0;       // pinned; what umigpu_result.kept_read_index points to
     u64 *h_roots = nullptr; size_t h_roots_cap = 0;     // pinned
+    u64 *h_umirep = nullptr;                            // pinned, same capacity as h_roots
+    DevBuf d_umirep;
     DevBuf d_chunks;
     // BAM feed
     DevBuf d_bamraw, d_bamoff, d_btid, d_bpos, d_brev, d_bumi2, d_bnmask, d_bscore, d_bvalid, d_orig;
@@ -155,7 +157,8 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
     if (ctx->h_kept) cudaFreeHost(ctx->h_kept);
     if (ctx->h_roots) cudaFreeHost(ctx->h_roots);
-    ctx->d_chunks.release();
+    if (ctx->h_umirep) cudaFreeHost(ctx->h_umirep);
+    ctx->d_chunks.release(); ctx->d_umirep.release();
     DevBuf *bb[] = {&ctx->d_bamraw, &ctx->d_bamoff, &ctx->d_btid, &ctx->d_bpos, &ctx->d_brev, &ctx->d_bumi2, &ctx->d_bnmask, &ctx->d_bscore, &ctx->d_bvalid, &ctx->d_orig};
     for (DevBuf *b : bb) b->release();
     for (int s = 0; s < UMIGPU_N_STAGES; s++) { if (ctx->ev[s][0]) cudaEventDestroy(ctx->ev[s][0]); if (ctx->ev[s][1]) cudaEventDestroy(ctx->ev[s][1]); }
@@ -812,9 +815,9 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     rc = run_scan(ctx, BitmapCount{ctx->d_bitmap.as<u32>()}, BitmapEmit{ctx->d_bitmap.as<u32>(), ctx->d_kept.as<u64>(), n_words, sc, cm}, n_words, nullptr);
     if (rc) return rc;
     if (want_labels) {
-        CK(ctx->d_roots.reserve(n * 8));
+        CK(ctx->d_roots.reserve(n * 8)); CK(ctx->d_umirep.reserve(n * 8));
         LAUNCH(read_roots_kernel, grid_for(n, 256), 256, n, (const u32 *)ctx->d_read_uid.p, (const unsigned long long *)label,
-               (const u32 *)ctx->d_repidx.p, cm, ctx->d_roots.as<u64>());
+               (const u32 *)ctx->d_repidx.p, cm, ctx->d_roots.as<u64>(), ctx->d_umirep.as<u64>());
     }
     STAGE_END(UMIGPU_STAGE_EMIT);
     STAGE_END(UMIGPU_STAGE_TOTAL);
@@ -843,11 +846,14 @@ static int fetch_internal(umigpu_ctx *ctx, bool want_labels) {
     if (want_labels && n) {
         if (n > ctx->h_roots_cap) {
             if (ctx->h_roots) cudaFreeHost(ctx->h_roots);
-            ctx->h_roots = nullptr; ctx->h_roots_cap = 0;
+            if (ctx->h_umirep) cudaFreeHost(ctx->h_umirep);
+            ctx->h_roots = ctx->h_umirep = nullptr; ctx->h_roots_cap = 0;
             CK(cudaMallocHost((void **)&ctx->h_roots, (n + 16) * 8));
+            CK(cudaMallocHost((void **)&ctx->h_umirep, (n + 16) * 8));
             ctx->h_roots_cap = n + 16;
         }
         CK(cudaMemcpyAsync(ctx->h_roots, ctx->d_roots.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_umirep, ctx->d_umirep.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     return UMIGPU_OK;
@@ -862,6 +868,7 @@ extern "C" int umigpu_fetch(umigpu_ctx *ctx, umigpu_result *out) {
     out->kept_read_index = ctx->h_kept;
     out->n_reads = ctx->n_reads;
     out->read_cluster_root = want_labels ? ctx->h_roots : nullptr;
+    out->read_umi_rep = want_labels ? ctx->h_umirep : nullptr;
     out->counters = ctx->ctr;
     return UMIGPU_OK;
 }
@@ -883,7 +890,8 @@ extern "C" void umigpu_result_free(umigpu_ctx *ctx) {
     if (!ctx) return;
     if (ctx->h_kept) cudaFreeHost(ctx->h_kept);
     if (ctx->h_roots) cudaFreeHost(ctx->h_roots);
-    ctx->h_kept = ctx->h_roots = nullptr; ctx->h_kept_cap = ctx->h_roots_cap = 0;
+    if (ctx->h_umirep) cudaFreeHost(ctx->h_umirep);
+    ctx->h_kept = ctx->h_roots = ctx->h_umirep = nullptr; ctx->h_kept_cap = ctx->h_roots_cap = 0;
 }
 
 extern "C" int umigpu_stage_ms(umigpu_ctx *ctx, int stage, float *ms) {

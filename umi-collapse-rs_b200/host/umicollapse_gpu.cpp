@@ -7,7 +7,9 @@
 // parsing, writing the surviving records); every per-record computation and the clustering run on the GPU.
 //
 // Differences from the reference, all deliberate: output is in input order, --algo cc
-// works, --mode fastq works (the reference's is an empty TODO, main.rs:49-51), --paired and --tag are refused.
+// works, --mode fastq works (the reference's is an empty TODO, main.rs:49-51), --tag is implemented from its help
+// text (src/cli.rs:64-76; the reference collects ClusterTrackers and then writes nothing, deduplicate_sam.rs:236-239),
+// --paired is refused.
 #include <zlib.h>
 
 #include <algorithm>
@@ -166,11 +168,12 @@ static void report(const umigpu_counters &c, uint64_t unmapped) {      // dedupl
     fprintf(stderr, "Number of UMIs: %llu\n", (unsigned long long)c.total_umis);
     fprintf(stderr, "Average number of UMIs per alignment position: %g\n", c.n_buckets ? (double)c.total_umis / (double)c.n_buckets : 0.0);
     fprintf(stderr, "Max number of UMIs over all alignment positions: %llu\n", (unsigned long long)c.max_umis);
-    fprintf(stderr, "Number of reads after deduplicating: %llu\n", (unsigned long long)c.n_kept);
+    fprintf(stderr, "Number of reads after deduplicating: %llu\n", (unsigned long long)c.n_kept);   // with --tag: "Number of groups of reads" (:261-263)
 }
 
 static umigpu_ctx *make_ctx(const Cli &a, unsigned umi_len) {
     umigpu_config cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.flags = a.track_clusters ? UMIGPU_FLAG_LABELS : 0;
     cfg.k = a.k; cfg.percentage = a.percentage; cfg.algo = algo_code(a); cfg.merge = merge_code(a); cfg.umi_len = umi_len; cfg.device = a.device;
     umigpu_ctx *ctx = nullptr;
     check(umigpu_create(&cfg, &ctx), nullptr, "umigpu_create");
@@ -220,14 +223,51 @@ static int run_bam(const Cli &a) {
         umigpu_result res;
         check(umigpu_finish(ctx, &res), ctx, "umigpu_finish");
         ctr = res.counters;
-        // merge kept indices with (optionally) the unmapped records, input order
-        uint64_t kpos = 0;
-        for (uint64_t i = 0; i < n; i++) {
-            const uint8_t *r = buf.data() + first + offs[i];
-            bool keep = kpos < res.n_kept && res.kept_read_index[kpos] == i;
-            if (keep) kpos++;
-            else if (a.keep_unmapped && ((r[18] | (r[19] << 8)) & 4)) keep = true;          // deduplicate_sam.rs:104-106
-            if (keep) { optr.push_back(r); olen.push_back(offs[i + 1] - offs[i]); }
+        std::vector<std::vector<uint8_t>> tagged;         // --tag: rewritten records (own storage)
+        if (!a.track_clusters) {
+            // merge kept indices with (optionally) the unmapped records, input order
+            uint64_t kpos = 0;
+            for (uint64_t i = 0; i < n; i++) {
+                const uint8_t *r = buf.data() + first + offs[i];
+                bool keep = kpos < res.n_kept && res.kept_read_index[kpos] == i;
+                if (keep) kpos++;
+                else if (a.keep_unmapped && ((r[18] | (r[19] << 8)) & 4)) keep = true;          // deduplicate_sam.rs:104-106
+                if (keep) { optr.push_back(r); olen.push_back(offs[i + 1] - offs[i]); }
+            }
+        } else {
+            // --tag (src/cli.rs:64-76): nothing is removed; every read but the consensus read of its cluster gets the
+            // duplicate flag, MI = cluster id, RX = UMI of the consensus read, cs = cluster size (consensus read only),
+            // su = reads with exactly this UMI (best read of the UMI only)
+            std::vector<uint64_t> rec_of(res.n_reads);                 // pushed read j -> record number
+            { uint64_t j = 0; for (uint64_t i = 0; i < n; i++) { const uint8_t *r = buf.data() + first + offs[i]; if (!((r[18] | (r[19] << 8)) & 4)) rec_of[j++] = i; } }
+            std::vector<uint32_t> csize(n, 0), same(n, 0), cid(n, 0);
+            for (uint64_t j = 0; j < res.n_reads; j++) { csize[res.read_cluster_root[j]]++; same[res.read_umi_rep[j]]++; }
+            { uint32_t next = 0; for (uint64_t i = 0; i < n; i++) if (csize[i]) cid[i] = next++; }
+            tagged.resize(n);
+            uint64_t j = 0;
+            for (uint64_t i = 0; i < n; i++) {
+                const uint8_t *r = buf.data() + first + offs[i];
+                const size_t len = offs[i + 1] - offs[i];
+                if ((r[18] | (r[19] << 8)) & 4) { if (a.keep_unmapped) { optr.push_back(r); olen.push_back(len); } continue; }
+                const uint64_t root = res.read_cluster_root[j], urep = res.read_umi_rep[j];
+                j++;
+                std::vector<uint8_t> &t = tagged[i];
+                t.assign(r, r + len);
+                if (root != i) { unsigned fl = (t[18] | (t[19] << 8)) | 0x400; t[18] = fl & 0xff; t[19] = (fl >> 8) & 0xff; }
+                auto tag_i = [&](char x, char y, uint32_t v) { t.push_back(x); t.push_back(y); t.push_back('I'); for (int b = 0; b < 4; b++) t.push_back((v >> (8 * b)) & 0xff); };
+                tag_i('M', 'I', cid[root]);
+                { // RX:Z = UMI of the consensus read
+                    const uint8_t *rr = buf.data() + first + offs[root]; const uint8_t *nm = rr + 36; unsigned nl = rr[12] ? rr[12] - 1 : 0, p = 0;
+                    while (p < nl && nm[p] != a.umi_separator) p++;
+                    t.push_back('R'); t.push_back('X'); t.push_back('Z');
+                    for (unsigned q = 0; q < umi_len && p + 1 + q < nl; q++) t.push_back(nm[p + 1 + q]);
+                    t.push_back(0);
+                }
+                if (root == i) tag_i('c', 's', csize[i]);
+                if (urep == i) tag_i('s', 'u', same[i]);
+                uint32_t bs = (uint32_t)(t.size() - 4); memcpy(t.data(), &bs, 4);
+                optr.push_back(t.data()); olen.push_back(t.size());
+            }
         }
         bgzf_write(a.output, optr, olen, a.num_threads);
         umigpu_destroy(ctx);
@@ -305,7 +345,7 @@ int main(int argc, char **argv) {
     Cli a = parse(argc, argv);
     auto t0 = std::chrono::steady_clock::now();
     if (a.paired) die("--paired is outside the scope of the GPU path (SURVEY.md §2); use the reference's CPU path");
-    if (a.track_clusters) die("--tag: the reference collects cluster trackers and writes nothing (deduplicate_sam.rs:236-239); not offered here");
+    if (a.track_clusters && a.mode == "fastq") die("--tag is implemented for --mode bam only");
     int rc;
     if (a.mode == "fastq") rc = run_fastq(a);
     else if (a.mode == "bam" || a.mode == "sam") rc = run_bam(a);

@@ -45,6 +45,7 @@ pub struct umigpu_result {
     pub n_reads: u64,
     pub read_cluster_root: *const u64,
     pub counters: umigpu_counters,
+    pub read_umi_rep: *const u64,
 }
 
 extern "C" {

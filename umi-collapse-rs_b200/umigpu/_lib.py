@@ -44,7 +44,7 @@ class Counters(C.Structure):
 
 class Result(C.Structure):
     _fields_ = [("n_kept", C.c_uint64), ("kept_read_index", C.POINTER(C.c_uint64)), ("n_reads", C.c_uint64),
-                ("read_cluster_root", C.POINTER(C.c_uint64)), ("counters", Counters)]
+                ("read_cluster_root", C.POINTER(C.c_uint64)), ("counters", Counters), ("read_umi_rep", C.POINTER(C.c_uint64))]
 
 
 class UmiGpuError(RuntimeError):

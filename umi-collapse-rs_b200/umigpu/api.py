@@ -135,6 +135,9 @@ class Context:
         roots = None
         if res.read_cluster_root:
             roots = np.ctypeslib.as_array(res.read_cluster_root, shape=(res.n_reads,))
+        self.last_umi_rep = None
+        if res.read_umi_rep:
+            self.last_umi_rep = np.ctypeslib.as_array(res.read_umi_rep, shape=(res.n_reads,)).copy()
         if copy:
             kept = kept.copy()
             roots = None if roots is None else roots.copy()
