@@ -228,3 +228,34 @@ def test_cpp_cli_tag_mode(tmp_path):
         assert ("cs" in tags) == is_root and (not is_root or tags["cs"] == csize[j])
         assert ("su" in tags) == (j in urep) and (j not in urep or tags["su"] == same[j])
     assert len(set(mi_of_root.values())) == len(mi_of_root) == len(kept)      # one id per cluster
+
+
+@pytest.mark.parametrize("batch_blocks", ["1", "3", "1024"])
+def test_cpp_cli_two_pass_streaming_equals_in_memory(tmp_path, batch_blocks):
+    """--two-pass (src/cli.rs:45-48): the input is streamed twice with bounded host memory; the output must carry
+    exactly the records of the in-memory mode.  Small batches force records to straddle batch boundaries."""
+    import os
+    rng = random.Random(44)
+    header, recs, truth = make_bam(rng, 6000, umi_len=8)
+    inp = str(tmp_path / "in.bam")
+    # small BGZF blocks so that many blocks / batches exist
+    bamio.bgzf_write_all(inp, header + b"".join(recs), block=2000)
+    outs = []
+    for extra in ([], ["--two-pass"]):
+        out = str(tmp_path / f"out{len(extra)}.bam")
+        env_backup = os.environ.get("UMICOLLAPSE_BATCH_BLOCKS")
+        os.environ["UMICOLLAPSE_BATCH_BLOCKS"] = batch_blocks
+        try:
+            r = _cli("--mode", "bam", "-i", inp, "-o", out, "--algo", "dir", "--merge", "avgqual", "--keep-unmapped", "--num-threads", "3", *extra)
+        finally:
+            if env_backup is None:
+                os.environ.pop("UMICOLLAPSE_BATCH_BLOCKS", None)
+            else:
+                os.environ["UMICOLLAPSE_BATCH_BLOCKS"] = env_backup
+        assert r.returncode == 0, r.stderr
+        outs.append((bamio.bgzf_read_all(out), r.stderr))
+    assert outs[0][0] == outs[1][0]
+    for line in ("Number of input reads", "Number of removed unmapped reads", "Number of reads after deduplicating"):
+        a = [l for l in outs[0][1].splitlines() if line in l]
+        b = [l for l in outs[1][1].splitlines() if line in l]
+        assert a == b and a

@@ -404,3 +404,30 @@ def test_labels_expose_cluster_root_and_umi_representative():
         best = min(m for m in members if d["score"][m] == max(d["score"][x] for x in members))
         assert all(int(urep[m]) == best for m in members)
     assert set(roots.tolist()) == set(kept.tolist())
+
+
+def test_error_convention_and_call_order():
+    """Every misuse returns a negative code with a message (never aborts): the Rust shim turns these into panics."""
+    import ctypes as C
+    from umigpu import _lib as L
+    lib = umigpu.load()
+    ctx = umigpu.Context(6)
+    one = (np.zeros(3, np.int32), np.zeros(3, np.int64), np.zeros(3, np.uint8), arr(["ACGTAC", "ACGTAA", "TTTTTT"]), np.array([1, 2, 3], np.int32))
+    res = L.Result()
+    assert lib.umigpu_fetch(ctx._h, C.byref(res)) == L.ERR_STATE and b"fetch before run" in lib.umigpu_last_error(ctx._h)
+    ctx.push_reads(*one)
+    with pytest.raises(umigpu.UmiGpuError, match="score/weight"):
+        ctx.push_reads(one[0], one[1], one[2], one[3], None, None, 10)               # score given for one chunk only
+    with pytest.raises(umigpu.UmiGpuError, match="ascending"):
+        ctx.push_reads(*one, None, 1)                                                # overlapping read-index range
+    kept, _, _ = ctx.finish()
+    assert kept.tolist() == [1, 2]          # ACGTAA / ACGTAC are one cluster of two freq-1 UMIs, root = canonical first (ACGTAA, read 1)
+    with pytest.raises(umigpu.UmiGpuError, match="reset"):
+        ctx.push_reads(*one, None, 100)                                              # push after run
+    assert lib.umigpu_run(ctx._h) == L.ERR_STATE
+    ctx.reset()
+    ctx.push_reads(*one)
+    assert ctx.finish()[0].tolist() == [1, 2]
+    assert lib.umigpu_push_reads(ctx._h, 3, None, None, None, None, None, None, 0) == L.ERR_ARG
+    assert lib.umigpu_stage_ms(ctx._h, 99, C.byref(C.c_float())) == L.ERR_ARG
+    ctx.close()

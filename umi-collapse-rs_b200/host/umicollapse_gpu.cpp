@@ -147,6 +147,87 @@ static void bgzf_write(const std::string &path, const std::vector<const uint8_t 
     fclose(f);
 }
 
+// ---- incremental BGZF reader / writer for --two-pass (bounded host memory) ----
+struct BgzfStream {
+    FILE *f; unsigned threads; bool eof = false;
+    explicit BgzfStream(const std::string &p, unsigned t) : f(fopen(p.c_str(), "rb")), threads(t) { if (!f) die("Invalid input path: " + p); }
+    ~BgzfStream() { if (f) fclose(f); }
+    // appends the inflated bytes of up to max_blocks BGZF blocks to out; returns false at end of file
+    bool next(std::vector<uint8_t> &out, size_t max_blocks = 1024) {
+        if (eof) return false;
+        std::vector<std::vector<uint8_t>> raw;
+        std::vector<size_t> usize;
+        while (raw.size() < max_blocks) {
+            uint8_t h[18];
+            size_t got = fread(h, 1, 18, f);
+            if (got == 0) { eof = true; break; }
+            if (got != 18 || h[0] != 0x1f || h[1] != 0x8b) die("not a BGZF stream");
+            unsigned xlen = h[10] | (h[11] << 8);
+            std::vector<uint8_t> blk(h, h + 18);
+            // the BC subfield is first in every BGZF block written by htslib / this program
+            if (!(h[12] == 'B' && h[13] == 'C')) die("unsupported BGZF extra field layout");
+            size_t bsize = (size_t)(h[16] | (h[17] << 8)) + 1;
+            blk.resize(bsize);
+            if (fread(blk.data() + 18, 1, bsize - 18, f) != bsize - 18) die("truncated BGZF block");
+            (void)xlen;
+            usize.push_back(blk[bsize - 4] | (blk[bsize - 3] << 8) | (blk[bsize - 2] << 16) | ((size_t)blk[bsize - 1] << 24));
+            raw.push_back(std::move(blk));
+        }
+        if (raw.empty()) return false;
+        std::vector<size_t> uoff(raw.size());
+        size_t base = out.size(), tot = 0;
+        for (size_t i = 0; i < raw.size(); i++) { uoff[i] = tot; tot += usize[i]; }
+        out.resize(base + tot);
+        parallel_for(raw.size(), threads, [&](size_t i) {
+            if (!usize[i]) return;
+            const std::vector<uint8_t> &b = raw[i];
+            unsigned xlen = b[10] | (b[11] << 8);
+            z_stream z; memset(&z, 0, sizeof z);
+            if (inflateInit2(&z, -15) != Z_OK) die("inflateInit2");
+            z.next_in = const_cast<Bytef *>(b.data() + 12 + xlen); z.avail_in = (uInt)(b.size() - 12 - xlen - 8);
+            z.next_out = out.data() + base + uoff[i]; z.avail_out = (uInt)usize[i];
+            if (inflate(&z, Z_FINISH) != Z_STREAM_END) die("inflate failed");
+            inflateEnd(&z);
+        });
+        return true;
+    }
+};
+struct BgzfOut {
+    std::string path; unsigned threads; FILE *f; std::vector<uint8_t> pend;
+    BgzfOut(const std::string &p, unsigned t) : path(p), threads(t), f(fopen(p.c_str(), "wb")) { if (!f) die("cannot open output " + p); }
+    void add(const uint8_t *p, size_t n) { pend.insert(pend.end(), p, p + n); if (pend.size() >= (64u << 20)) flush(false); }
+    void flush(bool all) {
+        const size_t B = 0xff00;
+        size_t nb = all ? (pend.size() + B - 1) / B : pend.size() / B;
+        if (!nb) return;
+        std::vector<std::vector<uint8_t>> comp(nb);
+        parallel_for(nb, threads, [&](size_t i) {
+            size_t s = i * B, n = std::min(B, pend.size() - s);
+            std::vector<uint8_t> &c = comp[i];
+            c.resize(compressBound((uLong)n) + 32);
+            z_stream z; memset(&z, 0, sizeof z);
+            if (deflateInit2(&z, 1, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) die("deflateInit2");
+            z.next_in = pend.data() + s; z.avail_in = (uInt)n; z.next_out = c.data() + 18; z.avail_out = (uInt)(c.size() - 26);
+            if (deflate(&z, Z_FINISH) != Z_STREAM_END) die("deflate failed");
+            size_t cs = z.total_out; deflateEnd(&z);
+            const uint8_t h[12] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0};
+            memcpy(c.data(), h, 12); c[12] = 'B'; c[13] = 'C'; c[14] = 2; c[15] = 0;
+            size_t bsize = cs + 26 - 1; c[16] = bsize & 0xff; c[17] = (bsize >> 8) & 0xff;
+            uint32_t crc = (uint32_t)crc32(crc32(0, nullptr, 0), pend.data() + s, (uInt)n), isz = (uint32_t)n;
+            memcpy(c.data() + 18 + cs, &crc, 4); memcpy(c.data() + 22 + cs, &isz, 4);
+            c.resize(cs + 26);
+        });
+        for (auto &c : comp) fwrite(c.data(), 1, c.size(), f);
+        size_t used = std::min(pend.size(), nb * B);
+        pend.erase(pend.begin(), pend.begin() + used);
+    }
+    void close() {
+        flush(true);
+        static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        fwrite(eof, 1, 28, f); fclose(f); f = nullptr;
+    }
+};
+
 static int algo_code(const Cli &a) {                       // main.rs:52-92 (+ cc, which the reference only documents)
     if (a.algo_str == "dir") return UMIGPU_ALGO_DIR;
     if (a.algo_str == "adj") return UMIGPU_ALGO_ADJ;
@@ -279,6 +360,94 @@ static int run_bam(const Cli &a) {
     return 0;
 }
 
+// ---- --mode bam --two-pass (src/cli.rs:45-48: "should use much less memory"): the input is streamed twice, the
+// host never holds more than one batch of inflated blocks; pass 1 feeds the device, pass 2 writes the survivors ----
+static int run_bam_two_pass(const Cli &a) {
+    umigpu_ctx *ctx = nullptr;
+    unsigned umi_len = a.umi_length;
+    uint64_t n_total = 0, unmapped = 0;
+    std::vector<uint8_t> header;
+    for (int pass = 0; pass < 2; pass++) {
+        BgzfStream in(a.input, a.num_threads);
+        std::vector<uint8_t> buf;
+        std::vector<uint64_t> offs;
+        bool have_header = false;
+        uint64_t index = 0, kpos = 0;
+        umigpu_result res; memset(&res, 0, sizeof res);
+        BgzfOut *out = nullptr;
+        if (pass == 1) {
+            if (ctx) check(umigpu_finish(ctx, &res), ctx, "umigpu_finish");
+            out = new BgzfOut(a.output, a.num_threads);
+            out->add(header.data(), header.size());
+        }
+        // UMICOLLAPSE_BATCH_BLOCKS: BGZF blocks inflated per batch (default 1024 = up to 64 MiB; tests use small values)
+        const char *bb = getenv("UMICOLLAPSE_BATCH_BLOCKS");
+        const size_t batch_blocks = bb ? (size_t)std::max(1, atoi(bb)) : 1024;
+        bool more = true;
+        while (more) {
+            more = in.next(buf, batch_blocks);
+            size_t start = 0;
+            if (!have_header) {
+                if (buf.size() < 12) { if (more) continue; die("Invalid input path: not a BAM file"); }
+                if (memcmp(buf.data(), "BAM\1", 4) != 0) die("Invalid input path: not a BAM file");
+                int32_t l_text; memcpy(&l_text, buf.data() + 4, 4);
+                size_t off = 8 + (size_t)l_text;
+                if (buf.size() < off + 4) { if (more) continue; die("truncated BAM header"); }
+                int32_t n_ref; memcpy(&n_ref, buf.data() + off, 4); off += 4;
+                bool ok = true;
+                for (int r = 0; r < n_ref; r++) { if (buf.size() < off + 4) { ok = false; break; } int32_t l; memcpy(&l, buf.data() + off, 4); off += 4 + (size_t)l + 4; }
+                if (!ok || buf.size() < off) { if (more) continue; die("truncated BAM header"); }
+                if (pass == 0) header.assign(buf.begin(), buf.begin() + off);
+                have_header = true; start = off;
+            }
+            offs.resize((buf.size() - start) / 36 + 2);
+            uint64_t n = 0, consumed = 0;
+            check(umigpu_bam_record_offsets(buf.data() + start, buf.size() - start, offs.data(), offs.size() - 1, &n, &consumed), nullptr, "umigpu_bam_record_offsets");
+            const uint8_t *recs = buf.data() + start;
+            if (pass == 0) {
+                for (uint64_t i = 0; i < n && umi_len == 0; i++) {             // -u 0: autodetect (utils/read.rs:65-75)
+                    const uint8_t *r = recs + offs[i];
+                    if ((r[18] | (r[19] << 8)) & 4) continue;
+                    unsigned l_name = r[12]; const uint8_t *name = r + 36; unsigned len = l_name ? l_name - 1 : 0, p = 0;
+                    for (;; p++) {
+                        while (p < len && name[p] != a.umi_separator) p++;
+                        if (p >= len) die("failed to get the umi");
+                        if (p + 1 < len && name[p + 1] && strchr("ACGTNacgtn", name[p + 1])) break;
+                    }
+                    for (unsigned q = p + 1; q < len && name[q] && strchr("ACGTNacgtn", name[q]); q++) umi_len++;
+                }
+                if (n && umi_len) {
+                    if (!ctx) ctx = make_ctx(a, umi_len);
+                    uint64_t nun = 0;
+                    check(umigpu_push_bam_records(ctx, n, recs, offs.data(), a.umi_separator, index, &nun), ctx, "umigpu_push_bam_records");
+                    unmapped += nun;
+                } else if (n) {
+                    unmapped += n;          // no mapped read seen yet: everything so far fails the unmapped filter
+                }
+                n_total += n;
+            } else {
+                for (uint64_t i = 0; i < n; i++) {
+                    const uint8_t *r = recs + offs[i];
+                    bool keep = kpos < res.n_kept && res.kept_read_index[kpos] == index + i;
+                    if (keep) kpos++;
+                    else if (a.keep_unmapped && ((r[18] | (r[19] << 8)) & 4)) keep = true;
+                    if (keep) out->add(r, offs[i + 1] - offs[i]);
+                }
+            }
+            index += n;
+            buf.erase(buf.begin(), buf.begin() + start + consumed);         // a trailing partial record stays for the next batch
+        }
+        if (pass == 1) {
+            out->close(); delete out;
+            umigpu_counters ctr; memset(&ctr, 0, sizeof ctr);
+            if (ctx) ctr = res.counters; else ctr.total_reads = n_total;
+            report(ctr, unmapped);
+            if (ctx) umigpu_destroy(ctx);
+        }
+    }
+    return 0;
+}
+
 // ---- --mode fastq: one global bucket (BASELINE config 4); the reference's fastq arm is an empty TODO (main.rs:49-51) ----
 static int run_fastq(const Cli &a) {
     std::vector<uint8_t> raw = read_file(a.input);
@@ -348,7 +517,7 @@ int main(int argc, char **argv) {
     if (a.track_clusters && a.mode == "fastq") die("--tag is implemented for --mode bam only");
     int rc;
     if (a.mode == "fastq") rc = run_fastq(a);
-    else if (a.mode == "bam" || a.mode == "sam") rc = run_bam(a);
+    else if (a.mode == "bam" || a.mode == "sam") rc = (a.two_pass && !a.track_clusters) ? run_bam_two_pass(a) : run_bam(a);
     else die("unknown mode " + a.mode);
     fprintf(stderr, "UMI collapsing finished in %.3f seconds\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());   // main.rs:97-102
     return rc;
