@@ -55,6 +55,11 @@ extern "C" {
 #define UMIGPU_FLAG_NO_CULL       2u  /* evaluate every tile pair (disable exact prefix culling)        */
 #define UMIGPU_FLAG_KERNEL_DIRECT 4u  /* use the direct XOR+popcount tile kernel instead of bit-sliced  */
 #define UMIGPU_FLAG_NO_MULTI_INDEX 16u /* big buckets in one pass (disable the pigeonhole multi-index passes) */
+#define UMIGPU_FLAG_PAIRED         32u /* --paired (src/cli.rs:49-54): umigpu_push_bam_records applies the paired-end
+                                          filters of deduplicate_sam.rs:96-129 and the template length joins the
+                                          bucket key (PairedAlignment, deduplicate_sam.rs:545-565)                */
+#define UMIGPU_FLAG_REMOVE_UNPAIRED 64u /* --remove-unpaired (src/cli.rs:55-57), BAM feed with FLAG_PAIRED only    */
+#define UMIGPU_FLAG_REMOVE_CHIMERIC 128u /* --remove-chimeric (src/cli.rs:58-60), BAM feed with FLAG_PAIRED only   */
 #define UMIGPU_FLAG_KERNEL_TILES  8u  /* use the shared-memory tile form of the bit-sliced kernel instead of
                                          the block-pair list form                                        */
 
@@ -90,7 +95,12 @@ typedef struct umigpu_counters {
     uint64_t n_sweeps;          /* label-propagation sweeps                                          */
     uint64_t n_block_pairs;     /* (128 x 128) block pairs evaluated by the block-pair kernel          */
     uint64_t n_unmapped;        /* records dropped by the unmapped filter (deduplicate_sam.rs:102-108;
-                                   BAM feed only)                                                    */
+                                   BAM feed only; in paired mode also reads whose mate is unmapped,
+                                   :118-121)                                                         */
+    uint64_t n_unpaired;        /* paired BAM feed: reads without the paired flag, :111-116          */
+    uint64_t n_chimeric;        /* paired BAM feed: tid != mtid, :123-128                            */
+    uint64_t n_mates_skipped;   /* paired BAM feed: last-in-template records skipped before they are
+                                   counted as input reads, :96-98                                    */
 } umigpu_counters;
 
 typedef struct umigpu_result {
@@ -153,6 +163,15 @@ int umigpu_push_reads(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, const int
 int umigpu_push_reads_device(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, const int64_t *unclipped_pos,
                              const uint8_t *is_reverse, const uint8_t *umi_ascii, const int32_t *score,
                              const int32_t *weight, uint64_t first_read_index);
+/*
+ * Paired-end form of umigpu_push_reads: `tlen` (record.insert_size(), deduplicate_sam.rs:138) is the fourth
+ * field of the bucket key — Align::Paired(PairedAlignment{strand, coord, ref, tlen}), deduplicate_sam.rs:133-139
+ * and :545-565.  The caller has already applied the paired-end filters of :96-129 (the BAM feed below applies
+ * them itself under UMIGPU_FLAG_PAIRED).  Paired and unpaired pushes cannot be mixed in one batch.
+ */
+int umigpu_push_reads_paired(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, const int64_t *unclipped_pos,
+                             const uint8_t *is_reverse, const int64_t *tlen, const uint8_t *umi_ascii,
+                             const int32_t *score, const int32_t *weight, uint64_t first_read_index);
 
 /*
  * Host feed on the device: `records` holds raw BAM alignment records exactly as they
@@ -162,7 +181,14 @@ int umigpu_push_reads_device(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, co
  * (utils/mod.rs:96-104), UcSAMRead::get_umi after the first `umi_sep` (utils/read.rs:96-111), the score of the
  * configured merge (avg_qual read.rs:56-63 / MAPQ :77-79) and the unmapped filter (deduplicate_sam.rs:102-108);
  * survivors are appended like umigpu_push_reads.  Kept indices are first_read_index + record number within this
- * call.  Single-end only (the reference's --paired path is out of scope).  Host pointers.
+ * call.  Host pointers.
+ * With UMIGPU_FLAG_PAIRED in the context's flags the device also applies, in the reference's order
+ * (deduplicate_sam.rs:96-129): paired last-in-template records are skipped without being counted as input
+ * reads; after the unmapped filter, unpaired reads are counted (and dropped under FLAG_REMOVE_UNPAIRED), reads
+ * whose mate is unmapped count as unmapped and are dropped, chimeric reads (tid != mtid) are counted (and dropped
+ * under FLAG_REMOVE_CHIMERIC); the survivors' insert size joins the bucket key.  *n_unmapped then receives this
+ * call's reference `unmapped` increment (:104 + :119).  The mates of the kept reads are selected by the caller
+ * (UcWriter::write_reversed, deduplicate_sam.rs:409-462 — see host/umicollapse_gpu.cpp).
  */
 int umigpu_push_bam_records(umigpu_ctx *ctx, uint64_t n, const uint8_t *records, const uint64_t *offsets,
                             uint8_t umi_sep, uint64_t first_read_index, uint64_t *n_unmapped);

@@ -160,11 +160,14 @@ def cluster_bucket(umis: list[bytes], freq: list[int], algo: int, k: int, p: flo
     return keep, label, data.dist_calls
 
 
-def dedup(tid, pos, rev, umis: list[bytes], score, algo: int, merge: int, k: int, p: float):
-    """deduplicate_sam.rs:93-233 on SoA input.  Returns (kept read indices ascending, counters dict)."""
+def dedup(tid, pos, rev, umis: list[bytes], score, algo: int, merge: int, k: int, p: float, tlen=None):
+    """deduplicate_sam.rs:93-233 on SoA input.  Returns (kept read indices ascending, counters dict).
+    tlen given = --paired: the bucket key is PairedAlignment (deduplicate_sam.rs:133-139, :545-565)."""
     align: dict = {}
     for i in range(len(umis)):                                                # HOT LOOP A, :93
         key = (bool(rev[i]), int(pos[i]), int(tid[i]))                        # Alignment :485-489
+        if tlen is not None:
+            key = key + (int(tlen[i]),)                                       # PairedAlignment :547-552
         umi_reads = align.setdefault(key, {})                                 # :148-150
         ukey = to_bitset(umis[i]).key()                                       # :158
         if ukey not in umi_reads:                                             # Vacant :161-163
@@ -210,3 +213,28 @@ def unclipped_pos(pos: int, is_reverse: bool, cigar: list[tuple[int, int]]) -> i
     if i >= 0 and cigar[i][0] == 4:
         soft = cigar[i][1]
     return end - 1 + soft + hard
+
+
+def paired_filter(flag: int, tid: int, mtid: int, remove_unpaired: bool, remove_chimeric: bool):
+    """deduplicate_sam.rs:96-129 with args.paired set, statement by statement.  Returns (passes, counted) where
+    counted is a dict of the reference counters this record increments (total_read_count, unmapped, unpaired, chimeric)."""
+    c = dict(total=0, unmapped=0, unpaired=0, chimeric=0)
+    is_paired, is_last, is_unmapped, mate_unmapped = bool(flag & 0x1), bool(flag & 0x80), bool(flag & 0x4), bool(flag & 0x8)
+    if is_paired and is_last:                                   # :96-98
+        return False, c
+    c["total"] += 1                                             # :100
+    if is_unmapped:                                             # :102-108
+        c["unmapped"] += 1
+        return False, c
+    if not is_paired:                                           # :111-116
+        c["unpaired"] += 1
+        if remove_unpaired:
+            return False, c
+    if is_paired and mate_unmapped:                             # :118-121
+        c["unmapped"] += 1
+        return False, c
+    if is_paired and tid != mtid:                               # :123-128
+        c["chimeric"] += 1
+        if remove_chimeric:
+            return False, c
+    return True, c

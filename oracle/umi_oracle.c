@@ -309,7 +309,7 @@ typedef struct {
     uint64_t unordered_pairs;  /* sum_b N_b (N_b - 1) / 2 (the pair-comparison metric's numerator) */
 } oracle_counters;
 
-typedef struct { int32_t tid; int64_t pos; uint8_t rev; } bkey_t;
+typedef struct { int32_t tid; int64_t pos; uint8_t rev; int64_t tlen; } bkey_t;
 
 static uint64_t mix64(uint64_t x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x;
@@ -338,7 +338,9 @@ static int merge_keep_existing(int merge, int32_t a_score, int32_t b_score) {
  * are truncated to that many canonical-first UMIs before clustering when > 0 (only used by the
  * bounded cpu_baseline timing; 0 = never truncate).
  */
-int oracle_dedup(int64_t n, const int32_t *tid, const int64_t *pos, const uint8_t *rev,
+/* tlen == NULL: Align::Unpaired(Alignment), deduplicate_sam.rs:141-145; otherwise Align::Paired(PairedAlignment)
+ * whose Eq/Hash add the template length, deduplicate_sam.rs:133-139 and :545-600. */
+int oracle_dedup_paired(int64_t n, const int32_t *tid, const int64_t *pos, const uint8_t *rev, const int64_t *tlen,
                  const uint8_t *umi_ascii, int umi_len, const int32_t *score,
                  int algo, int merge, int k, float percentage,
                  int64_t *kept_out, int64_t *per_read_root, oracle_counters *ctr,
@@ -366,12 +368,13 @@ int oracle_dedup(int64_t n, const int32_t *tid, const int64_t *pos, const uint8_
 
     for (int64_t i = 0; i < n; i++) {                               /* HOT LOOP A, deduplicate_sam.rs:93 */
         /* align.entry(alignment).or_insert_with(...)  :148-150 */
-        uint64_t h = hash_bkey(tid[i], pos[i], rev[i]) & (bcap - 1);
+        const int64_t tl = tlen ? tlen[i] : 0;
+        uint64_t h = (hash_bkey(tid[i], pos[i], rev[i]) ^ ((uint64_t)tl * 0x9E3779B97F4A7C15ull >> 17)) & (bcap - 1);
         int64_t b;
         for (;;) {
             b = btab[h];
-            if (b < 0) { b = nb++; btab[h] = b; bkeys[b].tid = tid[i]; bkeys[b].pos = pos[i]; bkeys[b].rev = rev[i]; break; }
-            if (bkeys[b].tid == tid[i] && bkeys[b].pos == pos[i] && bkeys[b].rev == rev[i]) break;
+            if (b < 0) { b = nb++; btab[h] = b; bkeys[b].tid = tid[i]; bkeys[b].pos = pos[i]; bkeys[b].rev = rev[i]; bkeys[b].tlen = tl; break; }
+            if (bkeys[b].tid == tid[i] && bkeys[b].pos == pos[i] && bkeys[b].rev == rev[i] && bkeys[b].tlen == tl) break;
             h = (h + 1) & (bcap - 1);
         }
         /* get_umi + to_bitset :158 */
@@ -492,8 +495,15 @@ int64_t oracle_unclipped_pos(int64_t pos, int is_reverse, const uint32_t *cigar,
  * (utils/read.rs:96-111: first separator byte of the read name, then umi_len bytes) and the score
  * (avg_qual read.rs:56-63 or MAPQ :77-79).  Returns 0, or -10 no separator ("failed to get the umi"),
  * -11 name too short (slice panic in the reference), -12 malformed record. */
-int oracle_bam_decode(const uint8_t *r, uint64_t rec_len, int umi_len, uint8_t sep, int use_mapq,
-                      int32_t *tid, int64_t *pos, uint8_t *rev, uint8_t *umi_out, int32_t *score, uint8_t *valid) {
+/* paired != 0 adds the filters of deduplicate_sam.rs:96-129; *cls receives ORACLE_CLS_* bits, *tlen record.insert_size() */
+#define ORACLE_CLS_MATE     1   /* :96-98  skipped before total_read_count */
+#define ORACLE_CLS_UNMAPPED 2   /* :102-108 and :118-121                    */
+#define ORACLE_CLS_UNPAIRED 4   /* :111-116                                 */
+#define ORACLE_CLS_CHIMERIC 8   /* :123-128                                 */
+int oracle_bam_decode_paired(const uint8_t *r, uint64_t rec_len, int umi_len, uint8_t sep, int use_mapq,
+                      int paired, int remove_unpaired, int remove_chimeric,
+                      int32_t *tid, int64_t *pos, uint8_t *rev, uint8_t *umi_out, int32_t *score, uint8_t *valid,
+                      int64_t *tlen, int32_t *cls) {
     if (rec_len < 36) return -12;
     uint32_t block_size; memcpy(&block_size, r, 4);
     if ((uint64_t)block_size + 4 > rec_len) return -12;
@@ -504,8 +514,17 @@ int oracle_bam_decode(const uint8_t *r, uint64_t rec_len, int umi_len, uint8_t s
     const uint8_t *qname = r + 36, *cigar = qname + l_read_name;
     const uint8_t *qual = cigar + 4 * (uint64_t)n_cigar + (l_seq + 1) / 2;
     if ((uint64_t)(qual - r) + l_seq > rec_len) return -12;
-    *valid = (flag & 0x4) ? 0 : 1;
-    if (!*valid) return ORACLE_OK;
+    *cls = 0; *valid = 0;
+    if (paired && (flag & 0x1) && (flag & 0x80)) { *cls = ORACLE_CLS_MATE; return ORACLE_OK; }     /* :96-98 */
+    if (flag & 0x4) { *cls = ORACLE_CLS_UNMAPPED; return ORACLE_OK; }                              /* :102-108 */
+    if (paired) {
+        int32_t mtid; memcpy(&mtid, r + 24, 4);
+        if (!(flag & 0x1)) { *cls |= ORACLE_CLS_UNPAIRED; if (remove_unpaired) return ORACLE_OK; }           /* :111-116 */
+        if ((flag & 0x1) && (flag & 0x8)) { *cls |= ORACLE_CLS_UNMAPPED; return ORACLE_OK; }                /* :118-121 */
+        if ((flag & 0x1) && ref_id != mtid) { *cls |= ORACLE_CLS_CHIMERIC; if (remove_chimeric) return ORACLE_OK; } /* :123-128 */
+        int32_t isz; memcpy(&isz, r + 32, 4); *tlen = isz;
+    }
+    *valid = 1;
     uint32_t *cig = (uint32_t *)malloc(4 * (size_t)(n_cigar ? n_cigar : 1));
     memcpy(cig, cigar, 4 * (size_t)n_cigar);
     *rev = (flag & 0x10) ? 1 : 0;
@@ -519,4 +538,19 @@ int oracle_bam_decode(const uint8_t *r, uint64_t rec_len, int umi_len, uint8_t s
     memcpy(umi_out, qname + q + 1, umi_len);
     *score = use_mapq ? (int32_t)mapq : oracle_avg_qual(qual, l_seq);
     return ORACLE_OK;
+}
+
+int oracle_bam_decode(const uint8_t *r, uint64_t rec_len, int umi_len, uint8_t sep, int use_mapq,
+                      int32_t *tid, int64_t *pos, uint8_t *rev, uint8_t *umi_out, int32_t *score, uint8_t *valid) {
+    int64_t tlen; int32_t cls;
+    return oracle_bam_decode_paired(r, rec_len, umi_len, sep, use_mapq, 0, 0, 0, tid, pos, rev, umi_out, score, valid, &tlen, &cls);
+}
+
+int oracle_dedup(int64_t n, const int32_t *tid, const int64_t *pos, const uint8_t *rev,
+                 const uint8_t *umi_ascii, int umi_len, const int32_t *score,
+                 int algo, int merge, int k, float percentage,
+                 int64_t *kept_out, int64_t *per_read_root, oracle_counters *ctr,
+                 int64_t max_bucket_umis_to_cluster) {
+    return oracle_dedup_paired(n, tid, pos, rev, NULL, umi_ascii, umi_len, score, algo, merge, k, percentage,
+                               kept_out, per_read_root, ctr, max_bucket_umis_to_cluster);
 }

@@ -65,7 +65,7 @@ def remove_near(umis: np.ndarray, freq, query: bytes, k, max_freq):
     return out
 
 
-def dedup(tid, pos, rev, umi, score, algo, merge, k, p, want_roots=False, max_bucket=0):
+def dedup(tid, pos, rev, umi, score, algo, merge, k, p, want_roots=False, max_bucket=0, tlen=None):
     tid = np.ascontiguousarray(tid, np.int32); pos = np.ascontiguousarray(pos, np.int64)
     rev = np.ascontiguousarray(rev, np.uint8); umi = np.ascontiguousarray(umi, np.uint8)
     score = None if score is None else np.ascontiguousarray(score, np.int32)
@@ -74,8 +74,9 @@ def dedup(tid, pos, rev, umi, score, algo, merge, k, p, want_roots=False, max_bu
     kept = np.zeros(max(n, 1), np.int64)
     roots = np.zeros(max(n, 1), np.int64) if want_roots else None
     ctr = Counters()
-    rc = lib().oracle_dedup(C.c_int64(n), _p(tid), _p(pos), _p(rev), _p(umi), L, _p(score), algo, merge, k, C.c_float(p),
-                            _p(kept), _p(roots), C.byref(ctr), C.c_int64(max_bucket))
+    tlen = None if tlen is None else np.ascontiguousarray(tlen, np.int64)
+    rc = lib().oracle_dedup_paired(C.c_int64(n), _p(tid), _p(pos), _p(rev), _p(tlen), _p(umi), L, _p(score), algo, merge, k,
+                                   C.c_float(p), _p(kept), _p(roots), C.byref(ctr), C.c_int64(max_bucket))
     if rc:
         raise RuntimeError(f"oracle_dedup rc={rc}")
     return kept[: ctr.n_kept].copy(), (roots[:n].copy() if want_roots else None), ctr.as_dict()
@@ -91,14 +92,19 @@ def unclipped_pos(pos, rev, cigar):
     return lib().oracle_unclipped_pos(pos, int(rev), _p(arr), len(arr))
 
 
-def bam_decode(rec: bytes, umi_len: int, sep: int, use_mapq: bool):
-    """oracle_bam_decode on one raw record; returns dict or raises on the reference's panic conditions."""
-    tid, score = C.c_int32(), C.c_int32()
-    pos = C.c_int64()
+CLS_MATE, CLS_UNMAPPED, CLS_UNPAIRED, CLS_CHIMERIC = 1, 2, 4, 8
+
+
+def bam_decode(rec: bytes, umi_len: int, sep: int, use_mapq: bool, paired=False, remove_unpaired=False, remove_chimeric=False):
+    """oracle_bam_decode(_paired) on one raw record; returns dict or raises on the reference's panic conditions."""
+    tid, score, cls = C.c_int32(), C.c_int32(), C.c_int32()
+    pos, tlen = C.c_int64(), C.c_int64()
     rev, valid = C.c_uint8(), C.c_uint8()
     umi = C.create_string_buffer(umi_len)
-    rc = lib().oracle_bam_decode(rec, C.c_uint64(len(rec)), umi_len, C.c_uint8(sep), int(use_mapq), C.byref(tid), C.byref(pos),
-                                 C.byref(rev), umi, C.byref(score), C.byref(valid))
+    rc = lib().oracle_bam_decode_paired(rec, C.c_uint64(len(rec)), umi_len, C.c_uint8(sep), int(use_mapq), int(paired),
+                                        int(remove_unpaired), int(remove_chimeric), C.byref(tid), C.byref(pos),
+                                        C.byref(rev), umi, C.byref(score), C.byref(valid), C.byref(tlen), C.byref(cls))
     if rc:
         raise RuntimeError(f"oracle_bam_decode rc={rc}")
-    return dict(valid=valid.value, tid=tid.value, pos=pos.value, rev=rev.value, umi=umi.raw, score=score.value)
+    return dict(valid=valid.value, tid=tid.value, pos=pos.value, rev=rev.value, umi=umi.raw, score=score.value,
+                tlen=tlen.value, cls=cls.value)

@@ -73,3 +73,28 @@ def test_umi_length_autodetect_follows_the_reference_regex():
     import pytest
     with pytest.raises(ValueError):
         length(b"read_12")
+
+
+def test_oracle_paired_filters_match_literal():
+    """deduplicate_sam.rs:96-129: the C oracle's record classes against the statement-by-statement restatement."""
+    import struct
+    from bam_fixtures import make_paired_bam
+    rng = random.Random(8)
+    _, recs = make_paired_bam(rng, 1500)
+    seen = set()
+    for ru in (False, True):
+        for rc in (False, True):
+            for rec in recs:
+                tid, = struct.unpack_from("<i", rec, 4); flag, = struct.unpack_from("<H", rec, 18)
+                mtid, = struct.unpack_from("<i", rec, 24); tlen, = struct.unpack_from("<i", rec, 32)
+                ok, c = R.paired_filter(flag, tid, mtid, ru, rc)
+                d = O.bam_decode(rec, 8, ord("_"), False, True, ru, rc)
+                assert d["valid"] == int(ok)
+                assert bool(d["cls"] & O.CLS_MATE) == (c["total"] == 0)
+                assert bool(d["cls"] & O.CLS_UNMAPPED) == bool(c["unmapped"])
+                assert bool(d["cls"] & O.CLS_UNPAIRED) == bool(c["unpaired"])
+                assert bool(d["cls"] & O.CLS_CHIMERIC) == bool(c["chimeric"])
+                if ok:
+                    assert d["tlen"] == tlen
+                seen.add((d["valid"], d["cls"]))
+    assert len(seen) >= 6      # the fixture exercises every branch

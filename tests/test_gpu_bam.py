@@ -259,3 +259,130 @@ def test_cpp_cli_two_pass_streaming_equals_in_memory(tmp_path, batch_blocks):
         a = [l for l in outs[0][1].splitlines() if line in l]
         b = [l for l in outs[1][1].splitlines() if line in l]
         assert a == b and a
+
+
+# ---- paired-end mode: PairedAlignment key + the filters of deduplicate_sam.rs:96-129 ----
+def oracle_paired_from_records(recs, umi_len, sep, use_mapq, algo, merge, k, p, remove_unpaired, remove_chimeric):
+    idx, tid, pos, rev, tlen, umi, score = [], [], [], [], [], [], []
+    n = dict(mates=0, unmapped=0, unpaired=0, chimeric=0)
+    for i, r in enumerate(recs):
+        d = O.bam_decode(r, umi_len, sep, use_mapq, True, remove_unpaired, remove_chimeric)
+        n["mates"] += bool(d["cls"] & O.CLS_MATE); n["unmapped"] += bool(d["cls"] & O.CLS_UNMAPPED)
+        n["unpaired"] += bool(d["cls"] & O.CLS_UNPAIRED); n["chimeric"] += bool(d["cls"] & O.CLS_CHIMERIC)
+        if d["valid"]:
+            idx.append(i); tid.append(d["tid"]); pos.append(d["pos"]); rev.append(d["rev"]); tlen.append(d["tlen"])
+            umi.append(d["umi"]); score.append(d["score"])
+    a = np.frombuffer(b"".join(umi), np.uint8).reshape(len(umi), umi_len)
+    kept, _, ctr = O.dedup(tid, pos, rev, a, score, algo, merge, k, p, tlen=tlen)
+    return [idx[j] for j in kept.tolist()], ctr, n
+
+
+def test_push_reads_paired_matches_oracle():
+    rng = np.random.default_rng(5)
+    n, L = 20000, 8
+    tid = rng.integers(0, 3, n).astype(np.int32); pos = rng.integers(0, 40, n).astype(np.int64) * 7 - 50
+    rev = rng.integers(0, 2, n).astype(np.uint8); tlen = rng.choice(np.array([-300, -1, 0, 150, 151, 2 ** 31 - 1], np.int64), n)
+    fam = rng.integers(0, 4, (60, L))
+    umi = np.frombuffer(b"ACGT", np.uint8)[np.where(rng.random((n, L)) < 0.05, rng.integers(0, 4, (n, L)), fam[rng.integers(0, 60, n)])]
+    score = rng.integers(0, 41, n).astype(np.int32)
+    for algo in (umigpu.ALGO_DIR, umigpu.ALGO_ADJ_UPSTREAM, umigpu.ALGO_CC):
+        with umigpu.Context(L, 1, 0.5, algo, umigpu.MERGE_AVGQUAL) as ctx:
+            half = n // 2
+            ctx.push_reads(tid[:half], pos[:half], rev[:half], umi[:half], score[:half], tlen=tlen[:half])
+            ctx.push_reads(tid[half:], pos[half:], rev[half:], umi[half:], score[half:], first_read_index=half, tlen=tlen[half:])
+            kept, _, ctr = ctx.finish()
+        okept, _, octr = O.dedup(tid, pos, rev, umi, score, algo, umigpu.MERGE_AVGQUAL, 1, 0.5, tlen=tlen)
+        assert kept.astype(np.int64).tolist() == okept.tolist()
+        assert ctr["n_buckets"] == octr["n_buckets"] and ctr["total_umis"] == octr["total_umis"]
+        # and the template length really splits buckets
+        _, _, uctr = O.dedup(tid, pos, rev, umi, score, algo, umigpu.MERGE_AVGQUAL, 1, 0.5)
+        assert uctr["n_buckets"] < octr["n_buckets"]
+    with umigpu.Context(L) as ctx:          # paired and unpaired chunks cannot share a batch
+        ctx.push_reads(tid[:10], pos[:10], rev[:10], umi[:10], score[:10], tlen=tlen[:10])
+        with pytest.raises(umigpu.UmiGpuError, match="cannot be mixed"):
+            ctx.push_reads(tid[10:20], pos[10:20], rev[10:20], umi[10:20], score[10:20], first_read_index=10)
+
+
+@pytest.mark.parametrize("remove_unpaired,remove_chimeric", [(False, False), (True, False), (False, True), (True, True)])
+def test_push_bam_records_paired_filters(remove_unpaired, remove_chimeric):
+    from bam_fixtures import make_paired_bam
+    rng = random.Random(11 + remove_unpaired + 2 * remove_chimeric)
+    header, recs = make_paired_bam(rng, 4000)
+    buf = header + b"".join(recs)
+    offs, _ = bamio.record_offsets(buf, len(header))
+    fl = umigpu.FLAG_PAIRED | (umigpu.FLAG_REMOVE_UNPAIRED if remove_unpaired else 0) | (umigpu.FLAG_REMOVE_CHIMERIC if remove_chimeric else 0)
+    okept, octr, on = oracle_paired_from_records(recs, 8, ord("_"), False, O.ALGO_DIR, umigpu.MERGE_AVGQUAL, 1, 0.5, remove_unpaired, remove_chimeric)
+    assert on["mates"] and on["unmapped"] and on["unpaired"] and on["chimeric"]
+    for chunk in (0, 1111):
+        with umigpu.Context(8, 1, 0.5, umigpu.ALGO_DIR, umigpu.MERGE_AVGQUAL, flags=fl) as ctx:
+            nun = 0
+            for s in range(0, len(recs), chunk or len(recs)):
+                e = min(len(recs), s + (chunk or len(recs)))
+                nun += bamio.push_bam(ctx, buf, offs[s: e + 1], ord("_"), s)
+            kept, _, ctr = ctx.finish()
+        assert kept.astype(np.int64).tolist() == okept
+        assert nun == on["unmapped"] == ctr["n_unmapped"]
+        assert ctr["total_reads"] == len(recs) - on["mates"] and ctr["n_mates_skipped"] == on["mates"]
+        assert ctr["n_unpaired"] == on["unpaired"] and ctr["n_chimeric"] == on["chimeric"]
+        assert ctr["n_buckets"] == octr["n_buckets"] and ctr["total_umis"] == octr["total_umis"] and ctr["max_umis"] == octr["max_umis"]
+
+
+def _expected_paired_output(recs, okept):
+    """UcWriter::write + write_reversed (deduplicate_sam.rs:382-462) restated on the test side: the kept reads plus, for
+    every kept paired read, the first mapped last-in-template record with the same name at (mate ref, mate pos)."""
+    import struct
+    def f(rec):
+        flag, = struct.unpack_from("<H", rec, 18)
+        tid, pos = struct.unpack_from("<ii", rec, 4); mtid, mpos = struct.unpack_from("<ii", rec, 24)
+        return rec[36: 36 + rec[12] - 1], flag, tid, pos, mtid, mpos
+    want = set()
+    for i in okept:
+        name, flag, _, _, mtid, mpos = f(recs[i])
+        if flag & 1:
+            want.add((name, mtid, mpos))
+    keep = set(okept)
+    for i, rec in enumerate(recs):
+        name, flag, tid, pos, _, _ = f(rec)
+        if not (flag & 4) and (flag & 1) and (flag & 0x80) and not (flag & 8) and (name, tid, pos) in want:
+            want.remove((name, tid, pos))
+            keep.add(i)
+    return [recs[i] for i in sorted(keep)]
+
+
+@pytest.mark.parametrize("extra", [[], ["--remove-unpaired"], ["--remove-chimeric", "--two-pass"], ["--two-pass"]])
+def test_cpp_cli_paired(tmp_path, extra):
+    """--paired (src/cli.rs:49-60): first reads are deduplicated with the template length in the key, their mates follow."""
+    import os
+    from bam_fixtures import make_paired_bam
+    rng = random.Random(77)
+    header, recs = make_paired_bam(rng, 5000)
+    inp, out = str(tmp_path / "in.bam"), str(tmp_path / "out.bam")
+    bamio.bgzf_write_all(inp, header + b"".join(recs), block=3000)
+    os.environ["UMICOLLAPSE_BATCH_BLOCKS"] = "5"
+    try:
+        r = _cli("--mode", "bam", "-i", inp, "-o", out, "--algo", "dir", "--merge", "avgqual", "--paired", "--num-threads", "3", *extra)
+    finally:
+        os.environ.pop("UMICOLLAPSE_BATCH_BLOCKS", None)
+    assert r.returncode == 0, r.stderr
+    ru, rc = "--remove-unpaired" in extra, "--remove-chimeric" in extra
+    okept, octr, on = oracle_paired_from_records(recs, 8, ord("_"), False, O.ALGO_DIR, O.MERGE_AVGQUAL, 1, 0.5, ru, rc)
+    back = bamio.bgzf_read_all(out)
+    hdr, _, first = bamio.parse_header(back)
+    offs, _ = bamio.record_offsets(back, first)
+    got = [bytes(back[int(offs[i]): int(offs[i + 1])]) for i in range(len(offs) - 1)]
+    expect = _expected_paired_output(recs, okept)
+    assert len(expect) > len(okept)                      # mates were added
+    assert hdr == header and got == expect
+    assert f"Number of input reads: {len(recs) - on['mates']}" in r.stderr
+    assert f"Number of removed unmapped reads: {on['unmapped']}" in r.stderr
+    assert f"Number of unpaired reads: {on['unpaired']}" in r.stderr
+    assert f"Number of chimeric reads: {on['chimeric']}" in r.stderr
+    assert f"Number of unique alignment positions: {octr['n_buckets']}" in r.stderr
+    assert f"Number of reads after deduplicating: {octr['n_kept']}" in r.stderr
+    # the Python driver writes the same file
+    out2 = str(tmp_path / "out2.bam")
+    args = umigpu.Cli(input=inp, output=out2, k=1, algo_str="dir", merge_str="avgqual", data_str="naive", paired=True,
+                      remove_unpaired=ru, remove_chimeric=rc)
+    bamio.deduplicate_and_merge(args)
+    assert bamio.bgzf_read_all(out2) == back
+

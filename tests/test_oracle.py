@@ -197,3 +197,18 @@ def test_avg_qual_and_unclipped_pos():
     for cig in ([(0, 10)], [(4, 2), (0, 10), (4, 3)], [(5, 1), (0, 5), (3, 100), (0, 5), (5, 2)]):
         for rev in (0, 1):
             assert O.unclipped_pos(1000, rev, cig) == R.unclipped_pos(1000, bool(rev), cig)
+
+
+def test_paired_key_c_oracle_matches_literal():
+    """--paired: the bucket key gains the template length (PairedAlignment, deduplicate_sam.rs:545-565)."""
+    rng = random.Random(21)
+    for trial in range(20):
+        tid, pos, rev, umi, score = _random_reads(rng, 300, 5, 6)
+        tlen = [rng.choice([-200, 0, 150, 151]) for _ in tid]
+        for algo in range(4):
+            a_kept, a_ctr = R.dedup(tid, pos, rev, [u.encode() for u in umi], score, algo, O.MERGE_AVGQUAL, 1, 0.5, tlen=tlen)
+            b_kept, _, b_ctr = O.dedup(tid, pos, rev, arr(umi), score, algo, O.MERGE_AVGQUAL, 1, 0.5, tlen=tlen)
+            assert a_kept == b_kept.tolist()
+            assert a_ctr["n_buckets"] == b_ctr["n_buckets"] and a_ctr["total_umis"] == b_ctr["total_umis"]
+        u_kept, _, u_ctr = O.dedup(tid, pos, rev, arr(umi), score, 0, O.MERGE_AVGQUAL, 1, 0.5)
+        assert u_ctr["n_buckets"] < b_ctr["n_buckets"]

@@ -26,11 +26,13 @@ struct DevScalars {
     u32 n_blocks, pad0;
     u64 n_block_pairs;
     u32 n_big, m_big;
+    i64 tlen_min, tlen_max;          // paired mode: template length is part of the bucket key (deduplicate_sam.rs:545-552)
+    u64 n_unpaired, n_chimeric, n_mates_skipped, n_bam_unmapped;   // running totals over the BAM pushes of this batch
 };
 
 struct KeyLayout {
-    int umi_len, umi_bits, pos_bits, tid_bits, bucket_bits, total_bits, nw, has_n;
-    i64 pos_min;
+    int umi_len, umi_bits, pos_bits, tid_bits, tlen_bits, bucket_bits, total_bits, nw, has_n;
+    i64 pos_min, tlen_min;
     i32 tid_min;
 };
 
@@ -38,8 +40,10 @@ struct KeyLayout {
 
 __global__ void __launch_bounds__(PACK_THREADS) umi_pack_kernel(
     const u8 *__restrict__ ascii, u64 n, int L, const i32 *__restrict__ tid, const i64 *__restrict__ pos,
-    u64 *__restrict__ umi2, u32 *__restrict__ nmask, DevScalars *sc) {
+    const i64 *__restrict__ tlen, u64 *__restrict__ umi2, u32 *__restrict__ nmask, DevScalars *sc) {
     __shared__ __align__(16) u8 sbuf[PACK_THREADS * 32];
+    __shared__ i64 s_lmin[PACK_THREADS / 32], s_lmax[PACK_THREADS / 32];
+    i64 lmin = 0x7fffffffffffffffLL, lmax = (i64)0x8000000000000000LL;
     __shared__ i32 s_tmin[PACK_THREADS / 32], s_tmax[PACK_THREADS / 32];
     __shared__ i64 s_pmin[PACK_THREADS / 32], s_pmax[PACK_THREADS / 32];
     __shared__ u32 s_flags[PACK_THREADS / 32];
@@ -78,6 +82,7 @@ __global__ void __launch_bounds__(PACK_THREADS) umi_pack_kernel(
             umi2[i] = code; nmask[i] = nm; if (nm) flags |= 1u;
             const i32 t = tid[i]; const i64 p = pos[i];
             tmin = min(tmin, t); tmax = max(tmax, t); pmin = min(pmin, p); pmax = max(pmax, p);
+            if (tlen) { const i64 l = tlen[i]; lmin = min(lmin, l); lmax = max(lmax, l); }
         }
     }
 #pragma unroll
@@ -86,16 +91,20 @@ __global__ void __launch_bounds__(PACK_THREADS) umi_pack_kernel(
         tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
         pmin = min(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
         pmax = max(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+        lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
         flags |= __shfl_xor_sync(0xffffffffu, flags, o);
     }
     const u32 w = threadIdx.x >> 5;
-    if (lane_id() == 0) { s_tmin[w] = tmin; s_tmax[w] = tmax; s_pmin[w] = pmin; s_pmax[w] = pmax; s_flags[w] = flags; }
+    if (lane_id() == 0) { s_tmin[w] = tmin; s_tmax[w] = tmax; s_pmin[w] = pmin; s_pmax[w] = pmax; s_lmin[w] = lmin; s_lmax[w] = lmax; s_flags[w] = flags; }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int k = 1; k < PACK_THREADS / 32; k++) {
             tmin = min(tmin, s_tmin[k]); tmax = max(tmax, s_tmax[k]); pmin = min(pmin, s_pmin[k]); pmax = max(pmax, s_pmax[k]);
+            lmin = min(lmin, s_lmin[k]); lmax = max(lmax, s_lmax[k]);
             flags |= s_flags[k];
         }
+        if (tlen && lmin <= lmax) { atomicMin((long long *)&sc->tlen_min, (long long)lmin); atomicMax((long long *)&sc->tlen_max, (long long)lmax); }
         if (tmin <= tmax) {
             atomicMin(&sc->tid_min, tmin); atomicMax(&sc->tid_max, tmax);
             atomicMin((long long *)&sc->pos_min, (long long)pmin); atomicMax((long long *)&sc->pos_max, (long long)pmax);
@@ -121,10 +130,11 @@ __device__ __forceinline__ u64 umi_sort_code(u64 umi2, u32 nm, int L, int has_n)
 template <int NW>
 __global__ void __launch_bounds__(256) build_keys_kernel(
     u64 n, const i32 *__restrict__ tid, const i64 *__restrict__ pos, const u8 *__restrict__ rev,
-    const u64 *__restrict__ umi2, const u32 *__restrict__ nmask, KeyLayout lay, u64 *__restrict__ k0, u64 *__restrict__ k1) {
+    const i64 *__restrict__ tlen, const u64 *__restrict__ umi2, const u32 *__restrict__ nmask, KeyLayout lay, u64 *__restrict__ k0, u64 *__restrict__ k1) {
     u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     u64 bucket = ((u64)(u32)(tid[i] - lay.tid_min) << (lay.pos_bits + 1)) | ((u64)(pos[i] - lay.pos_min) << 1) | (rev[i] ? 1u : 0u);
+    if (lay.tlen_bits) bucket = (bucket << lay.tlen_bits) | (u64)(tlen[i] - lay.tlen_min);    // PairedAlignment: + tlen
     u64 code = umi_sort_code(umi2[i], nmask[i], lay.umi_len, lay.has_n);
     int ub = lay.umi_bits;
     u64 lo = (ub < 64 ? bucket << ub : 0) | code;

@@ -37,7 +37,8 @@ struct umigpu_ctx {
     u64 n_reads = 0;
     std::vector<Chunk> chunks;
     int have_score = -1, have_weight = -1;
-    DevBuf d_tid, d_pos, d_rev, d_umi2, d_nmask, d_score, d_weight, d_ascii;
+    DevBuf d_tid, d_pos, d_rev, d_umi2, d_nmask, d_score, d_weight, d_ascii, d_tlen, d_btlen;
+    int have_tlen = -1;                   // paired mode (template length in the bucket key): -1 undecided, 0/1 fixed by the first push
     DevBuf d_sc;
     DevScalars *h_sc = nullptr;   // pinned
 
@@ -146,7 +147,7 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->d_tid, &ctx->d_pos, &ctx->d_rev, &ctx->d_umi2, &ctx->d_nmask, &ctx->d_score, &ctx->d_weight, &ctx->d_ascii,
+    DevBuf *bufs[] = {&ctx->d_tid, &ctx->d_pos, &ctx->d_rev, &ctx->d_umi2, &ctx->d_nmask, &ctx->d_score, &ctx->d_weight, &ctx->d_ascii, &ctx->d_tlen, &ctx->d_btlen,
                       &ctx->d_sc, &ctx->d_key[0][0], &ctx->d_key[0][1], &ctx->d_key[1][0], &ctx->d_key[1][1], &ctx->d_idx[0], &ctx->d_idx[1],
                       &ctx->d_hist, &ctx->d_tiles, &ctx->d_useg, &ctx->d_rep, &ctx->d_planes, &ctx->d_nplane, &ctx->d_bhead, &ctx->d_wsum,
                       &ctx->d_read_uid, &ctx->d_freq, &ctx->d_thr, &ctx->d_repidx, &ctx->d_label, &ctx->d_prio, &ctx->d_bstart, &ctx->d_itemoff,
@@ -175,6 +176,7 @@ static int init_scalars(umigpu_ctx *ctx) {
     DevScalars z; memset(&z, 0, sizeof z);
     z.tid_min = 0x7fffffff; z.tid_max = (i32)0x80000000;
     z.pos_min = 0x7fffffffffffffffLL; z.pos_max = (i64)0x8000000000000000LL;
+    z.tlen_min = 0x7fffffffffffffffLL; z.tlen_max = (i64)0x8000000000000000LL;
     *ctx->h_sc = z;
     CK(cudaMemcpyAsync(ctx->d_sc.p, ctx->h_sc, sizeof z, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));   // h_sc is reused as the read-back buffer
@@ -184,7 +186,7 @@ static int init_scalars(umigpu_ctx *ctx) {
 extern "C" int umigpu_reset(umigpu_ctx *ctx) {
     if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
     CK(cudaSetDevice(ctx->cfg.device));
-    ctx->n_reads = 0; ctx->chunks.clear(); ctx->have_score = ctx->have_weight = -1;
+    ctx->n_reads = 0; ctx->chunks.clear(); ctx->have_score = ctx->have_weight = ctx->have_tlen = -1;
     ctx->ran = false; ctx->n_unique = ctx->n_buckets = 0; ctx->n_edges = 0;
     ctx->use_orig = false; ctx->n_unmapped = 0; ctx->n_records = 0;
     memset(&ctx->ctr, 0, sizeof ctx->ctr);
@@ -202,7 +204,7 @@ static int read_scalars(umigpu_ctx *ctx) {
 // push
 // ------------------------------------------------------------------------------------------------
 static int push_common(umigpu_ctx *ctx, u64 n, const i32 *tid, const i64 *pos, const u8 *rev, const u8 *ascii,
-                       const i32 *score, const i32 *weight, u64 first_index, cudaMemcpyKind kind) {
+                       const i32 *score, const i32 *weight, u64 first_index, cudaMemcpyKind kind, const i64 *tlen = nullptr) {
     if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
     CK(cudaSetDevice(ctx->cfg.device));
     if (ctx->ran) return fail(ctx, UMIGPU_ERR_STATE, "push after run: call umigpu_reset first");
@@ -212,6 +214,8 @@ static int push_common(umigpu_ctx *ctx, u64 n, const i32 *tid, const i64 *pos, c
     if (ctx->have_score < 0) { ctx->have_score = score != nullptr; ctx->have_weight = weight != nullptr; }
     if ((score != nullptr) != (ctx->have_score == 1) || (weight != nullptr) != (ctx->have_weight == 1))
         return fail(ctx, UMIGPU_ERR_ARG, "score/weight must be given for all chunks or for none");
+    if (ctx->have_tlen < 0) ctx->have_tlen = tlen != nullptr;
+    if ((tlen != nullptr) != (ctx->have_tlen == 1)) return fail(ctx, UMIGPU_ERR_ARG, "paired and unpaired pushes cannot be mixed in one batch");
     if (!ctx->chunks.empty()) {
         const Chunk &c = ctx->chunks.back();
         if (first_index < c.first_index + c.n) return fail(ctx, UMIGPU_ERR_ARG, "chunks must be pushed in ascending read-index order");
@@ -227,6 +231,7 @@ static int push_common(umigpu_ctx *ctx, u64 n, const i32 *tid, const i64 *pos, c
     CK(ctx->d_nmask.reserve_keep(tot * 4, old * 4, s));
     if (score) CK(ctx->d_score.reserve_keep(tot * 4, old * 4, s));
     if (weight) CK(ctx->d_weight.reserve_keep(tot * 4, old * 4, s));
+    if (tlen) { CK(ctx->d_tlen.reserve_keep(tot * 8, old * 8, s)); CK(cudaMemcpyAsync(ctx->d_tlen.as<i64>() + old, tlen, n * 8, kind, s)); }
     if (tid) CK(cudaMemcpyAsync(ctx->d_tid.as<i32>() + old, tid, n * 4, kind, s)); else CK(cudaMemsetAsync(ctx->d_tid.as<i32>() + old, 0, n * 4, s));
     if (pos) CK(cudaMemcpyAsync(ctx->d_pos.as<i64>() + old, pos, n * 8, kind, s)); else CK(cudaMemsetAsync(ctx->d_pos.as<i64>() + old, 0, n * 8, s));
     if (rev) CK(cudaMemcpyAsync(ctx->d_rev.as<u8>() + old, rev, n, kind, s)); else CK(cudaMemsetAsync(ctx->d_rev.as<u8>() + old, 0, n, s));
@@ -239,7 +244,8 @@ static int push_common(umigpu_ctx *ctx, u64 n, const i32 *tid, const i64 *pos, c
         d_ascii = ctx->d_ascii.as<u8>();
     }
     LAUNCH(umi_pack_kernel, (u32)std::min<u64>(grid_for(n, PACK_THREADS), (u64)ctx->num_sms * 32), PACK_THREADS, d_ascii, n, L, ctx->d_tid.as<i32>() + old,
-           ctx->d_pos.as<i64>() + old, ctx->d_umi2.as<u64>() + old, ctx->d_nmask.as<u32>() + old, ctx->d_sc.as<DevScalars>());
+           ctx->d_pos.as<i64>() + old, (const i64 *)(tlen ? ctx->d_tlen.as<i64>() + old : nullptr), ctx->d_umi2.as<u64>() + old,
+           ctx->d_nmask.as<u32>() + old, ctx->d_sc.as<DevScalars>());
     STAGE_END(UMIGPU_STAGE_PACK);
     if (ctx->use_orig) {
         CK(ctx->d_orig.reserve_keep(tot * 4, old * 4, s));
@@ -262,6 +268,13 @@ extern "C" int umigpu_push_reads_device(umigpu_ctx *ctx, uint64_t n, const int32
                                         const int32_t *weight, uint64_t first_read_index) {
     if (n && (!tid || !unclipped_pos || !is_reverse)) return fail(ctx, UMIGPU_ERR_ARG, "tid/unclipped_pos/is_reverse are null");
     return push_common(ctx, n, tid, unclipped_pos, is_reverse, umi_ascii, score, weight, first_read_index, cudaMemcpyDeviceToDevice);
+}
+
+extern "C" int umigpu_push_reads_paired(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, const int64_t *unclipped_pos,
+                                        const uint8_t *is_reverse, const int64_t *tlen, const uint8_t *umi_ascii,
+                                        const int32_t *score, const int32_t *weight, uint64_t first_read_index) {
+    if (n && (!tid || !unclipped_pos || !is_reverse || !tlen)) return fail(ctx, UMIGPU_ERR_ARG, "tid/unclipped_pos/is_reverse/tlen are null");
+    return push_common(ctx, n, tid, unclipped_pos, is_reverse, umi_ascii, score, weight, first_read_index, cudaMemcpyHostToDevice, tlen);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -308,6 +321,9 @@ extern "C" int umigpu_push_bam_records(umigpu_ctx *ctx, uint64_t n, const uint8_
     if (n > 0xfffffffeull || ctx->n_reads + n > 0xfffffffeull) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "more than 2^32-2 reads in one batch");
     if (ctx->have_score < 0) { ctx->have_score = 1; ctx->have_weight = 0; }
     if (ctx->have_score != 1 || ctx->have_weight == 1) return fail(ctx, UMIGPU_ERR_ARG, "BAM pushes cannot be mixed with score-less or weighted pushes");
+    const bool paired = (ctx->cfg.flags & UMIGPU_FLAG_PAIRED) != 0;
+    if (ctx->have_tlen < 0) ctx->have_tlen = paired;
+    if (paired != (ctx->have_tlen == 1)) return fail(ctx, UMIGPU_ERR_ARG, "paired and unpaired pushes cannot be mixed in one batch");
     if (!ctx->chunks.empty()) {
         const Chunk &c = ctx->chunks.back();
         if (first_read_index < c.first_index + c.n) return fail(ctx, UMIGPU_ERR_ARG, "chunks must be pushed in ascending read-index order");
@@ -327,16 +343,19 @@ extern "C" int umigpu_push_bam_records(umigpu_ctx *ctx, uint64_t n, const uint8_
     CK(ctx->d_tid.reserve_keep(tot * 4, old * 4, s)); CK(ctx->d_pos.reserve_keep(tot * 8, old * 8, s));
     CK(ctx->d_rev.reserve_keep(tot, old, s)); CK(ctx->d_umi2.reserve_keep(tot * 8, old * 8, s));
     CK(ctx->d_nmask.reserve_keep(tot * 4, old * 4, s)); CK(ctx->d_score.reserve_keep(tot * 4, old * 4, s));
+    if (paired) { CK(ctx->d_btlen.reserve(n * 8)); CK(ctx->d_tlen.reserve_keep(tot * 8, old * 8, s)); }
+    const u64 prev_unmapped = ctx->h_sc->n_bam_unmapped, prev_mates = ctx->h_sc->n_mates_skipped;
     CK(cudaMemcpyAsync(ctx->d_bamraw.p, records + base, bytes, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_bamoff.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(&sc->bam_err, 0, 8, s));
     BamDecodeOut tmp{ctx->d_btid.as<i32>(), ctx->d_bpos.as<i64>(), ctx->d_brev.as<u8>(), ctx->d_bumi2.as<u64>(), ctx->d_bnmask.as<u32>(),
-                     ctx->d_bscore.as<i32>(), ctx->d_bvalid.as<u8>()};
+                     ctx->d_bscore.as<i32>(), ctx->d_bvalid.as<u8>(), paired ? ctx->d_btlen.as<i64>() : nullptr};
     // offsets are relative to `records`; the device copy starts at records + base
     LAUNCH(bam_decode_kernel, grid_for(n, 128), 128, n, (const u8 *)ctx->d_bamraw.p - base, (const u64 *)ctx->d_bamoff.p, (int)ctx->cfg.umi_len,
-           (u32)umi_sep, ctx->cfg.merge == UMIGPU_MERGE_MAPQUAL ? 1 : 0, tmp, &sc->bam_err);
+           (u32)umi_sep, ctx->cfg.merge == UMIGPU_MERGE_MAPQUAL ? 1 : 0, paired ? 1 : 0, (ctx->cfg.flags & UMIGPU_FLAG_REMOVE_UNPAIRED) ? 1 : 0,
+           (ctx->cfg.flags & UMIGPU_FLAG_REMOVE_CHIMERIC) ? 1 : 0, tmp, &sc->bam_err, sc);
     BamDecodeOut dst{ctx->d_tid.as<i32>() + old, ctx->d_pos.as<i64>() + old, ctx->d_rev.as<u8>() + old, ctx->d_umi2.as<u64>() + old,
-                     ctx->d_nmask.as<u32>() + old, ctx->d_score.as<i32>() + old, nullptr};
+                     ctx->d_nmask.as<u32>() + old, ctx->d_score.as<i32>() + old, nullptr, paired ? ctx->d_tlen.as<i64>() + old : nullptr};
     int rc = run_scan(ctx, BamValid{ctx->d_bvalid.as<u8>()}, BamCompact{tmp, dst, ctx->d_orig.as<u32>() + old, &sc->bam_valid, n}, n, nullptr);
     if (rc) return rc;
     rc = read_scalars(ctx);
@@ -347,13 +366,15 @@ extern "C" int umigpu_push_bam_records(umigpu_ctx *ctx, uint64_t n, const uint8_
     if (e & BAM_ERR_SHORT) return fail(ctx, UMIGPU_ERR_ARG, "read name too short for a UMI of %u bases", ctx->cfg.umi_len);
     if (e & BAM_ERR_BAD_BASE) return fail(ctx, UMIGPU_ERR_BAD_BASE, "Unknown character in UMI sequence");      // utils/mod.rs:78
     if (m) LAUNCH(range_reduce_kernel, grid_for(m, 256), 256, (u64)m, (const i32 *)(ctx->d_tid.as<i32>() + old), (const i64 *)(ctx->d_pos.as<i64>() + old),
-                  (const u32 *)(ctx->d_nmask.as<u32>() + old), sc);
+                  (const i64 *)(paired ? ctx->d_tlen.as<i64>() + old : nullptr), (const u32 *)(ctx->d_nmask.as<u32>() + old), sc);
     STAGE_END(UMIGPU_STAGE_PACK);
     if (m) ctx->chunks.push_back({old, m, first_read_index});
     ctx->n_reads = old + m;
-    ctx->n_records += n;
-    ctx->n_unmapped += n - m;
-    if (n_unmapped_out) *n_unmapped_out = n - m;
+    // deduplicate_sam.rs:96-100: skipped mates are not input reads; :104/:119 both count as unmapped
+    const u64 unm = ctx->h_sc->n_bam_unmapped - prev_unmapped, mates = ctx->h_sc->n_mates_skipped - prev_mates;
+    ctx->n_records += n - mates;
+    ctx->n_unmapped += unm;
+    if (n_unmapped_out) *n_unmapped_out = unm;
     return UMIGPU_OK;
 }
 
@@ -519,6 +540,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     memset(&ctx->ctr, 0, sizeof ctx->ctr);
     ctx->ctr.total_reads = ctx->n_records;          // deduplicate_sam.rs:100 counts every record, mapped or not
     ctx->ctr.n_unmapped = ctx->n_unmapped;
+    ctx->ctr.n_unpaired = ctx->h_sc->n_unpaired; ctx->ctr.n_chimeric = ctx->h_sc->n_chimeric; ctx->ctr.n_mates_skipped = ctx->h_sc->n_mates_skipped;
     ctx->ran = true;
     if (n == 0) return UMIGPU_OK;
     DevScalars *sc = ctx->d_sc.as<DevScalars>();
@@ -538,7 +560,12 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     u64 tid_range = (u64)((i64)ctx->h_sc->tid_max - (i64)ctx->h_sc->tid_min);
     u64 pos_range = (u64)ctx->h_sc->pos_max - (u64)ctx->h_sc->pos_min;
     lay.tid_bits = bits_for(tid_range); lay.pos_bits = bits_for(pos_range);
-    lay.bucket_bits = lay.tid_bits + lay.pos_bits + 1;
+    lay.tlen_bits = 0; lay.tlen_min = 0;
+    if (ctx->have_tlen == 1) {                       // PairedAlignment: (strand, coord, ref, tlen), deduplicate_sam.rs:545-565
+        lay.tlen_min = ctx->h_sc->tlen_min;
+        lay.tlen_bits = bits_for((u64)ctx->h_sc->tlen_max - (u64)ctx->h_sc->tlen_min);
+    }
+    lay.bucket_bits = lay.tid_bits + lay.pos_bits + 1 + lay.tlen_bits;
     if (lay.bucket_bits > 64) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "bucket key needs %d bits (> 64)", lay.bucket_bits);
     lay.total_bits = lay.bucket_bits + lay.umi_bits;
     lay.nw = lay.total_bits <= 64 ? 1 : 2;
@@ -554,10 +581,10 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     }
     if (lay.nw == 1)
         LAUNCH(build_keys_kernel<1>, grid_for(n, 256), 256, n, (const i32 *)ctx->d_tid.p, (const i64 *)ctx->d_pos.p, (const u8 *)ctx->d_rev.p,
-               (const u64 *)ctx->d_umi2.p, (const u32 *)ctx->d_nmask.p, lay, ctx->d_key[0][0].as<u64>(), (u64 *)nullptr);
+               (const i64 *)(lay.tlen_bits ? ctx->d_tlen.p : nullptr), (const u64 *)ctx->d_umi2.p, (const u32 *)ctx->d_nmask.p, lay, ctx->d_key[0][0].as<u64>(), (u64 *)nullptr);
     else
         LAUNCH(build_keys_kernel<2>, grid_for(n, 256), 256, n, (const i32 *)ctx->d_tid.p, (const i64 *)ctx->d_pos.p, (const u8 *)ctx->d_rev.p,
-               (const u64 *)ctx->d_umi2.p, (const u32 *)ctx->d_nmask.p, lay, ctx->d_key[0][0].as<u64>(), ctx->d_key[0][1].as<u64>());
+               (const i64 *)(lay.tlen_bits ? ctx->d_tlen.p : nullptr), (const u64 *)ctx->d_umi2.p, (const u32 *)ctx->d_nmask.p, lay, ctx->d_key[0][0].as<u64>(), ctx->d_key[0][1].as<u64>());
     STAGE_END(UMIGPU_STAGE_KEYS);
 
     // ---- K2 sort ----

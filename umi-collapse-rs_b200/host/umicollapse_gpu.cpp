@@ -9,7 +9,7 @@
 // Differences from the reference, all deliberate: output is in input order, --algo cc
 // works, --mode fastq works (the reference's is an empty TODO, main.rs:49-51), --tag is implemented from its help
 // text (src/cli.rs:64-76; the reference collects ClusterTrackers and then writes nothing, deduplicate_sam.rs:236-239),
-// --paired is refused.
+// --paired follows deduplicate_sam.rs:96-129 (filters, on the device) and UcWriter::write_reversed (:409-462, mates).
 #include <zlib.h>
 
 #include <algorithm>
@@ -21,6 +21,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/umigpu.h"
@@ -242,9 +243,13 @@ static int merge_code(const Cli &a) {
     die("Invalid algorithm combination: " + a.algo_str + " , " + a.merge_str + " and " + a.data_str);
 }
 
-static void report(const umigpu_counters &c, uint64_t unmapped) {      // deduplicate_sam.rs:243-267
+static void report(const umigpu_counters &c, uint64_t unmapped, bool paired = false) {      // deduplicate_sam.rs:243-267
     fprintf(stderr, "Number of input reads: %llu\n", (unsigned long long)c.total_reads);
     fprintf(stderr, "Number of removed unmapped reads: %llu\n", (unsigned long long)unmapped);
+    if (paired) {                                                                           // :245-248
+        fprintf(stderr, "Number of unpaired reads: %llu\n", (unsigned long long)c.n_unpaired);
+        fprintf(stderr, "Number of chimeric reads: %llu\n", (unsigned long long)c.n_chimeric);
+    }
     fprintf(stderr, "Number of unique alignment positions: %llu\n", (unsigned long long)c.n_buckets);
     fprintf(stderr, "Number of UMIs: %llu\n", (unsigned long long)c.total_umis);
     fprintf(stderr, "Average number of UMIs per alignment position: %g\n", c.n_buckets ? (double)c.total_umis / (double)c.n_buckets : 0.0);
@@ -255,11 +260,74 @@ static void report(const umigpu_counters &c, uint64_t unmapped) {      // dedupl
 static umigpu_ctx *make_ctx(const Cli &a, unsigned umi_len) {
     umigpu_config cfg; memset(&cfg, 0, sizeof cfg);
     cfg.flags = a.track_clusters ? UMIGPU_FLAG_LABELS : 0;
+    if (a.paired) cfg.flags |= UMIGPU_FLAG_PAIRED | (a.remove_unpaired ? UMIGPU_FLAG_REMOVE_UNPAIRED : 0) | (a.remove_chimeric ? UMIGPU_FLAG_REMOVE_CHIMERIC : 0);
     cfg.k = a.k; cfg.percentage = a.percentage; cfg.algo = algo_code(a); cfg.merge = merge_code(a); cfg.umi_len = umi_len; cfg.device = a.device;
     umigpu_ctx *ctx = nullptr;
     check(umigpu_create(&cfg, &ctx), nullptr, "umigpu_create");
     return ctx;
 }
+
+// ---- host mirror of the record filters (deduplicate_sam.rs:96-129): used for -u 0 autodetection, which looks at the
+// first read that reaches UcSAMRead::new (:152-156), and for batches that are seen before the UMI length is known ----
+enum { CLS_MATE = 1, CLS_UNMAPPED = 2, CLS_UNPAIRED = 4, CLS_CHIMERIC = 8 };
+static inline unsigned rec_flag(const uint8_t *r) { return r[18] | (r[19] << 8); }
+static inline int32_t rec_i32(const uint8_t *r, size_t o) { int32_t v; memcpy(&v, r + o, 4); return v; }
+static bool rec_passes(const uint8_t *r, const Cli &a, unsigned *cls_out = nullptr) {
+    const unsigned f = rec_flag(r);
+    unsigned cls = 0; bool ok = true;
+    if (a.paired && (f & 0x1) && (f & 0x80)) { if (cls_out) *cls_out = CLS_MATE; return false; }
+    if (f & 0x4) { cls = CLS_UNMAPPED; ok = false; }
+    else if (a.paired) {
+        if (!(f & 0x1)) { cls |= CLS_UNPAIRED; if (a.remove_unpaired) ok = false; }
+        if (ok && (f & 0x1) && (f & 0x8)) { cls |= CLS_UNMAPPED; ok = false; }
+        if (ok && (f & 0x1) && rec_i32(r, 4) != rec_i32(r, 24)) { cls |= CLS_CHIMERIC; if (a.remove_chimeric) ok = false; }
+    }
+    if (cls_out) *cls_out = cls;
+    return ok;
+}
+static void count_unfed(const uint8_t *r, const Cli &a, umigpu_counters &c, uint64_t &unmapped) {
+    unsigned cls = 0; rec_passes(r, a, &cls);
+    if (!(cls & CLS_MATE)) c.total_reads++; else c.n_mates_skipped++;
+    if (cls & CLS_UNMAPPED) unmapped++;
+    if (cls & CLS_UNPAIRED) c.n_unpaired++;
+    if (cls & CLS_CHIMERIC) c.n_chimeric++;
+}
+// the caseless regex ^(?:.*?)SEP([ATCGN]+)(?:.*?)$ (utils/read.rs:65-75,87-94): first separator that is followed by an [ATCGN] letter
+static unsigned detect_umi_len(const uint8_t *r, uint8_t sep) {
+    unsigned l_name = r[12]; const uint8_t *name = r + 36; unsigned len = l_name ? l_name - 1 : 0, p = 0, n = 0;
+    for (;; p++) {
+        while (p < len && name[p] != sep) p++;
+        if (p >= len) die("failed to get the umi");
+        if (p + 1 < len && name[p + 1] && strchr("ACGTNacgtn", name[p + 1])) break;
+    }
+    for (unsigned q = p + 1; q < len && name[q] && strchr("ACGTNacgtn", name[q]); q++) n++;
+    return n;
+}
+// ---- --paired: the mates of the kept reads.  UcWriter::write (deduplicate_sam.rs:382-407) remembers, for every written
+// paired read, ReverseRead{qname, mate ref, mate pos}; write_reversed (:409-462) re-reads the input and writes every mapped,
+// paired, last-in-template record with a mapped mate whose {qname, ref, pos} is in the set, removing the entry so that a
+// repeated mate record is written once.  (ReverseRead's Eq ignores the coordinate while its Hash includes it, :289-322,
+// so a lookup only ever finds an entry with the same coordinate short of a hash collision; the key here is all three.)
+static std::string mate_key(const uint8_t *name, unsigned name_len, int32_t tid, int32_t pos) {
+    std::string k((const char *)name, name_len);
+    k.append((const char *)&tid, 4); k.append((const char *)&pos, 4);
+    return k;
+}
+struct MateSet {
+    std::unordered_set<std::string> set;
+    void remember(const uint8_t *r) {                                  // :393-399
+        if (!(rec_flag(r) & 0x1)) return;
+        set.insert(mate_key(r + 36, r[12] ? r[12] - 1 : 0, rec_i32(r, 24), rec_i32(r, 28)));
+    }
+    bool take(const uint8_t *r) {                                      // :429-459
+        const unsigned f = rec_flag(r);
+        if ((f & 0x4) || !(f & 0x1) || !(f & 0x80) || (f & 0x8)) return false;
+        auto it = set.find(mate_key(r + 36, r[12] ? r[12] - 1 : 0, rec_i32(r, 4), rec_i32(r, 8)));
+        if (it == set.end()) return false;
+        set.erase(it);
+        return true;
+    }
+};
 
 // ---- --mode bam ----
 static int run_bam(const Cli &a) {
@@ -278,16 +346,8 @@ static int run_bam(const Cli &a) {
     unsigned umi_len = a.umi_length;
     for (uint64_t i = 0; i < n && umi_len == 0; i++) {
         const uint8_t *r = buf.data() + first + offs[i];
-        unsigned flag = r[18] | (r[19] << 8);
-        if (flag & 4) continue;
-        // the caseless regex ^(?:.*?)SEP([ATCGN]+)(?:.*?)$: first separator that is followed by an [ATCGN] letter
-        unsigned l_name = r[12]; const uint8_t *name = r + 36; unsigned len = l_name ? l_name - 1 : 0, p = 0;
-        for (;; p++) {
-            while (p < len && name[p] != a.umi_separator) p++;
-            if (p >= len) die("failed to get the umi");
-            if (p + 1 < len && name[p + 1] && strchr("ACGTNacgtn", name[p + 1])) break;
-        }
-        for (unsigned q = p + 1; q < len && name[q] && strchr("ACGTNacgtn", name[q]); q++) umi_len++;
+        if (!rec_passes(r, a)) continue;
+        umi_len = detect_umi_len(r, a.umi_separator);
         break;
     }
     std::vector<const uint8_t *> optr{buf.data()}; std::vector<size_t> olen{first};
@@ -306,13 +366,16 @@ static int run_bam(const Cli &a) {
         ctr = res.counters;
         std::vector<std::vector<uint8_t>> tagged;         // --tag: rewritten records (own storage)
         if (!a.track_clusters) {
-            // merge kept indices with (optionally) the unmapped records, input order
+            MateSet mates;
+            if (a.paired) for (uint64_t j = 0; j < res.n_kept; j++) mates.remember(buf.data() + first + offs[res.kept_read_index[j]]);
+            // merge kept indices with (optionally) the unmapped records and (--paired) the kept reads' mates, input order
             uint64_t kpos = 0;
             for (uint64_t i = 0; i < n; i++) {
                 const uint8_t *r = buf.data() + first + offs[i];
                 bool keep = kpos < res.n_kept && res.kept_read_index[kpos] == i;
                 if (keep) kpos++;
                 else if (a.keep_unmapped && ((r[18] | (r[19] << 8)) & 4)) keep = true;          // deduplicate_sam.rs:104-106
+                else if (a.paired && mates.take(r)) keep = true;                                // :429-459
                 if (keep) { optr.push_back(r); olen.push_back(offs[i + 1] - offs[i]); }
             }
         } else {
@@ -353,30 +416,38 @@ static int run_bam(const Cli &a) {
         bgzf_write(a.output, optr, olen, a.num_threads);
         umigpu_destroy(ctx);
     } else {
+        for (uint64_t i = 0; i < n; i++) {                       // nothing reached the device: every record failed a filter
+            const uint8_t *r = buf.data() + first + offs[i];
+            count_unfed(r, a, ctr, unmapped);
+            if (a.keep_unmapped && (rec_flag(r) & 4)) { optr.push_back(r); olen.push_back(offs[i + 1] - offs[i]); }
+        }
         bgzf_write(a.output, optr, olen, a.num_threads);
-        ctr.total_reads = n;
     }
-    report(ctr, unmapped);
+    report(ctr, unmapped, a.paired);
     return 0;
 }
 
 // ---- --mode bam --two-pass (src/cli.rs:45-48: "should use much less memory"): the input is streamed twice, the
-// host never holds more than one batch of inflated blocks; pass 1 feeds the device, pass 2 writes the survivors ----
+// host never holds more than one batch of inflated blocks; the first pass feeds the device, the last one writes the
+// survivors; --paired adds a pass in between that collects the mate keys of the kept reads (UcWriter::write, :393-399) ----
 static int run_bam_two_pass(const Cli &a) {
     umigpu_ctx *ctx = nullptr;
     unsigned umi_len = a.umi_length;
-    uint64_t n_total = 0, unmapped = 0;
+    uint64_t unmapped = 0;
+    umigpu_counters unfed; memset(&unfed, 0, sizeof unfed);       // records of batches seen before the UMI length was known
     std::vector<uint8_t> header;
-    for (int pass = 0; pass < 2; pass++) {
+    MateSet mates;
+    umigpu_result res; memset(&res, 0, sizeof res);
+    const int n_pass = a.paired ? 3 : 2, last_pass = n_pass - 1;
+    for (int pass = 0; pass < n_pass; pass++) {
         BgzfStream in(a.input, a.num_threads);
         std::vector<uint8_t> buf;
         std::vector<uint64_t> offs;
         bool have_header = false;
         uint64_t index = 0, kpos = 0;
-        umigpu_result res; memset(&res, 0, sizeof res);
         BgzfOut *out = nullptr;
-        if (pass == 1) {
-            if (ctx) check(umigpu_finish(ctx, &res), ctx, "umigpu_finish");
+        if (pass == 1 && ctx) check(umigpu_finish(ctx, &res), ctx, "umigpu_finish");
+        if (pass == last_pass) {
             out = new BgzfOut(a.output, a.num_threads);
             out->add(header.data(), header.size());
         }
@@ -407,41 +478,38 @@ static int run_bam_two_pass(const Cli &a) {
             if (pass == 0) {
                 for (uint64_t i = 0; i < n && umi_len == 0; i++) {             // -u 0: autodetect (utils/read.rs:65-75)
                     const uint8_t *r = recs + offs[i];
-                    if ((r[18] | (r[19] << 8)) & 4) continue;
-                    unsigned l_name = r[12]; const uint8_t *name = r + 36; unsigned len = l_name ? l_name - 1 : 0, p = 0;
-                    for (;; p++) {
-                        while (p < len && name[p] != a.umi_separator) p++;
-                        if (p >= len) die("failed to get the umi");
-                        if (p + 1 < len && name[p + 1] && strchr("ACGTNacgtn", name[p + 1])) break;
-                    }
-                    for (unsigned q = p + 1; q < len && name[q] && strchr("ACGTNacgtn", name[q]); q++) umi_len++;
+                    if (rec_passes(r, a)) umi_len = detect_umi_len(r, a.umi_separator);
                 }
                 if (n && umi_len) {
                     if (!ctx) ctx = make_ctx(a, umi_len);
                     uint64_t nun = 0;
                     check(umigpu_push_bam_records(ctx, n, recs, offs.data(), a.umi_separator, index, &nun), ctx, "umigpu_push_bam_records");
                     unmapped += nun;
-                } else if (n) {
-                    unmapped += n;          // no mapped read seen yet: everything so far fails the unmapped filter
+                } else {                    // no read has passed the filters yet: count the batch on the host
+                    for (uint64_t i = 0; i < n; i++) count_unfed(recs + offs[i], a, unfed, unmapped);
                 }
-                n_total += n;
+            } else if (pass < last_pass) {  // --paired: mate keys of the kept reads
+                for (uint64_t i = 0; i < n; i++)
+                    if (kpos < res.n_kept && res.kept_read_index[kpos] == index + i) { kpos++; mates.remember(recs + offs[i]); }
             } else {
                 for (uint64_t i = 0; i < n; i++) {
                     const uint8_t *r = recs + offs[i];
                     bool keep = kpos < res.n_kept && res.kept_read_index[kpos] == index + i;
                     if (keep) kpos++;
                     else if (a.keep_unmapped && ((r[18] | (r[19] << 8)) & 4)) keep = true;
+                    else if (a.paired && mates.take(r)) keep = true;
                     if (keep) out->add(r, offs[i + 1] - offs[i]);
                 }
             }
             index += n;
             buf.erase(buf.begin(), buf.begin() + start + consumed);         // a trailing partial record stays for the next batch
         }
-        if (pass == 1) {
+        if (pass == last_pass) {
             out->close(); delete out;
             umigpu_counters ctr; memset(&ctr, 0, sizeof ctr);
-            if (ctx) ctr = res.counters; else ctr.total_reads = n_total;
-            report(ctr, unmapped);
+            if (ctx) ctr = res.counters;
+            ctr.total_reads += unfed.total_reads; ctr.n_unpaired += unfed.n_unpaired; ctr.n_chimeric += unfed.n_chimeric;
+            report(ctr, unmapped, a.paired);
             if (ctx) umigpu_destroy(ctx);
         }
     }
@@ -513,7 +581,8 @@ static int run_fastq(const Cli &a) {
 int main(int argc, char **argv) {
     Cli a = parse(argc, argv);
     auto t0 = std::chrono::steady_clock::now();
-    if (a.paired) die("--paired is outside the scope of the GPU path (SURVEY.md §2); use the reference's CPU path");
+    if (a.paired && a.mode == "fastq") die("--paired applies to --mode bam only");
+    if (a.paired && a.track_clusters) die("--tag with --paired is not implemented (the reference's tag pass is an empty TODO, deduplicate_sam.rs:236-239)");
     if (a.track_clusters && a.mode == "fastq") die("--tag is implemented for --mode bam only");
     int rc;
     if (a.mode == "fastq") rc = run_fastq(a);

@@ -36,6 +36,7 @@ pub struct umigpu_counters {
     pub total_reads: u64, pub n_buckets: u64, pub total_umis: u64, pub max_umis: u64, pub n_kept: u64,
     pub unordered_pairs: u64, pub pairs_evaluated: u64, pub n_edges: u64, pub n_tile_items: u64,
     pub n_tile_candidates: u64, pub n_sweeps: u64, pub n_block_pairs: u64, pub n_unmapped: u64,
+    pub n_unpaired: u64, pub n_chimeric: u64, pub n_mates_skipped: u64,
 }
 
 #[repr(C)]
@@ -58,6 +59,9 @@ extern "C" {
                              umi_ascii: *const u8, score: *const i32, weight: *const i32, first_read_index: u64) -> c_int;
     pub fn umigpu_push_reads_device(ctx: *mut umigpu_ctx, n: u64, tid: *const i32, unclipped_pos: *const i64, is_reverse: *const u8,
                                     umi_ascii: *const u8, score: *const i32, weight: *const i32, first_read_index: u64) -> c_int;
+    pub fn umigpu_push_reads_paired(ctx: *mut umigpu_ctx, n: u64, tid: *const i32, unclipped_pos: *const i64, is_reverse: *const u8,
+                                    tlen: *const i64, umi_ascii: *const u8, score: *const i32, weight: *const i32,
+                                    first_read_index: u64) -> c_int;
     pub fn umigpu_push_bam_records(ctx: *mut umigpu_ctx, n: u64, records: *const u8, offsets: *const u64, umi_sep: u8,
                                    first_read_index: u64, n_unmapped: *mut u64) -> c_int;
     pub fn umigpu_bam_record_offsets(buf: *const u8, len: u64, offsets: *mut u64, max_records: u64, n_records: *mut u64,

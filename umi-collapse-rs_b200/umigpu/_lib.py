@@ -14,6 +14,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_BAD_BASE, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE = 0, 
 ALGO_DIR, ALGO_ADJ, ALGO_ADJ_UPSTREAM, ALGO_CC = 0, 1, 2, 3
 MERGE_ANY, MERGE_AVGQUAL, MERGE_MAPQUAL = 0, 1, 2
 FLAG_LABELS, FLAG_NO_CULL, FLAG_KERNEL_DIRECT, FLAG_KERNEL_TILES, FLAG_NO_MULTI_INDEX = 1, 2, 4, 8, 16
+FLAG_PAIRED, FLAG_REMOVE_UNPAIRED, FLAG_REMOVE_CHIMERIC = 32, 64, 128
 STAGES = ["pack", "keys", "sort", "unique", "worklist", "neighbours", "cluster", "emit", "total"]
 
 # every symbol include/umigpu.h declares (tests check that the built library exports all of them)
@@ -23,7 +24,7 @@ SYMBOLS = [
     "umigpu_get_counters", "umigpu_cluster_bucket", "umigpu_remove_near", "umigpu_neighbours",
     "umigpu_avg_qual", "umigpu_stage_ms", "umigpu_launch_count", "umigpu_result_free",
     "umigpu_shard_plan", "umigpu_int_peak", "umigpu_push_bam_records", "umigpu_bam_record_offsets",
-    "umigpu_dedup_sharded", "umigpu_free",
+    "umigpu_dedup_sharded", "umigpu_free", "umigpu_push_reads_paired",
 ]
 
 
@@ -36,7 +37,8 @@ class Config(C.Structure):
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "total_reads", "n_buckets", "total_umis", "max_umis", "n_kept", "unordered_pairs",
-        "pairs_evaluated", "n_edges", "n_tile_items", "n_tile_candidates", "n_sweeps", "n_block_pairs", "n_unmapped")]
+        "pairs_evaluated", "n_edges", "n_tile_items", "n_tile_candidates", "n_sweeps", "n_block_pairs", "n_unmapped",
+        "n_unpaired", "n_chimeric", "n_mates_skipped")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -75,6 +77,7 @@ def load() -> C.CDLL:
     lib.umigpu_reset.argtypes = [p]
     for name in ("umigpu_push_reads", "umigpu_push_reads_device"):
         getattr(lib, name).argtypes = [p, u64, p, p, p, p, p, p, u64]
+    lib.umigpu_push_reads_paired.argtypes = [p, u64, p, p, p, p, p, p, p, u64]
     lib.umigpu_push_bam_records.argtypes = [p, u64, p, p, C.c_uint8, u64, C.POINTER(u64)]
     lib.umigpu_bam_record_offsets.argtypes = [p, u64, p, u64, C.POINTER(u64), C.POINTER(u64)]
     lib.umigpu_dedup_sharded.argtypes = [C.POINTER(Config), i32, p, u64, p, p, p, p, p, C.POINTER(C.POINTER(u64)), C.POINTER(u64), C.POINTER(Counters)]

@@ -103,10 +103,19 @@ class Context:
         self._keepalive.clear()
         L.check(self._lib.umigpu_reset(self._h), self._h)
 
-    def push_reads(self, tid, pos, rev, umi, score=None, weight=None, first_read_index: int = 0):
-        """umigpu_push_reads / _device: arrays of equal length n; umi is [n, umi_len] uint8 ASCII."""
+    def push_reads(self, tid, pos, rev, umi, score=None, weight=None, first_read_index: int = 0, tlen=None):
+        """umigpu_push_reads / _device: arrays of equal length n; umi is [n, umi_len] uint8 ASCII.
+        tlen (int64, host arrays) selects umigpu_push_reads_paired: the template length joins the bucket key."""
         n = int(tid.shape[0])
         dev = _is_device(tid)
+        if tlen is not None:
+            assert not dev, "umigpu_push_reads_paired takes host arrays"
+            arrs = [np.ascontiguousarray(a, dtype=dt) if a is not None else None
+                    for a, dt in ((tid, "int32"), (pos, "int64"), (rev, "uint8"), (tlen, "int64"), (umi, "uint8"),
+                                  (score, "int32"), (weight, "int32"))]
+            self._keepalive.append(arrs)
+            L.check(self._lib.umigpu_push_reads_paired(self._h, n, *[_ptr(a) for a in arrs], first_read_index), self._h)
+            return
         arrs = []
         for a, dt in ((tid, "int32"), (pos, "int64"), (rev, "uint8"), (umi, "uint8"), (score, "int32"), (weight, "int32")):
             if a is None:

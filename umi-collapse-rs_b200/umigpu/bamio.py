@@ -61,10 +61,11 @@ def make_header(ref_names, ref_lens, text: str = "@HD\tVN:1.6\tSO:coordinate\n")
     return b"".join(out)
 
 
-def make_record(tid: int, pos: int, flag: int, mapq: int, qname: bytes, cigar, seq_len: int, qual: bytes) -> bytes:
+def make_record(tid: int, pos: int, flag: int, mapq: int, qname: bytes, cigar, seq_len: int, qual: bytes,
+                mtid: int = -1, mpos: int = -1, tlen: int = 0) -> bytes:
     """cigar = [(op, len)] with op codes M0 I1 D2 N3 S4 H5 P6 =7 X8; sequence bases are irrelevant to the path (all A)."""
     name = qname + b"\0"
-    body = struct.pack("<iiBBHHHiiii", tid, pos, len(name), mapq, 4680, len(cigar), flag, seq_len, -1, -1, 0)
+    body = struct.pack("<iiBBHHHiiii", tid, pos, len(name), mapq, 4680, len(cigar), flag, seq_len, mtid, mpos, tlen)
     body += name + b"".join(struct.pack("<I", (ln << 4) | op) for op, ln in cigar)
     body += bytes((seq_len + 1) // 2) + qual
     return struct.pack("<i", len(body)) + body
@@ -93,7 +94,54 @@ def push_bam(ctx: Context, buf, offsets: np.ndarray, umi_sep: int = ord("_"), fi
     return int(nun.value)
 
 
-def autodetect_umi_length(buf, offsets, sep: int) -> int:
+def _mate_fields(buf, o: int):
+    l_name = buf[o + 12]
+    flag, = struct.unpack_from("<H", buf, o + 18)
+    tid, pos = struct.unpack_from("<ii", buf, o + 4)
+    mtid, mpos = struct.unpack_from("<ii", buf, o + 24)
+    return bytes(buf[o + 36: o + 36 + max(l_name - 1, 0)]), flag, tid, pos, mtid, mpos
+
+
+def select_mates(buf, offsets, kept) -> list:
+    """UcWriter::write / write_reversed, deduplicate_sam.rs:382-462: record numbers of the mates of the kept reads.
+    Every kept paired read registers (qname, mate ref, mate pos); every mapped, paired, last-in-template record with a
+    mapped mate whose (qname, ref, pos) is registered is written and the entry removed (a repeated mate record is written
+    once, the first in file order)."""
+    want = set()
+    for i in kept:
+        name, flag, _tid, _pos, mtid, mpos = _mate_fields(buf, int(offsets[i]))
+        if flag & 0x1:
+            want.add((name, mtid, mpos))
+    out = []
+    for i in range(len(offsets) - 1):
+        name, flag, tid, pos, _mtid, _mpos = _mate_fields(buf, int(offsets[i]))
+        if (flag & 0x4) or not (flag & 0x1) or not (flag & 0x80) or (flag & 0x8):
+            continue
+        key = (name, tid, pos)
+        if key in want:
+            want.discard(key)
+            out.append(i)
+    return out
+
+
+def _passes_filters(buf, o: int, args) -> bool:
+    """deduplicate_sam.rs:96-129: does this record reach UcSAMRead::new (:152)?"""
+    flag, = struct.unpack_from("<H", buf, o + 18)
+    if args is not None and args.paired:
+        if (flag & 0x1) and (flag & 0x80):
+            return False
+        if flag & 0x4:
+            return False
+        if not (flag & 0x1):
+            return not args.remove_unpaired
+        if flag & 0x8:
+            return False
+        tid, = struct.unpack_from("<i", buf, o + 4); mtid, = struct.unpack_from("<i", buf, o + 24)
+        return not (tid != mtid and args.remove_chimeric)
+    return not (flag & 0x4)
+
+
+def autodetect_umi_length(buf, offsets, sep: int, args=None) -> int:
     """utils/read.rs:65-75,87-94 on the first mapped record: the caseless regex ^(?:.*?)SEP([ATCGN]+)(?:.*?)$ —
     i.e. the run of [ATCGN] after the FIRST separator that is followed by at least one such letter.  (get_umi
     itself always cuts after the first separator, utils/read.rs:100-101; when the two disagree the reference
@@ -101,8 +149,7 @@ def autodetect_umi_length(buf, offsets, sep: int) -> int:
     letters = b"ACGTNacgtn"
     for i in range(len(offsets) - 1):
         o = int(offsets[i])
-        flag, = struct.unpack_from("<H", buf, o + 18)
-        if flag & 4:
+        if not _passes_filters(buf, o, args):
             continue
         l_name = buf[o + 12]
         name = bytes(buf[o + 36: o + 36 + l_name - 1])
@@ -122,21 +169,22 @@ def autodetect_umi_length(buf, offsets, sep: int) -> int:
 
 def deduplicate_and_merge(args: Cli, device: int = 0, chunk_records: int = 1 << 22) -> dict:
     """BAM in -> BAM out, every CLI flag of the reference that reaches the single-end path honoured
-    (-k -u -p --umi_sep --algo --merge --keep-unmapped; --data ignored like the reference; --paired unsupported).
-    Survivors are written in input order (canonical), unmapped reads too with --keep-unmapped
-    (deduplicate_sam.rs:102-108)."""
+    (-k -u -p --umi_sep --algo --merge --keep-unmapped --paired --remove-unpaired --remove-chimeric; --data ignored
+    like the reference).  Survivors are written in input order (canonical), unmapped reads too with --keep-unmapped
+    (deduplicate_sam.rs:102-108); with --paired the kept reads' mates follow UcWriter::write_reversed (:409-462)."""
     algo, merge = resolve_cli(args)
-    if args.paired:
-        raise NotImplementedError("--paired is outside the scope of this path (SURVEY §2)")
     buf = bgzf_read_all(args.input)
     header, _names, first = parse_header(buf)
     offsets, consumed = record_offsets(buf, first)
     n = len(offsets) - 1
-    umi_len = args.umi_length or autodetect_umi_length(buf, offsets, args.umi_separator)
+    umi_len = args.umi_length or autodetect_umi_length(buf, offsets, args.umi_separator, args)
     if n == 0 or umi_len == 0:
         bgzf_write_all(args.output, header)
         return dict(total_reads=n, n_kept=0)
-    with Context(umi_len, args.k, args.percentage, algo, merge, device) as ctx:
+    fl = 0
+    if args.paired:
+        fl = L.FLAG_PAIRED | (L.FLAG_REMOVE_UNPAIRED if args.remove_unpaired else 0) | (L.FLAG_REMOVE_CHIMERIC if args.remove_chimeric else 0)
+    with Context(umi_len, args.k, args.percentage, algo, merge, device, fl) as ctx:
         for s in range(0, n, chunk_records):
             e = min(n, s + chunk_records)
             push_bam(ctx, buf, offsets[s: e + 1], args.umi_separator, s)
@@ -146,6 +194,8 @@ def deduplicate_and_merge(args: Cli, device: int = 0, chunk_records: int = 1 << 
     if args.keep_unmapped:
         flags = np.array([struct.unpack_from("<H", buf, int(o) + 18)[0] for o in offsets[:-1]], dtype=np.uint16)
         keep |= (flags & 4) != 0
+    if args.paired:
+        keep[select_mates(buf, offsets, kept.astype(np.int64))] = True
     out = [header]
     mv = memoryview(buf)
     for i in np.nonzero(keep)[0]:
