@@ -23,9 +23,12 @@ static inline u64 ceil_div_u64(u64 a, u64 b) { return (a + b - 1) / b; }
 struct DevBuf {
     void  *p = nullptr;
     size_t cap = 0;
+    bool   borrowed = false;   // p belongs to the caller (zero-copy device push); cap stays 0 so any growth copies out of it
+    void borrow(const void *ptr) { release(); p = const_cast<void *>(ptr); borrowed = true; }
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         size_t want = bytes + bytes / 8 + 256;
+        if (borrowed) { p = nullptr; borrowed = false; }
         if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { p = nullptr; cap = 0; return e; }
@@ -45,11 +48,11 @@ struct DevBuf {
             e = cudaStreamSynchronize(s);
             if (e != cudaSuccess) { cudaFree(q); return e; }
         }
-        if (p) cudaFree(p);
-        p = q; cap = want;
+        if (p && !borrowed) cudaFree(p);
+        p = q; cap = want; borrowed = false;
         return cudaSuccess;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p && !borrowed) cudaFree(p); p = nullptr; cap = 0; borrowed = false; }
     template <class T> T *as() const { return (T *)p; }
 };
 

@@ -50,9 +50,17 @@ struct UniqueEmit {
         }
     }
     __device__ void finish() { flush(); }
-    __device__ void operator()(u64 i, u32 flag, u32 ex) {
+    // the idx -> score / weight gathers of a thread's SCAN_ITEMS reads are independent: issue them all before the scan
+    u32 pf_r[SCAN_ITEMS]; i32 pf_s[SCAN_ITEMS], pf_w[SCAN_ITEMS];
+    __device__ __forceinline__ void prefetch(u64 i, int j) {
+        const u32 r = __ldg(idx + i);
+        pf_r[j] = r;
+        pf_s[j] = score ? __ldg(score + r) : 0;
+        pf_w[j] = weight ? __ldg(weight + r) : 0;
+    }
+    __device__ __forceinline__ void operator()(u64 i, u32 flag, u32 ex, int j) {
         u32 uid = ex + flag - 1;
-        u32 r = idx[i];
+        u32 r = pf_r[j];
         if (flag) {
             useg[uid] = (u32)i;
             u64 code = sk.umi_bits == 64 ? sk.k0[i] : (sk.k0[i] & ((1ull << sk.umi_bits) - 1));
@@ -64,9 +72,9 @@ struct UniqueEmit {
             bhead[uid] = (i == 0 || !sk.same_bucket(i, i - 1)) ? 1 : 0;
         }
         if (i == n - 1) useg[uid + 1] = (u32)n;
-        u32 s = score ? (u32)score[r] ^ 0x80000000u : 0u;
+        u32 s = score ? (u32)pf_s[j] ^ 0x80000000u : 0u;
         const unsigned long long pk = ((unsigned long long)s << 32) | (u32)~r;
-        const i32 wv = weight ? weight[r] : 0;
+        const i32 wv = pf_w[j];
         if (uid == pend_uid) { pend_val = pk > pend_val ? pk : pend_val; pend_w += wv; }
         else { flush(); pend_uid = uid; pend_val = pk; pend_w = wv; }
         if (read_uid) read_uid[r] = uid;
@@ -161,6 +169,16 @@ __global__ void __launch_bounds__(256) mi_gather_kernel(u32 m_total, const u32 *
 
 // cnts = row_cnt | col_cnt << 12 | diag << 31 (counts <= 2048); col_blk0 = global id of the column tile's first
 // 128-block (the row tile's is col_blk0 - (col_start - row_start) / 128: same bucket, 128-aligned)
+// multi-index pass q orders a big bucket by its part-q value first, so two blocks (or tiles) can only hold a pair that
+// agrees on part q if their part-q value RANGES overlap: with rows before columns in the order, iff last(rows) >=
+// first(cols).  The summaries keep the (top 32 bits of the) part value of their first and last UMI in words 5 and 6.
+__device__ __forceinline__ u32 mi_part_value32(const MiParams &mi, unsigned long long code) {
+    const unsigned long long m = mi.cmask[mi.part];
+    const int sh = __ffsll((long long)m) - 1, bits = __popcll(m);
+    unsigned long long v = (code & m) >> sh;
+    if (bits > 32) v >>= (bits - 32);
+    return (u32)v;
+}
 struct TileItem { u32 row_start, col_start, cnts, col_blk0; };
 __device__ __forceinline__ u32 item_row_cnt(const TileItem &it) { return it.cnts & 0xfffu; }
 __device__ __forceinline__ u32 item_col_cnt(const TileItem &it) { return (it.cnts >> 12) & 0xfffu; }
@@ -241,7 +259,8 @@ __global__ void __launch_bounds__(256) tile_summary_kernel(u32 n_tiles, u32 n_bu
                                                            const u32 *__restrict__ bstart, const uint2 *__restrict__ planes,
                                                            const u32 *__restrict__ nplane, int L, u32 *__restrict__ tsum,
                                                            const u32 *__restrict__ blk_off, u32 *__restrict__ bsum,
-                                                           u32 *__restrict__ blk_first, u32 *__restrict__ blk_cnt) {
+                                                           u32 *__restrict__ blk_first, u32 *__restrict__ blk_cnt,
+                                                           const u64 *__restrict__ ucode, MiParams mi) {
     u32 t = (blockIdx.x * 256 + threadIdx.x) >> 5;
     if (t >= n_tiles) return;
     u32 lo = 0, hi = n_buckets;
@@ -250,6 +269,7 @@ __global__ void __launch_bounds__(256) tile_summary_kernel(u32 n_tiles, u32 n_bu
     u32 first = s + ti * HT_ROWS, cnt = min((u32)HT_ROWS, nb - ti * HT_ROWS);
     u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
     u32 tot[5] = {0, 0, 0, 0, 0};
+    const bool filt = mi.part >= 0 && nb > mi.big;
     const u32 gb0 = blk_off[b] + ti * BLOCKS_PER_TILE;       // global id of the tile's first 128-block
     for (u32 blk = 0; blk * 128 < cnt; blk++) {
         u32 acc[5] = {0, 0, 0, 0, 0};
@@ -265,6 +285,8 @@ __global__ void __launch_bounds__(256) tile_summary_kernel(u32 n_tiles, u32 n_bu
             u32 v = 0;
 #pragma unroll
             for (int x = 0; x < 5; x++) if (lane_id() == (u32)x) v = acc[x];
+            if (filt && lane_id() == 5) v = mi_part_value32(mi, ucode[first + blk * 128]);
+            if (filt && lane_id() == 6) v = mi_part_value32(mi, ucode[first + min(cnt, (blk + 1) * 128) - 1]);
             bsum[((u64)gb0 + blk) * TS_WORDS + lane_id()] = v;
         }
         if (lane_id() == 0) { blk_first[gb0 + blk] = first + blk * 128; blk_cnt[gb0 + blk] = min(128u, cnt - blk * 128); }
@@ -273,6 +295,8 @@ __global__ void __launch_bounds__(256) tile_summary_kernel(u32 n_tiles, u32 n_bu
         u32 v = 0;
 #pragma unroll
         for (int x = 0; x < 5; x++) if (lane_id() == (u32)x) v = tot[x];
+        if (filt && lane_id() == 5) v = mi_part_value32(mi, ucode[first]);
+        if (filt && lane_id() == 6) v = mi_part_value32(mi, ucode[first + cnt - 1]);
         tsum[(u64)t * TS_WORDS + lane_id()] = v;
     }
 }
@@ -321,8 +345,9 @@ __global__ void __launch_bounds__(256) build_items_kernel(u32 n_cand, u32 n_buck
             const u32 *a = tsum + (u64)(tile_off[b] + ti) * TS_WORDS, *c = tsum + (u64)(tile_off[b] + tj) * TS_WORDS;
             live = disjoint_positions(a, c, lmask) <= (u32)k;
             if (live && filt) live = disjoint_positions(a, c, mi.pmask[mi.part]) == 0;
-        }
-        if (live) npairs = (u64)rc * cc;
+            if (live) npairs = (u64)rc * cc;          // the pair space the density heuristic compares with: before the range test
+            if (live && filt) live = a[6] >= c[5];    // part-q value ranges overlap
+        } else if (live) npairs = (u64)rc * cc;
     }
     // warp-aggregated append
     u32 m = __ballot_sync(0xffffffffu, live);

@@ -60,10 +60,11 @@ __global__ void __launch_bounds__(256) expand_blocks_kernel(const TileItem *__re
     const u32 row_blk0 = it.col_blk0 - ((it.col_start - it.row_start) >> 7);
     const u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
     const u32 r = lane & 15, c0 = (lane >> 4) * 8;
-    u32 rs[5] = {0, 0, 0, 0, 0};
+    u32 rs[5] = {0, 0, 0, 0, 0}, r_last = 0;
     if (r < nrb) {
 #pragma unroll
         for (int x = 0; x < 5; x++) rs[x] = bsum[(u64)(row_blk0 + r) * 8 + x];
+        r_last = bsum[(u64)(row_blk0 + r) * 8 + 6];
     }
     u32 live = 0;
 #pragma unroll
@@ -75,7 +76,8 @@ __global__ void __launch_bounds__(256) expand_blocks_kernel(const TileItem *__re
 #pragma unroll
             for (int x = 0; x < 5; x++) cs[x] = bsum[(u64)(it.col_blk0 + c) * 8 + x];
             ok = disjoint_positions(rs, cs, lmask) <= (u32)k;
-            if (ok && filt) ok = disjoint_positions(rs, cs, mi.pmask[mi.part]) == 0;     // part-q value ranges must overlap
+            if (ok && filt) ok = disjoint_positions(rs, cs, mi.pmask[mi.part]) == 0;     // part-q letter sets must intersect
+            if (ok && filt) ok = r_last >= bsum[(u64)(it.col_blk0 + c) * 8 + 5];         // part-q value ranges must overlap
         }
         if (ok) live |= 1u << i;
     }

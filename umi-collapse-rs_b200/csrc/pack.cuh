@@ -41,7 +41,7 @@ struct KeyLayout {
 __global__ void __launch_bounds__(PACK_THREADS) umi_pack_kernel(
     const u8 *__restrict__ ascii, u64 n, int L, const i32 *__restrict__ tid, const i64 *__restrict__ pos,
     const i64 *__restrict__ tlen, u64 *__restrict__ umi2, u32 *__restrict__ nmask, DevScalars *sc) {
-    __shared__ __align__(16) u8 sbuf[PACK_THREADS * 32];
+    __shared__ __align__(16) u8 sbuf[PACK_THREADS * 32 + 16];
     __shared__ i64 s_lmin[PACK_THREADS / 32], s_lmax[PACK_THREADS / 32];
     i64 lmin = 0x7fffffffffffffffLL, lmax = (i64)0x8000000000000000LL;
     __shared__ i32 s_tmin[PACK_THREADS / 32], s_tmax[PACK_THREADS / 32];
@@ -51,33 +51,56 @@ __global__ void __launch_bounds__(PACK_THREADS) umi_pack_kernel(
     i64 pmin = 0x7fffffffffffffffLL, pmax = (i64)0x8000000000000000LL;
     u32 flags = 0;     // bit 0 = any N, bit 1 = bad base
     // persistent CTAs: a grid-stride loop over 256-read tiles, ONE range reduction per CTA at the end
+    // L a multiple of 4 on a 4-byte aligned array: every read is whole words, loaded straight from global (a warp's loads
+    // cover one contiguous span; L1 serves the repeats) — no staging, no barriers
+    const bool direct = (L & 3) == 0 && (((unsigned long long)ascii) & 3ull) == 0;
     for (u64 base = (u64)blockIdx.x * PACK_THREADS; base < n; base += (u64)gridDim.x * PACK_THREADS) {
         const u32 cnt = (u32)min((u64)PACK_THREADS, n - base);
         const u32 bytes = cnt * (u32)L;
         const u8 *src = ascii + base * (u64)L;
-        __syncthreads();                      // the previous tile's bytes have been consumed
+        if (!direct) __syncthreads();         // the previous tile's bytes have been consumed
         // stage the tile's contiguous ASCII span with coalesced (vector) loads
-        if ((((unsigned long long)src) & 15ull) == 0) {
+        if (direct) {
+        } else if ((((unsigned long long)src) & 15ull) == 0) {
             const u32 nv = bytes >> 4;
             for (u32 v = threadIdx.x; v < nv; v += PACK_THREADS) reinterpret_cast<uint4 *>(sbuf)[v] = reinterpret_cast<const uint4 *>(src)[v];
             for (u32 b = (nv << 4) + threadIdx.x; b < bytes; b += PACK_THREADS) sbuf[b] = src[b];
         } else {
             for (u32 b = threadIdx.x; b < bytes; b += PACK_THREADS) sbuf[b] = src[b];
         }
-        __syncthreads();
+        if (!direct) __syncthreads();
         if (threadIdx.x < cnt) {
             const u64 i = base + threadIdx.x;
-            const u8 *s = sbuf + threadIdx.x * (u32)L;
+            // utils/read.rs:22-31 alphabet; anything else panics in the reference (utils/mod.rs:78).
+            // Four bases per step (SWAR): bits 1-2 of the ASCII code separate A,C,T,G (0,1,3,2 -> Gray step -> A0 C1 G2 T3);
+            // a byte is valid iff it equals the letter its own bits name (one PRMT rebuilds the four letters); one
+            // multiply gathers the four 2-bit codes.  Only words holding an N or a bad byte take the per-byte path.
+            const u32 o = threadIdx.x * (u32)L, sh = 8u * (o & 3u);
+            const u32 *sw = reinterpret_cast<const u32 *>(sbuf) + (o >> 2);
+            const u32 *gw = reinterpret_cast<const u32 *>(src) + (o >> 2);
             u64 code = 0; u32 nm = 0;
-            for (int b = 0; b < L; b++) {
-                // utils/read.rs:22-31 alphabet; anything else panics in the reference (utils/mod.rs:78).
-                // Branch-free: bits 1-2 of the ASCII code separate A,C,T,G (0,1,2,3); a Gray step turns that into
-                // A0 C1 G2 T3; the byte is valid iff it equals the letter its own bits name.
-                const u32 c = s[b], w = (c >> 1) & 3u;
-                u32 v = w ^ (w >> 1);
-                const bool acgt = c == ((0x47544341u >> (8u * w)) & 0xffu);
-                if (!acgt) { v = 0; if (c == 'N') nm |= 1u << (L - 1 - b); else flags |= 2u; }
-                code = (code << 2) | v;
+            u32 lo = direct ? 0u : sw[0];
+            for (int b = 0; b < L; b += 4) {
+                u32 word;
+                if (direct) word = __ldg(gw + (b >> 2));
+                else { const u32 hi = sw[(b >> 2) + 1]; word = __funnelshift_r(lo, hi, sh); lo = hi; }
+                const int nb = min(4, L - b);
+                if (nb < 4) { const u32 m = (1u << (8 * nb)) - 1u; word = (word & m) | (0x41414141u & ~m); }
+                const u32 x = (word >> 1) & 0x03030303u;
+                u32 v = x ^ ((x >> 1) & 0x01010101u);
+                const u32 t = v | (v >> 4);
+                const u32 rec = __byte_perm(0x54474341u, 0u, __byte_perm(t, 0u, 0x4420));
+                const u32 diff = word ^ rec;
+                if (diff) {
+                    for (int j = 0; j < nb; j++) {
+                        if ((diff >> (8 * j)) & 0xffu) {
+                            v &= ~(0xffu << (8 * j));
+                            if (((word >> (8 * j)) & 0xffu) == 'N') nm |= 1u << (L - 1 - (b + j)); else flags |= 2u;
+                        }
+                    }
+                }
+                const u32 p8 = (v * 0x40100401u) >> 24;          // v0<<6 | v1<<4 | v2<<2 | v3
+                code = (code << (2 * nb)) | (u64)(p8 >> (2 * (4 - nb)));
             }
             umi2[i] = code; nmask[i] = nm; if (nm) flags |= 1u;
             const i32 t = tid[i]; const i64 p = pos[i];

@@ -46,11 +46,12 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T *smem /* THREADS/32 + 1
 template <class T, class F>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums(F f, u64 n, T *tile_sums) {
     __shared__ T sm[SCAN_THREADS / 32 + 1];
-    u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+    // only the tile's sum is needed, so the tile is read striped (coalesced) rather than blocked
+    u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x;
     T s = 0;
 #pragma unroll
     for (int j = 0; j < SCAN_ITEMS; j++) {
-        u64 i = base + j;
+        u64 i = base + (u64)j * SCAN_THREADS;
         if (i < n) s += f(i);
     }
     T total;
@@ -77,11 +78,20 @@ __global__ void __launch_bounds__(1024) scan_spine(T *tile_sums, u64 ntiles, T *
 template <class G, class = void> struct scan_has_finish : std::false_type {};
 template <class G> struct scan_has_finish<G, std::void_t<decltype(std::declval<G &>().finish())>> : std::true_type {};
 
+// consumers with dependent gathers (index -> payload) can issue them for all of a thread's elements up front:
+// prefetch(i, j) is called for every valid element before the scan, operator() then receives the slot j as well
+template <class G, class = void> struct scan_has_prefetch : std::false_type {};
+template <class G> struct scan_has_prefetch<G, std::void_t<decltype(std::declval<G &>().prefetch(u64(0), 0))>> : std::true_type {};
+
 template <class T, class F, class G>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply(F f, G g_in, u64 n, const T *tile_sums) {
     G g = g_in;
     __shared__ T sm[SCAN_THREADS / 32 + 1];
     u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+    if constexpr (scan_has_prefetch<G>::value) {
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; j++) if (base + j < n) g.prefetch(base + j, j);
+    }
     T v[SCAN_ITEMS];
     T s = 0;
 #pragma unroll
@@ -95,7 +105,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply(F f, G g_in, u64 n, c
 #pragma unroll
     for (int j = 0; j < SCAN_ITEMS; j++) {
         u64 i = base + j;
-        if (i < n) g(i, v[j], ex);
+        if (i < n) {
+            if constexpr (scan_has_prefetch<G>::value) g(i, v[j], ex, j); else g(i, v[j], ex);
+        }
         ex += v[j];
     }
     if constexpr (scan_has_finish<G>::value) g.finish();

@@ -224,19 +224,21 @@ static int push_common(umigpu_ctx *ctx, u64 n, const i32 *tid, const i64 *pos, c
     const int L = (int)ctx->cfg.umi_len;
     cudaStream_t s = ctx->stream;
     STAGE_BEGIN(UMIGPU_STAGE_PACK);
-    CK(ctx->d_tid.reserve_keep(tot * 4, old * 4, s));
-    CK(ctx->d_pos.reserve_keep(tot * 8, old * 8, s));
-    CK(ctx->d_rev.reserve_keep(tot, old, s));
+    // a first chunk that already lives in HBM is borrowed, not copied (the caller keeps it valid until fetch/reset);
+    // a later chunk makes reserve_keep copy the borrowed part into owned storage
+    const bool zc = kind == cudaMemcpyDeviceToDevice && old == 0;
+    auto put = [&](DevBuf &b, const void *src, size_t esz) -> cudaError_t {
+        if (zc && src) { b.borrow(src); return cudaSuccess; }
+        cudaError_t e = b.reserve_keep(tot * esz, old * esz, s);
+        if (e != cudaSuccess) return e;
+        return src ? cudaMemcpyAsync((char *)b.p + old * esz, src, n * esz, kind, s) : cudaMemsetAsync((char *)b.p + old * esz, 0, n * esz, s);
+    };
+    CK(put(ctx->d_tid, tid, 4)); CK(put(ctx->d_pos, pos, 8)); CK(put(ctx->d_rev, rev, 1));
+    if (score) CK(put(ctx->d_score, score, 4));
+    if (weight) CK(put(ctx->d_weight, weight, 4));
+    if (tlen) CK(put(ctx->d_tlen, tlen, 8));
     CK(ctx->d_umi2.reserve_keep(tot * 8, old * 8, s));
     CK(ctx->d_nmask.reserve_keep(tot * 4, old * 4, s));
-    if (score) CK(ctx->d_score.reserve_keep(tot * 4, old * 4, s));
-    if (weight) CK(ctx->d_weight.reserve_keep(tot * 4, old * 4, s));
-    if (tlen) { CK(ctx->d_tlen.reserve_keep(tot * 8, old * 8, s)); CK(cudaMemcpyAsync(ctx->d_tlen.as<i64>() + old, tlen, n * 8, kind, s)); }
-    if (tid) CK(cudaMemcpyAsync(ctx->d_tid.as<i32>() + old, tid, n * 4, kind, s)); else CK(cudaMemsetAsync(ctx->d_tid.as<i32>() + old, 0, n * 4, s));
-    if (pos) CK(cudaMemcpyAsync(ctx->d_pos.as<i64>() + old, pos, n * 8, kind, s)); else CK(cudaMemsetAsync(ctx->d_pos.as<i64>() + old, 0, n * 8, s));
-    if (rev) CK(cudaMemcpyAsync(ctx->d_rev.as<u8>() + old, rev, n, kind, s)); else CK(cudaMemsetAsync(ctx->d_rev.as<u8>() + old, 0, n, s));
-    if (score) CK(cudaMemcpyAsync(ctx->d_score.as<i32>() + old, score, n * 4, kind, s));
-    if (weight) CK(cudaMemcpyAsync(ctx->d_weight.as<i32>() + old, weight, n * 4, kind, s));
     const u8 *d_ascii = ascii;
     if (kind == cudaMemcpyHostToDevice) {
         CK(ctx->d_ascii.reserve(n * L));
@@ -459,7 +461,8 @@ static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, E
     CK(ctx->d_blkfirst.reserve((size_t)std::max<u32>(n_blocks, 1) * 4));
     CK(ctx->d_blkcnt.reserve((size_t)std::max<u32>(n_blocks, 1) * 4));
     LAUNCH(tile_summary_kernel, grid_for((u64)n_tiles * 32, 256), 256, n_tiles, B, (const u32 *)ctx->d_tileoff.p, v.bstart, v.planes, v.nplane, L,
-           ctx->d_tsum.as<u32>(), (const u32 *)ctx->d_blkoff.p, ctx->d_bsum.as<u32>(), ctx->d_blkfirst.as<u32>(), ctx->d_blkcnt.as<u32>());
+           ctx->d_tsum.as<u32>(), (const u32 *)ctx->d_blkoff.p, ctx->d_bsum.as<u32>(), ctx->d_blkfirst.as<u32>(), ctx->d_blkcnt.as<u32>(),
+           v.ucode, mi);
     CK(ctx->d_items.reserve((size_t)n_cand * sizeof(TileItem)));
     CK(cudaMemsetAsync(&sc->n_items, 0, 4, ctx->stream));
     CK(cudaMemsetAsync(&sc->scratch2, 0, 8, ctx->stream));
