@@ -431,3 +431,40 @@ def test_error_convention_and_call_order():
     assert lib.umigpu_push_reads(ctx._h, 3, None, None, None, None, None, None, 0) == L.ERR_ARG
     assert lib.umigpu_stage_ms(ctx._h, 99, C.byref(C.c_float())) == L.ERR_ARG
     ctx.close()
+
+
+def _run_flags(d, cfg, algo, flags):
+    with umigpu.Context(cfg["umi_len"], cfg["k"], 0.5, algo, umigpu.MERGE_AVGQUAL, flags=flags) as ctx:
+        ctx.push_reads(d["tid"], d["pos"], d["rev"], d["umi"], d["score"])
+        return ctx.finish()
+
+
+@pytest.mark.parametrize("name,brute", [("C2", umigpu.FLAG_KERNEL_DIRECT | umigpu.FLAG_NO_CULL | umigpu.FLAG_NO_MULTI_INDEX),
+                                        ("C4", umigpu.FLAG_KERNEL_TILES | umigpu.FLAG_NO_CULL | umigpu.FLAG_NO_MULTI_INDEX)])
+def test_full_size_baseline_configs_production_equals_brute_force(name, brute):
+    """BASELINE.json configs at FULL size (C2: 50 M reads, hottest locus 1.5 M unique UMIs; C4: one bucket of 11.7 M).  The
+    oracle cannot run here, so the production neighbour search (multi-index passes, exact culling, block-pair lists)
+    is held against the all-pairs kernels that are themselves oracle-checked at small sizes: every one of the
+    ~1.7e12 (C2) / 6.8e13 (C4) unordered pairs is evaluated, nothing is culled — kept lists and edge counts must be identical.
+    Plus the size-independent properties: partition invariance (buckets are independent), ascending unique output."""
+    import torch
+    d, cfg = synth.generate_config(name, device="cuda", scale=1.0)
+    kept, _, ctr = _run_flags(d, cfg, umigpu.ALGO_DIR, 0)
+    bkept, _, bctr = _run_flags(d, cfg, umigpu.ALGO_DIR, brute)
+    assert bctr["pairs_evaluated"] >= bctr["unordered_pairs"] > 1e12          # really all pairs
+    assert ctr["pairs_evaluated"] < bctr["pairs_evaluated"] / 20               # and the production path really culls
+    assert ctr["n_edges"] == bctr["n_edges"] and ctr["n_kept"] == bctr["n_kept"]
+    assert np.array_equal(kept, bkept)
+    assert (np.diff(kept.astype(np.int64)) > 0).all()
+    for key in ("total_reads", "n_buckets", "total_umis", "max_umis"):
+        assert ctr[key] == bctr[key]
+    if name == "C2":
+        # partition invariance: deduplicating the reads of even and odd positions separately gives the same survivors
+        parts = []
+        for par in (0, 1):
+            sel = torch.nonzero((d["pos"] & 1) == par).squeeze(1)
+            sub = {k2: v[sel].contiguous() for k2, v in d.items()}
+            pk, _, _ = _run_flags(sub, cfg, umigpu.ALGO_DIR, 0)
+            parts.append(sel.cpu().numpy()[pk.astype(np.int64)])
+        merged = np.sort(np.concatenate(parts)).astype(np.uint64)
+        assert np.array_equal(merged, kept)

@@ -111,11 +111,34 @@ __global__ void __launch_bounds__(256) small_buckets_kernel(u32 n_buckets, const
             const bool v = lane < nb;
             const uint2 p = v ? planes[s + lane] : make_uint2(0u, 0u);
             const u32 pn = (v && nplane) ? nplane[s + lane] : 0u;
+            u32 hm = 0;                                   // bit j: UMI j (> lane) is within k of this lane's UMI
             for (u32 j = 1; j < nb; j++) {
                 const u32 q0 = __shfl_sync(0xffffffffu, p.x, j), q1 = __shfl_sync(0xffffffffu, p.y, j);
                 const u32 qn = __shfl_sync(0xffffffffu, pn, j);
                 const u32 m = (p.x ^ q0) | (p.y ^ q1) | (pn ^ qn);
-                if (lane < j && __popc(m) <= k) record_hit(es, s + lane, s + j);
+                if (lane < j && __popc(m) <= k) hm |= 1u << j;
+            }
+            if (__any_sync(0xffffffffu, hm != 0)) {
+                // the count rule (directional.rs:38) for every hit, then ONE reservation per bucket: a global atomic per
+                // hit serialises on the single edge counter
+                const i32 fa = v ? es.freq[s + lane] : 0, ta = v ? es.thr[s + lane] : 0;
+                u32 abm = 0, bam = 0;
+                for (u32 j = 1; j < nb; j++) {
+                    const i32 fj = __shfl_sync(0xffffffffu, fa, j), tj = __shfl_sync(0xffffffffu, ta, j);
+                    if ((hm >> j) & 1u) { if (fj <= ta) abm |= 1u << j; if (fa <= tj) bam |= 1u << j; }
+                }
+                const u32 cnt = __popc(abm) + __popc(bam);
+                u32 inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (u32)o) inc += t; }
+                const u32 total = __shfl_sync(0xffffffffu, inc, 31);
+                if (total) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(es.count, (unsigned long long)total);
+                    base = __shfl_sync(0xffffffffu, base, 0) + inc - cnt;
+                    while (abm) { const u32 j = __ffs(abm) - 1; abm &= abm - 1; if (base < es.cap) es.edges[base] = make_uint2(s + lane, s + j); base++; }
+                    while (bam) { const u32 j = __ffs(bam) - 1; bam &= bam - 1; if (base < es.cap) es.edges[base] = make_uint2(s + j, s + lane); base++; }
+                }
             }
             np = (u64)nb * (nb - 1) / 2;
         }

@@ -24,26 +24,35 @@ __global__ void __launch_bounds__(256) onehot_build_kernel(u32 n_groups /* 4 per
                                                            const u32 *__restrict__ nplane, int L, int LP, u32 *__restrict__ eq) {
     constexpr int XS = HASN ? 8 : 4;
     constexpr int NLET = HASN ? 5 : 4;
-    const u32 g = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = lane_id();
-    if (g >= n_groups) return;
-    const u32 gb = g >> 2, c = (g & 3) * 32 + lane;
-    const bool valid = c < blk_cnt[gb];
-    const u32 uid = blk_first[gb] + c;
-    const uint2 p = valid ? planes[uid] : make_uint2(0u, 0u);
-    const u32 pn = (HASN && valid) ? nplane[uid] : 0u;
-    u32 *dst = eq + (u64)gb * LP * XS * 4 + (g & 3);
-    for (int j = 0; j < LP; j++) {
-        u32 letter = ((p.y >> j) & 1u) * 2u + ((p.x >> j) & 1u);
-        if (HASN && ((pn >> j) & 1u)) letter = 4u;
-        if (!valid) letter = 15u;                 // padding column: matches no letter at any real position
-        u32 v = 0;
+    // one warp per 128-UMI block: lane x collects the four 32-UMI groups' words of letter x and stores them as one
+    // 16-byte vector, so every position is written as XS consecutive uint4
+    const u32 gb = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = lane_id();
+    if (gb >= (n_groups >> 2)) return;
+    const u32 cnt = blk_cnt[gb], first = blk_first[gb];
+    uint2 p[4]; u32 pn[4];
 #pragma unroll
-        for (int x = 0; x < NLET; x++) {
-            u32 b = __ballot_sync(0xffffffffu, letter == (u32)x);
-            if (lane == (u32)x) v = b;
+    for (int g = 0; g < 4; g++) {
+        const u32 c = g * 32 + lane;
+        p[g] = c < cnt ? planes[first + c] : make_uint2(0u, 0u);
+        pn[g] = (HASN && c < cnt) ? nplane[first + c] : 0u;
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(eq) + (u64)gb * LP * XS;
+    for (int j = 0; j < LP; j++) {
+        u32 v[4];
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            u32 letter = ((p[g].y >> j) & 1u) * 2u + ((p[g].x >> j) & 1u);
+            if (HASN && ((pn[g] >> j) & 1u)) letter = 4u;
+            if (g * 32 + lane >= cnt) letter = 15u;       // padding column: matches no letter at any real position
+            u32 w = 0;
+#pragma unroll
+            for (int x = 0; x < NLET; x++) {
+                u32 b = __ballot_sync(0xffffffffu, letter == (u32)x);
+                if (lane == (u32)x) w = b;
+            }
+            v[g] = j >= L ? 0xffffffffu : w;              // positions beyond umi_len always match
         }
-        if (j >= L) v = 0xffffffffu;              // positions beyond umi_len always match
-        if (lane < (u32)XS) dst[(j * XS + lane) * 4] = v;
+        if (lane < (u32)XS) dst[j * XS + lane] = make_uint4(v[0], v[1], v[2], v[3]);
     }
 }
 

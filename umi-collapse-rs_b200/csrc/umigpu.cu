@@ -490,9 +490,9 @@ static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, E
         if (!is_dense) {
             const int LP = blk_lp(L), XS = has_n ? 8 : 4;
             CK(ctx->d_eq.reserve((size_t)std::max<u32>(n_blocks, 1) * LP * XS * 16));
-            if (has_n) LAUNCH(onehot_build_kernel<true>, grid_for((u64)n_blocks * 4 * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
+            if (has_n) LAUNCH(onehot_build_kernel<true>, grid_for((u64)n_blocks * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
                               (const u32 *)ctx->d_blkcnt.p, v.planes, v.nplane, L, LP, ctx->d_eq.as<u32>());
-            else       LAUNCH(onehot_build_kernel<false>, grid_for((u64)n_blocks * 4 * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
+            else       LAUNCH(onehot_build_kernel<false>, grid_for((u64)n_blocks * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
                               (const u32 *)ctx->d_blkcnt.p, v.planes, v.nplane, L, LP, ctx->d_eq.as<u32>());
             CK(ctx->d_pairs.reserve(std::max<u64>(n_pairs, 1) * sizeof(uint2)));
             CK(cudaMemsetAsync(&sc->n_block_pairs, 0, 8, ctx->stream));
