@@ -63,12 +63,9 @@ struct UniqueEmit {
         u32 r = pf_r[j];
         if (flag) {
             useg[uid] = (u32)i;
-            u64 code = sk.umi_bits == 64 ? sk.k0[i] : (sk.k0[i] & ((1ull << sk.umi_bits) - 1));
-            u32 p0, p1, pn;
-            code_to_planes(code, L, has_n, p0, p1, pn);
-            planes[uid] = make_uint2(p0, p1);
-            ucode[uid] = code;
-            if (has_n) nplane[uid] = pn;
+            // the bit planes are derived from ucode in unique_finalize_kernel (one thread per unique): here the
+            // conversion would run divergently, once per element slot of every warp that holds a head
+            ucode[uid] = sk.umi_bits == 64 ? sk.k0[i] : (sk.k0[i] & ((1ull << sk.umi_bits) - 1));
             bhead[uid] = (i == 0 || !sk.same_bucket(i, i - 1)) ? 1 : 0;
         }
         if (i == n - 1) useg[uid + 1] = (u32)n;
@@ -87,9 +84,16 @@ struct UniqueEmit {
 __global__ void __launch_bounds__(256) unique_finalize_kernel(
     u32 n_unique, const u32 *__restrict__ useg, const unsigned long long *__restrict__ rep, const i32 *__restrict__ wsum,
     float percentage, int algo_inf_thr, i32 *__restrict__ freq, i32 *__restrict__ thr, u32 *__restrict__ rep_idx,
-    unsigned long long *__restrict__ label) {
+    unsigned long long *__restrict__ label, const u64 *__restrict__ ucode, int L, int has_n, uint2 *__restrict__ planes,
+    u32 *__restrict__ nplane) {
     u32 u = blockIdx.x * 256 + threadIdx.x;
     if (u >= n_unique) return;
+    {
+        u32 p0, p1, pn;
+        code_to_planes(ucode[u], L, has_n, p0, p1, pn);
+        planes[u] = make_uint2(p0, p1);
+        if (has_n) nplane[u] = pn;
+    }
     i32 f = wsum ? wsum[u] : (i32)(useg[u + 1] - useg[u]);
     freq[u] = f;
     thr[u] = algo_inf_thr ? 0x7fffffff : dir_threshold(percentage, f);

@@ -631,7 +631,8 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     const bool inf_thr = force_inf_thr || cfg.algo == UMIGPU_ALGO_CC || cfg.algo == UMIGPU_ALGO_ADJ_UPSTREAM;
     LAUNCH(unique_finalize_kernel, grid_for(U, 256), 256, U, (const u32 *)ctx->d_useg.p, (const unsigned long long *)ctx->d_rep.p,
            weighted ? (const i32 *)ctx->d_wsum.p : (const i32 *)nullptr, cfg.percentage, inf_thr ? 1 : 0, ctx->d_freq.as<i32>(),
-           ctx->d_thr.as<i32>(), ctx->d_repidx.as<u32>(), ctx->d_label.as<unsigned long long>());
+           ctx->d_thr.as<i32>(), ctx->d_repidx.as<u32>(), ctx->d_label.as<unsigned long long>(), (const u64 *)ctx->d_ucode.p, lay.umi_len, lay.has_n,
+           ctx->d_planes.as<uint2>(), ctx->d_nplane.as<u32>());
     STAGE_END(UMIGPU_STAGE_UNIQUE);
 
     // ---- buckets + work list ----
