@@ -24,6 +24,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 #include <limits.h>
 
 #define ORACLE_OK            0
@@ -132,7 +133,7 @@ typedef struct {
     int32_t score;
 } uentry_t;
 
-static int g_umi_len_cmp;   /* comparator context (single-threaded oracle) */
+static _Thread_local int g_umi_len_cmp;   /* comparator context (per thread: the all-core variant sorts buckets concurrently) */
 
 static int cmp_canon(const void *pa, const void *pb) {
     const uentry_t *a = (const uentry_t *)pa, *b = (const uentry_t *)pb;
@@ -338,6 +339,54 @@ static int merge_keep_existing(int merge, int32_t a_score, int32_t b_score) {
  * are truncated to that many canonical-first UMIs before clustering when > 0 (only used by the
  * bounded cpu_baseline timing; 0 = never truncate).
  */
+/* HOT LOOP B (deduplicate_sam.rs:207-233) over a shared bucket counter.  One worker = the reference (it clusters on one
+ * thread); oracle_set_threads(n > 1) is the "all-core" variant that SURVEY §8(d) asks to be reported beside
+ * it — buckets are independent, so they are handed out to n threads; this is NOT what the reference does. */
+static int g_oracle_threads = 1;
+void oracle_set_threads(int n) { g_oracle_threads = n; }
+typedef struct {
+    int64_t nb; const int64_t *bstart, *slot; const uentry_t *ue; const int64_t *read_uid;
+    int umi_len, algo, k; float percentage; int64_t max_bucket;
+    uint8_t *kept_flag; int64_t *uroot;
+    volatile int64_t next; volatile int rc;
+} bucket_job_t;
+typedef struct { bucket_job_t *job; oracle_counters ctr; } bucket_worker_t;
+
+static void *bucket_worker(void *arg) {
+    bucket_worker_t *w = (bucket_worker_t *)arg;
+    bucket_job_t *J = w->job;
+    oracle_counters *ctr = &w->ctr;
+    for (;;) {
+        int64_t b = __atomic_fetch_add(&J->next, 1, __ATOMIC_RELAXED);
+        if (b >= J->nb || J->rc) break;
+        int64_t nbu = J->bstart[b + 1] - J->bstart[b];
+        ctr->total_umis += nbu;                                     /* :217 */
+        if (nbu > ctr->max_umis) ctr->max_umis = nbu;               /* :218 */
+        ctr->unordered_pairs += (uint64_t)nbu * (uint64_t)(nbu - 1) / 2;
+        uentry_t *e = (uentry_t *)malloc(sizeof(uentry_t) * nbu);
+        uint8_t *keep = (uint8_t *)malloc(nbu);
+        int32_t *label = (int32_t *)malloc(sizeof(int32_t) * nbu);
+        if (!e || !keep || !label) { J->rc = ORACLE_ERR_NOMEM; break; }
+        for (int64_t j = 0; j < nbu; j++) { e[j] = J->ue[J->slot[J->bstart[b] + j]]; }
+        g_umi_len_cmp = J->umi_len;
+        qsort(e, nbu, sizeof(uentry_t), cmp_canon);
+        int64_t ncl = nbu;
+        if (J->max_bucket > 0 && ncl > J->max_bucket) ncl = J->max_bucket;
+        int rc = cluster_entries(e, ncl, J->umi_len, J->algo, J->k, J->percentage, keep, label, &ctr->dist_calls);
+        if (rc) { J->rc = rc; break; }
+        for (int64_t j = 0; j < ncl; j++) {
+            if (keep[j]) { J->kept_flag[e[j].rep] = 1; ctr->n_kept++; }   /* :219, :227-231 */
+        }
+        if (J->uroot) {
+            /* map entries back to unique ids through their representative's read_uid */
+            for (int64_t j = 0; j < ncl; j++)
+                J->uroot[J->read_uid[e[j].rep]] = label[j] < 0 ? -1 : e[label[j]].rep;
+        }
+        free(e); free(keep); free(label);
+    }
+    return NULL;
+}
+
 /* tlen == NULL: Align::Unpaired(Alignment), deduplicate_sam.rs:141-145; otherwise Align::Paired(PairedAlignment)
  * whose Eq/Hash add the template length, deduplicate_sam.rs:133-139 and :545-600. */
 int oracle_dedup_paired(int64_t n, const int32_t *tid, const int64_t *pos, const uint8_t *rev, const int64_t *tlen,
@@ -422,32 +471,27 @@ int oracle_dedup_paired(int64_t n, const int32_t *tid, const int64_t *pos, const
     for (int64_t u = 0; u < nu; u++) uroot[u] = -1;
     ctr->n_buckets = nb;
 
-    for (int64_t b = 0; b < nb; b++) {                              /* HOT LOOP B, deduplicate_sam.rs:207 */
-        int64_t nbu = bstart[b + 1] - bstart[b];
-        ctr->total_umis += nbu;                                     /* :217 */
-        if (nbu > ctr->max_umis) ctr->max_umis = nbu;               /* :218 */
-        ctr->unordered_pairs += (uint64_t)nbu * (uint64_t)(nbu - 1) / 2;
-        uentry_t *e = (uentry_t *)malloc(sizeof(uentry_t) * nbu);
-        int64_t *eid = (int64_t *)malloc(sizeof(int64_t) * nbu);
-        uint8_t *keep = (uint8_t *)malloc(nbu);
-        int32_t *label = (int32_t *)malloc(sizeof(int32_t) * nbu);
-        if (!e || !eid || !keep || !label) return ORACLE_ERR_NOMEM;
-        for (int64_t j = 0; j < nbu; j++) { e[j] = ue[slot[bstart[b] + j]]; }
-        g_umi_len_cmp = umi_len;
-        qsort(e, nbu, sizeof(uentry_t), cmp_canon);
-        int64_t ncl = nbu;
-        if (max_bucket_umis_to_cluster > 0 && ncl > max_bucket_umis_to_cluster) ncl = max_bucket_umis_to_cluster;
-        int rc = cluster_entries(e, ncl, umi_len, algo, k, percentage, keep, label, &ctr->dist_calls);
-        if (rc) return rc;
-        for (int64_t j = 0; j < ncl; j++) {
-            if (keep[j]) { kept_flag[e[j].rep] = 1; ctr->n_kept++; }   /* :219, :227-231 */
+    {
+        bucket_job_t job;
+        job.nb = nb; job.bstart = bstart; job.slot = slot; job.ue = ue; job.read_uid = read_uid; job.umi_len = umi_len; job.algo = algo;
+        job.k = k; job.percentage = percentage; job.max_bucket = max_bucket_umis_to_cluster; job.kept_flag = kept_flag;
+        job.uroot = per_read_root ? uroot : NULL; job.next = 0; job.rc = 0;
+        int nt = g_oracle_threads < 1 ? 1 : g_oracle_threads;
+        if (nt > 256) nt = 256;
+        bucket_worker_t wk[256];
+        pthread_t th[256];
+        for (int t = 0; t < nt; t++) { wk[t].job = &job; memset(&wk[t].ctr, 0, sizeof(oracle_counters)); }
+        if (nt == 1) bucket_worker(&wk[0]);                          /* the reference: one clustering thread */
+        else {
+            for (int t = 0; t < nt; t++) pthread_create(&th[t], NULL, bucket_worker, &wk[t]);
+            for (int t = 0; t < nt; t++) pthread_join(th[t], NULL);
         }
-        if (per_read_root) {
-            /* map entries back to unique ids through their representative's read_uid */
-            for (int64_t j = 0; j < ncl; j++)
-                uroot[read_uid[e[j].rep]] = label[j] < 0 ? -1 : e[label[j]].rep;
+        if (job.rc) return job.rc;
+        for (int t = 0; t < nt; t++) {
+            ctr->total_umis += wk[t].ctr.total_umis; ctr->unordered_pairs += wk[t].ctr.unordered_pairs;
+            ctr->n_kept += wk[t].ctr.n_kept; ctr->dist_calls += wk[t].ctr.dist_calls;
+            if (wk[t].ctr.max_umis > ctr->max_umis) ctr->max_umis = wk[t].ctr.max_umis;
         }
-        free(e); free(eid); free(keep); free(label);
     }
     int64_t w = 0;
     for (int64_t i = 0; i < n; i++) if (kept_flag[i]) kept_out[w++] = i;

@@ -82,6 +82,11 @@ def dedup(tid, pos, rev, umi, score, algo, merge, k, p, want_roots=False, max_bu
     return kept[: ctr.n_kept].copy(), (roots[:n].copy() if want_roots else None), ctr.as_dict()
 
 
+def set_threads(n: int):
+    """1 = the reference (one clustering thread); > 1 = the all-core variant (buckets handed out to n threads)."""
+    lib().oracle_set_threads(int(n))
+
+
 def avg_qual(q: np.ndarray) -> int:
     q = np.ascontiguousarray(q, np.uint8)
     return lib().oracle_avg_qual(_p(q), len(q))

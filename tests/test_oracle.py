@@ -212,3 +212,16 @@ def test_paired_key_c_oracle_matches_literal():
             assert a_ctr["n_buckets"] == b_ctr["n_buckets"] and a_ctr["total_umis"] == b_ctr["total_umis"]
         u_kept, _, u_ctr = O.dedup(tid, pos, rev, arr(umi), score, 0, O.MERGE_AVGQUAL, 1, 0.5)
         assert u_ctr["n_buckets"] < b_ctr["n_buckets"]
+
+
+def test_all_core_variant_equals_single_thread():
+    """oracle_set_threads(n): buckets are independent, so handing them to n threads changes nothing but the time."""
+    rng = random.Random(31)
+    tid, pos, rev, umi, score = _random_reads(rng, 4000, 6, 40)
+    a = O.dedup(tid, pos, rev, arr(umi), score, O.ALGO_DIR, O.MERGE_AVGQUAL, 1, 0.5, want_roots=True)
+    O.set_threads(4)
+    try:
+        b = O.dedup(tid, pos, rev, arr(umi), score, O.ALGO_DIR, O.MERGE_AVGQUAL, 1, 0.5, want_roots=True)
+    finally:
+        O.set_threads(1)
+    assert a[0].tolist() == b[0].tolist() and a[1].tolist() == b[1].tolist() and a[2] == b[2]
