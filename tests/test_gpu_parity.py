@@ -468,3 +468,52 @@ def test_full_size_baseline_configs_production_equals_brute_force(name, brute):
             parts.append(sel.cpu().numpy()[pk.astype(np.int64)])
         merged = np.sort(np.concatenate(parts)).astype(np.uint64)
         assert np.array_equal(merged, kept)
+
+
+def test_two_phase_clustering_forced_matches_oracle(monkeypatch):
+    """K6's second scheme (hook + jump on mutual edges, contracted propagation, expand) only takes over on graphs with
+    >= 8 Mi edges that plain sweeps do not settle — sizes the oracle cannot reach.  The test knobs force it on small
+    inputs, where it must reproduce the oracle's kept reads and cluster roots exactly (long chains, ties, saturated
+    UMI spaces)."""
+    monkeypatch.setenv("UMIGPU_SV_MIN_EDGES", "0")
+    monkeypatch.setenv("UMIGPU_PLAIN_ROUNDS", "0")
+    rng = random.Random(77)
+    total_sweeps = 0
+    for trial in range(24):
+        L = rng.choice([4, 5, 6, 8, 10])
+        alphabet = rng.choice(["ACGT", "AC", "ACG"])
+        n = rng.choice([300, 3000, 9000])
+        pool = ["".join(rng.choice(alphabet) for _ in range(L)) for _ in range(rng.choice([2, 30, 300]))]
+        umis = []
+        for _ in range(n):
+            u = list(rng.choice(pool))
+            for _ in range(rng.choice([0, 1, 1, 2])):
+                u[rng.randrange(L)] = rng.choice(alphabet)
+            umis.append("".join(u))
+        d = dict(tid=np.zeros(n, np.int32), pos=np.array([rng.randrange(3) for _ in range(n)], np.int64),
+                 rev=np.zeros(n, np.uint8), umi=arr(umis), score=np.array([rng.randrange(0, 40) for _ in range(n)], np.int32))
+        for algo in (umigpu.ALGO_DIR, umigpu.ALGO_CC):
+            ctr = check_against_oracle(d, algo, umigpu.MERGE_AVGQUAL, rng.choice([1, 1, 2]), rng.choice([0.5, 0.9]), labels=True)
+            total_sweeps += ctr["n_sweeps"]
+    assert total_sweeps > 0
+    # a long chain of frequency-1 UMIs (each one substitution from the next): the worst case for plain sweeps
+    L = 12
+    chain = ["A" * L]
+    for i in range(1, 400):
+        u = list(chain[-1]); u[i % L] = "ACGT"[("ACGT".index(u[i % L]) + 1) % 4]; chain.append("".join(u))
+    n = len(chain)
+    d = dict(tid=np.zeros(n, np.int32), pos=np.zeros(n, np.int64), rev=np.zeros(n, np.uint8), umi=arr(chain), score=np.full(n, 30, np.int32))
+    for algo in (umigpu.ALGO_DIR, umigpu.ALGO_CC):
+        check_against_oracle(d, algo, umigpu.MERGE_AVGQUAL, 1, 0.5, labels=True)
+
+
+def test_full_size_two_phase_equals_plain_sweeps(monkeypatch):
+    """C5 at full size (200 M reads, hottest locus 5.1 M unique UMIs, 3e7 edges in long chains): the two-phase clustering
+    that production takes here and plain label sweeps run to their fixpoint must keep exactly the same reads."""
+    d, cfg = synth.generate_config("C5", device="cuda", scale=1.0)
+    kept, _, ctr = _run_flags(d, cfg, umigpu.ALGO_DIR, 0)
+    monkeypatch.setenv("UMIGPU_SV_MIN_EDGES", str(1 << 62))
+    pkept, _, pctr = _run_flags(d, cfg, umigpu.ALGO_DIR, 0)
+    assert ctr["n_edges"] == pctr["n_edges"] > (8 << 20)
+    assert np.array_equal(kept, pkept) and ctr["n_kept"] == pctr["n_kept"]
+    assert pctr["n_sweeps"] != ctr["n_sweeps"]        # really two different schedules

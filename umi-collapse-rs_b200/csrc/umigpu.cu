@@ -780,10 +780,15 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
       // Plain sweeps first: most inputs converge in a handful of them and they have the lowest cost per sweep.
       // An input with long mutual chains (a hot locus with millions of frequency-1 UMIs) does not: after 8 sweeps the
       // labels are reset and the two-phase scheme (O(log) rounds) takes over.
+      // test knobs: UMIGPU_SV_MIN_EDGES (default 8 Mi) = smallest edge count that may switch to the two-phase scheme,
+      // UMIGPU_PLAIN_ROUNDS (default 2) = rounds of 4 plain sweeps tried first
       bool converged = false;
-      const bool big_graph = n_edges >= (8u << 20);
+      const char *e_sv = getenv("UMIGPU_SV_MIN_EDGES"), *e_pr = getenv("UMIGPU_PLAIN_ROUNDS");
+      const u64 sv_min = e_sv ? strtoull(e_sv, nullptr, 10) : (u64)(8u << 20);
+      const int plain_rounds = e_pr ? atoi(e_pr) : 2;
+      const bool big_graph = n_edges >= sv_min;
       if (big_graph) { CK(ctx->d_prio.reserve((size_t)U * 8)); CK(cudaMemcpyAsync(ctx->d_prio.p, label, (size_t)U * 8, cudaMemcpyDeviceToDevice, ctx->stream)); }
-      for (int round = 0; !converged && (round < 2 || !big_graph); round++) {
+      for (int round = 0; !converged && (round < plain_rounds || !big_graph); round++) {
           CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
           for (int i = 0; i < 4; i++) LAUNCH(label_sweep_kernel, egrid, 256, edges, n_edges, label, sc);
           sweeps += 4;

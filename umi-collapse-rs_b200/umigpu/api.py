@@ -128,6 +128,11 @@ class Context:
                 a = a.contiguous()
             arrs.append(a)
         self._keepalive.append(arrs)     # async copies: keep the sources alive until fetch/reset
+        if dev:
+            # the context works on its own (non-blocking) stream: the kernels that produced the tensors on torch's
+            # stream must have finished before the library reads them
+            import torch
+            torch.cuda.current_stream(tid.device).synchronize()
         fn = self._lib.umigpu_push_reads_device if dev else self._lib.umigpu_push_reads
         L.check(fn(self._h, n, *[_ptr(a) for a in arrs], first_read_index), self._h)
 
