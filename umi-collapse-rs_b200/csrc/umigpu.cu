@@ -29,6 +29,8 @@ struct umigpu_ctx {
     umigpu_config cfg;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t side = nullptr;          // second stream: work that is independent of the main neighbour pass overlaps it
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     u64 launches = 0;
     int num_sms = NUM_SMS_B200;
@@ -135,6 +137,8 @@ extern "C" int umigpu_create(const umigpu_config *cfg, umigpu_ctx **out) {
     ctx->num_sms = sms > 0 ? sms : NUM_SMS_B200;
     if (cfg->stream) { ctx->stream = (cudaStream_t)cfg->stream; ctx->own_stream = false; }
     else { CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    CKC(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     for (int s = 0; s < UMIGPU_N_STAGES; s++) { CKC(cudaEventCreate(&ctx->ev[s][0])); CKC(cudaEventCreate(&ctx->ev[s][1])); }
     CKC(ctx->d_sc.reserve(sizeof(DevScalars)));
     CKC(cudaMallocHost((void **)&ctx->h_sc, sizeof(DevScalars)));
@@ -163,6 +167,9 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
     DevBuf *bb[] = {&ctx->d_bamraw, &ctx->d_bamoff, &ctx->d_btid, &ctx->d_bpos, &ctx->d_brev, &ctx->d_bumi2, &ctx->d_bnmask, &ctx->d_bscore, &ctx->d_bvalid, &ctx->d_orig};
     for (DevBuf *b : bb) b->release();
     for (int s = 0; s < UMIGPU_N_STAGES; s++) { if (ctx->ev[s][0]) cudaEventDestroy(ctx->ev[s][0]); if (ctx->ev[s][1]) cudaEventDestroy(ctx->ev[s][1]); }
+    if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -701,16 +708,10 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
             ctx->ctr.n_tile_candidates = ctx->ctr.n_tile_items = ctx->ctr.n_block_pairs = 0;
             ctx->used_direct = false; ctx->direct_pairs = 0;
             EdgeSink es{ctx->d_edges.as<uint2>(), (unsigned long long *)&sc->edge_count, cap, ctx->d_freq.as<i32>(), ctx->d_thr.as<i32>()};
-            LAUNCH(small_buckets_kernel, grid_for((u64)B * 32, 256), 256, B, (const u32 *)ctx->d_bstart.p, (const uint2 *)ctx->d_planes.p,
-                   has_n ? (const u32 *)ctx->d_nplane.p : (const u32 *)nullptr, cfg.k, es, (unsigned long long *)&sc->pairs_eval);
-            // pass 0: every bucket with more than 32 unique UMIs in the main order (big buckets filtered on part 0)
-            MiParams mi = mi0; mi.part = mi_on ? 0 : -1;
-            bool dense = false;
-            rc = neighbour_pass(ctx, main_view, mi, es, has_n, cull, allow_blocks, &dense);
-            if (rc) return rc;
-            if (dense) { mi_on = false; continue; }          // culling does not thin this input out: restart without multi-index
-            // passes 1..k: big buckets only, re-ordered so that part q is the most significant
-            for (int q = 1; mi_on && q < P; q++) {
+            // Fork: the small buckets and the re-ordering of the big buckets for pass 1 (keys, radix sort, gather) depend on
+            // nothing pass 0 produces, have no host synchronisation, and are latency-bound: they run on the side stream
+            // while pass 0 (whose work-list construction waits on scalar read-backs) runs on the main one.
+            auto mi_prepare = [&](int q) -> int {
                 const int pbits = part_len[q] * bpb, rbits = bits_for(nbig - 1);
                 CK(ctx->d_key[0][0].reserve((size_t)m_big * 8)); CK(ctx->d_key[1][0].reserve((size_t)m_big * 8));
                 CK(ctx->d_idx[0].reserve((size_t)m_big * 4)); CK(ctx->d_idx[1].reserve((size_t)m_big * 4));
@@ -718,11 +719,39 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
                        (const u32 *)ctx->d_bstartbig.p, (const u64 *)ctx->d_ucode.p, part_lo[q] * bpb,
                        (unsigned long long)(pbits >= 64 ? ~0ull : ((1ull << pbits) - 1)), pbits, ctx->d_biguid.as<u32>(), ctx->d_key[0][0].as<u64>());
                 int cur = 0;
-                rc = run_sort(ctx, m_big, 1, rs_plan(pbits + rbits), &cur);
-                if (rc) return rc;
+                int r2 = run_sort(ctx, m_big, 1, rs_plan(pbits + rbits), &cur);
+                if (r2) return r2;
                 LAUNCH(mi_gather_kernel, grid_for(m_big, 256), 256, m_big, (const u32 *)ctx->d_idx[cur].p, (const u32 *)ctx->d_biguid.p,
                        (const uint2 *)ctx->d_planes.p, has_n ? (const u32 *)ctx->d_nplane.p : (const u32 *)nullptr, (const u64 *)ctx->d_ucode.p,
                        ctx->d_miplanes.as<uint2>(), ctx->d_minplane.as<u32>(), ctx->d_miucode.as<u64>(), ctx->d_miuid.as<u32>());
+                return UMIGPU_OK;
+            };
+            CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+            {
+                cudaStream_t main_stream = ctx->stream;
+                ctx->stream = ctx->side;
+                int r2 = [&]() -> int {
+                    LAUNCH(small_buckets_kernel, grid_for((u64)B * 32, 256), 256, B, (const u32 *)ctx->d_bstart.p, (const uint2 *)ctx->d_planes.p,
+                           has_n ? (const u32 *)ctx->d_nplane.p : (const u32 *)nullptr, cfg.k, es, (unsigned long long *)&sc->pairs_eval);
+                    if (mi_on && P > 1) return mi_prepare(1);
+                    return UMIGPU_OK;
+                }();
+                cudaError_t ej = cudaEventRecord(ctx->ev_join, ctx->side);
+                ctx->stream = main_stream;
+                if (r2) return r2;
+                CK(ej);
+            }
+            // pass 0: every bucket with more than 32 unique UMIs in the main order (big buckets filtered on part 0)
+            MiParams mi = mi0; mi.part = mi_on ? 0 : -1;
+            bool dense = false;
+            rc = neighbour_pass(ctx, main_view, mi, es, has_n, cull, allow_blocks, &dense);
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));      // join (also before a restart or an error return)
+            if (rc) return rc;
+            if (dense) { mi_on = false; continue; }          // culling does not thin this input out: restart without multi-index
+            // passes 1..k: big buckets only, re-ordered so that part q is the most significant
+            for (int q = 1; mi_on && q < P; q++) {
+                if (q > 1) { rc = mi_prepare(q); if (rc) return rc; }
                 const NView view{ctx->d_miplanes.as<uint2>(), has_n ? ctx->d_minplane.as<u32>() : (const u32 *)nullptr, ctx->d_miucode.as<u64>(),
                                  ctx->d_miuid.as<u32>(), ctx->d_bstartbig.as<u32>(), nbig};
                 mi.part = q;
