@@ -72,26 +72,47 @@ __global__ void __launch_bounds__(256) comp_from_label_kernel(u32 n_unique, cons
     u32 v = blockIdx.x * 256 + threadIdx.x;
     if (v < n_unique) comp[v] = (u32)label[v];
 }
-__global__ void __launch_bounds__(256) contracted_sweep_kernel(const uint2 *__restrict__ edges, u64 n_edges, const u32 *__restrict__ comp,
+// The contracted graph is materialised once: every edge becomes (comp[src], comp[dst]); edges inside a mutual component
+// (most edges of a hot locus) disappear.  Phase B then touches only this list: no per-sweep comp gathers, no pass over
+// all U labels.  *n_out is a device-resident count that the sweeps read (no host round trip).
+__global__ void __launch_bounds__(256) contract_edges_kernel(const uint2 *__restrict__ edges, u64 n_edges, const u32 *__restrict__ comp,
+                                                             uint2 *__restrict__ out, unsigned long long *n_out) {
+    const u64 stride = (u64)gridDim.x * 256;
+    const u64 rounds = (n_edges + stride - 1) / stride;          // every lane runs the same number of rounds (warp collectives)
+    for (u64 it = 0; it < rounds; it++) {
+        const u64 e = it * stride + (u64)blockIdx.x * 256 + threadIdx.x;
+        bool live = false; u32 cs = 0, cd = 0;
+        if (e < n_edges) { const uint2 ed = edges[e]; cs = comp[ed.x]; cd = comp[ed.y]; live = cs != cd; }
+        const u32 m = __ballot_sync(0xffffffffu, live);
+        if (m) {
+            unsigned long long base = 0;
+            if (lane_id() == 0) base = atomicAdd(n_out, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (live) out[base + __popc(m & lanemask_lt())] = make_uint2(cs, cd);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) contracted_sweep_kernel(const uint2 *__restrict__ cedges, const unsigned long long *__restrict__ n_ptr,
                                                                unsigned long long *label, DevScalars *sc) {
-    u64 stride = (u64)gridDim.x * 256;
+    const u64 n_edges = *n_ptr, stride = (u64)gridDim.x * 256;
     u32 any = 0;
     for (u64 e = (u64)blockIdx.x * 256 + threadIdx.x; e < n_edges; e += stride) {
-        uint2 ed = edges[e];
-        u32 cs = comp[ed.x], cd = comp[ed.y];
-        if (cs == cd) continue;
-        unsigned long long ms = label[cs];
-        if (ms < label[cd]) { atomicMin(&label[cd], ms); any = 1; }
+        const uint2 ed = cedges[e];
+        const unsigned long long ms = label[ed.x];
+        if (ms < label[ed.y]) { atomicMin(&label[ed.y], ms); any = 1; }
     }
     if (__any_sync(0xffffffffu, any) && lane_id() == 0) sc->changed = 1;
 }
-__global__ void __launch_bounds__(256) contracted_jump_kernel(u32 n_unique, const u32 *__restrict__ comp, unsigned long long *label, DevScalars *sc) {
-    u32 c = blockIdx.x * 256 + threadIdx.x;
+// pointer jumping on the contracted graph, driven by the edge list: only a destination's label can change
+__global__ void __launch_bounds__(256) contracted_jump_kernel(const uint2 *__restrict__ cedges, const unsigned long long *__restrict__ n_ptr,
+                                                              unsigned long long *label, DevScalars *sc) {
+    const u64 n_edges = *n_ptr, stride = (u64)gridDim.x * 256;
     u32 any = 0;
-    if (c < n_unique && comp[c] == c) {
-        unsigned long long l = label[c];
-        u32 r = comp[(u32)l];
-        if (r != c) { unsigned long long lr = label[r]; if (lr < l) { atomicMin(&label[c], lr); any = 1; } }
+    for (u64 e = (u64)blockIdx.x * 256 + threadIdx.x; e < n_edges; e += stride) {
+        const u32 c = cedges[e].y;
+        const unsigned long long l = label[c];
+        const u32 r = (u32)l;
+        if (r != c) { const unsigned long long lr = label[r]; if (lr < l) { atomicMin(&label[c], lr); any = 1; } }
     }
     if (__any_sync(0xffffffffu, any) && lane_id() == 0) sc->changed = 1;
 }

@@ -46,7 +46,7 @@ struct umigpu_ctx {
 
     DevBuf d_key[2][2], d_idx[2], d_hist, d_tiles;
     DevBuf d_useg, d_rep, d_planes, d_nplane, d_bhead, d_wsum, d_read_uid, d_freq, d_thr, d_repidx, d_label, d_prio;
-    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_tileoff, d_tsum, d_tilestate, d_bsum, d_blkoff, d_blkfirst, d_blkcnt, d_eq, d_pairs, d_comp, d_ucode, d_ubkt, d_brank, d_bigbid, d_bstartbig, d_biguid, d_miplanes, d_minplane, d_miucode, d_miuid;
+    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_tileoff, d_tsum, d_tilestate, d_bsum, d_blkoff, d_blkfirst, d_blkcnt, d_eq, d_pairs, d_comp, d_ucode, d_ubkt, d_brank, d_bigbid, d_bstartbig, d_biguid, d_miplanes, d_minplane, d_miucode, d_miuid, d_cedges;
 
     // results
     bool ran = false;
@@ -157,7 +157,7 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
                       &ctx->d_read_uid, &ctx->d_freq, &ctx->d_thr, &ctx->d_repidx, &ctx->d_label, &ctx->d_prio, &ctx->d_bstart, &ctx->d_itemoff,
                       &ctx->d_items, &ctx->d_edges, &ctx->d_keep, &ctx->d_state, &ctx->d_blocked, &ctx->d_bitmap, &ctx->d_kept, &ctx->d_roots,
                       &ctx->d_tileoff, &ctx->d_tsum, &ctx->d_tilestate, &ctx->d_bsum, &ctx->d_blkoff, &ctx->d_blkfirst, &ctx->d_blkcnt, &ctx->d_eq, &ctx->d_pairs, &ctx->d_comp, &ctx->d_ucode, &ctx->d_ubkt, &ctx->d_brank, &ctx->d_bigbid, &ctx->d_bstartbig, &ctx->d_biguid,
-                      &ctx->d_miplanes, &ctx->d_minplane, &ctx->d_miucode, &ctx->d_miuid};
+                      &ctx->d_miplanes, &ctx->d_minplane, &ctx->d_miucode, &ctx->d_miuid, &ctx->d_cedges};
     for (DevBuf *b : bufs) b->release();
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
     if (ctx->h_kept) cudaFreeHost(ctx->h_kept);
@@ -842,11 +842,15 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
             if (!ctx->h_sc->changed) break;
         }
         LAUNCH(comp_from_label_kernel, grid_for(U, 256), 256, U, (const unsigned long long *)label, comp);
+        CK(ctx->d_cedges.reserve(std::max<u64>(n_edges, 1) * sizeof(uint2)));
+        CK(cudaMemsetAsync(&sc->scratch, 0, 8, ctx->stream));
+        unsigned long long *n_c = (unsigned long long *)&sc->scratch;
+        LAUNCH(contract_edges_kernel, egrid, 256, edges, n_edges, (const u32 *)comp, ctx->d_cedges.as<uint2>(), n_c);
         for (;;) {
             CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
             for (int i = 0; i < 2; i++) {
-                LAUNCH(contracted_sweep_kernel, egrid, 256, edges, n_edges, (const u32 *)comp, label, sc);
-                LAUNCH(contracted_jump_kernel, grid_for(U, 256), 256, U, (const u32 *)comp, label, sc);
+                LAUNCH(contracted_sweep_kernel, egrid, 256, (const uint2 *)ctx->d_cedges.p, (const unsigned long long *)n_c, label, sc);
+                LAUNCH(contracted_jump_kernel, egrid, 256, (const uint2 *)ctx->d_cedges.p, (const unsigned long long *)n_c, label, sc);
             }
             sweeps += 2;
             rc = read_scalars(ctx);
