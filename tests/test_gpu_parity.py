@@ -508,9 +508,11 @@ def test_two_phase_clustering_forced_matches_oracle(monkeypatch):
 
 
 def test_full_size_two_phase_equals_plain_sweeps(monkeypatch):
-    """C5 at full size (200 M reads, hottest locus 5.1 M unique UMIs, 3e7 edges in long chains): the two-phase clustering
-    that production takes here and plain label sweeps run to their fixpoint must keep exactly the same reads."""
+    """C5 at full size (200 M reads, hottest locus 5.1 M unique UMIs, 3e7 edges, 40 plain sweeps): the two-phase
+    clustering (engaged after 8 sweeps through the test knob; production keeps sweeping up to 64) and plain label sweeps
+    run to their fixpoint must keep exactly the same reads."""
     d, cfg = synth.generate_config("C5", device="cuda", scale=1.0)
+    monkeypatch.setenv("UMIGPU_PLAIN_ROUNDS", "2")
     kept, _, ctr = _run_flags(d, cfg, umigpu.ALGO_DIR, 0)
     monkeypatch.setenv("UMIGPU_SV_MIN_EDGES", str(1 << 62))
     pkept, _, pctr = _run_flags(d, cfg, umigpu.ALGO_DIR, 0)

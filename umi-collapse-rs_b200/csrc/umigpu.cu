@@ -806,15 +806,17 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
         LAUNCH(mis_label_kernel, egrid, 256, edges, n_edges, prio, (const u8 *)ctx->d_state.p, label);
         LAUNCH(mis_keep_kernel, grid_for(U, 256), 256, U, (const u8 *)ctx->d_state.p, keep);
     } else {
-      // Plain sweeps first: most inputs converge in a handful of them and they have the lowest cost per sweep.
-      // An input with long mutual chains (a hot locus with millions of frequency-1 UMIs) does not: after 8 sweeps the
-      // labels are reset and the two-phase scheme (O(log) rounds) takes over.
+      // Plain sweeps first: they have the lowest cost per sweep, and in-place atomicMin lets a label travel several hops
+      // per sweep (C2 settles in 12, C5's 5 M-UMI locus in 40).  Measured on C5, neither the two-phase scheme after 8
+      // sweeps (11.5 ms) nor a pointer jump after every sweep (19.9 ms) beats 40 plain sweeps (10.5 ms), so the
+      // two-phase scheme (O(log) rounds whatever the chain length) is only the safety net for graphs that are still
+      // moving after 64 sweeps.
       // test knobs: UMIGPU_SV_MIN_EDGES (default 8 Mi) = smallest edge count that may switch to the two-phase scheme,
-      // UMIGPU_PLAIN_ROUNDS (default 2) = rounds of 4 plain sweeps tried first
+      // UMIGPU_PLAIN_ROUNDS (default 16) = rounds of 4 plain sweeps tried first
       bool converged = false;
       const char *e_sv = getenv("UMIGPU_SV_MIN_EDGES"), *e_pr = getenv("UMIGPU_PLAIN_ROUNDS");
       const u64 sv_min = e_sv ? strtoull(e_sv, nullptr, 10) : (u64)(8u << 20);
-      const int plain_rounds = e_pr ? atoi(e_pr) : 2;
+      const int plain_rounds = e_pr ? atoi(e_pr) : 16;
       const bool big_graph = n_edges >= sv_min;
       if (big_graph) { CK(ctx->d_prio.reserve((size_t)U * 8)); CK(cudaMemcpyAsync(ctx->d_prio.p, label, (size_t)U * 8, cudaMemcpyDeviceToDevice, ctx->stream)); }
       for (int round = 0; !converged && (round < plain_rounds || !big_graph); round++) {
