@@ -19,7 +19,9 @@
 #define RS_RB 8                  // digit width in bits (RS_RADIX bins)
 #endif
 #define RS_RADIX (1 << RS_RB)
-#define RS_THREADS 512
+#ifndef RS_THREADS
+#define RS_THREADS 512         // A/B builds: -DRS_THREADS=256 (4 CTAs/SM)
+#endif
 #define RS_WARPS   (RS_THREADS / 32)
 #define RS_MAX_PASSES 16
 #define RS_LB 8             // look-back window (predecessor tiles examined per round)
@@ -241,7 +243,7 @@ __device__ __forceinline__ void rs_onesweep_body(
 }
 
 template <int NW, int ITEMS>
-__global__ void __launch_bounds__(RS_THREADS, (NW == 1 ? 2 : 1)) radix_onesweep(
+__global__ void __launch_bounds__(RS_THREADS, (NW == 1 ? 1024 / RS_THREADS : 1)) radix_onesweep(
     KeyArr in, const u32 *__restrict__ idx_in, KeyArr out, u32 *__restrict__ idx_out, u64 n, int wsel, int sh, u32 mask,
     const u32 *__restrict__ digit_start, unsigned long long *tile_state /* [ntiles][RS_RADIX] */, u32 *ticket, u32 *err, int iota) {
     constexpr u32 TILE = RS_THREADS * ITEMS;
