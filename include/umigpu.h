@@ -131,6 +131,9 @@ enum {
 };
 
 const char *umigpu_version(void);
+/* Initialises CUDA on `device` (driver start-up + primary context: seconds on a large host).  Optional: a host that
+ * calls it from a helper thread before it starts reading its input hides that latency behind the I/O. */
+int umigpu_device_init(int32_t device);
 /* message of the last failing call on this thread (also valid when ctx == NULL) */
 const char *umigpu_last_error(const umigpu_ctx *ctx);
 

@@ -110,6 +110,13 @@ static inline u32 grid_for(u64 n, u32 block) { return (u32)std::max<u64>(1, ceil
 extern "C" const char *umigpu_version(void) { return "umigpu 0.1 (sm_100a)"; }
 extern "C" const char *umigpu_last_error(const umigpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
 
+extern "C" int umigpu_device_init(int32_t device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaFree(nullptr);
+    if (e != cudaSuccess) return fail(nullptr, UMIGPU_ERR_CUDA, "umigpu_device_init(%d): %s; libumigpu has no CPU fallback", device, cudaGetErrorString(e));
+    return UMIGPU_OK;
+}
+
 extern "C" int umigpu_create(const umigpu_config *cfg, umigpu_ctx **out) {
     umigpu_ctx *ctx = nullptr;
     if (!cfg || !out) return fail(nullptr, UMIGPU_ERR_ARG, "umigpu_create: null argument");

@@ -10,6 +10,10 @@
 // works, --mode fastq works (the reference's is an empty TODO, main.rs:49-51), --tag is implemented from its help
 // text (src/cli.rs:64-76; the reference collects ClusterTrackers and then writes nothing, deduplicate_sam.rs:236-239),
 // --paired follows deduplicate_sam.rs:96-129 (filters, on the device) and UcWriter::write_reversed (:409-462, mates).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -33,7 +37,12 @@ struct Cli {                                   // src/cli.rs:7-77 (same names, s
     int device = 0;
 };
 
-[[noreturn]] static void die(const std::string &msg) { fprintf(stderr, "umicollapse_gpu: %s\n", msg.c_str()); exit(2); }
+static std::thread *g_cuda_init = nullptr;     // CUDA start-up helper thread (main): joined before the process exits
+[[noreturn]] static void die(const std::string &msg) {
+    fprintf(stderr, "umicollapse_gpu: %s\n", msg.c_str());
+    if (g_cuda_init && g_cuda_init->joinable() && g_cuda_init->get_id() != std::this_thread::get_id()) g_cuda_init->join();
+    exit(2);
+}
 static void check(int rc, umigpu_ctx *ctx, const char *what) {
     if (rc != 0) die(std::string(what) + " failed (" + std::to_string(rc) + "): " + umigpu_last_error(ctx));   // the reference panics
 }
@@ -70,6 +79,36 @@ static Cli parse(int argc, char **argv) {
     return a;
 }
 
+// Uninitialised byte buffer: std::vector would zero-fill gigabytes on one thread before the parallel inflate touches them;
+// here the pages are first touched (and faulted in) by the worker threads.  Also wraps a read-only file mapping.
+struct RawBuf {
+    uint8_t *p = nullptr; size_t n = 0; bool mapped = false;
+    RawBuf() = default;
+    explicit RawBuf(size_t bytes) : p(bytes ? (uint8_t *)malloc(bytes) : nullptr), n(bytes) { if (bytes && !p) { fprintf(stderr, "umicollapse_gpu: out of memory\n"); exit(2); } }
+    RawBuf(const RawBuf &) = delete; RawBuf &operator=(const RawBuf &) = delete;
+    RawBuf(RawBuf &&o) noexcept : p(o.p), n(o.n), mapped(o.mapped) { o.p = nullptr; o.n = 0; }
+    RawBuf &operator=(RawBuf &&o) noexcept { release(); p = o.p; n = o.n; mapped = o.mapped; o.p = nullptr; o.n = 0; return *this; }
+    ~RawBuf() { release(); }
+    void release() { if (p) { if (mapped) munmap(p, n); else free(p); } p = nullptr; n = 0; }
+    uint8_t *data() { return p; } const uint8_t *data() const { return p; }
+    size_t size() const { return n; }
+    uint8_t operator[](size_t i) const { return p[i]; }
+};
+static RawBuf map_file(const std::string &path) {
+    int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) { fprintf(stderr, "umicollapse_gpu: Invalid input path: %s\n", path.c_str()); exit(2); }
+    struct stat st; fstat(fd, &st);
+    RawBuf b;
+    if (st.st_size > 0) {
+        void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { fprintf(stderr, "umicollapse_gpu: cannot map %s\n", path.c_str()); exit(2); }
+        madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+        b.p = (uint8_t *)m; b.n = (size_t)st.st_size; b.mapped = true;
+    }
+    close(fd);
+    return b;
+}
+
 static std::vector<uint8_t> read_file(const std::string &p) {
     FILE *f = fopen(p.c_str(), "rb");
     if (!f) die("Invalid input path: " + p);
@@ -89,7 +128,7 @@ template <class F> static void parallel_for(size_t n, unsigned threads, F f) {
 }
 
 // ---- BGZF (SAM/BAM specification §4.1): independent gzip members with a BC extra field ----
-static std::vector<uint8_t> bgzf_inflate(const std::vector<uint8_t> &in, unsigned threads) {
+static RawBuf bgzf_inflate(const RawBuf &in, unsigned threads) {
     struct Blk { size_t off, csize, usize, uoff; };
     std::vector<Blk> blks;
     size_t off = 0, utotal = 0;
@@ -103,7 +142,7 @@ static std::vector<uint8_t> bgzf_inflate(const std::vector<uint8_t> &in, unsigne
         blks.push_back({off + 12 + xlen, bsize - 12 - xlen - 8, usize, utotal});
         utotal += usize; off += bsize;
     }
-    std::vector<uint8_t> out(utotal);
+    RawBuf out(utotal);
     parallel_for(blks.size(), threads, [&](size_t i) {
         const Blk &b = blks[i];
         if (!b.usize) return;
@@ -119,9 +158,16 @@ static std::vector<uint8_t> bgzf_inflate(const std::vector<uint8_t> &in, unsigne
 
 static void bgzf_write(const std::string &path, const std::vector<const uint8_t *> &ptr, const std::vector<size_t> &len, unsigned threads) {
     // gather into one stream, cut into 0xff00-byte blocks, deflate the blocks in parallel
-    size_t total = 0; for (size_t l : len) total += l;
-    std::vector<uint8_t> data(total);
-    { size_t o = 0; for (size_t i = 0; i < ptr.size(); i++) { memcpy(data.data() + o, ptr[i], len[i]); o += len[i]; } }
+    std::vector<size_t> ooff(len.size() + 1, 0);
+    for (size_t i = 0; i < len.size(); i++) ooff[i + 1] = ooff[i] + len[i];
+    const size_t total = ooff.back();
+    RawBuf data(total);
+    {   // gather on all threads, contiguous slices of the record list
+        const size_t nrec = ptr.size(), per = (nrec + threads - 1) / std::max(1u, threads);
+        parallel_for(std::max(1u, threads), threads, [&](size_t t) {
+            for (size_t i = t * per; i < std::min(nrec, (t + 1) * per); i++) memcpy(data.data() + ooff[i], ptr[i], len[i]);
+        });
+    }
     const size_t B = 0xff00, nb = (total + B - 1) / B;
     std::vector<std::vector<uint8_t>> comp(nb);
     parallel_for(nb, threads, [&](size_t i) {
@@ -329,11 +375,22 @@ struct MateSet {
     }
 };
 
+// phase timing on stderr (the reference logs "UMI collapsing reading finished in ... seconds", deduplicate_sam.rs:179-182)
+struct PhaseClock {
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what) {
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "phase %s: %.3f s\n", what, std::chrono::duration<double>(n - t).count());
+        t = n;
+    }
+};
+
 // ---- --mode bam ----
 static int run_bam(const Cli &a) {
-    std::vector<uint8_t> raw = read_file(a.input);
-    std::vector<uint8_t> buf = bgzf_inflate(raw, a.num_threads);
-    std::vector<uint8_t>().swap(raw);
+    PhaseClock pc;
+    RawBuf raw = map_file(a.input);
+    RawBuf buf = bgzf_inflate(raw, a.num_threads);
+    raw.release();
     if (buf.size() < 12 || memcmp(buf.data(), "BAM\1", 4) != 0) die("Invalid input path: not a BAM file");
     int32_t l_text, n_ref; memcpy(&l_text, buf.data() + 4, 4);
     size_t off = 8 + (size_t)l_text; memcpy(&n_ref, buf.data() + off, 4); off += 4;
@@ -342,6 +399,7 @@ static int run_bam(const Cli &a) {
     std::vector<uint64_t> offs((buf.size() - first) / 36 + 2);
     uint64_t n = 0, consumed = 0;
     check(umigpu_bam_record_offsets(buf.data() + first, buf.size() - first, offs.data(), offs.size() - 1, &n, &consumed), nullptr, "umigpu_bam_record_offsets");
+    pc.lap("read + inflate + record offsets");
     // -u 0: autodetect from the first mapped read (utils/read.rs:65-75,87-94)
     unsigned umi_len = a.umi_length;
     for (uint64_t i = 0; i < n && umi_len == 0; i++) {
@@ -355,6 +413,7 @@ static int run_bam(const Cli &a) {
     uint64_t unmapped = 0;
     if (n && umi_len) {
         umigpu_ctx *ctx = make_ctx(a, umi_len);
+        pc.lap("context (CUDA init)");
         const uint64_t CH = 1ull << 22;
         for (uint64_t s = 0; s < n; s += CH) {
             uint64_t e = std::min(n, s + CH), nun = 0;
@@ -363,6 +422,7 @@ static int run_bam(const Cli &a) {
         }
         umigpu_result res;
         check(umigpu_finish(ctx, &res), ctx, "umigpu_finish");
+        pc.lap("device: record decode + dedup (umigpu_push_bam_records, umigpu_finish)");
         ctr = res.counters;
         std::vector<std::vector<uint8_t>> tagged;         // --tag: rewritten records (own storage)
         if (!a.track_clusters) {
@@ -413,8 +473,10 @@ static int run_bam(const Cli &a) {
                 optr.push_back(t.data()); olen.push_back(t.size());
             }
         }
+        pc.lap("select output records");
         bgzf_write(a.output, optr, olen, a.num_threads);
-        umigpu_destroy(ctx);
+        pc.lap("deflate + write");
+        (void)ctx;    // no umigpu_destroy: the process exits right after the output is closed (freeing pinned buffers and the CUDA context costs seconds)
     } else {
         for (uint64_t i = 0; i < n; i++) {                       // nothing reached the device: every record failed a filter
             const uint8_t *r = buf.data() + first + offs[i];
@@ -510,7 +572,7 @@ static int run_bam_two_pass(const Cli &a) {
             if (ctx) ctr = res.counters;
             ctr.total_reads += unfed.total_reads; ctr.n_unpaired += unfed.n_unpaired; ctr.n_chimeric += unfed.n_chimeric;
             report(ctr, unmapped, a.paired);
-            if (ctx) umigpu_destroy(ctx);
+            (void)ctx;    // no umigpu_destroy: see run_bam
         }
     }
     return 0;
@@ -572,7 +634,7 @@ static int run_fastq(const Cli &a) {
         FILE *f = fopen(a.output.c_str(), "wb"); if (!f) die("cannot open output " + a.output);
         for (size_t j = 0; j < optr.size(); j++) fwrite(optr[j], 1, olen[j], f);
         fclose(f);
-        umigpu_destroy(ctx);
+        (void)ctx;    // no umigpu_destroy: the process exits right after the output is closed (freeing pinned buffers and the CUDA context costs seconds)
     } else { FILE *f = fopen(a.output.c_str(), "wb"); if (f) fclose(f); ctr.total_reads = n; }
     report(ctr, 0);
     return 0;
@@ -584,10 +646,18 @@ int main(int argc, char **argv) {
     if (a.paired && a.mode == "fastq") die("--paired applies to --mode bam only");
     if (a.paired && a.track_clusters) die("--tag with --paired is not implemented (the reference's tag pass is an empty TODO, deduplicate_sam.rs:236-239)");
     if (a.track_clusters && a.mode == "fastq") die("--tag is implemented for --mode bam only");
+    // CUDA start-up takes seconds on a large host: do it on a helper thread while the input is read and inflated
+    std::thread cuda_init([dev = a.device] { umigpu_device_init(dev); });
+    g_cuda_init = &cuda_init;
     int rc;
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); g_cuda_init = nullptr; } } joiner{cuda_init};
     if (a.mode == "fastq") rc = run_fastq(a);
     else if (a.mode == "bam" || a.mode == "sam") rc = (a.two_pass && !a.track_clusters) ? run_bam_two_pass(a) : run_bam(a);
     else die("unknown mode " + a.mode);
     fprintf(stderr, "UMI collapsing finished in %.3f seconds\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());   // main.rs:97-102
-    return rc;
+    // the output is closed: skip the CUDA context teardown and the release of GBs of host buffers
+    if (cuda_init.joinable()) cuda_init.join();
+    g_cuda_init = nullptr;
+    fflush(stdout); fflush(stderr);
+    _exit(rc);
 }

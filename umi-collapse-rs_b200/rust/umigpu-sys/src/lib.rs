@@ -51,6 +51,7 @@ pub struct umigpu_result {
 
 extern "C" {
     pub fn umigpu_version() -> *const c_char;
+    pub fn umigpu_device_init(device: i32) -> c_int;
     pub fn umigpu_last_error(ctx: *const umigpu_ctx) -> *const c_char;
     pub fn umigpu_create(cfg: *const umigpu_config, out: *mut *mut umigpu_ctx) -> c_int;
     pub fn umigpu_destroy(ctx: *mut umigpu_ctx);
