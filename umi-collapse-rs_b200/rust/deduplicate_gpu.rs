@@ -36,6 +36,9 @@ impl DeduplicateInterface for DeduplicateGPU {
         let mut writer = UcWriter::new(&args.input, &args.output, &reader, args.paired, args);
 
         let (mut tid, mut pos, mut rev, mut umi, mut score) = (Vec::new(), Vec::new(), Vec::new(), Vec::new(), Vec::new());
+        let mut file_index: Vec<u64> = Vec::new();                           // pushed read number -> record number in the input
+        let mut tlen: Vec<i64> = Vec::new();                                 // --paired only: PairedAlignment's fourth field
+        let (mut unpaired, mut chimeric) = (0u64, 0u64);
         let mut ctx: Option<gpu::Context> = None;
         let mut umi_len = args.umi_length;
         let (mut total, mut unmapped, mut index) = (0u64, 0u64, 0u64);
@@ -44,23 +47,31 @@ impl DeduplicateInterface for DeduplicateGPU {
         while let Some(r) = reader.read(&mut record) {
             r.expect("Failed to parse record");
             let this = index; index += 1;                                   // index in the input file
+            // --paired filters, in the order of deduplicate_sam.rs:96-129 (mates are written back by UcWriter::close)
+            if args.paired && record.is_paired() && record.is_last_in_template() { continue; }
             total += 1;
             if record.is_unmapped() { unmapped += 1; if args.keep_unmapped { writer.write(&record).unwrap(); } continue; }
+            if args.paired {
+                if !record.is_paired() { unpaired += 1; if args.remove_unpaired { continue; } }
+                if record.is_paired() && record.is_mate_unmapped() { unmapped += 1; continue; }
+                if record.is_paired() && record.tid() != record.mtid() { chimeric += 1; if args.remove_chimeric { continue; } }
+            }
             let qname = record.qname();
             let p = one.find(qname).expect("failed to get the umi");        // utils/read.rs:100-110
             if umi_len == 0 { umi_len = qname[p + 1..].iter().take_while(|c| b"ACGTNacgtn".contains(c)).count(); }
-            if tid.is_empty() { first_of_chunk = this; }
-            // a chunk must be contiguous in index space: skipped (unmapped) reads close it
-            if !tid.is_empty() && this != first_of_chunk + tid.len() as u64 { flush(&mut ctx, args, self, umi_len, &mut tid, &mut pos, &mut rev, &mut umi, &mut score, first_of_chunk); first_of_chunk = this; }
+            // reads are numbered densely in push order; file_index maps a kept number back to its record in the input
+            if tid.is_empty() { first_of_chunk = file_index.len() as u64; }
+            file_index.push(this);
             tid.push(record.tid());
             pos.push(get_unclipped_pos(&record));                           // utils/mod.rs:96-104
             rev.push(record.is_reverse() as u8);
+            if args.paired { tlen.push(record.insert_size()); }
             umi.extend_from_slice(&qname[p + 1..p + 1 + umi_len]);
             score.push(if self.merge == gpu::UMIGPU_MERGE_MAPQUAL { record.mapq() as i32 }
                        else { let q = record.qual(); (q.iter().map(|&b| b as f32).sum::<f32>() / record.seq_len() as f32) as i32 }); // read.rs:56-63
-            if tid.len() == CHUNK { flush(&mut ctx, args, self, umi_len, &mut tid, &mut pos, &mut rev, &mut umi, &mut score, first_of_chunk); }
+            if tid.len() == CHUNK { flush(&mut ctx, args, self, umi_len, &mut tid, &mut pos, &mut rev, &mut tlen, &mut umi, &mut score, first_of_chunk); }
         }
-        flush(&mut ctx, args, self, umi_len, &mut tid, &mut pos, &mut rev, &mut umi, &mut score, first_of_chunk);
+        flush(&mut ctx, args, self, umi_len, &mut tid, &mut pos, &mut rev, &mut tlen, &mut umi, &mut score, first_of_chunk);
         info!("UMI collapsing reading finished in {:?} seconds", SystemTime::now().duration_since(*start_time).unwrap().as_secs_f32());
         drop(reader);
 
@@ -70,11 +81,12 @@ impl DeduplicateInterface for DeduplicateGPU {
         let mut reader = Reader::from_path(&args.input).expect("Invalid input path");
         reader.set_threads(args.num_threads).unwrap();
         let (mut i, mut k) = (0u64, 0usize);
-        while k < kept.len() { reader.read(&mut record).unwrap().unwrap(); if i == kept[k] { writer.write(&record).unwrap(); k += 1; } i += 1; }
+        while k < kept.len() { reader.read(&mut record).unwrap().unwrap(); if i == file_index[kept[k] as usize] { writer.write(&record).unwrap(); k += 1; } i += 1; }
         writer.close();
 
         debug!("Number of input reads: {}", total);                         // deduplicate_sam.rs:243-267
         debug!("Number of removed unmapped reads: {}", unmapped);
+        if args.paired { debug!("Number of unpaired reads: {}", unpaired); debug!("Number of chimeric reads: {}", chimeric); }
         debug!("Number of unique alignment positions: {}", ctr.n_buckets);
         debug!("Number of UMIs: {}", ctr.total_umis);
         debug!("Average number of UMIs per alignment position: {}", ctr.total_umis as f64 / ctr.n_buckets as f64);
@@ -85,11 +97,11 @@ impl DeduplicateInterface for DeduplicateGPU {
 
 #[allow(clippy::too_many_arguments)]
 fn flush(ctx: &mut Option<gpu::Context>, args: &Cli, me: &DeduplicateGPU, umi_len: usize, tid: &mut Vec<i32>, pos: &mut Vec<i64>,
-         rev: &mut Vec<u8>, umi: &mut Vec<u8>, score: &mut Vec<i32>, first: u64) {
+         rev: &mut Vec<u8>, tlen: &mut Vec<i64>, umi: &mut Vec<u8>, score: &mut Vec<i32>, first: u64) {
     if tid.is_empty() { return; }
     let c = ctx.get_or_insert_with(|| gpu::Context::new(gpu::umigpu_config {
         k: args.k, percentage: args.percentage, algo: me.algo, merge: me.merge, umi_len: umi_len as u32, device: 0,
         flags: 0, reserved: 0, stream: std::ptr::null_mut() }));
-    c.push_reads(tid, pos, rev, umi, Some(score), first);
-    tid.clear(); pos.clear(); rev.clear(); umi.clear(); score.clear();
+    if args.paired { c.push_reads_paired(tid, pos, rev, tlen, umi, Some(score), first); } else { c.push_reads(tid, pos, rev, umi, Some(score), first); }
+    tid.clear(); pos.clear(); rev.clear(); tlen.clear(); umi.clear(); score.clear();
 }

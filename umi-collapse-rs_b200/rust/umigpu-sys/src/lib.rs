@@ -112,6 +112,16 @@ impl Context {
         };
         self.check(rc, "umigpu_push_reads");
     }
+    /// `--paired`: the template length joins the bucket key (PairedAlignment, deduplicate_sam.rs:545-565).
+    pub fn push_reads_paired(&mut self, tid: &[i32], pos: &[i64], rev: &[u8], tlen: &[i64], umi: &[u8], score: Option<&[i32]>, first_read_index: u64) {
+        let n = tid.len();
+        assert!(pos.len() == n && rev.len() == n && tlen.len() == n && umi.len() % n.max(1) == 0);
+        let rc = unsafe {
+            umigpu_push_reads_paired(self.raw, n as u64, tid.as_ptr(), pos.as_ptr(), rev.as_ptr(), tlen.as_ptr(), umi.as_ptr(),
+                                     score.map_or(std::ptr::null(), |s| s.as_ptr()), std::ptr::null(), first_read_index)
+        };
+        self.check(rc, "umigpu_push_reads_paired");
+    }
     /// Kept read indices (ascending input order) and the end-of-run counters.
     pub fn finish(&mut self) -> (&[u64], umigpu_counters) {
         let mut res = std::mem::MaybeUninit::<umigpu_result>::zeroed();
