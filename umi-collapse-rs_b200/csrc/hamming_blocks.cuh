@@ -155,6 +155,10 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
     const u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
     const u64 nwarps = (u64)gridDim.x * (256 / 32);
     __shared__ uint2 s_edges[(256 / 32) * WB_CAP];
+    // the column block's match words, staged once per block pair by its warp (768 B at 12 nt): the four row slices then
+    // read them with LDS.128 (four distinct 16-byte rows per warp: conflict-free) instead of going through L1
+    __shared__ __align__(16) uint4 s_eq[256 / 32][LP * XS];
+    uint4 *sw = s_eq[threadIdx.x >> 5];
     WarpEdgeBuf wb{s_edges + (threadIdx.x >> 5) * WB_CAP, 0u};
     u64 evaluated = 0;
     for (u64 w = ((u64)blockIdx.x * 256 + threadIdx.x) >> 5; w < n_pairs; w += nwarps) {
@@ -169,6 +173,10 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
             for (int x = 0; x < NLET; x++) cs[x] = bsum[(u64)pr.y * 8 + x];
         }
         const uint4 *base = eq + (u64)pr.y * (LP * XS);
+        __syncwarp();                                  // the previous pair's slices are done with sw
+#pragma unroll
+        for (int i = 0; i < (LP * XS + 31) / 32; i++) { const u32 t = i * 32 + lane; if (t < (u32)(LP * XS)) sw[t] = __ldg(base + t); }
+        __syncwarp();
         for (u32 s = 0; s * 32 < rcnt; s++) {
             const u32 r = s * 32 + lane;
             const bool valid = r < rcnt;
@@ -194,7 +202,7 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
                 uint4 m1 = make_uint4(~0u, ~0u, ~0u, ~0u), m2 = m1, m3 = m1, m4 = m1;
 #pragma unroll
                 for (int j = 0; j < LP; j++) {
-                    const uint4 wv = __ldg(base + off[j]);
+                    const uint4 wv = sw[off[j]];
                     if (K >= 3) { m4.x = (wv.x & m4.x) | (~wv.x & m3.x); m4.y = (wv.y & m4.y) | (~wv.y & m3.y);
                                   m4.z = (wv.z & m4.z) | (~wv.z & m3.z); m4.w = (wv.w & m4.w) | (~wv.w & m3.w); }
                     if (K >= 2) { m3.x = (wv.x & m3.x) | (~wv.x & m2.x); m3.y = (wv.y & m3.y) | (~wv.y & m2.y);
