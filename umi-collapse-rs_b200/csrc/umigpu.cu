@@ -633,8 +633,18 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     ue.bhead = ctx->d_bhead.as<u8>(); ue.rep = ctx->d_rep.as<unsigned long long>(); ue.wsum = ctx->d_wsum.as<i32>();
     ue.read_uid = want_labels ? ctx->d_read_uid.as<u32>() : nullptr;
     ue.pend_uid = 0xffffffffu; ue.pend_val = 0; ue.pend_w = 0;
-    rc = run_scan(ctx, HeadFlag{sk}, ue, n, &sc->n_unique);
-    if (rc) return rc;
+    if (lay.nw == 1) {
+        // one-word keys: same three phases, the apply phase specialised (vector loads, predecessor by shuffle)
+        const u64 ntiles = ceil_div_u64(n, SCAN_TILE);
+        CK(ctx->d_tiles.reserve(ntiles * sizeof(u32)));
+        u32 *ts = ctx->d_tiles.as<u32>();
+        LAUNCH((scan_tile_sums<u32, HeadFlag>), (u32)ntiles, SCAN_THREADS, HeadFlag{sk}, n, ts);
+        LAUNCH((scan_spine<u32>), 1, 1024, ts, ntiles, &sc->n_unique);
+        LAUNCH(unique_apply1_kernel, (u32)ntiles, SCAN_THREADS, ue, n, (const u32 *)ts);
+    } else {
+        rc = run_scan(ctx, HeadFlag{sk}, ue, n, &sc->n_unique);
+        if (rc) return rc;
+    }
     rc = read_scalars(ctx);
     if (rc) return rc;
     if (ctx->h_sc->sort_err) return fail(ctx, UMIGPU_ERR_CUDA, "radix sort look-back exceeded its spin budget");
