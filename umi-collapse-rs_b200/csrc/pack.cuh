@@ -36,6 +36,52 @@ struct KeyLayout {
     i32 tid_min;
 };
 
+// Four bases per step (SWAR).  utils/read.rs:22-31 alphabet; anything else panics in the reference (utils/mod.rs:78).
+// Bits 1-2 of the ASCII code separate A,C,T,G (0,1,3,2 -> Gray step -> A0 C1 G2 T3); a byte is valid iff it equals the
+// letter its own bits name (one PRMT rebuilds the four letters); one multiply gathers the four 2-bit codes.  Only words
+// holding an N or a bad byte take the per-byte path.  `word` holds bases b .. b+nb-1 of an L-base UMI, first base in the
+// low byte.
+__device__ __forceinline__ void pack_word(u32 word, int nb, int L, int b, u64 &code, u32 &nm, u32 &flags) {
+    if (nb < 4) { const u32 m = (1u << (8 * nb)) - 1u; word = (word & m) | (0x41414141u & ~m); }
+    const u32 x = (word >> 1) & 0x03030303u;
+    u32 v = x ^ ((x >> 1) & 0x01010101u);
+    const u32 t = v | (v >> 4);
+    const u32 rec = __byte_perm(0x54474341u, 0u, __byte_perm(t, 0u, 0x4420));
+    const u32 diff = word ^ rec;
+    if (diff) {
+        for (int j = 0; j < nb; j++) {
+            if ((diff >> (8 * j)) & 0xffu) {
+                v &= ~(0xffu << (8 * j));
+                if (((word >> (8 * j)) & 0xffu) == 'N') nm |= 1u << (L - 1 - (b + j)); else flags |= 2u;
+            }
+        }
+    }
+    const u32 p8 = (v * 0x40100401u) >> 24;          // v0<<6 | v1<<4 | v2<<2 | v3
+    code = (code << (2 * nb)) | (u64)(p8 >> (2 * (4 - nb)));
+}
+
+// Four consecutive reads of a UMI length 4*LW per thread, everything as 16-byte vectors: LW loads of ASCII in, two
+// stores of codes and one of N masks out.
+template <int LW>
+__device__ __forceinline__ void pack_quad(const u8 *__restrict__ ascii, u64 g, u64 *__restrict__ umi2, u32 *__restrict__ nmask, u32 &flags) {
+    constexpr int L = 4 * LW;
+    const uint4 *src = reinterpret_cast<const uint4 *>(ascii) + g * LW;
+    u32 w[4 * LW];
+#pragma unroll
+    for (int q = 0; q < LW; q++) { const uint4 t = __ldg(src + q); w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w; }
+    u64 code[4]; u32 nm[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        code[r] = 0; nm[r] = 0;
+#pragma unroll
+        for (int k = 0; k < LW; k++) pack_word(w[r * LW + k], 4, L, 4 * k, code[r], nm[r], flags);
+    }
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(umi2 + 4 * g);
+    dst[0] = make_ulonglong2(code[0], code[1]); dst[1] = make_ulonglong2(code[2], code[3]);
+    *reinterpret_cast<uint4 *>(nmask + 4 * g) = make_uint4(nm[0], nm[1], nm[2], nm[3]);
+    if (nm[0] | nm[1] | nm[2] | nm[3]) flags |= 1u;
+}
+
 #define PACK_THREADS 256
 
 __global__ void __launch_bounds__(PACK_THREADS) umi_pack_kernel(
@@ -54,7 +100,26 @@ __global__ void __launch_bounds__(PACK_THREADS) umi_pack_kernel(
     // L a multiple of 4 on a 4-byte aligned array: every read is whole words, loaded straight from global (a warp's loads
     // cover one contiguous span; L1 serves the repeats) — no staging, no barriers
     const bool direct = (L & 3) == 0 && (((unsigned long long)ascii) & 3ull) == 0;
-    for (u64 base = (u64)blockIdx.x * PACK_THREADS; base < n; base += (u64)gridDim.x * PACK_THREADS) {
+    // 8-, 12- and 16-nt UMIs on 16-byte aligned arrays: four reads per thread, vector loads and stores throughout
+    u64 n4 = 0;
+    if ((L == 8 || L == 12 || L == 16) &&
+        ((((unsigned long long)ascii) | ((unsigned long long)tid) | ((unsigned long long)pos) | ((unsigned long long)umi2) |
+          ((unsigned long long)nmask) | ((unsigned long long)tlen)) & 15ull) == 0) {
+        n4 = n & ~3ull;
+        for (u64 g = (u64)blockIdx.x * PACK_THREADS + threadIdx.x; g < (n4 >> 2); g += (u64)gridDim.x * PACK_THREADS) {
+            if (L == 12) pack_quad<3>(ascii, g, umi2, nmask, flags); else if (L == 8) pack_quad<2>(ascii, g, umi2, nmask, flags);
+            else pack_quad<4>(ascii, g, umi2, nmask, flags);
+            const int4 t4 = __ldg(reinterpret_cast<const int4 *>(tid) + g);
+            tmin = min(tmin, min(min(t4.x, t4.y), min(t4.z, t4.w))); tmax = max(tmax, max(max(t4.x, t4.y), max(t4.z, t4.w)));
+            const longlong2 p0 = __ldg(reinterpret_cast<const longlong2 *>(pos) + 2 * g), p1 = __ldg(reinterpret_cast<const longlong2 *>(pos) + 2 * g + 1);
+            pmin = min(pmin, min(min((i64)p0.x, (i64)p0.y), min((i64)p1.x, (i64)p1.y))); pmax = max(pmax, max(max((i64)p0.x, (i64)p0.y), max((i64)p1.x, (i64)p1.y)));
+            if (tlen) {
+                const longlong2 l0 = __ldg(reinterpret_cast<const longlong2 *>(tlen) + 2 * g), l1 = __ldg(reinterpret_cast<const longlong2 *>(tlen) + 2 * g + 1);
+                lmin = min(lmin, min(min((i64)l0.x, (i64)l0.y), min((i64)l1.x, (i64)l1.y))); lmax = max(lmax, max(max((i64)l0.x, (i64)l0.y), max((i64)l1.x, (i64)l1.y)));
+            }
+        }
+    }
+    for (u64 base = n4 + (u64)blockIdx.x * PACK_THREADS; base < n; base += (u64)gridDim.x * PACK_THREADS) {
         const u32 cnt = (u32)min((u64)PACK_THREADS, n - base);
         const u32 bytes = cnt * (u32)L;
         const u8 *src = ascii + base * (u64)L;
@@ -71,10 +136,6 @@ __global__ void __launch_bounds__(PACK_THREADS) umi_pack_kernel(
         if (!direct) __syncthreads();
         if (threadIdx.x < cnt) {
             const u64 i = base + threadIdx.x;
-            // utils/read.rs:22-31 alphabet; anything else panics in the reference (utils/mod.rs:78).
-            // Four bases per step (SWAR): bits 1-2 of the ASCII code separate A,C,T,G (0,1,3,2 -> Gray step -> A0 C1 G2 T3);
-            // a byte is valid iff it equals the letter its own bits name (one PRMT rebuilds the four letters); one
-            // multiply gathers the four 2-bit codes.  Only words holding an N or a bad byte take the per-byte path.
             const u32 o = threadIdx.x * (u32)L, sh = 8u * (o & 3u);
             const u32 *sw = reinterpret_cast<const u32 *>(sbuf) + (o >> 2);
             const u32 *gw = reinterpret_cast<const u32 *>(src) + (o >> 2);
@@ -84,23 +145,7 @@ __global__ void __launch_bounds__(PACK_THREADS) umi_pack_kernel(
                 u32 word;
                 if (direct) word = __ldg(gw + (b >> 2));
                 else { const u32 hi = sw[(b >> 2) + 1]; word = __funnelshift_r(lo, hi, sh); lo = hi; }
-                const int nb = min(4, L - b);
-                if (nb < 4) { const u32 m = (1u << (8 * nb)) - 1u; word = (word & m) | (0x41414141u & ~m); }
-                const u32 x = (word >> 1) & 0x03030303u;
-                u32 v = x ^ ((x >> 1) & 0x01010101u);
-                const u32 t = v | (v >> 4);
-                const u32 rec = __byte_perm(0x54474341u, 0u, __byte_perm(t, 0u, 0x4420));
-                const u32 diff = word ^ rec;
-                if (diff) {
-                    for (int j = 0; j < nb; j++) {
-                        if ((diff >> (8 * j)) & 0xffu) {
-                            v &= ~(0xffu << (8 * j));
-                            if (((word >> (8 * j)) & 0xffu) == 'N') nm |= 1u << (L - 1 - (b + j)); else flags |= 2u;
-                        }
-                    }
-                }
-                const u32 p8 = (v * 0x40100401u) >> 24;          // v0<<6 | v1<<4 | v2<<2 | v3
-                code = (code << (2 * nb)) | (u64)(p8 >> (2 * (4 - nb)));
+                pack_word(word, min(4, L - b), L, b, code, nm, flags);
             }
             umi2[i] = code; nmask[i] = nm; if (nm) flags |= 1u;
             const i32 t = tid[i]; const i64 p = pos[i];
