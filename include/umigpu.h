@@ -101,6 +101,7 @@ typedef struct umigpu_counters {
     uint64_t n_chimeric;        /* paired BAM feed: tid != mtid, :123-128                            */
     uint64_t n_mates_skipped;   /* paired BAM feed: last-in-template records skipped before they are
                                    counted as input reads, :96-98                                    */
+    uint64_t key_bits;          /* width of the sort key this batch needed (<= 64: one-word keys)    */
 } umigpu_counters;
 
 typedef struct umigpu_result {

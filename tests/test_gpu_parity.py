@@ -519,3 +519,29 @@ def test_full_size_two_phase_equals_plain_sweeps(monkeypatch):
     assert ctr["n_edges"] == pctr["n_edges"] > (8 << 20)
     assert np.array_equal(kept, pkept) and ctr["n_kept"] == pctr["n_kept"]
     assert pctr["n_sweeps"] != ctr["n_sweeps"]        # really two different schedules
+
+
+def test_many_contigs_use_the_linear_coordinate_layout(monkeypatch):
+    """Thousands of contigs with positions up to 2^27 and 13-nt UMIs: [tid | pos | strand | UMI] needs 12 + 27 + 1 + 26 = 66
+    bits (two-word keys); laying the contigs' occupied ranges end to end keeps the key in one word.  Same survivors,
+    same counters either way, and both match the oracle."""
+    rng = np.random.default_rng(17)
+    n, L, n_tid = 60000, 13, 3000
+    tid = rng.integers(0, n_tid, n).astype(np.int32)
+    # every contig is occupied over a narrow window somewhere below 2^27 (plus a negative corner case on contig 0)
+    lo = rng.integers(0, (1 << 27) - 5000, n_tid)
+    pos = (lo[tid] + rng.integers(0, 40, n) * 97).astype(np.int64)
+    pos[tid == 0] -= (1 << 20)
+    tid[:2] = (0, n_tid - 1); pos[0] = -(1 << 20); pos[1] = (1 << 27) - 1
+    rev = rng.integers(0, 2, n).astype(np.uint8)
+    fam = rng.integers(0, 4, (200, L))
+    umi = np.frombuffer(b"ACGT", np.uint8)[np.where(rng.random((n, L)) < 0.05, rng.integers(0, 4, (n, L)), fam[rng.integers(0, 200, n)])]
+    score = rng.integers(0, 41, n).astype(np.int32)
+    d = dict(tid=tid, pos=pos, rev=rev, umi=umi, score=score)
+    ctr_lin = check_against_oracle(d, umigpu.ALGO_DIR, umigpu.MERGE_AVGQUAL, 1, 0.5, labels=True)
+    assert ctr_lin["key_bits"] <= 64
+    monkeypatch.setenv("UMIGPU_NO_LINEAR_KEYS", "1")
+    ctr_plain = check_against_oracle(d, umigpu.ALGO_DIR, umigpu.MERGE_AVGQUAL, 1, 0.5, labels=True)
+    assert ctr_plain["key_bits"] > 64
+    for key in ("n_buckets", "total_umis", "max_umis", "n_kept", "n_edges"):
+        assert ctr_lin[key] == ctr_plain[key]

@@ -34,6 +34,9 @@ struct KeyLayout {
     int umi_len, umi_bits, pos_bits, tid_bits, tlen_bits, bucket_bits, total_bits, nw, has_n;
     i64 pos_min, tlen_min;
     i32 tid_min;
+    // linear coordinate layout (many contigs): position field = lin_off[tid - tid_min] + (pos - lin_pmin[tid - tid_min]),
+    // i.e. the contigs' OCCUPIED position ranges laid end to end; tid_bits = 0.  nullptr = the plain [tid | pos] layout.
+    const u64 *lin_off; const i64 *lin_pmin;
 };
 
 // Four bases per step (SWAR).  utils/read.rs:22-31 alphabet; anything else panics in the reference (utils/mod.rs:78).
@@ -195,19 +198,44 @@ __device__ __forceinline__ u64 umi_sort_code(u64 umi2, u32 nm, int L, int has_n)
     return code;
 }
 
-template <int NW>
+template <int NW, bool LIN>
 __global__ void __launch_bounds__(256) build_keys_kernel(
     u64 n, const i32 *__restrict__ tid, const i64 *__restrict__ pos, const u8 *__restrict__ rev,
     const i64 *__restrict__ tlen, const u64 *__restrict__ umi2, const u32 *__restrict__ nmask, KeyLayout lay, u64 *__restrict__ k0, u64 *__restrict__ k1) {
     u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
-    u64 bucket = ((u64)(u32)(tid[i] - lay.tid_min) << (lay.pos_bits + 1)) | ((u64)(pos[i] - lay.pos_min) << 1) | (rev[i] ? 1u : 0u);
+    u64 bucket;
+    if (LIN) { const u32 t = (u32)(tid[i] - lay.tid_min); bucket = ((__ldg(lay.lin_off + t) + (u64)(pos[i] - __ldg(lay.lin_pmin + t))) << 1) | (rev[i] ? 1u : 0u); }
+    else bucket = ((u64)(u32)(tid[i] - lay.tid_min) << (lay.pos_bits + 1)) | ((u64)(pos[i] - lay.pos_min) << 1) | (rev[i] ? 1u : 0u);
     if (lay.tlen_bits) bucket = (bucket << lay.tlen_bits) | (u64)(tlen[i] - lay.tlen_min);    // PairedAlignment: + tlen
     u64 code = umi_sort_code(umi2[i], nmask[i], lay.umi_len, lay.has_n);
     int ub = lay.umi_bits;
     u64 lo = (ub < 64 ? bucket << ub : 0) | code;
     k0[i] = lo;
     if (NW == 2) k1[i] = ub == 64 ? bucket : (ub == 0 ? 0 : bucket >> (64 - ub));
+}
+
+// Occupied position range of every contig (order-preserving unsigned bias so that the tables can be memset), for the
+// linear coordinate layout.  Coordinate-sorted input: a warp usually holds one contig -> one pair of atomics per warp.
+#define POS_BIAS 0x8000000000000000ull
+__global__ void __launch_bounds__(256) tid_range_kernel(u64 n, const i32 *__restrict__ tid, const i64 *__restrict__ pos, i32 tid_min,
+                                                        unsigned long long *vmin, unsigned long long *vmax) {
+    const u64 stride = (u64)gridDim.x * 256, rounds = (n + stride - 1) / stride;
+    for (u64 it = 0; it < rounds; it++) {
+        const u64 i = it * stride + (u64)blockIdx.x * 256 + threadIdx.x;
+        const bool a = i < n;
+        const u32 t = a ? (u32)(tid[i] - tid_min) : 0xffffffffu;
+        unsigned long long lo = a ? ((unsigned long long)pos[i] ^ POS_BIAS) : ~0ull, hi = a ? lo : 0ull;
+        const u32 t0 = __shfl_sync(0xffffffffu, t, 0);
+        if (__all_sync(0xffffffffu, t == t0 || !a)) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+                lo = l2 < lo ? l2 : lo; hi = h2 > hi ? h2 : hi;
+            }
+            if (lane_id() == 0 && t0 != 0xffffffffu) { atomicMin(&vmin[t0], lo); atomicMax(&vmax[t0], hi); }
+        } else if (a) { atomicMin(&vmin[t], lo); atomicMax(&vmax[t], hi); }
+    }
 }
 
 // bit planes of a sort code: plane0 bit b = low bit of base b's code, plane1 = high bit, planeN = N flag.

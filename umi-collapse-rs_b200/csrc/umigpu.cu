@@ -46,7 +46,7 @@ struct umigpu_ctx {
 
     DevBuf d_key[2][2], d_idx[2], d_hist, d_tiles;
     DevBuf d_useg, d_rep, d_planes, d_nplane, d_bhead, d_wsum, d_read_uid, d_freq, d_thr, d_repidx, d_label, d_prio;
-    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_tileoff, d_tsum, d_tilestate, d_bsum, d_blkoff, d_blkfirst, d_blkcnt, d_eq, d_pairs, d_comp, d_ucode, d_ubkt, d_brank, d_bigbid, d_bstartbig, d_biguid, d_miplanes, d_minplane, d_miucode, d_miuid, d_cedges;
+    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_tileoff, d_tsum, d_tilestate, d_bsum, d_blkoff, d_blkfirst, d_blkcnt, d_eq, d_pairs, d_comp, d_ucode, d_ubkt, d_brank, d_bigbid, d_bstartbig, d_biguid, d_miplanes, d_minplane, d_miucode, d_miuid, d_cedges, d_tidtab, d_lintab;
 
     // results
     bool ran = false;
@@ -164,7 +164,7 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
                       &ctx->d_read_uid, &ctx->d_freq, &ctx->d_thr, &ctx->d_repidx, &ctx->d_label, &ctx->d_prio, &ctx->d_bstart, &ctx->d_itemoff,
                       &ctx->d_items, &ctx->d_edges, &ctx->d_keep, &ctx->d_state, &ctx->d_blocked, &ctx->d_bitmap, &ctx->d_kept, &ctx->d_roots,
                       &ctx->d_tileoff, &ctx->d_tsum, &ctx->d_tilestate, &ctx->d_bsum, &ctx->d_blkoff, &ctx->d_blkfirst, &ctx->d_blkcnt, &ctx->d_eq, &ctx->d_pairs, &ctx->d_comp, &ctx->d_ucode, &ctx->d_ubkt, &ctx->d_brank, &ctx->d_bigbid, &ctx->d_bstartbig, &ctx->d_biguid,
-                      &ctx->d_miplanes, &ctx->d_minplane, &ctx->d_miucode, &ctx->d_miuid, &ctx->d_cedges};
+                      &ctx->d_miplanes, &ctx->d_minplane, &ctx->d_miucode, &ctx->d_miuid, &ctx->d_cedges, &ctx->d_tidtab, &ctx->d_lintab};
     for (DevBuf *b : bufs) b->release();
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
     if (ctx->h_kept) cudaFreeHost(ctx->h_kept);
@@ -583,9 +583,45 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
         lay.tlen_bits = bits_for((u64)ctx->h_sc->tlen_max - (u64)ctx->h_sc->tlen_min);
     }
     lay.bucket_bits = lay.tid_bits + lay.pos_bits + 1 + lay.tlen_bits;
-    if (lay.bucket_bits > 64) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "bucket key needs %d bits (> 64)", lay.bucket_bits);
     lay.total_bits = lay.bucket_bits + lay.umi_bits;
+    lay.lin_off = nullptr; lay.lin_pmin = nullptr;
+    if (lay.total_bits > 64 && tid_range >= 1 && tid_range < 65536 && !getenv("UMIGPU_NO_LINEAR_KEYS")) {
+        // Many contigs (a genome with its alt/decoy contigs has thousands): [tid | pos] wastes bits on positions no contig
+        // reaches.  Lay the contigs' OCCUPIED position ranges end to end instead — a human genome fits 32 bits — so that the
+        // key stays one 64-bit word.  Only tried when the plain layout would need two words.
+        const u32 T = (u32)tid_range + 1;
+        CK(ctx->d_tidtab.reserve((size_t)T * 16));
+        unsigned long long *vmin = ctx->d_tidtab.as<unsigned long long>(), *vmax = vmin + T;
+        CK(cudaMemsetAsync(vmin, 0xff, (size_t)T * 8, ctx->stream)); CK(cudaMemsetAsync(vmax, 0, (size_t)T * 8, ctx->stream));
+        LAUNCH(tid_range_kernel, (u32)std::min<u64>(grid_for(n, 256), (u64)ctx->num_sms * 16), 256, n, (const i32 *)ctx->d_tid.p, (const i64 *)ctx->d_pos.p,
+               lay.tid_min, vmin, vmax);
+        std::vector<unsigned long long> h((size_t)T * 2);
+        CK(cudaMemcpyAsync(h.data(), vmin, (size_t)T * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::vector<unsigned long long> tab((size_t)T * 2);          // [0,T) offsets, [T,2T) per-contig minimum position
+        unsigned long long run = 0; bool ok = true;
+        for (u32 t = 0; t < T && ok; t++) {
+            tab[t] = run; tab[T + t] = 0;
+            if (h[T + t] >= h[t]) {
+                const unsigned long long span = h[T + t] - h[t];     // biased values: the difference is the true span - 1
+                tab[T + t] = (unsigned long long)(i64)(h[t] ^ POS_BIAS);
+                if (span >= (1ull << 62) || run + span + 1 >= (1ull << 62)) ok = false; else run += span + 1;
+            }
+        }
+        const int lin_bits = ok ? bits_for(run ? run - 1 : 0) : 999;
+        if (lin_bits < lay.tid_bits + lay.pos_bits) {
+            CK(ctx->d_lintab.reserve((size_t)T * 16));
+            CK(cudaMemcpyAsync(ctx->d_lintab.p, tab.data(), (size_t)T * 16, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));                   // tab is a stack-lifetime pageable buffer
+            lay.lin_off = ctx->d_lintab.as<u64>(); lay.lin_pmin = (const i64 *)(ctx->d_lintab.as<u64>() + T);
+            lay.tid_bits = 0; lay.pos_bits = lin_bits;
+            lay.bucket_bits = lay.pos_bits + 1 + lay.tlen_bits;
+            lay.total_bits = lay.bucket_bits + lay.umi_bits;
+        }
+    }
+    if (lay.bucket_bits > 64) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "bucket key needs %d bits (> 64)", lay.bucket_bits);
     lay.nw = lay.total_bits <= 64 ? 1 : 2;
+    ctx->ctr.key_bits = (u64)lay.total_bits;
     ctx->lay = lay;
     const bool has_n = lay.has_n != 0;
 
@@ -596,12 +632,12 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
         if (lay.nw == 2) CK(ctx->d_key[b][1].reserve(n * 8));
         CK(ctx->d_idx[b].reserve(n * 4));
     }
-    if (lay.nw == 1)
-        LAUNCH(build_keys_kernel<1>, grid_for(n, 256), 256, n, (const i32 *)ctx->d_tid.p, (const i64 *)ctx->d_pos.p, (const u8 *)ctx->d_rev.p,
-               (const i64 *)(lay.tlen_bits ? ctx->d_tlen.p : nullptr), (const u64 *)ctx->d_umi2.p, (const u32 *)ctx->d_nmask.p, lay, ctx->d_key[0][0].as<u64>(), (u64 *)nullptr);
-    else
-        LAUNCH(build_keys_kernel<2>, grid_for(n, 256), 256, n, (const i32 *)ctx->d_tid.p, (const i64 *)ctx->d_pos.p, (const u8 *)ctx->d_rev.p,
-               (const i64 *)(lay.tlen_bits ? ctx->d_tlen.p : nullptr), (const u64 *)ctx->d_umi2.p, (const u32 *)ctx->d_nmask.p, lay, ctx->d_key[0][0].as<u64>(), ctx->d_key[0][1].as<u64>());
+#define BUILD_KEYS(NWV, LINV, K1) LAUNCH((build_keys_kernel<NWV, LINV>), grid_for(n, 256), 256, n, (const i32 *)ctx->d_tid.p, (const i64 *)ctx->d_pos.p, \
+        (const u8 *)ctx->d_rev.p, (const i64 *)(lay.tlen_bits ? ctx->d_tlen.p : nullptr), (const u64 *)ctx->d_umi2.p, (const u32 *)ctx->d_nmask.p, lay, \
+        ctx->d_key[0][0].as<u64>(), K1)
+    if (lay.nw == 1) { if (lay.lin_off) BUILD_KEYS(1, true, (u64 *)nullptr); else BUILD_KEYS(1, false, (u64 *)nullptr); }
+    else { if (lay.lin_off) BUILD_KEYS(2, true, ctx->d_key[0][1].as<u64>()); else BUILD_KEYS(2, false, ctx->d_key[0][1].as<u64>()); }
+#undef BUILD_KEYS
     STAGE_END(UMIGPU_STAGE_KEYS);
 
     // ---- K2 sort ----
@@ -1289,6 +1325,7 @@ extern "C" int umigpu_dedup_sharded(const umigpu_config *cfg, int32_t n_devices,
             counters->unordered_pairs += p.ctr.unordered_pairs; counters->pairs_evaluated += p.ctr.pairs_evaluated; counters->n_edges += p.ctr.n_edges;
             counters->n_tile_items += p.ctr.n_tile_items; counters->n_tile_candidates += p.ctr.n_tile_candidates;
             counters->n_sweeps = std::max(counters->n_sweeps, p.ctr.n_sweeps); counters->n_block_pairs += p.ctr.n_block_pairs;
+            counters->key_bits = std::max(counters->key_bits, p.ctr.key_bits);
         }
     }
     return UMIGPU_OK;

@@ -36,7 +36,7 @@ pub struct umigpu_counters {
     pub total_reads: u64, pub n_buckets: u64, pub total_umis: u64, pub max_umis: u64, pub n_kept: u64,
     pub unordered_pairs: u64, pub pairs_evaluated: u64, pub n_edges: u64, pub n_tile_items: u64,
     pub n_tile_candidates: u64, pub n_sweeps: u64, pub n_block_pairs: u64, pub n_unmapped: u64,
-    pub n_unpaired: u64, pub n_chimeric: u64, pub n_mates_skipped: u64,
+    pub n_unpaired: u64, pub n_chimeric: u64, pub n_mates_skipped: u64, pub key_bits: u64,
 }
 
 #[repr(C)]

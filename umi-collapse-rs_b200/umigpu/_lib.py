@@ -38,7 +38,7 @@ class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "total_reads", "n_buckets", "total_umis", "max_umis", "n_kept", "unordered_pairs",
         "pairs_evaluated", "n_edges", "n_tile_items", "n_tile_candidates", "n_sweeps", "n_block_pairs", "n_unmapped",
-        "n_unpaired", "n_chimeric", "n_mates_skipped")]
+        "n_unpaired", "n_chimeric", "n_mates_skipped", "key_bits")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
