@@ -54,21 +54,22 @@ def build_bam(path, scale):
 def main():
     scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.1
     threads = sys.argv[2] if len(sys.argv) > 2 else str(min(os.cpu_count() or 1, 16))
-    exe = os.path.join(REPO, "umi-collapse-rs_b200", "host", "umicollapse_gpu")
+    exe = os.environ.get("UMICOLLAPSE_EXE") or os.path.join(REPO, "umi-collapse-rs_b200", "host", "umicollapse_gpu")
     with tempfile.TemporaryDirectory() as td:
         inp, out = os.path.join(td, "in.bam"), os.path.join(td, "out.bam")
         n, rec_len, t_build = build_bam(inp, scale)
         runs = []
-        for mode in ([], ["--two-pass"]):
-            for rep in range(2):          # first run warms the page cache and the CUDA driver
+        for mode in ([], ["--two-pass"]) if not os.environ.get("UMICOLLAPSE_EXE_B") else ([], ["__B__"]):
+            for rep in range(3 if os.environ.get("UMICOLLAPSE_EXE_B") else 2):          # first run warms the page cache and the CUDA driver
                 t0 = time.time()
-                r = subprocess.run([exe, "--mode", "bam", "-i", inp, "-o", out, "--algo", "dir", "--merge", "avgqual", "-k", "1",
-                                    "--num-threads", threads, *mode], capture_output=True, text=True)
+                this_exe = os.environ["UMICOLLAPSE_EXE_B"] if mode == ["__B__"] else exe
+                r = subprocess.run([this_exe, "--mode", "bam", "-i", inp, "-o", out, "--algo", "dir", "--merge", "avgqual", "-k", "1",
+                                    "--num-threads", threads, *([] if mode == ["__B__"] else mode)], capture_output=True, text=True)
                 dt = time.time() - t0
                 assert r.returncode == 0, r.stderr
             phases = {m.group(1): float(m.group(2)) for m in re.finditer(r"phase (.+?): ([0-9.]+) s", r.stderr)}
             kept = int(re.search(r"Number of reads after deduplicating: (\d+)", r.stderr).group(1))
-            runs.append({"mode": "two-pass (streaming)" if mode else "in-memory", "wall_s": dt, "reads_per_s": n / dt, "phases_s": phases, "kept": kept})
+            runs.append({"mode": ("A/B: " + os.path.basename(this_exe)) if os.environ.get("UMICOLLAPSE_EXE_B") else ("two-pass (streaming)" if mode else "in-memory"), "wall_s": dt, "reads_per_s": n / dt, "phases_s": phases, "kept": kept})
         print(json.dumps({"tool": "umicollapse_gpu (C++ CLI twin)", "workload": f"C2 generator x{scale}: {n} reads, {rec_len} B records, 100M CIGAR, coordinate-sorted BAM",
                           "input_bytes": os.path.getsize(inp), "output_bytes": os.path.getsize(out), "threads": int(threads),
                           "host_cores": os.cpu_count(), "runs": runs}))
