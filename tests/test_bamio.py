@@ -98,3 +98,38 @@ def test_oracle_paired_filters_match_literal():
                     assert d["tlen"] == tlen
                 seen.add((d["valid"], d["cls"]))
     assert len(seen) >= 6      # the fixture exercises every branch
+
+
+def test_select_mates_follows_write_reversed():
+    """UcWriter::write / write_reversed (deduplicate_sam.rs:382-462) on the host: for every kept paired read the first
+    mapped last-in-template record with its name at (mate ref, mate pos) is written, once."""
+    import struct
+    from bam_fixtures import make_paired_bam
+    rng = random.Random(19)
+    header, recs = make_paired_bam(rng, 1200)
+    buf = header + b"".join(recs)
+    offs, _ = bamio.record_offsets(buf, len(header))
+    def fields(i):
+        rec = recs[i]
+        flag, = struct.unpack_from("<H", rec, 18)
+        tid, pos = struct.unpack_from("<ii", rec, 4); mtid, mpos = struct.unpack_from("<ii", rec, 24)
+        return rec[36: 36 + rec[12] - 1], flag, tid, pos, mtid, mpos
+    # "kept" = every record that passes the paired filters (what reaches the writer when nothing is a duplicate)
+    kept = [i for i in range(len(recs)) if R.paired_filter(fields(i)[1], fields(i)[2], fields(i)[4], False, False)[0]]
+    mates = bamio.select_mates(buf, offs, np.array(kept, np.int64))
+    assert mates == sorted(set(mates)) and not set(mates) & set(kept)
+    want = {(fields(i)[0], fields(i)[4], fields(i)[5]) for i in kept if fields(i)[1] & 1}
+    seen = set()
+    for m in mates:
+        name, flag, tid, pos, _, _ = fields(m)
+        assert (flag & 1) and (flag & 0x80) and not (flag & 4) and not (flag & 8)      # :429-433
+        assert (name, tid, pos) in want and (name, tid, pos) not in seen                 # :444-458: written once
+        seen.add((name, tid, pos))
+    # nothing that could have been written was left out, and a repeated mate record yields its first copy
+    for i in range(len(recs)):
+        name, flag, tid, pos, _, _ = fields(i)
+        if (flag & 1) and (flag & 0x80) and not (flag & 4) and not (flag & 8) and (name, tid, pos) in want:
+            assert (name, tid, pos) in seen
+            first_copy = min(j for j in range(len(recs)) if recs[j] == recs[i])
+            assert first_copy in mates
+    assert len(mates) > 500
