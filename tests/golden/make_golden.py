@@ -19,9 +19,10 @@ def rand_umi(rng, L, alphabet):
     return "".join(rng.choice(alphabet) for _ in range(L))
 
 
-def make_reads_case(rng, name, n, L, n_pos, algo, merge, k, p, alphabet="ACGT", n_tid=1, neg=False):
+def make_reads_case(rng, name, n, L, n_pos, algo, merge, k, p, alphabet="ACGT", n_tid=1, neg=False, paired=False):
     pool = {}
     tid, pos, rev, umi, score = [], [], [], [], []
+    tlen = [] if paired else None
     for _ in range(n):
         t = rng.randrange(n_tid)
         q = rng.randrange(n_pos) * 7 - (50 if neg else 0)
@@ -32,10 +33,15 @@ def make_reads_case(rng, name, n, L, n_pos, algo, merge, k, p, alphabet="ACGT", 
         if rng.random() < 0.25:
             u[rng.randrange(L)] = rng.choice(alphabet)
         tid.append(t); pos.append(q); rev.append(r); umi.append("".join(u)); score.append(rng.randint(0, 41))
-    kept, ctr = R.dedup(tid, pos, rev, [u.encode() for u in umi], score, algo, merge, k, p)
+        if paired:
+            tlen.append(rng.choice([-310, -150, 0, 150, 151, 310]))      # --paired: PairedAlignment's fourth field
+    kept, ctr = R.dedup(tid, pos, rev, [u.encode() for u in umi], score, algo, merge, k, p, tlen=tlen)
     ctr.pop("dist_calls")
-    return dict(name=name, umi_len=L, algo=algo, merge=merge, k=k, p=p, tid=tid, pos=pos, rev=rev, umi=umi,
+    case = dict(name=name, umi_len=L, algo=algo, merge=merge, k=k, p=p, tid=tid, pos=pos, rev=rev, umi=umi,
                 score=score, kept=kept, counters=ctr)
+    if paired:
+        case["tlen"] = tlen
+    return case
 
 
 def make_bucket_case(rng, name, n, L, algo, k, p, alphabet="ACGT"):
@@ -63,6 +69,10 @@ def main():
                 reads_cases.append(make_reads_case(rng, f"reads{i}", 400, L, 12, algo, merge, k,
                                                    0.5 if i % 3 else 0.3, alphabet, n_tid, neg))
                 i += 1
+    # --paired cases from their own generator state, so that the cases above stay byte-identical
+    prng = random.Random(20261019)
+    for j, algo in enumerate((R.ALGO_DIR, R.ALGO_ADJ_REF, R.ALGO_ADJ_UPSTREAM, R.ALGO_CC)):
+        reads_cases.append(make_reads_case(prng, f"paired{j}", 500, 8, 6, algo, R.MERGE_AVGQUAL, 1, 0.5, "ACGT", 2, j % 2 == 1, paired=True))
     i = 0
     for algo in (R.ALGO_DIR, R.ALGO_ADJ_REF, R.ALGO_ADJ_UPSTREAM, R.ALGO_CC):
         for (L, k, alphabet) in ((5, 1, "ACGT"), (8, 2, "ACGT"), (12, 1, "ACGTN"), (22, 3, "ACGT"), (32, 2, "ACGT"), (21, 1, "ACGTN")):

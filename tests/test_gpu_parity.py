@@ -23,17 +23,19 @@ def arr(umis):
     return np.frombuffer("".join(umis).encode(), dtype=np.uint8).reshape(len(umis), len(umis[0]))
 
 
-def gpu_dedup(tid, pos, rev, umi, score, algo, merge, k, p, flags=0, chunk=0, labels=False):
+def gpu_dedup(tid, pos, rev, umi, score, algo, merge, k, p, flags=0, chunk=0, labels=False, tlen=None):
     ctx = umigpu.Context(umi.shape[1], k, p, algo, merge, 0, flags | (umigpu.FLAG_LABELS if labels else 0))
     n = len(tid)
     tid = np.asarray(tid, np.int32); pos = np.asarray(pos, np.int64); rev = np.asarray(rev, np.uint8)
     score = None if score is None else np.asarray(score, np.int32)
+    tlen = None if tlen is None else np.asarray(tlen, np.int64)
     if chunk:
         for s in range(0, n, chunk):
             e = min(n, s + chunk)
-            ctx.push_reads(tid[s:e], pos[s:e], rev[s:e], umi[s:e], None if score is None else score[s:e], None, s)
+            ctx.push_reads(tid[s:e], pos[s:e], rev[s:e], umi[s:e], None if score is None else score[s:e], None, s,
+                           tlen=None if tlen is None else tlen[s:e])
     else:
-        ctx.push_reads(tid, pos, rev, umi, score, None, 0)
+        ctx.push_reads(tid, pos, rev, umi, score, None, 0, tlen=tlen)
     kept, roots, ctr = ctx.finish()
     ctx.close()
     return kept, roots, ctr
@@ -60,7 +62,7 @@ def small(name, scale, seed=None, **kw):
 def test_golden_reads(case):
     algo = {0: umigpu.ALGO_DIR, 1: umigpu.ALGO_ADJ, 2: umigpu.ALGO_ADJ_UPSTREAM, 3: umigpu.ALGO_CC}[case["algo"]]
     kept, _, ctr = gpu_dedup(case["tid"], case["pos"], case["rev"], arr(case["umi"]), case["score"], algo, case["merge"],
-                             case["k"], case["p"])
+                             case["k"], case["p"], tlen=case.get("tlen"))
     assert kept.astype(np.int64).tolist() == case["kept"]
     for key, v in case["counters"].items():
         assert ctr[key] == v, key

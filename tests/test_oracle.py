@@ -89,7 +89,7 @@ def test_golden_buckets(case):
 @pytest.mark.parametrize("case", GOLD["reads"], ids=lambda c: c["name"])
 def test_golden_reads(case):
     kept, _, ctr = O.dedup(case["tid"], case["pos"], case["rev"], arr(case["umi"]), case["score"], case["algo"],
-                           case["merge"], case["k"], case["p"])
+                           case["merge"], case["k"], case["p"], tlen=case.get("tlen"))
     assert kept.tolist() == case["kept"]
     for key, v in case["counters"].items():
         assert ctr[key] == v, key
