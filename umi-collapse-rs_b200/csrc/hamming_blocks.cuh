@@ -7,10 +7,11 @@
 //                         12 nt): eq[block][j][x][4 groups], bit c of group g = "UMI 32g+c has letter x at position j"
 //   expand_blocks_kernel  one warp per surviving tile pair: tests its 16 x 16 block pairs with the per-block
 //                         letter sets (disjoint-positions bound) and appends the survivors
-//   hamming_blocks        one warp per block pair: four slices of 32 consecutive rows; a slice whose letter sets
-//                         are disjoint from the column block's in more than k positions is skipped; otherwise each
-//                         lane runs its row UMI against the 128 columns: one LDG.128 (L1-resident, 4 distinct
-//                         16-byte rows per warp) and 2(k+1) LOP3 per position.
+//   hamming_blocks        one warp per block pair: the warp stages the column block's words in its own slice of shared
+//                         memory (768 B at 12 nt, __syncwarp only), then runs four slices of 32 consecutive rows; a slice
+//                         whose letter sets are disjoint from the column block's in more than k positions is skipped;
+//                         otherwise each lane runs its row UMI against the 128 columns: one LDS.128 (4 distinct 16-byte rows
+//                         per warp: conflict-free) and 2(k+1) LOP3 per position.
 #pragma once
 #include "common.cuh"
 #include "hamming.cuh"
