@@ -181,6 +181,20 @@ int umigpu_push_reads_paired(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, co
                              const int32_t *score, const int32_t *weight, uint64_t first_read_index);
 
 /*
+ * Compact host format of umigpu_push_reads, for hosts that already hold the UMI as a bit set (the reference builds one per
+ * read, to_bitset utils/mod.rs:63-83): 14 (umi_len <= 16) or 18 bytes per read cross PCIe instead of 29.
+ *   pos32     unclipped position as int32 (BAM positions are 31-bit)
+ *   umi_2bit  2 bits per base, A0 C1 G2 T3, base 0 in the most significant used field (bits [2L-2, 2L)); element type
+ *             uint32_t when umi_len <= 16, uint64_t otherwise
+ *   n_mask    nullable; bit (L-1-b) set = base b is N (its 2-bit field is ignored)
+ *   score8    nullable; avg_qual / MAPQ as uint8 (both are < 256 by construction)
+ * Same semantics as umigpu_push_reads otherwise (single-end; host pointers).  Bits set beyond 2*umi_len / umi_len are reported
+ * like an unknown UMI byte (UMIGPU_ERR_BAD_BASE at run).
+ */
+int umigpu_push_reads_packed(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, const int32_t *pos32, const uint8_t *is_reverse,
+                             const void *umi_2bit, const uint32_t *n_mask, const uint8_t *score8, uint64_t first_read_index);
+
+/*
  * Host feed on the device: `records` holds raw BAM alignment records exactly as they
  * appear in the BGZF-inflated stream (int32 block_size, then block_size bytes), `offsets[i]` is the byte offset
  * of record i's block_size field relative to `records` and offsets[n] the end of the last one

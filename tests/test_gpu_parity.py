@@ -547,3 +547,40 @@ def test_many_contigs_use_the_linear_coordinate_layout(monkeypatch):
     assert ctr_plain["key_bits"] > 64
     for key in ("n_buckets", "total_umis", "max_umis", "n_kept", "n_edges"):
         assert ctr_lin[key] == ctr_plain[key]
+
+
+@pytest.mark.parametrize("L,alphabet", [(8, "ACGT"), (12, "ACGTN"), (16, "ACGT"), (17, "ACGTN"), (20, "ACGT"), (32, "ACGT")])
+def test_compact_host_format_equals_ascii_push(L, alphabet):
+    """umigpu_push_reads_packed (int32 positions, 2-bit UMIs, uint8 scores: 14-18 B/read over PCIe) must give exactly what
+    the ASCII entry gives, and so the oracle's answer."""
+    rng = random.Random(L)
+    n = 5000
+    pool = ["".join(rng.choice(alphabet) for _ in range(L)) for _ in range(60)]
+    umis = []
+    for _ in range(n):
+        u = list(rng.choice(pool))
+        if rng.random() < 0.3:
+            u[rng.randrange(L)] = rng.choice(alphabet)
+        umis.append("".join(u))
+    d = dict(tid=np.array([rng.randrange(3) for _ in range(n)], np.int32), pos=np.array([rng.randrange(9) * 13 - 20 for _ in range(n)], np.int64),
+             rev=np.array([rng.randrange(2) for _ in range(n)], np.uint8), umi=arr(umis), score=np.array([rng.randrange(0, 94) for _ in range(n)], np.int32))
+    ctr = check_against_oracle(d, umigpu.ALGO_DIR, umigpu.MERGE_AVGQUAL, 1, 0.5)
+    kept, _, _ = gpu_dedup(d["tid"], d["pos"], d["rev"], d["umi"], d["score"], umigpu.ALGO_DIR, umigpu.MERGE_AVGQUAL, 1, 0.5)
+    code, nm = umigpu.pack_umis(d["umi"])
+    assert (nm is not None) == ("N" in alphabet)
+    with umigpu.Context(L, 1, 0.5, umigpu.ALGO_DIR, umigpu.MERGE_AVGQUAL) as ctx:
+        half = n // 2 + 1
+        ctx.push_reads_packed(d["tid"][:half], d["pos"][:half].astype(np.int32), d["rev"][:half], code[:half], None if nm is None else nm[:half],
+                              d["score"][:half].astype(np.uint8), 0)
+        ctx.push_reads_packed(d["tid"][half:], d["pos"][half:].astype(np.int32), d["rev"][half:], code[half:], None if nm is None else nm[half:],
+                              d["score"][half:].astype(np.uint8), half)
+        pkept, _, pctr = ctx.finish()
+    assert np.array_equal(kept, pkept)
+    for key in ("total_reads", "n_buckets", "total_umis", "max_umis", "n_kept", "n_edges"):
+        assert ctr[key] == pctr[key]
+    if 2 * L < code.dtype.itemsize * 8:      # a code with bits beyond 2L is rejected like an unknown UMI byte
+        bad = code.copy(); bad[7] |= bad.dtype.type(1) << bad.dtype.type(2 * L)
+        with umigpu.Context(L) as ctx:
+            ctx.push_reads_packed(d["tid"], d["pos"].astype(np.int32), d["rev"], bad, nm, d["score"].astype(np.uint8), 0)
+            with pytest.raises(umigpu.UmiGpuError, match="Unknown character"):
+                ctx.finish()

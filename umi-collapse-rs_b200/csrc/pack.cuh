@@ -215,6 +215,29 @@ __global__ void __launch_bounds__(256) build_keys_kernel(
     if (NW == 2) k1[i] = ub == 64 ? bucket : (ub == 0 ? 0 : bucket >> (64 - ub));
 }
 
+// Compact host format (umigpu_push_reads_packed): 32-bit positions, UMIs already 2 bit/base (u32 when umi_len <= 16, else
+// u64), 8-bit scores.  Widened into the SoA the path works on; N positions get code 0 like in umi_pack_kernel; a code
+// with bits above 2*umi_len, or an N mask with bits above umi_len, is an error (bad_base).
+__global__ void __launch_bounds__(256) unpack_compact_kernel(u64 n, int L, const i32 *__restrict__ pos32, const void *__restrict__ umi_c,
+                                                             const u32 *__restrict__ nmask_c, const u8 *__restrict__ score8,
+                                                             i64 *__restrict__ pos, u64 *__restrict__ umi2, u32 *__restrict__ nmask,
+                                                             i32 *__restrict__ score, DevScalars *sc) {
+    const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    pos[i] = (i64)pos32[i];
+    u64 code = L <= 16 ? (u64)reinterpret_cast<const u32 *>(umi_c)[i] : reinterpret_cast<const u64 *>(umi_c)[i];
+    const u32 nm = nmask_c ? nmask_c[i] : 0u;
+    bool bad = (L < 32 && (code >> (2 * L)) != 0) || (L < 32 && (nm >> L) != 0);
+    if (nm) {
+        u64 spread = 0;
+        for (int b = 0; b < L; b++) if ((nm >> b) & 1u) spread |= 3ull << (2 * b);
+        code &= ~spread;
+    }
+    umi2[i] = code; nmask[i] = nm;
+    if (score) score[i] = (i32)score8[i];
+    if (bad) sc->bad_base = 1;
+}
+
 // Occupied position range of every contig (order-preserving unsigned bias so that the tables can be memset), for the
 // linear coordinate layout.  Coordinate-sorted input: a warp usually holds one contig -> one pair of atomics per warp.
 #define POS_BIAS 0x8000000000000000ull

@@ -286,6 +286,61 @@ extern "C" int umigpu_push_reads_device(umigpu_ctx *ctx, uint64_t n, const int32
     return push_common(ctx, n, tid, unclipped_pos, is_reverse, umi_ascii, score, weight, first_read_index, cudaMemcpyDeviceToDevice);
 }
 
+// Compact host format: 18 (14 when umi_len <= 16) bytes per read over PCIe instead of 29.
+extern "C" int umigpu_push_reads_packed(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, const int32_t *pos32, const uint8_t *is_reverse,
+                                        const void *umi_2bit, const uint32_t *n_mask, const uint8_t *score8, uint64_t first_read_index) {
+    if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (ctx->ran) return fail(ctx, UMIGPU_ERR_STATE, "push after run: call umigpu_reset first");
+    if (n == 0) return UMIGPU_OK;
+    if (!tid || !pos32 || !is_reverse || !umi_2bit) return fail(ctx, UMIGPU_ERR_ARG, "tid/pos32/is_reverse/umi_2bit are null");
+    if (ctx->n_reads + n > 0xfffffffeull) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "more than 2^32-2 reads in one batch");
+    if (ctx->have_score < 0) { ctx->have_score = score8 != nullptr; ctx->have_weight = 0; }
+    if ((score8 != nullptr) != (ctx->have_score == 1) || ctx->have_weight == 1)
+        return fail(ctx, UMIGPU_ERR_ARG, "score/weight must be given for all chunks or for none");
+    if (ctx->have_tlen < 0) ctx->have_tlen = 0;
+    if (ctx->have_tlen == 1) return fail(ctx, UMIGPU_ERR_ARG, "paired and unpaired pushes cannot be mixed in one batch");
+    if (!ctx->chunks.empty()) {
+        const Chunk &c = ctx->chunks.back();
+        if (first_read_index < c.first_index + c.n) return fail(ctx, UMIGPU_ERR_ARG, "chunks must be pushed in ascending read-index order");
+    }
+    const u64 old = ctx->n_reads, tot = old + n;
+    const int L = (int)ctx->cfg.umi_len;
+    const size_t ub = L <= 16 ? 4 : 8;
+    cudaStream_t s = ctx->stream;
+    STAGE_BEGIN(UMIGPU_STAGE_PACK);
+    CK(ctx->d_tid.reserve_keep(tot * 4, old * 4, s)); CK(ctx->d_pos.reserve_keep(tot * 8, old * 8, s)); CK(ctx->d_rev.reserve_keep(tot, old, s));
+    CK(ctx->d_umi2.reserve_keep(tot * 8, old * 8, s)); CK(ctx->d_nmask.reserve_keep(tot * 4, old * 4, s));
+    if (score8) CK(ctx->d_score.reserve_keep(tot * 4, old * 4, s));
+    // staging area for the compact arrays: [pos32 | umi | n_mask | score8], each 16-byte aligned
+    const size_t o_pos = 0, o_umi = (n * 4 + 15) & ~(size_t)15, o_nm = o_umi + ((n * ub + 15) & ~(size_t)15),
+                 o_sc = o_nm + (n_mask ? ((n * 4 + 15) & ~(size_t)15) : 0), total = o_sc + (score8 ? n : 0);
+    CK(ctx->d_ascii.reserve(total));
+    char *st = (char *)ctx->d_ascii.p;
+    CK(cudaMemcpyAsync(ctx->d_tid.as<i32>() + old, tid, n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_rev.as<u8>() + old, is_reverse, n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(st + o_pos, pos32, n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(st + o_umi, umi_2bit, n * ub, cudaMemcpyHostToDevice, s));
+    if (n_mask) CK(cudaMemcpyAsync(st + o_nm, n_mask, n * 4, cudaMemcpyHostToDevice, s));
+    if (score8) CK(cudaMemcpyAsync(st + o_sc, score8, n, cudaMemcpyHostToDevice, s));
+    DevScalars *sc = ctx->d_sc.as<DevScalars>();
+    LAUNCH(unpack_compact_kernel, grid_for(n, 256), 256, n, L, (const i32 *)(st + o_pos), (const void *)(st + o_umi),
+           n_mask ? (const u32 *)(st + o_nm) : (const u32 *)nullptr, score8 ? (const u8 *)(st + o_sc) : (const u8 *)nullptr,
+           ctx->d_pos.as<i64>() + old, ctx->d_umi2.as<u64>() + old, ctx->d_nmask.as<u32>() + old,
+           score8 ? ctx->d_score.as<i32>() + old : (i32 *)nullptr, sc);
+    LAUNCH(range_reduce_kernel, grid_for(n, 256), 256, n, (const i32 *)(ctx->d_tid.as<i32>() + old), (const i64 *)(ctx->d_pos.as<i64>() + old),
+           (const i64 *)nullptr, (const u32 *)(ctx->d_nmask.as<u32>() + old), sc);
+    STAGE_END(UMIGPU_STAGE_PACK);
+    if (ctx->use_orig) {
+        CK(ctx->d_orig.reserve_keep(tot * 4, old * 4, s));
+        LAUNCH(iota_kernel, grid_for(n, 256), 256, n, ctx->d_orig.as<u32>() + old);
+    }
+    ctx->chunks.push_back({old, n, first_read_index});
+    ctx->n_reads = tot;
+    ctx->n_records += n;
+    return UMIGPU_OK;
+}
+
 extern "C" int umigpu_push_reads_paired(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, const int64_t *unclipped_pos,
                                         const uint8_t *is_reverse, const int64_t *tlen, const uint8_t *umi_ascii,
                                         const int32_t *score, const int32_t *weight, uint64_t first_read_index) {

@@ -63,6 +63,8 @@ extern "C" {
     pub fn umigpu_push_reads_paired(ctx: *mut umigpu_ctx, n: u64, tid: *const i32, unclipped_pos: *const i64, is_reverse: *const u8,
                                     tlen: *const i64, umi_ascii: *const u8, score: *const i32, weight: *const i32,
                                     first_read_index: u64) -> c_int;
+    pub fn umigpu_push_reads_packed(ctx: *mut umigpu_ctx, n: u64, tid: *const i32, pos32: *const i32, is_reverse: *const u8,
+                                    umi_2bit: *const c_void, n_mask: *const u32, score8: *const u8, first_read_index: u64) -> c_int;
     pub fn umigpu_push_bam_records(ctx: *mut umigpu_ctx, n: u64, records: *const u8, offsets: *const u64, umi_sep: u8,
                                    first_read_index: u64, n_unmapped: *mut u64) -> c_int;
     pub fn umigpu_bam_record_offsets(buf: *const u8, len: u64, offsets: *mut u64, max_records: u64, n_records: *mut u64,

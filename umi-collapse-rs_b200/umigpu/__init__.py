@@ -3,6 +3,6 @@ from ._lib import (ALGO_ADJ, ALGO_ADJ_UPSTREAM, ALGO_CC, ALGO_DIR, FLAG_KERNEL_D
                    FLAG_PAIRED, FLAG_REMOVE_UNPAIRED, FLAG_REMOVE_CHIMERIC,
                    LIB_PATH, MERGE_ANY, MERGE_AVGQUAL, MERGE_MAPQUAL, STAGES, SYMBOLS, UmiGpuError, load)
 from .api import (Adjacency, AdjacencyUpstream, AnyMerge, AvgQualMerge, Cli, ConnectedComponents, Context,
-                  DeduplicateGPU, Directional, MapQualMerge, Naive, ReadFreq, dedup_sharded, resolve_cli, shard_plan)
+                  DeduplicateGPU, Directional, MapQualMerge, Naive, ReadFreq, dedup_sharded, pack_umis, resolve_cli, shard_plan)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

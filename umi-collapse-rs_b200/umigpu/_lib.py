@@ -24,7 +24,7 @@ SYMBOLS = [
     "umigpu_get_counters", "umigpu_cluster_bucket", "umigpu_remove_near", "umigpu_neighbours",
     "umigpu_avg_qual", "umigpu_stage_ms", "umigpu_launch_count", "umigpu_result_free",
     "umigpu_shard_plan", "umigpu_int_peak", "umigpu_push_bam_records", "umigpu_bam_record_offsets",
-    "umigpu_dedup_sharded", "umigpu_free", "umigpu_push_reads_paired", "umigpu_device_init",
+    "umigpu_dedup_sharded", "umigpu_free", "umigpu_push_reads_paired", "umigpu_device_init", "umigpu_push_reads_packed",
 ]
 
 
@@ -78,6 +78,7 @@ def load() -> C.CDLL:
     for name in ("umigpu_push_reads", "umigpu_push_reads_device"):
         getattr(lib, name).argtypes = [p, u64, p, p, p, p, p, p, u64]
     lib.umigpu_device_init.argtypes = [i32]
+    lib.umigpu_push_reads_packed.argtypes = [p, u64, p, p, p, p, p, p, u64]
     lib.umigpu_push_reads_paired.argtypes = [p, u64, p, p, p, p, p, p, p, u64]
     lib.umigpu_push_bam_records.argtypes = [p, u64, p, p, C.c_uint8, u64, C.POINTER(u64)]
     lib.umigpu_bam_record_offsets.argtypes = [p, u64, p, u64, C.POINTER(u64), C.POINTER(u64)]

@@ -58,6 +58,26 @@ def resolve_cli(args: Cli) -> tuple[int, int]:
     return ALGO_BY_NAME[args.algo_str], MERGE_BY_NAME[merge_str]
 
 
+def pack_umis(umi_ascii: np.ndarray):
+    """[n, L] uint8 ASCII -> (2-bit codes as uint32/uint64, N masks or None): the host-side half of the compact format
+    (what the reference's to_bitset does per read, utils/mod.rs:63-83).  Raises on bytes outside ACGTN."""
+    n, Lu = umi_ascii.shape
+    lut = np.full(256, 255, np.uint8)
+    for c, v in zip(b"ACGT", range(4)):
+        lut[c] = v
+    lut[ord("N")] = 4
+    v = lut[umi_ascii]
+    if (v == 255).any():
+        raise ValueError("Unknown character in UMI sequence")
+    isn = v == 4
+    code = np.zeros(n, np.uint64)
+    nm = np.zeros(n, np.uint32)
+    for b in range(Lu):
+        code = (code << np.uint64(2)) | np.where(isn[:, b], 0, v[:, b]).astype(np.uint64)
+        nm |= isn[:, b].astype(np.uint32) << np.uint32(Lu - 1 - b)
+    return (code.astype(np.uint32) if Lu <= 16 else code), (nm if isn.any() else None)
+
+
 def _ptr(a):
     """Pointer of a numpy array (host) or torch tensor (host or device); None -> NULL."""
     if a is None:
@@ -135,6 +155,15 @@ class Context:
             torch.cuda.current_stream(tid.device).synchronize()
         fn = self._lib.umigpu_push_reads_device if dev else self._lib.umigpu_push_reads
         L.check(fn(self._h, n, *[_ptr(a) for a in arrs], first_read_index), self._h)
+
+    def push_reads_packed(self, tid, pos32, rev, umi_2bit, n_mask=None, score8=None, first_read_index: int = 0):
+        """umigpu_push_reads_packed: the compact host format (int32 positions, 2-bit UMIs as uint32/uint64, uint8 scores)."""
+        n = int(tid.shape[0])
+        udt = "uint32" if self.umi_len <= 16 else "uint64"
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=dt)
+                for a, dt in ((tid, "int32"), (pos32, "int32"), (rev, "uint8"), (umi_2bit, udt), (n_mask, "uint32"), (score8, "uint8"))]
+        self._keepalive.append(arrs)
+        L.check(self._lib.umigpu_push_reads_packed(self._h, n, *[_ptr(a) for a in arrs], first_read_index), self._h)
 
     def run(self):
         L.check(self._lib.umigpu_run(self._h), self._h)
