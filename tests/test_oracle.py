@@ -225,3 +225,35 @@ def test_all_core_variant_equals_single_thread():
     finally:
         O.set_threads(1)
     assert a[0].tolist() == b[0].tolist() and a[1].tolist() == b[1].tolist() and a[2] == b[2]
+
+
+def test_hypothesis_properties_of_the_path():
+    """Property tests (hypothesis) of the oracle, i.e. of the reference's algorithm under the canonical tie-break:
+    (1) the kept (bucket, UMI) groups do not depend on the order of the reads; (2) splitting the input by bucket and
+    deduplicating the parts separately gives the union (buckets are independent — what the multi-GPU sharding relies on);
+    (3) adding an exact duplicate of a read never changes which (bucket, UMI) groups survive for adj/cc."""
+    from hypothesis import given, settings, strategies as st
+
+    read = st.tuples(st.integers(0, 1), st.integers(-2, 3), st.integers(0, 1), st.text("ACG", min_size=4, max_size=4), st.integers(0, 40))
+
+    def groups(reads, algo):
+        tid, pos, rev, umi, score = (list(x) for x in zip(*reads))
+        kept, _, _ = O.dedup(tid, pos, rev, arr(umi), score, algo, O.MERGE_AVGQUAL, 1, 0.5)
+        return {(tid[i], pos[i], rev[i], umi[i]) for i in kept.tolist()}, kept.tolist()
+
+    @settings(max_examples=120, deadline=None)
+    @given(st.lists(read, min_size=1, max_size=60), st.randoms(use_true_random=False), st.sampled_from([O.ALGO_DIR, O.ALGO_CC, O.ALGO_ADJ_REF, O.ALGO_ADJ_UPSTREAM]))
+    def check(reads, rnd, algo):
+        g, _ = groups(reads, algo)
+        shuffled = list(reads); rnd.shuffle(shuffled)
+        assert groups(shuffled, algo)[0] == g                                  # (1)
+        even = [r for r in reads if r[1] % 2 == 0]; odd = [r for r in reads if r[1] % 2 != 0]
+        parts = set()
+        for part in (even, odd):
+            if part:
+                parts |= groups(part, algo)[0]
+        assert parts == g                                                      # (2)
+        if algo in (O.ALGO_CC, O.ALGO_ADJ_REF):
+            assert groups(reads + [reads[0]], algo)[0] == g                     # (3)
+
+    check()
