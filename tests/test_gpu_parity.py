@@ -584,3 +584,21 @@ def test_compact_host_format_equals_ascii_push(L, alphabet):
             ctx.push_reads_packed(d["tid"], d["pos"].astype(np.int32), d["rev"], bad, nm, d["score"].astype(np.uint8), 0)
             with pytest.raises(umigpu.UmiGpuError, match="Unknown character"):
                 ctx.finish()
+
+
+def test_read_order_does_not_change_the_surviving_groups():
+    """Size-independent property (no oracle needed): the (bucket, UMI) groups that survive depend on frequencies and UMIs
+    only, never on the order in which the reads arrive; shuffling 2.5 M reads must keep exactly the same groups."""
+    d, cfg = small("C2", 0.05, seed=9)
+    n = len(d["tid"])
+    perm = np.random.default_rng(1).permutation(n)
+    def groups(dd):
+        kept, _, ctr = gpu_dedup(dd["tid"], dd["pos"], dd["rev"], dd["umi"], dd["score"], umigpu.ALGO_DIR, umigpu.MERGE_AVGQUAL, 1, 0.5)
+        k = kept.astype(np.int64)
+        key = np.concatenate([dd["tid"][k, None].astype(np.int64), dd["pos"][k, None], dd["rev"][k, None].astype(np.int64), dd["umi"][k].astype(np.int64)], axis=1)
+        return {tuple(r) for r in key.tolist()}, ctr
+    g0, c0 = groups(d)
+    g1, c1 = groups({kk: v[perm] for kk, v in d.items()})
+    assert g0 == g1 and len(g0) == c0["n_kept"] == c1["n_kept"]
+    for key in ("n_buckets", "total_umis", "max_umis", "n_edges"):
+        assert c0[key] == c1[key]
