@@ -128,6 +128,7 @@ enum {
     UMIGPU_STAGE_CLUSTER,       /* K6 cluster (label propagation)           */
     UMIGPU_STAGE_EMIT,          /* K7 emit_compact                          */
     UMIGPU_STAGE_TOTAL,         /* run() first launch -> last launch        */
+    UMIGPU_STAGE_HOT_BAND,      /* sharded run: this rank's band of the hot bucket (import, K5, edges out) */
     UMIGPU_N_STAGES
 };
 
@@ -265,25 +266,88 @@ uint64_t umigpu_launch_count(umigpu_ctx *ctx, int reset);
 void umigpu_result_free(umigpu_ctx *ctx);
 
 /*
- * Multi-GPU sharding plan: buckets are independent, so each device takes a
- * slice balanced by sum N_b^2 with no collective.  Given per-read bucket keys on the host it
- * assigns every read to one of n_shards with longest-processing-time-first over estimated
- * bucket cost (reads_in_bucket^2); shard_of_read[n] receives the shard id.  Pure host helper.
+ * ---- Several devices, ONE dataset ------------------------------------------------------------
+ * Buckets never interact (deduplicate_sam.rs:207-213 handles each map entry alone), so the path shards by bucket
+ * with no collective.  A coordinate-sorted stream is cut at bucket starts into one CONTIGUOUS slice per device
+ * (umigpu_shard_plan_sorted): slice r is reads [cuts[r], cuts[r+1]) — a plain pointer offset into the host arrays,
+ * one H2D range per device — and because the slices are ascending index ranges the merged kept list is the
+ * concatenation of the ranks' kept lists.  The one exchange step: a bucket that outweighs a device's fair share
+ * (the hot locus of a skewed run) stays on one device up to the unique/count stage, then its neighbour search is
+ * split over all devices of the group through peer-addressable EXCHANGE WINDOWS (cudaMemcpyAsync over NVLink /
+ * NVSwitch: unique-UMI arrays out, edges back), and the owner clusters it.
  */
-int umigpu_shard_plan(uint64_t n, const int32_t *tid, const int64_t *unclipped_pos, const uint8_t *is_reverse,
-                      int32_t n_shards, int32_t *shard_of_read, uint64_t *shard_cost /* n_shards */);
+typedef struct umigpu_hot {
+    int32_t  present;      /* 0 = no bucket is split                                                            */
+    int32_t  owner;        /* rank whose slice holds the bucket                                                 */
+    uint64_t read_index;   /* caller's index of ONE read of the bucket (identifies it on the owner)              */
+    uint64_t reads_est;    /* estimated reads in the bucket (sizes the exchange windows)                         */
+} umigpu_hot;
+
+/* (contig, position) as one ordered int64: the key space of the cuts.  Valid for |unclipped_pos| < 2^35. */
+int64_t umigpu_pos_key(int32_t tid, int64_t unclipped_pos);
 
 /*
- * One call, several GPUs of one box: plans the shards with umigpu_shard_plan, runs one context per
- * device on its own host thread (push -> run -> fetch), and merges the survivors back into input order.  No
- * collective and no peer traffic: buckets never interact (deduplicate_sam.rs:207-213).  device_ids may repeat a
- * device.  *kept receives a malloc'ed array of *n_kept ascending read indices (free with umigpu_free); counters
- * are summed over shards (max_umis is the maximum).  cfg->device and cfg->stream are ignored.
+ * Plan for a stream sorted by (tid, unclipped_pos) (strand and UMI in any order).  Pure host helper, O(65536 probes +
+ * log n): cuts[0..n_shards] ascending read indices with cuts[0] = 0, cuts[n_shards] = n, every cut on the first read of
+ * a (tid, pos); cut_keys[s] = umigpu_pos_key of read cuts[s] (INT64_MIN / INT64_MAX at the ends): slice s must only hold
+ * keys in [cut_keys[s], cut_keys[s+1]) — umigpu_run_sharded verifies that on the device, so an unsorted stream is an
+ * error, never a wrong answer.  Slices are balanced on a cost model fitted to the measured stages (linear per read +
+ * quadratic search and linear clustering per big bucket).  *hot describes the bucket to split, if one holds at least
+ * hot_min_reads reads (0 = default 2^20, UINT64_MAX = never split).  shard_cost (nullable) receives the modelled cost.
  */
+int umigpu_shard_plan_sorted(uint64_t n, const int32_t *tid, const int64_t *unclipped_pos, const uint8_t *is_reverse,
+                             int32_t n_shards, uint64_t hot_min_reads, uint64_t *cuts /* n_shards + 1 */,
+                             int64_t *cut_keys /* n_shards + 1 */, umigpu_hot *hot, double *shard_cost /* n_shards */);
+
+/*
+ * Exchange window of one rank: device memory holding the hot bucket's unique-UMI arrays (when this rank owns it) and
+ * one inbox region per rank for edges.  Every rank of a group creates its window with the SAME sizes, then attaches to
+ * the others': ranks in different processes exchange the 64-byte CUDA IPC handle (ipc_handle_out) by any means and call
+ * umigpu_xchg_attach_ipc with all n_ranks handles in rank order; ranks inside one process call umigpu_xchg_attach_local
+ * with the group's contexts (peer access is enabled as needed; the same device may appear more than once).
+ */
+int umigpu_xchg_create(umigpu_ctx *ctx, int32_t rank, int32_t n_ranks, uint64_t max_hot_uniques, uint64_t max_hot_edges,
+                       uint8_t *ipc_handle_out /* 64 bytes, nullable */);
+int umigpu_xchg_attach_ipc(umigpu_ctx *ctx, const uint8_t *handles /* n_ranks x 64 bytes */);
+int umigpu_xchg_attach_local(umigpu_ctx *ctx, umigpu_ctx *const *group /* n_ranks contexts, rank order */);
+
+/*
+ * umigpu_run for one rank of a group: the reads pushed into ctx are slice `rank` of the plan (first_read_index =
+ * cuts[rank]); key_lo / key_hi = cut_keys[rank] / cut_keys[rank + 1].  With hot->present every rank of the group must
+ * make this call (a rank with an empty slice too): the owner publishes the bucket, every rank searches the row tiles
+ * ti with ti % n_ranks == rank, the owner gathers the edges and clusters.  hot may be NULL (or present = 0): the ranks
+ * are then fully independent and no window is needed.  Results through umigpu_fetch as usual.
+ */
+int umigpu_run_sharded(umigpu_ctx *ctx, const umigpu_hot *hot, int64_t key_lo, int64_t key_hi);
+
+/*
+ * One process, several devices (what the Rust host calls): a persistent group of contexts.  umigpu_group_dedup plans
+ * (umigpu_shard_plan_sorted), pushes every device its slice straight from the caller's arrays on its own host thread,
+ * runs umigpu_run_sharded and concatenates.  *kept receives a malloc'ed array of *n_kept ascending read indices (free
+ * with umigpu_free); counters are summed over ranks (max_umis, n_sweeps, key_bits: maximum); rank_ms (nullable) the
+ * device time of every rank's run.  Input that is not coordinate-sorted is detected by the devices and re-run through
+ * the hash plan below (gather per shard on the host).  device_ids may repeat a device.
+ */
+typedef struct umigpu_group umigpu_group;
+int  umigpu_group_create(const umigpu_config *cfg, int32_t n_devices, const int32_t *device_ids, umigpu_group **out);
+void umigpu_group_destroy(umigpu_group *g);
+umigpu_ctx *umigpu_group_context(umigpu_group *g, int32_t rank);
+int  umigpu_group_dedup(umigpu_group *g, uint64_t n, const int32_t *tid, const int64_t *unclipped_pos, const uint8_t *is_reverse,
+                        const uint8_t *umi_ascii, const int32_t *score, uint64_t **kept, uint64_t *n_kept,
+                        umigpu_counters *counters, float *rank_ms);
+/* create + dedup + destroy.  cfg->device and cfg->stream are ignored. */
 int umigpu_dedup_sharded(const umigpu_config *cfg, int32_t n_devices, const int32_t *device_ids, uint64_t n,
                          const int32_t *tid, const int64_t *unclipped_pos, const uint8_t *is_reverse, const uint8_t *umi_ascii,
                          const int32_t *score, uint64_t **kept, uint64_t *n_kept, umigpu_counters *counters);
 void umigpu_free(void *p);
+
+/*
+ * Hash plan for reads in ARBITRARY order: longest-processing-time-first over per-bucket cost (reads^2 + 64 reads),
+ * shard_of_read[n] receives the shard id; the caller gathers each shard's reads.  Pure host helper, one hash probe per
+ * read — use umigpu_shard_plan_sorted whenever the stream is coordinate-sorted (a BAM is).
+ */
+int umigpu_shard_plan(uint64_t n, const int32_t *tid, const int64_t *unclipped_pos, const uint8_t *is_reverse,
+                      int32_t n_shards, int32_t *shard_of_read, uint64_t *shard_cost /* n_shards */);
 
 /* integer-pipe microbenchmark used as the roofline denominator of the neighbour search:
  * ops/s of a dependent-free LOP3 stream and of POPC on the context's device. */

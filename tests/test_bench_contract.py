@@ -18,7 +18,9 @@ def test_reference_arm_prints_one_contract_line():
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"].startswith("C2")
+    assert d["config"]["workload"].startswith("C5")
+    # the sample size is part of the config: the two arms never claim the same config on different input sizes
+    assert d["config"]["sample_reads"] == 400000 and d["pairs_per_s"] > 0 and d["dist_calls_per_s"] > 0 and d["scaling"] == "strong"
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -195,7 +195,7 @@ __device__ __forceinline__ bool mi_accept(const MiParams &mi, unsigned long long
     for (int q = 0; q < mi.part; q++) if (!(x & mi.cmask[q])) return false;   // ... and on no earlier one
     return true;
 }
-struct BucketIsBig { const u32 *bstart; u32 big; __device__ u32 operator()(u64 b) const { return bstart[b + 1] - bstart[b] > big ? 1u : 0u; } };
+struct BucketIsBig { const u32 *bstart; u32 big; u32 skip; __device__ u32 operator()(u64 b) const { return (b != skip && bstart[b + 1] - bstart[b] > big) ? 1u : 0u; } };
 struct BucketBigEmit {
     u32 *brank, *big_bid; u64 n_buckets;
     __device__ void operator()(u64 b, u32 flag, u32 ex) const { brank[b] = flag ? ex : 0xffffffffu; if (flag) big_bid[ex] = (u32)b; }
@@ -255,11 +255,12 @@ __device__ __forceinline__ bool item_filtered(const TileItem &it) { return (it.c
 __device__ __forceinline__ u32 bucket_tiles(u32 nb) { return (nb + HT_ROWS - 1) / HT_ROWS; }
 
 // number of tile pairs (ti <= tj) of a bucket; buckets with one UMI need no comparison at all
+// `skip` = a bucket left out of this device's search (sharded run: the hot bucket is searched by the whole group)
 struct BucketItems {
-    const u32 *bstart;
+    const u32 *bstart; u32 skip;
     __device__ u32 operator()(u64 b) const {
         u32 nb = bstart[b + 1] - bstart[b];
-        if (nb <= SMALL_BUCKET) return 0;          // 0/1 UMIs: nothing to compare; 2..32: small_buckets_kernel
+        if (nb <= SMALL_BUCKET || b == skip) return 0;          // 0/1 UMIs: nothing to compare; 2..32: small_buckets_kernel
         u32 t = bucket_tiles(nb);
         return t * (t + 1) / 2;
     }
@@ -298,8 +299,8 @@ __global__ void __launch_bounds__(256) bucket_stats_kernel(u32 n_buckets, const 
 #define TS_WORDS 8      // letter-set words per tile (A C G T N + padding)
 
 struct BucketTiles {
-    const u32 *bstart;
-    __device__ u32 operator()(u64 b) const { u32 nb = bstart[b + 1] - bstart[b]; return nb <= SMALL_BUCKET ? 0 : bucket_tiles(nb); }
+    const u32 *bstart; u32 skip;
+    __device__ u32 operator()(u64 b) const { u32 nb = bstart[b + 1] - bstart[b]; return (nb <= SMALL_BUCKET || b == skip) ? 0 : bucket_tiles(nb); }
 };
 struct BucketTilesEmit {
     u32 *tile_off; u64 n_buckets;
@@ -311,8 +312,8 @@ struct BucketTilesEmit {
 
 // 128-UMI blocks of the buckets that go through the tile / block path (global block id = blk_off[b] + local block)
 struct BucketBlocks {
-    const u32 *bstart;
-    __device__ u32 operator()(u64 b) const { u32 nb = bstart[b + 1] - bstart[b]; return nb <= SMALL_BUCKET ? 0 : (nb + 127) / 128; }
+    const u32 *bstart; u32 skip;
+    __device__ u32 operator()(u64 b) const { u32 nb = bstart[b + 1] - bstart[b]; return (nb <= SMALL_BUCKET || b == skip) ? 0 : (nb + 127) / 128; }
 };
 
 __device__ __forceinline__ void onehot_planes(uint2 p, u32 pn, u32 lmask, u32 *oh /*5*/) {
@@ -378,7 +379,7 @@ __device__ __forceinline__ u32 disjoint_positions(const u32 *a, const u32 *b, u3
 __global__ void __launch_bounds__(256) build_items_kernel(u32 n_cand, u32 n_buckets, const u32 *__restrict__ item_off,
                                                           const u32 *__restrict__ bstart, const u32 *__restrict__ tile_off,
                                                           const u32 *__restrict__ blk_off, const u32 *__restrict__ tsum, int L, int k, int cull,
-                                                          MiParams mi, TileItem *__restrict__ items, DevScalars *sc) {
+                                                          MiParams mi, TileItem *__restrict__ items, DevScalars *sc, u32 band, u32 n_bands) {
     u32 w = blockIdx.x * 256 + threadIdx.x;
     u64 npairs = 0;
     bool live = false;
@@ -406,15 +407,18 @@ __global__ void __launch_bounds__(256) build_items_kernel(u32 n_cand, u32 n_buck
         const bool filt = mi.part >= 0 && nb > mi.big;         // multi-index pass: big buckets only see near-diagonal blocks
         it.cnts = rc | (cc << 12) | (filt ? 0x40000000u : 0u) | (ti == tj ? 0x80000000u : 0u);
         it.col_blk0 = blk_off[b] + tj * BLOCKS_PER_TILE;
-        live = true;
-        if (cull && ti != tj) {
+        // sharded hot bucket: the row tiles are dealt out to the devices of the group round robin (near-diagonal survivors
+        // make every row tile about equally expensive)
+        live = n_bands <= 1 || (ti % n_bands) == band;
+        if (!live) {
+        } else if (cull && ti != tj) {
             u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
             const u32 *a = tsum + (u64)(tile_off[b] + ti) * TS_WORDS, *c = tsum + (u64)(tile_off[b] + tj) * TS_WORDS;
             live = disjoint_positions(a, c, lmask) <= (u32)k;
             if (live && filt) live = disjoint_positions(a, c, mi.pmask[mi.part]) == 0;
             if (live) npairs = (u64)rc * cc;          // the pair space the density heuristic compares with: before the range test
             if (live && filt) live = a[6] >= c[5];    // part-q value ranges overlap
-        } else if (live) npairs = (u64)rc * cc;
+        } else npairs = (u64)rc * cc;
     }
     // warp-aggregated append
     u32 m = __ballot_sync(0xffffffffu, live);

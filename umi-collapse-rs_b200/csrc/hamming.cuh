@@ -102,10 +102,10 @@ __global__ void __launch_bounds__(HT_THREADS) hamming_tiles_direct(
 // per lane, every other UMI of the bucket arrives by shuffle.  No shared memory, no tile item.
 __global__ void __launch_bounds__(256) small_buckets_kernel(u32 n_buckets, const u32 *__restrict__ bstart,
                                                             const uint2 *__restrict__ planes, const u32 *__restrict__ nplane,
-                                                            int k, EdgeSink es, unsigned long long *pairs_eval) {
+                                                            int k, EdgeSink es, unsigned long long *pairs_eval, u32 skip) {
     const u32 b = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = lane_id();
     u64 np = 0;
-    if (b < n_buckets) {
+    if (b < n_buckets && b != skip) {
         const u32 s = bstart[b], nb = bstart[b + 1] - s;
         if (nb >= 2 && nb <= SMALL_BUCKET) {
             const bool v = lane < nb;

@@ -28,6 +28,10 @@ struct DevScalars {
     u32 n_big, m_big;
     i64 tlen_min, tlen_max;          // paired mode: template length is part of the bucket key (deduplicate_sam.rs:545-552)
     u64 n_unpaired, n_chimeric, n_mates_skipped, n_bam_unmapped;   // running totals over the BAM pushes of this batch
+    u32 n_lowered, unsorted;         // label lowerings of the last sweep; bucket part of the keys not non-decreasing in input order
+    u32 frontier_cnt[2];             // frontier clustering: sizes of the two ping-pong frontiers
+    u32 hot_bucket, hot_u0, hot_cnt, hot_pad;   // sharded run: the bucket whose neighbour search is split across devices
+    i64 key_lo, key_hi;              // sharded run: smallest / largest (tid << 32 | biased pos) of the slice (range check of the cuts)
 };
 
 struct KeyLayout {

@@ -4,6 +4,10 @@
 
 #include "pack.cuh"
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <queue>
 #include <thread>
 #include <stdarg.h>
@@ -69,6 +73,17 @@ struct umigpu_ctx {
 
     cudaEvent_t ev[UMIGPU_N_STAGES][2];
     bool ev_ok[UMIGPU_N_STAGES];
+
+    // state handed from stage to stage of one run
+    bool st_weighted = false, st_need_edges = false;
+    int sorted_cur = 0;                   // which ping-pong buffer holds the sorted keys / indices
+    DevBuf d_stamp, d_rowptr, d_front[2]; // frontier clustering
+    // sharded run (several devices, one dataset): see "shard group" below
+    u32 skip_bucket = 0xffffffffu;        // owner: the hot bucket is searched by every device of the group, not here
+    u32 band = 0, n_bands = 1;            // hot child: this device evaluates the row tiles ti with ti % n_bands == band
+    struct Xchg *x = nullptr;
+    umigpu_ctx *hot = nullptr;            // child context that runs this device's band of the hot bucket
+    bool is_child = false;
 };
 
 static int fail(umigpu_ctx *ctx, int code, const char *fmt, ...) {
@@ -154,6 +169,8 @@ extern "C" int umigpu_create(const umigpu_config *cfg, umigpu_ctx **out) {
     return umigpu_reset(ctx);
 }
 
+static void xchg_release(umigpu_ctx *ctx);
+
 extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
@@ -171,6 +188,9 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
     if (ctx->h_roots) cudaFreeHost(ctx->h_roots);
     if (ctx->h_umirep) cudaFreeHost(ctx->h_umirep);
     ctx->d_chunks.release(); ctx->d_umirep.release();
+    ctx->d_stamp.release(); ctx->d_rowptr.release(); ctx->d_front[0].release(); ctx->d_front[1].release();
+    if (ctx->hot) { umigpu_destroy(ctx->hot); ctx->hot = nullptr; }
+    xchg_release(ctx);
     DevBuf *bb[] = {&ctx->d_bamraw, &ctx->d_bamoff, &ctx->d_btid, &ctx->d_bpos, &ctx->d_brev, &ctx->d_bumi2, &ctx->d_bnmask, &ctx->d_bscore, &ctx->d_bvalid, &ctx->d_orig};
     for (DevBuf *b : bb) b->release();
     for (int s = 0; s < UMIGPU_N_STAGES; s++) { if (ctx->ev[s][0]) cudaEventDestroy(ctx->ev[s][0]); if (ctx->ev[s][1]) cudaEventDestroy(ctx->ev[s][1]); }
@@ -191,6 +211,8 @@ static int init_scalars(umigpu_ctx *ctx) {
     z.tid_min = 0x7fffffff; z.tid_max = (i32)0x80000000;
     z.pos_min = 0x7fffffffffffffffLL; z.pos_max = (i64)0x8000000000000000LL;
     z.tlen_min = 0x7fffffffffffffffLL; z.tlen_max = (i64)0x8000000000000000LL;
+    z.key_lo = 0x7fffffffffffffffLL; z.key_hi = (i64)0x8000000000000000LL;
+    z.hot_bucket = 0xffffffffu;
     *ctx->h_sc = z;
     CK(cudaMemcpyAsync(ctx->d_sc.p, ctx->h_sc, sizeof z, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));   // h_sc is reused as the read-back buffer
@@ -499,7 +521,7 @@ struct NView {
 
 // Work list (tile pairs -> block pairs) and evaluation for one ordering.  *dense is set (and nothing is evaluated)
 // when a multi-index pass finds that culling does not thin the work out: the caller then restarts without it.
-static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, EdgeSink es, bool has_n, int cull, bool allow_blocks, bool *dense) {
+static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, EdgeSink es, bool has_n, int cull, bool allow_blocks, bool *dense, u32 skip) {
     const umigpu_config &cfg = ctx->cfg;
     DevScalars *sc = ctx->d_sc.as<DevScalars>();
     const int k = cfg.k, L = (int)cfg.umi_len;
@@ -509,11 +531,11 @@ static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, E
     CK(ctx->d_itemoff.reserve(((size_t)B + 1) * 4));
     CK(ctx->d_tileoff.reserve(((size_t)B + 1) * 4));
     CK(ctx->d_blkoff.reserve(((size_t)B + 1) * 4));
-    int rc = run_scan(ctx, BucketItems{v.bstart}, BucketItemsEmit{ctx->d_itemoff.as<u32>(), B}, B, &sc->n_cand);
+    int rc = run_scan(ctx, BucketItems{v.bstart, skip}, BucketItemsEmit{ctx->d_itemoff.as<u32>(), B}, B, &sc->n_cand);
     if (rc) return rc;
-    rc = run_scan(ctx, BucketTiles{v.bstart}, BucketTilesEmit{ctx->d_tileoff.as<u32>(), B}, B, &sc->n_tiles);
+    rc = run_scan(ctx, BucketTiles{v.bstart, skip}, BucketTilesEmit{ctx->d_tileoff.as<u32>(), B}, B, &sc->n_tiles);
     if (rc) return rc;
-    rc = run_scan(ctx, BucketBlocks{v.bstart}, BucketTilesEmit{ctx->d_blkoff.as<u32>(), B}, B, &sc->n_blocks);
+    rc = run_scan(ctx, BucketBlocks{v.bstart, skip}, BucketTilesEmit{ctx->d_blkoff.as<u32>(), B}, B, &sc->n_blocks);
     if (rc) return rc;
     rc = read_scalars(ctx);
     if (rc) return rc;
@@ -536,7 +558,7 @@ static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, E
     CK(cudaMemsetAsync(&sc->n_items, 0, 4, ctx->stream));
     CK(cudaMemsetAsync(&sc->scratch2, 0, 8, ctx->stream));
     LAUNCH(build_items_kernel, grid_for(n_cand, 256), 256, n_cand, B, (const u32 *)ctx->d_itemoff.p, v.bstart, (const u32 *)ctx->d_tileoff.p,
-           (const u32 *)ctx->d_blkoff.p, (const u32 *)ctx->d_tsum.p, L, k, cull, mi, ctx->d_items.as<TileItem>(), sc);
+           (const u32 *)ctx->d_blkoff.p, (const u32 *)ctx->d_tsum.p, L, k, cull, mi, ctx->d_items.as<TileItem>(), sc, ctx->band, ctx->n_bands);
     rc = read_scalars(ctx);
     if (rc) return rc;
     const u32 W = ctx->h_sc->n_items;
@@ -602,21 +624,11 @@ static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, E
 // ------------------------------------------------------------------------------------------------
 enum RunMode { RUN_FULL = 0, RUN_EDGES_ONLY = 1 };
 
-
-static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_inf_thr) {
-    if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
-    CK(cudaSetDevice(ctx->cfg.device));
-    if (ctx->ran) return fail(ctx, UMIGPU_ERR_STATE, "run called twice without reset");
+// ---- stage 1: key layout, K1b keys, K2 sort, K3 unique / count / merge, bucket segmentation ----
+static int stage_group(umigpu_ctx *ctx, bool want_labels, bool force_inf_thr) {
     const u64 n = ctx->n_reads;
     const umigpu_config &cfg = ctx->cfg;
-    memset(&ctx->ctr, 0, sizeof ctx->ctr);
-    ctx->ctr.total_reads = ctx->n_records;          // deduplicate_sam.rs:100 counts every record, mapped or not
-    ctx->ctr.n_unmapped = ctx->n_unmapped;
-    ctx->ctr.n_unpaired = ctx->h_sc->n_unpaired; ctx->ctr.n_chimeric = ctx->h_sc->n_chimeric; ctx->ctr.n_mates_skipped = ctx->h_sc->n_mates_skipped;
-    ctx->ran = true;
-    if (n == 0) return UMIGPU_OK;
     DevScalars *sc = ctx->d_sc.as<DevScalars>();
-    STAGE_BEGIN(UMIGPU_STAGE_TOTAL);
 
     // ---- key layout from the batch's ranges ----
     int rc = read_scalars(ctx);
@@ -701,6 +713,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     rc = run_sort(ctx, n, lay.nw, rs_plan(lay.total_bits), &cur);
     if (rc) return rc;
     STAGE_END(UMIGPU_STAGE_SORT);
+    ctx->sorted_cur = cur;
     SortedKeys sk{ctx->d_key[cur][0].as<u64>(), lay.nw == 2 ? ctx->d_key[cur][1].as<u64>() : nullptr, lay.umi_bits};
     const u32 *sorted_idx = ctx->d_idx[cur].as<u32>();
 
@@ -713,6 +726,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     if (has_n) CK(ctx->d_nplane.reserve(n * 4));
     CK(ctx->d_bhead.reserve(n));
     const bool weighted = ctx->have_weight == 1;
+    ctx->st_weighted = weighted;
     if (weighted) { CK(ctx->d_wsum.reserve(n * 4)); CK(cudaMemsetAsync(ctx->d_wsum.p, 0, n * 4, ctx->stream)); }
     if (want_labels) CK(ctx->d_read_uid.reserve(n * 4));
     CK(cudaMemsetAsync(ctx->d_rep.p, 0, n * 8, ctx->stream));
@@ -750,7 +764,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
            ctx->d_planes.as<uint2>(), ctx->d_nplane.as<u32>());
     STAGE_END(UMIGPU_STAGE_UNIQUE);
 
-    // ---- buckets + work list ----
+    // ---- buckets ----
     STAGE_BEGIN(UMIGPU_STAGE_WORKLIST);
     CK(ctx->d_bstart.reserve(((size_t)U + 1) * 4));
     CK(ctx->d_ubkt.reserve((size_t)U * 4));
@@ -761,12 +775,27 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     const u32 B = ctx->h_sc->n_buckets;
     ctx->n_buckets = B;
     LAUNCH(bucket_stats_kernel, grid_for(B, 256), 256, B, (const u32 *)ctx->d_bstart.p, sc);
+    STAGE_END(UMIGPU_STAGE_WORKLIST);
+    return UMIGPU_OK;
+}
 
+// ---- stage 2: K5 neighbour search over the buckets of ctx (unique arrays, bstart, ubkt, freq, thr) -> ctx->d_edges ----
+// ctx->skip_bucket is left out (its search is shared by the shard group); a hot child evaluates only its band of row tiles.
+static int stage_neighbours(umigpu_ctx *ctx, int mode) {
+    const umigpu_config &cfg = ctx->cfg;
+    DevScalars *sc = ctx->d_sc.as<DevScalars>();
+    const KeyLayout &lay = ctx->lay;
+    const bool has_n = lay.has_n != 0;
+    const u32 U = ctx->n_unique, B = ctx->n_buckets;
+    const u32 skip = ctx->skip_bucket;
+    int rc;
     const bool need_edges = (mode == RUN_EDGES_ONLY || cfg.algo != UMIGPU_ALGO_ADJ) && cfg.k > 0 && U > B;
+    ctx->st_need_edges = need_edges;
     const int cull = (cfg.flags & UMIGPU_FLAG_NO_CULL) ? 0 : 1;
     const int k = cfg.k, L = lay.umi_len;
     const bool allow_blocks = !(cfg.flags & (UMIGPU_FLAG_KERNEL_DIRECT | UMIGPU_FLAG_KERNEL_TILES)) && k >= 1 && k <= 3 && !(has_n && L > 24) && cull;
     u64 n_edges = 0;
+    STAGE_BEGIN(UMIGPU_STAGE_NEIGHBOURS);
     // ---- multi-index preparation: which buckets are big, their compacted unique list ----
     const int P = k + 1;                                   // parts (pigeonhole)
     bool mi_on = need_edges && allow_blocks && !(cfg.flags & UMIGPU_FLAG_NO_MULTI_INDEX) && L >= 2 * P;
@@ -783,7 +812,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
             mi0.cmask[q] = (((len * bpb) >= 64 ? ~0ull : ((1ull << (len * bpb)) - 1))) << (part_lo[q] * bpb);
         }
         CK(ctx->d_brank.reserve((size_t)B * 4)); CK(ctx->d_bigbid.reserve((size_t)B * 4));
-        rc = run_scan(ctx, BucketIsBig{ctx->d_bstart.as<u32>(), MI_BIG}, BucketBigEmit{ctx->d_brank.as<u32>(), ctx->d_bigbid.as<u32>(), B}, B, &sc->n_big);
+        rc = run_scan(ctx, BucketIsBig{ctx->d_bstart.as<u32>(), MI_BIG, skip}, BucketBigEmit{ctx->d_brank.as<u32>(), ctx->d_bigbid.as<u32>(), B}, B, &sc->n_big);
         if (rc) return rc;
         rc = read_scalars(ctx);
         if (rc) return rc;
@@ -800,10 +829,8 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
         CK(ctx->d_biguid.reserve((size_t)m_big * 4)); CK(ctx->d_miplanes.reserve((size_t)m_big * 8)); CK(ctx->d_miucode.reserve((size_t)m_big * 8));
         CK(ctx->d_miuid.reserve((size_t)m_big * 4)); if (has_n) CK(ctx->d_minplane.reserve((size_t)m_big * 4));
     }
-    STAGE_END(UMIGPU_STAGE_WORKLIST);
 
     // ---- K5 neighbours ----
-    STAGE_BEGIN(UMIGPU_STAGE_NEIGHBOURS);
     if (need_edges) {
         u64 cap = std::max<u64>((u64)1 << 20, (u64)U * 8);
         if (ctx->d_edges.cap / sizeof(uint2) > cap) cap = ctx->d_edges.cap / sizeof(uint2);
@@ -841,7 +868,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
                 ctx->stream = ctx->side;
                 int r2 = [&]() -> int {
                     LAUNCH(small_buckets_kernel, grid_for((u64)B * 32, 256), 256, B, (const u32 *)ctx->d_bstart.p, (const uint2 *)ctx->d_planes.p,
-                           has_n ? (const u32 *)ctx->d_nplane.p : (const u32 *)nullptr, cfg.k, es, (unsigned long long *)&sc->pairs_eval);
+                           has_n ? (const u32 *)ctx->d_nplane.p : (const u32 *)nullptr, cfg.k, es, (unsigned long long *)&sc->pairs_eval, skip);
                     if (mi_on && P > 1) return mi_prepare(1);
                     return UMIGPU_OK;
                 }();
@@ -853,7 +880,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
             // pass 0: every bucket with more than 32 unique UMIs in the main order (big buckets filtered on part 0)
             MiParams mi = mi0; mi.part = mi_on ? 0 : -1;
             bool dense = false;
-            rc = neighbour_pass(ctx, main_view, mi, es, has_n, cull, allow_blocks, &dense);
+            rc = neighbour_pass(ctx, main_view, mi, es, has_n, cull, allow_blocks, &dense, skip);
             CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));      // join (also before a restart or an error return)
             if (rc) return rc;
             if (dense) { mi_on = false; continue; }          // culling does not thin this input out: restart without multi-index
@@ -863,7 +890,7 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
                 const NView view{ctx->d_miplanes.as<uint2>(), has_n ? ctx->d_minplane.as<u32>() : (const u32 *)nullptr, ctx->d_miucode.as<u64>(),
                                  ctx->d_miuid.as<u32>(), ctx->d_bstartbig.as<u32>(), nbig};
                 mi.part = q;
-                rc = neighbour_pass(ctx, view, mi, es, has_n, cull, true, &dense);
+                rc = neighbour_pass(ctx, view, mi, es, has_n, cull, true, &dense, 0xffffffffu);
                 if (rc) return rc;
                 if (dense) break;
             }
@@ -886,9 +913,16 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     ctx->ctr.unordered_pairs = ctx->h_sc->pairs;
     ctx->ctr.pairs_evaluated = ctx->h_sc->pairs_eval + (ctx->used_direct ? ctx->direct_pairs : 0);
     ctx->ctr.n_edges = n_edges;
-    if (mode == RUN_EDGES_ONLY) { STAGE_END(UMIGPU_STAGE_TOTAL); return UMIGPU_OK; }
+    return UMIGPU_OK;
+}
 
-    // ---- K6 cluster ----
+// ---- stage 3: K6 cluster over ctx->d_edges[0, ctx->n_edges) ----
+static int stage_cluster(umigpu_ctx *ctx) {
+    const umigpu_config &cfg = ctx->cfg;
+    DevScalars *sc = ctx->d_sc.as<DevScalars>();
+    const u32 U = ctx->n_unique;
+    const u64 n_edges = ctx->n_edges;
+    int rc;
     STAGE_BEGIN(UMIGPU_STAGE_CLUSTER);
     u8 *keep = ctx->d_keep.as<u8>();
     unsigned long long *label = ctx->d_label.as<unsigned long long>();
@@ -914,28 +948,81 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
         LAUNCH(mis_label_kernel, egrid, 256, edges, n_edges, prio, (const u8 *)ctx->d_state.p, label);
         LAUNCH(mis_keep_kernel, grid_for(U, 256), 256, U, (const u8 *)ctx->d_state.p, keep);
     } else {
-      // Plain sweeps first: they have the lowest cost per sweep, and in-place atomicMin lets a label travel several hops
-      // per sweep (C2 settles in 12, C5's 5 M-UMI locus in 40).  Measured on C5, neither the two-phase scheme after 8
-      // sweeps (11.5 ms) nor a pointer jump after every sweep (19.9 ms) beats 40 plain sweeps (10.5 ms), so the
-      // two-phase scheme (O(log) rounds whatever the chain length) is only the safety net for graphs that are still
-      // moving after 64 sweeps.
+      // Plain sweeps first: they have the lowest cost per sweep while most labels still move, and in-place atomicMin lets a
+      // label travel several hops per sweep.  A sweep skips every edge whose source was not lowered since the sweep before
+      // (stamp array), so late sweeps cost the edge stream only.  Graphs that are still moving after 4 sweeps while few labels
+      // change per sweep (hot loci: a percolating component of frequency-1 UMIs, tens of hops deep) switch to the frontier
+      // form: edges sorted by source once, then rounds over the lowered UMIs only (C5: 40 sweeps x 3.1e7 edges = 10.9 ms
+      // before).  The two-phase scheme (mutual components + contracted graph, O(log) rounds whatever the chain length)
+      // remains the safety net for graphs that are still moving after UMIGPU_PLAIN_ROUNDS rounds of 4 sweeps / 4096 frontier rounds.
       // test knobs: UMIGPU_SV_MIN_EDGES (default 8 Mi) = smallest edge count that may switch to the two-phase scheme,
-      // UMIGPU_PLAIN_ROUNDS (default 16) = rounds of 4 plain sweeps tried first
+      // UMIGPU_PLAIN_ROUNDS (default 16) = rounds of 4 plain sweeps tried first, UMIGPU_FRONTIER_MIN_EDGES (default 2 Mi;
+      // 0 = never) = smallest edge count that may switch to the frontier form
       bool converged = false;
-      const char *e_sv = getenv("UMIGPU_SV_MIN_EDGES"), *e_pr = getenv("UMIGPU_PLAIN_ROUNDS");
+      const char *e_sv = getenv("UMIGPU_SV_MIN_EDGES"), *e_pr = getenv("UMIGPU_PLAIN_ROUNDS"), *e_fr = getenv("UMIGPU_FRONTIER_MIN_EDGES");
       const u64 sv_min = e_sv ? strtoull(e_sv, nullptr, 10) : (u64)(8u << 20);
       const int plain_rounds = e_pr ? atoi(e_pr) : 16;
+      const u64 fr_min = e_fr ? strtoull(e_fr, nullptr, 10) : (u64)(2u << 20);
       const bool big_graph = n_edges >= sv_min;
+      const bool sv_forced = e_sv != nullptr || e_pr != nullptr;          // the tests drive the two-phase scheme through these
+      const bool may_frontier = fr_min != 0 && n_edges >= fr_min && !sv_forced && U < 0xfffffff0u;
       if (big_graph) { CK(ctx->d_prio.reserve((size_t)U * 8)); CK(cudaMemcpyAsync(ctx->d_prio.p, label, (size_t)U * 8, cudaMemcpyDeviceToDevice, ctx->stream)); }
-      for (int round = 0; !converged && (round < plain_rounds || !big_graph); round++) {
+      CK(ctx->d_stamp.reserve((size_t)U * 4));
+      CK(cudaMemsetAsync(ctx->d_stamp.p, 0, (size_t)U * 4, ctx->stream));
+      u32 *stamp = ctx->d_stamp.as<u32>();
+      u32 sweep_no = 0;
+      // UMIGPU_FRONTIER_FORCE=1 (tests): no plain sweeps at all, the first frontier is every UMI
+      bool use_frontier = getenv("UMIGPU_FRONTIER_FORCE") != nullptr && !sv_forced && U < 0xfffffff0u;
+      for (int round = 0; !use_frontier && !converged && (round < plain_rounds || !big_graph); round++) {
           CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
-          for (int i = 0; i < 4; i++) LAUNCH(label_sweep_kernel, egrid, 256, edges, n_edges, label, sc);
+          for (int i = 0; i < 4; i++) {
+              if (i == 3) CK(cudaMemsetAsync(&sc->n_lowered, 0, 4, ctx->stream));
+              LAUNCH(label_sweep_kernel, egrid, 256, edges, n_edges, label, sc, stamp, ++sweep_no);
+          }
           sweeps += 4;
           rc = read_scalars(ctx);
           if (rc) return rc;
-          converged = !ctx->h_sc->changed;
+          converged = !ctx->h_sc->changed || ctx->h_sc->n_lowered == 0;
+          // still moving, but the last sweep lowered few labels compared with the edges it streamed: the frontier form pays
+          if (!converged && may_frontier && (u64)ctx->h_sc->n_lowered * 16 < n_edges) { use_frontier = true; break; }
+      }
+      if (!converged && use_frontier) {
+          // CSR by source: radix sort of (src << 32 | dst) on the source bits, rows cut at source changes
+          CK(ctx->d_key[0][0].reserve(n_edges * 8)); CK(ctx->d_key[1][0].reserve(n_edges * 8));
+          CK(ctx->d_idx[0].reserve(n_edges * 4)); CK(ctx->d_idx[1].reserve(n_edges * 4));
+          LAUNCH(edges_pack_kernel, grid_for(n_edges, 256), 256, edges, n_edges, ctx->d_key[0][0].as<u64>());
+          SortPlan plan; plan.npass = 0;
+          { const int nb = std::max(1, bits_for((u64)U - 1)); int done = 0; const int np = (nb + RS_RB - 1) / RS_RB;
+            for (int i = 0; i < np; i++) { int b = (nb - done + (np - i) - 1) / (np - i); plan.p[plan.npass++] = {0, 32 + done, b}; done += b; } }
+          int cur = 0;
+          rc = run_sort(ctx, n_edges, 1, plan, &cur);
+          if (rc) return rc;
+          const u64 *keys = ctx->d_key[cur][0].as<u64>();
+          CK(ctx->d_rowptr.reserve(((size_t)U + 2) * 4));
+          LAUNCH(csr_rows_kernel, grid_for(n_edges + 1, 256), 256, keys, n_edges, U, ctx->d_rowptr.as<u32>());
+          CK(ctx->d_front[0].reserve((size_t)U * 4)); CK(ctx->d_front[1].reserve((size_t)U * 4));
+          CK(cudaMemsetAsync(&sc->frontier_cnt[0], 0, 8, ctx->stream));
+          LAUNCH(frontier_init_kernel, grid_for(U, 256), 256, U, (const u32 *)stamp, sweep_no, ctx->d_front[0].as<u32>(), &sc->frontier_cnt[0]);
+          const u32 fgrid = (u32)ctx->num_sms * 8;
+          int in = 0;
+          u64 rounds = 0;
+          while (!converged && rounds < 4096) {
+              for (int i = 0; i < 8; i++) {
+                  CK(cudaMemsetAsync(&sc->frontier_cnt[in ^ 1], 0, 4, ctx->stream));
+                  LAUNCH(frontier_relax_kernel, fgrid, 256, (const u32 *)ctx->d_rowptr.p, keys, label, stamp, (const u32 *)ctx->d_front[in].p,
+                         (const u32 *)&sc->frontier_cnt[in], ctx->d_front[in ^ 1].as<u32>(), &sc->frontier_cnt[in ^ 1], ++sweep_no);
+                  in ^= 1;
+              }
+              rounds += 8; sweeps += 8;
+              rc = read_scalars(ctx);
+              if (rc) return rc;
+              if (ctx->h_sc->sort_err) return fail(ctx, UMIGPU_ERR_CUDA, "radix sort look-back exceeded its spin budget");
+              converged = ctx->h_sc->frontier_cnt[in] == 0;
+          }
+          if (!converged && !big_graph) return fail(ctx, UMIGPU_ERR_CUDA, "label propagation did not settle in 4096 frontier rounds");
       }
       if (!converged) {
+        if (!big_graph) return fail(ctx, UMIGPU_ERR_STATE, "internal: label propagation left its loop without a fixpoint");
         CK(cudaMemcpyAsync(label, ctx->d_prio.p, (size_t)U * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         // Phase A: mutual components (hook + jump), Phase B: contracted propagation (cluster.cuh)
         CK(ctx->d_comp.reserve((size_t)U * 4));
@@ -973,8 +1060,17 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     }
     ctx->ctr.n_sweeps = sweeps;
     STAGE_END(UMIGPU_STAGE_CLUSTER);
+    return UMIGPU_OK;
+}
 
-    // ---- K7 emit ----
+// ---- stage 4: K7 emit ----
+static int stage_emit(umigpu_ctx *ctx, bool want_labels) {
+    DevScalars *sc = ctx->d_sc.as<DevScalars>();
+    const u64 n = ctx->n_reads;
+    const u32 U = ctx->n_unique;
+    u8 *keep = ctx->d_keep.as<u8>();
+    unsigned long long *label = ctx->d_label.as<unsigned long long>();
+    int rc;
     STAGE_BEGIN(UMIGPU_STAGE_EMIT);
     u64 n_words = ceil_div_u64(n, 32);
     CK(ctx->d_bitmap.reserve(n_words * 4));
@@ -1004,6 +1100,35 @@ static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_
     if (rc) return rc;
     ctx->ctr.n_kept = ctx->h_sc->n_kept;
     return UMIGPU_OK;
+}
+
+static int run_begin(umigpu_ctx *ctx) {
+    if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (ctx->ran) return fail(ctx, UMIGPU_ERR_STATE, "run called twice without reset");
+    memset(&ctx->ctr, 0, sizeof ctx->ctr);
+    ctx->ctr.total_reads = ctx->n_records;          // deduplicate_sam.rs:100 counts every record, mapped or not
+    ctx->ctr.n_unmapped = ctx->n_unmapped;
+    ctx->ctr.n_unpaired = ctx->h_sc->n_unpaired; ctx->ctr.n_chimeric = ctx->h_sc->n_chimeric; ctx->ctr.n_mates_skipped = ctx->h_sc->n_mates_skipped;
+    ctx->ran = true;
+    ctx->n_unique = ctx->n_buckets = 0; ctx->n_edges = 0;
+    ctx->skip_bucket = 0xffffffffu;
+    return UMIGPU_OK;
+}
+
+static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_inf_thr) {
+    int rc = run_begin(ctx);
+    if (rc) return rc;
+    if (ctx->n_reads == 0) return UMIGPU_OK;
+    STAGE_BEGIN(UMIGPU_STAGE_TOTAL);
+    rc = stage_group(ctx, want_labels, force_inf_thr);
+    if (rc) return rc;
+    rc = stage_neighbours(ctx, mode);
+    if (rc) return rc;
+    if (mode == RUN_EDGES_ONLY) { STAGE_END(UMIGPU_STAGE_TOTAL); return UMIGPU_OK; }
+    rc = stage_cluster(ctx);
+    if (rc) return rc;
+    return stage_emit(ctx, want_labels);
 }
 
 extern "C" int umigpu_run(umigpu_ctx *ctx) {
@@ -1304,12 +1429,14 @@ extern "C" int umigpu_shard_plan(uint64_t n, const int32_t *tid, const int64_t *
     return UMIGPU_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// several GPUs of one box in one call: shard by bucket, one context + one host thread per device, merge
-// ------------------------------------------------------------------------------------------------
 extern "C" void umigpu_free(void *p) { free(p); }
 
-extern "C" int umigpu_dedup_sharded(const umigpu_config *cfg, int32_t n_devices, const int32_t *device_ids, uint64_t n,
+// ------------------------------------------------------------------------------------------------
+// several GPUs of one box, inputs in ARBITRARY order: hash plan (umigpu_shard_plan), gather per shard, one context + one host
+// thread per device, k-way merge.  Fallback of umigpu_dedup_sharded for inputs that are not coordinate-sorted.
+// ------------------------------------------------------------------------------------------------
+
+static int dedup_sharded_lpt(const umigpu_config *cfg, int32_t n_devices, const int32_t *device_ids, uint64_t n,
                                     const int32_t *tid, const int64_t *unclipped_pos, const uint8_t *is_reverse,
                                     const uint8_t *umi_ascii, const int32_t *score, uint64_t **kept, uint64_t *n_kept,
                                     umigpu_counters *counters) {
@@ -1384,4 +1511,625 @@ extern "C" int umigpu_dedup_sharded(const umigpu_config *cfg, int32_t n_devices,
         }
     }
     return UMIGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shard group: ONE dataset over several devices (deduplicate_sam.rs:207-213: buckets never interact)
+//
+// The coordinate-sorted read stream is cut at bucket boundaries into one contiguous slice per device (a contiguous H2D
+// range, no gather on the host); every device runs the whole path on its slice and returns ascending kept indices, so the
+// merged result is the concatenation in rank order.  No collective.
+//
+// The exception is a bucket that is bigger than a device's fair share (the hot locus of a skewed run): its reads stay on
+// one device (the owner) up to K3, then its neighbour search is split.  The owner publishes the bucket's unique-UMI arrays
+// in its EXCHANGE WINDOW (device memory the other devices of the group can address: peer access inside one process,
+// CUDA IPC between processes); every device copies them over NVLink, searches the row tiles ti with ti % n == rank
+// (stage_neighbours on a child context), and copies its edges into its region of the owner's window; the owner
+// appends them to its edge list and clusters.  All transfers are cudaMemcpyAsync (copy engines over NVLink / NVSwitch);
+// hand-over is a flag word written after the data in stream order and polled by the consumer's host thread — no kernel
+// ever spins on a peer, so nothing can deadlock against an implicit device synchronisation (cudaFree).
+// ------------------------------------------------------------------------------------------------
+#define XCHG_MAX_RANKS 16
+struct XchgSlot { unsigned long long count, epoch; };      // rank r -> owner: count (bit 63 = region overflow) first, epoch last
+struct XchgHeader {
+    unsigned long long info;        // hot_cnt | has_n << 32 | err << 33, written before `ready`
+    unsigned long long ready;       // epoch of the arrays in this window
+    XchgSlot slot[XCHG_MAX_RANKS];
+    unsigned long long ucap, ecap, n_ranks;    // what the window was created with (checked at attach)
+    unsigned long long pad[27];
+};
+static_assert(sizeof(XchgHeader) == 512, "exchange header layout");
+
+struct Xchg {
+    int rank = 0, n = 1;
+    bool ipc = false;
+    char *local = nullptr;
+    std::vector<char *> peer;       // window of every rank as this device addresses it (peer[rank] == local)
+    std::vector<char> opened;       // peer[r] came from cudaIpcOpenMemHandle
+    u64 ucap = 0, ecap = 0, region = 0, epoch = 0;
+    size_t off_planes = 0, off_ucode = 0, off_freq = 0, off_thr = 0, off_nplane = 0, off_inbox = 0, bytes = 0;
+    unsigned long long *h_pin = nullptr;      // pinned: [0] info [1] ready [2] count [3] epoch, [8..] poll buffer
+    cudaStream_t xs = nullptr;                // polling stream
+    double timeout_s = 120.0;
+    std::atomic<int> *abort = nullptr;        // in-process groups: set when a rank of the group failed (waits give up at once)
+};
+
+static void xchg_release(umigpu_ctx *ctx) {
+    Xchg *x = ctx->x;
+    if (!x) return;
+    for (size_t r = 0; r < x->peer.size(); r++) if (x->opened[r] && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
+    if (x->local) cudaFree(x->local);
+    if (x->h_pin) cudaFreeHost(x->h_pin);
+    if (x->xs) cudaStreamDestroy(x->xs);
+    delete x;
+    ctx->x = nullptr;
+}
+
+extern "C" int umigpu_xchg_create(umigpu_ctx *ctx, int32_t rank, int32_t n_ranks, uint64_t max_hot_uniques, uint64_t max_hot_edges,
+                                  uint8_t *ipc_handle_out /* 64 bytes, nullable */) {
+    if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
+    if (n_ranks < 1 || n_ranks > XCHG_MAX_RANKS || rank < 0 || rank >= n_ranks)
+        return fail(ctx, UMIGPU_ERR_ARG, "umigpu_xchg_create: rank %d of %d (at most %d ranks)", rank, n_ranks, XCHG_MAX_RANKS);
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    xchg_release(ctx);
+    Xchg *x = new (std::nothrow) Xchg();
+    if (!x) return fail(ctx, UMIGPU_ERR_NOMEM, "out of host memory");
+    ctx->x = x;
+    x->rank = rank; x->n = n_ranks;
+    x->ucap = std::max<u64>(max_hot_uniques, 64);
+    x->region = std::max<u64>(ceil_div_u64(std::max<u64>(max_hot_edges, 1), (u64)n_ranks), 1024);
+    x->ecap = x->region * (u64)n_ranks;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o = sizeof(XchgHeader);
+    x->off_planes = o; o = al(o + x->ucap * 8);
+    x->off_ucode = o;  o = al(o + x->ucap * 8);
+    x->off_freq = o;   o = al(o + x->ucap * 4);
+    x->off_thr = o;    o = al(o + x->ucap * 4);
+    x->off_nplane = o; o = al(o + x->ucap * 4);
+    x->off_inbox = o;  o = al(o + x->ecap * 8);
+    x->bytes = o;
+    if (const char *e = getenv("UMIGPU_XCHG_TIMEOUT_S")) x->timeout_s = atof(e);
+    CK(cudaMalloc((void **)&x->local, x->bytes));                 // cudaMalloc (not the async pool): the window is IPC-exportable
+    XchgHeader h; memset(&h, 0, sizeof h);
+    h.ucap = x->ucap; h.ecap = x->ecap; h.n_ranks = (u64)n_ranks;
+    CK(cudaMemcpy(x->local, &h, sizeof h, cudaMemcpyHostToDevice));
+    CK(cudaMallocHost((void **)&x->h_pin, (8 + 2 * XCHG_MAX_RANKS) * sizeof(unsigned long long)));
+    CK(cudaStreamCreateWithFlags(&x->xs, cudaStreamNonBlocking));
+    x->peer.assign((size_t)n_ranks, nullptr); x->opened.assign((size_t)n_ranks, 0);
+    x->peer[(size_t)rank] = x->local;
+    if (ipc_handle_out) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+        cudaIpcMemHandle_t hd;
+        CK(cudaIpcGetMemHandle(&hd, x->local));
+        memcpy(ipc_handle_out, &hd, 64);
+    }
+    return UMIGPU_OK;
+}
+
+static int xchg_check_peer(umigpu_ctx *ctx, int r) {
+    Xchg *x = ctx->x;
+    XchgHeader h;
+    CK(cudaMemcpy(&h, x->peer[(size_t)r], sizeof h, cudaMemcpyDefault));
+    if (h.ucap != x->ucap || h.ecap != x->ecap || h.n_ranks != (u64)x->n)
+        return fail(ctx, UMIGPU_ERR_ARG, "exchange window of rank %d was created with other sizes (%llu uniques / %llu edges / %llu ranks)", r,
+                    (unsigned long long)h.ucap, (unsigned long long)h.ecap, (unsigned long long)h.n_ranks);
+    return UMIGPU_OK;
+}
+
+extern "C" int umigpu_xchg_attach_ipc(umigpu_ctx *ctx, const uint8_t *handles /* n_ranks x 64 bytes, rank order */) {
+    if (!ctx || !ctx->x || !handles) return fail(ctx, UMIGPU_ERR_ARG, "umigpu_xchg_attach_ipc: no exchange window / null handles");
+    CK(cudaSetDevice(ctx->cfg.device));
+    Xchg *x = ctx->x;
+    x->ipc = true;
+    for (int r = 0; r < x->n; r++) {
+        if (r == x->rank) continue;
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, handles + (size_t)r * 64, 64);
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        x->peer[(size_t)r] = (char *)p; x->opened[(size_t)r] = 1;
+        int rc = xchg_check_peer(ctx, r);
+        if (rc) return rc;
+    }
+    return UMIGPU_OK;
+}
+
+extern "C" int umigpu_xchg_attach_local(umigpu_ctx *ctx, umigpu_ctx *const *group /* n_ranks contexts of THIS process, rank order */) {
+    if (!ctx || !ctx->x || !group) return fail(ctx, UMIGPU_ERR_ARG, "umigpu_xchg_attach_local: no exchange window / null group");
+    CK(cudaSetDevice(ctx->cfg.device));
+    Xchg *x = ctx->x;
+    for (int r = 0; r < x->n; r++) {
+        if (r == x->rank) continue;
+        umigpu_ctx *o = group[r];
+        if (!o || !o->x || !o->x->local) return fail(ctx, UMIGPU_ERR_ARG, "rank %d of the group has no exchange window", r);
+        if (o->cfg.device != ctx->cfg.device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, ctx->cfg.device, o->cfg.device));
+            if (!can) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "device %d cannot address device %d (no peer access)", ctx->cfg.device, o->cfg.device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->cfg.device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); else CK(e);
+        }
+        x->peer[(size_t)r] = o->x->local;
+        int rc = xchg_check_peer(ctx, r);
+        if (rc) return rc;
+    }
+    return UMIGPU_OK;
+}
+
+// combined (contig, position) key of the cuts: monotone in (tid, pos) for |pos| < 2^35
+static inline i64 host_pos_key(i32 tid, i64 pos) { return (i64)((u64)(i64)tid << 36) + pos; }
+extern "C" int64_t umigpu_pos_key(int32_t tid, int64_t unclipped_pos) { return host_pos_key(tid, unclipped_pos); }
+
+__global__ void __launch_bounds__(256) slice_range_kernel(u64 n, const i32 *__restrict__ tid, const i64 *__restrict__ pos, DevScalars *sc) {
+    const u64 stride = (u64)gridDim.x * 256;
+    long long lo = 0x7fffffffffffffffLL, hi = (long long)0x8000000000000000LL;
+    u32 bad = 0;
+    for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        const i64 p = pos[i];
+        if (p >= (1LL << 35) || p < -(1LL << 35)) bad = 1;
+        const long long k = (long long)((u64)(i64)tid[i] << 36) + p;
+        lo = k < lo ? k : lo; hi = k > hi ? k : hi;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = l2 < lo ? l2 : lo; hi = h2 > hi ? h2 : hi;
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if (lane_id() == 0) {
+        if (lo <= hi) { atomicMin((long long *)&sc->key_lo, lo); atomicMax((long long *)&sc->key_hi, hi); }
+        if (bad) sc->hot_pad = 1;
+    }
+}
+// sorted position of one read (push-order position `target`)
+__global__ void __launch_bounds__(256) find_read_kernel(u64 n, const u32 *__restrict__ sorted_idx, u32 target, DevScalars *sc) {
+    const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i < n && sorted_idx[i] == target) sc->scratch = i;
+}
+// ... -> its unique -> its bucket
+__global__ void hot_locate_kernel(DevScalars *sc, const u32 *__restrict__ useg, u32 n_unique, const u32 *__restrict__ ubkt, const u32 *__restrict__ bstart) {
+    const u64 p = sc->scratch;
+    if (p == ~0ull) { sc->hot_bucket = 0xffffffffu; sc->hot_u0 = sc->hot_cnt = 0; return; }
+    u32 lo = 0, hi = n_unique;               // last u with useg[u] <= p
+    while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if ((u64)useg[mid] <= p) lo = mid; else hi = mid; }
+    const u32 b = ubkt[lo];
+    sc->hot_bucket = b; sc->hot_u0 = bstart[b]; sc->hot_cnt = bstart[b + 1] - bstart[b];
+}
+__global__ void __launch_bounds__(256) hot_child_init_kernel(u32 n_unique, u32 *__restrict__ bstart, u32 *__restrict__ ubkt) {
+    const u32 u = blockIdx.x * 256 + threadIdx.x;
+    if (u < n_unique) ubkt[u] = 0;
+    if (u == 0) { bstart[0] = 0; bstart[1] = n_unique; }
+}
+__global__ void __launch_bounds__(256) hot_append_kernel(const uint2 *__restrict__ in, u64 n, u32 u0, uint2 *__restrict__ out) {
+    const u64 e = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (e < n) { const uint2 ed = in[e]; out[e] = make_uint2(ed.x + u0, ed.y + u0); }
+}
+
+// host-side wait on a word of a window: small peer reads on the polling stream until pred(value)
+template <class Pred>
+static int xchg_poll(umigpu_ctx *ctx, const char *src, size_t bytes, Pred pred, const char *what) {
+    Xchg *x = ctx->x;
+    unsigned long long *buf = x->h_pin + 8;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (u64 it = 0;; it++) {
+        CK(cudaMemcpyAsync(buf, src, bytes, cudaMemcpyDefault, x->xs));
+        CK(cudaStreamSynchronize(x->xs));
+        if (pred(buf)) return UMIGPU_OK;
+        if (x->abort && x->abort->load()) return fail(ctx, UMIGPU_ERR_STATE, "shard group: rank %d gave up waiting for %s: another rank failed", x->rank, what);
+        if ((it & 63) == 63) {
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (dt > x->timeout_s) return fail(ctx, UMIGPU_ERR_STATE, "shard group: rank %d waited %.0f s for %s (a rank of the group failed or never ran)", x->rank, dt, what);
+        }
+        if (it > 256) std::this_thread::yield();
+    }
+}
+
+// owner: find the hot bucket among this slice's buckets, copy its unique arrays into the window, publish
+static int hot_publish(umigpu_ctx *ctx, const umigpu_hot *hot, u32 *u0_out) {
+    Xchg *x = ctx->x;
+    DevScalars *sc = ctx->d_sc.as<DevScalars>();
+    const u64 n = ctx->n_reads;
+    const bool has_n = ctx->lay.has_n != 0;
+    u64 local = ~0ull;
+    for (const Chunk &c : ctx->chunks) if (hot->read_index >= c.first_index && hot->read_index < c.first_index + c.n) local = c.start + (hot->read_index - c.first_index);
+    u32 hb = 0xffffffffu, u0 = 0, uh = 0;
+    const char *why = nullptr;
+    int rc = UMIGPU_OK;
+    if (ctx->use_orig) why = "the BAM feed cannot be combined with a split hot bucket";
+    else if (local == ~0ull || n == 0) why = "the hot bucket's read is not in the owner's slice";
+    if (!why) {
+        CK(cudaMemsetAsync(&sc->scratch, 0xff, 8, ctx->stream));
+        LAUNCH(find_read_kernel, grid_for(n, 256), 256, n, (const u32 *)ctx->d_idx[ctx->sorted_cur].p, (u32)local, sc);
+        LAUNCH(hot_locate_kernel, 1, 1, sc, (const u32 *)ctx->d_useg.p, ctx->n_unique, (const u32 *)ctx->d_ubkt.p, (const u32 *)ctx->d_bstart.p);
+        rc = read_scalars(ctx);
+        if (rc) return rc;
+        hb = ctx->h_sc->hot_bucket; u0 = ctx->h_sc->hot_u0; uh = ctx->h_sc->hot_cnt;
+        if (hb == 0xffffffffu) why = "the hot bucket's read was not found after the sort";
+        else if ((u64)uh > x->ucap) why = "the exchange window is too small for the hot bucket's unique UMIs";
+    }
+    if (!why) {
+        char *w = x->local;
+        CK(cudaMemcpyAsync(w + x->off_planes, ctx->d_planes.as<uint2>() + u0, (size_t)uh * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(w + x->off_ucode, ctx->d_ucode.as<u64>() + u0, (size_t)uh * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(w + x->off_freq, ctx->d_freq.as<i32>() + u0, (size_t)uh * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(w + x->off_thr, ctx->d_thr.as<i32>() + u0, (size_t)uh * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (has_n) CK(cudaMemcpyAsync(w + x->off_nplane, ctx->d_nplane.as<u32>() + u0, (size_t)uh * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    // info first, ready last (stream order = the order the words land in the window)
+    x->h_pin[0] = why ? (1ull << 33) : ((unsigned long long)uh | ((unsigned long long)(has_n ? 1 : 0) << 32));
+    x->h_pin[1] = x->epoch;
+    CK(cudaMemcpyAsync(x->local + offsetof(XchgHeader, info), &x->h_pin[0], 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(x->local + offsetof(XchgHeader, ready), &x->h_pin[1], 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (why) { cudaStreamSynchronize(ctx->stream); return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "shard group: %s (%u unique UMIs, window holds %llu)", why, uh, (unsigned long long)x->ucap); }
+    ctx->skip_bucket = hb;
+    *u0_out = u0;
+    return UMIGPU_OK;
+}
+
+// every rank: import the hot bucket's arrays from the owner, search this rank's band of row tiles, put the edges
+static int hot_band(umigpu_ctx *ctx, const umigpu_hot *hot);
+static int hot_collect(umigpu_ctx *ctx, u32 u0);
+
+static int hot_band(umigpu_ctx *ctx, const umigpu_hot *hot) {
+    Xchg *x = ctx->x;
+    const char *ow = x->peer[(size_t)hot->owner];
+    const unsigned long long epoch = x->epoch;
+    int rc = xchg_poll(ctx, ow + offsetof(XchgHeader, ready), 8, [&](const unsigned long long *b) { return b[0] >= epoch; }, "the owner's hot bucket");
+    if (rc) return rc;
+    rc = xchg_poll(ctx, ow + offsetof(XchgHeader, info), 8, [](const unsigned long long *) { return true; }, "the owner's header");
+    if (rc) return rc;
+    const unsigned long long info = x->h_pin[8];
+    if (info >> 33) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "shard group: the owner (rank %d) could not publish the hot bucket", hot->owner);
+    const u32 uh = (u32)info;
+    const bool has_n = ((info >> 32) & 1ull) != 0;
+    STAGE_BEGIN(UMIGPU_STAGE_HOT_BAND);
+    // child context: same configuration, this context's stream, its own buffers
+    if (!ctx->hot) {
+        umigpu_config c = ctx->cfg;
+        c.stream = (void *)ctx->stream;
+        c.flags &= ~UMIGPU_FLAG_LABELS;
+        rc = umigpu_create(&c, &ctx->hot);
+        if (rc) { ctx->err = g_last_error; return rc; }
+        ctx->hot->is_child = true;
+    }
+    umigpu_ctx *ch = ctx->hot;
+    rc = umigpu_reset(ch);
+    if (rc) { ctx->err = ch->err; return rc; }
+    ch->ran = true;
+    memset(&ch->ctr, 0, sizeof ch->ctr);
+    ch->n_edges = 0;
+    ch->skip_bucket = 0xffffffffu;
+    ch->band = (u32)x->rank; ch->n_bands = (u32)x->n;
+    ch->lay = ctx->lay;
+    ch->lay.umi_len = (int)ctx->cfg.umi_len; ch->lay.has_n = has_n ? 1 : 0;
+    ch->n_unique = uh; ch->n_buckets = uh ? 1 : 0;
+    u64 c_edges = 0;
+    if (uh > 1 && !(uh <= SMALL_BUCKET && x->rank != 0)) {        // a bucket of <= 32 UMIs is one warp's work: rank 0 takes it
+#define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, UMIGPU_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+        CKH(ch->d_planes.reserve((size_t)uh * 8)); CKH(ch->d_ucode.reserve((size_t)uh * 8)); CKH(ch->d_freq.reserve((size_t)uh * 4));
+        CKH(ch->d_thr.reserve((size_t)uh * 4)); CKH(ch->d_bstart.reserve(2 * 4)); CKH(ch->d_ubkt.reserve((size_t)uh * 4));
+        if (has_n) CKH(ch->d_nplane.reserve((size_t)uh * 4));
+        cudaStream_t s = ctx->stream;
+        CKH(cudaMemcpyAsync(ch->d_planes.p, ow + x->off_planes, (size_t)uh * 8, cudaMemcpyDefault, s));
+        CKH(cudaMemcpyAsync(ch->d_ucode.p, ow + x->off_ucode, (size_t)uh * 8, cudaMemcpyDefault, s));
+        CKH(cudaMemcpyAsync(ch->d_freq.p, ow + x->off_freq, (size_t)uh * 4, cudaMemcpyDefault, s));
+        CKH(cudaMemcpyAsync(ch->d_thr.p, ow + x->off_thr, (size_t)uh * 4, cudaMemcpyDefault, s));
+        if (has_n) CKH(cudaMemcpyAsync(ch->d_nplane.p, ow + x->off_nplane, (size_t)uh * 4, cudaMemcpyDefault, s));
+        hot_child_init_kernel<<<grid_for(uh, 256), 256, 0, s>>>(uh, ch->d_bstart.as<u32>(), ch->d_ubkt.as<u32>());
+        bucket_stats_kernel<<<1, 256, 0, s>>>(1, (const u32 *)ch->d_bstart.p, ch->d_sc.as<DevScalars>());
+        ctx->launches += 2;
+        CKH(cudaGetLastError());
+#undef CKH
+        rc = stage_neighbours(ch, RUN_EDGES_ONLY);
+        if (rc) { ctx->err = ch->err; return rc; }
+        c_edges = ch->n_edges;
+        ctx->launches += ch->launches; ch->launches = 0;
+    }
+    // put: edges into this rank's region of the owner's window, then the slot (count, then epoch)
+    unsigned long long count = c_edges;
+    char *inbox = const_cast<char *>(ow) + x->off_inbox + (size_t)x->rank * x->region * 8;
+    if (c_edges > x->region) count |= 1ull << 63;
+    else if (c_edges) CK(cudaMemcpyAsync(inbox, ctx->hot->d_edges.p, (size_t)c_edges * 8, cudaMemcpyDefault, ctx->stream));
+    x->h_pin[2] = count; x->h_pin[3] = epoch;
+    char *slot = const_cast<char *>(ow) + offsetof(XchgHeader, slot) + (size_t)x->rank * sizeof(XchgSlot);
+    CK(cudaMemcpyAsync(slot + offsetof(XchgSlot, count), &x->h_pin[2], 8, cudaMemcpyDefault, ctx->stream));
+    CK(cudaMemcpyAsync(slot + offsetof(XchgSlot, epoch), &x->h_pin[3], 8, cudaMemcpyDefault, ctx->stream));
+    STAGE_END(UMIGPU_STAGE_HOT_BAND);
+    return UMIGPU_OK;
+}
+
+// owner: wait for every rank's edges, append them (hot-bucket-local ids + u0) to this context's edge list
+static int hot_collect(umigpu_ctx *ctx, u32 u0) {
+    Xchg *x = ctx->x;
+    const unsigned long long epoch = x->epoch;
+    const int nr = x->n;
+    int rc = xchg_poll(ctx, x->local + offsetof(XchgHeader, slot), (size_t)nr * sizeof(XchgSlot),
+                       [&](const unsigned long long *b) { for (int r = 0; r < nr; r++) if (b[2 * r + 1] < epoch) return false; return true; },
+                       "the edges of the other ranks");
+    if (rc) return rc;
+    u64 cnt[XCHG_MAX_RANKS], total = 0;
+    for (int r = 0; r < nr; r++) {
+        const unsigned long long c = x->h_pin[8 + 2 * r];
+        if (c >> 63) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "shard group: rank %d found %llu edges in its band of the hot bucket, its window region holds %llu "
+                                 "(create the exchange window with a larger max_hot_edges)", r, (unsigned long long)(c & ~(1ull << 63)), (unsigned long long)x->region);
+        cnt[r] = c; total += c;
+    }
+    const u64 own = ctx->n_edges;
+    if (total) {
+        CK(ctx->d_edges.reserve_keep((own + total) * sizeof(uint2), own * sizeof(uint2), ctx->stream));
+        u64 at = own;
+        for (int r = 0; r < nr; r++) {
+            if (!cnt[r]) continue;
+            LAUNCH(hot_append_kernel, grid_for(cnt[r], 256), 256, (const uint2 *)(x->local + x->off_inbox + (size_t)r * x->region * 8), cnt[r], u0,
+                   ctx->d_edges.as<uint2>() + at);
+            at += cnt[r];
+        }
+    }
+    ctx->n_edges = own + total;
+    ctx->ctr.n_edges = ctx->n_edges;
+    return UMIGPU_OK;
+}
+
+extern "C" int umigpu_run_sharded(umigpu_ctx *ctx, const umigpu_hot *hot, int64_t key_lo, int64_t key_hi) {
+    if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
+    Xchg *x = ctx->x;
+    const bool want_labels = (ctx->cfg.flags & UMIGPU_FLAG_LABELS) != 0;
+    const bool edges_possible = ctx->cfg.algo != UMIGPU_ALGO_ADJ && ctx->cfg.k > 0;
+    const bool hot_on = hot && hot->present && edges_possible;
+    if (hot_on && !x) return fail(ctx, UMIGPU_ERR_STATE, "umigpu_run_sharded: a hot bucket needs an exchange window (umigpu_xchg_create + attach)");
+    if (hot_on && (hot->owner < 0 || hot->owner >= x->n)) return fail(ctx, UMIGPU_ERR_ARG, "hot bucket owner %d outside the group", hot->owner);
+    int rc = run_begin(ctx);
+    if (rc) return rc;
+    const u64 n = ctx->n_reads;
+    DevScalars *sc = ctx->d_sc.as<DevScalars>();
+    STAGE_BEGIN(UMIGPU_STAGE_TOTAL);
+    if (n) {
+        LAUNCH(slice_range_kernel, (u32)std::min<u64>(grid_for(n, 256), (u64)ctx->num_sms * 16), 256, n, (const i32 *)ctx->d_tid.p, (const i64 *)ctx->d_pos.p, sc);
+        rc = stage_group(ctx, want_labels, false);
+        if (rc) return rc;
+        // every (contig, position) of this slice must lie inside the slice's key range, or a bucket could straddle two devices
+        if (ctx->h_sc->hot_pad) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "sharded run: positions beyond +-2^35");
+        if (ctx->h_sc->key_lo < key_lo || (key_hi != INT64_MAX && ctx->h_sc->key_hi >= key_hi))
+            return fail(ctx, UMIGPU_ERR_ARG, "sharded run: the slice is not range-partitioned by (contig, position): keys [%lld, %lld] outside [%lld, %lld) — "
+                        "the input is not coordinate-sorted (use umigpu_shard_plan)", (long long)ctx->h_sc->key_lo, (long long)ctx->h_sc->key_hi,
+                        (long long)key_lo, (long long)key_hi);
+    }
+    u32 u0 = 0;
+    const bool owner = hot_on && x->rank == hot->owner;
+    if (hot_on) {
+        x->epoch++;
+        if (owner) { rc = hot_publish(ctx, hot, &u0); if (rc) return rc; }
+        rc = hot_band(ctx, hot);
+        if (rc) return rc;
+    }
+    if (n) { rc = stage_neighbours(ctx, RUN_FULL); if (rc) return rc; }
+    if (owner) { rc = hot_collect(ctx, u0); if (rc) return rc; }
+    if (hot_on && ctx->hot) {          // this rank's share of the hot bucket's search
+        const umigpu_counters &h = ctx->hot->ctr;
+        ctx->ctr.pairs_evaluated += h.pairs_evaluated; ctx->ctr.n_tile_items += h.n_tile_items;
+        ctx->ctr.n_tile_candidates += h.n_tile_candidates; ctx->ctr.n_block_pairs += h.n_block_pairs;
+    }
+    if (!n) { STAGE_END(UMIGPU_STAGE_TOTAL); return UMIGPU_OK; }
+    rc = stage_cluster(ctx);
+    if (rc) return rc;
+    return stage_emit(ctx, want_labels);
+}
+
+// ---- plan for a coordinate-sorted stream ----
+// Samples the stream (<= 65536 probes), estimates the big buckets from runs of equal (contig, position) in the sample, finds
+// the hot bucket's exact extent by binary search, and cuts at bucket starts so that the modelled cost is balanced.  Cost
+// model (ns, fitted to the measured stage times of C5 on one B200, profiles/): linear stages 0.11 per read; a bucket of r
+// reads adds 1e-8 r^2 for its neighbour search and 0.1 r for its clustering; the hot bucket's search is shared by the
+// group, so it only adds its clustering to the owner.  O(samples + log n) host work; the devices verify the cuts.
+extern "C" int umigpu_shard_plan_sorted(uint64_t n, const int32_t *tid, const int64_t *unclipped_pos, const uint8_t *is_reverse,
+                                        int32_t n_shards, uint64_t hot_min_reads, uint64_t *cuts, int64_t *cut_keys, umigpu_hot *hot,
+                                        double *shard_cost) {
+    if (n_shards < 1 || n_shards > XCHG_MAX_RANKS || !cuts || !cut_keys || (n && (!tid || !unclipped_pos || !is_reverse)))
+        return fail(nullptr, UMIGPU_ERR_ARG, "umigpu_shard_plan_sorted: bad argument");
+    if (hot) { hot->present = 0; hot->owner = 0; hot->read_index = 0; hot->reads_est = 0; }
+    if (hot_min_reads == 0) hot_min_reads = 1u << 20;
+    auto key = [&](u64 i) { return host_pos_key(tid[i], unclipped_pos[i]); };
+    auto lower = [&](i64 k) { u64 lo = 0, hi = n; while (lo < hi) { u64 mid = lo + (hi - lo) / 2; if (key(mid) < k) lo = mid + 1; else hi = mid; } return lo; };
+    for (int s = 0; s <= n_shards; s++) { cuts[s] = s == n_shards ? n : 0; cut_keys[s] = s == 0 ? INT64_MIN : INT64_MAX; }
+    if (shard_cost) for (int s = 0; s < n_shards; s++) shard_cost[s] = 0.0;
+    if (n == 0) return UMIGPU_OK;
+    const double A = 0.11, C2 = 1e-8, C1 = 0.10;
+    const u64 m = std::min<u64>(n, 65536);
+    const double per = (double)n / (double)m;
+    struct Unit { u64 first_sample; double reads, cost; i64 key; bool run; };
+    std::vector<Unit> units; units.reserve((size_t)m);
+    u64 hot_c = 0; i64 hot_key = 0;
+    for (u64 j = 0; j < m;) {
+        const i64 kj = key(j * n / m);
+        u64 e = j + 1;
+        while (e < m && key(e * n / m) == kj) e++;
+        const u64 c = e - j;
+        if (c >= 4) { units.push_back({j, c * per, 0.0, kj, true}); if (c > hot_c) { hot_c = c; hot_key = kj; } }
+        else for (u64 q = j; q < e; q++) units.push_back({q, per, 0.0, kj, false});
+        j = e;
+    }
+    bool have_hot = false;
+    u64 hb = 0, he = 0;
+    if (hot && n_shards >= 1 && hot_c && (double)hot_c * per >= (double)hot_min_reads) {
+        hb = lower(hot_key); he = lower(hot_key + 1);
+        if (he > hb) {
+            u64 nrev = 0, probes = std::min<u64>(he - hb, 256);
+            for (u64 q = 0; q < probes; q++) nrev += is_reverse[hb + q * (he - hb) / probes] ? 1 : 0;
+            const u8 maj = nrev * 2 > probes ? 1 : 0;
+            u64 r = hb;
+            while (r < he && (is_reverse[r] ? 1 : 0) != maj) r++;
+            if (r < he) {
+                have_hot = true;
+                hot->present = 1; hot->read_index = r;
+                hot->reads_est = (u64)((double)(he - hb) * (maj ? (double)nrev : (double)(probes - nrev)) / (double)probes) + 1;
+            }
+        }
+    }
+    double total = 0.0;
+    for (Unit &u : units) {
+        u.cost = A * u.reads;
+        if (u.run) u.cost += (have_hot && u.key == hot_key) ? C1 * u.reads : C2 * u.reads * u.reads + C1 * u.reads;
+        total += u.cost;
+    }
+    // greedy prefix partition over the units; a cut lands on the first read of a unit's key
+    size_t at = 0;
+    double acc = 0.0;
+    for (int s = 1; s < n_shards; s++) {
+        // what is left is shared evenly among the shards that are left (a bucket that outweighs the fair share must not
+        // starve the shards behind it)
+        const double target = acc + (total - acc) / (double)(n_shards - s + 1);
+        while (at < units.size() && acc + units[at].cost * 0.5 < target) { acc += units[at].cost; at++; }
+        u64 c = at < units.size() ? lower(units[at].key) : n;
+        if (c < cuts[s - 1]) c = cuts[s - 1];
+        cuts[s] = c;
+        cut_keys[s] = c < n ? key(c) : INT64_MAX;
+        // everything up to the cut is accounted for (the unit that holds the cut key may have started in the previous units)
+        while (at < units.size() && units[at].first_sample * n / m < c) { acc += units[at].cost; at++; }
+    }
+    if (have_hot) for (int s = 0; s < n_shards; s++) if (hb >= cuts[s] && hb < cuts[s + 1]) hot->owner = s;
+    if (shard_cost) {
+        size_t q = 0;
+        for (int s = 0; s < n_shards; s++)
+            for (; q < units.size() && units[q].first_sample * n / m < cuts[s + 1]; q++) shard_cost[s] += units[q].cost;
+    }
+    return UMIGPU_OK;
+}
+
+// ---- one process, several devices: a persistent group of contexts, one host thread per device per call ----
+struct umigpu_group {
+    umigpu_config cfg;
+    std::vector<int> devices;
+    std::vector<umigpu_ctx *> ctx;
+    u64 ucap = 0, ecap = 0;
+    std::atomic<int> abort{0};
+};
+
+extern "C" int umigpu_group_create(const umigpu_config *cfg, int32_t n_devices, const int32_t *device_ids, umigpu_group **out) {
+    if (!cfg || !device_ids || !out || n_devices < 1 || n_devices > XCHG_MAX_RANKS) return fail(nullptr, UMIGPU_ERR_ARG, "umigpu_group_create: bad argument");
+    *out = nullptr;
+    umigpu_group *g = new (std::nothrow) umigpu_group();
+    if (!g) return fail(nullptr, UMIGPU_ERR_NOMEM, "out of host memory");
+    g->cfg = *cfg;
+    for (int r = 0; r < n_devices; r++) {
+        umigpu_config c = *cfg; c.device = device_ids[r]; c.stream = nullptr;
+        umigpu_ctx *x = nullptr;
+        int rc = umigpu_create(&c, &x);
+        if (rc) { for (umigpu_ctx *p : g->ctx) umigpu_destroy(p); delete g; return rc; }
+        g->ctx.push_back(x); g->devices.push_back(device_ids[r]);
+    }
+    *out = g;
+    return UMIGPU_OK;
+}
+
+extern "C" void umigpu_group_destroy(umigpu_group *g) {
+    if (!g) return;
+    for (umigpu_ctx *p : g->ctx) umigpu_destroy(p);
+    delete g;
+}
+
+extern "C" umigpu_ctx *umigpu_group_context(umigpu_group *g, int32_t rank) {
+    return (g && rank >= 0 && rank < (int)g->ctx.size()) ? g->ctx[(size_t)rank] : nullptr;
+}
+
+static int group_windows(umigpu_group *g, u64 ucap, u64 ecap) {
+    if (ucap <= g->ucap && ecap <= g->ecap && g->ucap) return UMIGPU_OK;
+    ucap = std::max(ucap, g->ucap); ecap = std::max(ecap, g->ecap);
+    const int nd = (int)g->ctx.size();
+    for (int r = 0; r < nd; r++) { int rc = umigpu_xchg_create(g->ctx[(size_t)r], r, nd, ucap, ecap, nullptr); if (rc) return rc; }
+    for (int r = 0; r < nd; r++) { int rc = umigpu_xchg_attach_local(g->ctx[(size_t)r], g->ctx.data()); if (rc) return rc; }
+    for (int r = 0; r < nd; r++) g->ctx[(size_t)r]->x->abort = &g->abort;
+    g->ucap = ucap; g->ecap = ecap;
+    return UMIGPU_OK;
+}
+
+extern "C" int umigpu_group_dedup(umigpu_group *g, uint64_t n, const int32_t *tid, const int64_t *unclipped_pos, const uint8_t *is_reverse,
+                                  const uint8_t *umi_ascii, const int32_t *score, uint64_t **kept, uint64_t *n_kept, umigpu_counters *counters,
+                                  float *rank_ms /* nullable, n_devices */) {
+    if (!g || !kept || !n_kept) return fail(nullptr, UMIGPU_ERR_ARG, "umigpu_group_dedup: bad argument");
+    *kept = nullptr; *n_kept = 0;
+    if (counters) memset(counters, 0, sizeof *counters);
+    if (n == 0) return UMIGPU_OK;
+    if (!tid || !unclipped_pos || !is_reverse || !umi_ascii) return fail(nullptr, UMIGPU_ERR_ARG, "umigpu_group_dedup: null input");
+    const int nd = (int)g->ctx.size();
+    const size_t L = g->cfg.umi_len;
+    std::vector<u64> cuts((size_t)nd + 1);
+    std::vector<i64> ckeys((size_t)nd + 1);
+    umigpu_hot hot;
+    const char *e_hm = getenv("UMIGPU_HOT_MIN_READS");
+    int rc = umigpu_shard_plan_sorted(n, tid, unclipped_pos, is_reverse, nd, nd > 1 ? (e_hm ? strtoull(e_hm, nullptr, 10) : 0) : UINT64_MAX,
+                                      cuts.data(), ckeys.data(), &hot, nullptr);
+    if (rc) return rc;
+    if (hot.present) {
+        const char *e_ec = getenv("UMIGPU_XCHG_EDGES");
+        rc = group_windows(g, hot.reads_est + 1024, e_ec ? strtoull(e_ec, nullptr, 10) : std::max<u64>((u64)1 << 22, 4 * hot.reads_est));
+        if (rc) return rc;
+    }
+    // a call that failed half way leaves the ranks' epochs apart: flags compare with >=, so any common larger value resynchronises
+    {
+        u64 e = 0;
+        for (umigpu_ctx *c : g->ctx) if (c->x) e = std::max(e, c->x->epoch);
+        for (umigpu_ctx *c : g->ctx) if (c->x) c->x->epoch = e;
+        g->abort.store(0);
+    }
+    std::vector<int> rcs((size_t)nd, 0);
+    std::vector<std::string> errs((size_t)nd);
+    std::vector<umigpu_result> res((size_t)nd);
+    std::vector<std::thread> th;
+    for (int r = 0; r < nd; r++) {
+        th.emplace_back([&, r] {
+            umigpu_ctx *c = g->ctx[(size_t)r];
+            const u64 a = cuts[(size_t)r], m = cuts[(size_t)r + 1] - a;
+            int q = umigpu_reset(c);
+            if (!q && m) q = umigpu_push_reads(c, m, tid + a, unclipped_pos + a, is_reverse + a, umi_ascii + a * L, score ? score + a : nullptr, nullptr, a);
+            if (!q) q = umigpu_run_sharded(c, &hot, ckeys[(size_t)r], ckeys[(size_t)r + 1]);
+            if (!q) q = umigpu_fetch(c, &res[(size_t)r]);
+            rcs[(size_t)r] = q;
+            if (q) { errs[(size_t)r] = umigpu_last_error(c); g->abort.store(1); }
+        });
+    }
+    for (auto &t : th) t.join();
+    bool unsorted = false;
+    for (int r = 0; r < nd; r++) if (rcs[(size_t)r] == UMIGPU_ERR_ARG && errs[(size_t)r].find("not range-partitioned") != std::string::npos) unsorted = true;
+    if (unsorted) {
+        // every rank validates its own slice before anything is exchanged; a rank that passed may be waiting for the owner: its
+        // wait times out on its own.  Arbitrary order: gather per shard on the host instead.
+        return dedup_sharded_lpt(&g->cfg, nd, g->devices.data(), n, tid, unclipped_pos, is_reverse, umi_ascii, score, kept, n_kept, counters);
+    }
+    u64 total = 0;
+    for (int r = 0; r < nd; r++) { if (rcs[(size_t)r]) return fail(nullptr, rcs[(size_t)r], "shard %d failed: %s", r, errs[(size_t)r].c_str()); total += res[(size_t)r].n_kept; }
+    u64 *out = (u64 *)malloc(std::max<u64>(total, 1) * sizeof(u64));
+    if (!out) return fail(nullptr, UMIGPU_ERR_NOMEM, "out of host memory");
+    u64 o = 0;
+    for (int r = 0; r < nd; r++) {                 // slices are ascending index ranges: concatenation is the merge
+        if (res[(size_t)r].n_kept) memcpy(out + o, res[(size_t)r].kept_read_index, res[(size_t)r].n_kept * 8);
+        o += res[(size_t)r].n_kept;
+    }
+    *kept = out; *n_kept = total;
+    for (int r = 0; r < nd; r++) {
+        const umigpu_counters &p = res[(size_t)r].counters;
+        if (counters) {
+            counters->total_reads += p.total_reads; counters->n_buckets += p.n_buckets; counters->total_umis += p.total_umis;
+            counters->max_umis = std::max(counters->max_umis, p.max_umis); counters->n_kept += p.n_kept;
+            counters->unordered_pairs += p.unordered_pairs; counters->pairs_evaluated += p.pairs_evaluated; counters->n_edges += p.n_edges;
+            counters->n_tile_items += p.n_tile_items; counters->n_tile_candidates += p.n_tile_candidates;
+            counters->n_sweeps = std::max(counters->n_sweeps, p.n_sweeps); counters->n_block_pairs += p.n_block_pairs;
+            counters->key_bits = std::max(counters->key_bits, p.key_bits);
+        }
+        if (rank_ms) { float ms = 0; umigpu_stage_ms(g->ctx[(size_t)r], UMIGPU_STAGE_TOTAL, &ms); rank_ms[r] = ms; }
+    }
+    return UMIGPU_OK;
+}
+
+extern "C" int umigpu_dedup_sharded(const umigpu_config *cfg, int32_t n_devices, const int32_t *device_ids, uint64_t n,
+                                    const int32_t *tid, const int64_t *unclipped_pos, const uint8_t *is_reverse,
+                                    const uint8_t *umi_ascii, const int32_t *score, uint64_t **kept, uint64_t *n_kept,
+                                    umigpu_counters *counters) {
+    if (!cfg || !device_ids || n_devices < 1 || !kept || !n_kept) return fail(nullptr, UMIGPU_ERR_ARG, "umigpu_dedup_sharded: bad argument");
+    umigpu_group *g = nullptr;
+    int rc = umigpu_group_create(cfg, n_devices, device_ids, &g);
+    if (rc) return rc;
+    rc = umigpu_group_dedup(g, n, tid, unclipped_pos, is_reverse, umi_ascii, score, kept, n_kept, counters, nullptr);
+    umigpu_group_destroy(g);
+    return rc;
 }

@@ -15,7 +15,7 @@ ALGO_DIR, ALGO_ADJ, ALGO_ADJ_UPSTREAM, ALGO_CC = 0, 1, 2, 3
 MERGE_ANY, MERGE_AVGQUAL, MERGE_MAPQUAL = 0, 1, 2
 FLAG_LABELS, FLAG_NO_CULL, FLAG_KERNEL_DIRECT, FLAG_KERNEL_TILES, FLAG_NO_MULTI_INDEX = 1, 2, 4, 8, 16
 FLAG_PAIRED, FLAG_REMOVE_UNPAIRED, FLAG_REMOVE_CHIMERIC = 32, 64, 128
-STAGES = ["pack", "keys", "sort", "unique", "worklist", "neighbours", "cluster", "emit", "total"]
+STAGES = ["pack", "keys", "sort", "unique", "worklist", "neighbours", "cluster", "emit", "total", "hot_band"]
 
 # every symbol include/umigpu.h declares (tests check that the built library exports all of them)
 SYMBOLS = [
@@ -25,6 +25,8 @@ SYMBOLS = [
     "umigpu_avg_qual", "umigpu_stage_ms", "umigpu_launch_count", "umigpu_result_free",
     "umigpu_shard_plan", "umigpu_int_peak", "umigpu_push_bam_records", "umigpu_bam_record_offsets",
     "umigpu_dedup_sharded", "umigpu_free", "umigpu_push_reads_paired", "umigpu_device_init", "umigpu_push_reads_packed",
+    "umigpu_pos_key", "umigpu_shard_plan_sorted", "umigpu_xchg_create", "umigpu_xchg_attach_ipc", "umigpu_xchg_attach_local",
+    "umigpu_run_sharded", "umigpu_group_create", "umigpu_group_destroy", "umigpu_group_context", "umigpu_group_dedup",
 ]
 
 
@@ -47,6 +49,11 @@ class Counters(C.Structure):
 class Result(C.Structure):
     _fields_ = [("n_kept", C.c_uint64), ("kept_read_index", C.POINTER(C.c_uint64)), ("n_reads", C.c_uint64),
                 ("read_cluster_root", C.POINTER(C.c_uint64)), ("counters", Counters), ("read_umi_rep", C.POINTER(C.c_uint64))]
+
+
+class Hot(C.Structure):
+    """umigpu_hot: the bucket whose neighbour search is split over the devices of a shard group."""
+    _fields_ = [("present", C.c_int32), ("owner", C.c_int32), ("read_index", C.c_uint64), ("reads_est", C.c_uint64)]
 
 
 class UmiGpuError(RuntimeError):
@@ -100,6 +107,19 @@ def load() -> C.CDLL:
     lib.umigpu_result_free.restype = None
     lib.umigpu_shard_plan.argtypes = [u64, p, p, p, i32, p, p]
     lib.umigpu_int_peak.argtypes = [p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.umigpu_pos_key.argtypes = [i32, C.c_int64]
+    lib.umigpu_pos_key.restype = C.c_int64
+    lib.umigpu_shard_plan_sorted.argtypes = [u64, p, p, p, i32, u64, p, p, C.POINTER(Hot), p]
+    lib.umigpu_xchg_create.argtypes = [p, i32, i32, u64, u64, p]
+    lib.umigpu_xchg_attach_ipc.argtypes = [p, p]
+    lib.umigpu_xchg_attach_local.argtypes = [p, p]
+    lib.umigpu_run_sharded.argtypes = [p, C.POINTER(Hot), C.c_int64, C.c_int64]
+    lib.umigpu_group_create.argtypes = [C.POINTER(Config), i32, p, C.POINTER(p)]
+    lib.umigpu_group_destroy.argtypes = [p]
+    lib.umigpu_group_destroy.restype = None
+    lib.umigpu_group_context.argtypes = [p, i32]
+    lib.umigpu_group_context.restype = p
+    lib.umigpu_group_dedup.argtypes = [p, u64, p, p, p, p, p, C.POINTER(C.POINTER(u64)), C.POINTER(u64), C.POINTER(Counters), p]
     _lib = lib
     return lib
 

@@ -123,7 +123,7 @@ class Context:
         self._keepalive.clear()
         L.check(self._lib.umigpu_reset(self._h), self._h)
 
-    def push_reads(self, tid, pos, rev, umi, score=None, weight=None, first_read_index: int = 0, tlen=None):
+    def push_reads(self, tid, pos, rev, umi, score=None, weight=None, first_read_index: int = 0, tlen=None, sync: bool = True):
         """umigpu_push_reads / _device: arrays of equal length n; umi is [n, umi_len] uint8 ASCII.
         tlen (int64, host arrays) selects umigpu_push_reads_paired: the template length joins the bucket key."""
         n = int(tid.shape[0])
@@ -148,9 +148,9 @@ class Context:
                 a = a.contiguous()
             arrs.append(a)
         self._keepalive.append(arrs)     # async copies: keep the sources alive until fetch/reset
-        if dev:
+        if dev and sync:
             # the context works on its own (non-blocking) stream: the kernels that produced the tensors on torch's
-            # stream must have finished before the library reads them
+            # stream must have finished before the library reads them (sync=False: the caller guarantees that)
             import torch
             torch.cuda.current_stream(tid.device).synchronize()
         fn = self._lib.umigpu_push_reads_device if dev else self._lib.umigpu_push_reads
@@ -167,6 +167,24 @@ class Context:
 
     def run(self):
         L.check(self._lib.umigpu_run(self._h), self._h)
+
+    # ---- shard group (several devices, one dataset): include/umigpu.h "Several devices, ONE dataset" ----
+    def xchg_create(self, rank: int, n_ranks: int, max_hot_uniques: int, max_hot_edges: int) -> bytes:
+        """umigpu_xchg_create: this rank's exchange window; returns its 64-byte CUDA IPC handle."""
+        h = (C.c_uint8 * 64)()
+        L.check(self._lib.umigpu_xchg_create(self._h, rank, n_ranks, max_hot_uniques, max_hot_edges, h), self._h)
+        return bytes(h)
+
+    def xchg_attach_ipc(self, handles: list):
+        buf = (C.c_uint8 * (64 * len(handles))).from_buffer_copy(b"".join(handles))
+        L.check(self._lib.umigpu_xchg_attach_ipc(self._h, buf), self._h)
+
+    def xchg_attach_local(self, group: list):
+        arr = (C.c_void_p * len(group))(*[g._h for g in group])
+        L.check(self._lib.umigpu_xchg_attach_local(self._h, arr), self._h)
+
+    def run_sharded(self, hot=None, key_lo: int = -2 ** 63, key_hi: int = 2 ** 63 - 1):
+        L.check(self._lib.umigpu_run_sharded(self._h, C.byref(hot) if hot is not None else None, key_lo, key_hi), self._h)
 
     def fetch(self, copy: bool = True):
         """copy=False returns views of the library-owned (pinned) result buffers: valid until the next
@@ -268,6 +286,59 @@ def dedup_sharded(umi_len: int, devices, tid, pos, rev, umi, score=None, k: int 
     kept = np.ctypeslib.as_array(kept_p, shape=(nk.value,)).copy() if nk.value else np.zeros(0, np.uint64)
     lib.umigpu_free(kept_p)
     return kept, ctr.as_dict()
+
+
+def shard_plan_sorted(tid, pos, rev, n_shards: int, hot_min_reads: int = 0):
+    """umigpu_shard_plan_sorted: contiguous slices of a coordinate-sorted stream.  Returns (cuts uint64[n_shards + 1],
+    cut_keys int64[n_shards + 1], hot (umigpu_hot), modelled cost per shard)."""
+    lib = L.load()
+    tid = np.ascontiguousarray(tid, np.int32); pos = np.ascontiguousarray(pos, np.int64); rev = np.ascontiguousarray(rev, np.uint8)
+    cuts = np.zeros(n_shards + 1, np.uint64)
+    keys = np.zeros(n_shards + 1, np.int64)
+    cost = np.zeros(n_shards, np.float64)
+    hot = L.Hot()
+    L.check(lib.umigpu_shard_plan_sorted(tid.shape[0], _ptr(tid), _ptr(pos), _ptr(rev), n_shards, hot_min_reads, _ptr(cuts), _ptr(keys),
+                                         C.byref(hot), _ptr(cost)))
+    return cuts, keys, hot, cost
+
+
+class Group:
+    """umigpu_group_*: a persistent group of contexts in ONE process, one per device; dedup() shards one coordinate-sorted
+    dataset over them (contiguous slices, hot bucket split over NVLink) and returns the merged kept list."""
+
+    def __init__(self, umi_len: int, devices, k: int = 1, percentage: float = 0.5, algo: int = L.ALGO_DIR,
+                 merge: int = L.MERGE_AVGQUAL, flags: int = 0):
+        self._lib = L.load()
+        cfg = L.Config(k=k, percentage=percentage, algo=algo, merge=merge, umi_len=umi_len, device=0, flags=flags, reserved=0, stream=None)
+        dev = np.ascontiguousarray(devices, np.int32)
+        self.n = len(dev)
+        h = C.c_void_p()
+        L.check(self._lib.umigpu_group_create(C.byref(cfg), self.n, _ptr(dev), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.umigpu_group_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def dedup(self, tid, pos, rev, umi, score=None):
+        tid = np.ascontiguousarray(tid, np.int32); pos = np.ascontiguousarray(pos, np.int64); rev = np.ascontiguousarray(rev, np.uint8)
+        umi = np.ascontiguousarray(umi, np.uint8); score = None if score is None else np.ascontiguousarray(score, np.int32)
+        kept_p, nk, ctr = C.POINTER(C.c_uint64)(), C.c_uint64(), L.Counters()
+        ms = np.zeros(self.n, np.float32)
+        L.check(self._lib.umigpu_group_dedup(self._h, tid.shape[0], _ptr(tid), _ptr(pos), _ptr(rev), _ptr(umi), _ptr(score),
+                                             C.byref(kept_p), C.byref(nk), C.byref(ctr), _ptr(ms)))
+        kept = np.ctypeslib.as_array(kept_p, shape=(nk.value,)).copy() if nk.value else np.zeros(0, np.uint64)
+        self._lib.umigpu_free(kept_p)
+        return kept, ctr.as_dict(), ms
 
 
 def shard_plan(tid, pos, rev, n_shards: int):
