@@ -17,6 +17,9 @@
 #include "common.cuh"
 #include "pack.cuh"
 
+// STAMPED = false: the first sweeps, where nearly every source has just been lowered — reading the stamp would only add a
+// gather per edge; lowerings are stamped all the same so that later sweeps can skip.
+template <bool STAMPED>
 __global__ void __launch_bounds__(256) label_sweep_kernel(const uint2 *__restrict__ edges, u64 n_edges,
                                                           unsigned long long *label, DevScalars *sc, u32 *stamp, u32 sweep) {
     u64 stride = (u64)gridDim.x * 256;
@@ -25,14 +28,16 @@ __global__ void __launch_bounds__(256) label_sweep_kernel(const uint2 *__restric
         uint2 ed = edges[e];
         // an edge only has to be looked at again if its source was lowered in the previous sweep or earlier in this one
         // (stamp = sweep of the last lowering; sweep 1 sees stamp 0 everywhere and relaxes every edge)
-        if (stamp[ed.x] + 1u < sweep) continue;
+        if (STAMPED && stamp[ed.x] + 1u < sweep) continue;
         unsigned long long ls = label[ed.x];
         if (ls < label[ed.y]) { atomicMin(&label[ed.y], ls); stamp[ed.y] = sweep; any++; }
     }
     // number of lowerings of this sweep: the host switches to the frontier form when sweeps stop paying for themselves
+    if (__any_sync(0xffffffffu, any != 0)) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) any += __shfl_xor_sync(0xffffffffu, any, o);
-    if (any && lane_id() == 0) { sc->changed = 1; atomicAdd(&sc->n_lowered, any); }
+        for (int o = 16; o > 0; o >>= 1) any += __shfl_xor_sync(0xffffffffu, any, o);
+        if (lane_id() == 0) { sc->changed = 1; atomicAdd(&sc->n_lowered, any); }
+    }
 }
 
 // ---- frontier form (hot loci: tens of sweeps over 10^7 edges, almost all of them wasted) ----
@@ -40,18 +45,23 @@ __global__ void __launch_bounds__(256) label_sweep_kernel(const uint2 *__restric
 // out-edges of the UMIs whose label was lowered in the round before.  Same unique fixpoint as the sweeps (label[v] = the
 // earliest-visited UMI that reaches v, directional.rs:30-54): every lowering of label[u] puts u on the next frontier, so
 // no out-edge of u is left unrelaxed with u's final label.
-__global__ void __launch_bounds__(256) edges_pack_kernel(const uint2 *__restrict__ edges, u64 n_edges, u64 *__restrict__ keys) {
-    u64 e = (u64)blockIdx.x * 256 + threadIdx.x;
-    if (e < n_edges) { uint2 ed = edges[e]; keys[e] = ((u64)ed.x << 32) | ed.y; }
+// CSR by source without a sort: out-degree histogram, exclusive scan (scan.cuh), scatter.  The order of a row's
+// neighbours is whatever the atomics produce — the fixpoint only depends on the edge SET.
+__global__ void __launch_bounds__(256) csr_degree_kernel(const uint2 *__restrict__ edges, u64 n_edges, u32 *__restrict__ deg) {
+    const u64 stride = (u64)gridDim.x * 256;
+    for (u64 e = (u64)blockIdx.x * 256 + threadIdx.x; e < n_edges; e += stride) atomicAdd(&deg[edges[e].x], 1u);
 }
-// row_ptr[r] = first e with src >= r (keys sorted by src); rows [0, n_rows]
-__global__ void __launch_bounds__(256) csr_rows_kernel(const u64 *__restrict__ keys, u64 n_edges, u32 n_rows, u32 *__restrict__ row_ptr) {
-    u64 e = (u64)blockIdx.x * 256 + threadIdx.x;
-    if (e > n_edges) return;
-    u32 src_here = e < n_edges ? (u32)(keys[e] >> 32) : n_rows;
-    u32 src_prev = e > 0 ? (u32)(keys[e - 1] >> 32) : 0;
-    if (e == 0) for (u32 r = 0; r <= src_here; r++) row_ptr[r] = 0;
-    else for (u32 r = src_prev + 1; r <= src_here; r++) row_ptr[r] = (u32)e;
+struct DegreeOf { const u32 *deg; __device__ u32 operator()(u64 u) const { return deg[u]; } };
+struct RowEmit {
+    u32 *row_ptr, *fill; u64 n_rows;
+    __device__ void operator()(u64 u, u32 v, u32 ex) const {
+        row_ptr[u] = ex; fill[u] = ex;
+        if (u == n_rows - 1) row_ptr[u + 1] = ex + v;
+    }
+};
+__global__ void __launch_bounds__(256) csr_fill_kernel(const uint2 *__restrict__ edges, u64 n_edges, u32 *__restrict__ fill, u32 *__restrict__ col) {
+    const u64 stride = (u64)gridDim.x * 256;
+    for (u64 e = (u64)blockIdx.x * 256 + threadIdx.x; e < n_edges; e += stride) { const uint2 ed = edges[e]; col[atomicAdd(&fill[ed.x], 1u)] = ed.y; }
 }
 // first frontier after the plain sweeps: every UMI lowered in the last sweep
 __global__ void __launch_bounds__(256) frontier_init_kernel(u32 n_unique, const u32 *__restrict__ stamp, u32 last_sweep,
@@ -67,7 +77,7 @@ __global__ void __launch_bounds__(256) frontier_init_kernel(u32 n_unique, const 
     }
 }
 // one round: thread per frontier UMI (out-degree is small: at most 3*L neighbours per unit of k)
-__global__ void __launch_bounds__(256) frontier_relax_kernel(const u32 *__restrict__ row_ptr, const u64 *__restrict__ keys,
+__global__ void __launch_bounds__(256) frontier_relax_kernel(const u32 *__restrict__ row_ptr, const u32 *__restrict__ col,
                                                              unsigned long long *label, u32 *stamp, const u32 *__restrict__ fin,
                                                              const u32 *__restrict__ cnt_in, u32 *__restrict__ fout, u32 *cnt_out, u32 round) {
     const u32 n = *cnt_in, stride = gridDim.x * 256;
@@ -76,10 +86,18 @@ __global__ void __launch_bounds__(256) frontier_relax_kernel(const u32 *__restri
         const unsigned long long lu = label[u];
         const u32 e1 = row_ptr[u + 1];
         for (u32 e = row_ptr[u]; e < e1; e++) {
-            const u32 d = (u32)keys[e];
+            const u32 d = col[e];
             if (lu < label[d]) {
                 const unsigned long long old = atomicMin(&label[d], lu);
-                if (lu < old && atomicExch(&stamp[d], round) != round) fout[atomicAdd(cnt_out, 1u)] = d;
+                if (lu < old && atomicExch(&stamp[d], round) != round) {
+                    // warp-aggregated append (lanes that reach this point together share one reservation)
+                    const u32 act = __activemask();
+                    const u32 leader = (u32)__ffs(act) - 1u;
+                    u32 base = 0;
+                    if (lane_id() == leader) base = atomicAdd(cnt_out, (u32)__popc(act));
+                    base = __shfl_sync(act, base, leader);
+                    fout[base + __popc(act & lanemask_lt())] = d;
+                }
             }
         }
     }

@@ -576,7 +576,9 @@ static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, E
         if (rc) return rc;
         const u64 n_pairs = ctx->h_sc->n_block_pairs;
         // more than ~30 % of the scheduled pair space survives block culling: dense work runs better as shared-memory tiles
-        const bool is_dense = (double)n_pairs * 16384.0 > 0.30 * (double)item_pairs;
+        // (a band of a split hot bucket never leaves the multi-index scheme: which pass reports a pair must not depend on
+        // the rank, and the density a rank sees in its band does)
+        const bool is_dense = (double)n_pairs * 16384.0 > 0.30 * (double)item_pairs && !(ctx->n_bands > 1 && mi.part >= 0);
         if (is_dense && mi.part >= 0) { *dense = true; return UMIGPU_OK; }
         if (!is_dense) {
             const int LP = blk_lp(L), XS = has_n ? 8 : 4;
@@ -977,7 +979,9 @@ static int stage_cluster(umigpu_ctx *ctx) {
           CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
           for (int i = 0; i < 4; i++) {
               if (i == 3) CK(cudaMemsetAsync(&sc->n_lowered, 0, 4, ctx->stream));
-              LAUNCH(label_sweep_kernel, egrid, 256, edges, n_edges, label, sc, stamp, ++sweep_no);
+              ++sweep_no;
+              if (sweep_no <= 2) LAUNCH(label_sweep_kernel<false>, egrid, 256, edges, n_edges, label, sc, stamp, sweep_no);
+              else               LAUNCH(label_sweep_kernel<true>, egrid, 256, edges, n_edges, label, sc, stamp, sweep_no);
           }
           sweeps += 4;
           rc = read_scalars(ctx);
@@ -987,20 +991,18 @@ static int stage_cluster(umigpu_ctx *ctx) {
           if (!converged && may_frontier && (u64)ctx->h_sc->n_lowered * 16 < n_edges) { use_frontier = true; break; }
       }
       if (!converged && use_frontier) {
-          // CSR by source: radix sort of (src << 32 | dst) on the source bits, rows cut at source changes
-          CK(ctx->d_key[0][0].reserve(n_edges * 8)); CK(ctx->d_key[1][0].reserve(n_edges * 8));
-          CK(ctx->d_idx[0].reserve(n_edges * 4)); CK(ctx->d_idx[1].reserve(n_edges * 4));
-          LAUNCH(edges_pack_kernel, grid_for(n_edges, 256), 256, edges, n_edges, ctx->d_key[0][0].as<u64>());
-          SortPlan plan; plan.npass = 0;
-          { const int nb = std::max(1, bits_for((u64)U - 1)); int done = 0; const int np = (nb + RS_RB - 1) / RS_RB;
-            for (int i = 0; i < np; i++) { int b = (nb - done + (np - i) - 1) / (np - i); plan.p[plan.npass++] = {0, 32 + done, b}; done += b; } }
-          int cur = 0;
-          rc = run_sort(ctx, n_edges, 1, plan, &cur);
-          if (rc) return rc;
-          const u64 *keys = ctx->d_key[cur][0].as<u64>();
+          // CSR by source: out-degree histogram, scan, scatter (no sort: a row's order does not matter)
+          if (n_edges >= 0xffffffffull) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "more than 2^32 edges in one batch");
           CK(ctx->d_rowptr.reserve(((size_t)U + 2) * 4));
-          LAUNCH(csr_rows_kernel, grid_for(n_edges + 1, 256), 256, keys, n_edges, U, ctx->d_rowptr.as<u32>());
+          CK(ctx->d_comp.reserve(std::max<size_t>((size_t)U * 4, 4)));                 // row fill cursors (the two-phase scheme's buffer, unused here)
+          CK(ctx->d_cedges.reserve(std::max<u64>(n_edges, 1) * sizeof(u32)));          // column indices
           CK(ctx->d_front[0].reserve((size_t)U * 4)); CK(ctx->d_front[1].reserve((size_t)U * 4));
+          CK(cudaMemsetAsync(ctx->d_front[1].p, 0, (size_t)U * 4, ctx->stream));       // degrees live in the second frontier buffer until the scan
+          LAUNCH(csr_degree_kernel, egrid, 256, edges, n_edges, ctx->d_front[1].as<u32>());
+          rc = run_scan(ctx, DegreeOf{ctx->d_front[1].as<u32>()}, RowEmit{ctx->d_rowptr.as<u32>(), ctx->d_comp.as<u32>(), U}, U, nullptr);
+          if (rc) return rc;
+          LAUNCH(csr_fill_kernel, egrid, 256, edges, n_edges, ctx->d_comp.as<u32>(), ctx->d_cedges.as<u32>());
+          const u32 *col = ctx->d_cedges.as<u32>();
           CK(cudaMemsetAsync(&sc->frontier_cnt[0], 0, 8, ctx->stream));
           LAUNCH(frontier_init_kernel, grid_for(U, 256), 256, U, (const u32 *)stamp, sweep_no, ctx->d_front[0].as<u32>(), &sc->frontier_cnt[0]);
           const u32 fgrid = (u32)ctx->num_sms * 8;
@@ -1009,14 +1011,13 @@ static int stage_cluster(umigpu_ctx *ctx) {
           while (!converged && rounds < 4096) {
               for (int i = 0; i < 8; i++) {
                   CK(cudaMemsetAsync(&sc->frontier_cnt[in ^ 1], 0, 4, ctx->stream));
-                  LAUNCH(frontier_relax_kernel, fgrid, 256, (const u32 *)ctx->d_rowptr.p, keys, label, stamp, (const u32 *)ctx->d_front[in].p,
+                  LAUNCH(frontier_relax_kernel, fgrid, 256, (const u32 *)ctx->d_rowptr.p, col, label, stamp, (const u32 *)ctx->d_front[in].p,
                          (const u32 *)&sc->frontier_cnt[in], ctx->d_front[in ^ 1].as<u32>(), &sc->frontier_cnt[in ^ 1], ++sweep_no);
                   in ^= 1;
               }
               rounds += 8; sweeps += 8;
               rc = read_scalars(ctx);
               if (rc) return rc;
-              if (ctx->h_sc->sort_err) return fail(ctx, UMIGPU_ERR_CUDA, "radix sort look-back exceeded its spin budget");
               converged = ctx->h_sc->frontier_cnt[in] == 0;
           }
           if (!converged && !big_graph) return fail(ctx, UMIGPU_ERR_CUDA, "label propagation did not settle in 4096 frontier rounds");
