@@ -20,8 +20,9 @@
 // STAMPED = false: the first sweeps, where nearly every source has just been lowered — reading the stamp would only add a
 // gather per edge; lowerings are stamped all the same so that later sweeps can skip.
 template <bool STAMPED>
-__global__ void __launch_bounds__(256) label_sweep_kernel(const uint2 *__restrict__ edges, u64 n_edges,
+__global__ void __launch_bounds__(256) label_sweep_kernel(const uint2 *__restrict__ edges, u64 n_edges_host, const unsigned long long *n_ptr,
                                                           unsigned long long *label, DevScalars *sc, u32 *stamp, u32 sweep) {
+    const u64 n_edges = n_ptr ? *n_ptr : n_edges_host;       // the contracted list's length lives on the device
     u64 stride = (u64)gridDim.x * 256;
     u32 any = 0;
     for (u64 e = (u64)blockIdx.x * 256 + threadIdx.x; e < n_edges; e += stride) {
@@ -103,48 +104,54 @@ __global__ void __launch_bounds__(256) frontier_relax_kernel(const u32 *__restri
     }
 }
 
-// Pointer jumping: label[v] names a UMI r that reaches v; whatever reaches r reaches v too, so label[v] may take
-// label[r].  One jump per sweep turns the number of sweeps from O(longest chain) into O(log) of it.
-__global__ void __launch_bounds__(256) label_jump_kernel(u32 n_unique, unsigned long long *label, DevScalars *sc) {
-    u32 v = blockIdx.x * 256 + threadIdx.x;
-    u32 any = 0;
-    if (v < n_unique) {
-        unsigned long long l = label[v];
-        u32 r = (u32)l;
-        if (r != v) {
-            unsigned long long lr = label[r];
-            if (lr < l) { atomicMin(&label[v], lr); any = 1; }
+// ---- two-phase fixpoint: mutual components first, then the contracted graph ----
+// An edge (s,d) whose reverse (d,s) also passed the count rule is MUTUAL: s and d reach each other, so they end with the
+// same label.  With -p 0.5 exactly the edges among frequency-1 UMIs are mutual (1 >= 2*1-1; f_s >= 2 f_d - 1 and
+// f_d >= 2 f_s - 1 force f_s = f_d = 1), and in a hot locus those UMIs (sequencing errors, molecules seen once) form
+// components tens of hops across — which is what makes plain propagation need tens of sweeps.
+//   Phase A  connected components over the mutual edges with a lock-free union-find (one pass over the edge list: find with
+//            path halving, the larger root is hooked under the smaller by atomicCAS; then one flatten pass).  Work does not
+//            depend on the diameter.  The component's label = min over its members (atomicMin into the root's slot).
+//   Phase B  the contracted graph is materialised once — every edge becomes (root[src], root[dst]), edges inside a
+//            component vanish — and min-label propagation runs on it: one-way edges follow strictly falling frequency, so
+//            its depth is ~log2(max frequency) and a handful of sweeps settle it.  Then every UMI takes its root's label.
+// Same unique fixpoint (label[v] = earliest visited UMI that reaches v): all members of a mutual component reach each other,
+// so they share the minimum over everything that reaches any of them.
+__device__ __forceinline__ u32 uf_find(u32 *parent, u32 v) {
+    u32 p = parent[v];
+    while (p != v) {
+        const u32 gp = parent[p];
+        if (gp != p) parent[v] = gp;          // path halving: racy but benign (always an ancestor, ids fall along a path)
+        v = p; p = gp;
+    }
+    return v;
+}
+__global__ void __launch_bounds__(256) uf_init_kernel(u32 n_unique, u32 *__restrict__ parent) {
+    const u32 v = blockIdx.x * 256 + threadIdx.x;
+    if (v < n_unique) parent[v] = v;
+}
+__global__ void __launch_bounds__(256) uf_union_kernel(const uint2 *__restrict__ edges, u64 n_edges, const i32 *__restrict__ freq,
+                                                       const i32 *__restrict__ thr, u32 *parent) {
+    const u64 stride = (u64)gridDim.x * 256;
+    for (u64 e = (u64)blockIdx.x * 256 + threadIdx.x; e < n_edges; e += stride) {
+        const uint2 ed = edges[e];
+        if (ed.x > ed.y) continue;                            // a mutual pair is in the list in both directions: take one
+        if (freq[ed.x] > thr[ed.y]) continue;                 // reverse edge did not pass the rule: one-way
+        u32 ra = ed.x, rb = ed.y;
+        for (;;) {
+            ra = uf_find(parent, ra); rb = uf_find(parent, rb);
+            if (ra == rb) break;
+            if (ra < rb) { const u32 t = ra; ra = rb; rb = t; }
+            if (atomicCAS(&parent[ra], ra, rb) == ra) break;  // hooked the larger root under the smaller
         }
     }
-    if (__any_sync(0xffffffffu, any) && lane_id() == 0) sc->changed = 1;
 }
-
-// ---- two-phase fixpoint: mutual components first, then the contracted graph ----
-// An edge (s,d) whose reverse (d,s) also passed the count rule is MUTUAL: s and d reach each other, so they end
-// with the same label.  Among frequency-1 UMIs every edge is mutual (1 >= 2*1-1) and their components can have a
-// large diameter, which is what made plain propagation need tens of sweeps on hot loci.
-//   Phase A  min-label connected components over the mutual edges only, with hooking (the smaller label is
-//            written to the current root of the other side) and pointer jumping: O(log) rounds.  Invariant:
-//            label[v] is always the priority of a UMI in v's own mutual component, so hooking is sound.
-//   Phase B  min-label propagation over ALL edges on the contracted graph (one entry per mutual component,
-//            comp[v] = its minimum-priority member): depth = chains of one-way edges, which follow strictly
-//            falling frequency and are short.
-// The fixpoint is the same unique one (label[v] = earliest visited UMI reaching v).
-__global__ void __launch_bounds__(256) sv_hook_kernel(const uint2 *__restrict__ edges, u64 n_edges, const i32 *__restrict__ freq,
-                                                      const i32 *__restrict__ thr, unsigned long long *label, DevScalars *sc) {
-    u64 stride = (u64)gridDim.x * 256;
-    u32 any = 0;
-    for (u64 e = (u64)blockIdx.x * 256 + threadIdx.x; e < n_edges; e += stride) {
-        uint2 ed = edges[e];
-        if (freq[ed.x] > thr[ed.y]) continue;                 // reverse edge did not pass the rule: one-way
-        unsigned long long ls = label[ed.x], ld = label[ed.y];
-        if (ls < ld) { atomicMin(&label[(u32)ld], ls); atomicMin(&label[ed.y], ls); any = 1; }
-    }
-    if (__any_sync(0xffffffffu, any) && lane_id() == 0) sc->changed = 1;
-}
-__global__ void __launch_bounds__(256) comp_from_label_kernel(u32 n_unique, const unsigned long long *__restrict__ label, u32 *__restrict__ comp) {
-    u32 v = blockIdx.x * 256 + threadIdx.x;
-    if (v < n_unique) comp[v] = (u32)label[v];
+// flatten + component label: parent[v] = root, label[root] = min over the members
+__global__ void __launch_bounds__(256) uf_flatten_kernel(u32 n_unique, u32 *parent, unsigned long long *label) {
+    const u32 v = blockIdx.x * 256 + threadIdx.x;
+    if (v >= n_unique) return;
+    const u32 r = uf_find(parent, v);
+    if (r != v) { parent[v] = r; atomicMin(&label[r], label[v]); }
 }
 // The contracted graph is materialised once: every edge becomes (comp[src], comp[dst]); edges inside a mutual component
 // (most edges of a hot locus) disappear.  Phase B then touches only this list: no per-sweep comp gathers, no pass over
@@ -165,30 +172,6 @@ __global__ void __launch_bounds__(256) contract_edges_kernel(const uint2 *__rest
             if (live) out[base + __popc(m & lanemask_lt())] = make_uint2(cs, cd);
         }
     }
-}
-__global__ void __launch_bounds__(256) contracted_sweep_kernel(const uint2 *__restrict__ cedges, const unsigned long long *__restrict__ n_ptr,
-                                                               unsigned long long *label, DevScalars *sc) {
-    const u64 n_edges = *n_ptr, stride = (u64)gridDim.x * 256;
-    u32 any = 0;
-    for (u64 e = (u64)blockIdx.x * 256 + threadIdx.x; e < n_edges; e += stride) {
-        const uint2 ed = cedges[e];
-        const unsigned long long ms = label[ed.x];
-        if (ms < label[ed.y]) { atomicMin(&label[ed.y], ms); any = 1; }
-    }
-    if (__any_sync(0xffffffffu, any) && lane_id() == 0) sc->changed = 1;
-}
-// pointer jumping on the contracted graph, driven by the edge list: only a destination's label can change
-__global__ void __launch_bounds__(256) contracted_jump_kernel(const uint2 *__restrict__ cedges, const unsigned long long *__restrict__ n_ptr,
-                                                              unsigned long long *label, DevScalars *sc) {
-    const u64 n_edges = *n_ptr, stride = (u64)gridDim.x * 256;
-    u32 any = 0;
-    for (u64 e = (u64)blockIdx.x * 256 + threadIdx.x; e < n_edges; e += stride) {
-        const u32 c = cedges[e].y;
-        const unsigned long long l = label[c];
-        const u32 r = (u32)l;
-        if (r != c) { const unsigned long long lr = label[r]; if (lr < l) { atomicMin(&label[c], lr); any = 1; } }
-    }
-    if (__any_sync(0xffffffffu, any) && lane_id() == 0) sc->changed = 1;
 }
 __global__ void __launch_bounds__(256) expand_labels_kernel(u32 n_unique, const u32 *__restrict__ comp, unsigned long long *label) {
     u32 v = blockIdx.x * 256 + threadIdx.x;

@@ -950,46 +950,49 @@ static int stage_cluster(umigpu_ctx *ctx) {
         LAUNCH(mis_label_kernel, egrid, 256, edges, n_edges, prio, (const u8 *)ctx->d_state.p, label);
         LAUNCH(mis_keep_kernel, grid_for(U, 256), 256, U, (const u8 *)ctx->d_state.p, keep);
     } else {
-      // Plain sweeps first: they have the lowest cost per sweep while most labels still move, and in-place atomicMin lets a
-      // label travel several hops per sweep.  A sweep skips every edge whose source was not lowered since the sweep before
-      // (stamp array), so late sweeps cost the edge stream only.  Graphs that are still moving after 4 sweeps while few labels
-      // change per sweep (hot loci: a percolating component of frequency-1 UMIs, tens of hops deep) switch to the frontier
-      // form: edges sorted by source once, then rounds over the lowered UMIs only (C5: 40 sweeps x 3.1e7 edges = 10.9 ms
-      // before).  The two-phase scheme (mutual components + contracted graph, O(log) rounds whatever the chain length)
-      // remains the safety net for graphs that are still moving after UMIGPU_PLAIN_ROUNDS rounds of 4 sweeps / 4096 frontier rounds.
-      // test knobs: UMIGPU_SV_MIN_EDGES (default 8 Mi) = smallest edge count that may switch to the two-phase scheme,
-      // UMIGPU_PLAIN_ROUNDS (default 16) = rounds of 4 plain sweeps tried first, UMIGPU_FRONTIER_MIN_EDGES (default 2 Mi;
-      // 0 = never) = smallest edge count that may switch to the frontier form
+      // Three schedules for the same unique fixpoint (label[v] = earliest visited UMI that reaches v):
+      //  (1) plain sweeps over the edge list, in place (a label can travel several hops per sweep); from the third sweep on an
+      //      edge is skipped unless its source was lowered since the sweep before (stamp array).  Small graphs settle here.
+      //  (2) frontier rounds (edges bucketed by source once, then only the out-edges of lowered UMIs): graphs between
+      //      UMIGPU_FRONTIER_MIN_EDGES (2 Mi) and UMIGPU_SV_MIN_EDGES that are still moving while few labels change per sweep.
+      //  (3) two-phase (cluster.cuh): union-find over the mutual edges, contracted propagation, expand — work independent of
+      //      the diameter.  Graphs of >= UMIGPU_SV_MIN_EDGES (default 4 Mi) edges go there after UMIGPU_PLAIN_ROUNDS (default 0)
+      //      rounds of 4 plain sweeps: the hot locus of C5 (3.1e7 edges, 40 sweeps = 10.9 ms in round 1) is its case.
       bool converged = false;
       const char *e_sv = getenv("UMIGPU_SV_MIN_EDGES"), *e_pr = getenv("UMIGPU_PLAIN_ROUNDS"), *e_fr = getenv("UMIGPU_FRONTIER_MIN_EDGES");
-      const u64 sv_min = e_sv ? strtoull(e_sv, nullptr, 10) : (u64)(8u << 20);
-      const int plain_rounds = e_pr ? atoi(e_pr) : 16;
+      const u64 sv_min = e_sv ? strtoull(e_sv, nullptr, 10) : (u64)(4u << 20);
+      const int plain_rounds = e_pr ? atoi(e_pr) : 0;
       const u64 fr_min = e_fr ? strtoull(e_fr, nullptr, 10) : (u64)(2u << 20);
       const bool big_graph = n_edges >= sv_min;
       const bool sv_forced = e_sv != nullptr || e_pr != nullptr;          // the tests drive the two-phase scheme through these
-      const bool may_frontier = fr_min != 0 && n_edges >= fr_min && !sv_forced && U < 0xfffffff0u;
-      if (big_graph) { CK(ctx->d_prio.reserve((size_t)U * 8)); CK(cudaMemcpyAsync(ctx->d_prio.p, label, (size_t)U * 8, cudaMemcpyDeviceToDevice, ctx->stream)); }
+      const bool may_frontier = fr_min != 0 && n_edges >= fr_min && !sv_forced && !big_graph && U < 0xfffffff0u;
       CK(ctx->d_stamp.reserve((size_t)U * 4));
       CK(cudaMemsetAsync(ctx->d_stamp.p, 0, (size_t)U * 4, ctx->stream));
       u32 *stamp = ctx->d_stamp.as<u32>();
       u32 sweep_no = 0;
       // UMIGPU_FRONTIER_FORCE=1 (tests): no plain sweeps at all, the first frontier is every UMI
       bool use_frontier = getenv("UMIGPU_FRONTIER_FORCE") != nullptr && !sv_forced && U < 0xfffffff0u;
-      for (int round = 0; !use_frontier && !converged && (round < plain_rounds || !big_graph); round++) {
-          CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
-          for (int i = 0; i < 4; i++) {
-              if (i == 3) CK(cudaMemsetAsync(&sc->n_lowered, 0, 4, ctx->stream));
-              ++sweep_no;
-              if (sweep_no <= 2) LAUNCH(label_sweep_kernel<false>, egrid, 256, edges, n_edges, label, sc, stamp, sweep_no);
-              else               LAUNCH(label_sweep_kernel<true>, egrid, 256, edges, n_edges, label, sc, stamp, sweep_no);
+      // sweeps until the fixpoint, in batches of 4 with one read-back; *n_ptr (optional) = device-resident edge count
+      auto sweep_batches = [&](const uint2 *el, u64 ne, const unsigned long long *n_ptr, int max_rounds, bool allow_frontier) -> int {
+          const u32 g = (u32)std::min<u64>(std::max<u64>(1, ceil_div_u64(ne, 256)), (u64)ctx->num_sms * 16);
+          for (int round = 0; !converged && (max_rounds < 0 || round < max_rounds); round++) {
+              CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
+              for (int i = 0; i < 4; i++) {
+                  if (i == 3) CK(cudaMemsetAsync(&sc->n_lowered, 0, 4, ctx->stream));
+                  ++sweep_no;
+                  if (sweep_no <= 2) LAUNCH(label_sweep_kernel<false>, g, 256, el, ne, n_ptr, label, sc, stamp, sweep_no);
+                  else               LAUNCH(label_sweep_kernel<true>, g, 256, el, ne, n_ptr, label, sc, stamp, sweep_no);
+              }
+              sweeps += 4;
+              int r2 = read_scalars(ctx);
+              if (r2) return r2;
+              converged = !ctx->h_sc->changed || ctx->h_sc->n_lowered == 0;
+              // still moving, but the last sweep lowered few labels compared with the edges it streamed: the frontier form pays
+              if (!converged && allow_frontier && (u64)ctx->h_sc->n_lowered * 16 < ne) { use_frontier = true; break; }
           }
-          sweeps += 4;
-          rc = read_scalars(ctx);
-          if (rc) return rc;
-          converged = !ctx->h_sc->changed || ctx->h_sc->n_lowered == 0;
-          // still moving, but the last sweep lowered few labels compared with the edges it streamed: the frontier form pays
-          if (!converged && may_frontier && (u64)ctx->h_sc->n_lowered * 16 < n_edges) { use_frontier = true; break; }
-      }
+          return UMIGPU_OK;
+      };
+      if (!use_frontier) { rc = sweep_batches(edges, n_edges, nullptr, big_graph ? plain_rounds : -1, may_frontier); if (rc) return rc; }
       if (!converged && use_frontier) {
           // CSR by source: out-degree histogram, scan, scatter (no sort: a row's order does not matter)
           if (n_edges >= 0xffffffffull) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "more than 2^32 edges in one batch");
@@ -1008,7 +1011,7 @@ static int stage_cluster(umigpu_ctx *ctx) {
           const u32 fgrid = (u32)ctx->num_sms * 8;
           int in = 0;
           u64 rounds = 0;
-          while (!converged && rounds < 4096) {
+          while (!converged && rounds < 65536) {
               for (int i = 0; i < 8; i++) {
                   CK(cudaMemsetAsync(&sc->frontier_cnt[in ^ 1], 0, 4, ctx->stream));
                   LAUNCH(frontier_relax_kernel, fgrid, 256, (const u32 *)ctx->d_rowptr.p, col, label, stamp, (const u32 *)ctx->d_front[in].p,
@@ -1020,41 +1023,26 @@ static int stage_cluster(umigpu_ctx *ctx) {
               if (rc) return rc;
               converged = ctx->h_sc->frontier_cnt[in] == 0;
           }
-          if (!converged && !big_graph) return fail(ctx, UMIGPU_ERR_CUDA, "label propagation did not settle in 4096 frontier rounds");
+          if (!converged) return fail(ctx, UMIGPU_ERR_CUDA, "label propagation did not settle in 65536 frontier rounds");
       }
       if (!converged) {
-        if (!big_graph) return fail(ctx, UMIGPU_ERR_STATE, "internal: label propagation left its loop without a fixpoint");
-        CK(cudaMemcpyAsync(label, ctx->d_prio.p, (size_t)U * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        // Phase A: mutual components (hook + jump), Phase B: contracted propagation (cluster.cuh)
-        CK(ctx->d_comp.reserve((size_t)U * 4));
+        // two-phase.  Labels may already have moved (plain rounds): any state with label[v] = priority of a UMI that reaches v
+        // leads to the same fixpoint, so nothing is reset.
+        CK(ctx->d_comp.reserve(std::max<size_t>((size_t)U * 4, 4)));
         u32 *comp = ctx->d_comp.as<u32>();
-        for (;;) {
-            CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
-            for (int i = 0; i < 2; i++) {
-                LAUNCH(sv_hook_kernel, egrid, 256, edges, n_edges, (const i32 *)ctx->d_freq.p, (const i32 *)ctx->d_thr.p, label, sc);
-                LAUNCH(label_jump_kernel, grid_for(U, 256), 256, U, label, sc);
-            }
-            sweeps += 2;
-            rc = read_scalars(ctx);
-            if (rc) return rc;
-            if (!ctx->h_sc->changed) break;
-        }
-        LAUNCH(comp_from_label_kernel, grid_for(U, 256), 256, U, (const unsigned long long *)label, comp);
+        LAUNCH(uf_init_kernel, grid_for(U, 256), 256, U, comp);
+        LAUNCH(uf_union_kernel, egrid, 256, edges, n_edges, (const i32 *)ctx->d_freq.p, (const i32 *)ctx->d_thr.p, comp);
+        LAUNCH(uf_flatten_kernel, grid_for(U, 256), 256, U, comp, label);
         CK(ctx->d_cedges.reserve(std::max<u64>(n_edges, 1) * sizeof(uint2)));
         CK(cudaMemsetAsync(&sc->scratch, 0, 8, ctx->stream));
         unsigned long long *n_c = (unsigned long long *)&sc->scratch;
         LAUNCH(contract_edges_kernel, egrid, 256, edges, n_edges, (const u32 *)comp, ctx->d_cedges.as<uint2>(), n_c);
-        for (;;) {
-            CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
-            for (int i = 0; i < 2; i++) {
-                LAUNCH(contracted_sweep_kernel, egrid, 256, (const uint2 *)ctx->d_cedges.p, (const unsigned long long *)n_c, label, sc);
-                LAUNCH(contracted_jump_kernel, egrid, 256, (const uint2 *)ctx->d_cedges.p, (const unsigned long long *)n_c, label, sc);
-            }
-            sweeps += 2;
-            rc = read_scalars(ctx);
-            if (rc) return rc;
-            if (!ctx->h_sc->changed) break;
-        }
+        sweeps += 1;
+        // Phase B on the contracted list (its length stays on the device); stamps restart: every contracted edge is relaxed once
+        CK(cudaMemsetAsync(ctx->d_stamp.p, 0, (size_t)U * 4, ctx->stream));
+        sweep_no = 0;
+        rc = sweep_batches(ctx->d_cedges.as<uint2>(), n_edges, n_c, -1, false);
+        if (rc) return rc;
         LAUNCH(expand_labels_kernel, grid_for(U, 256), 256, U, (const u32 *)comp, label);
       }
         LAUNCH(keep_from_label_kernel, grid_for(U, 256), 256, U, (const unsigned long long *)label, keep);
