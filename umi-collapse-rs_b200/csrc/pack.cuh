@@ -32,6 +32,7 @@ struct DevScalars {
     u32 frontier_cnt[2];             // frontier clustering: sizes of the two ping-pong frontiers
     u32 hot_bucket, hot_u0, hot_cnt, hot_pad;   // sharded run: the bucket whose neighbour search is split across devices
     i64 key_lo, key_hi;              // sharded run: smallest / largest (tid << 32 | biased pos) of the slice (range check of the cuts)
+    u32 seg_n_big, seg_n_tiles, seg_unsorted, seg_pad;   // segmented sort plan (SegPlanOut, seg_sort.cuh)
 };
 
 struct KeyLayout {

@@ -1,0 +1,407 @@
+// seg_sort.cuh — K2 bucket_group for coordinate-sorted input (what a BAM is): a SEGMENTED sort.
+//
+// The sort key is [P | S] with P = (contig, position) and S = (strand, [tlen,] UMI).  When the reads arrive ordered by P —
+// src/deduplicate_sam.rs:93 streams a coordinate-sorted BAM — the generic LSD radix sort (radix_sort.cuh) spends more than
+// half of its passes re-establishing an order the input already has.  Here the runs of equal P ("segments") stay where they
+// are and only their insides are ordered by S:
+//   plan     seg_block_summary_kernel  one read of the keys: per block of 2048 positions the number of segment heads, the
+//                                      first and the last head; also detects input that is NOT ordered by P (-> generic sort)
+//            seg_plan_kernel           one CTA over the block table (n / 2048 entries): previous / next head per block, the
+//                                      list of BIG segments (> 2048 reads: only the last head of a block can start one) and
+//                                      their tile table
+//   small    seg_window_sort_kernel    CTA b owns the segments that START in block b (at most 4095 reads): composite
+//                                      (segment-in-window | S | position) sorted by an LSD radix sort entirely in shared
+//                                      memory, ceil((bits(S) + bits(#segments)) / 8) passes, one global read + one write
+//   big      seg_hist_kernel + seg_onesweep  one-sweep LSD passes over S only (4 passes for 25 bits instead of 7 for 53),
+//                                      8-byte elements (S << idx_bits | read index) instead of key + index (24 B -> 16 B
+//                                      per read per pass), all big segments batched in one launch per pass: a tile belongs
+//                                      to one segment, its look-back stops at the segment's first tile
+// Output is exactly what the generic sort produces (sorted one-word keys + read indices), so K3 does not change.
+#pragma once
+#include "common.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+#define SEG_BLK 2048u                 // block of positions; segments longer than this are "big"
+#define SEG_WIN (2 * SEG_BLK)         // capacity of a window (segments starting in one block: < SEG_BLK + SEG_BLK reads)
+#define SEG_THREADS RS_THREADS        // 512: shares rs_rank_tile / RsShared with the one-sweep kernel
+#define SEG_WIN_ITEMS (SEG_WIN / SEG_THREADS)   // 8
+#define SEG_POS_BITS 12               // position-in-window field of the composite
+#define SEG_NONE 0xffffffffu
+
+struct SegBlock { u32 nheads, first, last, pad; };        // heads of segments that start in this block (positions), SEG_NONE = none
+struct SegBig { u32 start, len, tile0, pad; };            // a big segment and the index of its first tile
+struct SegPlanOut { u32 n_big, n_tiles, unsorted, pad; };
+
+// ---- plan, step 1: block table ----
+__global__ void __launch_bounds__(256) seg_block_summary_kernel(const u64 *__restrict__ key, u64 n, int sbits, SegBlock *__restrict__ blk,
+                                                                SegPlanOut *plan) {
+    const u64 base = (u64)blockIdx.x * SEG_BLK + (u64)threadIdx.x * 8;
+    u64 k[8];
+    u64 prev = 0;
+    if (base < n) {
+        if (base + 8 <= n) {
+            const ulonglong2 *kv = reinterpret_cast<const ulonglong2 *>(key + base);
+#pragma unroll
+            for (int q = 0; q < 4; q++) { const ulonglong2 t = __ldg(kv + q); k[2 * q] = t.x; k[2 * q + 1] = t.y; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) k[j] = base + j < n ? key[base + j] : 0;
+        }
+    }
+    prev = __shfl_up_sync(0xffffffffu, base < n ? k[7] : 0ull, 1);
+    if (lane_id() == 0) prev = (base > 0 && base < n) ? key[base - 1] : 0;
+    u32 cnt = 0, first = SEG_NONE, last = SEG_NONE, bad = 0;
+    if (base < n) {
+        u64 p = prev >> sbits;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const u64 i = base + j;
+            if (i < n) {
+                const u64 c = k[j] >> sbits;
+                if (i == 0 || c != p) { cnt++; if (first == SEG_NONE) first = (u32)i; last = (u32)i; }
+                if (i != 0 && c < p) bad = 1;
+                p = c;
+            }
+        }
+    }
+    // CTA reduction: sum, min (first), max (last; SEG_NONE = all ones must lose: map to 0 via +1 trick)
+    __shared__ u32 s_cnt[8], s_first[8], s_last[8], s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    u32 lastp = last == SEG_NONE ? 0u : last + 1u;           // 0 = none
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        lastp = max(lastp, __shfl_xor_sync(0xffffffffu, lastp, o));
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    __syncthreads();
+    if (lane_id() == 0) { s_cnt[threadIdx.x >> 5] = cnt; s_first[threadIdx.x >> 5] = first; s_last[threadIdx.x >> 5] = lastp; if (bad) s_bad = 1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 c = 0, f = SEG_NONE, l = 0;
+        for (int w = 0; w < 8; w++) { c += s_cnt[w]; f = min(f, s_first[w]); l = max(l, s_last[w]); }
+        blk[blockIdx.x] = SegBlock{c, f, l ? l - 1u : SEG_NONE, 0u};
+        if (s_bad) plan->unsorted = 1;
+    }
+}
+
+// ---- plan, step 2 (one CTA): next head after every block, big segments, tile table ----
+// next[b] = position of the first head in a block > b (n if none).  The last head of block b starts a big segment iff
+// next[b] - last[b] > SEG_BLK.  big_of_blk[b] = 1 in that case (the window kernel then stops before it).
+__global__ void __launch_bounds__(1024) seg_plan_kernel(const SegBlock *__restrict__ blk, u32 n_blk, u64 n, u32 tile, u32 *__restrict__ next_head,
+                                                        u8 *__restrict__ big_of_blk, SegBig *__restrict__ big, SegPlanOut *plan) {
+    __shared__ u32 sm[1024 / 32 + 1];
+    __shared__ u32 s_carry;
+    // suffix minimum of `first`, walking the block table backwards in chunks of 1024
+    if (threadIdx.x == 0) s_carry = (u32)n;
+    __syncthreads();
+    for (long long hi = (long long)n_blk; hi > 0; hi -= 1024) {
+        const long long b = hi - 1 - (long long)threadIdx.x;          // thread 0 takes the last block of the chunk
+        u32 v = (b >= 0 && blk[b].first != SEG_NONE) ? blk[b].first : SEG_NONE;
+        // exclusive suffix-min within the chunk = exclusive prefix-min in thread order
+        u32 inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane_id() >= (u32)o) inc = min(inc, t); }
+        if (lane_id() == 31) sm[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            u32 s = sm[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, s, o); if (lane_id() >= (u32)o) s = min(s, t); }
+            sm[threadIdx.x] = s;                                       // inclusive over warps
+        }
+        __syncthreads();
+        u32 ex = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane_id() == 0) ex = SEG_NONE;
+        const u32 w = threadIdx.x >> 5;
+        if (w > 0) ex = min(ex, sm[w - 1]);
+        const u32 carry = s_carry;
+        ex = min(ex, carry);                                           // heads in later chunks / n
+        if (b >= 0) next_head[b] = ex;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = min(carry, min(ex, v));
+        __syncthreads();
+    }
+    // big segments in block order, with their first tile (exclusive prefix sum of tile counts)
+    u32 carry_big = 0, carry_tiles = 0;
+    for (u32 lo = 0; lo < n_blk; lo += 1024) {
+        const u32 b = lo + threadIdx.x;
+        u32 start = 0, len = 0, is_big = 0;
+        if (b < n_blk && blk[b].last != SEG_NONE) {
+            start = blk[b].last; len = next_head[b] - start;
+            is_big = len > SEG_BLK ? 1u : 0u;
+        }
+        if (b < n_blk) big_of_blk[b] = (u8)is_big;
+        const u32 nt = is_big ? (len + tile - 1) / tile : 0u;
+        u32 tot_b, tot_t;
+        const u32 ex_b = block_exclusive_scan<u32, 1024>(is_big, sm, &tot_b);
+        const u32 ex_t = block_exclusive_scan<u32, 1024>(nt, sm, &tot_t);
+        if (is_big) big[carry_big + ex_b] = SegBig{start, len, carry_tiles + ex_t, 0u};
+        carry_big += tot_b; carry_tiles += tot_t;
+    }
+    if (threadIdx.x == 0) { plan->n_big = carry_big; plan->n_tiles = carry_tiles; }
+}
+
+// ---- small segments: one window per block, sorted in shared memory ----
+struct SegWinShared {
+    u32 whist[RS_WARPS][RS_RADIX];
+    u32 slocal[RS_RADIX];
+    u32 sscan[SEG_THREADS / 32 + 1];
+};
+
+// one LSD pass over the elements held in registers (slot e = warp * ITEMS * 32 + j * 32 + lane); result back in x[], in slot order
+template <int ITEMS>
+__device__ __forceinline__ void seg_local_pass(u64 (&x)[ITEMS], u32 count, int shift, u32 mask, SegWinShared &S, u64 *sbuf) {
+    const u32 w = threadIdx.x >> 5, lane = lane_id();
+    u32 packed[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 e = (w * ITEMS + j) * 32 + lane;
+        packed[j] = e < count ? ((u32)(x[j] >> shift) & mask) : 0xffffffffu;
+    }
+    rs_rank_tile<ITEMS, false>(packed, S.whist);
+    __syncthreads();
+    u32 total = 0;
+    if (threadIdx.x < RS_RADIX) {
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) { const u32 t = S.whist[ww][threadIdx.x]; S.whist[ww][threadIdx.x] = total; total += t; }
+    }
+    u32 tot_all;
+    const u32 lstart = block_exclusive_scan<u32, SEG_THREADS>(total, S.sscan, &tot_all);
+    if (threadIdx.x < RS_RADIX) S.slocal[threadIdx.x] = lstart;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        if (packed[j] != 0xffffffffu) {
+            const u32 d = packed[j] & (RS_RADIX - 1), r = packed[j] >> RS_RB;
+            sbuf[S.slocal[d] + S.whist[w][d] + r] = x[j];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 e = (w * ITEMS + j) * 32 + lane;
+        x[j] = e < count ? sbuf[e] : 0;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SEG_THREADS, 2) seg_window_sort_kernel(const u64 *__restrict__ key_in, u64 n, int sbits, const SegBlock *__restrict__ blk,
+                                                                         const u32 *__restrict__ next_head, const u8 *__restrict__ big_of_blk,
+                                                                         u64 *__restrict__ key_out, u32 *__restrict__ idx_out) {
+    __shared__ SegWinShared S;
+    extern __shared__ __align__(16) unsigned char seg_win_dyn[];         // u64 sbuf[SEG_WIN] (static + this exceeds 48 KB)
+    u64 *sbuf = reinterpret_cast<u64 *>(seg_win_dyn);
+    const SegBlock sb = blk[blockIdx.x];
+    if (sb.nheads == 0) return;                                   // the block lies inside a segment that started earlier
+    const u32 lo = sb.first;
+    const u32 hi = big_of_blk[blockIdx.x] ? sb.last : next_head[blockIdx.x];
+    const u32 count = hi - lo;                                    // < SEG_WIN
+    if (count == 0) return;
+    const u64 smask = (1ull << sbits) - 1;
+    // blocked load (8 consecutive reads per thread) for the head scan
+    const u32 e0 = threadIdx.x * SEG_WIN_ITEMS;
+    u64 k[SEG_WIN_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SEG_WIN_ITEMS; j++) k[j] = e0 + j < count ? key_in[(u64)lo + e0 + j] : 0;
+    u64 prev = __shfl_up_sync(0xffffffffu, k[SEG_WIN_ITEMS - 1], 1);
+    if (lane_id() == 0) prev = (e0 > 0 && e0 < count) ? key_in[(u64)lo + e0 - 1] : 0;
+    u32 hm = 0;
+    {
+        u64 p = prev >> sbits;
+#pragma unroll
+        for (int j = 0; j < SEG_WIN_ITEMS; j++) {
+            const u64 c = k[j] >> sbits;
+            if (e0 + j < count && e0 + j > 0 && c != p) hm |= 1u << j;
+            p = c;
+        }
+    }
+    u32 nseg_m1;
+    u32 seg = block_exclusive_scan<u32, SEG_THREADS>((u32)__popc(hm), S.sscan, &nseg_m1);      // segment-in-window of the element before e0
+    // composite = (segment | S | position in window)
+#pragma unroll
+    for (int j = 0; j < SEG_WIN_ITEMS; j++) {
+        seg += (hm >> j) & 1u;
+        if (e0 + j < count) sbuf[e0 + j] = ((((u64)seg << sbits) | (k[j] & smask)) << SEG_POS_BITS) | (u64)(e0 + j);
+    }
+    __syncthreads();
+    const u32 w = threadIdx.x >> 5, lane = lane_id();
+    u64 x[SEG_WIN_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SEG_WIN_ITEMS; j++) {
+        const u32 e = (w * SEG_WIN_ITEMS + j) * 32 + lane;
+        x[j] = e < count ? sbuf[e] : 0;
+    }
+    __syncthreads();
+    int segbits = 0;
+    while ((nseg_m1 >> segbits) != 0) segbits++;
+    const int bits = sbits + segbits;
+    for (int done = 0; done < bits; done += RS_RB) {
+        const int b = min(RS_RB, bits - done);
+        seg_local_pass<SEG_WIN_ITEMS>(x, count, SEG_POS_BITS + done, (1u << b) - 1u, S, sbuf);
+    }
+    // slot e now holds the element of sorted position lo + e; P comes from the (unsorted) input at the same position
+#pragma unroll
+    for (int j = 0; j < SEG_WIN_ITEMS; j++) {
+        const u32 e = (w * SEG_WIN_ITEMS + j) * 32 + lane;
+        if (e < count) {
+            const u64 i = (u64)lo + e;
+            key_out[i] = (key_in[i] & ~smask) | ((x[j] >> SEG_POS_BITS) & smask);
+            idx_out[i] = lo + (u32)(x[j] & ((1u << SEG_POS_BITS) - 1u));
+        }
+    }
+}
+
+// ---- big segments: batched one-sweep passes over S ----
+#define SEG_ITEMS 12
+#define SEG_TILE (SEG_THREADS * SEG_ITEMS)     // 6144
+#define SEG_MAX_PASSES 6
+
+__device__ __forceinline__ u32 seg_find_big(const SegBig *__restrict__ big, u32 n_big, u32 tile) {
+    u32 lo = 0, hi = n_big;                    // last segment with tile0 <= tile
+    while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (big[mid].tile0 <= tile) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// digit histograms of every pass for every big segment: hist[seg][pass][digit]
+__global__ void __launch_bounds__(SEG_THREADS) seg_hist_kernel(const u64 *__restrict__ key_in, int sbits, int npass, const SegBig *__restrict__ big,
+                                                               u32 n_big, u32 n_tiles, u32 *__restrict__ hist) {
+    __shared__ u32 sh[SEG_MAX_PASSES * RS_RADIX];
+    __shared__ u32 s_seg;
+    for (u32 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_seg = seg_find_big(big, n_big, tile);
+        for (u32 i = threadIdx.x; i < (u32)npass * RS_RADIX; i += SEG_THREADS) sh[i] = 0;
+        __syncthreads();
+        const SegBig sg = big[s_seg];
+        const u32 off = (tile - sg.tile0) * SEG_TILE, cnt = min((u32)SEG_TILE, sg.len - off);
+        const u64 smask = (1ull << sbits) - 1;
+        for (u32 e = threadIdx.x; e < cnt; e += SEG_THREADS) {
+            const u64 s = key_in[(u64)sg.start + off + e] & smask;
+            for (int p = 0; p < npass; p++) atomicAdd(&sh[p * RS_RADIX + ((u32)(s >> (p * RS_RB)) & (RS_RADIX - 1))], 1u);
+        }
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < (u32)npass * RS_RADIX; i += SEG_THREADS)
+            if (sh[i]) atomicAdd(&hist[(u64)s_seg * npass * RS_RADIX + i], sh[i]);
+    }
+}
+// exclusive scan of each (segment, pass) histogram: one CTA of RS_RADIX threads per row
+__global__ void __launch_bounds__(RS_RADIX) seg_digit_starts_kernel(u32 *hist, u32 n_rows) {
+    __shared__ u32 sm[RS_RADIX / 32 + 1];
+    for (u32 row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const u32 v = hist[(u64)row * RS_RADIX + threadIdx.x];
+        u32 tot;
+        const u32 ex = block_exclusive_scan<u32, RS_RADIX>(v, sm, &tot);
+        hist[(u64)row * RS_RADIX + threadIdx.x] = ex;
+    }
+}
+
+// One pass.  FIRST: elements are built from key_in (S << ib | read index); LAST: writes sorted keys and indices.
+template <int ITEMS>
+__global__ void __launch_bounds__(SEG_THREADS, 2) seg_onesweep(const u64 *__restrict__ key_in, const u64 *__restrict__ w_in, u64 *__restrict__ w_out,
+                                                               u64 *__restrict__ key_out, u32 *__restrict__ idx_out, int sbits, int ib, int pass,
+                                                               int npass, const SegBig *__restrict__ big, u32 n_big, u32 n_tiles,
+                                                               const u32 *__restrict__ hist, unsigned long long *tile_state, u32 *ticket, u32 *err) {
+    constexpr u32 TILE = SEG_THREADS * ITEMS;
+    extern __shared__ __align__(16) unsigned char seg_dyn[];            // u64 selem[TILE]
+    u64 *selem = reinterpret_cast<u64 *>(seg_dyn);
+    __shared__ RsShared S;
+    __shared__ u32 s_seg;
+    if (threadIdx.x == 0) { const u32 t = atomicAdd(ticket, 1u); S.s_tile = t; s_seg = t < n_tiles ? seg_find_big(big, n_big, t) : 0u; }
+    __syncthreads();
+    const u32 tile = S.s_tile;
+    if (tile >= n_tiles) return;
+    const u32 seg_i = s_seg;
+    const SegBig sg = big[seg_i];
+    const u32 off = (tile - sg.tile0) * TILE, tile_count = min(TILE, sg.len - off);
+    const u64 tile_base = (u64)sg.start + off;
+    const bool first = pass == 0, last = pass == npass - 1;
+    const u64 smask = (1ull << sbits) - 1;
+    const int sh = ib + pass * RS_RB;
+    const u32 mask = (1u << min(RS_RB, sbits - pass * RS_RB)) - 1u;
+    const u32 *digit_start = hist + ((u64)seg_i * npass + pass) * RS_RADIX;
+    u32 (*whist)[RS_RADIX] = S.whist;
+    u32 *sbase = S.sbase, *slocal = S.slocal, *sscan = S.sscan;
+    const u32 w = threadIdx.x >> 5, lane = lane_id();
+    u64 x[ITEMS];
+    u32 packed[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 e = (w * ITEMS + j) * 32 + lane;
+        const u64 i = tile_base + e;
+        if (e < tile_count) x[j] = first ? (((key_in[i] & smask) << ib) | i) : w_in[i]; else x[j] = 0;
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 e = (w * ITEMS + j) * 32 + lane;
+        packed[j] = e < tile_count ? ((u32)(x[j] >> sh) & mask) : 0xffffffffu;
+    }
+    rs_rank_tile<ITEMS, false>(packed, whist);
+    __syncthreads();
+    u32 total = 0;
+    if (threadIdx.x < RS_RADIX) {
+        const u32 d = threadIdx.x;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) { const u32 t = whist[ww][d]; whist[ww][d] = total; total += t; }
+        atomicExch(tile_state + (u64)tile * RS_RADIX + d, (tile == sg.tile0 ? RS_FLAG_PREFIX : RS_FLAG_AGG) | (unsigned long long)total);
+    }
+    u32 tot_all;
+    const u32 lstart = block_exclusive_scan<u32, SEG_THREADS>(total, sscan, &tot_all);
+    if (threadIdx.x < RS_RADIX) slocal[threadIdx.x] = lstart;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        if (packed[j] != 0xffffffffu) {
+            const u32 d = packed[j] & (RS_RADIX - 1), r = packed[j] >> RS_RB;
+            selem[slocal[d] + whist[w][d] + r] = x[j];
+        }
+    }
+    if (threadIdx.x < RS_RADIX) {
+        const u32 d = threadIdx.x;
+        unsigned long long *mine = tile_state + (u64)tile * RS_RADIX + d;
+        u64 excl = 0;
+        if (tile != sg.tile0) {
+            u32 p = tile;                      // predecessors [tile0, p) of this segment are still to be accounted for
+            u32 spins = 0;
+            bool done = false;
+            while (!done && p > sg.tile0) {
+                unsigned long long v[RS_LB];
+#pragma unroll
+                for (int i = 0; i < RS_LB; i++) {
+                    const volatile unsigned long long *prev = tile_state + (u64)(p > sg.tile0 + (u32)i ? p - 1 - i : sg.tile0) * RS_RADIX + d;
+                    v[i] = *prev;
+                }
+#pragma unroll
+                for (int i = 0; i < RS_LB; i++) {
+                    if (done || p == sg.tile0) break;
+                    if ((v[i] & RS_FLAG_MASK) == 0) {
+                        if (++spins > (1u << 24)) { err[0] = 1; done = true; }
+                        if (i == 0) __nanosleep(40);
+                        break;
+                    }
+                    excl += v[i] & ~RS_FLAG_MASK;
+                    p--;
+                    if ((v[i] & RS_FLAG_MASK) == RS_FLAG_PREFIX) done = true;
+                }
+            }
+            atomicExch(mine, RS_FLAG_PREFIX | (unsigned long long)(excl + total));
+        }
+        sbase[d] = digit_start[d] + (u32)excl;
+    }
+    __syncthreads();
+    const u64 pseg = last ? (key_in[sg.start] & ~smask) : 0ull;        // every read of the segment has this (contig, position)
+    const u64 imask = (1ull << ib) - 1;
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 i = threadIdx.x + j * SEG_THREADS;
+        if (i < tile_count) {
+            const u64 v = selem[i];
+            const u32 d = (u32)(v >> sh) & mask;
+            const u64 pos = (u64)sg.start + sbase[d] + (i - slocal[d]);
+            if (last) { key_out[pos] = pseg | (v >> ib); idx_out[pos] = (u32)(v & imask); }
+            else w_out[pos] = v;
+        }
+    }
+}

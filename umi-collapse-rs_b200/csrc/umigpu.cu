@@ -24,6 +24,7 @@
 #include "pack.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
+#include "seg_sort.cuh"
 
 static thread_local std::string g_last_error;
 
@@ -78,6 +79,8 @@ struct umigpu_ctx {
     bool st_weighted = false, st_need_edges = false;
     int sorted_cur = 0;                   // which ping-pong buffer holds the sorted keys / indices
     DevBuf d_stamp, d_rowptr, d_front[2]; // frontier clustering
+    DevBuf d_segblk, d_segnext, d_segflag, d_segbig, d_seghist, d_wbuf[2];   // segmented sort (coordinate-sorted input)
+    bool used_seg_sort = false;
     // sharded run (several devices, one dataset): see "shard group" below
     u32 skip_bucket = 0xffffffffu;        // owner: the hot bucket is searched by every device of the group, not here
     u32 band = 0, n_bands = 1;            // hot child: this device evaluates the row tiles ti with ti % n_bands == band
@@ -189,6 +192,8 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
     if (ctx->h_umirep) cudaFreeHost(ctx->h_umirep);
     ctx->d_chunks.release(); ctx->d_umirep.release();
     ctx->d_stamp.release(); ctx->d_rowptr.release(); ctx->d_front[0].release(); ctx->d_front[1].release();
+    ctx->d_segblk.release(); ctx->d_segnext.release(); ctx->d_segflag.release(); ctx->d_segbig.release(); ctx->d_seghist.release();
+    ctx->d_wbuf[0].release(); ctx->d_wbuf[1].release();
     if (ctx->hot) { umigpu_destroy(ctx->hot); ctx->hot = nullptr; }
     xchg_release(ctx);
     DevBuf *bb[] = {&ctx->d_bamraw, &ctx->d_bamoff, &ctx->d_btid, &ctx->d_bpos, &ctx->d_brev, &ctx->d_bumi2, &ctx->d_bnmask, &ctx->d_bscore, &ctx->d_bvalid, &ctx->d_orig};
@@ -512,6 +517,72 @@ static int run_sort(umigpu_ctx *ctx, u64 n, int nw, const SortPlan &plan, int *c
     return UMIGPU_OK;
 }
 
+// Segmented sort for input that arrives ordered by (contig, position) — seg_sort.cuh.  *done = false: the input is not
+// ordered that way (or the key does not fit the packed element): the caller runs the generic sort.  Result in buffer 1.
+static int run_sort_presorted(umigpu_ctx *ctx, u64 n, const KeyLayout &lay, bool *done) {
+    *done = false;
+    DevScalars *sc = ctx->d_sc.as<DevScalars>();
+    const int sbits = 1 + lay.tlen_bits + lay.umi_bits, ib = std::max(1, bits_for(n - 1));
+    if (lay.nw != 1 || sbits > 40 || sbits + ib > 64 || getenv("UMIGPU_NO_SEG_SORT")) return UMIGPU_OK;
+    const u32 nblk = (u32)ceil_div_u64(n, SEG_BLK);
+    CK(ctx->d_segblk.reserve((size_t)nblk * sizeof(SegBlock))); CK(ctx->d_segnext.reserve((size_t)nblk * 4)); CK(ctx->d_segflag.reserve(nblk));
+    CK(ctx->d_segbig.reserve(((size_t)nblk + 1) * sizeof(SegBig)));
+    CK(cudaMemsetAsync(&sc->seg_n_big, 0, 16, ctx->stream));
+    SegPlanOut *plan = reinterpret_cast<SegPlanOut *>(&sc->seg_n_big);
+    const u64 *key_in = ctx->d_key[0][0].as<u64>();
+    u64 *key_out = ctx->d_key[1][0].as<u64>();
+    u32 *idx_out = ctx->d_idx[1].as<u32>();
+    LAUNCH(seg_block_summary_kernel, nblk, 256, key_in, n, sbits, ctx->d_segblk.as<SegBlock>(), plan);
+    LAUNCH(seg_plan_kernel, 1, 1024, (const SegBlock *)ctx->d_segblk.p, nblk, n, (u32)SEG_TILE, ctx->d_segnext.as<u32>(), ctx->d_segflag.as<u8>(),
+           ctx->d_segbig.as<SegBig>(), plan);
+    int rc = read_scalars(ctx);
+    if (rc) return rc;
+    if (ctx->h_sc->seg_unsorted) return UMIGPU_OK;
+    const u32 n_big = ctx->h_sc->seg_n_big, n_tiles = ctx->h_sc->seg_n_tiles;
+    // small segments: one window per block, on the side stream while the big segments' passes run on the main one
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    {
+        cudaStream_t main_stream = ctx->stream;
+        ctx->stream = n_big ? ctx->side : main_stream;
+        int r2 = [&]() -> int {
+            LAUNCH_SMEM(seg_window_sort_kernel, nblk, SEG_THREADS, (size_t)SEG_WIN * 8, key_in, n, sbits, (const SegBlock *)ctx->d_segblk.p,
+                        (const u32 *)ctx->d_segnext.p, (const u8 *)ctx->d_segflag.p, key_out, idx_out);
+            return UMIGPU_OK;
+        }();
+        cudaError_t ej = cudaEventRecord(ctx->ev_join, ctx->stream);
+        ctx->stream = main_stream;
+        if (r2) return r2;
+        CK(ej);
+    }
+    if (n_big) {
+        const int npass = (sbits + RS_RB - 1) / RS_RB;
+        if (npass > SEG_MAX_PASSES) return fail(ctx, UMIGPU_ERR_STATE, "internal: segmented sort with %d passes", npass);
+        const size_t hist_bytes = (size_t)n_big * npass * RS_RADIX * 4;
+        CK(ctx->d_seghist.reserve(hist_bytes));
+        CK(ctx->d_tilestate.reserve((size_t)n_tiles * RS_RADIX * 8));
+        if (npass > 1) { CK(ctx->d_wbuf[0].reserve(n * 8)); if (npass > 2) CK(ctx->d_wbuf[1].reserve(n * 8)); }
+        CK(cudaMemsetAsync(ctx->d_seghist.p, 0, hist_bytes, ctx->stream));
+        CK(cudaMemsetAsync(&sc->sort_err, 0, 4, ctx->stream));
+        const SegBig *big = (const SegBig *)ctx->d_segbig.p;
+        LAUNCH(seg_hist_kernel, std::min<u32>(n_tiles, (u32)ctx->num_sms * 4), SEG_THREADS, key_in, sbits, npass, big, n_big, n_tiles, ctx->d_seghist.as<u32>());
+        LAUNCH(seg_digit_starts_kernel, std::min<u32>(n_big * (u32)npass, (u32)ctx->num_sms * 8), RS_RADIX, ctx->d_seghist.as<u32>(), n_big * (u32)npass);
+        int wcur = 0;
+        for (int p = 0; p < npass; p++) {
+            CK(cudaMemsetAsync(ctx->d_tilestate.p, 0, (size_t)n_tiles * RS_RADIX * 8, ctx->stream));
+            CK(cudaMemsetAsync(&sc->sort_ticket, 0, 4, ctx->stream));
+            const u64 *w_in = p == 0 ? nullptr : ctx->d_wbuf[wcur].as<u64>();
+            u64 *w_out = p == npass - 1 ? nullptr : ctx->d_wbuf[p == 0 ? 0 : wcur ^ 1].as<u64>();
+            LAUNCH_SMEM((seg_onesweep<SEG_ITEMS>), n_tiles, SEG_THREADS, (size_t)SEG_TILE * 8, key_in, w_in, w_out, key_out, idx_out, sbits, ib, p, npass,
+                        big, n_big, n_tiles, (const u32 *)ctx->d_seghist.p, ctx->d_tilestate.as<unsigned long long>(), &sc->sort_ticket, &sc->sort_err);
+            if (p > 0) wcur ^= 1;
+        }
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    }
+    *done = true;
+    return UMIGPU_OK;
+}
+
 // One ordering of the unique UMIs of a set of buckets, as seen by the neighbour search.
 struct NView {
     const uint2 *planes; const u32 *nplane; const u64 *ucode;
@@ -712,8 +783,12 @@ static int stage_group(umigpu_ctx *ctx, bool want_labels, bool force_inf_thr) {
     // ---- K2 sort ----
     STAGE_BEGIN(UMIGPU_STAGE_SORT);
     int cur = 0;
-    rc = run_sort(ctx, n, lay.nw, rs_plan(lay.total_bits), &cur);
+    bool seg_done = false;
+    rc = run_sort_presorted(ctx, n, lay, &seg_done);
     if (rc) return rc;
+    ctx->used_seg_sort = seg_done;
+    if (seg_done) cur = 1;
+    else { rc = run_sort(ctx, n, lay.nw, rs_plan(lay.total_bits), &cur); if (rc) return rc; }
     STAGE_END(UMIGPU_STAGE_SORT);
     ctx->sorted_cur = cur;
     SortedKeys sk{ctx->d_key[cur][0].as<u64>(), lay.nw == 2 ? ctx->d_key[cur][1].as<u64>() : nullptr, lay.umi_bits};
