@@ -22,13 +22,15 @@
 template <bool HASN>
 __global__ void __launch_bounds__(256) onehot_build_kernel(u32 n_groups /* 4 per block */, const u32 *__restrict__ blk_first,
                                                            const u32 *__restrict__ blk_cnt, const uint2 *__restrict__ planes,
-                                                           const u32 *__restrict__ nplane, int L, int LP, u32 *__restrict__ eq) {
+                                                           const u32 *__restrict__ nplane, int L, int LP, u32 *__restrict__ eq,
+                                                           const u8 *__restrict__ need /* nullable: only blocks that are a column of some pair */) {
     constexpr int XS = HASN ? 8 : 4;
     constexpr int NLET = HASN ? 5 : 4;
     // one warp per 128-UMI block: lane x collects the four 32-UMI groups' words of letter x and stores them as one
     // 16-byte vector, so every position is written as XS consecutive uint4
     const u32 gb = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = lane_id();
     if (gb >= (n_groups >> 2)) return;
+    if (need && !need[gb]) return;
     const u32 cnt = blk_cnt[gb], first = blk_first[gb];
     uint2 p[4]; u32 pn[4];
 #pragma unroll
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(256) onehot_build_kernel(u32 n_groups /* 4 per
 // fill == 0: only counts (out_count += survivors); fill == 1: appends uint2(row block, col block)
 __global__ void __launch_bounds__(256) expand_blocks_kernel(const TileItem *__restrict__ items, u32 n_items, const u32 *__restrict__ bsum,
                                                             int L, int k, int cull, MiParams mi, int fill, uint2 *__restrict__ pairs,
-                                                            unsigned long long *out_count) {
+                                                            unsigned long long *out_count, u8 *__restrict__ need = nullptr) {
     const u32 w = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = lane_id();
     if (w >= n_items) return;
     const TileItem it = items[w];
@@ -104,7 +106,10 @@ __global__ void __launch_bounds__(256) expand_blocks_kernel(const TileItem *__re
     if (fill) {
         u64 o = base + inc - cnt;
 #pragma unroll
-        for (int i = 0; i < 8; i++) if (live & (1u << i)) pairs[o++] = make_uint2((row_blk0 + r) | (filt ? 0x80000000u : 0u), it.col_blk0 + c0 + i);
+        for (int i = 0; i < 8; i++) if (live & (1u << i)) {
+            pairs[o++] = make_uint2((row_blk0 + r) | (filt ? 0x80000000u : 0u), it.col_blk0 + c0 + i);
+            if (need) need[it.col_blk0 + c0 + i] = 1;
+        }
     }
 }
 

@@ -258,6 +258,14 @@ __global__ void __launch_bounds__(SEG_THREADS, 2) seg_window_sort_kernel(const u
 #define SEG_ITEMS 12
 #define SEG_TILE (SEG_THREADS * SEG_ITEMS)     // 6144
 #define SEG_MAX_PASSES 6
+// the bits of S spread evenly over the passes (25 bits -> 7,6,6,6: a pass of one leftover bit would cost a full pass)
+struct SegPasses { int npass; int shift[SEG_MAX_PASSES]; int bits[SEG_MAX_PASSES]; };
+static inline SegPasses seg_passes(int sbits) {
+    SegPasses sp; sp.npass = (sbits + RS_RB - 1) / RS_RB;
+    int done = 0;
+    for (int i = 0; i < sp.npass; i++) { const int b = (sbits - done + (sp.npass - i) - 1) / (sp.npass - i); sp.shift[i] = done; sp.bits[i] = b; done += b; }
+    return sp;
+}
 
 __device__ __forceinline__ u32 seg_find_big(const SegBig *__restrict__ big, u32 n_big, u32 tile) {
     u32 lo = 0, hi = n_big;                    // last segment with tile0 <= tile
@@ -266,8 +274,9 @@ __device__ __forceinline__ u32 seg_find_big(const SegBig *__restrict__ big, u32 
 }
 
 // digit histograms of every pass for every big segment: hist[seg][pass][digit]
-__global__ void __launch_bounds__(SEG_THREADS) seg_hist_kernel(const u64 *__restrict__ key_in, int sbits, int npass, const SegBig *__restrict__ big,
+__global__ void __launch_bounds__(SEG_THREADS) seg_hist_kernel(const u64 *__restrict__ key_in, int sbits, SegPasses sp, const SegBig *__restrict__ big,
                                                                u32 n_big, u32 n_tiles, u32 *__restrict__ hist) {
+    const int npass = sp.npass;
     __shared__ u32 sh[SEG_MAX_PASSES * RS_RADIX];
     __shared__ u32 s_seg;
     for (u32 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -280,7 +289,7 @@ __global__ void __launch_bounds__(SEG_THREADS) seg_hist_kernel(const u64 *__rest
         const u64 smask = (1ull << sbits) - 1;
         for (u32 e = threadIdx.x; e < cnt; e += SEG_THREADS) {
             const u64 s = key_in[(u64)sg.start + off + e] & smask;
-            for (int p = 0; p < npass; p++) atomicAdd(&sh[p * RS_RADIX + ((u32)(s >> (p * RS_RB)) & (RS_RADIX - 1))], 1u);
+            for (int p = 0; p < npass; p++) atomicAdd(&sh[p * RS_RADIX + ((u32)(s >> sp.shift[p]) & ((1u << sp.bits[p]) - 1u))], 1u);
         }
         __syncthreads();
         for (u32 i = threadIdx.x; i < (u32)npass * RS_RADIX; i += SEG_THREADS)
@@ -299,29 +308,22 @@ __global__ void __launch_bounds__(RS_RADIX) seg_digit_starts_kernel(u32 *hist, u
 }
 
 // One pass.  FIRST: elements are built from key_in (S << ib | read index); LAST: writes sorted keys and indices.
-template <int ITEMS>
-__global__ void __launch_bounds__(SEG_THREADS, 2) seg_onesweep(const u64 *__restrict__ key_in, const u64 *__restrict__ w_in, u64 *__restrict__ w_out,
-                                                               u64 *__restrict__ key_out, u32 *__restrict__ idx_out, int sbits, int ib, int pass,
-                                                               int npass, const SegBig *__restrict__ big, u32 n_big, u32 n_tiles,
-                                                               const u32 *__restrict__ hist, unsigned long long *tile_state, u32 *ticket, u32 *err) {
+// FULL = the tile has all TILE elements (every tile of a segment but its last): no bounds checks, no activity ballots.
+struct SegPassArgs {
+    const u64 *key_in; const u64 *w_in; u64 *w_out; u64 *key_out; u32 *idx_out;
+    int sbits, ib, pass; SegPasses sp;
+    const SegBig *big; u32 n_big, n_tiles; const u32 *hist; unsigned long long *tile_state; u32 *ticket, *err;
+};
+template <int ITEMS, bool FULL>
+__device__ __forceinline__ void seg_onesweep_body(const SegPassArgs &a, RsShared &S, u64 *selem, u32 tile, u32 seg_i, const SegBig sg, u32 off, u32 tile_count) {
     constexpr u32 TILE = SEG_THREADS * ITEMS;
-    extern __shared__ __align__(16) unsigned char seg_dyn[];            // u64 selem[TILE]
-    u64 *selem = reinterpret_cast<u64 *>(seg_dyn);
-    __shared__ RsShared S;
-    __shared__ u32 s_seg;
-    if (threadIdx.x == 0) { const u32 t = atomicAdd(ticket, 1u); S.s_tile = t; s_seg = t < n_tiles ? seg_find_big(big, n_big, t) : 0u; }
-    __syncthreads();
-    const u32 tile = S.s_tile;
-    if (tile >= n_tiles) return;
-    const u32 seg_i = s_seg;
-    const SegBig sg = big[seg_i];
-    const u32 off = (tile - sg.tile0) * TILE, tile_count = min(TILE, sg.len - off);
     const u64 tile_base = (u64)sg.start + off;
+    const int npass = a.sp.npass, pass = a.pass, ib = a.ib;
     const bool first = pass == 0, last = pass == npass - 1;
-    const u64 smask = (1ull << sbits) - 1;
-    const int sh = ib + pass * RS_RB;
-    const u32 mask = (1u << min(RS_RB, sbits - pass * RS_RB)) - 1u;
-    const u32 *digit_start = hist + ((u64)seg_i * npass + pass) * RS_RADIX;
+    const u64 smask = (1ull << a.sbits) - 1;
+    const int sh = ib + a.sp.shift[pass];
+    const u32 mask = (1u << a.sp.bits[pass]) - 1u;
+    const u32 *digit_start = a.hist + ((u64)seg_i * npass + pass) * RS_RADIX;
     u32 (*whist)[RS_RADIX] = S.whist;
     u32 *sbase = S.sbase, *slocal = S.slocal, *sscan = S.sscan;
     const u32 w = threadIdx.x >> 5, lane = lane_id();
@@ -331,21 +333,21 @@ __global__ void __launch_bounds__(SEG_THREADS, 2) seg_onesweep(const u64 *__rest
     for (int j = 0; j < ITEMS; j++) {
         const u32 e = (w * ITEMS + j) * 32 + lane;
         const u64 i = tile_base + e;
-        if (e < tile_count) x[j] = first ? (((key_in[i] & smask) << ib) | i) : w_in[i]; else x[j] = 0;
+        if (FULL || e < tile_count) x[j] = first ? (((a.key_in[i] & smask) << ib) | i) : a.w_in[i]; else x[j] = 0;
     }
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         const u32 e = (w * ITEMS + j) * 32 + lane;
-        packed[j] = e < tile_count ? ((u32)(x[j] >> sh) & mask) : 0xffffffffu;
+        packed[j] = (FULL || e < tile_count) ? ((u32)(x[j] >> sh) & mask) : 0xffffffffu;
     }
-    rs_rank_tile<ITEMS, false>(packed, whist);
+    rs_rank_tile<ITEMS, FULL>(packed, whist);
     __syncthreads();
     u32 total = 0;
     if (threadIdx.x < RS_RADIX) {
         const u32 d = threadIdx.x;
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ww++) { const u32 t = whist[ww][d]; whist[ww][d] = total; total += t; }
-        atomicExch(tile_state + (u64)tile * RS_RADIX + d, (tile == sg.tile0 ? RS_FLAG_PREFIX : RS_FLAG_AGG) | (unsigned long long)total);
+        atomicExch(a.tile_state + (u64)tile * RS_RADIX + d, (tile == sg.tile0 ? RS_FLAG_PREFIX : RS_FLAG_AGG) | (unsigned long long)total);
     }
     u32 tot_all;
     const u32 lstart = block_exclusive_scan<u32, SEG_THREADS>(total, sscan, &tot_all);
@@ -353,14 +355,14 @@ __global__ void __launch_bounds__(SEG_THREADS, 2) seg_onesweep(const u64 *__rest
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
-        if (packed[j] != 0xffffffffu) {
+        if (FULL || packed[j] != 0xffffffffu) {
             const u32 d = packed[j] & (RS_RADIX - 1), r = packed[j] >> RS_RB;
             selem[slocal[d] + whist[w][d] + r] = x[j];
         }
     }
     if (threadIdx.x < RS_RADIX) {
         const u32 d = threadIdx.x;
-        unsigned long long *mine = tile_state + (u64)tile * RS_RADIX + d;
+        unsigned long long *mine = a.tile_state + (u64)tile * RS_RADIX + d;
         u64 excl = 0;
         if (tile != sg.tile0) {
             u32 p = tile;                      // predecessors [tile0, p) of this segment are still to be accounted for
@@ -370,14 +372,14 @@ __global__ void __launch_bounds__(SEG_THREADS, 2) seg_onesweep(const u64 *__rest
                 unsigned long long v[RS_LB];
 #pragma unroll
                 for (int i = 0; i < RS_LB; i++) {
-                    const volatile unsigned long long *prev = tile_state + (u64)(p > sg.tile0 + (u32)i ? p - 1 - i : sg.tile0) * RS_RADIX + d;
+                    const volatile unsigned long long *prev = a.tile_state + (u64)(p > sg.tile0 + (u32)i ? p - 1 - i : sg.tile0) * RS_RADIX + d;
                     v[i] = *prev;
                 }
 #pragma unroll
                 for (int i = 0; i < RS_LB; i++) {
                     if (done || p == sg.tile0) break;
                     if ((v[i] & RS_FLAG_MASK) == 0) {
-                        if (++spins > (1u << 24)) { err[0] = 1; done = true; }
+                        if (++spins > (1u << 24)) { a.err[0] = 1; done = true; }
                         if (i == 0) __nanosleep(40);
                         break;
                     }
@@ -391,17 +393,35 @@ __global__ void __launch_bounds__(SEG_THREADS, 2) seg_onesweep(const u64 *__rest
         sbase[d] = digit_start[d] + (u32)excl;
     }
     __syncthreads();
-    const u64 pseg = last ? (key_in[sg.start] & ~smask) : 0ull;        // every read of the segment has this (contig, position)
+    const u64 pseg = last ? (a.key_in[sg.start] & ~smask) : 0ull;      // every read of the segment has this (contig, position)
     const u64 imask = (1ull << ib) - 1;
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         const u32 i = threadIdx.x + j * SEG_THREADS;
-        if (i < tile_count) {
+        if (FULL || i < tile_count) {
             const u64 v = selem[i];
             const u32 d = (u32)(v >> sh) & mask;
             const u64 pos = (u64)sg.start + sbase[d] + (i - slocal[d]);
-            if (last) { key_out[pos] = pseg | (v >> ib); idx_out[pos] = (u32)(v & imask); }
-            else w_out[pos] = v;
+            if (last) { a.key_out[pos] = pseg | (v >> ib); a.idx_out[pos] = (u32)(v & imask); }
+            else a.w_out[pos] = v;
         }
     }
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(SEG_THREADS, 2) seg_onesweep(SegPassArgs a) {
+    constexpr u32 TILE = SEG_THREADS * ITEMS;
+    extern __shared__ __align__(16) unsigned char seg_dyn[];            // u64 selem[TILE]
+    u64 *selem = reinterpret_cast<u64 *>(seg_dyn);
+    __shared__ RsShared S;
+    __shared__ u32 s_seg;
+    if (threadIdx.x == 0) { const u32 t = atomicAdd(a.ticket, 1u); S.s_tile = t; s_seg = t < a.n_tiles ? seg_find_big(a.big, a.n_big, t) : 0u; }
+    __syncthreads();
+    const u32 tile = S.s_tile;
+    if (tile >= a.n_tiles) return;
+    const u32 seg_i = s_seg;
+    const SegBig sg = a.big[seg_i];
+    const u32 off = (tile - sg.tile0) * TILE, tile_count = min(TILE, sg.len - off);
+    if (tile_count == TILE) seg_onesweep_body<ITEMS, true>(a, S, selem, tile, seg_i, sg, off, tile_count);
+    else                    seg_onesweep_body<ITEMS, false>(a, S, selem, tile, seg_i, sg, off, tile_count);
 }

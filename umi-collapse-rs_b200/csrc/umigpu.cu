@@ -556,7 +556,8 @@ static int run_sort_presorted(umigpu_ctx *ctx, u64 n, const KeyLayout &lay, bool
         CK(ej);
     }
     if (n_big) {
-        const int npass = (sbits + RS_RB - 1) / RS_RB;
+        const SegPasses sp = seg_passes(sbits);
+        const int npass = sp.npass;
         if (npass > SEG_MAX_PASSES) return fail(ctx, UMIGPU_ERR_STATE, "internal: segmented sort with %d passes", npass);
         const size_t hist_bytes = (size_t)n_big * npass * RS_RADIX * 4;
         CK(ctx->d_seghist.reserve(hist_bytes));
@@ -565,7 +566,7 @@ static int run_sort_presorted(umigpu_ctx *ctx, u64 n, const KeyLayout &lay, bool
         CK(cudaMemsetAsync(ctx->d_seghist.p, 0, hist_bytes, ctx->stream));
         CK(cudaMemsetAsync(&sc->sort_err, 0, 4, ctx->stream));
         const SegBig *big = (const SegBig *)ctx->d_segbig.p;
-        LAUNCH(seg_hist_kernel, std::min<u32>(n_tiles, (u32)ctx->num_sms * 4), SEG_THREADS, key_in, sbits, npass, big, n_big, n_tiles, ctx->d_seghist.as<u32>());
+        LAUNCH(seg_hist_kernel, std::min<u32>(n_tiles, (u32)ctx->num_sms * 4), SEG_THREADS, key_in, sbits, sp, big, n_big, n_tiles, ctx->d_seghist.as<u32>());
         LAUNCH(seg_digit_starts_kernel, std::min<u32>(n_big * (u32)npass, (u32)ctx->num_sms * 8), RS_RADIX, ctx->d_seghist.as<u32>(), n_big * (u32)npass);
         int wcur = 0;
         for (int p = 0; p < npass; p++) {
@@ -573,8 +574,9 @@ static int run_sort_presorted(umigpu_ctx *ctx, u64 n, const KeyLayout &lay, bool
             CK(cudaMemsetAsync(&sc->sort_ticket, 0, 4, ctx->stream));
             const u64 *w_in = p == 0 ? nullptr : ctx->d_wbuf[wcur].as<u64>();
             u64 *w_out = p == npass - 1 ? nullptr : ctx->d_wbuf[p == 0 ? 0 : wcur ^ 1].as<u64>();
-            LAUNCH_SMEM((seg_onesweep<SEG_ITEMS>), n_tiles, SEG_THREADS, (size_t)SEG_TILE * 8, key_in, w_in, w_out, key_out, idx_out, sbits, ib, p, npass,
-                        big, n_big, n_tiles, (const u32 *)ctx->d_seghist.p, ctx->d_tilestate.as<unsigned long long>(), &sc->sort_ticket, &sc->sort_err);
+            SegPassArgs pa{key_in, w_in, w_out, key_out, idx_out, sbits, ib, p, sp, big, n_big, n_tiles, (const u32 *)ctx->d_seghist.p,
+                           ctx->d_tilestate.as<unsigned long long>(), &sc->sort_ticket, &sc->sort_err};
+            LAUNCH_SMEM((seg_onesweep<SEG_ITEMS>), n_tiles, SEG_THREADS, (size_t)SEG_TILE * 8, pa);
             if (p > 0) wcur ^= 1;
         }
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
@@ -654,14 +656,22 @@ static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, E
         if (!is_dense) {
             const int LP = blk_lp(L), XS = has_n ? 8 : 4;
             CK(ctx->d_eq.reserve((size_t)std::max<u32>(n_blocks, 1) * LP * XS * 16));
-            if (has_n) LAUNCH(onehot_build_kernel<true>, grid_for((u64)n_blocks * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
-                              (const u32 *)ctx->d_blkcnt.p, v.planes, v.nplane, L, LP, ctx->d_eq.as<u32>());
-            else       LAUNCH(onehot_build_kernel<false>, grid_for((u64)n_blocks * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
-                              (const u32 *)ctx->d_blkcnt.p, v.planes, v.nplane, L, LP, ctx->d_eq.as<u32>());
             CK(ctx->d_pairs.reserve(std::max<u64>(n_pairs, 1) * sizeof(uint2)));
             CK(cudaMemsetAsync(&sc->n_block_pairs, 0, 8, ctx->stream));
+            // a band of a split hot bucket only touches the column blocks near its own row tiles: build the one-hot words of
+            // those alone (the pair list is filled first and flags its column blocks)
+            u8 *need = nullptr;
+            if (ctx->n_bands > 1) {
+                CK(ctx->d_blocked.reserve(std::max<u32>(n_blocks, 1)));
+                need = ctx->d_blocked.as<u8>();
+                CK(cudaMemsetAsync(need, 0, n_blocks, ctx->stream));
+            }
             LAUNCH(expand_blocks_kernel, grid_for((u64)W * 32, 256), 256, items, W, (const u32 *)ctx->d_bsum.p, L, k, cull, mi, 1, ctx->d_pairs.as<uint2>(),
-                   (unsigned long long *)&sc->n_block_pairs);
+                   (unsigned long long *)&sc->n_block_pairs, need);
+            if (has_n) LAUNCH(onehot_build_kernel<true>, grid_for((u64)n_blocks * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
+                              (const u32 *)ctx->d_blkcnt.p, v.planes, v.nplane, L, LP, ctx->d_eq.as<u32>(), (const u8 *)need);
+            else       LAUNCH(onehot_build_kernel<false>, grid_for((u64)n_blocks * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
+                              (const u32 *)ctx->d_blkcnt.p, v.planes, v.nplane, L, LP, ctx->d_eq.as<u32>(), (const u8 *)need);
             rc = launch_neighbours_blocks(ctx->stream, ctx->num_sms, ctx->d_pairs.as<uint2>(), n_pairs, (const u32 *)ctx->d_blkfirst.p,
                                           (const u32 *)ctx->d_blkcnt.p, (const u32 *)ctx->d_bsum.p, v.planes, v.nplane, v.ucode, ctx->d_eq.as<uint4>(),
                                           L, k, has_n, cull, es, mi, v.uidmap, (unsigned long long *)&sc->pairs_eval);
