@@ -1606,7 +1606,7 @@ static int dedup_sharded_lpt(const umigpu_config *cfg, int32_t n_devices, const 
 #define XCHG_MAX_RANKS 16
 struct XchgSlot { unsigned long long count, epoch; };      // rank r -> owner: count (bit 63 = region overflow) first, epoch last
 struct XchgHeader {
-    unsigned long long info;        // hot_cnt | has_n << 32 | err << 33, written before `ready`
+    unsigned long long info;        // hot_cnt | has_n << 32 | err << 33 | narrow codes << 34, written before `ready`
     unsigned long long ready;       // epoch of the arrays in this window
     XchgSlot slot[XCHG_MAX_RANKS];
     unsigned long long ucap, ecap, n_ranks;    // what the window was created with (checked at attach)
@@ -1621,7 +1621,7 @@ struct Xchg {
     std::vector<char *> peer;       // window of every rank as this device addresses it (peer[rank] == local)
     std::vector<char> opened;       // peer[r] came from cudaIpcOpenMemHandle
     u64 ucap = 0, ecap = 0, region = 0, epoch = 0;
-    size_t off_planes = 0, off_ucode = 0, off_freq = 0, off_thr = 0, off_nplane = 0, off_inbox = 0, bytes = 0;
+    size_t off_code = 0, off_freq = 0, off_inbox = 0, bytes = 0;
     unsigned long long *h_pin = nullptr;      // pinned: [0] info [1] ready [2] count [3] epoch, [8..] poll buffer
     cudaStream_t xs = nullptr;                // polling stream
     double timeout_s = 120.0;
@@ -1656,11 +1656,8 @@ extern "C" int umigpu_xchg_create(umigpu_ctx *ctx, int32_t rank, int32_t n_ranks
     x->ecap = x->region * (u64)n_ranks;
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t o = sizeof(XchgHeader);
-    x->off_planes = o; o = al(o + x->ucap * 8);
-    x->off_ucode = o;  o = al(o + x->ucap * 8);
+    x->off_code = o;   o = al(o + x->ucap * 8);       // sort codes of the hot bucket's unique UMIs (u32 each when they fit)
     x->off_freq = o;   o = al(o + x->ucap * 4);
-    x->off_thr = o;    o = al(o + x->ucap * 4);
-    x->off_nplane = o; o = al(o + x->ucap * 4);
     x->off_inbox = o;  o = al(o + x->ecap * 8);
     x->bytes = o;
     if (const char *e = getenv("UMIGPU_XCHG_TIMEOUT_S")) x->timeout_s = atof(e);
@@ -1770,10 +1767,31 @@ __global__ void hot_locate_kernel(DevScalars *sc, const u32 *__restrict__ useg, 
     const u32 b = ubkt[lo];
     sc->hot_bucket = b; sc->hot_u0 = bstart[b]; sc->hot_cnt = bstart[b + 1] - bstart[b];
 }
-__global__ void __launch_bounds__(256) hot_child_init_kernel(u32 n_unique, u32 *__restrict__ bstart, u32 *__restrict__ ubkt) {
+// What crosses NVLink per unique UMI of the hot bucket is its sort code (4 bytes when 2 or 3 bits per base fit 32 bits) and
+// its frequency: every rank pulls the arrays from the owner at the same time, so the owner's egress is the bottleneck, and
+// bit planes, N plane and threshold are functions of those two.
+__global__ void __launch_bounds__(256) hot_export_kernel(u32 n, const u64 *__restrict__ ucode, const i32 *__restrict__ freq, int narrow,
+                                                         void *__restrict__ out_code, i32 *__restrict__ out_freq) {
     const u32 u = blockIdx.x * 256 + threadIdx.x;
-    if (u < n_unique) ubkt[u] = 0;
+    if (u >= n) return;
+    if (narrow) reinterpret_cast<u32 *>(out_code)[u] = (u32)ucode[u]; else reinterpret_cast<u64 *>(out_code)[u] = ucode[u];
+    out_freq[u] = freq[u];
+}
+__global__ void __launch_bounds__(256) hot_child_expand_kernel(u32 n_unique, const void *__restrict__ code_in, int narrow, const i32 *__restrict__ freq,
+                                                               float percentage, int inf_thr, int L, int has_n, uint2 *__restrict__ planes,
+                                                               u32 *__restrict__ nplane, u64 *__restrict__ ucode, i32 *__restrict__ thr,
+                                                               u32 *__restrict__ bstart, u32 *__restrict__ ubkt) {
+    const u32 u = blockIdx.x * 256 + threadIdx.x;
     if (u == 0) { bstart[0] = 0; bstart[1] = n_unique; }
+    if (u >= n_unique) return;
+    const u64 c = narrow ? (u64)reinterpret_cast<const u32 *>(code_in)[u] : reinterpret_cast<const u64 *>(code_in)[u];
+    u32 p0, p1, pn;
+    code_to_planes(c, L, has_n, p0, p1, pn);
+    planes[u] = make_uint2(p0, p1);
+    if (has_n) nplane[u] = pn;
+    ucode[u] = c;
+    thr[u] = inf_thr ? 0x7fffffff : dir_threshold(percentage, freq[u]);     // same expression as unique_finalize_kernel
+    ubkt[u] = 0;
 }
 __global__ void __launch_bounds__(256) hot_append_kernel(const uint2 *__restrict__ in, u64 n, u32 u0, uint2 *__restrict__ out) {
     const u64 e = (u64)blockIdx.x * 256 + threadIdx.x;
@@ -1822,16 +1840,14 @@ static int hot_publish(umigpu_ctx *ctx, const umigpu_hot *hot, u32 *u0_out) {
         if (hb == 0xffffffffu) why = "the hot bucket's read was not found after the sort";
         else if ((u64)uh > x->ucap) why = "the exchange window is too small for the hot bucket's unique UMIs";
     }
+    const int narrow = ctx->lay.umi_bits <= 32 ? 1 : 0;
     if (!why) {
         char *w = x->local;
-        CK(cudaMemcpyAsync(w + x->off_planes, ctx->d_planes.as<uint2>() + u0, (size_t)uh * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(w + x->off_ucode, ctx->d_ucode.as<u64>() + u0, (size_t)uh * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(w + x->off_freq, ctx->d_freq.as<i32>() + u0, (size_t)uh * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(w + x->off_thr, ctx->d_thr.as<i32>() + u0, (size_t)uh * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        if (has_n) CK(cudaMemcpyAsync(w + x->off_nplane, ctx->d_nplane.as<u32>() + u0, (size_t)uh * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        LAUNCH(hot_export_kernel, grid_for(uh, 256), 256, uh, (const u64 *)(ctx->d_ucode.as<u64>() + u0), (const i32 *)(ctx->d_freq.as<i32>() + u0), narrow,
+               (void *)(w + x->off_code), (i32 *)(w + x->off_freq));
     }
     // info first, ready last (stream order = the order the words land in the window)
-    x->h_pin[0] = why ? (1ull << 33) : ((unsigned long long)uh | ((unsigned long long)(has_n ? 1 : 0) << 32));
+    x->h_pin[0] = why ? (1ull << 33) : ((unsigned long long)uh | ((unsigned long long)(has_n ? 1 : 0) << 32) | ((unsigned long long)narrow << 34));
     x->h_pin[1] = x->epoch;
     CK(cudaMemcpyAsync(x->local + offsetof(XchgHeader, info), &x->h_pin[0], 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(x->local + offsetof(XchgHeader, ready), &x->h_pin[1], 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -1854,9 +1870,10 @@ static int hot_band(umigpu_ctx *ctx, const umigpu_hot *hot) {
     rc = xchg_poll(ctx, ow + offsetof(XchgHeader, info), 8, [](const unsigned long long *) { return true; }, "the owner's header");
     if (rc) return rc;
     const unsigned long long info = x->h_pin[8];
-    if (info >> 33) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "shard group: the owner (rank %d) could not publish the hot bucket", hot->owner);
+    if ((info >> 33) & 1ull) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "shard group: the owner (rank %d) could not publish the hot bucket", hot->owner);
     const u32 uh = (u32)info;
     const bool has_n = ((info >> 32) & 1ull) != 0;
+    const int narrow = (int)((info >> 34) & 1ull);
     STAGE_BEGIN(UMIGPU_STAGE_HOT_BAND);
     // child context: same configuration, this context's stream, its own buffers
     if (!ctx->hot) {
@@ -1883,14 +1900,16 @@ static int hot_band(umigpu_ctx *ctx, const umigpu_hot *hot) {
 #define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, UMIGPU_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
         CKH(ch->d_planes.reserve((size_t)uh * 8)); CKH(ch->d_ucode.reserve((size_t)uh * 8)); CKH(ch->d_freq.reserve((size_t)uh * 4));
         CKH(ch->d_thr.reserve((size_t)uh * 4)); CKH(ch->d_bstart.reserve(2 * 4)); CKH(ch->d_ubkt.reserve((size_t)uh * 4));
+        CKH(ch->d_umi2.reserve((size_t)uh * 8));                   // staging of the codes as they come over the link
         if (has_n) CKH(ch->d_nplane.reserve((size_t)uh * 4));
         cudaStream_t s = ctx->stream;
-        CKH(cudaMemcpyAsync(ch->d_planes.p, ow + x->off_planes, (size_t)uh * 8, cudaMemcpyDefault, s));
-        CKH(cudaMemcpyAsync(ch->d_ucode.p, ow + x->off_ucode, (size_t)uh * 8, cudaMemcpyDefault, s));
+        CKH(cudaMemcpyAsync(ch->d_umi2.p, ow + x->off_code, (size_t)uh * (narrow ? 4 : 8), cudaMemcpyDefault, s));
         CKH(cudaMemcpyAsync(ch->d_freq.p, ow + x->off_freq, (size_t)uh * 4, cudaMemcpyDefault, s));
-        CKH(cudaMemcpyAsync(ch->d_thr.p, ow + x->off_thr, (size_t)uh * 4, cudaMemcpyDefault, s));
-        if (has_n) CKH(cudaMemcpyAsync(ch->d_nplane.p, ow + x->off_nplane, (size_t)uh * 4, cudaMemcpyDefault, s));
-        hot_child_init_kernel<<<grid_for(uh, 256), 256, 0, s>>>(uh, ch->d_bstart.as<u32>(), ch->d_ubkt.as<u32>());
+        const umigpu_config &cf = ctx->cfg;
+        const int inf_thr = (cf.algo == UMIGPU_ALGO_CC || cf.algo == UMIGPU_ALGO_ADJ_UPSTREAM) ? 1 : 0;
+        hot_child_expand_kernel<<<grid_for(uh, 256), 256, 0, s>>>(uh, (const void *)ch->d_umi2.p, narrow, (const i32 *)ch->d_freq.p, cf.percentage, inf_thr,
+                                                                   (int)cf.umi_len, has_n ? 1 : 0, ch->d_planes.as<uint2>(), ch->d_nplane.as<u32>(),
+                                                                   ch->d_ucode.as<u64>(), ch->d_thr.as<i32>(), ch->d_bstart.as<u32>(), ch->d_ubkt.as<u32>());
         bucket_stats_kernel<<<1, 256, 0, s>>>(1, (const u32 *)ch->d_bstart.p, ch->d_sc.as<DevScalars>());
         ctx->launches += 2;
         CKH(cudaGetLastError());
