@@ -116,3 +116,22 @@ def test_full_size_c2_segmented_equals_generic(monkeypatch):
     for key in ("n_buckets", "total_umis", "max_umis", "n_kept", "n_edges"):
         assert outs[0][1][key] == outs[1][1][key]
     print("sort ms: segmented %.2f generic %.2f" % (outs[0][2], outs[1][2]))
+
+
+def test_bulk_copy_staging_variant_of_the_block_pair_kernel(monkeypatch):
+    """hamming_blocks<..., BULK>: the next pair's column words arrive by cp.async.bulk + mbarrier (double buffered).  Same
+    edges, same survivors as the plain-load variant and the oracle, for every k and a few lengths."""
+    for L, k, name, scale in ((12, 1, "C2", 0.004), (16, 2, "C3", 0.002), (8, 3, "C2", 0.001), (12, 1, "C4", 0.003), (30, 1, "C2", 0.001)):
+        d, cfg = small(name, scale, seed=L, umi_len=L)
+        outs = []
+        for env in ("0", "1"):
+            monkeypatch.setenv("UMIGPU_K5_BULK", env)
+            with umigpu.Context(L, k, 0.5, umigpu.ALGO_DIR, umigpu.MERGE_AVGQUAL, 0) as ctx:
+                ctx.push_reads(d["tid"], d["pos"], d["rev"], d["umi"], d["score"])
+                kept, _, ctr = ctx.finish()
+            outs.append((kept, ctr))
+        monkeypatch.delenv("UMIGPU_K5_BULK")
+        assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1]["n_edges"] == outs[1][1]["n_edges"]
+        assert outs[1][1]["n_block_pairs"] > 0, "the block-pair kernel must have run"
+        okept, _, _ = O.dedup(d["tid"], d["pos"], d["rev"], d["umi"], d["score"], O.ALGO_DIR, O.MERGE_AVGQUAL, k, 0.5)
+        assert outs[1][0].astype(np.int64).tolist() == okept.tolist()

@@ -148,8 +148,30 @@ __device__ __forceinline__ void wb_emit(WarpEdgeBuf &wb, const EdgeSink &es, boo
     wb.fill += total;
 }
 
+// ---- bulk asynchronous copy (TMA engine, non-tensor form) + mbarrier: the BULK variant of the evaluation kernel prefetches
+// the NEXT block pair's column words (768 B at 12 nt, contiguous, 16-byte aligned) while the current pair is evaluated ----
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, u32 phase) {
+    asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}"
+                 ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+
 // ---- evaluation: one warp per block pair ----
-template <int LP, int K, bool HASN>
+// BULK = false: the warp copies the column block's words with two 16-byte loads per lane, then evaluates (the load latency is
+// exposed once per pair unless another warp covers it).  BULK = true: two buffers per warp; the copy of pair i+1 is issued as
+// ONE cp.async.bulk by lane 0 before pair i is evaluated and completes on an mbarrier.  A/B in profiles/ ("TMA").
+template <int LP, int K, bool HASN, bool BULK>
 __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ pairs, u64 n_pairs, const u32 *__restrict__ blk_first,
                                                       const u32 *__restrict__ blk_cnt, const u32 *__restrict__ bsum,
                                                       const uint2 *__restrict__ planes, const u32 *__restrict__ nplane,
@@ -161,13 +183,23 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
     const u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
     const u64 nwarps = (u64)gridDim.x * (256 / 32);
     __shared__ uint2 s_edges[(256 / 32) * WB_CAP];
-    // the column block's match words, staged once per block pair by its warp (768 B at 12 nt): the four row slices then
-    // read them with LDS.128 (four distinct 16-byte rows per warp: conflict-free) instead of going through L1
-    __shared__ __align__(16) uint4 s_eq[256 / 32][LP * XS];
-    uint4 *sw = s_eq[threadIdx.x >> 5];
-    WarpEdgeBuf wb{s_edges + (threadIdx.x >> 5) * WB_CAP, 0u};
+    constexpr int NBUF = BULK ? 2 : 1;
+    constexpr u32 COL_BYTES = (u32)(LP * XS * 16);
+    __shared__ __align__(128) uint4 s_eq[256 / 32][NBUF][LP * XS];
+    __shared__ __align__(8) unsigned long long s_bar[256 / 32][2];
+    const u32 wid = threadIdx.x >> 5;
+    WarpEdgeBuf wb{s_edges + wid * WB_CAP, 0u};
     u64 evaluated = 0;
-    for (u64 w = ((u64)blockIdx.x * 256 + threadIdx.x) >> 5; w < n_pairs; w += nwarps) {
+    u64 w = ((u64)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (BULK) {
+        if (lane == 0) { mbar_init(&s_bar[wid][0], 1); mbar_init(&s_bar[wid][1], 1); mbar_fence_init(); }
+        __syncwarp();
+        if (lane == 0 && w < n_pairs) {
+            mbar_expect_tx(&s_bar[wid][0], COL_BYTES);
+            bulk_g2s(s_eq[wid][0], eq + (u64)pairs[w].y * (LP * XS), COL_BYTES, &s_bar[wid][0]);
+        }
+    }
+    for (u32 it = 0; w < n_pairs; w += nwarps, it++) {
         uint2 pr = pairs[w];
         const bool filt = pr.x >> 31;                 // multi-index pass: report a pair only in the pass of its first equal part
         pr.x &= 0x7fffffffu;
@@ -178,11 +210,27 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
 #pragma unroll
             for (int x = 0; x < NLET; x++) cs[x] = bsum[(u64)pr.y * 8 + x];
         }
-        const uint4 *base = eq + (u64)pr.y * (LP * XS);
-        __syncwarp();                                  // the previous pair's slices are done with sw
+        const uint4 *sw;
+        if (BULK) {
+            const u32 cur = it & 1u;
+            // the other buffer's readers finished at the end of the previous iteration (__syncwarp below): refill it now
+            const u64 wn = w + nwarps;
+            __syncwarp();
+            if (lane == 0 && wn < n_pairs) {
+                mbar_expect_tx(&s_bar[wid][cur ^ 1u], COL_BYTES);
+                bulk_g2s(s_eq[wid][cur ^ 1u], eq + (u64)pairs[wn].y * (LP * XS), COL_BYTES, &s_bar[wid][cur ^ 1u]);
+            }
+            mbar_wait(&s_bar[wid][cur], (it >> 1) & 1u);
+            sw = s_eq[wid][cur];
+        } else {
+            uint4 *swr = s_eq[wid][0];
+            const uint4 *base = eq + (u64)pr.y * (LP * XS);
+            __syncwarp();                                  // the previous pair's slices are done with the buffer
 #pragma unroll
-        for (int i = 0; i < (LP * XS + 31) / 32; i++) { const u32 t = i * 32 + lane; if (t < (u32)(LP * XS)) sw[t] = __ldg(base + t); }
-        __syncwarp();
+            for (int i = 0; i < (LP * XS + 31) / 32; i++) { const u32 t = i * 32 + lane; if (t < (u32)(LP * XS)) swr[t] = __ldg(base + t); }
+            __syncwarp();
+            sw = swr;
+        }
         for (u32 s = 0; s * 32 < rcnt; s++) {
             const u32 r = s * 32 + lane;
             const bool valid = r < rcnt;
@@ -248,11 +296,19 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
     if (lane == 0 && evaluated) atomicAdd(pairs_eval, (unsigned long long)evaluated);
 }
 
+// UMIGPU_K5_BULK=0/1 selects the staging variant at run time (A/B); the default is the measured winner ("TMA").
+static inline bool blk_use_bulk() {
+    const char *e = getenv("UMIGPU_K5_BULK");
+    return e ? atoi(e) != 0 : false;
+}
 template <int LP, int K, bool HASN>
 static int blk_launch_one(cudaStream_t stream, int num_sms, const uint2 *pairs, u64 n_pairs, const u32 *blk_first, const u32 *blk_cnt,
                           const u32 *bsum, const uint2 *planes, const u32 *nplane, const u64 *ucode, const uint4 *eq, int L, int cull, EdgeSink es,
                           MiParams mi, const u32 *uidmap, unsigned long long *pairs_eval) {
-    auto kern = hamming_blocks<LP, K, HASN>;
+    // the bulk variant keeps two column buffers per warp: instantiated where they stay small (no N plane)
+    constexpr bool CAN_BULK = !HASN;
+    const bool bulk = CAN_BULK && blk_use_bulk();
+    auto kern = (bulk && CAN_BULK) ? hamming_blocks<LP, K, HASN, CAN_BULK> : hamming_blocks<LP, K, HASN, false>;
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0) != cudaSuccess || occ < 1) occ = 1;
     u32 grid = (u32)std::min<u64>((n_pairs + 7) / 8, (u64)num_sms * occ * 4);
