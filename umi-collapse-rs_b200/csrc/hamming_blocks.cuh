@@ -17,6 +17,9 @@
 #include "hamming.cuh"
 
 #define BLK_COLS 128
+#ifndef ROWS_MIN_BLOCKS
+#define ROWS_MIN_BLOCKS 2      // A/B builds: -DROWS_MIN_BLOCKS=3 / 4 cap hamming_rows at 85 / 64 registers
+#endif
 
 // ---- one-hot words of every 128-block (built once per run) ----
 template <bool HASN>
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
 // 32-row slices stay in registers — and streams the row block's column blocks through shared memory; the next column block's
 // words and metadata are fetched into registers while the current one is evaluated, so no load latency sits between pairs.
 template <int LP, int K, bool HASN>
-__global__ void __launch_bounds__(256, 2) hamming_rows(const u32 *__restrict__ rowptr, const u32 *__restrict__ cols, u32 n_blocks,
+__global__ void __launch_bounds__(256, ROWS_MIN_BLOCKS) hamming_rows(const u32 *__restrict__ rowptr, const u32 *__restrict__ cols, u32 n_blocks,
                                                        const u32 *__restrict__ blk_first, const u32 *__restrict__ blk_cnt, const u32 *__restrict__ bsum,
                                                        const uint2 *__restrict__ planes, const u32 *__restrict__ nplane, const u64 *__restrict__ ucode,
                                                        const uint4 *__restrict__ eq, int L, int cull, EdgeSink es, MiParams mi,
@@ -453,10 +456,12 @@ __global__ void __launch_bounds__(256, 2) hamming_rows(const u32 *__restrict__ r
     if (lane == 0 && evaluated) atomicAdd(pairs_eval, (unsigned long long)evaluated);
 }
 
-// UMIGPU_K5_ROWS=0/1: block-pair list (round 1) or row-grouped form.  Default = the measured winner.
+// UMIGPU_K5_ROWS=0/1: block-pair list or row-grouped form.  Default = the measured winner: the block-pair list (the row-grouped
+// form executes fewer instructions but needs 114 registers: 16 warps per SM instead of 32 cannot hide the LDS -> LOP3 chains;
+// measured 3.5 vs 2.1 ms on C2, 19.9 vs 9.1 ms on C5, profiles/r2k_ab_*.jsonl).
 static inline bool blk_use_rows() {
     const char *e = getenv("UMIGPU_K5_ROWS");
-    return e ? atoi(e) != 0 : true;
+    return e ? atoi(e) != 0 : false;
 }
 template <int LP, int K, bool HASN>
 static int rows_launch_one(cudaStream_t stream, int num_sms, const u32 *rowptr, const u32 *cols, u32 n_blocks, const u32 *blk_first, const u32 *blk_cnt,
