@@ -17,9 +17,6 @@
 #include "hamming.cuh"
 
 #define BLK_COLS 128
-#ifndef ROWS_MIN_BLOCKS
-#define ROWS_MIN_BLOCKS 2      // A/B builds: -DROWS_MIN_BLOCKS=3 / 4 cap hamming_rows at 85 / 64 registers
-#endif
 
 // ---- one-hot words of every 128-block (built once per run) ----
 template <bool HASN>
@@ -64,12 +61,9 @@ __global__ void __launch_bounds__(256) onehot_build_kernel(u32 n_groups /* 4 per
 
 // ---- surviving tile pairs -> surviving (128 x 128) block pairs ----
 // fill == 0: only counts (out_count += survivors); fill == 1: appends uint2(row block, col block)
-// rows != nullptr selects the row-grouped form (hamming_rows): fill == 0 adds every row block's survivors to rows[row block];
-// fill == 1 takes rows[] as per-row-block fill cursors and writes cols[] = column block | multi-index flag << 31.
 __global__ void __launch_bounds__(256) expand_blocks_kernel(const TileItem *__restrict__ items, u32 n_items, const u32 *__restrict__ bsum,
                                                             int L, int k, int cull, MiParams mi, int fill, uint2 *__restrict__ pairs,
-                                                            unsigned long long *out_count, u8 *__restrict__ need = nullptr,
-                                                            u32 *__restrict__ rows = nullptr, u32 *__restrict__ cols = nullptr) {
+                                                            unsigned long long *out_count, u8 *__restrict__ need = nullptr) {
     const u32 w = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = lane_id();
     if (w >= n_items) return;
     const TileItem it = items[w];
@@ -100,20 +94,6 @@ __global__ void __launch_bounds__(256) expand_blocks_kernel(const TileItem *__re
         if (ok) live |= 1u << i;
     }
     u32 cnt = __popc(live);
-    if (rows) {
-        if (cnt) {
-            if (!fill) atomicAdd(&rows[row_blk0 + r], cnt);
-            else {
-                u32 o = atomicAdd(&rows[row_blk0 + r], cnt);
-#pragma unroll
-                for (int i = 0; i < 8; i++) if (live & (1u << i)) {
-                    cols[o++] = (it.col_blk0 + c0 + i) | (filt ? 0x80000000u : 0u);
-                    if (need) need[it.col_blk0 + c0 + i] = 1;
-                }
-            }
-        }
-        if (fill) return;
-    }
     // warp exclusive prefix of cnt
     u32 inc = cnt;
 #pragma unroll
@@ -132,12 +112,6 @@ __global__ void __launch_bounds__(256) expand_blocks_kernel(const TileItem *__re
         }
     }
 }
-struct RowCount { const u32 *cnt; __device__ u32 operator()(u64 b) const { return cnt[b]; } };
-struct RowPtrEmit {
-    u32 *rowptr, *fill; u64 n_rows;
-    __device__ void operator()(u64 b, u32 v, u32 ex) const { rowptr[b] = ex; fill[b] = ex; if (b == n_rows - 1) rowptr[b + 1] = ex + v; }
-};
-
 // ---- warp-buffered edge output ----
 // Every hit used to cost one atomicAdd on the single global edge counter; in a saturated UMI space (the fastq
 // single-bucket config: ~170 M edges) that one address serialises the whole kernel.  Each warp now stages its
@@ -292,26 +266,48 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
                 }
                 h = K == 1 ? m2 : (K == 2 ? m3 : m4);
             }
-            // ---- hits (rare): warp-uniform loop, one candidate per lane per round ----
+            // ---- hits (rare) ----
+            // round 1 spent 34 % of this kernel's instructions here (ncu source view, profiles/r2m_*): every row of a diagonal
+            // block "hits" itself and its lower triangle, each of the four 32-column groups ran its own warp-uniform loop, and
+            // every round paid two five-step shuffle scans.  Now: on the diagonal the self / lower-triangle bits are masked out
+            // before anything loops, one loop serves all four groups (rounds = the busiest lane's hit count), and an edge's
+            // slot in the warp buffer comes from two ballots.
+            if (same) {
+                // keep columns c > r: group i keeps bits above (r - 32 i)
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int d = (int)r - 32 * i;                    // r = row index within the block (= column index of itself)
+                    const u32 keep = d < 0 ? 0xffffffffu : (d >= 31 ? 0u : (0xffffffffu << (d + 1)));
+                    if (i == 0) h.x &= keep; else if (i == 1) h.y &= keep; else if (i == 2) h.z &= keep; else h.w &= keep;
+                }
+            }
             if (__any_sync(0xffffffffu, (h.x | h.y | h.z | h.w) != 0u)) {
                 const u32 a = rfirst + r;                               // index in this pass's order
                 const u32 ao = (valid && uidmap) ? uidmap[a] : a;       // unique id (edges, freq, thr use the main order)
                 i32 fa = 0, ta = 0;
                 if (valid && (h.x | h.y | h.z | h.w)) { fa = es.freq[ao]; ta = es.thr[ao]; }
-                u32 hv[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    while (__any_sync(0xffffffffu, hv[i] != 0u)) {
-                        bool ok = hv[i] != 0u;
-                        u32 b = ok ? (u32)__ffs(hv[i]) - 1 : 0u;
-                        hv[i] &= hv[i] - 1;
-                        const u32 c = i * 32 + b, bb = cfirst + c;
-                        ok = ok && c < ccnt && (!same || a < bb);
-                        if (ok && filt) ok = mi_accept(mi, rc, ucode[bb]);
-                        bool ab = false, ba = false;
-                        u32 bo = bb;
-                        if (ok) { if (uidmap) bo = uidmap[bb]; ab = es.freq[bo] <= ta; ba = fa <= es.thr[bo]; }
-                        wb_emit(wb, es, ab, ba, ao, bo);
+                while (__any_sync(0xffffffffu, (h.x | h.y | h.z | h.w) != 0u)) {
+                    bool ok = (h.x | h.y | h.z | h.w) != 0u;
+                    // next hit of this lane: lowest bit of the first non-empty group
+                    const u32 g = h.x ? 0u : (h.y ? 1u : (h.z ? 2u : 3u));
+                    const u32 word = h.x ? h.x : (h.y ? h.y : (h.z ? h.z : h.w));
+                    const u32 bit = ok ? (u32)__ffs(word) - 1u : 0u;
+                    const u32 cleared = word & (word - 1u);
+                    if (g == 0u) h.x = cleared; else if (g == 1u) h.y = cleared; else if (g == 2u) h.z = cleared; else h.w = cleared;
+                    const u32 c = g * 32u + bit, bb = cfirst + c;
+                    ok = ok && c < ccnt;
+                    if (ok && filt) ok = mi_accept(mi, rc, ucode[bb]);
+                    bool ab = false, ba = false;
+                    u32 bo = bb;
+                    if (ok) { if (uidmap) bo = uidmap[bb]; ab = es.freq[bo] <= ta; ba = fa <= es.thr[bo]; }
+                    const u32 mab = __ballot_sync(0xffffffffu, ab), mba = __ballot_sync(0xffffffffu, ba);
+                    const u32 total = (u32)__popc(mab) + (u32)__popc(mba);
+                    if (total) {
+                        if (wb.fill + total > WB_CAP) wb_flush(wb, es);
+                        const u32 lt = lanemask_lt();
+                        if (ab) wb.buf[wb.fill + __popc(mab & lt)] = make_uint2(ao, bo);
+                        if (ba) wb.buf[wb.fill + __popc(mab) + __popc(mba & lt)] = make_uint2(bo, ao);
+                        wb.fill += total;
                     }
                 }
             }
@@ -321,192 +317,10 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
     if (lane == 0 && evaluated) atomicAdd(pairs_eval, (unsigned long long)evaluated);
 }
 
-// ---- evaluation, row-grouped form: one warp per ROW block ----
-// The block-pair form sets up its 128 rows again for every pair (three global loads per lane and slice, the per-slice letter
-// sets by four warp reductions): after culling a row block meets ~10-20 column blocks, so most executed instructions were
-// set-up, not distance arithmetic.  Here the warp loads its row block once — planes, codes and the letter sets of its four
-// 32-row slices stay in registers — and streams the row block's column blocks through shared memory; the next column block's
-// words and metadata are fetched into registers while the current one is evaluated, so no load latency sits between pairs.
-template <int LP, int K, bool HASN>
-__global__ void __launch_bounds__(256, ROWS_MIN_BLOCKS) hamming_rows(const u32 *__restrict__ rowptr, const u32 *__restrict__ cols, u32 n_blocks,
-                                                       const u32 *__restrict__ blk_first, const u32 *__restrict__ blk_cnt, const u32 *__restrict__ bsum,
-                                                       const uint2 *__restrict__ planes, const u32 *__restrict__ nplane, const u64 *__restrict__ ucode,
-                                                       const uint4 *__restrict__ eq, int L, int cull, EdgeSink es, MiParams mi,
-                                                       const u32 *__restrict__ uidmap, unsigned long long *pairs_eval) {
-    constexpr int XS = HASN ? 8 : 4;
-    constexpr int NLET = HASN ? 5 : 4;
-    constexpr int NLD = (LP * XS + 31) / 32;              // 16-byte words of a column block per lane
-    constexpr int BPB = HASN ? 3 : 2;
-    const u32 lane = lane_id();
-    const u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
-    const u32 nwarps = gridDim.x * (256 / 32);
-    __shared__ uint2 s_edges[(256 / 32) * WB_CAP];
-    __shared__ __align__(16) uint4 s_eq[256 / 32][LP * XS];
-    uint4 *sw = s_eq[threadIdx.x >> 5];
-    WarpEdgeBuf wb{s_edges + (threadIdx.x >> 5) * WB_CAP, 0u};
-    u64 evaluated = 0;
-    for (u32 rb = (blockIdx.x * 256 + threadIdx.x) >> 5; rb < n_blocks; rb += nwarps) {
-        const u32 p0 = rowptr[rb], p1 = rowptr[rb + 1];
-        if (p0 == p1) continue;
-        const u32 rfirst = blk_first[rb], rcnt = blk_cnt[rb];
-        uint2 rp[4]; u32 rn[4]; u64 rc[4]; u32 rset[4][NLET];
-#pragma unroll
-        for (int s = 0; s < 4; s++) {
-            const u32 r = s * 32 + lane;
-            const bool valid = r < rcnt;
-            rp[s] = valid ? planes[rfirst + r] : make_uint2(0u, 0u);
-            rn[s] = (HASN && valid) ? nplane[rfirst + r] : 0u;
-            rc[s] = valid ? ucode[rfirst + r] : 0ull;
-        }
-#pragma unroll
-        for (int s = 0; s < 4; s++) {
-            u32 oh[5];
-            onehot_planes(rp[s], rn[s], (u32)(s * 32) + lane < rcnt ? lmask : 0u, oh);
-#pragma unroll
-            for (int x = 0; x < NLET; x++) rset[s][x] = __reduce_or_sync(0xffffffffu, oh[x]);
-        }
-        // software pipeline: words and metadata of the column block after the current one are already in registers
-        uint4 nx[NLD];
-        u32 cw = cols[p0];
-        u32 nmeta = 0;
-        {
-            const u32 cb = cw & 0x7fffffffu;
-            const uint4 *base = eq + (u64)cb * (LP * XS);
-#pragma unroll
-            for (int i = 0; i < NLD; i++) { const u32 t = i * 32 + lane; nx[i] = t < (u32)(LP * XS) ? __ldg(base + t) : make_uint4(0u, 0u, 0u, 0u); }
-            nmeta = lane < 5 ? bsum[(u64)cb * 8 + lane] : (lane == 5 ? blk_first[cb] : (lane == 6 ? blk_cnt[cb] : 0u));
-        }
-        for (u32 p = p0; p < p1; p++) {
-            const bool filt = cw >> 31;
-            const u32 cb = cw & 0x7fffffffu;
-            const u32 meta = nmeta;
-            __syncwarp();                                  // the previous column block's slices are done with sw
-#pragma unroll
-            for (int i = 0; i < NLD; i++) { const u32 t = i * 32 + lane; if (t < (u32)(LP * XS)) sw[t] = nx[i]; }
-            __syncwarp();
-            if (p + 1 < p1) {
-                cw = cols[p + 1];
-                const u32 nb = cw & 0x7fffffffu;
-                const uint4 *base = eq + (u64)nb * (LP * XS);
-#pragma unroll
-                for (int i = 0; i < NLD; i++) { const u32 t = i * 32 + lane; if (t < (u32)(LP * XS)) nx[i] = __ldg(base + t); }
-                nmeta = lane < 5 ? bsum[(u64)nb * 8 + lane] : (lane == 5 ? blk_first[nb] : (lane == 6 ? blk_cnt[nb] : 0u));
-            }
-            u32 cs[NLET];
-#pragma unroll
-            for (int x = 0; x < NLET; x++) cs[x] = __shfl_sync(0xffffffffu, meta, x);
-            const u32 cfirst = __shfl_sync(0xffffffffu, meta, 5), ccnt = __shfl_sync(0xffffffffu, meta, 6);
-            const bool same = cb == rb;
-#pragma unroll
-            for (int s = 0; s < 4; s++) {
-                if ((u32)(s * 32) >= rcnt) break;
-                if (cull && !same) {
-                    u32 t = 0;
-#pragma unroll
-                    for (int x = 0; x < NLET; x++) t |= rset[s][x] & cs[x];
-                    if (__popc(~t & lmask) > K) continue;          // > K positions with disjoint letter sets
-                }
-                const u32 r = s * 32 + lane;
-                const bool valid = r < rcnt;
-                evaluated += (u64)min(32u, rcnt - (u32)(s * 32)) * ccnt;
-                uint4 h = make_uint4(0u, 0u, 0u, 0u);
-                if (valid) {
-                    const u64 code = rc[s];
-                    uint4 m1 = make_uint4(~0u, ~0u, ~0u, ~0u), m2 = m1, m3 = m1, m4 = m1;
-#pragma unroll
-                    for (int j = 0; j < LP; j++) {
-                        const uint4 wv = sw[(u32)(j * XS) + ((u32)(code >> (BPB * j)) & (HASN ? 7u : 3u))];
-                        if (K >= 3) { m4.x = (wv.x & m4.x) | (~wv.x & m3.x); m4.y = (wv.y & m4.y) | (~wv.y & m3.y);
-                                      m4.z = (wv.z & m4.z) | (~wv.z & m3.z); m4.w = (wv.w & m4.w) | (~wv.w & m3.w); }
-                        if (K >= 2) { m3.x = (wv.x & m3.x) | (~wv.x & m2.x); m3.y = (wv.y & m3.y) | (~wv.y & m2.y);
-                                      m3.z = (wv.z & m3.z) | (~wv.z & m2.z); m3.w = (wv.w & m3.w) | (~wv.w & m2.w); }
-                        m2.x = (wv.x & m2.x) | (~wv.x & m1.x); m2.y = (wv.y & m2.y) | (~wv.y & m1.y);
-                        m2.z = (wv.z & m2.z) | (~wv.z & m1.z); m2.w = (wv.w & m2.w) | (~wv.w & m1.w);
-                        m1.x &= wv.x; m1.y &= wv.y; m1.z &= wv.z; m1.w &= wv.w;
-                    }
-                    h = K == 1 ? m2 : (K == 2 ? m3 : m4);
-                }
-                // ---- hits (rare): warp-uniform loop, one candidate per lane per round ----
-                if (__any_sync(0xffffffffu, (h.x | h.y | h.z | h.w) != 0u)) {
-                    const u32 a = rfirst + r;                               // index in this pass's order
-                    const u32 ao = (valid && uidmap) ? uidmap[a] : a;       // unique id (edges, freq, thr use the main order)
-                    i32 fa = 0, ta = 0;
-                    if (valid && (h.x | h.y | h.z | h.w)) { fa = es.freq[ao]; ta = es.thr[ao]; }
-                    u32 hv[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        while (__any_sync(0xffffffffu, hv[i] != 0u)) {
-                            bool ok = hv[i] != 0u;
-                            u32 b = ok ? (u32)__ffs(hv[i]) - 1 : 0u;
-                            hv[i] &= hv[i] - 1;
-                            const u32 c = i * 32 + b, bb = cfirst + c;
-                            ok = ok && c < ccnt && (!same || a < bb);
-                            if (ok && filt) ok = mi_accept(mi, rc[s], ucode[bb]);
-                            bool ab = false, ba = false;
-                            u32 bo = bb;
-                            if (ok) { if (uidmap) bo = uidmap[bb]; ab = es.freq[bo] <= ta; ba = fa <= es.thr[bo]; }
-                            wb_emit(wb, es, ab, ba, ao, bo);
-                        }
-                    }
-                }
-            }
-        }
-    }
-    wb_flush(wb, es);
-    if (lane == 0 && evaluated) atomicAdd(pairs_eval, (unsigned long long)evaluated);
-}
-
-// UMIGPU_K5_ROWS=0/1: block-pair list or row-grouped form.  Default = the measured winner: the block-pair list (the row-grouped
-// form executes fewer instructions but needs 114 registers: 16 warps per SM instead of 32 cannot hide the LDS -> LOP3 chains;
-// measured 3.5 vs 2.1 ms on C2, 19.9 vs 9.1 ms on C5, profiles/r2k_ab_*.jsonl).
-static inline bool blk_use_rows() {
-    const char *e = getenv("UMIGPU_K5_ROWS");
-    return e ? atoi(e) != 0 : false;
-}
-template <int LP, int K, bool HASN>
-static int rows_launch_one(cudaStream_t stream, int num_sms, const u32 *rowptr, const u32 *cols, u32 n_blocks, const u32 *blk_first, const u32 *blk_cnt,
-                           const u32 *bsum, const uint2 *planes, const u32 *nplane, const u64 *ucode, const uint4 *eq, int L, int cull, EdgeSink es,
-                           MiParams mi, const u32 *uidmap, unsigned long long *pairs_eval) {
-    auto kern = hamming_rows<LP, K, HASN>;
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0) != cudaSuccess || occ < 1) occ = 1;
-    u32 grid = (u32)std::min<u64>(((u64)n_blocks + 7) / 8, (u64)num_sms * occ * 8);
-    if (grid == 0) return 0;
-    kern<<<grid, 256, 0, stream>>>(rowptr, cols, n_blocks, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, mi, uidmap, pairs_eval);
-    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
-}
-template <int K, bool HASN>
-static int rows_launch_k(cudaStream_t stream, int num_sms, const u32 *rowptr, const u32 *cols, u32 n_blocks, const u32 *blk_first, const u32 *blk_cnt,
-                         const u32 *bsum, const uint2 *planes, const u32 *nplane, const u64 *ucode, const uint4 *eq, int L, int cull, EdgeSink es,
-                         MiParams mi, const u32 *uidmap, unsigned long long *pairs_eval) {
-#define ROWS_ARGS stream, num_sms, rowptr, cols, n_blocks, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, mi, uidmap, pairs_eval
-    const int lp = L <= 8 ? 8 : L <= 12 ? 12 : L <= 16 ? 16 : L <= 24 ? 24 : 32;
-    switch (lp) {
-    case 8:  return rows_launch_one<8, K, HASN>(ROWS_ARGS);
-    case 12: return rows_launch_one<12, K, HASN>(ROWS_ARGS);
-    case 16: return rows_launch_one<16, K, HASN>(ROWS_ARGS);
-    case 24: return rows_launch_one<24, K, HASN>(ROWS_ARGS);
-    default: if (HASN) return 1; return rows_launch_one<32, K, false>(ROWS_ARGS);
-    }
-#undef ROWS_ARGS
-}
-// returns 0 = launched, 1 = configuration not covered, -1 = CUDA error
-static int launch_neighbours_rows(cudaStream_t stream, int num_sms, const u32 *rowptr, const u32 *cols, u32 n_blocks, const u32 *blk_first,
-                                  const u32 *blk_cnt, const u32 *bsum, const uint2 *planes, const u32 *nplane, const u64 *ucode,
-                                  const uint4 *eq, int L, int k, bool has_n, int cull, EdgeSink es, MiParams mi, const u32 *uidmap,
-                                  unsigned long long *pairs_eval) {
-#define ROWS_ARGS stream, num_sms, rowptr, cols, n_blocks, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, mi, uidmap, pairs_eval
-    if (k < 1 || k > 3) return 1;
-    if (!has_n) {
-        if (k == 1) return rows_launch_k<1, false>(ROWS_ARGS);
-        if (k == 2) return rows_launch_k<2, false>(ROWS_ARGS);
-        return rows_launch_k<3, false>(ROWS_ARGS);
-    }
-    if (k == 1) return rows_launch_k<1, true>(ROWS_ARGS);
-    if (k == 2) return rows_launch_k<2, true>(ROWS_ARGS);
-    return rows_launch_k<3, true>(ROWS_ARGS);
-#undef ROWS_ARGS
-}
+// (A row-grouped form — one warp per row block streaming its list of column blocks, rows set up once — was built and measured in
+// round 2: same instruction count as this kernel (set-up was not where the instructions went: 34 % were hit handling), 114
+// registers, 2-3x slower.  Numbers in profiles/r2k_ab_rows_vs_pairs_*.jsonl and r2m_ncu_full_hamming_rows_C2.txt; the code is in
+// the history at the commit "Row-grouped neighbour evaluation (hamming_rows)".)
 
 // UMIGPU_K5_BULK=0/1 selects the staging variant at run time (A/B); the default is the measured winner ("TMA").
 static inline bool blk_use_bulk() {

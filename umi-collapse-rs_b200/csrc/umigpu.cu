@@ -79,7 +79,6 @@ struct umigpu_ctx {
     bool st_weighted = false, st_need_edges = false;
     int sorted_cur = 0;                   // which ping-pong buffer holds the sorted keys / indices
     DevBuf d_stamp, d_rowptr, d_front[2]; // frontier clustering
-    DevBuf d_blkrowcnt, d_blkrowptr, d_blkcols;   // row-grouped block pairs (hamming_rows)
     DevBuf d_segblk, d_segnext, d_segflag, d_segbig, d_seghist, d_wbuf[2];   // segmented sort (coordinate-sorted input)
     bool used_seg_sort = false;
     // sharded run (several devices, one dataset): see "shard group" below
@@ -193,7 +192,6 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
     if (ctx->h_umirep) cudaFreeHost(ctx->h_umirep);
     ctx->d_chunks.release(); ctx->d_umirep.release();
     ctx->d_stamp.release(); ctx->d_rowptr.release(); ctx->d_front[0].release(); ctx->d_front[1].release();
-    ctx->d_blkrowcnt.release(); ctx->d_blkrowptr.release(); ctx->d_blkcols.release();
     ctx->d_segblk.release(); ctx->d_segnext.release(); ctx->d_segflag.release(); ctx->d_segbig.release(); ctx->d_seghist.release();
     ctx->d_wbuf[0].release(); ctx->d_wbuf[1].release();
     if (ctx->hot) { umigpu_destroy(ctx->hot); ctx->hot = nullptr; }
@@ -643,17 +641,10 @@ static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, E
     const TileItem *items = ctx->d_items.as<TileItem>();
 
     if (allow_blocks) {
-        // ---- sparse form: global one-hot words, surviving block pairs grouped by row block, one warp per row block ----
-        const bool use_rows = blk_use_rows();
-        u32 *rowcnt = nullptr;
-        if (use_rows) {
-            CK(ctx->d_blkrowcnt.reserve((size_t)std::max<u32>(n_blocks, 1) * 4)); CK(ctx->d_blkrowptr.reserve(((size_t)n_blocks + 1) * 4));
-            rowcnt = ctx->d_blkrowcnt.as<u32>();
-            CK(cudaMemsetAsync(rowcnt, 0, (size_t)n_blocks * 4, ctx->stream));
-        }
+        // ---- sparse form: global one-hot words, block-pair list, one warp per block pair ----
         CK(cudaMemsetAsync(&sc->n_block_pairs, 0, 8, ctx->stream));
         LAUNCH(expand_blocks_kernel, grid_for((u64)W * 32, 256), 256, items, W, (const u32 *)ctx->d_bsum.p, L, k, cull, mi, 0, (uint2 *)nullptr,
-               (unsigned long long *)&sc->n_block_pairs, (u8 *)nullptr, rowcnt, (u32 *)nullptr);
+               (unsigned long long *)&sc->n_block_pairs, (u8 *)nullptr);
         rc = read_scalars(ctx);
         if (rc) return rc;
         const u64 n_pairs = ctx->h_sc->n_block_pairs;
@@ -673,31 +664,17 @@ static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, E
                 need = ctx->d_blocked.as<u8>();
                 CK(cudaMemsetAsync(need, 0, n_blocks, ctx->stream));
             }
-            if (use_rows) {
-                if (n_pairs >= 0xffffffffull) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "more than 2^32 block pairs in one pass: split the batch");
-                rc = run_scan(ctx, RowCount{rowcnt}, RowPtrEmit{ctx->d_blkrowptr.as<u32>(), rowcnt, n_blocks}, n_blocks, nullptr);
-                if (rc) return rc;
-                CK(ctx->d_blkcols.reserve(std::max<u64>(n_pairs, 1) * 4));
-                LAUNCH(expand_blocks_kernel, grid_for((u64)W * 32, 256), 256, items, W, (const u32 *)ctx->d_bsum.p, L, k, cull, mi, 1, (uint2 *)nullptr,
-                       (unsigned long long *)&sc->n_block_pairs, need, rowcnt, ctx->d_blkcols.as<u32>());
-            } else {
-                CK(ctx->d_pairs.reserve(std::max<u64>(n_pairs, 1) * sizeof(uint2)));
-                CK(cudaMemsetAsync(&sc->n_block_pairs, 0, 8, ctx->stream));
-                LAUNCH(expand_blocks_kernel, grid_for((u64)W * 32, 256), 256, items, W, (const u32 *)ctx->d_bsum.p, L, k, cull, mi, 1, ctx->d_pairs.as<uint2>(),
-                       (unsigned long long *)&sc->n_block_pairs, need, (u32 *)nullptr, (u32 *)nullptr);
-            }
+            CK(ctx->d_pairs.reserve(std::max<u64>(n_pairs, 1) * sizeof(uint2)));
+            CK(cudaMemsetAsync(&sc->n_block_pairs, 0, 8, ctx->stream));
+            LAUNCH(expand_blocks_kernel, grid_for((u64)W * 32, 256), 256, items, W, (const u32 *)ctx->d_bsum.p, L, k, cull, mi, 1, ctx->d_pairs.as<uint2>(),
+                   (unsigned long long *)&sc->n_block_pairs, need);
             if (has_n) LAUNCH(onehot_build_kernel<true>, grid_for((u64)n_blocks * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
                               (const u32 *)ctx->d_blkcnt.p, v.planes, v.nplane, L, LP, ctx->d_eq.as<u32>(), (const u8 *)need);
             else       LAUNCH(onehot_build_kernel<false>, grid_for((u64)n_blocks * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
                               (const u32 *)ctx->d_blkcnt.p, v.planes, v.nplane, L, LP, ctx->d_eq.as<u32>(), (const u8 *)need);
-            if (use_rows)
-                rc = launch_neighbours_rows(ctx->stream, ctx->num_sms, (const u32 *)ctx->d_blkrowptr.p, (const u32 *)ctx->d_blkcols.p, n_blocks,
-                                            (const u32 *)ctx->d_blkfirst.p, (const u32 *)ctx->d_blkcnt.p, (const u32 *)ctx->d_bsum.p, v.planes, v.nplane, v.ucode,
-                                            ctx->d_eq.as<uint4>(), L, k, has_n, cull, es, mi, v.uidmap, (unsigned long long *)&sc->pairs_eval);
-            else
-                rc = launch_neighbours_blocks(ctx->stream, ctx->num_sms, ctx->d_pairs.as<uint2>(), n_pairs, (const u32 *)ctx->d_blkfirst.p,
-                                              (const u32 *)ctx->d_blkcnt.p, (const u32 *)ctx->d_bsum.p, v.planes, v.nplane, v.ucode, ctx->d_eq.as<uint4>(),
-                                              L, k, has_n, cull, es, mi, v.uidmap, (unsigned long long *)&sc->pairs_eval);
+            rc = launch_neighbours_blocks(ctx->stream, ctx->num_sms, ctx->d_pairs.as<uint2>(), n_pairs, (const u32 *)ctx->d_blkfirst.p,
+                                          (const u32 *)ctx->d_blkcnt.p, (const u32 *)ctx->d_bsum.p, v.planes, v.nplane, v.ucode, ctx->d_eq.as<uint4>(),
+                                          L, k, has_n, cull, es, mi, v.uidmap, (unsigned long long *)&sc->pairs_eval);
             if (rc != 0) return fail(ctx, UMIGPU_ERR_CUDA, "block-pair neighbour kernel: %s", cudaGetErrorString(cudaGetLastError()));
             ctx->launches += 1;
             CK(cudaGetLastError());
