@@ -165,9 +165,11 @@ int umigpu_push_reads(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, const int
                       const uint8_t *is_reverse, const uint8_t *umi_ascii, const int32_t *score,
                       const int32_t *weight, uint64_t first_read_index);
 /* same, but every pointer is a DEVICE pointer valid on ctx's device (inputs already in HBM).  The first chunk of a batch
- * is borrowed, not copied: its arrays must stay valid and unchanged until umigpu_fetch / umigpu_reset (umi_ascii is
- * consumed by the call itself).  The context's stream does not synchronise with other streams: whatever produced the
- * arrays must have completed (or been ordered before cfg.stream) when this is called. */
+ * is borrowed, not copied, and the packing kernel that reads umi_ascii is only ENQUEUED on the context's stream: ALL the
+ * arrays of the call, umi_ascii included, must stay valid and unchanged until the next umigpu_run / umigpu_fetch /
+ * umigpu_reset of this context returns (the same rule as for pinned host buffers above).  The context's stream does not
+ * synchronise with other streams: whatever produced the arrays must have completed (or been ordered before cfg.stream)
+ * when this is called. */
 int umigpu_push_reads_device(umigpu_ctx *ctx, uint64_t n, const int32_t *tid, const int64_t *unclipped_pos,
                              const uint8_t *is_reverse, const uint8_t *umi_ascii, const int32_t *score,
                              const int32_t *weight, uint64_t first_read_index);

@@ -602,3 +602,58 @@ def test_read_order_does_not_change_the_surviving_groups():
     assert g0 == g1 and len(g0) == c0["n_kept"] == c1["n_kept"]
     for key in ("n_buckets", "total_umis", "max_umis", "n_edges"):
         assert c0[key] == c1[key]
+
+
+def test_n_bases_in_long_umis():
+    """N is a fifth letter at any UMI length the path supports (BitSet + n_bits in the reference, utils/bitset.rs:9-14): with
+    N the sort code takes 3 bits per base, beyond 21 nt it spills into the second key word (dual 12-nt UMIs = 24 nt, 32 nt)."""
+    rng = random.Random(5)
+    for L in (22, 24, 27, 32):
+        for trial in range(3):
+            n = rng.choice([400, 6000])
+            pool = ["".join(rng.choice("ACGT") for _ in range(L)) for _ in range(rng.choice([5, 60, 700]))]
+            umis = []
+            for _ in range(n):
+                u = list(rng.choice(pool))
+                for _ in range(rng.choice([0, 0, 1, 2])):
+                    u[rng.randrange(L)] = rng.choice("ACGTN")
+                umis.append("".join(u))
+            d = dict(tid=np.zeros(n, np.int32), pos=np.array(sorted(rng.randrange(4) * 100 for _ in range(n)), np.int64),
+                     rev=np.array([rng.randrange(2) for _ in range(n)], np.uint8), umi=arr(umis),
+                     score=np.array([rng.randrange(0, 40) for _ in range(n)], np.int32))
+            assert (d["umi"] == ord("N")).any()
+            for algo in (umigpu.ALGO_DIR, umigpu.ALGO_CC, umigpu.ALGO_ADJ_UPSTREAM):
+                check_against_oracle(d, algo, umigpu.MERGE_AVGQUAL, rng.choice([1, 2]), 0.5, labels=True)
+    # a single N read in a large N-free batch of dual 12-nt UMIs (the case the CLI twin used to die on)
+    d, cfg = small("C2", 0.002, seed=3, umi_len=24)
+    d["umi"][len(d["umi"]) // 2, 7] = ord("N")
+    check_against_oracle(d, umigpu.ALGO_DIR, umigpu.MERGE_AVGQUAL, 1, 0.5)
+
+
+@pytest.mark.parametrize("algo", [umigpu.ALGO_CC, umigpu.ALGO_ADJ_UPSTREAM])
+def test_full_size_c3_production_equals_brute_force(algo):
+    """C3 at FULL size (50 M reads, 16-nt UMIs, k = 2: three multi-index passes, hamming_blocks<16,2,0>) for both algorithms
+    BASELINE.json names (cc and the upstream-intended adjacency): the production search against the all-pairs direct kernel
+    (3.6e10 pairs, nothing culled) — same edges, same survivors."""
+    d, cfg = synth.generate_config("C3", device="cuda", scale=1.0)
+    kept, _, ctr = _run_flags(d, cfg, algo, 0)
+    bkept, _, bctr = _run_flags(d, cfg, algo, umigpu.FLAG_KERNEL_DIRECT | umigpu.FLAG_NO_CULL | umigpu.FLAG_NO_MULTI_INDEX)
+    assert bctr["pairs_evaluated"] >= bctr["unordered_pairs"] > 1e10
+    assert ctr["pairs_evaluated"] < bctr["pairs_evaluated"]
+    assert ctr["n_edges"] == bctr["n_edges"] > 0 and ctr["n_kept"] == bctr["n_kept"]
+    assert np.array_equal(kept, bkept)
+    assert (np.diff(kept.astype(np.int64)) > 0).all()
+
+
+def test_full_size_c5_production_equals_brute_force():
+    """C5 at FULL size (200 M reads, hottest locus 5.1 M unique UMIs, 2.1e13 unordered pairs): production (segmented sort,
+    multi-index passes, culling, two-phase clustering) against the dense bit-sliced tile kernel with culling and multi-index
+    switched off and against the generic sort: same edge count, same survivors."""
+    d, cfg = synth.generate_config("C5", device="cuda", scale=1.0)
+    kept, _, ctr = _run_flags(d, cfg, umigpu.ALGO_DIR, 0)
+    bkept, _, bctr = _run_flags(d, cfg, umigpu.ALGO_DIR, umigpu.FLAG_KERNEL_TILES | umigpu.FLAG_NO_CULL | umigpu.FLAG_NO_MULTI_INDEX)
+    assert bctr["pairs_evaluated"] >= bctr["unordered_pairs"] > 1e13
+    assert ctr["n_edges"] == bctr["n_edges"] > 1e7 and ctr["n_kept"] == bctr["n_kept"]
+    assert np.array_equal(kept, bkept)
+    for key in ("total_reads", "n_buckets", "total_umis", "max_umis"):
+        assert ctr[key] == bctr[key]

@@ -244,3 +244,50 @@ def test_frontier_clustering_matches_oracle(monkeypatch):
         kept, _, ctr = ctx.finish()
     okept, _, _ = O.dedup(tid, pos, rev, umis, score, O.ALGO_DIR, O.MERGE_AVGQUAL, 1, 0.5)
     assert kept.astype(np.int64).tolist() == okept.tolist()
+
+
+def test_full_size_c2_sharded_equals_unsharded():
+    """C2 at FULL size (50 M reads) over 4 ranks — all the box's GPUs when it has several, else four contexts on device 0:
+    contiguous slices + hot-bucket split must keep exactly the reads of the one-context run."""
+    import threading
+
+    import torch
+    d, cfg = synth.generate_config("C2", device="cuda:0", scale=1.0)
+    with umigpu.Context(cfg["umi_len"], 1, 0.5, umigpu.ALGO_DIR, umigpu.MERGE_AVGQUAL, 0) as c:
+        c.push_reads(d["tid"], d["pos"], d["rev"], d["umi"], d["score"])
+        full, _, fctr = c.finish()
+    h = {k: v.cpu().numpy() for k, v in d.items()}
+    del d
+    nd = torch.cuda.device_count()
+    N = 4
+    devices = [r % nd for r in range(N)]
+    cuts, keys, hot, _ = umigpu.shard_plan_sorted(h["tid"], h["pos"], h["rev"], N)
+    assert hot.present and hot.reads_est > 1_000_000
+    ctxs = [umigpu.Context(cfg["umi_len"], 1, 0.5, umigpu.ALGO_DIR, umigpu.MERGE_AVGQUAL, devices[r]) for r in range(N)]
+    for r, c in enumerate(ctxs):
+        c.xchg_create(r, N, int(hot.reads_est) + 4096, 4 * int(hot.reads_est))
+    for c in ctxs:
+        c.xchg_attach_local(ctxs)
+    out, errs = [None] * N, []
+
+    def work(r):
+        try:
+            a, b = int(cuts[r]), int(cuts[r + 1])
+            c = ctxs[r]
+            c.push_reads(h["tid"][a:b], h["pos"][a:b], h["rev"][a:b], h["umi"][a:b], h["score"][a:b], None, a)
+            c.run_sharded(hot, int(keys[r]), int(keys[r + 1]))
+            out[r] = c.fetch()
+        except Exception as e:      # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(N)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    merged = np.concatenate([o[0] for o in out])
+    assert np.array_equal(merged, full)
+    assert sum(o[2]["n_buckets"] for o in out) == fctr["n_buckets"] and sum(o[2]["n_edges"] for o in out) == fctr["n_edges"]
+    for c in ctxs:
+        c.close()

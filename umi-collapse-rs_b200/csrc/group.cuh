@@ -15,7 +15,7 @@ struct SortedKeys {
         return k0[i] == k0[j] && (k1 == nullptr || k1[i] == k1[j]);
     }
     __device__ __forceinline__ bool same_bucket(u64 i, u64 j) const {
-        if (umi_bits == 64) return k1[i] == k1[j];
+        if (umi_bits >= 64) return (k1[i] >> (umi_bits - 64)) == (k1[j] >> (umi_bits - 64));
         if ((k0[i] >> umi_bits) != (k0[j] >> umi_bits)) return false;
         return k1 == nullptr || k1[i] == k1[j];
     }
@@ -65,7 +65,7 @@ struct UniqueEmit {
             useg[uid] = (u32)i;
             // the bit planes are derived from ucode in unique_finalize_kernel (one thread per unique): here the
             // conversion would run divergently, once per element slot of every warp that holds a head
-            ucode[uid] = sk.umi_bits == 64 ? sk.k0[i] : (sk.k0[i] & ((1ull << sk.umi_bits) - 1));
+            ucode[uid] = sk.umi_bits >= 64 ? sk.k0[i] : (sk.k0[i] & ((1ull << sk.umi_bits) - 1));
             bhead[uid] = (i == 0 || !sk.same_bucket(i, i - 1)) ? 1 : 0;
         }
         if (i == n - 1) useg[uid + 1] = (u32)n;
@@ -148,10 +148,20 @@ __global__ void __launch_bounds__(256) unique_finalize_kernel(
     u32 n_unique, const u32 *__restrict__ useg, const unsigned long long *__restrict__ rep, const i32 *__restrict__ wsum,
     float percentage, int algo_inf_thr, i32 *__restrict__ freq, i32 *__restrict__ thr, u32 *__restrict__ rep_idx,
     unsigned long long *__restrict__ label, const u64 *__restrict__ ucode, int L, int has_n, uint2 *__restrict__ planes,
-    u32 *__restrict__ nplane) {
+    u32 *__restrict__ nplane, const u64 *__restrict__ umi2 = nullptr, const u32 *__restrict__ nmask = nullptr) {
     u32 u = blockIdx.x * 256 + threadIdx.x;
     if (u >= n_unique) return;
-    {
+    if (umi2) {
+        // wide codes (N present, more than 21 nt: 3 bits per base do not fit ucode): the planes come from the representative
+        // read's 2-bit code and N mask — same position convention (base b at plane bit L-1-b)
+        const u32 r = ~(u32)rep[u];
+        const u64 c = umi2[r];
+        u32 p0 = 0, p1 = 0;
+        for (int b = 0; b < L; b++) { p0 |= (u32)((c >> (2 * b)) & 1ull) << b; p1 |= (u32)((c >> (2 * b + 1)) & 1ull) << b; }
+        const u32 pn = nmask[r];
+        planes[u] = make_uint2(p0 & ~pn, p1 & ~pn);
+        nplane[u] = pn;
+    } else {
         u32 p0, p1, pn;
         code_to_planes(ucode[u], L, has_n, p0, p1, pn);
         planes[u] = make_uint2(p0, p1);

@@ -203,6 +203,18 @@ __device__ __forceinline__ u64 umi_sort_code(u64 umi2, u32 nm, int L, int has_n)
     return code;
 }
 
+// the same code for UMIs whose 3-bit form exceeds one word (N present, 22..32 nt): low 64 bits returned, the rest in hi
+__device__ __forceinline__ u64 umi_sort_code_wide(u64 umi2, u32 nm, int L, u64 &hi) {
+    u64 lo = 0; hi = 0;
+    for (int b = 0; b < L; b++) {
+        int sh = L - 1 - b;
+        u64 c = (nm >> sh) & 1 ? 4 : (umi2 >> (2 * sh)) & 3;
+        hi = (hi << 3) | (lo >> 61);
+        lo = (lo << 3) | c;
+    }
+    return lo;
+}
+
 template <int NW, bool LIN>
 __global__ void __launch_bounds__(256) build_keys_kernel(
     u64 n, const i32 *__restrict__ tid, const i64 *__restrict__ pos, const u8 *__restrict__ rev,
@@ -213,8 +225,14 @@ __global__ void __launch_bounds__(256) build_keys_kernel(
     if (LIN) { const u32 t = (u32)(tid[i] - lay.tid_min); bucket = ((__ldg(lay.lin_off + t) + (u64)(pos[i] - __ldg(lay.lin_pmin + t))) << 1) | (rev[i] ? 1u : 0u); }
     else bucket = ((u64)(u32)(tid[i] - lay.tid_min) << (lay.pos_bits + 1)) | ((u64)(pos[i] - lay.pos_min) << 1) | (rev[i] ? 1u : 0u);
     if (lay.tlen_bits) bucket = (bucket << lay.tlen_bits) | (u64)(tlen[i] - lay.tlen_min);    // PairedAlignment: + tlen
-    u64 code = umi_sort_code(umi2[i], nmask[i], lay.umi_len, lay.has_n);
     int ub = lay.umi_bits;
+    if (NW == 2 && ub > 64) {                 // N present and 3 bits per base exceed one word: [bucket | code] = k1:k0 with the code's top in k1
+        u64 chi;
+        k0[i] = umi_sort_code_wide(umi2[i], nmask[i], lay.umi_len, chi);
+        k1[i] = (bucket << (ub - 64)) | chi;
+        return;
+    }
+    u64 code = umi_sort_code(umi2[i], nmask[i], lay.umi_len, lay.has_n);
     u64 lo = (ub < 64 ? bucket << ub : 0) | code;
     k0[i] = lo;
     if (NW == 2) k1[i] = ub == 64 ? bucket : (ub == 0 ? 0 : bucket >> (64 - ub));

@@ -721,7 +721,6 @@ static int stage_group(umigpu_ctx *ctx, bool want_labels, bool force_inf_thr) {
     KeyLayout lay;
     lay.umi_len = (int)cfg.umi_len;
     lay.has_n = ctx->h_sc->any_n ? 1 : 0;
-    if (lay.has_n && lay.umi_len > 21) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "UMIs containing N are supported up to 21 nt");
     lay.umi_bits = lay.has_n ? 3 * lay.umi_len : 2 * lay.umi_len;
     lay.tid_min = ctx->h_sc->tid_min; lay.pos_min = ctx->h_sc->pos_min;
     u64 tid_range = (u64)((i64)ctx->h_sc->tid_max - (i64)ctx->h_sc->tid_min);
@@ -770,6 +769,8 @@ static int stage_group(umigpu_ctx *ctx, bool want_labels, bool force_inf_thr) {
         }
     }
     if (lay.bucket_bits > 64) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "bucket key needs %d bits (> 64)", lay.bucket_bits);
+    if (lay.total_bits > 128) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "sort key needs %d bits (> 128): %d-nt UMIs with N leave %d bits for the bucket", lay.total_bits,
+                                          lay.umi_len, 128 - lay.umi_bits);
     lay.nw = lay.total_bits <= 64 ? 1 : 2;
     ctx->ctr.key_bits = (u64)lay.total_bits;
     ctx->lay = lay;
@@ -848,7 +849,8 @@ static int stage_group(umigpu_ctx *ctx, bool want_labels, bool force_inf_thr) {
     LAUNCH(unique_finalize_kernel, grid_for(U, 256), 256, U, (const u32 *)ctx->d_useg.p, (const unsigned long long *)ctx->d_rep.p,
            weighted ? (const i32 *)ctx->d_wsum.p : (const i32 *)nullptr, cfg.percentage, inf_thr ? 1 : 0, ctx->d_freq.as<i32>(),
            ctx->d_thr.as<i32>(), ctx->d_repidx.as<u32>(), ctx->d_label.as<unsigned long long>(), (const u64 *)ctx->d_ucode.p, lay.umi_len, lay.has_n,
-           ctx->d_planes.as<uint2>(), ctx->d_nplane.as<u32>());
+           ctx->d_planes.as<uint2>(), ctx->d_nplane.as<u32>(), lay.umi_bits > 64 ? (const u64 *)ctx->d_umi2.p : (const u64 *)nullptr,
+           lay.umi_bits > 64 ? (const u32 *)ctx->d_nmask.p : (const u32 *)nullptr);
     STAGE_END(UMIGPU_STAGE_UNIQUE);
 
     // ---- buckets ----
@@ -880,7 +882,7 @@ static int stage_neighbours(umigpu_ctx *ctx, int mode) {
     ctx->st_need_edges = need_edges;
     const int cull = (cfg.flags & UMIGPU_FLAG_NO_CULL) ? 0 : 1;
     const int k = cfg.k, L = lay.umi_len;
-    const bool allow_blocks = !(cfg.flags & (UMIGPU_FLAG_KERNEL_DIRECT | UMIGPU_FLAG_KERNEL_TILES)) && k >= 1 && k <= 3 && !(has_n && L > 24) && cull;
+    const bool allow_blocks = !(cfg.flags & (UMIGPU_FLAG_KERNEL_DIRECT | UMIGPU_FLAG_KERNEL_TILES)) && k >= 1 && k <= 3 && !(has_n && L > 21) && cull;      // (with N beyond 21 nt the 3-bit codes exceed ucode: plane kernels only)
     u64 n_edges = 0;
     STAGE_BEGIN(UMIGPU_STAGE_NEIGHBOURS);
     // ---- multi-index preparation: which buckets are big, their compacted unique list ----
@@ -1831,6 +1833,7 @@ static int hot_publish(umigpu_ctx *ctx, const umigpu_hot *hot, u32 *u0_out) {
     const char *why = nullptr;
     int rc = UMIGPU_OK;
     if (ctx->use_orig) why = "the BAM feed cannot be combined with a split hot bucket";
+    else if (ctx->lay.umi_bits > 64) why = "UMIs with N beyond 21 nt cannot be split over devices";
     else if (local == ~0ull || n == 0) why = "the hot bucket's read is not in the owner's slice";
     if (!why) {
         CK(cudaMemsetAsync(&sc->scratch, 0xff, 8, ctx->stream));

@@ -1,7 +1,8 @@
 //! The one file a maintainer adds to the reference (`src/deduplicate_gpu.rs`): a new
 //! `impl DeduplicateInterface` that replaces HOT LOOP A's map updates and all of HOT LOOP B
 //! (src/deduplicate_sam.rs:148-233) with libumigpu, keeping htslib I/O, the CLI and every flag.
-//! NOT COMPILED HERE (no Rust toolchain in the build image).  See INTEGRATION.md.
+//! NOT COMPILED HERE (no Rust toolchain in the build image).  See INTEGRATION.md, which also lists the two one-word
+//! visibility changes this file needs in the reference (`pub(crate) struct UcWriter`, `pub(crate) fn umi_pattern`).
 use std::time::SystemTime;
 
 use memchr::arch::x86_64::avx2::memchr::One;
@@ -12,6 +13,7 @@ use umigpu_sys as gpu;
 use crate::cli::Cli;
 use crate::deduplicate_sam::{DeduplicateInterface, UcWriter};
 use crate::utils::get_unclipped_pos;
+use crate::utils::read::UcSAMRead;
 
 const CHUNK: usize = 1 << 22; // reads per umigpu_push_reads call (H2D overlaps BAM decoding)
 
@@ -30,6 +32,10 @@ impl DeduplicateGPU {
 
 impl DeduplicateInterface for DeduplicateGPU {
     fn deduplicate_and_merge(&mut self, args: &Cli, start_time: &SystemTime) {
+        // the reference collects ClusterTrackers under --tag and then writes nothing (deduplicate_sam.rs:236-239); the GPU arm
+        // refuses instead of silently ignoring the flag (umicollapse_gpu, the C++ twin, implements it from FLAG_LABELS)
+        if args.track_clusters { panic!("--tag is not wired into the GPU arm of the Rust host yet"); }
+        let pattern = UcSAMRead::umi_pattern(args.umi_separator);           // utils/read.rs:65-75, used once for the autodetection
         let one = One::new(args.umi_separator).expect("failed to create a new searcher");
         let mut reader = Reader::from_path(&args.input).expect("Invalid input path");
         reader.set_threads(args.num_threads).expect("Failed to set the number of threads for reader.");
@@ -58,7 +64,12 @@ impl DeduplicateInterface for DeduplicateGPU {
             }
             let qname = record.qname();
             let p = one.find(qname).expect("failed to get the umi");        // utils/read.rs:100-110
-            if umi_len == 0 { umi_len = qname[p + 1..].iter().take_while(|c| b"ACGTNacgtn".contains(c)).count(); }
+            // utils/read.rs:87-94: the length is the regex's first group — the FIRST separator that is followed by [ATCGN]+
+            // (caseless), which may be a later separator than the one get_umi cuts at
+            if umi_len == 0 {
+                let caps = pattern.captures(qname).unwrap().unwrap();
+                umi_len = caps.get(1).expect("No UMI group found in pattern match").as_bytes().len();
+            }
             // reads are numbered densely in push order; file_index maps a kept number back to its record in the input
             if tid.is_empty() { first_of_chunk = file_index.len() as u64; }
             file_index.push(this);
@@ -76,7 +87,14 @@ impl DeduplicateInterface for DeduplicateGPU {
         drop(reader);
 
         // all buckets at once on the GPU, then a second pass over the input writes the survivors in input order
-        let mut ctx = ctx.expect("no mapped reads");
+        let Some(mut ctx) = ctx else {
+            // no read survived the filters: the reference writes a header-only BAM (its bucket map is simply empty)
+            writer.close();
+            debug!("Number of input reads: {}", total);
+            debug!("Number of removed unmapped reads: {}", unmapped);
+            debug!("Number of reads after deduplicating: 0");
+            return;
+        };
         let (kept, ctr) = ctx.finish();
         let mut reader = Reader::from_path(&args.input).expect("Invalid input path");
         reader.set_threads(args.num_threads).unwrap();
@@ -105,3 +123,14 @@ fn flush(ctx: &mut Option<gpu::Context>, args: &Cli, me: &DeduplicateGPU, umi_le
     if args.paired { c.push_reads_paired(tid, pos, rev, tlen, umi, Some(score), first); } else { c.push_reads(tid, pos, rev, umi, Some(score), first); }
     tid.clear(); pos.clear(); rev.clear(); tlen.clear(); umi.clear(); score.clear();
 }
+
+// ---- several GPUs of one box (UMICOLLAPSE_GPUS=8): the same reader loop keeps ALL reads' arrays (25 B per read) instead of
+// flushing chunks, then ONE call shards the coordinate-sorted stream into contiguous slices, one per device, splits the
+// hot locus' neighbour search over NVLink, and returns the merged kept list (include/umigpu.h, "Several devices, ONE
+// dataset"):
+//
+//     let group = gpu::Group::new(cfg, &(0..n_gpus).collect::<Vec<i32>>());      // umigpu_group_create
+//     let (kept, ctr) = group.dedup(&tid, &pos, &rev, &umi, Some(&score));       // umigpu_group_dedup -> ascending indices
+//
+// followed by the same second pass over the input.  Input that is not coordinate-sorted is detected by the devices and
+// re-routed through the hash plan inside the call.

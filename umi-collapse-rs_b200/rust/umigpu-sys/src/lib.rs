@@ -40,6 +40,14 @@ pub struct umigpu_counters {
 }
 
 #[repr(C)]
+pub struct umigpu_group { _private: [u8; 0] }
+
+/// The bucket whose neighbour search is split over the devices of a shard group.
+#[repr(C)]
+#[derive(Clone, Copy, Default, Debug)]
+pub struct umigpu_hot { pub present: i32, pub owner: i32, pub read_index: u64, pub reads_est: u64 }
+
+#[repr(C)]
 pub struct umigpu_result {
     pub n_kept: u64,
     pub kept_read_index: *const u64,
@@ -88,6 +96,21 @@ extern "C" {
                                 unclipped_pos: *const i64, is_reverse: *const u8, umi_ascii: *const u8, score: *const i32,
                                 kept: *mut *mut u64, n_kept: *mut u64, counters: *mut umigpu_counters) -> c_int;
     pub fn umigpu_free(p: *mut c_void);
+    // several devices, ONE dataset
+    pub fn umigpu_pos_key(tid: i32, unclipped_pos: i64) -> i64;
+    pub fn umigpu_shard_plan_sorted(n: u64, tid: *const i32, unclipped_pos: *const i64, is_reverse: *const u8, n_shards: i32,
+                                    hot_min_reads: u64, cuts: *mut u64, cut_keys: *mut i64, hot: *mut umigpu_hot, shard_cost: *mut f64) -> c_int;
+    pub fn umigpu_xchg_create(ctx: *mut umigpu_ctx, rank: i32, n_ranks: i32, max_hot_uniques: u64, max_hot_edges: u64,
+                              ipc_handle_out: *mut u8) -> c_int;
+    pub fn umigpu_xchg_attach_ipc(ctx: *mut umigpu_ctx, handles: *const u8) -> c_int;
+    pub fn umigpu_xchg_attach_local(ctx: *mut umigpu_ctx, group: *const *mut umigpu_ctx) -> c_int;
+    pub fn umigpu_run_sharded(ctx: *mut umigpu_ctx, hot: *const umigpu_hot, key_lo: i64, key_hi: i64) -> c_int;
+    pub fn umigpu_group_create(cfg: *const umigpu_config, n_devices: i32, device_ids: *const i32, out: *mut *mut umigpu_group) -> c_int;
+    pub fn umigpu_group_destroy(g: *mut umigpu_group);
+    pub fn umigpu_group_context(g: *mut umigpu_group, rank: i32) -> *mut umigpu_ctx;
+    pub fn umigpu_group_dedup(g: *mut umigpu_group, n: u64, tid: *const i32, unclipped_pos: *const i64, is_reverse: *const u8,
+                              umi_ascii: *const u8, score: *const i32, kept: *mut *mut u64, n_kept: *mut u64,
+                              counters: *mut umigpu_counters, rank_ms: *mut c_float) -> c_int;
     pub fn umigpu_int_peak(ctx: *mut umigpu_ctx, lop3_ops_per_s: *mut f64, popc_ops_per_s: *mut f64) -> c_int;
 }
 
@@ -141,3 +164,31 @@ impl Drop for Context { fn drop(&mut self) { unsafe { umigpu_destroy(self.raw) }
 fn last_error(ctx: *const umigpu_ctx) -> String {
     unsafe { std::ffi::CStr::from_ptr(umigpu_last_error(ctx)).to_string_lossy().into_owned() }
 }
+
+/// Several GPUs of one box in one process: contiguous coordinate slices, hot bucket split over NVLink (umigpu_group_*).
+pub struct Group { raw: *mut umigpu_group }
+
+impl Group {
+    pub fn new(cfg: umigpu_config, devices: &[i32]) -> Self {
+        let mut raw = std::ptr::null_mut();
+        let rc = unsafe { umigpu_group_create(&cfg, devices.len() as i32, devices.as_ptr(), &mut raw) };
+        if rc != 0 { panic!("umigpu_group_create failed ({rc}): {}", last_error(std::ptr::null())); }
+        Self { raw }
+    }
+    /// Kept read indices of the whole dataset (ascending) and the summed counters.
+    pub fn dedup(&mut self, tid: &[i32], pos: &[i64], rev: &[u8], umi: &[u8], score: Option<&[i32]>) -> (Vec<u64>, umigpu_counters) {
+        let n = tid.len();
+        assert!(pos.len() == n && rev.len() == n && umi.len() % n.max(1) == 0);
+        let (mut kept, mut n_kept, mut ctr) = (std::ptr::null_mut(), 0u64, umigpu_counters::default());
+        let rc = unsafe {
+            umigpu_group_dedup(self.raw, n as u64, tid.as_ptr(), pos.as_ptr(), rev.as_ptr(), umi.as_ptr(),
+                               score.map_or(std::ptr::null(), |s| s.as_ptr()), &mut kept, &mut n_kept, &mut ctr, std::ptr::null_mut())
+        };
+        if rc != 0 { panic!("umigpu_group_dedup failed ({rc}): {}", last_error(std::ptr::null())); }
+        let out = if n_kept == 0 { Vec::new() } else { unsafe { std::slice::from_raw_parts(kept, n_kept as usize) }.to_vec() };
+        unsafe { umigpu_free(kept as *mut c_void) };
+        (out, ctr)
+    }
+}
+
+impl Drop for Group { fn drop(&mut self) { unsafe { umigpu_group_destroy(self.raw) } } }
