@@ -67,6 +67,7 @@ struct umigpu_ctx {
     u64 *h_umirep = nullptr;                            // pinned, same capacity as h_roots
     DevBuf d_umirep;
     DevBuf d_chunks;
+    u64 *h_chunks = nullptr; size_t h_chunks_cap = 0;    // pinned staging of the chunk table
     // BAM feed
     DevBuf d_bamraw, d_bamoff, d_btid, d_bpos, d_brev, d_bumi2, d_bnmask, d_bscore, d_bvalid, d_orig;
     bool use_orig = false;
@@ -190,6 +191,7 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
     if (ctx->h_kept) cudaFreeHost(ctx->h_kept);
     if (ctx->h_roots) cudaFreeHost(ctx->h_roots);
     if (ctx->h_umirep) cudaFreeHost(ctx->h_umirep);
+    if (ctx->h_chunks) cudaFreeHost(ctx->h_chunks);
     ctx->d_chunks.release(); ctx->d_umirep.release();
     ctx->d_stamp.release(); ctx->d_rowptr.release(); ctx->d_front[0].release(); ctx->d_front[1].release();
     ctx->d_segblk.release(); ctx->d_segnext.release(); ctx->d_segflag.release(); ctx->d_segbig.release(); ctx->d_seghist.release();
@@ -1158,11 +1160,17 @@ static int stage_emit(umigpu_ctx *ctx, bool want_labels) {
     // chunk table (push-order position -> caller's read index) for the device-side translation
     const u32 nch = (u32)ctx->chunks.size();
     {
-        std::vector<u64> tab(2 * (size_t)nch);
+        // context-owned pinned staging: no synchronisation needed for the upload (it stays untouched until the next run)
+        if (2 * (size_t)nch > ctx->h_chunks_cap) {
+            if (ctx->h_chunks) cudaFreeHost(ctx->h_chunks);
+            ctx->h_chunks = nullptr; ctx->h_chunks_cap = 0;
+            CK(cudaMallocHost((void **)&ctx->h_chunks, (2 * (size_t)nch + 64) * 8));
+            ctx->h_chunks_cap = 2 * (size_t)nch + 64;
+        }
+        u64 *tab = ctx->h_chunks;
         for (u32 c = 0; c < nch; c++) { tab[c] = ctx->chunks[c].start; tab[nch + c] = ctx->chunks[c].first_index; }
-        CK(ctx->d_chunks.reserve(tab.size() * 8));
-        CK(cudaMemcpyAsync(ctx->d_chunks.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));     // tab is a stack-lifetime pageable buffer
+        CK(ctx->d_chunks.reserve(2 * (size_t)nch * 8));
+        CK(cudaMemcpyAsync(ctx->d_chunks.p, tab, 2 * (size_t)nch * 8, cudaMemcpyHostToDevice, ctx->stream));
     }
     ChunkMap cm{ctx->d_chunks.as<u64>(), ctx->d_chunks.as<u64>() + nch, nch, ctx->use_orig ? ctx->d_orig.as<u32>() : (const u32 *)nullptr};
     rc = run_scan(ctx, BitmapCount{ctx->d_bitmap.as<u32>()}, BitmapEmit{ctx->d_bitmap.as<u32>(), ctx->d_kept.as<u64>(), n_words, sc, cm}, n_words, nullptr);
@@ -1632,6 +1640,10 @@ struct Xchg {
     std::atomic<int> *abort = nullptr;        // in-process groups: set when a rank of the group failed (waits give up at once)
 };
 
+// UMIGPU_XCHG_DEBUG=1: one stderr line per hand-over step and rank (which rank waits for what, for how long)
+static bool xchg_debug() { static int v = -1; if (v < 0) v = getenv("UMIGPU_XCHG_DEBUG") ? 1 : 0; return v == 1; }
+#define XDBG(...) do { if (xchg_debug()) { fprintf(stderr, "[umigpu xchg] " __VA_ARGS__); fputc('\n', stderr); } } while (0)
+
 static void xchg_release(umigpu_ctx *ctx) {
     Xchg *x = ctx->x;
     if (!x) return;
@@ -1808,10 +1820,15 @@ static int xchg_poll(umigpu_ctx *ctx, const char *src, size_t bytes, Pred pred, 
     Xchg *x = ctx->x;
     unsigned long long *buf = x->h_pin + 8;
     const auto t0 = std::chrono::steady_clock::now();
+    XDBG("rank %d (device %d) epoch %llu: waiting for %s", x->rank, ctx->cfg.device, (unsigned long long)x->epoch, what);
     for (u64 it = 0;; it++) {
         CK(cudaMemcpyAsync(buf, src, bytes, cudaMemcpyDefault, x->xs));
         CK(cudaStreamSynchronize(x->xs));
-        if (pred(buf)) return UMIGPU_OK;
+        if (pred(buf)) {
+            XDBG("rank %d epoch %llu: got %s after %.3f ms (%llu polls)", x->rank, (unsigned long long)x->epoch, what,
+                 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), (unsigned long long)it + 1);
+            return UMIGPU_OK;
+        }
         if (x->abort && x->abort->load()) return fail(ctx, UMIGPU_ERR_STATE, "shard group: rank %d gave up waiting for %s: another rank failed", x->rank, what);
         if ((it & 63) == 63) {
             const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -1859,6 +1876,7 @@ static int hot_publish(umigpu_ctx *ctx, const umigpu_hot *hot, u32 *u0_out) {
     if (why) { cudaStreamSynchronize(ctx->stream); return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "shard group: %s (%u unique UMIs, window holds %llu)", why, uh, (unsigned long long)x->ucap); }
     ctx->skip_bucket = hb;
     *u0_out = u0;
+    XDBG("rank %d epoch %llu: published hot bucket %u (%u unique UMIs from unique id %u)", x->rank, (unsigned long long)x->epoch, hb, uh, u0);
     return UMIGPU_OK;
 }
 
@@ -1929,6 +1947,7 @@ static int hot_band(umigpu_ctx *ctx, const umigpu_hot *hot) {
     char *inbox = const_cast<char *>(ow) + x->off_inbox + (size_t)x->rank * x->region * 8;
     if (c_edges > x->region) count |= 1ull << 63;
     else if (c_edges) CK(cudaMemcpyAsync(inbox, ctx->hot->d_edges.p, (size_t)c_edges * 8, cudaMemcpyDefault, ctx->stream));
+    XDBG("rank %d epoch %llu: band done, %llu edges -> owner %d", x->rank, (unsigned long long)epoch, (unsigned long long)c_edges, hot->owner);
     x->h_pin[2] = count; x->h_pin[3] = epoch;
     char *slot = const_cast<char *>(ow) + offsetof(XchgHeader, slot) + (size_t)x->rank * sizeof(XchgSlot);
     CK(cudaMemcpyAsync(slot + offsetof(XchgSlot, count), &x->h_pin[2], 8, cudaMemcpyDefault, ctx->stream));
