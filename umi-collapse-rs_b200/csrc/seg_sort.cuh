@@ -90,27 +90,36 @@ __global__ void __launch_bounds__(256) seg_block_summary_kernel(const u64 *__res
 // ---- plan, step 2 (one CTA): next head after every block, big segments, tile table ----
 // next[b] = position of the first head in a block > b (n if none).  The last head of block b starts a big segment iff
 // next[b] - last[b] > SEG_BLK.  big_of_blk[b] = 1 in that case (the window kernel then stops before it).
+#define SEG_PLAN_PER 4          // block-table entries per thread and round
 __global__ void __launch_bounds__(1024) seg_plan_kernel(const SegBlock *__restrict__ blk, u32 n_blk, u64 n, u32 tile, u32 *__restrict__ next_head,
                                                         u8 *__restrict__ big_of_blk, SegBig *__restrict__ big, SegPlanOut *plan) {
     __shared__ u32 sm[1024 / 32 + 1];
     __shared__ u32 s_carry;
-    // suffix minimum of `first`, walking the block table backwards in chunks of 1024
+    constexpr int PER = SEG_PLAN_PER;
+    constexpr long long CHUNK = 1024LL * PER;
+    // suffix minimum of `first`, walking the block table backwards: thread t of a round owns the PER entries below
+    // hi - PER * t (descending), so "entries after mine" = lower threads + the rounds already done
     if (threadIdx.x == 0) s_carry = (u32)n;
     __syncthreads();
-    for (long long hi = (long long)n_blk; hi > 0; hi -= 1024) {
-        const long long b = hi - 1 - (long long)threadIdx.x;          // thread 0 takes the last block of the chunk
-        u32 v = (b >= 0 && blk[b].first != SEG_NONE) ? blk[b].first : SEG_NONE;
-        // exclusive suffix-min within the chunk = exclusive prefix-min in thread order
-        u32 inc = v;
+    for (long long hi = (long long)n_blk; hi > 0; hi -= CHUNK) {
+        u32 v[PER];
+        u32 agg = SEG_NONE;
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const long long b = hi - 1 - (long long)threadIdx.x * PER - q;
+            v[q] = (b >= 0 && blk[b].first != SEG_NONE) ? blk[b].first : SEG_NONE;
+            agg = min(agg, v[q]);
+        }
+        u32 inc = agg;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane_id() >= (u32)o) inc = min(inc, t); }
         if (lane_id() == 31) sm[threadIdx.x >> 5] = inc;
         __syncthreads();
         if (threadIdx.x < 32) {
-            u32 s = sm[threadIdx.x];
+            u32 sv = sm[threadIdx.x];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, s, o); if (lane_id() >= (u32)o) s = min(s, t); }
-            sm[threadIdx.x] = s;                                       // inclusive over warps
+            for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, sv, o); if (lane_id() >= (u32)o) sv = min(sv, t); }
+            sm[threadIdx.x] = sv;                                      // inclusive over warps
         }
         __syncthreads();
         u32 ex = __shfl_up_sync(0xffffffffu, inc, 1);
@@ -118,27 +127,42 @@ __global__ void __launch_bounds__(1024) seg_plan_kernel(const SegBlock *__restri
         const u32 w = threadIdx.x >> 5;
         if (w > 0) ex = min(ex, sm[w - 1]);
         const u32 carry = s_carry;
-        ex = min(ex, carry);                                           // heads in later chunks / n
-        if (b >= 0) next_head[b] = ex;
+        ex = min(ex, carry);                                           // heads in later rounds / n
+        u32 run = ex;
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const long long b = hi - 1 - (long long)threadIdx.x * PER - q;
+            if (b >= 0) next_head[b] = run;
+            run = min(run, v[q]);
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) s_carry = min(carry, min(ex, v));
+        if (threadIdx.x == 1023) s_carry = run;                        // minimum over everything from this round's lowest entry up
         __syncthreads();
     }
     // big segments in block order, with their first tile (exclusive prefix sum of tile counts)
     u32 carry_big = 0, carry_tiles = 0;
-    for (u32 lo = 0; lo < n_blk; lo += 1024) {
-        const u32 b = lo + threadIdx.x;
-        u32 start = 0, len = 0, is_big = 0;
-        if (b < n_blk && blk[b].last != SEG_NONE) {
-            start = blk[b].last; len = next_head[b] - start;
-            is_big = len > SEG_BLK ? 1u : 0u;
+    for (u32 lo = 0; lo < n_blk; lo += (u32)CHUNK) {
+        u32 start[PER], len[PER], nt[PER];
+        u32 cnt_b = 0, cnt_t = 0;
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const u32 b = lo + threadIdx.x * PER + q;
+            start[q] = 0; len[q] = 0; nt[q] = 0;
+            u32 is_big = 0;
+            if (b < n_blk && blk[b].last != SEG_NONE) {
+                start[q] = blk[b].last; len[q] = next_head[b] - start[q];
+                is_big = len[q] > SEG_BLK ? 1u : 0u;
+            }
+            if (b < n_blk) big_of_blk[b] = (u8)is_big;
+            if (is_big) { nt[q] = (len[q] + tile - 1) / tile; cnt_b++; cnt_t += nt[q]; } else len[q] = 0;
         }
-        if (b < n_blk) big_of_blk[b] = (u8)is_big;
-        const u32 nt = is_big ? (len + tile - 1) / tile : 0u;
         u32 tot_b, tot_t;
-        const u32 ex_b = block_exclusive_scan<u32, 1024>(is_big, sm, &tot_b);
-        const u32 ex_t = block_exclusive_scan<u32, 1024>(nt, sm, &tot_t);
-        if (is_big) big[carry_big + ex_b] = SegBig{start, len, carry_tiles + ex_t, 0u};
+        u32 ex_b = block_exclusive_scan<u32, 1024>(cnt_b, sm, &tot_b);
+        u32 ex_t = block_exclusive_scan<u32, 1024>(cnt_t, sm, &tot_t);
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            if (len[q]) { big[carry_big + ex_b] = SegBig{start[q], len[q], carry_tiles + ex_t, 0u}; ex_b++; ex_t += nt[q]; }
+        }
         carry_big += tot_b; carry_tiles += tot_t;
     }
     if (threadIdx.x == 0) { plan->n_big = carry_big; plan->n_tiles = carry_tiles; }
@@ -188,6 +212,37 @@ __device__ __forceinline__ void seg_local_pass(u64 (&x)[ITEMS], u32 count, int s
     __syncthreads();
 }
 
+// Windows are mostly far from full (a block whose tail lies inside a big segment, sparse loci): the element count picks how many
+// slots a thread owns (1, 2, 4 or 8), so a window of 500 reads ranks 512 slots per pass, not 4096.
+template <int ITEMS>
+__device__ __forceinline__ void seg_window_body(SegWinShared &S, u64 *sbuf, const u64 *__restrict__ key_in, u32 lo, u32 count, int sbits, int segbits,
+                                                u64 *__restrict__ key_out, u32 *__restrict__ idx_out) {
+    const u64 smask = (1ull << sbits) - 1;
+    const u32 w = threadIdx.x >> 5, lane = lane_id();
+    u64 x[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 e = (w * ITEMS + j) * 32 + lane;
+        x[j] = e < count ? sbuf[e] : 0;
+    }
+    __syncthreads();
+    const int bits = sbits + segbits;
+    for (int done = 0; done < bits; done += RS_RB) {
+        const int b = min(RS_RB, bits - done);
+        seg_local_pass<ITEMS>(x, count, SEG_POS_BITS + done, (1u << b) - 1u, S, sbuf);
+    }
+    // slot e now holds the element of sorted position lo + e; P comes from the (unsorted) input at the same position
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 e = (w * ITEMS + j) * 32 + lane;
+        if (e < count) {
+            const u64 i = (u64)lo + e;
+            key_out[i] = (key_in[i] & ~smask) | ((x[j] >> SEG_POS_BITS) & smask);
+            idx_out[i] = lo + (u32)(x[j] & ((1u << SEG_POS_BITS) - 1u));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(SEG_THREADS, 2) seg_window_sort_kernel(const u64 *__restrict__ key_in, u64 n, int sbits, const SegBlock *__restrict__ blk,
                                                                          const u32 *__restrict__ next_head, const u8 *__restrict__ big_of_blk,
                                                                          u64 *__restrict__ key_out, u32 *__restrict__ idx_out) {
@@ -227,31 +282,12 @@ __global__ void __launch_bounds__(SEG_THREADS, 2) seg_window_sort_kernel(const u
         if (e0 + j < count) sbuf[e0 + j] = ((((u64)seg << sbits) | (k[j] & smask)) << SEG_POS_BITS) | (u64)(e0 + j);
     }
     __syncthreads();
-    const u32 w = threadIdx.x >> 5, lane = lane_id();
-    u64 x[SEG_WIN_ITEMS];
-#pragma unroll
-    for (int j = 0; j < SEG_WIN_ITEMS; j++) {
-        const u32 e = (w * SEG_WIN_ITEMS + j) * 32 + lane;
-        x[j] = e < count ? sbuf[e] : 0;
-    }
-    __syncthreads();
     int segbits = 0;
     while ((nseg_m1 >> segbits) != 0) segbits++;
-    const int bits = sbits + segbits;
-    for (int done = 0; done < bits; done += RS_RB) {
-        const int b = min(RS_RB, bits - done);
-        seg_local_pass<SEG_WIN_ITEMS>(x, count, SEG_POS_BITS + done, (1u << b) - 1u, S, sbuf);
-    }
-    // slot e now holds the element of sorted position lo + e; P comes from the (unsorted) input at the same position
-#pragma unroll
-    for (int j = 0; j < SEG_WIN_ITEMS; j++) {
-        const u32 e = (w * SEG_WIN_ITEMS + j) * 32 + lane;
-        if (e < count) {
-            const u64 i = (u64)lo + e;
-            key_out[i] = (key_in[i] & ~smask) | ((x[j] >> SEG_POS_BITS) & smask);
-            idx_out[i] = lo + (u32)(x[j] & ((1u << SEG_POS_BITS) - 1u));
-        }
-    }
+    if (count <= SEG_THREADS)          seg_window_body<1>(S, sbuf, key_in, lo, count, sbits, segbits, key_out, idx_out);
+    else if (count <= 2 * SEG_THREADS) seg_window_body<2>(S, sbuf, key_in, lo, count, sbits, segbits, key_out, idx_out);
+    else if (count <= 4 * SEG_THREADS) seg_window_body<4>(S, sbuf, key_in, lo, count, sbits, segbits, key_out, idx_out);
+    else                               seg_window_body<8>(S, sbuf, key_in, lo, count, sbits, segbits, key_out, idx_out);
 }
 
 // ---- big segments: batched one-sweep passes over S ----
