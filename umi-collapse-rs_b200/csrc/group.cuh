@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(256) tile_summary_kernel(u32 n_tiles, u32 n_bu
                                                            const u32 *__restrict__ nplane, int L, u32 *__restrict__ tsum,
                                                            const u32 *__restrict__ blk_off, u32 *__restrict__ bsum,
                                                            u32 *__restrict__ blk_first, u32 *__restrict__ blk_cnt,
-                                                           const u64 *__restrict__ ucode, MiParams mi, u32 *__restrict__ ssum) {
+                                                           const u64 *__restrict__ ucode, MiParams mi) {
     u32 t = (blockIdx.x * 256 + threadIdx.x) >> 5;
     if (t >= n_tiles) return;
     u32 lo = 0, hi = n_buckets;
@@ -351,21 +351,14 @@ __global__ void __launch_bounds__(256) tile_summary_kernel(u32 n_tiles, u32 n_bu
     const u32 gb0 = blk_off[b] + ti * BLOCKS_PER_TILE;       // global id of the tile's first 128-block
     for (u32 blk = 0; blk * 128 < cnt; blk++) {
         u32 acc[5] = {0, 0, 0, 0, 0};
-        const u32 bend = min(cnt, (blk + 1) * 128);
-        // letter sets of each 32-UMI slice of the block as well (ssum): the evaluation kernel tests a row slice against a
-        // column block with four loads instead of loading the 32 rows and reducing their one-hot planes
+        for (u32 i = blk * 128 + lane_id(); i < min(cnt, (blk + 1) * 128); i += 32) {
+            u32 oh[5];
+            onehot_planes(planes[first + i], nplane ? nplane[first + i] : 0u, lmask, oh);
 #pragma unroll
-        for (u32 sl = 0; sl < 4; sl++) {
-            const u32 i = blk * 128 + sl * 32 + lane_id();
-            u32 oh[5] = {0, 0, 0, 0, 0};
-            if (i < bend) onehot_planes(planes[first + i], nplane ? nplane[first + i] : 0u, lmask, oh);
-            u32 v = 0;
-#pragma unroll
-            for (int x = 0; x < 5; x++) { const u32 r = __reduce_or_sync(0xffffffffu, oh[x]); acc[x] |= r; if (lane_id() == (u32)x) v = r; }
-            if (lane_id() < TS_WORDS) ssum[(((u64)gb0 + blk) * 4 + sl) * TS_WORDS + lane_id()] = v;
+            for (int x = 0; x < 5; x++) acc[x] |= oh[x];
         }
 #pragma unroll
-        for (int x = 0; x < 5; x++) tot[x] |= acc[x];
+        for (int x = 0; x < 5; x++) { acc[x] = __reduce_or_sync(0xffffffffu, acc[x]); tot[x] |= acc[x]; }
         if (lane_id() < TS_WORDS) {
             u32 v = 0;
 #pragma unroll

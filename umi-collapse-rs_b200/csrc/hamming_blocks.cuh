@@ -175,8 +175,7 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
                                                       const u32 *__restrict__ blk_cnt, const u32 *__restrict__ bsum,
                                                       const uint2 *__restrict__ planes, const u32 *__restrict__ nplane,
                                                       const u64 *__restrict__ ucode, const uint4 *__restrict__ eq, int L, int cull, EdgeSink es,
-                                                      MiParams mi, const u32 *__restrict__ uidmap, unsigned long long *pairs_eval,
-                                                      const u32 *__restrict__ ssum) {
+                                                      MiParams mi, const u32 *__restrict__ uidmap, unsigned long long *pairs_eval) {
     constexpr int XS = HASN ? 8 : 4;
     constexpr int NLET = HASN ? 5 : 4;
     const u32 lane = lane_id();
@@ -232,22 +231,20 @@ __global__ void __launch_bounds__(256) hamming_blocks(const uint2 *__restrict__ 
             sw = swr;
         }
         for (u32 s = 0; s * 32 < rcnt; s++) {
-            if (cull && !same) {
-                // letter sets of the row slice (tile_summary_kernel) against the column block's: more than K positions with
-                // disjoint sets -> no pair of the slice can be within K, and its rows are never loaded
-                const u32 *sp = ssum + ((u64)pr.x * 4 + s) * 8;
-                u32 t = 0;
-#pragma unroll
-                for (int x = 0; x < NLET; x++) t |= __ldg(sp + x) & cs[x];
-                if (__popc(~t & lmask) > K) continue;
-            }
             const u32 r = s * 32 + lane;
             const bool valid = r < rcnt;
             const uint2 rp = valid ? planes[rfirst + r] : make_uint2(0u, 0u);
             const u32 rn = (HASN && valid) ? nplane[rfirst + r] : 0u;
             const u64 rc = valid ? ucode[rfirst + r] : 0ull;
-            (void)rp; (void)rn;
-            evaluated += (u64)min(32u, rcnt - s * 32) * ccnt;
+            if (cull && !same) {
+                // the 32 rows of a slice are consecutive sorted UMIs: few letters per position
+                u32 oh[5], t = 0;
+                onehot_planes(rp, rn, valid ? lmask : 0u, oh);
+#pragma unroll
+                for (int x = 0; x < NLET; x++) t |= __reduce_or_sync(0xffffffffu, oh[x]) & cs[x];
+                if (__popc(~t & lmask) > K) continue;          // > K positions with disjoint letter sets
+            }
+            evaluated += (u64)__popc(__ballot_sync(0xffffffffu, valid)) * ccnt;
             uint4 h = make_uint4(0u, 0u, 0u, 0u);
             if (valid) {
                 u32 off[LP];                                   // uint4 index of the row's letter slot at position j
@@ -333,7 +330,7 @@ static inline bool blk_use_bulk() {
 template <int LP, int K, bool HASN>
 static int blk_launch_one(cudaStream_t stream, int num_sms, const uint2 *pairs, u64 n_pairs, const u32 *blk_first, const u32 *blk_cnt,
                           const u32 *bsum, const uint2 *planes, const u32 *nplane, const u64 *ucode, const uint4 *eq, int L, int cull, EdgeSink es,
-                          MiParams mi, const u32 *uidmap, unsigned long long *pairs_eval, const u32 *ssum) {
+                          MiParams mi, const u32 *uidmap, unsigned long long *pairs_eval) {
     // the bulk variant keeps two column buffers per warp: instantiated where they stay small (no N plane)
     constexpr bool CAN_BULK = !HASN;
     const bool bulk = CAN_BULK && blk_use_bulk();
@@ -342,7 +339,7 @@ static int blk_launch_one(cudaStream_t stream, int num_sms, const uint2 *pairs, 
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0) != cudaSuccess || occ < 1) occ = 1;
     u32 grid = (u32)std::min<u64>((n_pairs + 7) / 8, (u64)num_sms * occ * 4);
     if (grid == 0) return 0;
-    kern<<<grid, 256, 0, stream>>>(pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, mi, uidmap, pairs_eval, ssum);
+    kern<<<grid, 256, 0, stream>>>(pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, mi, uidmap, pairs_eval);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -351,8 +348,8 @@ static inline int blk_lp(int L) { return L <= 8 ? 8 : L <= 12 ? 12 : L <= 16 ? 1
 template <int K, bool HASN>
 static int blk_launch_k(cudaStream_t stream, int num_sms, const uint2 *pairs, u64 n_pairs, const u32 *blk_first, const u32 *blk_cnt,
                         const u32 *bsum, const uint2 *planes, const u32 *nplane, const u64 *ucode, const uint4 *eq, int L, int cull, EdgeSink es,
-                        MiParams mi, const u32 *uidmap, unsigned long long *pairs_eval, const u32 *ssum) {
-#define BLK_ARGS stream, num_sms, pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, mi, uidmap, pairs_eval, ssum
+                        MiParams mi, const u32 *uidmap, unsigned long long *pairs_eval) {
+#define BLK_ARGS stream, num_sms, pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, mi, uidmap, pairs_eval
     switch (blk_lp(L)) {
     case 8:  return blk_launch_one<8, K, HASN>(BLK_ARGS);
     case 12: return blk_launch_one<12, K, HASN>(BLK_ARGS);
@@ -367,8 +364,8 @@ static int blk_launch_k(cudaStream_t stream, int num_sms, const uint2 *pairs, u6
 static int launch_neighbours_blocks(cudaStream_t stream, int num_sms, const uint2 *pairs, u64 n_pairs, const u32 *blk_first,
                                     const u32 *blk_cnt, const u32 *bsum, const uint2 *planes, const u32 *nplane, const u64 *ucode,
                                     const uint4 *eq, int L, int k, bool has_n, int cull, EdgeSink es, MiParams mi, const u32 *uidmap,
-                                    unsigned long long *pairs_eval, const u32 *ssum) {
-#define BLK_ARGS stream, num_sms, pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, mi, uidmap, pairs_eval, ssum
+                                    unsigned long long *pairs_eval) {
+#define BLK_ARGS stream, num_sms, pairs, n_pairs, blk_first, blk_cnt, bsum, planes, nplane, ucode, eq, L, cull, es, mi, uidmap, pairs_eval
     if (k < 1 || k > 3) return 1;
     if (!has_n) {
         if (k == 1) return blk_launch_k<1, false>(BLK_ARGS);

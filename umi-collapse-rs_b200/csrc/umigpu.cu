@@ -51,7 +51,7 @@ struct umigpu_ctx {
 
     DevBuf d_key[2][2], d_idx[2], d_hist, d_tiles;
     DevBuf d_useg, d_rep, d_planes, d_nplane, d_bhead, d_wsum, d_read_uid, d_freq, d_thr, d_repidx, d_label, d_prio;
-    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_tileoff, d_tsum, d_tilestate, d_bsum, d_blkoff, d_blkfirst, d_blkcnt, d_ssum, d_eq, d_pairs, d_comp, d_ucode, d_ubkt, d_brank, d_bigbid, d_bstartbig, d_biguid, d_miplanes, d_minplane, d_miucode, d_miuid, d_cedges, d_tidtab, d_lintab;
+    DevBuf d_bstart, d_itemoff, d_items, d_edges, d_keep, d_state, d_blocked, d_bitmap, d_kept, d_roots, d_tileoff, d_tsum, d_tilestate, d_bsum, d_blkoff, d_blkfirst, d_blkcnt, d_eq, d_pairs, d_comp, d_ucode, d_ubkt, d_brank, d_bigbid, d_bstartbig, d_biguid, d_miplanes, d_minplane, d_miucode, d_miuid, d_cedges, d_tidtab, d_lintab;
 
     // results
     bool ran = false;
@@ -184,7 +184,7 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
                       &ctx->d_hist, &ctx->d_tiles, &ctx->d_useg, &ctx->d_rep, &ctx->d_planes, &ctx->d_nplane, &ctx->d_bhead, &ctx->d_wsum,
                       &ctx->d_read_uid, &ctx->d_freq, &ctx->d_thr, &ctx->d_repidx, &ctx->d_label, &ctx->d_prio, &ctx->d_bstart, &ctx->d_itemoff,
                       &ctx->d_items, &ctx->d_edges, &ctx->d_keep, &ctx->d_state, &ctx->d_blocked, &ctx->d_bitmap, &ctx->d_kept, &ctx->d_roots,
-                      &ctx->d_tileoff, &ctx->d_tsum, &ctx->d_tilestate, &ctx->d_bsum, &ctx->d_blkoff, &ctx->d_blkfirst, &ctx->d_blkcnt, &ctx->d_ssum, &ctx->d_eq, &ctx->d_pairs, &ctx->d_comp, &ctx->d_ucode, &ctx->d_ubkt, &ctx->d_brank, &ctx->d_bigbid, &ctx->d_bstartbig, &ctx->d_biguid,
+                      &ctx->d_tileoff, &ctx->d_tsum, &ctx->d_tilestate, &ctx->d_bsum, &ctx->d_blkoff, &ctx->d_blkfirst, &ctx->d_blkcnt, &ctx->d_eq, &ctx->d_pairs, &ctx->d_comp, &ctx->d_ucode, &ctx->d_ubkt, &ctx->d_brank, &ctx->d_bigbid, &ctx->d_bstartbig, &ctx->d_biguid,
                       &ctx->d_miplanes, &ctx->d_minplane, &ctx->d_miucode, &ctx->d_miuid, &ctx->d_cedges, &ctx->d_tidtab, &ctx->d_lintab};
     for (DevBuf *b : bufs) b->release();
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
@@ -626,10 +626,9 @@ static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, E
     CK(ctx->d_bsum.reserve((size_t)std::max<u32>(n_blocks, 1) * TS_WORDS * 4));
     CK(ctx->d_blkfirst.reserve((size_t)std::max<u32>(n_blocks, 1) * 4));
     CK(ctx->d_blkcnt.reserve((size_t)std::max<u32>(n_blocks, 1) * 4));
-    CK(ctx->d_ssum.reserve((size_t)std::max<u32>(n_blocks, 1) * 4 * TS_WORDS * 4));
     LAUNCH(tile_summary_kernel, grid_for((u64)n_tiles * 32, 256), 256, n_tiles, B, (const u32 *)ctx->d_tileoff.p, v.bstart, v.planes, v.nplane, L,
            ctx->d_tsum.as<u32>(), (const u32 *)ctx->d_blkoff.p, ctx->d_bsum.as<u32>(), ctx->d_blkfirst.as<u32>(), ctx->d_blkcnt.as<u32>(),
-           v.ucode, mi, ctx->d_ssum.as<u32>());
+           v.ucode, mi);
     CK(ctx->d_items.reserve((size_t)n_cand * sizeof(TileItem)));
     CK(cudaMemsetAsync(&sc->n_items, 0, 4, ctx->stream));
     CK(cudaMemsetAsync(&sc->scratch2, 0, 8, ctx->stream));
@@ -677,7 +676,7 @@ static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, E
                               (const u32 *)ctx->d_blkcnt.p, v.planes, v.nplane, L, LP, ctx->d_eq.as<u32>(), (const u8 *)need);
             rc = launch_neighbours_blocks(ctx->stream, ctx->num_sms, ctx->d_pairs.as<uint2>(), n_pairs, (const u32 *)ctx->d_blkfirst.p,
                                           (const u32 *)ctx->d_blkcnt.p, (const u32 *)ctx->d_bsum.p, v.planes, v.nplane, v.ucode, ctx->d_eq.as<uint4>(),
-                                          L, k, has_n, cull, es, mi, v.uidmap, (unsigned long long *)&sc->pairs_eval, (const u32 *)ctx->d_ssum.p);
+                                          L, k, has_n, cull, es, mi, v.uidmap, (unsigned long long *)&sc->pairs_eval);
             if (rc != 0) return fail(ctx, UMIGPU_ERR_CUDA, "block-pair neighbour kernel: %s", cudaGetErrorString(cudaGetLastError()));
             ctx->launches += 1;
             CK(cudaGetLastError());
