@@ -1816,8 +1816,7 @@ __global__ void __launch_bounds__(256) hot_append_kernel(const uint2 *__restrict
 
 // host-side wait on a word of a window: small peer reads on the polling stream until pred(value)
 template <class Pred>
-static int xchg_poll(umigpu_ctx *ctx, const char *src, size_t bytes, Pred pred, const char *what) {
-    Xchg *x = ctx->x;
+static int xchg_poll(Xchg *x, umigpu_ctx *ctx /* receives the error message */, const char *src, size_t bytes, Pred pred, const char *what) {
     unsigned long long *buf = x->h_pin + 8;
     const auto t0 = std::chrono::steady_clock::now();
     XDBG("rank %d (device %d) epoch %llu: waiting for %s", x->rank, ctx->cfg.device, (unsigned long long)x->epoch, what);
@@ -1881,78 +1880,84 @@ static int hot_publish(umigpu_ctx *ctx, const umigpu_hot *hot, u32 *u0_out) {
 }
 
 // every rank: import the hot bucket's arrays from the owner, search this rank's band of row tiles, put the edges
-static int hot_band(umigpu_ctx *ctx, const umigpu_hot *hot);
+static int hot_band(umigpu_ctx *parent, const umigpu_hot *hot);
 static int hot_collect(umigpu_ctx *ctx, u32 u0);
 
-static int hot_band(umigpu_ctx *ctx, const umigpu_hot *hot) {
-    Xchg *x = ctx->x;
+// child context of a rank: same configuration, its OWN stream and buffers (the band runs beside the rank's own neighbour
+// search, from a second host thread: both are chains of small kernels and scalar read-backs that leave the device idle half
+// of the time when run one after the other)
+static int hot_child(umigpu_ctx *ctx) {
+    if (ctx->hot) return UMIGPU_OK;
+    umigpu_config c = ctx->cfg;
+    c.stream = nullptr;
+    c.flags &= ~UMIGPU_FLAG_LABELS;
+    int rc = umigpu_create(&c, &ctx->hot);
+    if (rc) { ctx->err = g_last_error; return rc; }
+    ctx->hot->is_child = true;
+    return UMIGPU_OK;
+}
+
+// Runs on its own host thread.  Errors are recorded in the CHILD context (parent->hot->err); only the child's stream, the
+// exchange window's staging words [2], [3], [8..] and the polling stream are touched.
+static int hot_band(umigpu_ctx *parent, const umigpu_hot *hot) {
+    Xchg *x = parent->x;
+    umigpu_ctx *ctx = parent->hot;                    // CK / LAUNCH / fail below act on the child
+    umigpu_ctx *ch = ctx;
+    CK(cudaSetDevice(parent->cfg.device));
     const char *ow = x->peer[(size_t)hot->owner];
     const unsigned long long epoch = x->epoch;
-    int rc = xchg_poll(ctx, ow + offsetof(XchgHeader, ready), 8, [&](const unsigned long long *b) { return b[0] >= epoch; }, "the owner's hot bucket");
+    int rc = xchg_poll(x, ch, ow + offsetof(XchgHeader, ready), 8, [&](const unsigned long long *b) { return b[0] >= epoch; }, "the owner's hot bucket");
     if (rc) return rc;
-    rc = xchg_poll(ctx, ow + offsetof(XchgHeader, info), 8, [](const unsigned long long *) { return true; }, "the owner's header");
+    rc = xchg_poll(x, ch, ow + offsetof(XchgHeader, info), 8, [](const unsigned long long *) { return true; }, "the owner's header");
     if (rc) return rc;
     const unsigned long long info = x->h_pin[8];
-    if ((info >> 33) & 1ull) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "shard group: the owner (rank %d) could not publish the hot bucket", hot->owner);
+    if ((info >> 33) & 1ull) return fail(ch, UMIGPU_ERR_UNSUPPORTED, "shard group: the owner (rank %d) could not publish the hot bucket", hot->owner);
     const u32 uh = (u32)info;
     const bool has_n = ((info >> 32) & 1ull) != 0;
     const int narrow = (int)((info >> 34) & 1ull);
-    STAGE_BEGIN(UMIGPU_STAGE_HOT_BAND);
-    // child context: same configuration, this context's stream, its own buffers
-    if (!ctx->hot) {
-        umigpu_config c = ctx->cfg;
-        c.stream = (void *)ctx->stream;
-        c.flags &= ~UMIGPU_FLAG_LABELS;
-        rc = umigpu_create(&c, &ctx->hot);
-        if (rc) { ctx->err = g_last_error; return rc; }
-        ctx->hot->is_child = true;
-    }
-    umigpu_ctx *ch = ctx->hot;
     rc = umigpu_reset(ch);
-    if (rc) { ctx->err = ch->err; return rc; }
+    if (rc) return rc;
+    CK(cudaEventRecord(parent->ev[UMIGPU_STAGE_HOT_BAND][0], ch->stream));
     ch->ran = true;
     memset(&ch->ctr, 0, sizeof ch->ctr);
     ch->n_edges = 0;
     ch->skip_bucket = 0xffffffffu;
     ch->band = (u32)x->rank; ch->n_bands = (u32)x->n;
-    ch->lay = ctx->lay;
-    ch->lay.umi_len = (int)ctx->cfg.umi_len; ch->lay.has_n = has_n ? 1 : 0;
+    memset(&ch->lay, 0, sizeof ch->lay);
+    ch->lay.umi_len = (int)ch->cfg.umi_len; ch->lay.has_n = has_n ? 1 : 0;
+    ch->lay.umi_bits = (has_n ? 3 : 2) * ch->lay.umi_len;
     ch->n_unique = uh; ch->n_buckets = uh ? 1 : 0;
     u64 c_edges = 0;
     if (uh > 1 && !(uh <= SMALL_BUCKET && x->rank != 0)) {        // a bucket of <= 32 UMIs is one warp's work: rank 0 takes it
-#define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, UMIGPU_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
-        CKH(ch->d_planes.reserve((size_t)uh * 8)); CKH(ch->d_ucode.reserve((size_t)uh * 8)); CKH(ch->d_freq.reserve((size_t)uh * 4));
-        CKH(ch->d_thr.reserve((size_t)uh * 4)); CKH(ch->d_bstart.reserve(2 * 4)); CKH(ch->d_ubkt.reserve((size_t)uh * 4));
-        CKH(ch->d_umi2.reserve((size_t)uh * 8));                   // staging of the codes as they come over the link
-        if (has_n) CKH(ch->d_nplane.reserve((size_t)uh * 4));
-        cudaStream_t s = ctx->stream;
-        CKH(cudaMemcpyAsync(ch->d_umi2.p, ow + x->off_code, (size_t)uh * (narrow ? 4 : 8), cudaMemcpyDefault, s));
-        CKH(cudaMemcpyAsync(ch->d_freq.p, ow + x->off_freq, (size_t)uh * 4, cudaMemcpyDefault, s));
-        const umigpu_config &cf = ctx->cfg;
+        CK(ch->d_planes.reserve((size_t)uh * 8)); CK(ch->d_ucode.reserve((size_t)uh * 8)); CK(ch->d_freq.reserve((size_t)uh * 4));
+        CK(ch->d_thr.reserve((size_t)uh * 4)); CK(ch->d_bstart.reserve(2 * 4)); CK(ch->d_ubkt.reserve((size_t)uh * 4));
+        CK(ch->d_umi2.reserve((size_t)uh * 8));                   // staging of the codes as they come over the link
+        if (has_n) CK(ch->d_nplane.reserve((size_t)uh * 4));
+        cudaStream_t s = ch->stream;
+        CK(cudaMemcpyAsync(ch->d_umi2.p, ow + x->off_code, (size_t)uh * (narrow ? 4 : 8), cudaMemcpyDefault, s));
+        CK(cudaMemcpyAsync(ch->d_freq.p, ow + x->off_freq, (size_t)uh * 4, cudaMemcpyDefault, s));
+        const umigpu_config &cf = ch->cfg;
         const int inf_thr = (cf.algo == UMIGPU_ALGO_CC || cf.algo == UMIGPU_ALGO_ADJ_UPSTREAM) ? 1 : 0;
-        hot_child_expand_kernel<<<grid_for(uh, 256), 256, 0, s>>>(uh, (const void *)ch->d_umi2.p, narrow, (const i32 *)ch->d_freq.p, cf.percentage, inf_thr,
-                                                                   (int)cf.umi_len, has_n ? 1 : 0, ch->d_planes.as<uint2>(), ch->d_nplane.as<u32>(),
-                                                                   ch->d_ucode.as<u64>(), ch->d_thr.as<i32>(), ch->d_bstart.as<u32>(), ch->d_ubkt.as<u32>());
-        bucket_stats_kernel<<<1, 256, 0, s>>>(1, (const u32 *)ch->d_bstart.p, ch->d_sc.as<DevScalars>());
-        ctx->launches += 2;
-        CKH(cudaGetLastError());
-#undef CKH
+        LAUNCH(hot_child_expand_kernel, grid_for(uh, 256), 256, uh, (const void *)ch->d_umi2.p, narrow, (const i32 *)ch->d_freq.p, cf.percentage, inf_thr,
+               (int)cf.umi_len, has_n ? 1 : 0, ch->d_planes.as<uint2>(), ch->d_nplane.as<u32>(), ch->d_ucode.as<u64>(), ch->d_thr.as<i32>(),
+               ch->d_bstart.as<u32>(), ch->d_ubkt.as<u32>());
+        LAUNCH(bucket_stats_kernel, 1, 256, 1, (const u32 *)ch->d_bstart.p, ch->d_sc.as<DevScalars>());
         rc = stage_neighbours(ch, RUN_EDGES_ONLY);
-        if (rc) { ctx->err = ch->err; return rc; }
+        if (rc) return rc;
         c_edges = ch->n_edges;
-        ctx->launches += ch->launches; ch->launches = 0;
     }
     // put: edges into this rank's region of the owner's window, then the slot (count, then epoch)
     unsigned long long count = c_edges;
     char *inbox = const_cast<char *>(ow) + x->off_inbox + (size_t)x->rank * x->region * 8;
     if (c_edges > x->region) count |= 1ull << 63;
-    else if (c_edges) CK(cudaMemcpyAsync(inbox, ctx->hot->d_edges.p, (size_t)c_edges * 8, cudaMemcpyDefault, ctx->stream));
+    else if (c_edges) CK(cudaMemcpyAsync(inbox, ch->d_edges.p, (size_t)c_edges * 8, cudaMemcpyDefault, ch->stream));
     XDBG("rank %d epoch %llu: band done, %llu edges -> owner %d", x->rank, (unsigned long long)epoch, (unsigned long long)c_edges, hot->owner);
     x->h_pin[2] = count; x->h_pin[3] = epoch;
     char *slot = const_cast<char *>(ow) + offsetof(XchgHeader, slot) + (size_t)x->rank * sizeof(XchgSlot);
-    CK(cudaMemcpyAsync(slot + offsetof(XchgSlot, count), &x->h_pin[2], 8, cudaMemcpyDefault, ctx->stream));
-    CK(cudaMemcpyAsync(slot + offsetof(XchgSlot, epoch), &x->h_pin[3], 8, cudaMemcpyDefault, ctx->stream));
-    STAGE_END(UMIGPU_STAGE_HOT_BAND);
+    CK(cudaMemcpyAsync(slot + offsetof(XchgSlot, count), &x->h_pin[2], 8, cudaMemcpyDefault, ch->stream));
+    CK(cudaMemcpyAsync(slot + offsetof(XchgSlot, epoch), &x->h_pin[3], 8, cudaMemcpyDefault, ch->stream));
+    CK(cudaEventRecord(parent->ev[UMIGPU_STAGE_HOT_BAND][1], ch->stream));
+    parent->ev_ok[UMIGPU_STAGE_HOT_BAND] = true;
     return UMIGPU_OK;
 }
 
@@ -1961,7 +1966,7 @@ static int hot_collect(umigpu_ctx *ctx, u32 u0) {
     Xchg *x = ctx->x;
     const unsigned long long epoch = x->epoch;
     const int nr = x->n;
-    int rc = xchg_poll(ctx, x->local + offsetof(XchgHeader, slot), (size_t)nr * sizeof(XchgSlot),
+    int rc = xchg_poll(x, ctx, x->local + offsetof(XchgHeader, slot), (size_t)nr * sizeof(XchgSlot),
                        [&](const unsigned long long *b) { for (int r = 0; r < nr; r++) if (b[2 * r + 1] < epoch) return false; return true; },
                        "the edges of the other ranks");
     if (rc) return rc;
@@ -2016,11 +2021,21 @@ extern "C" int umigpu_run_sharded(umigpu_ctx *ctx, const umigpu_hot *hot, int64_
     const bool owner = hot_on && x->rank == hot->owner;
     if (hot_on) {
         x->epoch++;
+        rc = hot_child(ctx);
+        if (rc) return rc;
         if (owner) { rc = hot_publish(ctx, hot, &u0); if (rc) return rc; }
-        rc = hot_band(ctx, hot);
+        // this rank's band of the hot bucket beside its own neighbour search: two host threads, two streams
+        int band_rc = UMIGPU_OK;
+        std::thread band([&] { band_rc = hot_band(ctx, hot); });
+        if (n) rc = stage_neighbours(ctx, RUN_FULL);
+        band.join();
+        ctx->launches += ctx->hot->launches; ctx->hot->launches = 0;
+        if (band_rc) return fail(ctx, band_rc, "%s", ctx->hot->err.c_str());
+        if (rc) return rc;
+    } else if (n) {
+        rc = stage_neighbours(ctx, RUN_FULL);
         if (rc) return rc;
     }
-    if (n) { rc = stage_neighbours(ctx, RUN_FULL); if (rc) return rc; }
     if (owner) { rc = hot_collect(ctx, u0); if (rc) return rc; }
     if (hot_on && ctx->hot) {          // this rank's share of the hot bucket's search
         const umigpu_counters &h = ctx->hot->ctr;
