@@ -104,7 +104,7 @@ def test_plan_sorted_cuts_are_bucket_boundaries_and_balanced():
         assert cuts[hot.owner] <= r < cuts[hot.owner + 1]
         assert abs(int(hot.reads_est) - int(counts.max())) <= 0.1 * counts.max() + 8
         if N > 1:       # balanced up to the one bucket that cannot be cut (it may outweigh the fair share)
-            hot_cost = 0.21 * counts.max()
+            hot_cost = 0.27 * counts.max()
             assert cost.max() <= max(1.6 * cost.mean(), hot_cost + 1.3 * cost.mean()), (N, cost)
             assert (cost > 0).sum() >= min(N, 8) - 1, (N, cost)
     # no bucket big enough: nothing is split

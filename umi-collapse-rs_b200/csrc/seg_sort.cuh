@@ -28,6 +28,39 @@
 #define SEG_WIN_ITEMS (SEG_WIN / SEG_THREADS)   // 8
 #define SEG_POS_BITS 12               // position-in-window field of the composite
 #define SEG_NONE 0xffffffffu
+// Digit width of the segmented passes.  The passes are issue-bound on the ranking (one ballot per key bit), so what a wider
+// digit buys is not fewer ballots but fewer passes' worth of everything else: 25 bits of S = 3 passes of 9,8,8 instead of 4,
+// a window's 33 bits = 4 passes instead of 5 (round 1 measured a 9-bit pass 15 % dearer than an 8-bit one).
+#define SEG_RB 9
+#define SEG_RADIX (1 << SEG_RB)
+
+// rs_rank_tile (radix_sort.cuh) with the digit width as a template parameter.  packed[j] = digit | (rank within (warp, digit)
+// << RB), or 0xffffffff past the end.  On return whist[w][d] = number of keys with digit d in warp w's slice.
+template <int ITEMS, bool FULL, int RB>
+__device__ __forceinline__ void seg_rank_tile(u32 *packed, u32 (*whist)[1 << RB]) {
+    const u32 w = threadIdx.x >> 5, lane = lane_id();
+    for (u32 i = threadIdx.x; i < RS_WARPS * (1u << RB); i += SEG_THREADS) (&whist[0][0])[i] = 0;
+    __syncthreads();
+    const u32 lt = lanemask_lt();
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const u32 d = packed[j];
+        const bool active = FULL || d != 0xffffffffu;
+        u32 peers = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, active);
+#pragma unroll
+        for (int b = 0; b < RB; b++) {
+            const bool bit = (d & (1u << b)) != 0u;
+            const u32 m = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? m : ~m;
+        }
+        const u32 leader = active ? (u32)__ffs(peers) - 1u : lane;
+        u32 old = 0;
+        if (active && lane == leader) { old = whist[w][d]; whist[w][d] = old + __popc(peers); }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        if (active) packed[j] = d | ((old + __popc(peers & lt)) << RB);
+        __syncwarp();
+    }
+}
 
 struct SegBlock { u32 nheads, first, last, pad; };        // heads of segments that start in this block (positions), SEG_NONE = none
 struct SegBig { u32 start, len, tile0, pad; };            // a big segment and the index of its first tile
@@ -170,10 +203,11 @@ __global__ void __launch_bounds__(1024) seg_plan_kernel(const SegBlock *__restri
 
 // ---- small segments: one window per block, sorted in shared memory ----
 struct SegWinShared {
-    u32 whist[RS_WARPS][RS_RADIX];
-    u32 slocal[RS_RADIX];
+    u32 whist[RS_WARPS][SEG_RADIX];
+    u32 slocal[SEG_RADIX];
     u32 sscan[SEG_THREADS / 32 + 1];
 };
+static_assert(SEG_RADIX <= SEG_THREADS, "one thread per digit in the per-digit steps");
 
 // one LSD pass over the elements held in registers (slot e = warp * ITEMS * 32 + j * 32 + lane); result back in x[], in slot order
 template <int ITEMS>
@@ -185,21 +219,21 @@ __device__ __forceinline__ void seg_local_pass(u64 (&x)[ITEMS], u32 count, int s
         const u32 e = (w * ITEMS + j) * 32 + lane;
         packed[j] = e < count ? ((u32)(x[j] >> shift) & mask) : 0xffffffffu;
     }
-    rs_rank_tile<ITEMS, false>(packed, S.whist);
+    seg_rank_tile<ITEMS, false, SEG_RB>(packed, S.whist);
     __syncthreads();
     u32 total = 0;
-    if (threadIdx.x < RS_RADIX) {
+    if (threadIdx.x < SEG_RADIX) {
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ww++) { const u32 t = S.whist[ww][threadIdx.x]; S.whist[ww][threadIdx.x] = total; total += t; }
     }
     u32 tot_all;
     const u32 lstart = block_exclusive_scan<u32, SEG_THREADS>(total, S.sscan, &tot_all);
-    if (threadIdx.x < RS_RADIX) S.slocal[threadIdx.x] = lstart;
+    if (threadIdx.x < SEG_RADIX) S.slocal[threadIdx.x] = lstart;
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         if (packed[j] != 0xffffffffu) {
-            const u32 d = packed[j] & (RS_RADIX - 1), r = packed[j] >> RS_RB;
+            const u32 d = packed[j] & (SEG_RADIX - 1), r = packed[j] >> SEG_RB;
             sbuf[S.slocal[d] + S.whist[w][d] + r] = x[j];
         }
     }
@@ -227,9 +261,12 @@ __device__ __forceinline__ void seg_window_body(SegWinShared &S, u64 *sbuf, cons
     }
     __syncthreads();
     const int bits = sbits + segbits;
-    for (int done = 0; done < bits; done += RS_RB) {
-        const int b = min(RS_RB, bits - done);
+    // bits spread evenly over the passes (33 bits -> 9,8,8,8)
+    const int npass = (bits + SEG_RB - 1) / SEG_RB;
+    for (int p = 0, done = 0; p < npass; p++) {
+        const int b = (bits - done + (npass - p) - 1) / (npass - p);
         seg_local_pass<ITEMS>(x, count, SEG_POS_BITS + done, (1u << b) - 1u, S, sbuf);
+        done += b;
     }
     // slot e now holds the element of sorted position lo + e; P comes from the (unsorted) input at the same position
 #pragma unroll
@@ -297,7 +334,7 @@ __global__ void __launch_bounds__(SEG_THREADS, 2) seg_window_sort_kernel(const u
 // the bits of S spread evenly over the passes (25 bits -> 7,6,6,6: a pass of one leftover bit would cost a full pass)
 struct SegPasses { int npass; int shift[SEG_MAX_PASSES]; int bits[SEG_MAX_PASSES]; };
 static inline SegPasses seg_passes(int sbits) {
-    SegPasses sp; sp.npass = (sbits + RS_RB - 1) / RS_RB;
+    SegPasses sp; sp.npass = (sbits + SEG_RB - 1) / SEG_RB;
     int done = 0;
     for (int i = 0; i < sp.npass; i++) { const int b = (sbits - done + (sp.npass - i) - 1) / (sp.npass - i); sp.shift[i] = done; sp.bits[i] = b; done += b; }
     return sp;
@@ -313,33 +350,33 @@ __device__ __forceinline__ u32 seg_find_big(const SegBig *__restrict__ big, u32 
 __global__ void __launch_bounds__(SEG_THREADS) seg_hist_kernel(const u64 *__restrict__ key_in, int sbits, SegPasses sp, const SegBig *__restrict__ big,
                                                                u32 n_big, u32 n_tiles, u32 *__restrict__ hist) {
     const int npass = sp.npass;
-    __shared__ u32 sh[SEG_MAX_PASSES * RS_RADIX];
+    __shared__ u32 sh[SEG_MAX_PASSES * SEG_RADIX];
     __shared__ u32 s_seg;
     for (u32 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();
         if (threadIdx.x == 0) s_seg = seg_find_big(big, n_big, tile);
-        for (u32 i = threadIdx.x; i < (u32)npass * RS_RADIX; i += SEG_THREADS) sh[i] = 0;
+        for (u32 i = threadIdx.x; i < (u32)npass * SEG_RADIX; i += SEG_THREADS) sh[i] = 0;
         __syncthreads();
         const SegBig sg = big[s_seg];
         const u32 off = (tile - sg.tile0) * SEG_TILE, cnt = min((u32)SEG_TILE, sg.len - off);
         const u64 smask = (1ull << sbits) - 1;
         for (u32 e = threadIdx.x; e < cnt; e += SEG_THREADS) {
             const u64 s = key_in[(u64)sg.start + off + e] & smask;
-            for (int p = 0; p < npass; p++) atomicAdd(&sh[p * RS_RADIX + ((u32)(s >> sp.shift[p]) & ((1u << sp.bits[p]) - 1u))], 1u);
+            for (int p = 0; p < npass; p++) atomicAdd(&sh[p * SEG_RADIX + ((u32)(s >> sp.shift[p]) & ((1u << sp.bits[p]) - 1u))], 1u);
         }
         __syncthreads();
-        for (u32 i = threadIdx.x; i < (u32)npass * RS_RADIX; i += SEG_THREADS)
-            if (sh[i]) atomicAdd(&hist[(u64)s_seg * npass * RS_RADIX + i], sh[i]);
+        for (u32 i = threadIdx.x; i < (u32)npass * SEG_RADIX; i += SEG_THREADS)
+            if (sh[i]) atomicAdd(&hist[(u64)s_seg * npass * SEG_RADIX + i], sh[i]);
     }
 }
-// exclusive scan of each (segment, pass) histogram: one CTA of RS_RADIX threads per row
-__global__ void __launch_bounds__(RS_RADIX) seg_digit_starts_kernel(u32 *hist, u32 n_rows) {
-    __shared__ u32 sm[RS_RADIX / 32 + 1];
+// exclusive scan of each (segment, pass) histogram: one CTA of SEG_RADIX threads per row
+__global__ void __launch_bounds__(SEG_RADIX) seg_digit_starts_kernel(u32 *hist, u32 n_rows) {
+    __shared__ u32 sm[SEG_RADIX / 32 + 1];
     for (u32 row = blockIdx.x; row < n_rows; row += gridDim.x) {
-        const u32 v = hist[(u64)row * RS_RADIX + threadIdx.x];
+        const u32 v = hist[(u64)row * SEG_RADIX + threadIdx.x];
         u32 tot;
-        const u32 ex = block_exclusive_scan<u32, RS_RADIX>(v, sm, &tot);
-        hist[(u64)row * RS_RADIX + threadIdx.x] = ex;
+        const u32 ex = block_exclusive_scan<u32, SEG_RADIX>(v, sm, &tot);
+        hist[(u64)row * SEG_RADIX + threadIdx.x] = ex;
     }
 }
 
@@ -350,8 +387,14 @@ struct SegPassArgs {
     int sbits, ib, pass; SegPasses sp;
     const SegBig *big; u32 n_big, n_tiles; const u32 *hist; unsigned long long *tile_state; u32 *ticket, *err;
 };
+struct SegShared {
+    u32 whist[RS_WARPS][SEG_RADIX];
+    u32 sbase[SEG_RADIX], slocal[SEG_RADIX];
+    u32 sscan[SEG_THREADS / 32 + 1];
+    u32 s_tile;
+};
 template <int ITEMS, bool FULL>
-__device__ __forceinline__ void seg_onesweep_body(const SegPassArgs &a, RsShared &S, u64 *selem, u32 tile, u32 seg_i, const SegBig sg, u32 off, u32 tile_count) {
+__device__ __forceinline__ void seg_onesweep_body(const SegPassArgs &a, SegShared &S, u64 *selem, u32 tile, u32 seg_i, const SegBig sg, u32 off, u32 tile_count) {
     constexpr u32 TILE = SEG_THREADS * ITEMS;
     const u64 tile_base = (u64)sg.start + off;
     const int npass = a.sp.npass, pass = a.pass, ib = a.ib;
@@ -359,8 +402,8 @@ __device__ __forceinline__ void seg_onesweep_body(const SegPassArgs &a, RsShared
     const u64 smask = (1ull << a.sbits) - 1;
     const int sh = ib + a.sp.shift[pass];
     const u32 mask = (1u << a.sp.bits[pass]) - 1u;
-    const u32 *digit_start = a.hist + ((u64)seg_i * npass + pass) * RS_RADIX;
-    u32 (*whist)[RS_RADIX] = S.whist;
+    const u32 *digit_start = a.hist + ((u64)seg_i * npass + pass) * SEG_RADIX;
+    u32 (*whist)[SEG_RADIX] = S.whist;
     u32 *sbase = S.sbase, *slocal = S.slocal, *sscan = S.sscan;
     const u32 w = threadIdx.x >> 5, lane = lane_id();
     u64 x[ITEMS];
@@ -376,29 +419,29 @@ __device__ __forceinline__ void seg_onesweep_body(const SegPassArgs &a, RsShared
         const u32 e = (w * ITEMS + j) * 32 + lane;
         packed[j] = (FULL || e < tile_count) ? ((u32)(x[j] >> sh) & mask) : 0xffffffffu;
     }
-    rs_rank_tile<ITEMS, FULL>(packed, whist);
+    seg_rank_tile<ITEMS, FULL, SEG_RB>(packed, whist);
     __syncthreads();
     u32 total = 0;
-    if (threadIdx.x < RS_RADIX) {
+    if (threadIdx.x < SEG_RADIX) {
         const u32 d = threadIdx.x;
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ww++) { const u32 t = whist[ww][d]; whist[ww][d] = total; total += t; }
-        atomicExch(a.tile_state + (u64)tile * RS_RADIX + d, (tile == sg.tile0 ? RS_FLAG_PREFIX : RS_FLAG_AGG) | (unsigned long long)total);
+        atomicExch(a.tile_state + (u64)tile * SEG_RADIX + d, (tile == sg.tile0 ? RS_FLAG_PREFIX : RS_FLAG_AGG) | (unsigned long long)total);
     }
     u32 tot_all;
     const u32 lstart = block_exclusive_scan<u32, SEG_THREADS>(total, sscan, &tot_all);
-    if (threadIdx.x < RS_RADIX) slocal[threadIdx.x] = lstart;
+    if (threadIdx.x < SEG_RADIX) slocal[threadIdx.x] = lstart;
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         if (FULL || packed[j] != 0xffffffffu) {
-            const u32 d = packed[j] & (RS_RADIX - 1), r = packed[j] >> RS_RB;
+            const u32 d = packed[j] & (SEG_RADIX - 1), r = packed[j] >> SEG_RB;
             selem[slocal[d] + whist[w][d] + r] = x[j];
         }
     }
-    if (threadIdx.x < RS_RADIX) {
+    if (threadIdx.x < SEG_RADIX) {
         const u32 d = threadIdx.x;
-        unsigned long long *mine = a.tile_state + (u64)tile * RS_RADIX + d;
+        unsigned long long *mine = a.tile_state + (u64)tile * SEG_RADIX + d;
         u64 excl = 0;
         if (tile != sg.tile0) {
             u32 p = tile;                      // predecessors [tile0, p) of this segment are still to be accounted for
@@ -408,7 +451,7 @@ __device__ __forceinline__ void seg_onesweep_body(const SegPassArgs &a, RsShared
                 unsigned long long v[RS_LB];
 #pragma unroll
                 for (int i = 0; i < RS_LB; i++) {
-                    const volatile unsigned long long *prev = a.tile_state + (u64)(p > sg.tile0 + (u32)i ? p - 1 - i : sg.tile0) * RS_RADIX + d;
+                    const volatile unsigned long long *prev = a.tile_state + (u64)(p > sg.tile0 + (u32)i ? p - 1 - i : sg.tile0) * SEG_RADIX + d;
                     v[i] = *prev;
                 }
 #pragma unroll
@@ -449,7 +492,7 @@ __global__ void __launch_bounds__(SEG_THREADS, 2) seg_onesweep(SegPassArgs a) {
     constexpr u32 TILE = SEG_THREADS * ITEMS;
     extern __shared__ __align__(16) unsigned char seg_dyn[];            // u64 selem[TILE]
     u64 *selem = reinterpret_cast<u64 *>(seg_dyn);
-    __shared__ RsShared S;
+    __shared__ SegShared S;
     __shared__ u32 s_seg;
     if (threadIdx.x == 0) { const u32 t = atomicAdd(a.ticket, 1u); S.s_tile = t; s_seg = t < a.n_tiles ? seg_find_big(a.big, a.n_big, t) : 0u; }
     __syncthreads();

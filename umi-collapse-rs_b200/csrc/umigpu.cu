@@ -561,18 +561,18 @@ static int run_sort_presorted(umigpu_ctx *ctx, u64 n, const KeyLayout &lay, bool
         const SegPasses sp = seg_passes(sbits);
         const int npass = sp.npass;
         if (npass > SEG_MAX_PASSES) return fail(ctx, UMIGPU_ERR_STATE, "internal: segmented sort with %d passes", npass);
-        const size_t hist_bytes = (size_t)n_big * npass * RS_RADIX * 4;
+        const size_t hist_bytes = (size_t)n_big * npass * SEG_RADIX * 4;
         CK(ctx->d_seghist.reserve(hist_bytes));
-        CK(ctx->d_tilestate.reserve((size_t)n_tiles * RS_RADIX * 8));
+        CK(ctx->d_tilestate.reserve((size_t)n_tiles * SEG_RADIX * 8));
         if (npass > 1) { CK(ctx->d_wbuf[0].reserve(n * 8)); if (npass > 2) CK(ctx->d_wbuf[1].reserve(n * 8)); }
         CK(cudaMemsetAsync(ctx->d_seghist.p, 0, hist_bytes, ctx->stream));
         CK(cudaMemsetAsync(&sc->sort_err, 0, 4, ctx->stream));
         const SegBig *big = (const SegBig *)ctx->d_segbig.p;
         LAUNCH(seg_hist_kernel, std::min<u32>(n_tiles, (u32)ctx->num_sms * 4), SEG_THREADS, key_in, sbits, sp, big, n_big, n_tiles, ctx->d_seghist.as<u32>());
-        LAUNCH(seg_digit_starts_kernel, std::min<u32>(n_big * (u32)npass, (u32)ctx->num_sms * 8), RS_RADIX, ctx->d_seghist.as<u32>(), n_big * (u32)npass);
+        LAUNCH(seg_digit_starts_kernel, std::min<u32>(n_big * (u32)npass, (u32)ctx->num_sms * 8), SEG_RADIX, ctx->d_seghist.as<u32>(), n_big * (u32)npass);
         int wcur = 0;
         for (int p = 0; p < npass; p++) {
-            CK(cudaMemsetAsync(ctx->d_tilestate.p, 0, (size_t)n_tiles * RS_RADIX * 8, ctx->stream));
+            CK(cudaMemsetAsync(ctx->d_tilestate.p, 0, (size_t)n_tiles * SEG_RADIX * 8, ctx->stream));
             CK(cudaMemsetAsync(&sc->sort_ticket, 0, 4, ctx->stream));
             const u64 *w_in = p == 0 ? nullptr : ctx->d_wbuf[wcur].as<u64>();
             u64 *w_out = p == npass - 1 ? nullptr : ctx->d_wbuf[p == 0 ? 0 : wcur ^ 1].as<u64>();
@@ -1127,11 +1127,12 @@ static int stage_cluster(umigpu_ctx *ctx) {
         CK(ctx->d_cedges.reserve(std::max<u64>(n_edges, 1) * sizeof(uint2)));
         CK(cudaMemsetAsync(&sc->scratch, 0, 8, ctx->stream));
         unsigned long long *n_c = (unsigned long long *)&sc->scratch;
-        LAUNCH(contract_edges_kernel, egrid, 256, edges, n_edges, (const u32 *)comp, ctx->d_cedges.as<uint2>(), n_c);
-        sweeps += 1;
-        // Phase B on the contracted list (its length stays on the device); stamps restart: every contracted edge is relaxed once
+        // Phase B on the contracted list (its length stays on the device); stamps restart, and the contraction itself does the
+        // first relaxation (sweep 1)
         CK(cudaMemsetAsync(ctx->d_stamp.p, 0, (size_t)U * 4, ctx->stream));
-        sweep_no = 0;
+        LAUNCH(contract_edges_kernel, egrid, 256, edges, n_edges, (const u32 *)comp, ctx->d_cedges.as<uint2>(), n_c, label, stamp, sc);
+        sweeps += 1;
+        sweep_no = 1;
         rc = sweep_batches(ctx->d_cedges.as<uint2>(), n_edges, n_c, -1, false);
         if (rc) return rc;
         LAUNCH(expand_labels_kernel, grid_for(U, 256), 256, U, (const u32 *)comp, label);
@@ -2066,7 +2067,9 @@ extern "C" int umigpu_shard_plan_sorted(uint64_t n, const int32_t *tid, const in
     for (int s = 0; s <= n_shards; s++) { cuts[s] = s == n_shards ? n : 0; cut_keys[s] = s == 0 ? INT64_MIN : INT64_MAX; }
     if (shard_cost) for (int s = 0; s < n_shards; s++) shard_cost[s] = 0.0;
     if (n == 0) return UMIGPU_OK;
-    const double A = 0.11, C2 = 1e-8, C1 = 0.10;
+    // C1H: the split bucket's owner sits on the group's critical path (every rank's band waits for its K1-K3, its clustering
+    // waits for every rank's band), so the model charges it enough that it receives little besides the bucket itself
+    const double A = 0.11, C2 = 1e-8, C1 = 0.10, C1H = 0.16;
     const u64 m = std::min<u64>(n, 65536);
     const double per = (double)n / (double)m;
     struct Unit { u64 first_sample; double reads, cost; i64 key; bool run; };
@@ -2101,7 +2104,7 @@ extern "C" int umigpu_shard_plan_sorted(uint64_t n, const int32_t *tid, const in
     double total = 0.0;
     for (Unit &u : units) {
         u.cost = A * u.reads;
-        if (u.run) u.cost += (have_hot && u.key == hot_key) ? C1 * u.reads : C2 * u.reads * u.reads + C1 * u.reads;
+        if (u.run) u.cost += (have_hot && u.key == hot_key) ? C1H * u.reads : C2 * u.reads * u.reads + C1 * u.reads;
         total += u.cost;
     }
     // greedy prefix partition over the units; a cut lands on the first read of a unit's key
