@@ -157,20 +157,13 @@ __global__ void __launch_bounds__(256) uf_flatten_kernel(u32 n_unique, u32 *pare
 // (most edges of a hot locus) disappear.  Phase B then touches only this list: no per-sweep comp gathers, no pass over
 // all U labels.  *n_out is a device-resident count that the sweeps read (no host round trip).
 __global__ void __launch_bounds__(256) contract_edges_kernel(const uint2 *__restrict__ edges, u64 n_edges, const u32 *__restrict__ comp,
-                                                             uint2 *__restrict__ out, unsigned long long *n_out, unsigned long long *label,
-                                                             u32 *stamp, DevScalars *sc) {
+                                                             uint2 *__restrict__ out, unsigned long long *n_out) {
     const u64 stride = (u64)gridDim.x * 256;
     const u64 rounds = (n_edges + stride - 1) / stride;          // every lane runs the same number of rounds (warp collectives)
-    u32 any = 0;
     for (u64 it = 0; it < rounds; it++) {
         const u64 e = it * stride + (u64)blockIdx.x * 256 + threadIdx.x;
         bool live = false; u32 cs = 0, cd = 0;
         if (e < n_edges) { const uint2 ed = edges[e]; cs = comp[ed.x]; cd = comp[ed.y]; live = cs != cd; }
-        // the first relaxation of Phase B rides along (the roots are in hand): one full sweep less afterwards
-        if (live) {
-            const unsigned long long ls = label[cs];
-            if (ls < label[cd]) { atomicMin(&label[cd], ls); stamp[cd] = 1u; any = 1; }
-        }
         const u32 m = __ballot_sync(0xffffffffu, live);
         if (m) {
             unsigned long long base = 0;
@@ -179,7 +172,6 @@ __global__ void __launch_bounds__(256) contract_edges_kernel(const uint2 *__rest
             if (live) out[base + __popc(m & lanemask_lt())] = make_uint2(cs, cd);
         }
     }
-    if (__any_sync(0xffffffffu, any != 0) && lane_id() == 0) sc->changed = 1;
 }
 __global__ void __launch_bounds__(256) expand_labels_kernel(u32 n_unique, const u32 *__restrict__ comp, unsigned long long *label) {
     u32 v = blockIdx.x * 256 + threadIdx.x;

@@ -31,8 +31,10 @@
 // Digit width of the segmented passes.  The passes are issue-bound on the ranking (one ballot per key bit), so what a wider
 // digit buys is not fewer ballots but fewer passes' worth of everything else: 25 bits of S = 3 passes of 9,8,8 instead of 4,
 // a window's 33 bits = 4 passes instead of 5 (round 1 measured a 9-bit pass 15 % dearer than an 8-bit one).
-#define SEG_RB 9
+#define SEG_RB 9                      // widest digit; tables are laid out for it
 #define SEG_RADIX (1 << SEG_RB)
+// 9-bit digits only where they save a pass (25 bits: 3 instead of 4; 40 bits: 5 either way -> 8-bit digits)
+static __host__ __device__ __forceinline__ int seg_pick_rb(int bits) { return (bits + 8) / 9 < (bits + 7) / 8 ? 9 : 8; }
 
 // rs_rank_tile (radix_sort.cuh) with the digit width as a template parameter.  packed[j] = digit | (rank within (warp, digit)
 // << RB), or 0xffffffff past the end.  On return whist[w][d] = number of keys with digit d in warp w's slice.
@@ -210,8 +212,10 @@ struct SegWinShared {
 static_assert(SEG_RADIX <= SEG_THREADS, "one thread per digit in the per-digit steps");
 
 // one LSD pass over the elements held in registers (slot e = warp * ITEMS * 32 + j * 32 + lane); result back in x[], in slot order
-template <int ITEMS>
+template <int ITEMS, int RB>
 __device__ __forceinline__ void seg_local_pass(u64 (&x)[ITEMS], u32 count, int shift, u32 mask, SegWinShared &S, u64 *sbuf) {
+    constexpr u32 RADIX = 1u << RB;
+    u32 (*whist)[RADIX] = reinterpret_cast<u32 (*)[RADIX]>(&S.whist[0][0]);
     const u32 w = threadIdx.x >> 5, lane = lane_id();
     u32 packed[ITEMS];
 #pragma unroll
@@ -219,22 +223,22 @@ __device__ __forceinline__ void seg_local_pass(u64 (&x)[ITEMS], u32 count, int s
         const u32 e = (w * ITEMS + j) * 32 + lane;
         packed[j] = e < count ? ((u32)(x[j] >> shift) & mask) : 0xffffffffu;
     }
-    seg_rank_tile<ITEMS, false, SEG_RB>(packed, S.whist);
+    seg_rank_tile<ITEMS, false, RB>(packed, whist);
     __syncthreads();
     u32 total = 0;
-    if (threadIdx.x < SEG_RADIX) {
+    if (threadIdx.x < RADIX) {
 #pragma unroll
-        for (int ww = 0; ww < RS_WARPS; ww++) { const u32 t = S.whist[ww][threadIdx.x]; S.whist[ww][threadIdx.x] = total; total += t; }
+        for (int ww = 0; ww < RS_WARPS; ww++) { const u32 t = whist[ww][threadIdx.x]; whist[ww][threadIdx.x] = total; total += t; }
     }
     u32 tot_all;
     const u32 lstart = block_exclusive_scan<u32, SEG_THREADS>(total, S.sscan, &tot_all);
-    if (threadIdx.x < SEG_RADIX) S.slocal[threadIdx.x] = lstart;
+    if (threadIdx.x < RADIX) S.slocal[threadIdx.x] = lstart;
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         if (packed[j] != 0xffffffffu) {
-            const u32 d = packed[j] & (SEG_RADIX - 1), r = packed[j] >> SEG_RB;
-            sbuf[S.slocal[d] + S.whist[w][d] + r] = x[j];
+            const u32 d = packed[j] & (RADIX - 1), r = packed[j] >> RB;
+            sbuf[S.slocal[d] + whist[w][d] + r] = x[j];
         }
     }
     __syncthreads();
@@ -248,7 +252,7 @@ __device__ __forceinline__ void seg_local_pass(u64 (&x)[ITEMS], u32 count, int s
 
 // Windows are mostly far from full (a block whose tail lies inside a big segment, sparse loci): the element count picks how many
 // slots a thread owns (1, 2, 4 or 8), so a window of 500 reads ranks 512 slots per pass, not 4096.
-template <int ITEMS>
+template <int ITEMS, int RB>
 __device__ __forceinline__ void seg_window_body(SegWinShared &S, u64 *sbuf, const u64 *__restrict__ key_in, u32 lo, u32 count, int sbits, int segbits,
                                                 u64 *__restrict__ key_out, u32 *__restrict__ idx_out) {
     const u64 smask = (1ull << sbits) - 1;
@@ -262,10 +266,10 @@ __device__ __forceinline__ void seg_window_body(SegWinShared &S, u64 *sbuf, cons
     __syncthreads();
     const int bits = sbits + segbits;
     // bits spread evenly over the passes (33 bits -> 9,8,8,8)
-    const int npass = (bits + SEG_RB - 1) / SEG_RB;
+    const int npass = (bits + RB - 1) / RB;
     for (int p = 0, done = 0; p < npass; p++) {
         const int b = (bits - done + (npass - p) - 1) / (npass - p);
-        seg_local_pass<ITEMS>(x, count, SEG_POS_BITS + done, (1u << b) - 1u, S, sbuf);
+        seg_local_pass<ITEMS, RB>(x, count, SEG_POS_BITS + done, (1u << b) - 1u, S, sbuf);
         done += b;
     }
     // slot e now holds the element of sorted position lo + e; P comes from the (unsorted) input at the same position
@@ -321,10 +325,14 @@ __global__ void __launch_bounds__(SEG_THREADS, 2) seg_window_sort_kernel(const u
     __syncthreads();
     int segbits = 0;
     while ((nseg_m1 >> segbits) != 0) segbits++;
-    if (count <= SEG_THREADS)          seg_window_body<1>(S, sbuf, key_in, lo, count, sbits, segbits, key_out, idx_out);
-    else if (count <= 2 * SEG_THREADS) seg_window_body<2>(S, sbuf, key_in, lo, count, sbits, segbits, key_out, idx_out);
-    else if (count <= 4 * SEG_THREADS) seg_window_body<4>(S, sbuf, key_in, lo, count, sbits, segbits, key_out, idx_out);
-    else                               seg_window_body<8>(S, sbuf, key_in, lo, count, sbits, segbits, key_out, idx_out);
+#define SEG_WIN_GO(IT) do { if (rb9) seg_window_body<IT, 9>(S, sbuf, key_in, lo, count, sbits, segbits, key_out, idx_out); \
+                            else     seg_window_body<IT, 8>(S, sbuf, key_in, lo, count, sbits, segbits, key_out, idx_out); } while (0)
+    const bool rb9 = seg_pick_rb(sbits + segbits) == 9;
+    if (count <= SEG_THREADS)          SEG_WIN_GO(1);
+    else if (count <= 2 * SEG_THREADS) SEG_WIN_GO(2);
+    else if (count <= 4 * SEG_THREADS) SEG_WIN_GO(4);
+    else                               SEG_WIN_GO(8);
+#undef SEG_WIN_GO
 }
 
 // ---- big segments: batched one-sweep passes over S ----
@@ -332,9 +340,9 @@ __global__ void __launch_bounds__(SEG_THREADS, 2) seg_window_sort_kernel(const u
 #define SEG_TILE (SEG_THREADS * SEG_ITEMS)     // 6144
 #define SEG_MAX_PASSES 6
 // the bits of S spread evenly over the passes (25 bits -> 7,6,6,6: a pass of one leftover bit would cost a full pass)
-struct SegPasses { int npass; int shift[SEG_MAX_PASSES]; int bits[SEG_MAX_PASSES]; };
+struct SegPasses { int npass, rb; int shift[SEG_MAX_PASSES]; int bits[SEG_MAX_PASSES]; };
 static inline SegPasses seg_passes(int sbits) {
-    SegPasses sp; sp.npass = (sbits + SEG_RB - 1) / SEG_RB;
+    SegPasses sp; sp.rb = seg_pick_rb(sbits); sp.npass = (sbits + sp.rb - 1) / sp.rb;
     int done = 0;
     for (int i = 0; i < sp.npass; i++) { const int b = (sbits - done + (sp.npass - i) - 1) / (sp.npass - i); sp.shift[i] = done; sp.bits[i] = b; done += b; }
     return sp;
@@ -393,7 +401,7 @@ struct SegShared {
     u32 sscan[SEG_THREADS / 32 + 1];
     u32 s_tile;
 };
-template <int ITEMS, bool FULL>
+template <int ITEMS, bool FULL, int RB>
 __device__ __forceinline__ void seg_onesweep_body(const SegPassArgs &a, SegShared &S, u64 *selem, u32 tile, u32 seg_i, const SegBig sg, u32 off, u32 tile_count) {
     constexpr u32 TILE = SEG_THREADS * ITEMS;
     const u64 tile_base = (u64)sg.start + off;
@@ -403,7 +411,8 @@ __device__ __forceinline__ void seg_onesweep_body(const SegPassArgs &a, SegShare
     const int sh = ib + a.sp.shift[pass];
     const u32 mask = (1u << a.sp.bits[pass]) - 1u;
     const u32 *digit_start = a.hist + ((u64)seg_i * npass + pass) * SEG_RADIX;
-    u32 (*whist)[SEG_RADIX] = S.whist;
+    constexpr u32 RADIX = 1u << RB;                           // digits of this build; table rows stay SEG_RADIX wide
+    u32 (*whist)[RADIX] = reinterpret_cast<u32 (*)[RADIX]>(&S.whist[0][0]);
     u32 *sbase = S.sbase, *slocal = S.slocal, *sscan = S.sscan;
     const u32 w = threadIdx.x >> 5, lane = lane_id();
     u64 x[ITEMS];
@@ -419,10 +428,10 @@ __device__ __forceinline__ void seg_onesweep_body(const SegPassArgs &a, SegShare
         const u32 e = (w * ITEMS + j) * 32 + lane;
         packed[j] = (FULL || e < tile_count) ? ((u32)(x[j] >> sh) & mask) : 0xffffffffu;
     }
-    seg_rank_tile<ITEMS, FULL, SEG_RB>(packed, whist);
+    seg_rank_tile<ITEMS, FULL, RB>(packed, whist);
     __syncthreads();
     u32 total = 0;
-    if (threadIdx.x < SEG_RADIX) {
+    if (threadIdx.x < RADIX) {
         const u32 d = threadIdx.x;
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ww++) { const u32 t = whist[ww][d]; whist[ww][d] = total; total += t; }
@@ -430,16 +439,16 @@ __device__ __forceinline__ void seg_onesweep_body(const SegPassArgs &a, SegShare
     }
     u32 tot_all;
     const u32 lstart = block_exclusive_scan<u32, SEG_THREADS>(total, sscan, &tot_all);
-    if (threadIdx.x < SEG_RADIX) slocal[threadIdx.x] = lstart;
+    if (threadIdx.x < RADIX) slocal[threadIdx.x] = lstart;
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         if (FULL || packed[j] != 0xffffffffu) {
-            const u32 d = packed[j] & (SEG_RADIX - 1), r = packed[j] >> SEG_RB;
+            const u32 d = packed[j] & (RADIX - 1), r = packed[j] >> RB;
             selem[slocal[d] + whist[w][d] + r] = x[j];
         }
     }
-    if (threadIdx.x < SEG_RADIX) {
+    if (threadIdx.x < RADIX) {
         const u32 d = threadIdx.x;
         unsigned long long *mine = a.tile_state + (u64)tile * SEG_RADIX + d;
         u64 excl = 0;
@@ -487,7 +496,7 @@ __device__ __forceinline__ void seg_onesweep_body(const SegPassArgs &a, SegShare
     }
 }
 
-template <int ITEMS>
+template <int ITEMS, int RB>
 __global__ void __launch_bounds__(SEG_THREADS, 2) seg_onesweep(SegPassArgs a) {
     constexpr u32 TILE = SEG_THREADS * ITEMS;
     extern __shared__ __align__(16) unsigned char seg_dyn[];            // u64 selem[TILE]
@@ -501,6 +510,6 @@ __global__ void __launch_bounds__(SEG_THREADS, 2) seg_onesweep(SegPassArgs a) {
     const u32 seg_i = s_seg;
     const SegBig sg = a.big[seg_i];
     const u32 off = (tile - sg.tile0) * TILE, tile_count = min(TILE, sg.len - off);
-    if (tile_count == TILE) seg_onesweep_body<ITEMS, true>(a, S, selem, tile, seg_i, sg, off, tile_count);
-    else                    seg_onesweep_body<ITEMS, false>(a, S, selem, tile, seg_i, sg, off, tile_count);
+    if (tile_count == TILE) seg_onesweep_body<ITEMS, true, RB>(a, S, selem, tile, seg_i, sg, off, tile_count);
+    else                    seg_onesweep_body<ITEMS, false, RB>(a, S, selem, tile, seg_i, sg, off, tile_count);
 }

@@ -578,7 +578,8 @@ static int run_sort_presorted(umigpu_ctx *ctx, u64 n, const KeyLayout &lay, bool
             u64 *w_out = p == npass - 1 ? nullptr : ctx->d_wbuf[p == 0 ? 0 : wcur ^ 1].as<u64>();
             SegPassArgs pa{key_in, w_in, w_out, key_out, idx_out, sbits, ib, p, sp, big, n_big, n_tiles, (const u32 *)ctx->d_seghist.p,
                            ctx->d_tilestate.as<unsigned long long>(), &sc->sort_ticket, &sc->sort_err};
-            LAUNCH_SMEM((seg_onesweep<SEG_ITEMS>), n_tiles, SEG_THREADS, (size_t)SEG_TILE * 8, pa);
+            if (sp.rb == 9) LAUNCH_SMEM((seg_onesweep<SEG_ITEMS, 9>), n_tiles, SEG_THREADS, (size_t)SEG_TILE * 8, pa);
+            else            LAUNCH_SMEM((seg_onesweep<SEG_ITEMS, 8>), n_tiles, SEG_THREADS, (size_t)SEG_TILE * 8, pa);
             if (p > 0) wcur ^= 1;
         }
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
@@ -1127,12 +1128,13 @@ static int stage_cluster(umigpu_ctx *ctx) {
         CK(ctx->d_cedges.reserve(std::max<u64>(n_edges, 1) * sizeof(uint2)));
         CK(cudaMemsetAsync(&sc->scratch, 0, 8, ctx->stream));
         unsigned long long *n_c = (unsigned long long *)&sc->scratch;
-        // Phase B on the contracted list (its length stays on the device); stamps restart, and the contraction itself does the
-        // first relaxation (sweep 1)
-        CK(cudaMemsetAsync(ctx->d_stamp.p, 0, (size_t)U * 4, ctx->stream));
-        LAUNCH(contract_edges_kernel, egrid, 256, edges, n_edges, (const u32 *)comp, ctx->d_cedges.as<uint2>(), n_c, label, stamp, sc);
+        LAUNCH(contract_edges_kernel, egrid, 256, edges, n_edges, (const u32 *)comp, ctx->d_cedges.as<uint2>(), n_c);
         sweeps += 1;
-        sweep_no = 1;
+        // Phase B on the contracted list (its length stays on the device); stamps restart: every contracted edge is relaxed once.
+        // (Folding the first relaxation into the contraction kernel was tried: the sweeps run in batches of four with one
+        // read-back, so it saved no batch and made the contraction 0.5 ms slower on C5.)
+        CK(cudaMemsetAsync(ctx->d_stamp.p, 0, (size_t)U * 4, ctx->stream));
+        sweep_no = 0;
         rc = sweep_batches(ctx->d_cedges.as<uint2>(), n_edges, n_c, -1, false);
         if (rc) return rc;
         LAUNCH(expand_labels_kernel, grid_for(U, 256), 256, U, (const u32 *)comp, label);
