@@ -55,6 +55,21 @@ def test_group_hot_bucket_split_matches_oracle(hot_env):
                 assert ctr["max_umis"] == octr["max_umis"]
 
 
+def test_group_reused_for_different_datasets(hot_env):
+    """One group, three different datasets in a row (different hot buckets, sizes, owners): nothing of an earlier call —
+    window contents, hand-over words, child buffers — may leak into the next."""
+    devs = device_lists()[-1]
+    if len(devs) < 3:
+        devs = [0, 0, 0]
+    with umigpu.Group(12, devs) as g:
+        for seed, scale in ((1, 0.004), (2, 0.002), (3, 0.006), (1, 0.004)):
+            d, cfg = small("C2", scale, seed=seed)
+            okept, _, octr = oracle(d)
+            kept, ctr, _ = g.dedup(d["tid"], d["pos"], d["rev"], d["umi"], d["score"])
+            assert kept.astype(np.int64).tolist() == okept.tolist(), (seed, scale)
+            assert ctr["total_umis"] == octr["total_umis"]
+
+
 @pytest.mark.parametrize("algo,oalgo,k,L", [(umigpu.ALGO_CC, O.ALGO_CC, 2, 16), (umigpu.ALGO_ADJ_UPSTREAM, O.ALGO_ADJ_UPSTREAM, 1, 12),
                                             (umigpu.ALGO_ADJ, O.ALGO_ADJ_REF, 1, 12)])
 def test_group_other_algorithms(hot_env, algo, oalgo, k, L):

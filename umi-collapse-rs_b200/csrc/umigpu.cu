@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <memory>
 #include <condition_variable>
 #include <mutex>
 #include <queue>
@@ -1629,9 +1630,31 @@ struct XchgHeader {
 };
 static_assert(sizeof(XchgHeader) == 512, "exchange header layout");
 
+// In-process groups hand over through HOST memory instead of flag words in the window: the producer's stream runs a host
+// function (cudaLaunchHostFunc) after its data is in place, the consumer's host thread spins on a std::atomic.  (Polling a peer
+// device's memory with small copies works between processes over CUDA IPC mappings, but inside one process with
+// cudaDeviceEnablePeerAccess it returned stale words on an 8-GPU box — rank 0 "waited 10 s for the owner's hot bucket" that
+// the owner had published; profiles/r2v_*.)
+struct XchgHostFlags {
+    std::atomic<unsigned long long> ready[XCHG_MAX_RANKS], info[XCHG_MAX_RANKS];
+    std::atomic<unsigned long long> slot_epoch[XCHG_MAX_RANKS][XCHG_MAX_RANKS], slot_count[XCHG_MAX_RANKS][XCHG_MAX_RANKS];   // [owner][rank]
+    XchgHostFlags() {
+        for (int a = 0; a < XCHG_MAX_RANKS; a++) { ready[a].store(0); info[a].store(0); for (int b = 0; b < XCHG_MAX_RANKS; b++) { slot_epoch[a][b].store(0); slot_count[a][b].store(0); } }
+    }
+};
+struct XchgHostSig { std::atomic<unsigned long long> *first = nullptr, *second = nullptr; unsigned long long v1 = 0, v2 = 0; };
+static void CUDART_CB xchg_host_sig_fn(void *p) {
+    XchgHostSig *s = static_cast<XchgHostSig *>(p);
+    s->first->store(s->v1, std::memory_order_relaxed);
+    s->second->store(s->v2, std::memory_order_release);        // the word the consumer waits for goes last
+}
+
 struct Xchg {
     int rank = 0, n = 1;
     bool ipc = false;
+    std::shared_ptr<XchgHostFlags> hf_own, hf_shared;   // every rank makes one; an in-process group uses rank 0's
+    XchgHostFlags *hf = nullptr;              // = hf_shared.get(); null between processes (flag words in the windows instead)
+    XchgHostSig sig_pub, sig_put;
     char *local = nullptr;
     std::vector<char *> peer;       // window of every rank as this device addresses it (peer[rank] == local)
     std::vector<char> opened;       // peer[r] came from cudaIpcOpenMemHandle
@@ -1686,6 +1709,7 @@ extern "C" int umigpu_xchg_create(umigpu_ctx *ctx, int32_t rank, int32_t n_ranks
     CK(cudaMemcpy(x->local, &h, sizeof h, cudaMemcpyHostToDevice));
     CK(cudaMallocHost((void **)&x->h_pin, (8 + 2 * XCHG_MAX_RANKS) * sizeof(unsigned long long)));
     CK(cudaStreamCreateWithFlags(&x->xs, cudaStreamNonBlocking));
+    x->hf_own = std::make_shared<XchgHostFlags>();
     x->peer.assign((size_t)n_ranks, nullptr); x->opened.assign((size_t)n_ranks, 0);
     x->peer[(size_t)rank] = x->local;
     if (ipc_handle_out) {
@@ -1729,6 +1753,9 @@ extern "C" int umigpu_xchg_attach_local(umigpu_ctx *ctx, umigpu_ctx *const *grou
     if (!ctx || !ctx->x || !group) return fail(ctx, UMIGPU_ERR_ARG, "umigpu_xchg_attach_local: no exchange window / null group");
     CK(cudaSetDevice(ctx->cfg.device));
     Xchg *x = ctx->x;
+    if (!group[0] || !group[0]->x || !group[0]->x->hf_own) return fail(ctx, UMIGPU_ERR_ARG, "rank 0 of the group has no exchange window");
+    x->hf_shared = group[0]->x->hf_own;          // hand-over words of the whole group: host memory of this process
+    x->hf = x->hf_shared.get();
     for (int r = 0; r < x->n; r++) {
         if (r == x->rank) continue;
         umigpu_ctx *o = group[r];
@@ -1840,6 +1867,22 @@ static int xchg_poll(Xchg *x, umigpu_ctx *ctx /* receives the error message */, 
     }
 }
 
+// in-process hand-over: spin on host words
+template <class Pred>
+static int xchg_wait_host(Xchg *x, umigpu_ctx *ctx, Pred pred, const char *what) {
+    const auto t0 = std::chrono::steady_clock::now();
+    XDBG("rank %d (device %d) epoch %llu: waiting (host flags) for %s", x->rank, ctx->cfg.device, (unsigned long long)x->epoch, what);
+    for (u64 it = 0;; it++) {
+        if (pred()) return UMIGPU_OK;
+        if (x->abort && x->abort->load()) return fail(ctx, UMIGPU_ERR_STATE, "shard group: rank %d gave up waiting for %s: another rank failed", x->rank, what);
+        if ((it & 1023) == 1023) {
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (dt > x->timeout_s) return fail(ctx, UMIGPU_ERR_STATE, "shard group: rank %d waited %.0f s for %s (a rank of the group failed or never ran)", x->rank, dt, what);
+        }
+        if (it > 64) std::this_thread::yield();
+    }
+}
+
 // owner: find the hot bucket among this slice's buckets, copy its unique arrays into the window, publish
 static int hot_publish(umigpu_ctx *ctx, const umigpu_hot *hot, u32 *u0_out) {
     Xchg *x = ctx->x;
@@ -1873,8 +1916,13 @@ static int hot_publish(umigpu_ctx *ctx, const umigpu_hot *hot, u32 *u0_out) {
     // info first, ready last (stream order = the order the words land in the window)
     x->h_pin[0] = why ? (1ull << 33) : ((unsigned long long)uh | ((unsigned long long)(has_n ? 1 : 0) << 32) | ((unsigned long long)narrow << 34));
     x->h_pin[1] = x->epoch;
-    CK(cudaMemcpyAsync(x->local + offsetof(XchgHeader, info), &x->h_pin[0], 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(x->local + offsetof(XchgHeader, ready), &x->h_pin[1], 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (x->hf) {
+        x->sig_pub = XchgHostSig{&x->hf->info[x->rank], &x->hf->ready[x->rank], x->h_pin[0], x->epoch};
+        CK(cudaLaunchHostFunc(ctx->stream, xchg_host_sig_fn, &x->sig_pub));
+    } else {
+        CK(cudaMemcpyAsync(x->local + offsetof(XchgHeader, info), &x->h_pin[0], 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(x->local + offsetof(XchgHeader, ready), &x->h_pin[1], 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
     if (why) { cudaStreamSynchronize(ctx->stream); return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "shard group: %s (%u unique UMIs, window holds %llu)", why, uh, (unsigned long long)x->ucap); }
     ctx->skip_bucket = hb;
     *u0_out = u0;
@@ -1909,11 +1957,19 @@ static int hot_band(umigpu_ctx *parent, const umigpu_hot *hot) {
     CK(cudaSetDevice(parent->cfg.device));
     const char *ow = x->peer[(size_t)hot->owner];
     const unsigned long long epoch = x->epoch;
-    int rc = xchg_poll(x, ch, ow + offsetof(XchgHeader, ready), 8, [&](const unsigned long long *b) { return b[0] >= epoch; }, "the owner's hot bucket");
-    if (rc) return rc;
-    rc = xchg_poll(x, ch, ow + offsetof(XchgHeader, info), 8, [](const unsigned long long *) { return true; }, "the owner's header");
-    if (rc) return rc;
-    const unsigned long long info = x->h_pin[8];
+    int rc;
+    unsigned long long info;
+    if (x->hf) {
+        rc = xchg_wait_host(x, ch, [&] { return x->hf->ready[hot->owner].load(std::memory_order_acquire) >= epoch; }, "the owner's hot bucket");
+        if (rc) return rc;
+        info = x->hf->info[hot->owner].load(std::memory_order_relaxed);
+    } else {
+        rc = xchg_poll(x, ch, ow + offsetof(XchgHeader, ready), 8, [&](const unsigned long long *b) { return b[0] >= epoch; }, "the owner's hot bucket");
+        if (rc) return rc;
+        rc = xchg_poll(x, ch, ow + offsetof(XchgHeader, info), 8, [](const unsigned long long *) { return true; }, "the owner's header");
+        if (rc) return rc;
+        info = x->h_pin[8];
+    }
     if ((info >> 33) & 1ull) return fail(ch, UMIGPU_ERR_UNSUPPORTED, "shard group: the owner (rank %d) could not publish the hot bucket", hot->owner);
     const u32 uh = (u32)info;
     const bool has_n = ((info >> 32) & 1ull) != 0;
@@ -1956,9 +2012,14 @@ static int hot_band(umigpu_ctx *parent, const umigpu_hot *hot) {
     else if (c_edges) CK(cudaMemcpyAsync(inbox, ch->d_edges.p, (size_t)c_edges * 8, cudaMemcpyDefault, ch->stream));
     XDBG("rank %d epoch %llu: band done, %llu edges -> owner %d", x->rank, (unsigned long long)epoch, (unsigned long long)c_edges, hot->owner);
     x->h_pin[2] = count; x->h_pin[3] = epoch;
-    char *slot = const_cast<char *>(ow) + offsetof(XchgHeader, slot) + (size_t)x->rank * sizeof(XchgSlot);
-    CK(cudaMemcpyAsync(slot + offsetof(XchgSlot, count), &x->h_pin[2], 8, cudaMemcpyDefault, ch->stream));
-    CK(cudaMemcpyAsync(slot + offsetof(XchgSlot, epoch), &x->h_pin[3], 8, cudaMemcpyDefault, ch->stream));
+    if (x->hf) {
+        x->sig_put = XchgHostSig{&x->hf->slot_count[hot->owner][x->rank], &x->hf->slot_epoch[hot->owner][x->rank], count, epoch};
+        CK(cudaLaunchHostFunc(ch->stream, xchg_host_sig_fn, &x->sig_put));
+    } else {
+        char *slot = const_cast<char *>(ow) + offsetof(XchgHeader, slot) + (size_t)x->rank * sizeof(XchgSlot);
+        CK(cudaMemcpyAsync(slot + offsetof(XchgSlot, count), &x->h_pin[2], 8, cudaMemcpyDefault, ch->stream));
+        CK(cudaMemcpyAsync(slot + offsetof(XchgSlot, epoch), &x->h_pin[3], 8, cudaMemcpyDefault, ch->stream));
+    }
     CK(cudaEventRecord(parent->ev[UMIGPU_STAGE_HOT_BAND][1], ch->stream));
     parent->ev_ok[UMIGPU_STAGE_HOT_BAND] = true;
     return UMIGPU_OK;
@@ -1969,10 +2030,18 @@ static int hot_collect(umigpu_ctx *ctx, u32 u0) {
     Xchg *x = ctx->x;
     const unsigned long long epoch = x->epoch;
     const int nr = x->n;
-    int rc = xchg_poll(x, ctx, x->local + offsetof(XchgHeader, slot), (size_t)nr * sizeof(XchgSlot),
+    int rc;
+    if (x->hf) {
+        rc = xchg_wait_host(x, ctx, [&] { for (int r = 0; r < nr; r++) if (x->hf->slot_epoch[x->rank][r].load(std::memory_order_acquire) < epoch) return false; return true; },
+                            "the edges of the other ranks");
+        if (rc) return rc;
+        for (int r = 0; r < nr; r++) x->h_pin[8 + 2 * r] = x->hf->slot_count[x->rank][r].load(std::memory_order_relaxed);
+    } else {
+        rc = xchg_poll(x, ctx, x->local + offsetof(XchgHeader, slot), (size_t)nr * sizeof(XchgSlot),
                        [&](const unsigned long long *b) { for (int r = 0; r < nr; r++) if (b[2 * r + 1] < epoch) return false; return true; },
                        "the edges of the other ranks");
-    if (rc) return rc;
+        if (rc) return rc;
+    }
     u64 cnt[XCHG_MAX_RANKS], total = 0;
     for (int r = 0; r < nr; r++) {
         const unsigned long long c = x->h_pin[8 + 2 * r];
