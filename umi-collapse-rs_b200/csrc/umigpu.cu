@@ -1066,17 +1066,20 @@ static int stage_cluster(umigpu_ctx *ctx) {
       // UMIGPU_FRONTIER_FORCE=1 (tests): no plain sweeps at all, the first frontier is every UMI
       bool use_frontier = getenv("UMIGPU_FRONTIER_FORCE") != nullptr && !sv_forced && U < 0xfffffff0u;
       // sweeps until the fixpoint, in batches of 4 with one read-back; *n_ptr (optional) = device-resident edge count
-      auto sweep_batches = [&](const uint2 *el, u64 ne, const unsigned long long *n_ptr, int max_rounds, bool allow_frontier) -> int {
+      // later_batch: sweeps per read-back after the first batch of four (the contracted graph of the two-phase scheme is shallow:
+      // two more usually settle it, four would mostly stream edges for nothing)
+      auto sweep_batches = [&](const uint2 *el, u64 ne, const unsigned long long *n_ptr, int max_rounds, bool allow_frontier, int later_batch) -> int {
           const u32 g = (u32)std::min<u64>(std::max<u64>(1, ceil_div_u64(ne, 256)), (u64)ctx->num_sms * 16);
           for (int round = 0; !converged && (max_rounds < 0 || round < max_rounds); round++) {
               CK(cudaMemsetAsync(&sc->changed, 0, 4, ctx->stream));
-              for (int i = 0; i < 4; i++) {
-                  if (i == 3) CK(cudaMemsetAsync(&sc->n_lowered, 0, 4, ctx->stream));
+              const int nb = round == 0 ? 4 : later_batch;
+              for (int i = 0; i < nb; i++) {
+                  if (i == nb - 1) CK(cudaMemsetAsync(&sc->n_lowered, 0, 4, ctx->stream));
                   ++sweep_no;
                   if (sweep_no <= 2) LAUNCH(label_sweep_kernel<false>, g, 256, el, ne, n_ptr, label, sc, stamp, sweep_no);
                   else               LAUNCH(label_sweep_kernel<true>, g, 256, el, ne, n_ptr, label, sc, stamp, sweep_no);
               }
-              sweeps += 4;
+              sweeps += nb;
               int r2 = read_scalars(ctx);
               if (r2) return r2;
               converged = !ctx->h_sc->changed || ctx->h_sc->n_lowered == 0;
@@ -1085,7 +1088,7 @@ static int stage_cluster(umigpu_ctx *ctx) {
           }
           return UMIGPU_OK;
       };
-      if (!use_frontier) { rc = sweep_batches(edges, n_edges, nullptr, big_graph ? plain_rounds : -1, may_frontier); if (rc) return rc; }
+      if (!use_frontier) { rc = sweep_batches(edges, n_edges, nullptr, big_graph ? plain_rounds : -1, may_frontier, 4); if (rc) return rc; }
       if (!converged && use_frontier) {
           // CSR by source: out-degree histogram, scan, scatter (no sort: a row's order does not matter)
           if (n_edges >= 0xffffffffull) return fail(ctx, UMIGPU_ERR_UNSUPPORTED, "more than 2^32 edges in one batch");
@@ -1136,7 +1139,7 @@ static int stage_cluster(umigpu_ctx *ctx) {
         // read-back, so it saved no batch and made the contraction 0.5 ms slower on C5.)
         CK(cudaMemsetAsync(ctx->d_stamp.p, 0, (size_t)U * 4, ctx->stream));
         sweep_no = 0;
-        rc = sweep_batches(ctx->d_cedges.as<uint2>(), n_edges, n_c, -1, false);
+        rc = sweep_batches(ctx->d_cedges.as<uint2>(), n_edges, n_c, -1, false, 2);
         if (rc) return rc;
         LAUNCH(expand_labels_kernel, grid_for(U, 256), 256, U, (const u32 *)comp, label);
       }
