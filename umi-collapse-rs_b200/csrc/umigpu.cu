@@ -88,6 +88,7 @@ struct umigpu_ctx {
     u32 band = 0, n_bands = 1;            // hot child: this device evaluates the row tiles ti with ti % n_bands == band
     struct Xchg *x = nullptr;
     umigpu_ctx *hot = nullptr;            // child context that runs this device's band of the hot bucket
+    umigpu_ctx *helper = nullptr;         // work context of the later multi-index passes (second host thread, own stream and buffers)
     bool is_child = false;
 };
 
@@ -198,6 +199,7 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
     ctx->d_segblk.release(); ctx->d_segnext.release(); ctx->d_segflag.release(); ctx->d_segbig.release(); ctx->d_seghist.release();
     ctx->d_wbuf[0].release(); ctx->d_wbuf[1].release();
     if (ctx->hot) { umigpu_destroy(ctx->hot); ctx->hot = nullptr; }
+    if (ctx->helper) { umigpu_destroy(ctx->helper); ctx->helper = nullptr; }
     xchg_release(ctx);
     DevBuf *bb[] = {&ctx->d_bamraw, &ctx->d_bamoff, &ctx->d_btid, &ctx->d_bpos, &ctx->d_brev, &ctx->d_bumi2, &ctx->d_bnmask, &ctx->d_bscore, &ctx->d_bvalid, &ctx->d_orig};
     for (DevBuf *b : bb) b->release();
@@ -874,6 +876,56 @@ static int stage_group(umigpu_ctx *ctx, bool want_labels, bool force_inf_thr) {
 
 // ---- stage 2: K5 neighbour search over the buckets of ctx (unique arrays, bstart, ubkt, freq, thr) -> ctx->d_edges ----
 // ctx->skip_bucket is left out (its search is shared by the shard group); a hot child evaluates only its band of row tiles.
+struct MiPlan { int P, bpb; int part_lo[MI_MAX_PARTS], part_len[MI_MAX_PARTS]; u32 nbig, m_big; MiParams mi0; };
+
+// Re-orders the unique UMIs of the big buckets of `src` so that part q is the most significant (keys, radix sort, gather).
+// Everything that is written lives in the WORK context `ctx` (= src for the serial form, the helper for the threaded one).
+static int mi_prepare(umigpu_ctx *ctx, const umigpu_ctx *src, const MiPlan &mp, int q, bool has_n) {
+    const u32 U = src->n_unique, m_big = mp.m_big;
+    const int pbits = mp.part_len[q] * mp.bpb, rbits = bits_for(mp.nbig - 1);
+    CK(ctx->d_key[0][0].reserve((size_t)m_big * 8)); CK(ctx->d_key[1][0].reserve((size_t)m_big * 8));
+    CK(ctx->d_idx[0].reserve((size_t)m_big * 4)); CK(ctx->d_idx[1].reserve((size_t)m_big * 4));
+    CK(ctx->d_biguid.reserve((size_t)m_big * 4)); CK(ctx->d_miplanes.reserve((size_t)m_big * 8)); CK(ctx->d_miucode.reserve((size_t)m_big * 8));
+    CK(ctx->d_miuid.reserve((size_t)m_big * 4)); if (has_n) CK(ctx->d_minplane.reserve((size_t)m_big * 4));
+    LAUNCH(mi_keys_kernel, grid_for(U, 256), 256, U, (const u32 *)src->d_ubkt.p, (const u32 *)src->d_brank.p, (const u32 *)src->d_bstart.p,
+           (const u32 *)src->d_bstartbig.p, (const u64 *)src->d_ucode.p, mp.part_lo[q] * mp.bpb,
+           (unsigned long long)(pbits >= 64 ? ~0ull : ((1ull << pbits) - 1)), pbits, ctx->d_biguid.as<u32>(), ctx->d_key[0][0].as<u64>());
+    int cur = 0;
+    int r2 = run_sort(ctx, m_big, 1, rs_plan(pbits + rbits), &cur);
+    if (r2) return r2;
+    LAUNCH(mi_gather_kernel, grid_for(m_big, 256), 256, m_big, (const u32 *)ctx->d_idx[cur].p, (const u32 *)ctx->d_biguid.p,
+           (const uint2 *)src->d_planes.p, has_n ? (const u32 *)src->d_nplane.p : (const u32 *)nullptr, (const u64 *)src->d_ucode.p,
+           ctx->d_miplanes.as<uint2>(), ctx->d_minplane.as<u32>(), ctx->d_miucode.as<u64>(), ctx->d_miuid.as<u32>());
+    return UMIGPU_OK;
+}
+
+// Passes 1..P-1 of the multi-index search, on the helper context `ctx` (its own stream, buffers and scalars) from a second host
+// thread, while the caller runs pass 0: the two are independent chains of small kernels and scalar read-backs, and both append
+// to the same edge sink.  Ends with the helper's stream drained.
+static int mi_later_passes(umigpu_ctx *ctx, const umigpu_ctx *src, const MiPlan &mp, EdgeSink es, bool has_n, int cull, bool *dense) {
+    CK(cudaSetDevice(ctx->cfg.device));
+    DevScalars *sc = ctx->d_sc.as<DevScalars>();
+    CK(cudaMemsetAsync(&sc->pairs_eval, 0, sizeof(u64), ctx->stream));
+    CK(cudaMemsetAsync(&sc->sort_err, 0, 4, ctx->stream));
+    CK(cudaMemcpyAsync(&sc->max_umis, &src->d_sc.as<DevScalars>()->max_umis, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->ctr.n_tile_candidates = ctx->ctr.n_tile_items = ctx->ctr.n_block_pairs = 0;
+    MiParams mi = mp.mi0;
+    int rc = UMIGPU_OK;
+    for (int q = 1; q < mp.P && !*dense; q++) {
+        rc = mi_prepare(ctx, src, mp, q, has_n);
+        if (rc) break;
+        const NView view{ctx->d_miplanes.as<uint2>(), has_n ? ctx->d_minplane.as<u32>() : (const u32 *)nullptr, ctx->d_miucode.as<u64>(),
+                         ctx->d_miuid.as<u32>(), src->d_bstartbig.as<u32>(), mp.nbig};
+        mi.part = q;
+        rc = neighbour_pass(ctx, view, mi, es, has_n, cull, true, dense, 0xffffffffu);
+        if (rc) break;
+    }
+    const int rc2 = read_scalars(ctx);                         // drains the helper's stream
+    if (!rc && rc2) rc = rc2;
+    if (!rc && ctx->h_sc->sort_err) rc = fail(ctx, UMIGPU_ERR_CUDA, "radix sort look-back exceeded its spin budget");
+    return rc;
+}
+
 static int stage_neighbours(umigpu_ctx *ctx, int mode) {
     const umigpu_config &cfg = ctx->cfg;
     DevScalars *sc = ctx->d_sc.as<DevScalars>();
@@ -892,35 +944,43 @@ static int stage_neighbours(umigpu_ctx *ctx, int mode) {
     // ---- multi-index preparation: which buckets are big, their compacted unique list ----
     const int P = k + 1;                                   // parts (pigeonhole)
     bool mi_on = need_edges && allow_blocks && !(cfg.flags & UMIGPU_FLAG_NO_MULTI_INDEX) && L >= 2 * P;
-    u32 nbig = 0, m_big = 0;
-    MiParams mi0; memset(&mi0, 0, sizeof mi0); mi0.part = -1; mi0.big = MI_BIG;
-    int part_lo[MI_MAX_PARTS] = {0, 0, 0, 0}, part_len[MI_MAX_PARTS] = {0, 0, 0, 0};
-    const int bpb = has_n ? 3 : 2;
+    MiPlan mp; memset(&mp, 0, sizeof mp);
+    mp.P = P; mp.bpb = has_n ? 3 : 2;
+    mp.mi0.part = -1; mp.mi0.big = MI_BIG;
+    const MiParams &mi0 = mp.mi0;
     if (mi_on) {
         int hi = L;
         for (int q = 0; q < P; q++) {                      // part 0 = the most significant positions of the main order
             int len = L / P + (q < L % P ? 1 : 0);
-            part_len[q] = len; part_lo[q] = hi - len; hi -= len;
-            mi0.pmask[q] = (u32)(((1ull << len) - 1) << part_lo[q]);
-            mi0.cmask[q] = (((len * bpb) >= 64 ? ~0ull : ((1ull << (len * bpb)) - 1))) << (part_lo[q] * bpb);
+            mp.part_len[q] = len; mp.part_lo[q] = hi - len; hi -= len;
+            mp.mi0.pmask[q] = (u32)(((1ull << len) - 1) << mp.part_lo[q]);
+            mp.mi0.cmask[q] = (((len * mp.bpb) >= 64 ? ~0ull : ((1ull << (len * mp.bpb)) - 1))) << (mp.part_lo[q] * mp.bpb);
         }
         CK(ctx->d_brank.reserve((size_t)B * 4)); CK(ctx->d_bigbid.reserve((size_t)B * 4));
         rc = run_scan(ctx, BucketIsBig{ctx->d_bstart.as<u32>(), MI_BIG, skip}, BucketBigEmit{ctx->d_brank.as<u32>(), ctx->d_bigbid.as<u32>(), B}, B, &sc->n_big);
         if (rc) return rc;
         rc = read_scalars(ctx);
         if (rc) return rc;
-        nbig = ctx->h_sc->n_big;
-        if (nbig == 0) mi_on = false;
+        mp.nbig = ctx->h_sc->n_big;
+        if (mp.nbig == 0) mi_on = false;
     }
     if (mi_on) {
-        CK(ctx->d_bstartbig.reserve(((size_t)nbig + 1) * 4));
-        rc = run_scan(ctx, BigSize{ctx->d_bstart.as<u32>(), ctx->d_bigbid.as<u32>()}, BigStartEmit{ctx->d_bstartbig.as<u32>(), nbig}, nbig, &sc->m_big);
+        CK(ctx->d_bstartbig.reserve(((size_t)mp.nbig + 1) * 4));
+        rc = run_scan(ctx, BigSize{ctx->d_bstart.as<u32>(), ctx->d_bigbid.as<u32>()}, BigStartEmit{ctx->d_bstartbig.as<u32>(), mp.nbig}, mp.nbig, &sc->m_big);
         if (rc) return rc;
         rc = read_scalars(ctx);
         if (rc) return rc;
-        m_big = ctx->h_sc->m_big;
-        CK(ctx->d_biguid.reserve((size_t)m_big * 4)); CK(ctx->d_miplanes.reserve((size_t)m_big * 8)); CK(ctx->d_miucode.reserve((size_t)m_big * 8));
-        CK(ctx->d_miuid.reserve((size_t)m_big * 4)); if (has_n) CK(ctx->d_minplane.reserve((size_t)m_big * 4));
+        mp.m_big = ctx->h_sc->m_big;
+    }
+    // the later passes run beside pass 0 on a helper context (second host thread, own stream); UMIGPU_MI_SERIAL=1 = one after the other
+    const bool threaded = mi_on && P > 1 && !getenv("UMIGPU_MI_SERIAL");
+    if (threaded && !ctx->helper) {
+        umigpu_config c = ctx->cfg;
+        c.stream = nullptr;
+        c.flags &= ~UMIGPU_FLAG_LABELS;
+        rc = umigpu_create(&c, &ctx->helper);
+        if (rc) { ctx->err = g_last_error; return rc; }
+        ctx->helper->is_child = true;
     }
 
     // ---- K5 neighbours ----
@@ -936,24 +996,8 @@ static int stage_neighbours(umigpu_ctx *ctx, int mode) {
             ctx->ctr.n_tile_candidates = ctx->ctr.n_tile_items = ctx->ctr.n_block_pairs = 0;
             ctx->used_direct = false; ctx->direct_pairs = 0;
             EdgeSink es{ctx->d_edges.as<uint2>(), (unsigned long long *)&sc->edge_count, cap, ctx->d_freq.as<i32>(), ctx->d_thr.as<i32>()};
-            // Fork: the small buckets and the re-ordering of the big buckets for pass 1 (keys, radix sort, gather) depend on
-            // nothing pass 0 produces, have no host synchronisation, and are latency-bound: they run on the side stream
-            // while pass 0 (whose work-list construction waits on scalar read-backs) runs on the main one.
-            auto mi_prepare = [&](int q) -> int {
-                const int pbits = part_len[q] * bpb, rbits = bits_for(nbig - 1);
-                CK(ctx->d_key[0][0].reserve((size_t)m_big * 8)); CK(ctx->d_key[1][0].reserve((size_t)m_big * 8));
-                CK(ctx->d_idx[0].reserve((size_t)m_big * 4)); CK(ctx->d_idx[1].reserve((size_t)m_big * 4));
-                LAUNCH(mi_keys_kernel, grid_for(U, 256), 256, U, (const u32 *)ctx->d_ubkt.p, (const u32 *)ctx->d_brank.p, (const u32 *)ctx->d_bstart.p,
-                       (const u32 *)ctx->d_bstartbig.p, (const u64 *)ctx->d_ucode.p, part_lo[q] * bpb,
-                       (unsigned long long)(pbits >= 64 ? ~0ull : ((1ull << pbits) - 1)), pbits, ctx->d_biguid.as<u32>(), ctx->d_key[0][0].as<u64>());
-                int cur = 0;
-                int r2 = run_sort(ctx, m_big, 1, rs_plan(pbits + rbits), &cur);
-                if (r2) return r2;
-                LAUNCH(mi_gather_kernel, grid_for(m_big, 256), 256, m_big, (const u32 *)ctx->d_idx[cur].p, (const u32 *)ctx->d_biguid.p,
-                       (const uint2 *)ctx->d_planes.p, has_n ? (const u32 *)ctx->d_nplane.p : (const u32 *)nullptr, (const u64 *)ctx->d_ucode.p,
-                       ctx->d_miplanes.as<uint2>(), ctx->d_minplane.as<u32>(), ctx->d_miucode.as<u64>(), ctx->d_miuid.as<u32>());
-                return UMIGPU_OK;
-            };
+            // Fork: the small buckets depend on nothing pass 0 produces and have no host synchronisation: side stream.  In the
+            // serial form the re-ordering for pass 1 goes there as well.
             CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
             CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
             {
@@ -962,7 +1006,7 @@ static int stage_neighbours(umigpu_ctx *ctx, int mode) {
                 int r2 = [&]() -> int {
                     LAUNCH(small_buckets_kernel, grid_for((u64)B * 32, 256), 256, B, (const u32 *)ctx->d_bstart.p, (const uint2 *)ctx->d_planes.p,
                            has_n ? (const u32 *)ctx->d_nplane.p : (const u32 *)nullptr, cfg.k, es, (unsigned long long *)&sc->pairs_eval, skip);
-                    if (mi_on && P > 1) return mi_prepare(1);
+                    if (mi_on && P > 1 && !threaded) return mi_prepare(ctx, ctx, mp, 1, has_n);
                     return UMIGPU_OK;
                 }();
                 cudaError_t ej = cudaEventRecord(ctx->ev_join, ctx->side);
@@ -970,24 +1014,44 @@ static int stage_neighbours(umigpu_ctx *ctx, int mode) {
                 if (r2) return r2;
                 CK(ej);
             }
+            bool dense = false, dense_later = false;
+            int later_rc = UMIGPU_OK;
+            std::thread later;
+            umigpu_ctx *hp = ctx->helper;
+            if (threaded && mi_on) {
+                hp->band = ctx->band; hp->n_bands = ctx->n_bands; hp->lay = ctx->lay;
+                // the helper's stream starts after the counters of this attempt have been reset on the main stream
+                CK(cudaStreamWaitEvent(hp->stream, ctx->ev_fork, 0));
+                later = std::thread([&] { later_rc = mi_later_passes(hp, ctx, mp, es, has_n, cull, &dense_later); });
+            }
             // pass 0: every bucket with more than 32 unique UMIs in the main order (big buckets filtered on part 0)
             MiParams mi = mi0; mi.part = mi_on ? 0 : -1;
-            bool dense = false;
             rc = neighbour_pass(ctx, main_view, mi, es, has_n, cull, allow_blocks, &dense, skip);
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));      // join (also before a restart or an error return)
-            if (rc) return rc;
-            if (dense) { mi_on = false; continue; }          // culling does not thin this input out: restart without multi-index
-            // passes 1..k: big buckets only, re-ordered so that part q is the most significant
-            for (int q = 1; mi_on && q < P; q++) {
-                if (q > 1) { rc = mi_prepare(q); if (rc) return rc; }
-                const NView view{ctx->d_miplanes.as<uint2>(), has_n ? ctx->d_minplane.as<u32>() : (const u32 *)nullptr, ctx->d_miucode.as<u64>(),
-                                 ctx->d_miuid.as<u32>(), ctx->d_bstartbig.as<u32>(), nbig};
-                mi.part = q;
-                rc = neighbour_pass(ctx, view, mi, es, has_n, cull, true, &dense, 0xffffffffu);
-                if (rc) return rc;
-                if (dense) break;
+            if (later.joinable()) later.join();
+            cudaError_t ew = cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);      // join (also before a restart or an error return)
+            if (threaded && mi_on) {
+                ctx->launches += hp->launches; hp->launches = 0;
+                if (later_rc) return fail(ctx, later_rc, "%s", hp->err.c_str());
             }
-            if (dense) { mi_on = false; continue; }
+            if (rc) return rc;
+            CK(ew);
+            if (dense || dense_later) { mi_on = false; continue; }          // culling does not thin this input out: restart without multi-index
+            if (threaded && mi_on) {
+                ctx->ctr.n_tile_candidates += hp->ctr.n_tile_candidates; ctx->ctr.n_tile_items += hp->ctr.n_tile_items;
+                ctx->ctr.n_block_pairs += hp->ctr.n_block_pairs;
+            } else {
+                // passes 1..k: big buckets only, re-ordered so that part q is the most significant
+                for (int q = 1; mi_on && q < P; q++) {
+                    if (q > 1) { rc = mi_prepare(ctx, ctx, mp, q, has_n); if (rc) return rc; }
+                    const NView view{ctx->d_miplanes.as<uint2>(), has_n ? ctx->d_minplane.as<u32>() : (const u32 *)nullptr, ctx->d_miucode.as<u64>(),
+                                     ctx->d_miuid.as<u32>(), ctx->d_bstartbig.as<u32>(), mp.nbig};
+                    mi.part = q;
+                    rc = neighbour_pass(ctx, view, mi, es, has_n, cull, true, &dense, 0xffffffffu);
+                    if (rc) return rc;
+                    if (dense) break;
+                }
+                if (dense) { mi_on = false; continue; }
+            }
             rc = read_scalars(ctx);
             if (rc) return rc;
             if (ctx->h_sc->sort_err) return fail(ctx, UMIGPU_ERR_CUDA, "radix sort look-back exceeded its spin budget");
@@ -1005,6 +1069,7 @@ static int stage_neighbours(umigpu_ctx *ctx, int mode) {
     ctx->ctr.n_buckets = B; ctx->ctr.total_umis = U; ctx->ctr.max_umis = ctx->h_sc->max_umis;
     ctx->ctr.unordered_pairs = ctx->h_sc->pairs;
     ctx->ctr.pairs_evaluated = ctx->h_sc->pairs_eval + (ctx->used_direct ? ctx->direct_pairs : 0);
+    if (threaded && mi_on && ctx->helper) ctx->ctr.pairs_evaluated += ctx->helper->h_sc->pairs_eval;
     ctx->ctr.n_edges = n_edges;
     return UMIGPU_OK;
 }
