@@ -16,7 +16,9 @@
  *   - inputs are borrowed for the duration of the call; results are library-owned until
  *     umigpu_result_free / umigpu_destroy;
  *   - a context is bound to one CUDA device and is not thread-safe (the reference is
- *     single-threaded: &mut self on every trait method);
+ *     single-threaded: &mut self on every trait method); a run may start short-lived host threads
+ *     of its own (independent stages on a second stream: later multi-index passes, the band of a
+ *     split hot bucket) and joins them before it returns;
  *   - there is no CPU fallback: without a CUDA device umigpu_create fails.
  */
 #ifndef UMIGPU_H

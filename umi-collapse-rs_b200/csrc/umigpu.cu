@@ -1022,12 +1022,15 @@ static int stage_neighbours(umigpu_ctx *ctx, int mode) {
                 hp->band = ctx->band; hp->n_bands = ctx->n_bands; hp->lay = ctx->lay;
                 // the helper's stream starts after the counters of this attempt have been reset on the main stream
                 CK(cudaStreamWaitEvent(hp->stream, ctx->ev_fork, 0));
-                later = std::thread([&] { later_rc = mi_later_passes(hp, ctx, mp, es, has_n, cull, &dense_later); });
+                // (no exception may cross the C ABI: if the thread cannot be started the passes run here, after pass 0)
+                try { later = std::thread([&] { later_rc = mi_later_passes(hp, ctx, mp, es, has_n, cull, &dense_later); }); }
+                catch (...) { later_rc = -1000; }
             }
             // pass 0: every bucket with more than 32 unique UMIs in the main order (big buckets filtered on part 0)
             MiParams mi = mi0; mi.part = mi_on ? 0 : -1;
             rc = neighbour_pass(ctx, main_view, mi, es, has_n, cull, allow_blocks, &dense, skip);
             if (later.joinable()) later.join();
+            else if (later_rc == -1000) later_rc = mi_later_passes(hp, ctx, mp, es, has_n, cull, &dense_later);
             cudaError_t ew = cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);      // join (also before a restart or an error return)
             if (threaded && mi_on) {
                 ctx->launches += hp->launches; hp->launches = 0;
@@ -2166,9 +2169,11 @@ extern "C" int umigpu_run_sharded(umigpu_ctx *ctx, const umigpu_hot *hot, int64_
         if (owner) { rc = hot_publish(ctx, hot, &u0); if (rc) return rc; }
         // this rank's band of the hot bucket beside its own neighbour search: two host threads, two streams
         int band_rc = UMIGPU_OK;
-        std::thread band([&] { band_rc = hot_band(ctx, hot); });
+        std::thread band;
+        try { band = std::thread([&] { band_rc = hot_band(ctx, hot); }); } catch (...) { band_rc = -1000; }
+        if (band_rc == -1000) band_rc = hot_band(ctx, hot);            // no thread: band first, then the own search
         if (n) rc = stage_neighbours(ctx, RUN_FULL);
-        band.join();
+        if (band.joinable()) band.join();
         ctx->launches += ctx->hot->launches; ctx->hot->launches = 0;
         if (band_rc) return fail(ctx, band_rc, "%s", ctx->hot->err.c_str());
         if (rc) return rc;
