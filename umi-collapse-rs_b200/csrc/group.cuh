@@ -141,6 +141,127 @@ __global__ void __launch_bounds__(SCAN_THREADS) unique_apply1_kernel(UniqueEmit 
     g.flush();
 }
 
+// The merge scan in ONE pass over the sorted keys (one-word keys, no weights): tiles take tickets, publish their number of
+// unique heads and look back over their predecessors' (decoupled look-back, a warp reads 32 predecessors at a time), so the
+// separate head-count pass — a second 8 B/read sweep — is gone.  rep[] needs no memset either: a tile zeroes the slots of the
+// uniques that START in it before its own atomics touch them.  Reads that continue the last unique of an EARLIER tile (the
+// ones before the tile's first head) never touch rep[] here — that slot belongs to a tile that may not have zeroed it yet —
+// they are folded into one (unique id, value) pair per tile which unique_carry_kernel applies afterwards.
+#define UQ_FLAG_AGG    (1ull << 62)
+#define UQ_FLAG_PREFIX (2ull << 62)
+#define UQ_FLAG_MASK   (3ull << 62)
+__global__ void __launch_bounds__(SCAN_THREADS) unique_onepass_kernel(UniqueEmit g_in, u64 n, u32 ntiles, unsigned long long *tile_state, u32 *ticket,
+                                                                      u32 *__restrict__ carry_uid, unsigned long long *__restrict__ carry_val,
+                                                                      u32 *n_unique_out, u32 *err) {
+    static_assert(SCAN_ITEMS == 8, "vector loads below assume 8 elements per thread");
+    UniqueEmit g = g_in;
+    __shared__ u32 sm[SCAN_THREADS / 32 + 1];
+    __shared__ u32 s_tile, s_excl;
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) { s_tile = atomicAdd(ticket, 1u); s_carry = 0ull; }
+    __syncthreads();
+    const u32 tile = s_tile;
+    if (tile >= ntiles) return;
+    const u64 base = (u64)tile * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+    const u64 *__restrict__ k0 = g.sk.k0;
+    u64 key[SCAN_ITEMS]; u32 ridx[SCAN_ITEMS];
+    if (base + SCAN_ITEMS <= n) {
+        const ulonglong2 *kv = reinterpret_cast<const ulonglong2 *>(k0 + base);
+        const uint4 *iv = reinterpret_cast<const uint4 *>(g.idx + base);
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const ulonglong2 t = __ldg(kv + q); key[2 * q] = t.x; key[2 * q + 1] = t.y; }
+#pragma unroll
+        for (int q = 0; q < 2; q++) { const uint4 t = __ldg(iv + q); ridx[4 * q] = t.x; ridx[4 * q + 1] = t.y; ridx[4 * q + 2] = t.z; ridx[4 * q + 3] = t.w; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; j++) { const u64 i = base + j; key[j] = i < n ? k0[i] : 0; ridx[j] = i < n ? g.idx[i] : 0; }
+    }
+    u64 prev = __shfl_up_sync(0xffffffffu, key[SCAN_ITEMS - 1], 1);
+    if (lane_id() == 0) prev = (base > 0 && base <= n) ? k0[base - 1] : 0;
+    i32 sc_[SCAN_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; j++) sc_[j] = (base + j < n && g.score) ? __ldg(g.score + ridx[j]) : 0;
+    u32 fmask = 0, bmask = 0;                                // bit j: element j starts a unique / a bucket
+    {
+        u64 p = prev;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; j++) {
+            const u64 i = base + j;
+            if (i < n && (i == 0 || key[j] != p)) fmask |= 1u << j;
+            if (i == 0 || (key[j] >> g.sk.umi_bits) != (p >> g.sk.umi_bits)) bmask |= 1u << j;
+            p = key[j];
+        }
+    }
+    u32 total;
+    u32 ex = block_exclusive_scan<u32, SCAN_THREADS>((u32)__popc(fmask), sm, &total);
+    // ---- look-back (warp 0): exclusive prefix of `total` over the tiles before this one ----
+    if (threadIdx.x < 32) {
+        const u32 lane = lane_id();
+        u32 excl = 0;
+        if (tile != 0) {
+            if (lane == 0) atomicExch(tile_state + tile, UQ_FLAG_AGG | (unsigned long long)total);
+            long long p = (long long)tile - 1;              // highest predecessor not yet accounted for
+            u32 spins = 0;
+            for (;;) {
+                const long long t = p - (long long)lane;
+                unsigned long long v = UQ_FLAG_PREFIX;      // before tile 0: prefix 0
+                if (t >= 0) v = *reinterpret_cast<volatile unsigned long long *>(tile_state + t);
+                const u32 m_empty = __ballot_sync(0xffffffffu, (v & UQ_FLAG_MASK) == 0ull);
+                const u32 m_pref = __ballot_sync(0xffffffffu, (v & UQ_FLAG_MASK) == UQ_FLAG_PREFIX);
+                const u32 fe = m_empty ? (u32)__ffs(m_empty) - 1u : 32u, fp = m_pref ? (u32)__ffs(m_pref) - 1u : 32u;
+                const u32 upto = min(fe, fp + 1u);          // lanes [0, upto) hold published values up to (and including) a prefix
+                excl += __reduce_add_sync(0xffffffffu, lane < upto ? (u32)(v & ~UQ_FLAG_MASK) : 0u);
+                if (fp < fe) break;
+                p -= (long long)upto;
+                if (upto == 0u) { if (++spins > (1u << 22)) { if (lane == 0) err[0] = 1; break; } __nanosleep(40); }      // a would-be hang becomes a reported error
+            }
+        }
+        if (lane == 0) {
+            atomicExch(tile_state + tile, UQ_FLAG_PREFIX | (unsigned long long)(excl + total));
+            s_excl = excl;
+            if (tile == ntiles - 1) *n_unique_out = excl + total;
+        }
+    }
+    __syncthreads();
+    const u32 excl = s_excl;
+    for (u32 u = threadIdx.x; u < total; u += SCAN_THREADS) g.rep[excl + u] = 0ull;
+    __syncthreads();
+    ex += excl;
+    const u64 cmask = (1ull << g.sk.umi_bits) - 1;          // one-word keys: umi_bits < 64
+    u32 pend_uid = 0xffffffffu; unsigned long long pend_val = 0ull;
+#define UQ_FLUSH() do { if (pend_uid != 0xffffffffu) { if (pend_uid + 1u == excl) atomicMax(&s_carry, pend_val); else atomicMax(&g.rep[pend_uid], pend_val); } } while (0)
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; j++) {
+        const u64 i = base + j;
+        const u32 fl = (fmask >> j) & 1u;
+        if (i < n) {
+            const u32 uid = ex + fl - 1;
+            const u32 r = ridx[j];
+            if (fl) { g.useg[uid] = (u32)i; g.ucode[uid] = key[j] & cmask; g.bhead[uid] = (u8)((bmask >> j) & 1u); }
+            if (i == n - 1) g.useg[uid + 1] = (u32)n;
+            const u32 sv = g.score ? (u32)sc_[j] ^ 0x80000000u : 0u;
+            const unsigned long long pk = ((unsigned long long)sv << 32) | (u32)~r;
+            if (uid == pend_uid) pend_val = pk > pend_val ? pk : pend_val;
+            else { UQ_FLUSH(); pend_uid = uid; pend_val = pk; }
+            if (g.read_uid) g.read_uid[r] = uid;
+        }
+        ex += fl;
+    }
+    UQ_FLUSH();
+#undef UQ_FLUSH
+    __syncthreads();
+    if (threadIdx.x == 0) { carry_uid[tile] = excl - 1u; carry_val[tile] = s_carry; }
+}
+
+// the contributions a tile held back for the unique that started before it (0 = none: a packed value is never 0)
+__global__ void __launch_bounds__(256) unique_carry_kernel(u32 ntiles, const u32 *__restrict__ carry_uid, const unsigned long long *__restrict__ carry_val,
+                                                           unsigned long long *__restrict__ rep) {
+    const u32 t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= ntiles) return;
+    const unsigned long long v = carry_val[t];
+    if (v) atomicMax(&rep[carry_uid[t]], v);
+}
+
 // per unique: freq, directional threshold (directional.rs:38), representative read, initial label.
 // label = (~freq << 32 | unique id): ascending label = the reference's visit order (freq descending,
 // directional.rs:67-72) with the canonical tie-break (UMI ascending = unique id ascending in a bucket).
@@ -283,19 +404,29 @@ struct BucketItemsEmit {
     }
 };
 
-__global__ void __launch_bounds__(256) bucket_stats_kernel(u32 n_buckets, const u32 *__restrict__ bstart, DevScalars *sc) {
-    u32 b = blockIdx.x * 256 + threadIdx.x;
-    u32 nb = b < n_buckets ? bstart[b + 1] - bstart[b] : 0;
-    u64 pairs = (u64)nb * (nb ? nb - 1 : 0) / 2;
-    u32 mx = nb;
+// Grid-stride over the buckets; n_ptr (optional) = device-resident bucket count, so that the launch need not wait for it.
+// Also counts the big buckets (multi-index passes) and their unique UMIs: one read-back serves the work-list sizing.
+__global__ void __launch_bounds__(256) bucket_stats_kernel(u32 n_buckets, const u32 *__restrict__ n_ptr, const u32 *__restrict__ bstart, DevScalars *sc) {
+    if (n_ptr) n_buckets = *n_ptr;
+    u64 pairs = 0;
+    u32 mx = 0, nbig = 0, mbig = 0;
+    for (u64 b = (u64)blockIdx.x * 256 + threadIdx.x; b < n_buckets; b += (u64)gridDim.x * 256) {
+        const u32 nb = bstart[b + 1] - bstart[b];
+        pairs += (u64)nb * (nb ? nb - 1 : 0) / 2;
+        mx = max(mx, nb);
+        if (nb > MI_BIG) { nbig++; mbig += nb; }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        nbig += __shfl_xor_sync(0xffffffffu, nbig, o);
+        mbig += __shfl_xor_sync(0xffffffffu, mbig, o);
     }
     if (lane_id() == 0 && mx) {
         atomicAdd((unsigned long long *)&sc->pairs, (unsigned long long)pairs);
         atomicMax(&sc->max_umis, mx);
+        if (nbig) { atomicAdd(&sc->n_big_all, nbig); atomicAdd(&sc->m_big_all, mbig); }
     }
 }
 

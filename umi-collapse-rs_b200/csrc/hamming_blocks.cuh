@@ -60,55 +60,60 @@ __global__ void __launch_bounds__(256) onehot_build_kernel(u32 n_groups /* 4 per
 }
 
 // ---- surviving tile pairs -> surviving (128 x 128) block pairs ----
-// fill == 0: only counts (out_count += survivors); fill == 1: appends uint2(row block, col block)
+// fill == 0: only counts (out_count += survivors); fill == 1: appends uint2(row block, col block) while there is room (cap)
 __global__ void __launch_bounds__(256) expand_blocks_kernel(const TileItem *__restrict__ items, u32 n_items, const u32 *__restrict__ bsum,
                                                             int L, int k, int cull, MiParams mi, int fill, uint2 *__restrict__ pairs,
-                                                            unsigned long long *out_count, u8 *__restrict__ need = nullptr) {
-    const u32 w = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = lane_id();
-    if (w >= n_items) return;
-    const TileItem it = items[w];
-    const u32 nrb = (item_row_cnt(it) + 127) >> 7, ncb = (item_col_cnt(it) + 127) >> 7;
-    const bool diag = item_diag(it), filt = item_filtered(it);
-    const u32 row_blk0 = it.col_blk0 - ((it.col_start - it.row_start) >> 7);
-    const u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
-    const u32 r = lane & 15, c0 = (lane >> 4) * 8;
-    u32 rs[5] = {0, 0, 0, 0, 0}, r_last = 0;
-    if (r < nrb) {
+                                                            unsigned long long *out_count, u8 *__restrict__ need = nullptr,
+                                                            unsigned long long cap = ~0ull /* fill: slots in pairs[]; the count runs on past it */,
+                                                            const u32 *__restrict__ n_items_ptr = nullptr /* device-resident item count: no read-back before the launch */) {
+    if (n_items_ptr) n_items = *n_items_ptr;
+    const u32 lane = lane_id(), n_warps = (gridDim.x * 256) >> 5;
+    for (u32 w = (blockIdx.x * 256 + threadIdx.x) >> 5; w < n_items; w += n_warps) {
+        const TileItem it = items[w];
+        const u32 nrb = (item_row_cnt(it) + 127) >> 7, ncb = (item_col_cnt(it) + 127) >> 7;
+        const bool diag = item_diag(it), filt = item_filtered(it);
+        const u32 row_blk0 = it.col_blk0 - ((it.col_start - it.row_start) >> 7);
+        const u32 lmask = L >= 32 ? 0xffffffffu : ((1u << L) - 1);
+        const u32 r = lane & 15, c0 = (lane >> 4) * 8;
+        u32 rs[5] = {0, 0, 0, 0, 0}, r_last = 0;
+        if (r < nrb) {
 #pragma unroll
-        for (int x = 0; x < 5; x++) rs[x] = bsum[(u64)(row_blk0 + r) * 8 + x];
-        r_last = bsum[(u64)(row_blk0 + r) * 8 + 6];
-    }
-    u32 live = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const u32 c = c0 + i;
-        bool ok = r < nrb && c < ncb && (!diag || r <= c);
-        if (ok && cull && !(diag && r == c)) {
-            u32 cs[5];
-#pragma unroll
-            for (int x = 0; x < 5; x++) cs[x] = bsum[(u64)(it.col_blk0 + c) * 8 + x];
-            ok = disjoint_positions(rs, cs, lmask) <= (u32)k;
-            if (ok && filt) ok = disjoint_positions(rs, cs, mi.pmask[mi.part]) == 0;     // part-q letter sets must intersect
-            if (ok && filt) ok = r_last >= bsum[(u64)(it.col_blk0 + c) * 8 + 5];         // part-q value ranges must overlap
+            for (int x = 0; x < 5; x++) rs[x] = bsum[(u64)(row_blk0 + r) * 8 + x];
+            r_last = bsum[(u64)(row_blk0 + r) * 8 + 6];
         }
-        if (ok) live |= 1u << i;
-    }
-    u32 cnt = __popc(live);
-    // warp exclusive prefix of cnt
-    u32 inc = cnt;
+        u32 live = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (u32)o) inc += t; }
-    const u32 total = __shfl_sync(0xffffffffu, inc, 31);
-    if (total == 0) return;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(out_count, (unsigned long long)total);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (fill) {
-        u64 o = base + inc - cnt;
+        for (int i = 0; i < 8; i++) {
+            const u32 c = c0 + i;
+            bool ok = r < nrb && c < ncb && (!diag || r <= c);
+            if (ok && cull && !(diag && r == c)) {
+                u32 cs[5];
 #pragma unroll
-        for (int i = 0; i < 8; i++) if (live & (1u << i)) {
-            pairs[o++] = make_uint2((row_blk0 + r) | (filt ? 0x80000000u : 0u), it.col_blk0 + c0 + i);
-            if (need) need[it.col_blk0 + c0 + i] = 1;
+                for (int x = 0; x < 5; x++) cs[x] = bsum[(u64)(it.col_blk0 + c) * 8 + x];
+                ok = disjoint_positions(rs, cs, lmask) <= (u32)k;
+                if (ok && filt) ok = disjoint_positions(rs, cs, mi.pmask[mi.part]) == 0;     // part-q letter sets must intersect
+                if (ok && filt) ok = r_last >= bsum[(u64)(it.col_blk0 + c) * 8 + 5];         // part-q value ranges must overlap
+            }
+            if (ok) live |= 1u << i;
+        }
+        u32 cnt = __popc(live);
+        // warp exclusive prefix of cnt
+        u32 inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (u32)o) inc += t; }
+        const u32 total = __shfl_sync(0xffffffffu, inc, 31);
+        if (total == 0) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(out_count, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (fill) {
+            u64 o = base + inc - cnt;
+#pragma unroll
+            for (int i = 0; i < 8; i++) if (live & (1u << i)) {
+                if (o < cap) pairs[o] = make_uint2((row_blk0 + r) | (filt ? 0x80000000u : 0u), it.col_blk0 + c0 + i);
+                o++;
+                if (need) need[it.col_blk0 + c0 + i] = 1;
+            }
         }
     }
 }

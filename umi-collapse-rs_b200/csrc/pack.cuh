@@ -33,6 +33,7 @@ struct DevScalars {
     u32 hot_bucket, hot_u0, hot_cnt, hot_pad;   // sharded run: the bucket whose neighbour search is split across devices
     i64 key_lo, key_hi;              // sharded run: smallest / largest (tid << 32 | biased pos) of the slice (range check of the cuts)
     u32 seg_n_big, seg_n_tiles, seg_unsorted, seg_pad;   // segmented sort plan (SegPlanOut, seg_sort.cuh)
+    u32 n_big_all, m_big_all;        // buckets with more than MI_BIG unique UMIs and their unique UMIs (bucket_stats_kernel)
 };
 
 struct KeyLayout {

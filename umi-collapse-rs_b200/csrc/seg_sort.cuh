@@ -19,6 +19,7 @@
 // Output is exactly what the generic sort produces (sorted one-word keys + read indices), so K3 does not change.
 #pragma once
 #include "common.cuh"
+#include "pack.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
 
@@ -68,6 +69,29 @@ struct SegBlock { u32 nheads, first, last, pad; };        // heads of segments t
 struct SegBig { u32 start, len, tile0, pad; };            // a big segment and the index of its first tile
 struct SegPlanOut { u32 n_big, n_tiles, unsorted, pad; };
 
+// CTA reduction of a block's table entry: sum, min (first), max (last; SEG_NONE = all ones must lose: map to 0 via +1 trick)
+__device__ __forceinline__ void seg_block_reduce(u32 cnt, u32 first, u32 last, u32 bad, SegBlock *__restrict__ blk, SegPlanOut *plan) {
+    __shared__ u32 s_cnt[8], s_first[8], s_last[8], s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    u32 lastp = last == SEG_NONE ? 0u : last + 1u;           // 0 = none
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        lastp = max(lastp, __shfl_xor_sync(0xffffffffu, lastp, o));
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    __syncthreads();
+    if (lane_id() == 0) { s_cnt[threadIdx.x >> 5] = cnt; s_first[threadIdx.x >> 5] = first; s_last[threadIdx.x >> 5] = lastp; if (bad) s_bad = 1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 c = 0, f = SEG_NONE, l = 0;
+        for (int w = 0; w < 8; w++) { c += s_cnt[w]; f = min(f, s_first[w]); l = max(l, s_last[w]); }
+        blk[blockIdx.x] = SegBlock{c, f, l ? l - 1u : SEG_NONE, 0u};
+        if (s_bad) plan->unsorted = 1;
+    }
+}
+
 // ---- plan, step 1: block table ----
 __global__ void __launch_bounds__(256) seg_block_summary_kernel(const u64 *__restrict__ key, u64 n, int sbits, SegBlock *__restrict__ blk,
                                                                 SegPlanOut *plan) {
@@ -100,26 +124,53 @@ __global__ void __launch_bounds__(256) seg_block_summary_kernel(const u64 *__res
             }
         }
     }
-    // CTA reduction: sum, min (first), max (last; SEG_NONE = all ones must lose: map to 0 via +1 trick)
-    __shared__ u32 s_cnt[8], s_first[8], s_last[8], s_bad;
-    if (threadIdx.x == 0) s_bad = 0;
-    u32 lastp = last == SEG_NONE ? 0u : last + 1u;           // 0 = none
+    seg_block_reduce(cnt, first, last, bad, blk, plan);
+}
+
+// K1b and plan step 1 in ONE read of the inputs: the one-word keys of a block of 2048 reads are built (what
+// build_keys_kernel<1, LIN> writes) and the block's table entry is filled from the keys while they are in registers, so the
+// plan no longer re-reads 8 B per read.  Reads are taken striped (coalesced scalar loads: no alignment demands on the
+// caller's arrays) and the keys staged in shared memory for the comparison with the predecessor.  (First form: predecessor
+// by shuffle, lane 0 rebuilding its own from the inputs — eight divergent reload bubbles per warp made the kernel 0.33 ms
+// slower on C5 than the two kernels it replaced; profiles/r3a_ab_C5.jsonl.)
+template <bool LIN>
+__device__ __forceinline__ u64 seg_key_of(u64 i, const i32 *__restrict__ tid, const i64 *__restrict__ pos, const u8 *__restrict__ rev,
+                                          const i64 *__restrict__ tlen, const u64 *__restrict__ umi2, const u32 *__restrict__ nmask, const KeyLayout &lay) {
+    u64 bucket;
+    if (LIN) { const u32 t = (u32)(tid[i] - lay.tid_min); bucket = ((__ldg(lay.lin_off + t) + (u64)(pos[i] - __ldg(lay.lin_pmin + t))) << 1) | (rev[i] ? 1u : 0u); }
+    else bucket = ((u64)(u32)(tid[i] - lay.tid_min) << (lay.pos_bits + 1)) | ((u64)(pos[i] - lay.pos_min) << 1) | (rev[i] ? 1u : 0u);
+    if (lay.tlen_bits) bucket = (bucket << lay.tlen_bits) | (u64)(tlen[i] - lay.tlen_min);
+    const u64 code = umi_sort_code(umi2[i], lay.has_n ? nmask[i] : 0u, lay.umi_len, lay.has_n);
+    return (lay.umi_bits < 64 ? bucket << lay.umi_bits : 0) | code;
+}
+
+template <bool LIN>
+__global__ void __launch_bounds__(256) build_keys_summary_kernel(u64 n, const i32 *__restrict__ tid, const i64 *__restrict__ pos, const u8 *__restrict__ rev,
+                                                                 const i64 *__restrict__ tlen, const u64 *__restrict__ umi2, const u32 *__restrict__ nmask,
+                                                                 KeyLayout lay, u64 *__restrict__ k0, int sbits, SegBlock *__restrict__ blk, SegPlanOut *plan) {
+    // skey[1 + e] = key of the block's read e, skey[0] = key of the read before the block (the only one built twice)
+    __shared__ u64 skey[SEG_BLK + 1];
+    const u64 blk_base = (u64)blockIdx.x * SEG_BLK;
+    if (threadIdx.x == 0) skey[0] = blk_base > 0 ? seg_key_of<LIN>(blk_base - 1, tid, pos, rev, tlen, umi2, nmask, lay) : 0ull;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-        lastp = max(lastp, __shfl_xor_sync(0xffffffffu, lastp, o));
-        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    for (int j = 0; j < (int)(SEG_BLK / 256); j++) {
+        const u32 e = (u32)j * 256 + threadIdx.x;
+        const u64 i = blk_base + e;
+        if (i < n) { const u64 key = seg_key_of<LIN>(i, tid, pos, rev, tlen, umi2, nmask, lay); k0[i] = key; skey[1 + e] = key; }
     }
     __syncthreads();
-    if (lane_id() == 0) { s_cnt[threadIdx.x >> 5] = cnt; s_first[threadIdx.x >> 5] = first; s_last[threadIdx.x >> 5] = lastp; if (bad) s_bad = 1; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        u32 c = 0, f = SEG_NONE, l = 0;
-        for (int w = 0; w < 8; w++) { c += s_cnt[w]; f = min(f, s_first[w]); l = max(l, s_last[w]); }
-        blk[blockIdx.x] = SegBlock{c, f, l ? l - 1u : SEG_NONE, 0u};
-        if (s_bad) plan->unsorted = 1;
+    u32 cnt = 0, first = SEG_NONE, last = SEG_NONE, bad = 0;
+#pragma unroll
+    for (int j = 0; j < (int)(SEG_BLK / 256); j++) {
+        const u32 e = (u32)j * 256 + threadIdx.x;
+        const u64 i = blk_base + e;
+        if (i < n) {
+            const u64 c = skey[1 + e] >> sbits, p = skey[e] >> sbits;
+            if (i == 0 || c != p) { cnt++; if (first == SEG_NONE) first = (u32)i; last = (u32)i; }      // i ascends with j
+            if (i != 0 && c < p) bad = 1;
+        }
     }
+    seg_block_reduce(cnt, first, last, bad, blk, plan);
 }
 
 // ---- plan, step 2 (one CTA): next head after every block, big segments, tile table ----

@@ -49,6 +49,7 @@ struct umigpu_ctx {
     int have_tlen = -1;                   // paired mode (template length in the bucket key): -1 undecided, 0/1 fixed by the first push
     DevBuf d_sc;
     DevScalars *h_sc = nullptr;   // pinned
+    DevScalars *h_sc_init = nullptr;   // pinned, constant: the image umigpu_reset uploads (no host synchronisation needed)
 
     DevBuf d_key[2][2], d_idx[2], d_hist, d_tiles;
     DevBuf d_useg, d_rep, d_planes, d_nplane, d_bhead, d_wsum, d_read_uid, d_freq, d_thr, d_repidx, d_label, d_prio;
@@ -85,6 +86,7 @@ struct umigpu_ctx {
     bool used_seg_sort = false;
     // sharded run (several devices, one dataset): see "shard group" below
     u32 skip_bucket = 0xffffffffu;        // owner: the hot bucket is searched by every device of the group, not here
+    bool big_known = false;               // h_sc->n_big_all / m_big_all describe this run's buckets (set by stage_group)
     u32 band = 0, n_bands = 1;            // hot child: this device evaluates the row tiles ti with ti % n_bands == band
     struct Xchg *x = nullptr;
     umigpu_ctx *hot = nullptr;            // child context that runs this device's band of the hot bucket
@@ -170,6 +172,7 @@ extern "C" int umigpu_create(const umigpu_config *cfg, umigpu_ctx **out) {
     for (int s = 0; s < UMIGPU_N_STAGES; s++) { CKC(cudaEventCreate(&ctx->ev[s][0])); CKC(cudaEventCreate(&ctx->ev[s][1])); }
     CKC(ctx->d_sc.reserve(sizeof(DevScalars)));
     CKC(cudaMallocHost((void **)&ctx->h_sc, sizeof(DevScalars)));
+    CKC(cudaMallocHost((void **)&ctx->h_sc_init, sizeof(DevScalars)));
 #undef CKC
     *out = ctx;
     return umigpu_reset(ctx);
@@ -190,6 +193,7 @@ extern "C" void umigpu_destroy(umigpu_ctx *ctx) {
                       &ctx->d_miplanes, &ctx->d_minplane, &ctx->d_miucode, &ctx->d_miuid, &ctx->d_cedges, &ctx->d_tidtab, &ctx->d_lintab};
     for (DevBuf *b : bufs) b->release();
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
+    if (ctx->h_sc_init) cudaFreeHost(ctx->h_sc_init);
     if (ctx->h_kept) cudaFreeHost(ctx->h_kept);
     if (ctx->h_roots) cudaFreeHost(ctx->h_roots);
     if (ctx->h_umirep) cudaFreeHost(ctx->h_umirep);
@@ -223,9 +227,11 @@ static int init_scalars(umigpu_ctx *ctx) {
     z.tlen_min = 0x7fffffffffffffffLL; z.tlen_max = (i64)0x8000000000000000LL;
     z.key_lo = 0x7fffffffffffffffLL; z.key_hi = (i64)0x8000000000000000LL;
     z.hot_bucket = 0xffffffffu;
+    // h_sc doubles as the read-back buffer (every read-back ends with a synchronisation, so none is in flight here); the upload
+    // comes from a second pinned image that never changes: stream order is all it needs
     *ctx->h_sc = z;
-    CK(cudaMemcpyAsync(ctx->d_sc.p, ctx->h_sc, sizeof z, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));   // h_sc is reused as the read-back buffer
+    *ctx->h_sc_init = z;
+    CK(cudaMemcpyAsync(ctx->d_sc.p, ctx->h_sc_init, sizeof z, cudaMemcpyHostToDevice, ctx->stream));
     return UMIGPU_OK;
 }
 
@@ -524,20 +530,35 @@ static int run_sort(umigpu_ctx *ctx, u64 n, int nw, const SortPlan &plan, int *c
 
 // Segmented sort for input that arrives ordered by (contig, position) — seg_sort.cuh.  *done = false: the input is not
 // ordered that way (or the key does not fit the packed element): the caller runs the generic sort.  Result in buffer 1.
-static int run_sort_presorted(umigpu_ctx *ctx, u64 n, const KeyLayout &lay, bool *done) {
-    *done = false;
-    DevScalars *sc = ctx->d_sc.as<DevScalars>();
+static bool seg_sort_applies(const KeyLayout &lay, u64 n) {
     const int sbits = 1 + lay.tlen_bits + lay.umi_bits, ib = std::max(1, bits_for(n - 1));
-    if (lay.nw != 1 || sbits > 40 || sbits + ib > 64 || getenv("UMIGPU_NO_SEG_SORT")) return UMIGPU_OK;
+    return lay.nw == 1 && sbits <= 40 && sbits + ib <= 64 && !getenv("UMIGPU_NO_SEG_SORT");
+}
+// block table + plan scalars of the segmented sort (before the keys are built: the fused key kernel fills the table)
+static int seg_sort_prepare(umigpu_ctx *ctx, u64 n) {
+    DevScalars *sc = ctx->d_sc.as<DevScalars>();
     const u32 nblk = (u32)ceil_div_u64(n, SEG_BLK);
     CK(ctx->d_segblk.reserve((size_t)nblk * sizeof(SegBlock))); CK(ctx->d_segnext.reserve((size_t)nblk * 4)); CK(ctx->d_segflag.reserve(nblk));
     CK(ctx->d_segbig.reserve(((size_t)nblk + 1) * sizeof(SegBig)));
     CK(cudaMemsetAsync(&sc->seg_n_big, 0, 16, ctx->stream));
+    return UMIGPU_OK;
+}
+// have_table: the block table was filled while the keys were built (build_keys_summary_kernel)
+static int run_sort_presorted(umigpu_ctx *ctx, u64 n, const KeyLayout &lay, bool have_table, bool *done) {
+    *done = false;
+    DevScalars *sc = ctx->d_sc.as<DevScalars>();
+    const int sbits = 1 + lay.tlen_bits + lay.umi_bits, ib = std::max(1, bits_for(n - 1));
+    if (!seg_sort_applies(lay, n)) return UMIGPU_OK;
+    const u32 nblk = (u32)ceil_div_u64(n, SEG_BLK);
     SegPlanOut *plan = reinterpret_cast<SegPlanOut *>(&sc->seg_n_big);
     const u64 *key_in = ctx->d_key[0][0].as<u64>();
     u64 *key_out = ctx->d_key[1][0].as<u64>();
     u32 *idx_out = ctx->d_idx[1].as<u32>();
-    LAUNCH(seg_block_summary_kernel, nblk, 256, key_in, n, sbits, ctx->d_segblk.as<SegBlock>(), plan);
+    if (!have_table) {
+        int r0 = seg_sort_prepare(ctx, n);
+        if (r0) return r0;
+        LAUNCH(seg_block_summary_kernel, nblk, 256, key_in, n, sbits, ctx->d_segblk.as<SegBlock>(), plan);
+    }
     LAUNCH(seg_plan_kernel, 1, 1024, (const SegBlock *)ctx->d_segblk.p, nblk, n, (u32)SEG_TILE, ctx->d_segnext.as<u32>(), ctx->d_segflag.as<u8>(),
            ctx->d_segbig.as<SegBig>(), plan);
     int rc = read_scalars(ctx);
@@ -638,21 +659,40 @@ static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, E
     CK(cudaMemsetAsync(&sc->scratch2, 0, 8, ctx->stream));
     LAUNCH(build_items_kernel, grid_for(n_cand, 256), 256, n_cand, B, (const u32 *)ctx->d_itemoff.p, v.bstart, (const u32 *)ctx->d_tileoff.p,
            (const u32 *)ctx->d_blkoff.p, (const u32 *)ctx->d_tsum.p, L, k, cull, mi, ctx->d_items.as<TileItem>(), sc, ctx->band, ctx->n_bands);
+    const TileItem *items = ctx->d_items.as<TileItem>();
+    ctx->ctr.n_tile_candidates += n_cand;
+    // The surviving tile pairs (W of them, counted on the device) are expanded straight away — the expansion reads W from the
+    // device — and ONE read-back returns W, the scheduled pair space and the number of block pairs.
+    u8 *need = nullptr;
+    u64 pcap = 0;
+    const bool twice = getenv("UMIGPU_EXPAND_TWICE") != nullptr;       // count first, then fill: the former schedule
+    const u32 xgrid = (u32)std::min<u64>(grid_for((u64)n_cand * 32, 256), (u64)ctx->num_sms * 16);
+    if (allow_blocks) {
+        // ---- sparse form: global one-hot words, block-pair list, one warp per block pair ----
+        // The list is filled speculatively into the room there is (the count runs on past it): one expansion when it fits —
+        // every run after the first on similar input — and a second one after growing when it does not.
+        // A band of a split hot bucket only touches the column blocks near its own row tiles: the expansion flags the column
+        // blocks of its pairs and the one-hot words are built for those alone.
+        if (ctx->n_bands > 1) {
+            CK(ctx->d_blocked.reserve(std::max<u32>(n_blocks, 1)));
+            need = ctx->d_blocked.as<u8>();
+            CK(cudaMemsetAsync(need, 0, n_blocks, ctx->stream));
+        }
+        if (!twice) CK(ctx->d_pairs.reserve(std::min<u64>(std::max<u64>((u64)n_cand * 4, (u64)1 << 16), (u64)4 << 20) * sizeof(uint2)));   // first guess: at most 32 MB
+        pcap = twice ? 0 : ctx->d_pairs.cap / sizeof(uint2);
+        CK(cudaMemsetAsync(&sc->n_block_pairs, 0, 8, ctx->stream));
+        LAUNCH(expand_blocks_kernel, xgrid, 256, items, 0u, (const u32 *)ctx->d_bsum.p, L, k, cull, mi, twice ? 0 : 1,
+               twice ? (uint2 *)nullptr : ctx->d_pairs.as<uint2>(), (unsigned long long *)&sc->n_block_pairs, twice ? (u8 *)nullptr : need,
+               (unsigned long long)pcap, (const u32 *)&sc->n_items);
+    }
     rc = read_scalars(ctx);
     if (rc) return rc;
     const u32 W = ctx->h_sc->n_items;
     const u64 item_pairs = ctx->h_sc->scratch2;
-    ctx->ctr.n_tile_candidates += n_cand;
     if (W == 0) return UMIGPU_OK;
-    const TileItem *items = ctx->d_items.as<TileItem>();
 
     if (allow_blocks) {
-        // ---- sparse form: global one-hot words, block-pair list, one warp per block pair ----
-        CK(cudaMemsetAsync(&sc->n_block_pairs, 0, 8, ctx->stream));
-        LAUNCH(expand_blocks_kernel, grid_for((u64)W * 32, 256), 256, items, W, (const u32 *)ctx->d_bsum.p, L, k, cull, mi, 0, (uint2 *)nullptr,
-               (unsigned long long *)&sc->n_block_pairs, (u8 *)nullptr);
-        rc = read_scalars(ctx);
-        if (rc) return rc;
+        const int LP = blk_lp(L), XS = has_n ? 8 : 4;
         const u64 n_pairs = ctx->h_sc->n_block_pairs;
         // more than ~30 % of the scheduled pair space survives block culling: dense work runs better as shared-memory tiles
         // (a band of a split hot bucket never leaves the multi-index scheme: which pass reports a pair must not depend on
@@ -660,20 +700,14 @@ static int neighbour_pass(umigpu_ctx *ctx, const NView &v, const MiParams &mi, E
         const bool is_dense = (double)n_pairs * 16384.0 > 0.30 * (double)item_pairs && !(ctx->n_bands > 1 && mi.part >= 0);
         if (is_dense && mi.part >= 0) { *dense = true; return UMIGPU_OK; }
         if (!is_dense) {
-            const int LP = blk_lp(L), XS = has_n ? 8 : 4;
             CK(ctx->d_eq.reserve((size_t)std::max<u32>(n_blocks, 1) * LP * XS * 16));
-            // a band of a split hot bucket only touches the column blocks near its own row tiles: build the one-hot words of
-            // those alone (the pair list is filled first and flags its column blocks)
-            u8 *need = nullptr;
-            if (ctx->n_bands > 1) {
-                CK(ctx->d_blocked.reserve(std::max<u32>(n_blocks, 1)));
-                need = ctx->d_blocked.as<u8>();
-                CK(cudaMemsetAsync(need, 0, n_blocks, ctx->stream));
+            if (n_pairs > pcap) {
+                CK(ctx->d_pairs.reserve(std::max<u64>(n_pairs, 1) * sizeof(uint2)));
+                pcap = ctx->d_pairs.cap / sizeof(uint2);
+                CK(cudaMemsetAsync(&sc->n_block_pairs, 0, 8, ctx->stream));
+                LAUNCH(expand_blocks_kernel, xgrid, 256, items, W, (const u32 *)ctx->d_bsum.p, L, k, cull, mi, 1, ctx->d_pairs.as<uint2>(),
+                       (unsigned long long *)&sc->n_block_pairs, need, (unsigned long long)pcap);
             }
-            CK(ctx->d_pairs.reserve(std::max<u64>(n_pairs, 1) * sizeof(uint2)));
-            CK(cudaMemsetAsync(&sc->n_block_pairs, 0, 8, ctx->stream));
-            LAUNCH(expand_blocks_kernel, grid_for((u64)W * 32, 256), 256, items, W, (const u32 *)ctx->d_bsum.p, L, k, cull, mi, 1, ctx->d_pairs.as<uint2>(),
-                   (unsigned long long *)&sc->n_block_pairs, need);
             if (has_n) LAUNCH(onehot_build_kernel<true>, grid_for((u64)n_blocks * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
                               (const u32 *)ctx->d_blkcnt.p, v.planes, v.nplane, L, LP, ctx->d_eq.as<u32>(), (const u8 *)need);
             else       LAUNCH(onehot_build_kernel<false>, grid_for((u64)n_blocks * 32, 256), 256, n_blocks * 4, (const u32 *)ctx->d_blkfirst.p,
@@ -792,7 +826,20 @@ static int stage_group(umigpu_ctx *ctx, bool want_labels, bool force_inf_thr) {
 #define BUILD_KEYS(NWV, LINV, K1) LAUNCH((build_keys_kernel<NWV, LINV>), grid_for(n, 256), 256, n, (const i32 *)ctx->d_tid.p, (const i64 *)ctx->d_pos.p, \
         (const u8 *)ctx->d_rev.p, (const i64 *)(lay.tlen_bits ? ctx->d_tlen.p : nullptr), (const u64 *)ctx->d_umi2.p, (const u32 *)ctx->d_nmask.p, lay, \
         ctx->d_key[0][0].as<u64>(), K1)
-    if (lay.nw == 1) { if (lay.lin_off) BUILD_KEYS(1, true, (u64 *)nullptr); else BUILD_KEYS(1, false, (u64 *)nullptr); }
+    // input that may be coordinate-sorted: the keys and the segmented sort's block table come out of one kernel
+    const bool fused_table = seg_sort_applies(lay, n) && !getenv("UMIGPU_NO_FUSED_SUMMARY");
+    if (fused_table) {
+        rc = seg_sort_prepare(ctx, n);
+        if (rc) return rc;
+        const int sbits = 1 + lay.tlen_bits + lay.umi_bits;
+        SegPlanOut *plan = reinterpret_cast<SegPlanOut *>(&sc->seg_n_big);
+#define BUILD_KEYS_SEG(LINV) LAUNCH((build_keys_summary_kernel<LINV>), (u32)ceil_div_u64(n, SEG_BLK), 256, n, (const i32 *)ctx->d_tid.p, (const i64 *)ctx->d_pos.p, \
+        (const u8 *)ctx->d_rev.p, (const i64 *)(lay.tlen_bits ? ctx->d_tlen.p : nullptr), (const u64 *)ctx->d_umi2.p, (const u32 *)ctx->d_nmask.p, lay, \
+        ctx->d_key[0][0].as<u64>(), sbits, ctx->d_segblk.as<SegBlock>(), plan)
+        if (lay.lin_off) BUILD_KEYS_SEG(true); else BUILD_KEYS_SEG(false);
+#undef BUILD_KEYS_SEG
+    }
+    else if (lay.nw == 1) { if (lay.lin_off) BUILD_KEYS(1, true, (u64 *)nullptr); else BUILD_KEYS(1, false, (u64 *)nullptr); }
     else { if (lay.lin_off) BUILD_KEYS(2, true, ctx->d_key[0][1].as<u64>()); else BUILD_KEYS(2, false, ctx->d_key[0][1].as<u64>()); }
 #undef BUILD_KEYS
     STAGE_END(UMIGPU_STAGE_KEYS);
@@ -801,7 +848,7 @@ static int stage_group(umigpu_ctx *ctx, bool want_labels, bool force_inf_thr) {
     STAGE_BEGIN(UMIGPU_STAGE_SORT);
     int cur = 0;
     bool seg_done = false;
-    rc = run_sort_presorted(ctx, n, lay, &seg_done);
+    rc = run_sort_presorted(ctx, n, lay, fused_table, &seg_done);
     if (rc) return rc;
     ctx->used_seg_sort = seg_done;
     if (seg_done) cur = 1;
@@ -823,7 +870,6 @@ static int stage_group(umigpu_ctx *ctx, bool want_labels, bool force_inf_thr) {
     ctx->st_weighted = weighted;
     if (weighted) { CK(ctx->d_wsum.reserve(n * 4)); CK(cudaMemsetAsync(ctx->d_wsum.p, 0, n * 4, ctx->stream)); }
     if (want_labels) CK(ctx->d_read_uid.reserve(n * 4));
-    CK(cudaMemsetAsync(ctx->d_rep.p, 0, n * 8, ctx->stream));
     const bool use_score = ctx->have_score == 1 && cfg.merge != UMIGPU_MERGE_ANY;
     UniqueEmit ue;
     ue.sk = sk; ue.n = n; ue.idx = sorted_idx; ue.score = use_score ? ctx->d_score.as<i32>() : nullptr;
@@ -832,8 +878,21 @@ static int stage_group(umigpu_ctx *ctx, bool want_labels, bool force_inf_thr) {
     ue.bhead = ctx->d_bhead.as<u8>(); ue.rep = ctx->d_rep.as<unsigned long long>(); ue.wsum = ctx->d_wsum.as<i32>();
     ue.read_uid = want_labels ? ctx->d_read_uid.as<u32>() : nullptr;
     ue.pend_uid = 0xffffffffu; ue.pend_val = 0; ue.pend_w = 0;
-    if (lay.nw == 1) {
-        // one-word keys: same three phases, the apply phase specialised (vector loads, predecessor by shuffle)
+    if (lay.nw == 1 && !weighted && !getenv("UMIGPU_UNIQUE_TWO_PASS")) {
+        // one-word keys: ONE pass (ticketed tiles, decoupled look-back); rep[] is zeroed by the tiles that own its slots
+        const u64 ntiles = ceil_div_u64(n, SCAN_TILE);
+        CK(ctx->d_tiles.reserve(ntiles * sizeof(u32)));
+        CK(ctx->d_tilestate.reserve(2 * ntiles * 8));
+        unsigned long long *state = ctx->d_tilestate.as<unsigned long long>();
+        CK(cudaMemsetAsync(state, 0, ntiles * 8, ctx->stream));
+        CK(cudaMemsetAsync(&sc->sort_ticket, 0, 4, ctx->stream));
+        LAUNCH(unique_onepass_kernel, (u32)ntiles, SCAN_THREADS, ue, n, (u32)ntiles, state, &sc->sort_ticket, ctx->d_tiles.as<u32>(), state + ntiles,
+               &sc->n_unique, &sc->sort_err);
+        LAUNCH(unique_carry_kernel, grid_for(ntiles, 256), 256, (u32)ntiles, (const u32 *)ctx->d_tiles.p, (const unsigned long long *)(state + ntiles),
+               ctx->d_rep.as<unsigned long long>());
+    } else if (lay.nw == 1) {
+        // three phases, the apply phase specialised (vector loads, predecessor by shuffle)
+        CK(cudaMemsetAsync(ctx->d_rep.p, 0, n * 8, ctx->stream));
         const u64 ntiles = ceil_div_u64(n, SCAN_TILE);
         CK(ctx->d_tiles.reserve(ntiles * sizeof(u32)));
         u32 *ts = ctx->d_tiles.as<u32>();
@@ -841,6 +900,7 @@ static int stage_group(umigpu_ctx *ctx, bool want_labels, bool force_inf_thr) {
         LAUNCH((scan_spine<u32>), 1, 1024, ts, ntiles, &sc->n_unique);
         LAUNCH(unique_apply1_kernel, (u32)ntiles, SCAN_THREADS, ue, n, (const u32 *)ts);
     } else {
+        CK(cudaMemsetAsync(ctx->d_rep.p, 0, n * 8, ctx->stream));
         rc = run_scan(ctx, HeadFlag{sk}, ue, n, &sc->n_unique);
         if (rc) return rc;
     }
@@ -865,11 +925,14 @@ static int stage_group(umigpu_ctx *ctx, bool want_labels, bool force_inf_thr) {
     CK(ctx->d_ubkt.reserve((size_t)U * 4));
     rc = run_scan(ctx, BucketHead{ctx->d_bhead.as<u8>()}, BucketEmit{ctx->d_bstart.as<u32>(), U, ctx->d_ubkt.as<u32>()}, U, &sc->n_buckets);
     if (rc) return rc;
+    // the statistics run off the device-resident bucket count, so that ONE read-back returns the count, the largest bucket and
+    // the number / size of the big buckets (stage_neighbours then sizes the multi-index lists without asking again)
+    LAUNCH(bucket_stats_kernel, (u32)std::min<u64>(grid_for(U, 256), (u64)ctx->num_sms * 8), 256, 0u, (const u32 *)&sc->n_buckets, (const u32 *)ctx->d_bstart.p, sc);
     rc = read_scalars(ctx);
     if (rc) return rc;
     const u32 B = ctx->h_sc->n_buckets;
     ctx->n_buckets = B;
-    LAUNCH(bucket_stats_kernel, grid_for(B, 256), 256, B, (const u32 *)ctx->d_bstart.p, sc);
+    ctx->big_known = true;
     STAGE_END(UMIGPU_STAGE_WORKLIST);
     return UMIGPU_OK;
 }
@@ -957,20 +1020,31 @@ static int stage_neighbours(umigpu_ctx *ctx, int mode) {
             mp.mi0.cmask[q] = (((len * mp.bpb) >= 64 ? ~0ull : ((1ull << (len * mp.bpb)) - 1))) << (mp.part_lo[q] * mp.bpb);
         }
         CK(ctx->d_brank.reserve((size_t)B * 4)); CK(ctx->d_bigbid.reserve((size_t)B * 4));
-        rc = run_scan(ctx, BucketIsBig{ctx->d_bstart.as<u32>(), MI_BIG, skip}, BucketBigEmit{ctx->d_brank.as<u32>(), ctx->d_bigbid.as<u32>(), B}, B, &sc->n_big);
-        if (rc) return rc;
-        rc = read_scalars(ctx);
-        if (rc) return rc;
-        mp.nbig = ctx->h_sc->n_big;
-        if (mp.nbig == 0) mi_on = false;
-    }
-    if (mi_on) {
-        CK(ctx->d_bstartbig.reserve(((size_t)mp.nbig + 1) * 4));
-        rc = run_scan(ctx, BigSize{ctx->d_bstart.as<u32>(), ctx->d_bigbid.as<u32>()}, BigStartEmit{ctx->d_bstartbig.as<u32>(), mp.nbig}, mp.nbig, &sc->m_big);
-        if (rc) return rc;
-        rc = read_scalars(ctx);
-        if (rc) return rc;
-        mp.m_big = ctx->h_sc->m_big;
+        // counts already on the host (stage_group's last read-back) unless a bucket is left out or this is a hot child
+        const bool known = ctx->big_known && skip == 0xffffffffu && !getenv("UMIGPU_BIG_READBACK");
+        if (known && ctx->h_sc->n_big_all == 0) mi_on = false;
+        else {
+            rc = run_scan(ctx, BucketIsBig{ctx->d_bstart.as<u32>(), MI_BIG, skip}, BucketBigEmit{ctx->d_brank.as<u32>(), ctx->d_bigbid.as<u32>(), B}, B, &sc->n_big);
+            if (rc) return rc;
+            if (known) mp.nbig = ctx->h_sc->n_big_all;
+            else {
+                rc = read_scalars(ctx);
+                if (rc) return rc;
+                mp.nbig = ctx->h_sc->n_big;
+            }
+            if (mp.nbig == 0) mi_on = false;
+        }
+        if (mi_on) {
+            CK(ctx->d_bstartbig.reserve(((size_t)mp.nbig + 1) * 4));
+            rc = run_scan(ctx, BigSize{ctx->d_bstart.as<u32>(), ctx->d_bigbid.as<u32>()}, BigStartEmit{ctx->d_bstartbig.as<u32>(), mp.nbig}, mp.nbig, &sc->m_big);
+            if (rc) return rc;
+            if (known) mp.m_big = ctx->h_sc->m_big_all;
+            else {
+                rc = read_scalars(ctx);
+                if (rc) return rc;
+                mp.m_big = ctx->h_sc->m_big;
+            }
+        }
     }
     // the later passes run beside pass 0 on a helper context (second host thread, own stream); UMIGPU_MI_SERIAL=1 = one after the other
     const bool threaded = mi_on && P > 1 && !getenv("UMIGPU_MI_SERIAL");
@@ -1274,6 +1348,7 @@ static int run_begin(umigpu_ctx *ctx) {
     ctx->ran = true;
     ctx->n_unique = ctx->n_buckets = 0; ctx->n_edges = 0;
     ctx->skip_bucket = 0xffffffffu;
+    ctx->big_known = false;
     return UMIGPU_OK;
 }
 
@@ -2071,7 +2146,8 @@ static int hot_band(umigpu_ctx *parent, const umigpu_hot *hot) {
         LAUNCH(hot_child_expand_kernel, grid_for(uh, 256), 256, uh, (const void *)ch->d_umi2.p, narrow, (const i32 *)ch->d_freq.p, cf.percentage, inf_thr,
                (int)cf.umi_len, has_n ? 1 : 0, ch->d_planes.as<uint2>(), ch->d_nplane.as<u32>(), ch->d_ucode.as<u64>(), ch->d_thr.as<i32>(),
                ch->d_bstart.as<u32>(), ch->d_ubkt.as<u32>());
-        LAUNCH(bucket_stats_kernel, 1, 256, 1, (const u32 *)ch->d_bstart.p, ch->d_sc.as<DevScalars>());
+        LAUNCH(bucket_stats_kernel, 1, 256, 1u, (const u32 *)nullptr, (const u32 *)ch->d_bstart.p, ch->d_sc.as<DevScalars>());
+        ch->big_known = false;
         rc = stage_neighbours(ch, RUN_EDGES_ONLY);
         if (rc) return rc;
         c_edges = ch->n_edges;
