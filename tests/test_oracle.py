@@ -231,7 +231,9 @@ def test_hypothesis_properties_of_the_path():
     """Property tests (hypothesis) of the oracle, i.e. of the reference's algorithm under the canonical tie-break:
     (1) the kept (bucket, UMI) groups do not depend on the order of the reads; (2) splitting the input by bucket and
     deduplicating the parts separately gives the union (buckets are independent — what the multi-GPU sharding relies on);
-    (3) adding an exact duplicate of a read never changes which (bucket, UMI) groups survive for adj/cc."""
+    (3) adding an exact duplicate of a read never changes which (bucket, UMI) groups survive for adj as written; for cc it
+    never changes HOW MANY survive (the components are the same; the extra read can make another UMI of a component the most
+    frequent one, i.e. its representative).  derandomize: the same examples on every run."""
     from hypothesis import given, settings, strategies as st
 
     read = st.tuples(st.integers(0, 1), st.integers(-2, 3), st.integers(0, 1), st.text("ACG", min_size=4, max_size=4), st.integers(0, 40))
@@ -241,7 +243,7 @@ def test_hypothesis_properties_of_the_path():
         kept, _, _ = O.dedup(tid, pos, rev, arr(umi), score, algo, O.MERGE_AVGQUAL, 1, 0.5)
         return {(tid[i], pos[i], rev[i], umi[i]) for i in kept.tolist()}, kept.tolist()
 
-    @settings(max_examples=120, deadline=None)
+    @settings(max_examples=120, deadline=None, derandomize=True)
     @given(st.lists(read, min_size=1, max_size=60), st.randoms(use_true_random=False), st.sampled_from([O.ALGO_DIR, O.ALGO_CC, O.ALGO_ADJ_REF, O.ALGO_ADJ_UPSTREAM]))
     def check(reads, rnd, algo):
         g, _ = groups(reads, algo)
@@ -253,7 +255,9 @@ def test_hypothesis_properties_of_the_path():
             if part:
                 parts |= groups(part, algo)[0]
         assert parts == g                                                      # (2)
-        if algo in (O.ALGO_CC, O.ALGO_ADJ_REF):
+        if algo == O.ALGO_ADJ_REF:
             assert groups(reads + [reads[0]], algo)[0] == g                     # (3)
+        elif algo == O.ALGO_CC:
+            assert len(groups(reads + [reads[0]], algo)[0]) == len(g)           # (3)
 
     check()
