@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) unique_apply1_kernel(UniqueEmit 
 #define UQ_FLAG_AGG    (1ull << 62)
 #define UQ_FLAG_PREFIX (2ull << 62)
 #define UQ_FLAG_MASK   (3ull << 62)
-__global__ void __launch_bounds__(SCAN_THREADS) unique_onepass_kernel(UniqueEmit g_in, u64 n, u32 ntiles, unsigned long long *tile_state, u32 *ticket,
+__global__ void __launch_bounds__(SCAN_THREADS, 4) unique_onepass_kernel(UniqueEmit g_in, u64 n, u32 ntiles, unsigned long long *tile_state, u32 *ticket,
                                                                       u32 *__restrict__ carry_uid, unsigned long long *__restrict__ carry_val,
                                                                       u32 *n_unique_out, u32 *err) {
     static_assert(SCAN_ITEMS == 8, "vector loads below assume 8 elements per thread");
