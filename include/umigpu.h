@@ -145,7 +145,9 @@ const char *umigpu_last_error(const umigpu_ctx *ctx);
  * directional.rs:22-28, main.rs:52-92). */
 int  umigpu_create(const umigpu_config *cfg, umigpu_ctx **out);
 void umigpu_destroy(umigpu_ctx *ctx);
-/* forget all pushed reads and results, keep device buffers (next batch / next bucket) */
+/* forget all pushed reads and results, keep device buffers (next batch / next bucket).  After a run that returned
+ * UMIGPU_OK nothing is in flight and the call does not synchronise; after pushes that no successful run followed it waits for
+ * their copies and kernels, so the buffer rule of umigpu_push_reads* ("until the next run / fetch / reset returns") holds. */
 int  umigpu_reset(umigpu_ctx *ctx);
 
 /*

@@ -86,6 +86,7 @@ struct umigpu_ctx {
     bool used_seg_sort = false;
     // sharded run (several devices, one dataset): see "shard group" below
     u32 skip_bucket = 0xffffffffu;        // owner: the hot bucket is searched by every device of the group, not here
+    bool run_ok = false;                  // the last run returned UMIGPU_OK (its last step is a read-back: the stream is drained)
     bool big_known = false;               // h_sc->n_big_all / m_big_all describe this run's buckets (set by stage_group)
     u32 band = 0, n_bands = 1;            // hot child: this device evaluates the row tiles ti with ti % n_bands == band
     struct Xchg *x = nullptr;
@@ -238,6 +239,10 @@ static int init_scalars(umigpu_ctx *ctx) {
 extern "C" int umigpu_reset(umigpu_ctx *ctx) {
     if (!ctx) return fail(nullptr, UMIGPU_ERR_ARG, "null context");
     CK(cudaSetDevice(ctx->cfg.device));
+    // include/umigpu.h: the caller's pinned / device arrays of a push are free again when the next run, fetch or RESET returns.
+    // A successful run ends synchronised; a batch that is abandoned after its pushes (no run), or whose run failed half way, is
+    // the case with work still in flight.
+    if ((ctx->n_reads > 0 || ctx->n_records > 0) && !(ctx->ran && ctx->run_ok)) CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_reads = 0; ctx->chunks.clear(); ctx->have_score = ctx->have_weight = ctx->have_tlen = -1;
     ctx->ran = false; ctx->n_unique = ctx->n_buckets = 0; ctx->n_edges = 0;
     ctx->use_orig = false; ctx->n_unmapped = 0; ctx->n_records = 0;
@@ -1334,6 +1339,7 @@ static int stage_emit(umigpu_ctx *ctx, bool want_labels) {
     rc = read_scalars(ctx);
     if (rc) return rc;
     ctx->ctr.n_kept = ctx->h_sc->n_kept;
+    ctx->run_ok = true;
     return UMIGPU_OK;
 }
 
@@ -1349,19 +1355,20 @@ static int run_begin(umigpu_ctx *ctx) {
     ctx->n_unique = ctx->n_buckets = 0; ctx->n_edges = 0;
     ctx->skip_bucket = 0xffffffffu;
     ctx->big_known = false;
+    ctx->run_ok = false;
     return UMIGPU_OK;
 }
 
 static int run_internal(umigpu_ctx *ctx, int mode, bool want_labels, bool force_inf_thr) {
     int rc = run_begin(ctx);
     if (rc) return rc;
-    if (ctx->n_reads == 0) return UMIGPU_OK;
+    if (ctx->n_reads == 0) { ctx->run_ok = true; return UMIGPU_OK; }
     STAGE_BEGIN(UMIGPU_STAGE_TOTAL);
     rc = stage_group(ctx, want_labels, force_inf_thr);
     if (rc) return rc;
     rc = stage_neighbours(ctx, mode);
     if (rc) return rc;
-    if (mode == RUN_EDGES_ONLY) { STAGE_END(UMIGPU_STAGE_TOTAL); return UMIGPU_OK; }
+    if (mode == RUN_EDGES_ONLY) { STAGE_END(UMIGPU_STAGE_TOTAL); ctx->run_ok = true; return UMIGPU_OK; }
     rc = stage_cluster(ctx);
     if (rc) return rc;
     return stage_emit(ctx, want_labels);
