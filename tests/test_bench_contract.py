@@ -28,3 +28,20 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--scale", "0.002"],
                        capture_output=True, text=True, timeout=600, cwd=REPO, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_cpu_sample_of_a_single_bucket_workload_is_bounded():
+    """C4 is ONE bucket: the faithful Naive scan is quadratic in it, so the CPU sample is capped at 80 k reads whatever
+    --cpu-sample-reads says (2 M reads there would run for hours and stall `bench.py --workload C4`)."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(REPO, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    sys.path.insert(0, os.path.join(REPO, "umi-collapse-rs_b200"))
+    from umigpu import synth
+    args = types.SimpleNamespace(scale=1.0, cpu_sample_reads=2_000_000)
+    s4 = bench.cpu_sample_scale(args, synth.CONFIGS["C4"])
+    assert int(synth.CONFIGS["C4"]["n_reads"] * s4) == 80_000
+    s5 = bench.cpu_sample_scale(args, synth.CONFIGS["C5"])
+    assert int(round(synth.CONFIGS["C5"]["n_reads"] * s5)) == 2_000_000
