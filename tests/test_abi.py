@@ -28,6 +28,16 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in umigpu.load().umigpu_version()
 
 
+def test_rust_binding_declares_the_same_entry_points():
+    """The FFI crate a reference maintainer would add (uncompiled here: no cargo) binds exactly the header's
+    entry points — no stale or missing `extern "C"` item."""
+    header = open(os.path.join(REPO, "include", "umigpu.h")).read()
+    declared = sorted(set(re.findall(r"\b(umigpu_[a-z_0-9]+)\s*\(", header)))
+    rust = open(os.path.join(REPO, "umi-collapse-rs_b200", "rust", "umigpu-sys", "src", "lib.rs")).read()
+    bound = sorted(set(re.findall(r"\bfn\s+(umigpu_[a-z_0-9]+)\s*\(", rust)))
+    assert bound == declared
+
+
 def test_struct_layouts_match_header():
     assert C.sizeof(L.Config) == 40
     assert C.sizeof(L.Counters) == 136
